@@ -1,0 +1,190 @@
+"""Hot-path helpers mirroring ``src/synference/utils.py`` of the reference.
+
+Only the helpers on the mock-library path are present:
+constant-R wavelength grid (``utils.py:257-289``), min/max grid limits
+(``utils.py:115-126``), asinh magnitude conversions (``utils.py:647-805``), the
+scaling checks (``utils.py:929-988``) and the library file reader
+(``utils.py:37-112``).
+"""
+
+from __future__ import annotations
+
+import json
+import logging
+import os
+
+import numpy as np
+
+from .units import Angstrom, Jy, Quantity, has_units, nJy, strip_units
+
+logger = logging.getLogger("synference_b200")
+if not logger.handlers:
+    _h = logging.StreamHandler()
+    _h.setFormatter(logging.Formatter("%(asctime)s | %(name)s | %(levelname)s | %(message)s"))
+    logger.addHandler(_h)
+    # INFO on rank 0, WARNING elsewhere (utils.py:2331-2376 semantics, with RANK instead of MPI)
+    logger.setLevel(logging.INFO if int(os.environ.get("RANK", "0")) == 0 else logging.WARNING)
+    if os.environ.get("SYNFERENCE_B200_QUIET"):
+        logger.setLevel(logging.WARNING)
+
+
+def calculate_min_max_wav_grid(filterset, max_redshift, min_redshift=0):
+    """Wavelength limits so every filter stays on the grid for min_z <= z <= max_z (utils.py:115-126)."""
+    lo, hi = filterset.get_non_zero_lam_lims()
+    return lo / (1 + max_redshift), hi / (1 + min_redshift)
+
+
+def generate_constant_R(R=300, start=1 * Angstrom, end=9e5 * Angstrom, auto_start_stop=False,
+                        filterset=None, **kwargs):
+    """lambda_{i+1} = lambda_i (1 + 0.5/R), built by repeated multiplication (utils.py:257-289)."""
+    if auto_start_stop and filterset is not None:
+        start, end = calculate_min_max_wav_grid(filterset, **kwargs)
+    start_v = float(strip_units(start, "Angstrom"))
+    end_v = float(strip_units(end, "Angstrom"))
+    assert start_v < end_v, "Start wavelength must be less than end wavelength."
+    assert R > 0, "R must be greater than 0."
+    x = [start_v]
+    while x[-1] < end_v:
+        x.append(x[-1] * (1.0 + 0.5 / R))
+    return Quantity(x, Angstrom)
+
+
+# ---- asinh magnitudes (utils.py:647-805) ------------------------------------
+
+_POGSON = 2.5 * np.log10(np.e)
+
+
+def _jy(x):
+    return strip_units(x, "Jy") if has_units(x) else np.asarray(x, dtype=float)
+
+
+def _broadcast_b(f_b, like):
+    f_b = _jy(f_b)
+    if f_b.ndim == 1 and like.ndim == 2:
+        assert f_b.shape[0] == like.shape[0], "Flux softening must match the number of filters."
+        return np.tile(f_b, (like.shape[1], 1)).T
+    if f_b.ndim == 0:
+        return np.full_like(like, float(f_b), dtype=float)
+    assert f_b.shape == like.shape, "Flux and flux softening must have the same shape."
+    return f_b
+
+
+def f_jy_to_asinh(f_jy, f_b=5 * nJy):
+    f = _jy(f_jy)
+    b = _broadcast_b(f_b, f)
+    return -_POGSON * (np.arcsinh(f / (2 * b)) + np.log(b / 3631.0))
+
+
+def f_jy_err_to_asinh(f_jy, f_jy_err, f_b=5 * nJy):
+    f, e = _jy(f_jy), _jy(f_jy_err)
+    assert f.shape == e.shape, "Flux and flux error must have the same shape."
+    b = _broadcast_b(f_b, f)
+    return _POGSON * e / np.sqrt(f**2 + (2 * b) ** 2)
+
+
+def asinh_to_f_jy(f_asinh, f_b=5 * nJy):
+    m = np.asarray(f_asinh, dtype=float)
+    b = _broadcast_b(f_b, m)
+    return Quantity(2 * b * np.sinh(-m / _POGSON - np.log(b / 3631.0)), Jy)
+
+
+def asinh_err_to_f_jy(f_asinh, f_asinh_err, f_b=5 * nJy):
+    m, me = np.asarray(f_asinh, dtype=float), np.asarray(f_asinh_err, dtype=float)
+    b = _broadcast_b(f_b, m)
+    f = 2 * b * np.sinh(-m / _POGSON - np.log(b / 3631.0))
+    return Quantity(me * np.sqrt(f**2 + (2 * b) ** 2) / _POGSON, Jy)
+
+
+def asinh_to_snr(f_asinh, f_asinh_err, f_b=5 * nJy):
+    f = np.asarray(asinh_to_f_jy(f_asinh, f_b))
+    return f / np.asarray(asinh_err_to_f_jy(f_asinh, f_asinh_err, f_b))
+
+
+# ---- scaling checks (utils.py:929-988) ---------------------------------------
+
+def check_scaling(arr) -> bool:
+    """True when a quantity scales linearly with stellar mass (its unit carries Msun)."""
+    return has_units(arr) and "Msun" in str(arr.units) and "log" not in str(arr.units)
+
+
+def check_log_scaling(arr) -> bool:
+    return has_units(arr) and "log10" in str(arr.units) and "Msun" in str(arr.units)
+
+
+# ---- library container --------------------------------------------------------
+# The reference writes HDF5 (library.py:4074-4153).  h5py is not installable here, so
+# the same logical layout (dataset paths + attrs) is kept in an .npz next to a JSON
+# attribute block; when h5py is importable a real HDF5 file is written instead.
+
+def _have_h5py():
+    try:
+        import h5py  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def write_container(path, datasets: dict, attrs: dict, compress=True):
+    """Write ``{dataset path: array}`` and ``{attr: value}``; returns the path actually written."""
+    if _have_h5py() and not os.environ.get("SYNFERENCE_B200_FORCE_NPZ"):
+        import h5py
+        with h5py.File(path, "w") as f:
+            for k, v in datasets.items():
+                f.create_dataset(k, data=v, compression="gzip" if compress and np.ndim(v) else None)
+            for k, v in attrs.items():
+                f.attrs[k] = v
+        return path
+    payload = {k.replace("/", "::"): np.asarray(v) for k, v in datasets.items()}
+    payload["__attrs__"] = np.frombuffer(json.dumps(_jsonable(attrs)).encode(), dtype=np.uint8)
+    with open(path, "wb") as fh:  # keep the reference's file name, whatever its suffix
+        (np.savez_compressed if compress else np.savez)(fh, **payload)
+    return path
+
+
+def _jsonable(x):
+    if isinstance(x, dict):
+        return {k: _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    if isinstance(x, np.ndarray):
+        return x.tolist()
+    if isinstance(x, (np.floating, np.integer, np.bool_)):
+        return x.item()
+    return x
+
+
+def read_container(path):
+    """Inverse of :func:`write_container` -> ``(datasets, attrs)``."""
+    with open(path, "rb") as fh:
+        magic = fh.read(4)
+    if magic[:2] == b"PK":
+        d = np.load(path, allow_pickle=False)
+        attrs = json.loads(bytes(d["__attrs__"]).decode()) if "__attrs__" in d.files else {}
+        return {k.replace("::", "/"): d[k] for k in d.files if k != "__attrs__"}, attrs
+    import h5py
+    out, attrs = {}, {}
+    with h5py.File(path, "r") as f:
+        f.visititems(lambda n, o: out.__setitem__(n, o[()]) if isinstance(o, h5py.Dataset) else None)
+        attrs = {k: f.attrs[k] for k in f.attrs}
+    return out, attrs
+
+
+def load_library_from_hdf5(hdf5_path, photometry_key="Grid/Photometry", parameters_key="Grid/Parameters",
+                           filter_codes_attr="FilterCodes", parameters_attr="ParameterNames",
+                           supp_key="Grid/SupplementaryParameters", spectra_key="Grid/Spectra"):
+    """Read a library written by ``CombinedBasis.save_library`` (utils.py:37-112)."""
+    data, attrs = read_container(hdf5_path)
+    out = {"parameters": data[parameters_key],
+           "filter_codes": list(attrs.get(filter_codes_attr, [])),
+           "parameter_names": list(attrs.get(parameters_attr, [])),
+           "parameter_units": list(attrs.get("ParameterUnits", [])),
+           "photometry_units": attrs.get("PhotometryUnits", "nJy")}
+    if photometry_key in data:
+        out["photometry"] = data[photometry_key]
+    if spectra_key in data:
+        out["spectra"] = data[spectra_key]
+    if supp_key in data:
+        out["supplementary_parameters"] = data[supp_key]
+        out["supplementary_parameter_names"] = list(attrs.get("SupplementaryParameterNames", []))
+        out["supplementary_parameter_units"] = list(attrs.get("SupplementaryParameterUnits", []))
+    return out
