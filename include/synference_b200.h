@@ -1,0 +1,157 @@
+/*
+ * synference_b200 -- C ABI of the B200-native mock-library hot path.
+ *
+ * The reference (synthesizer-project/synference) is pure Python and has no FFI of its
+ * own: the path is reached through its Python API (src/synference/__init__.py:49-115)
+ * and runs inside the third-party `synthesizer` package.  This header declares the
+ * entry points a ctypes binding in the reference would call in place of those stages.
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * reference repository).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative sb2_status and records a message retrievable with sb2_last_error(); no
+ * function throws or allocates caller-visible memory; `stream` is a cudaStream_t passed
+ * as void* (NULL = default stream).  There is no CPU fallback: without a CUDA device the
+ * compute entry points fail with SB2_ERR_CUDA.
+ */
+#ifndef SYNFERENCE_B200_H
+#define SYNFERENCE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sb2_status {
+  SB2_OK = 0,
+  SB2_ERR_INVALID = -1, /* bad argument / unsupported shape */
+  SB2_ERR_CUDA = -2,    /* CUDA runtime or driver error     */
+  SB2_ERR_CAPACITY = -3 /* batch larger than the context's workspace */
+} sb2_status;
+
+/* SFH families (synthesizer.parametric.SFH.* as constructed at
+ * src/synference/library.py:1313). Row layout of sb2_params.sfh_rows:
+ *   [0]=min_age [1]=max_age (yr, lookback) then
+ *   GAUSSIAN: peak_age, sigma | EXPONENTIAL/DECLINING/DELAYED: tau | LOGNORMAL: tau, peak_age
+ *   CONTINUITY: n_bins, edges[n_bins+1] (yr), logsfr_ratios[n_bins-1]                        */
+enum { SB2_SFH_CONSTANT = 0, SB2_SFH_GAUSSIAN = 1, SB2_SFH_EXPONENTIAL = 2, SB2_SFH_DECLINING_EXP = 3,
+       SB2_SFH_DELAYED_EXP = 4, SB2_SFH_LOGNORMAL = 5, SB2_SFH_DOUBLE_POWERLAW = 6, SB2_SFH_CONTINUITY = 7 };
+#define SB2_SFH_ROW 24
+
+/* Metallicity distributions (synthesizer.parametric.ZDist.*). */
+enum { SB2_ZD_DELTA_LINEAR = 0, SB2_ZD_DELTA_LOG10 = 1, SB2_ZD_NORMAL_LINEAR = 2, SB2_ZD_NORMAL_LOG10 = 3 };
+
+/* Static model: SPS grid, emission recipe, dust curve, filters, IGM and cosmology tables.
+ * Replaces the objects handed to GalaxyBasis(...) (src/synference/library.py:1515-1531):
+ * grid, emission_model, instrument, cosmo.  All pointers are HOST pointers, copied at
+ * sb2_model_create time.                                                                  */
+typedef struct sb2_model_desc {
+  int32_t n_age, n_z, n_lam, n_comp, n_filt;
+  int32_t k_pad;   /* n_age*n_z rounded up to a multiple of 32                              */
+  int32_t n_chunk; /* wavelength chunks of 256/n_comp bins                                  */
+  const double* log10ages;     /* [n_age]                                                   */
+  const double* metallicities; /* [n_z]                                                     */
+  /* Transposed, TF32 hi/lo-split grid in internal units, K-major:
+   * row = chunk*256 + comp*(256/n_comp) + bin_in_chunk ; column k = iz*n_age + ia          */
+  const float* gt_hi; /* [n_chunk*256][k_pad]                                               */
+  const float* gt_lo; /* [n_chunk*256][k_pad]                                               */
+  double grid_scale;  /* erg/s/Hz/Msun per internal unit                                    */
+  const float* kappa; /* [n_chunk*256/n_comp] tau(lambda)/tau_V, zero padded (NULL: no dust) */
+  double lam0, q;     /* geometric wavelength axis lam_i = lam0*q^i [Angstrom]              */
+  int32_t interp_variant; /* 0: filters interpolated/integrated in nu, 1: in lambda (A9)    */
+  /* filters on the shared axis: band [filt_lo, filt_hi], packed (U, DV) weight pairs       */
+  const int32_t* filt_lo;
+  const int32_t* filt_hi;
+  const int32_t* filt_off;
+  const float* filt_uv; /* float2[filt_uv_len]                                              */
+  int32_t filt_uv_len;
+  const double* filt_su;  /* [n_filt] denominator = su + beta*sdv                           */
+  const double* filt_sdv; /* [n_filt]                                                       */
+  /* Inoue+14 tables (NULL igm_bin_pow: no IGM)                                             */
+  int32_t n_blue, n_lines;
+  const double* igm_bin_pow; /* [8][n_blue] */
+  const int32_t* igm_nline;  /* [n_blue]    */
+  const int32_t* igm_lc_on;  /* [n_blue]    */
+  const double* igm_thr;     /* [3][64]     */
+  const double* igm_pre;     /* [5][n_lines+1] */
+  /* cosmology: cubic-Hermite tables over s = ln(1+z)                                       */
+  int32_t cosmo_n;
+  double cosmo_smax;
+  const double* cosmo_dc;   /* comoving distance [Mpc] */
+  const double* cosmo_ddc;  /* d/ds                    */
+  const double* cosmo_age;  /* age [Gyr]               */
+  const double* cosmo_dage; /* d/ds                    */
+  double base_mass;         /* Msun the base photometry is quoted at (1e9, library.py:3217) */
+  int64_t max_batch;        /* workspace capacity in galaxies                               */
+} sb2_model_desc;
+
+/* Per-galaxy parameters, struct of arrays (float64).  Replaces the per-galaxy object lists
+ * (sfhs, metal_dists, redshifts, galaxy_params) of GalaxyBasis / create_galaxy
+ * (src/synference/library.py:1340-1424, 2168-2261).                                        */
+typedef struct sb2_params {
+  int64_t n;
+  const double* redshift; /* [n] */
+  const double* log_mass; /* [n] log10(M/Msun) (NULL: base mass)                            */
+  const double* tau_v;    /* [n] (NULL: 0)                                                  */
+  int32_t sfh_type;
+  int32_t sfh_stride;     /* doubles per row actually stored (<= SB2_SFH_ROW; rest are 0)   */
+  const double* sfh_rows; /* [n][sfh_stride]                                                */
+  /* optional: derive max_age = age(z) - age_zmax on device (library.py:1206) and scale
+   * `_norm` parameters by it (library.py:1287-1289): bit i set => row[2+i] *= max_age       */
+  int32_t max_age_from_z;
+  uint32_t norm_mask;
+  double age_zmax_gyr;
+  int32_t zd_type;
+  const double* zd_value; /* [n] */
+  const double* zd_sigma; /* [n] (NULL for delta) */
+  const double* coef_att;   /* [n] optional per-galaxy factor on the attenuated component   */
+  const double* coef_unatt; /* [n] optional per-galaxy factor on the unattenuated component */
+} sb2_params;
+
+typedef struct sb2_model sb2_model;
+
+const char* sb2_last_error(void);
+int sb2_device_count(void);
+
+/* Build / destroy the device-resident model.  `device` is the CUDA ordinal. */
+int sb2_model_create(const sb2_model_desc* desc, int device, sb2_model** out);
+int sb2_model_destroy(sb2_model* m);
+
+/* SFZH weights only (parity hook for Stars.__init__ -> _get_sfzh, library.py:1372-1379).
+ * params: DEVICE pointers. w_out: device float64 [n][n_age*n_z] (k = iz*n_age + ia).       */
+int sb2_build_weights(sb2_model* m, const sb2_params* params, double* w_out, void* stream);
+
+/* The fused path for one batch with DEVICE-resident parameters:
+ * weights -> grid-weighted sum (tcgen05) -> dust -> redshift/IGM -> filter integration.
+ * Replaces GalaxyBasis.process_galaxies -> Pipeline.run (library.py:2447-2694) and the mass
+ * scaling loop of CombinedBasis.create_full_library (library.py:4567-4609).
+ *   flux_base   device float32 [n][n_filt]  nJy at base_mass            (may be NULL)
+ *   flux_scaled device float64 [n][n_filt]  float32(base)*10^logM/base  (may be NULL)
+ *   spec_out    device float32 [n][n_lam]   observed-frame f_nu [nJy] at base_mass on the
+ *               rest-frame axis (Pipeline.get_observed_spectra, library.py:2604) (may be NULL) */
+int sb2_synth_photometry(sb2_model* m, const sb2_params* params, float* flux_base, double* flux_scaled,
+                         float* spec_out, void* stream);
+
+/* Same, with HOST buffers: copies parameters in, runs, copies results out (synchronous). */
+int sb2_synth_photometry_host(sb2_model* m, const sb2_params* params, float* flux_base, double* flux_scaled,
+                              float* spec_out);
+
+/* Depth-based scatter + flux->AB feature rows on DEVICE buffers.
+ * Replaces SBI_Fitter._apply_depths (sbi_runner.py:580-691) and the AB branch of
+ * create_feature_array_from_raw_photometry (sbi_runner.py:1698-1716, 1927-1932).
+ *   flux      float64 [n_gal][n_filt] (nJy)        sigma float64 [n_filt] (nJy, depth/sigma level)
+ *   normals   float64 [n_filt][n_gal*n_scatter] injected N(0,1) draws, or NULL => Philox4x32-10
+ *             keyed by (seed, epoch) with counter (row, filter)
+ *   out_flux  float64 [n_filt][n_rows] noisy flux (may be NULL)   -- bit-exact vs numpy for injected draws
+ *   out_feat  float32 [n_rows][2*n_filt] = (mag..., mag_err...)   (may be NULL)
+ * n_rows = n_gal*n_scatter, row r = g*n_scatter + s (np.repeat order).                      */
+int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, int32_t n_scatter,
+                             const double* sigma, double min_flux_pc_error, const double* normals,
+                             uint64_t seed, uint64_t epoch, double norm_mag_limit, double* out_flux,
+                             double* out_sigma, float* out_feat, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNFERENCE_B200_H */

@@ -1,0 +1,426 @@
+// C ABI of the B200-native mock-library hot path (see include/synference_b200.h).
+// Owns the device-resident model, the per-batch workspace, the TMA descriptors and the launches.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/synference_b200.h"
+#include "noise_kernel.cuh"
+#include "prep_kernel.cuh"
+#include "synth_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                         \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(SB2_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+template <class T>
+int upload(T** dst, const T* src, size_t n) {
+  *dst = nullptr;
+  if (n == 0 || src == nullptr) return SB2_OK;
+  CU_TRY(cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(T)));
+  CU_TRY(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return SB2_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D row-major float32 matrix [rows][cols]; box = 32 columns (128 B) x box_rows, SWIZZLE_128B.
+int make_tmap(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(SB2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SB2_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return SB2_OK;
+}
+
+__global__ void sort_keys_kernel(const double* z, float* keys, int* idx, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = (float)z[i];
+    idx[i] = (int)i;
+  }
+}
+
+}  // namespace
+
+struct sb2_model {
+  int device = 0;
+  int n_sm = 0;
+  sb2_model_desc d{};  // dims and scalars (pointers inside are NOT valid after create)
+  long long cap = 0, cap_pad = 0;
+  // model tables
+  double *ages = nullptr, *edges = nullptr, *zmet = nullptr, *log10zmet = nullptr;
+  float *gt_hi = nullptr, *gt_lo = nullptr, *kappa = nullptr, *filt_uv = nullptr;
+  int *filt_lo = nullptr, *filt_hi = nullptr;
+  double *bin_pow = nullptr, *thr = nullptr, *pre = nullptr;
+  int *nline = nullptr, *lc_on = nullptr;
+  double *dc = nullptr, *ddc = nullptr, *age = nullptr, *dage = nullptr;
+  std::vector<int> h_lo, h_hi, h_off;
+  std::vector<float> h_su, h_sdv;
+  // workspace
+  float *w_hi = nullptr, *w_lo = nullptr, *igm = nullptr;
+  int *g_m = nullptr, *g_orig = nullptr, *perm = nullptr, *idx = nullptr;
+  float *g_beta = nullptr, *g_taut = nullptr, *g_scale = nullptr, *g_ca = nullptr, *g_cb = nullptr;
+  float *keys = nullptr, *keys_sorted = nullptr;
+  double* g_mscale = nullptr;
+  unsigned* g_trunc = nullptr;
+  void* cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  // host-entry staging (device side)
+  double* stage_params = nullptr;  // redshift | log_mass | tau_v | zd_value | zd_sigma | ca | cb | sfh rows
+  float* stage_flux = nullptr;
+  double* stage_flux64 = nullptr;
+  CUtensorMap tm_w_hi, tm_w_lo, tm_g_hi, tm_g_lo;
+  size_t smem_bytes = 0;
+};
+
+extern "C" {
+
+const char* sb2_last_error(void) { return g_err.c_str(); }
+
+int sb2_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int sb2_model_destroy(sb2_model* m) {
+  if (!m) return SB2_OK;
+  cudaSetDevice(m->device);
+  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->filt_uv, m->filt_lo,
+                  m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage,
+                  m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_taut, m->g_scale,
+                  m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->g_mscale, m->g_trunc, m->cub_tmp, m->stage_params,
+                  m->stage_flux, m->stage_flux64};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete m;
+  return SB2_OK;
+}
+
+int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
+  if (!d || !out) return fail(SB2_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (d->n_comp != 1 && d->n_comp != 2) return fail(SB2_ERR_INVALID, "n_comp must be 1 or 2");
+  if (d->n_filt < 1 || d->n_filt > sb2::kMaxFilt) return fail(SB2_ERR_INVALID, "n_filt must be in [1, 32]");
+  if (d->k_pad % 32 != 0 || d->k_pad < d->n_age * d->n_z) return fail(SB2_ERR_INVALID, "bad k_pad");
+  const int lch = sb2::kBN / d->n_comp;
+  if (d->n_chunk != (d->n_lam + lch - 1) / lch) return fail(SB2_ERR_INVALID, "bad n_chunk");
+  if (d->max_batch < 1) return fail(SB2_ERR_INVALID, "max_batch must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SB2_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SB2_ERR_CUDA, "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                                  "; this library carries sm_100a (B200) code only");
+  sb2_model* m = new sb2_model();
+  m->device = device;
+  m->n_sm = prop.multiProcessorCount;
+  m->d = *d;
+  int rc = SB2_OK;
+#define UP(dst, src, n) if ((rc = upload(&m->dst, src, (size_t)(n))) != SB2_OK) { sb2_model_destroy(m); return rc; }
+  // ages and bin edges (A2): e_0 = 0, e_{i+1} = (t_i + t_{i+1})/2
+  std::vector<double> ages(d->n_age), edges(d->n_age), lz(d->n_z);
+  for (int i = 0; i < d->n_age; ++i) ages[i] = std::pow(10.0, d->log10ages[i]);
+  edges[0] = 0.0;
+  for (int i = 0; i + 1 < d->n_age; ++i) edges[i + 1] = 0.5 * (ages[i] + ages[i + 1]);
+  for (int i = 0; i < d->n_z; ++i) lz[i] = std::log10(d->metallicities[i]);
+  UP(ages, ages.data(), d->n_age);
+  UP(edges, edges.data(), d->n_age);
+  UP(zmet, d->metallicities, d->n_z);
+  UP(log10zmet, lz.data(), d->n_z);
+  const size_t g_elems = (size_t)d->n_chunk * sb2::kBN * d->k_pad;
+  UP(gt_hi, d->gt_hi, g_elems);
+  UP(gt_lo, d->gt_lo, g_elems);
+  {
+    std::vector<float> kap((size_t)d->n_chunk * lch, 0.f);
+    if (d->kappa) std::memcpy(kap.data(), d->kappa, kap.size() * sizeof(float));
+    UP(kappa, kap.data(), kap.size());
+  }
+  UP(filt_uv, d->filt_uv, (size_t)d->filt_uv_len * 2);
+  UP(filt_lo, d->filt_lo, d->n_filt);
+  UP(filt_hi, d->filt_hi, d->n_filt);
+  m->h_lo.assign(d->filt_lo, d->filt_lo + d->n_filt);
+  m->h_hi.assign(d->filt_hi, d->filt_hi + d->n_filt);
+  m->h_off.assign(d->filt_off, d->filt_off + d->n_filt);
+  for (int f = 0; f < d->n_filt; ++f) {
+    m->h_su.push_back((float)d->filt_su[f]);
+    m->h_sdv.push_back((float)d->filt_sdv[f]);
+  }
+  if (d->igm_bin_pow && d->n_blue > 0) {
+    UP(bin_pow, d->igm_bin_pow, (size_t)8 * d->n_blue);
+    UP(nline, d->igm_nline, d->n_blue);
+    UP(lc_on, d->igm_lc_on, d->n_blue);
+    UP(thr, d->igm_thr, 3 * 64);
+    UP(pre, d->igm_pre, (size_t)5 * (d->n_lines + 1));
+  } else {
+    m->d.n_blue = 0;
+  }
+  UP(dc, d->cosmo_dc, d->cosmo_n + 1);
+  UP(ddc, d->cosmo_ddc, d->cosmo_n + 1);
+  UP(age, d->cosmo_age, d->cosmo_n + 1);
+  UP(dage, d->cosmo_dage, d->cosmo_n + 1);
+#undef UP
+  // workspace
+  m->cap = d->max_batch;
+  m->cap_pad = (m->cap + 127) / 128 * 128;
+  const size_t np = (size_t)m->cap_pad;
+#define AL(ptr, bytes) { cudaError_t e_ = cudaMalloc(reinterpret_cast<void**>(&m->ptr), (bytes)); \
+    if (e_ != cudaSuccess) { sb2_model_destroy(m); return fail(SB2_ERR_CUDA, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_)); } }
+  AL(w_hi, np * d->k_pad * 4);
+  AL(w_lo, np * d->k_pad * 4);
+  AL(igm, (np / 128) * (size_t)(m->d.n_blue > 0 ? m->d.n_blue : 1) * 128 * 4);
+  AL(g_m, np * 4); AL(g_orig, np * 4); AL(perm, np * 4); AL(idx, np * 4);
+  AL(g_beta, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
+  AL(keys, np * 4); AL(keys_sorted, np * 4);
+  AL(g_mscale, np * 8); AL(g_trunc, np * 4);
+  m->cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)m->cap);
+  AL(cub_tmp, m->cub_bytes + 16);
+  AL(stage_params, (size_t)m->cap * (7 + SB2_SFH_ROW) * 8);
+  AL(stage_flux, (size_t)m->cap * d->n_filt * 4);
+  AL(stage_flux64, (size_t)m->cap * d->n_filt * 8);
+#undef AL
+  if ((rc = make_tmap(&m->tm_w_hi, m->w_hi, np, d->k_pad, sb2::kBM)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_w_lo, m->w_lo, np, d->k_pad, sb2::kBM)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK) {
+    sb2_model_destroy(m);
+    return rc;
+  }
+  m->smem_bytes = 1024 + (size_t)sb2::kStages * sb2::kStageBytes + (((size_t)d->filt_uv_len * 8 + 15) & ~size_t(15)) + 128;
+  if (m->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+    sb2_model_destroy(m);
+    return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to the operand pipeline (" +
+                                     std::to_string(m->smem_bytes) + " B needed)");
+  }
+  *out = m;
+  return SB2_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <int C, int NF>
+int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
+  auto k = sb2::synth_kernel<C, NF>;
+  CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes));
+  k<<<grid, sb2::kSynthThreads, m->smem_bytes, st>>>(m->tm_w_hi, m->tm_w_lo, m->tm_g_hi, m->tm_g_lo, a);
+  CU_TRY(cudaGetLastError());
+  return SB2_OK;
+}
+
+int launch_synth(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
+  const int nf = m->d.n_filt, c = m->d.n_comp;
+  if (c == 1) {
+    if (nf <= 8) return launch_synth_t<1, 8>(m, a, grid, st);
+    if (nf <= 24) return launch_synth_t<1, 24>(m, a, grid, st);
+    return launch_synth_t<1, 32>(m, a, grid, st);
+  }
+  if (nf <= 8) return launch_synth_t<2, 8>(m, a, grid, st);
+  if (nf <= 24) return launch_synth_t<2, 24>(m, a, grid, st);
+  return launch_synth_t<2, 32>(m, a, grid, st);
+}
+
+sb2::PrepModel prep_model(const sb2_model* m) {
+  sb2::PrepModel M{};
+  const sb2_model_desc& d = m->d;
+  M.n_age = d.n_age; M.n_z = d.n_z; M.K = d.n_age * d.n_z; M.k_pad = d.k_pad; M.n_lam = d.n_lam;
+  M.n_filt = d.n_filt; M.n_blue = d.n_blue; M.n_lines = d.n_lines; M.variant = d.interp_variant;
+  M.igm_on = d.n_blue > 0;
+  M.ages = m->ages; M.edges = m->edges; M.zmet = m->zmet; M.log10zmet = m->log10zmet;
+  M.lam0 = d.lam0; M.q = d.q; M.ln_q = std::log(d.q); M.grid_scale = d.grid_scale; M.base_mass = d.base_mass;
+  M.filt_lo = m->filt_lo; M.filt_hi = m->filt_hi;
+  M.bin_pow = m->bin_pow; M.nline = m->nline; M.lc_on = m->lc_on; M.thr = m->thr; M.pre = m->pre;
+  M.cosmo_n = d.cosmo_n; M.cosmo_ds = d.cosmo_smax / d.cosmo_n;
+  M.dc = m->dc; M.ddc = m->ddc; M.age = m->age; M.dage = m->dage;
+  return M;
+}
+
+sb2::PrepParams prep_params(const sb2_params* p) {
+  sb2::PrepParams P{};
+  P.n = p->n; P.redshift = p->redshift; P.log_mass = p->log_mass; P.tau_v = p->tau_v;
+  P.sfh_type = p->sfh_type; P.sfh_stride = p->sfh_stride; P.sfh_rows = p->sfh_rows;
+  P.max_age_from_z = p->max_age_from_z; P.norm_mask = p->norm_mask; P.age_zmax_gyr = p->age_zmax_gyr;
+  P.zd_type = p->zd_type; P.zd_value = p->zd_value; P.zd_sigma = p->zd_sigma;
+  P.coef_att = p->coef_att; P.coef_unatt = p->coef_unatt;
+  return P;
+}
+
+int check_params(const sb2_model* m, const sb2_params* p) {
+  if (!m || !p) return fail(SB2_ERR_INVALID, "null argument");
+  if (p->n < 1) return fail(SB2_ERR_INVALID, "empty batch");
+  if (p->n > m->cap) return fail(SB2_ERR_CAPACITY, "batch of " + std::to_string(p->n) + " exceeds max_batch " + std::to_string(m->cap));
+  if (!p->redshift || !p->sfh_rows || !p->zd_value) return fail(SB2_ERR_INVALID, "redshift, sfh_rows and zd_value are required");
+  if (p->sfh_stride < 2 || p->sfh_stride > SB2_SFH_ROW) return fail(SB2_ERR_INVALID, "sfh_stride out of range");
+  if (p->sfh_type < 0 || p->sfh_type > SB2_SFH_CONTINUITY || p->sfh_type == SB2_SFH_DOUBLE_POWERLAW)
+    return fail(SB2_ERR_INVALID, "unsupported sfh_type");
+  if (p->zd_type < 0 || p->zd_type > SB2_ZD_NORMAL_LOG10) return fail(SB2_ERR_INVALID, "bad zd_type");
+  if (p->zd_type >= SB2_ZD_NORMAL_LINEAR && !p->zd_sigma) return fail(SB2_ERR_INVALID, "zd_sigma required for Normal");
+  return SB2_OK;
+}
+
+// sort by redshift -> perm ; prep kernel
+int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, cudaStream_t st) {
+  const long long n = p->n;
+  const long long n_pad = (n + 127) / 128 * 128;
+  const int* perm = nullptr;
+  if (sorted) {
+    const int tb = 256;
+    sort_keys_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(p->redshift, m->keys, m->idx, n);
+    CU_TRY(cudaGetLastError());
+    size_t bytes = m->cub_bytes;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)n, 0, 32, st));
+    perm = m->perm;
+  }
+  sb2::PrepModel M = prep_model(m);
+  sb2::PrepParams P = prep_params(p);
+  sb2::PrepOut O{};
+  O.w_hi = m->w_hi; O.w_lo = m->w_lo; O.w_f64 = w_f64; O.igm = m->igm; O.g_m = m->g_m; O.g_beta = m->g_beta;
+  O.g_taut = m->g_taut; O.g_scale = m->g_scale; O.g_ca = m->g_ca; O.g_cb = m->g_cb; O.g_orig = m->g_orig;
+  O.g_mscale = m->g_mscale; O.g_trunc = m->g_trunc;
+  const size_t sh = (size_t)sb2::kPrepWarps * (M.n_age + M.n_z + SB2_SFH_ROW) * sizeof(double);
+  const unsigned blocks = (unsigned)((n_pad + sb2::kPrepWarps - 1) / sb2::kPrepWarps);
+  sb2::prep_kernel<<<blocks, sb2::kPrepWarps * 32, sh, st>>>(M, P, O, perm, n_pad);
+  CU_TRY(cudaGetLastError());
+  return SB2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb2_build_weights(sb2_model* m, const sb2_params* p, double* w_out, void* stream) {
+  int rc = check_params(m, p);
+  if (rc != SB2_OK) return rc;
+  if (!w_out) return fail(SB2_ERR_INVALID, "w_out is null");
+  CU_TRY(cudaSetDevice(m->device));
+  return run_prep(m, p, w_out, false, (cudaStream_t)stream);
+}
+
+int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, double* flux_scaled,
+                         float* spec_out, void* stream) {
+  int rc = check_params(m, p);
+  if (rc != SB2_OK) return rc;
+  if (!flux_base && !flux_scaled && !spec_out) return fail(SB2_ERR_INVALID, "no output requested");
+  CU_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = run_prep(m, p, nullptr, true, st)) != SB2_OK) return rc;
+  const sb2_model_desc& d = m->d;
+  sb2::SynthArgs a{};
+  a.n_gal = (int)p->n;
+  a.n_tiles = (int)((p->n + 127) / 128);
+  a.n_chunk = d.n_chunk; a.n_kb = d.k_pad / sb2::kBK; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
+  a.n_blue = d.n_blue; a.uv_len = d.filt_uv_len;
+  a.kappa = m->kappa; a.filt_uv = reinterpret_cast<const float2*>(m->filt_uv); a.igm = m->igm;
+  a.g_m = m->g_m; a.g_beta = m->g_beta; a.g_taut = m->g_taut; a.g_scale = m->g_scale; a.g_ca = m->g_ca;
+  a.g_cb = m->g_cb; a.g_orig = m->g_orig; a.g_mscale = m->g_mscale; a.g_trunc = m->g_trunc;
+  a.out_base = flux_base; a.out_scaled = flux_scaled; a.out_spec = spec_out;
+  for (int f = 0; f < d.n_filt; ++f) {
+    a.filt_lo[f] = m->h_lo[f]; a.filt_hi[f] = m->h_hi[f]; a.filt_off[f] = m->h_off[f];
+    a.filt_su[f] = m->h_su[f]; a.filt_sdv[f] = m->h_sdv[f];
+  }
+  const int grid = a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm;
+  return launch_synth(m, a, grid, st);
+}
+
+int sb2_synth_photometry_host(sb2_model* m, const sb2_params* p, float* flux_base, double* flux_scaled,
+                              float* spec_out) {
+  int rc = check_params(m, p);
+  if (rc != SB2_OK) return rc;
+  if (spec_out) return fail(SB2_ERR_INVALID, "spec_out is only supported through the device entry point");
+  CU_TRY(cudaSetDevice(m->device));
+  const size_t n = (size_t)p->n;
+  double* s = m->stage_params;
+  sb2_params dp = *p;
+  auto put = [&](const double* src, size_t count, const double** dst) -> cudaError_t {
+    *dst = nullptr;
+    if (!src) return cudaSuccess;
+    cudaError_t e = cudaMemcpyAsync(s, src, count * sizeof(double), cudaMemcpyHostToDevice, 0);
+    *dst = s;
+    s += count;
+    return e;
+  };
+  CU_TRY(put(p->redshift, n, &dp.redshift));
+  CU_TRY(put(p->log_mass, n, &dp.log_mass));
+  CU_TRY(put(p->tau_v, n, &dp.tau_v));
+  CU_TRY(put(p->zd_value, n, &dp.zd_value));
+  CU_TRY(put(p->zd_sigma, n, &dp.zd_sigma));
+  CU_TRY(put(p->coef_att, n, &dp.coef_att));
+  CU_TRY(put(p->coef_unatt, n, &dp.coef_unatt));
+  CU_TRY(put(p->sfh_rows, n * p->sfh_stride, &dp.sfh_rows));
+  rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux : nullptr, flux_scaled ? m->stage_flux64 : nullptr,
+                            nullptr, nullptr);
+  if (rc != SB2_OK) return rc;
+  if (flux_base) CU_TRY(cudaMemcpyAsync(flux_base, m->stage_flux, n * m->d.n_filt * 4, cudaMemcpyDeviceToHost, 0));
+  if (flux_scaled) CU_TRY(cudaMemcpyAsync(flux_scaled, m->stage_flux64, n * m->d.n_filt * 8, cudaMemcpyDeviceToHost, 0));
+  CU_TRY(cudaStreamSynchronize(0));
+  return SB2_OK;
+}
+
+int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, int32_t n_scatter,
+                             const double* sigma, double min_flux_pc_error, const double* normals, uint64_t seed,
+                             uint64_t epoch, double norm_mag_limit, double* out_flux, double* out_sigma,
+                             float* out_feat, void* stream) {
+  if (!flux || !sigma || n_gal < 1 || n_filt < 1 || n_scatter < 1) return fail(SB2_ERR_INVALID, "bad argument");
+  if (!out_flux && !out_feat) return fail(SB2_ERR_INVALID, "no output requested");
+  sb2::NoiseArgs a{};
+  a.flux = flux; a.n_gal = n_gal; a.n_filt = n_filt; a.n_scatter = n_scatter; a.sigma = sigma;
+  a.min_pc = min_flux_pc_error; a.normals = normals; a.seed = seed; a.epoch = epoch; a.mag_limit = norm_mag_limit;
+  a.out_flux = out_flux; a.out_sigma = out_sigma; a.out_feat = out_feat;
+  const long long rows = (long long)n_gal * n_scatter;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (rows + 255) / 256;
+  const long long cap = (long long)n_sm * 16;
+  if (blocks > cap) blocks = cap;
+  sb2::depth_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  CU_TRY(cudaGetLastError());
+  return SB2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+// Weight construction ("prep") kernel: one warp per galaxy, float64.
+//
+// For the galaxy in sorted slot t it produces everything the contraction kernel needs:
+//   * SFZH weights  w[iz*n_age + ia] = sf[ia] * zd[iz]  (Stars.__init__ in the
+//     reference, library.py:1372-1379), written as a TF32 hi/lo pair (3xTF32 operand A);
+//   * the Inoue+14 transmission row exp(-tau(z, lam_i (1+z))) for the bins blueward of Ly-alpha;
+//   * per-galaxy scalars: integer/fractional filter shift (m, beta) on the geometric axis,
+//     dust exponent scale, flux scale (1+z)/(4 pi d_L^2) from the cosmology table, mass scale.
+// HBM-bound by design: algorithmic bytes per galaxy = 2 * 4 * k_pad (weights) + 4 * n_blue (IGM).
+#pragma once
+#include "ptx.cuh"
+#include "../../include/synference_b200.h"
+
+namespace sb2 {
+
+struct PrepModel {
+  int n_age, n_z, K, k_pad, n_lam, n_filt, n_blue, n_lines, variant, igm_on;
+  const double* ages;      // [n_age] yr
+  const double* edges;     // [n_age] e_0..e_{n_age-1} (bin a spans [e_a, e_{a+1}], a < n_age-1)
+  const double* zmet;      // [n_z]
+  const double* log10zmet; // [n_z]
+  double lam0, q, ln_q, grid_scale, base_mass;
+  const int* filt_lo;
+  const int* filt_hi;
+  // igm tables
+  const double* bin_pow;  // [8][n_blue]
+  const int* nline;       // [n_blue]
+  const int* lc_on;       // [n_blue]
+  const double* thr;      // [3][64]
+  const double* pre;      // [5][n_lines+1]
+  // cosmology
+  int cosmo_n;
+  double cosmo_ds;
+  const double* dc;
+  const double* ddc;
+  const double* age;
+  const double* dage;
+};
+
+struct PrepParams {  // device pointers (sb2_params with device arrays)
+  long long n;
+  const double* redshift;
+  const double* log_mass;
+  const double* tau_v;
+  int sfh_type;
+  int sfh_stride;
+  const double* sfh_rows;
+  int max_age_from_z;
+  unsigned norm_mask;
+  double age_zmax_gyr;
+  int zd_type;
+  const double* zd_value;
+  const double* zd_sigma;
+  const double* coef_att;
+  const double* coef_unatt;
+};
+
+struct PrepOut {
+  float* w_hi;      // [n_pad][k_pad]
+  float* w_lo;      // [n_pad][k_pad]
+  double* w_f64;    // optional [n][K] in ORIGINAL order (parity hook), else nullptr
+  float* igm;       // [n_tiles][n_blue][128]
+  int* g_m;         // [n_pad]
+  float* g_beta;    // [n_pad]
+  float* g_taut;    // [n_pad]
+  float* g_scale;   // [n_pad]
+  float* g_ca;      // [n_pad]
+  float* g_cb;      // [n_pad]
+  int* g_orig;      // [n_pad]  original index, -1 for padding rows
+  double* g_mscale; // [n_pad]
+  unsigned* g_trunc;// [n_pad]  bit f set: filter f not fully covered by the grid at this z
+};
+
+__device__ __forceinline__ double hermite_lut(const double* y, const double* dy, double ds, int n, double s) {
+  double x = s / ds;
+  x = fmin(fmax(x, 0.0), (double)n - 1e-9);
+  int k = (int)x;
+  double t = x - (double)k;
+  double omt = 1.0 - t;
+  double h00 = (1.0 + 2.0 * t) * omt * omt, h10 = t * omt * omt;
+  double h01 = t * t * (3.0 - 2.0 * t), h11 = t * t * (t - 1.0);
+  return h00 * y[k] + h10 * ds * dy[k] + h01 * y[k + 1] + h11 * ds * dy[k + 1];
+}
+
+// Phi(uh) - Phi(ul) evaluated in whichever tail avoids cancellation.
+__device__ __forceinline__ double phi_diff(double ul, double uh) {
+  const double r = 0.70710678118654752440;
+  if (ul + uh > 0.0) return 0.5 * (erfc(ul * r) - erfc(uh * r));
+  return 0.5 * (erfc(-uh * r) - erfc(-ul * r));
+}
+
+// Mass formed between lookback ages [lo, hi] (already clipped to [min_age, max_age]).
+__device__ double sfh_bin_mass(int type, const double* p, double mn, double mx, double lo, double hi,
+                               double e_lo, double e_hi) {
+  if (type == SB2_SFH_CONTINUITY) {
+    const int nb = (int)p[0];
+    const double* edges = p + 1;
+    const double* ratios = p + 1 + nb + 1;
+    double sfr = 1.0, m = 0.0;
+    for (int j = 0; j < nb; ++j) {
+      if (j > 0) sfr *= pow(10.0, -ratios[j - 1]);
+      double ov = fmin(e_hi, edges[j + 1]) - fmax(e_lo, edges[j]);
+      if (ov > 0.0) m += sfr * ov;
+    }
+    return m;
+  }
+  if (!(hi > lo)) return 0.0;
+  switch (type) {
+    case SB2_SFH_CONSTANT:
+      return hi - lo;
+    case SB2_SFH_GAUSSIAN: {
+      double pk = p[0], s = p[1];
+      return s * 2.50662827463100050242 * phi_diff((lo - pk) / s, (hi - pk) / s);
+    }
+    case SB2_SFH_EXPONENTIAL:
+    case SB2_SFH_DECLINING_EXP: {
+      double tau = (type == SB2_SFH_EXPONENTIAL) ? p[0] : -p[0];
+      double shift = tau > 0.0 ? (mx - mn) / tau : 0.0;
+      return tau * (exp((mx - lo) / tau - shift) - exp((mx - hi) / tau - shift));
+    }
+    case SB2_SFH_DELAYED_EXP: {
+      double tau = p[0];
+      double t1 = mx - lo, t2 = mx - hi;
+      return -tau * (t1 + tau) * exp(-t1 / tau) + tau * (t2 + tau) * exp(-t2 / tau);
+    }
+    case SB2_SFH_LOGNORMAL: {
+      double tau = p[0], pk = p[1];
+      double t0 = log(mx - pk) + tau * tau;
+      double u_hi = (log(fmax(mx - hi, 1e-300)) - t0) / tau;
+      double u_lo = (log(fmax(mx - lo, 1e-300)) - t0) / tau;
+      return tau * 2.50662827463100050242 * phi_diff(u_hi, u_lo);
+    }
+    default:
+      return nan("");
+  }
+}
+
+constexpr int kPrepWarps = 8;
+
+__global__ void __launch_bounds__(kPrepWarps * 32)
+prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, long long n_pad) {
+  extern __shared__ double prep_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * kPrepWarps + warp;
+  if (t >= n_pad) return;
+  double* sf = prep_smem + (size_t)warp * (M.n_age + M.n_z + SB2_SFH_ROW);
+  double* zd = sf + M.n_age;
+  double* prow = zd + M.n_z;
+  const unsigned FULL = 0xffffffffu;
+
+  if (t >= P.n) {  // padding row of the last tile
+    for (int k = lane; k < M.k_pad; k += 32) {
+      O.w_hi[t * M.k_pad + k] = 0.f;
+      O.w_lo[t * M.k_pad + k] = 0.f;
+    }
+    if (M.igm_on)
+      for (int i = lane; i < M.n_blue; i += 32)
+        O.igm[((t >> 7) * M.n_blue + i) * 128 + (t & 127)] = 1.f;
+    if (lane == 0) {
+      O.g_m[t] = 0; O.g_beta[t] = 0.5f; O.g_taut[t] = 0.f; O.g_scale[t] = 0.f; O.g_ca[t] = 0.f;
+      O.g_cb[t] = 0.f; O.g_orig[t] = -1; O.g_mscale[t] = 0.0; O.g_trunc[t] = 0u;
+    }
+    return;
+  }
+
+  const long long g = perm ? (long long)perm[t] : t;
+  const double z = P.redshift[g];
+  const double zp = 1.0 + z;
+  const double s = log1p(z);
+
+  // ---- SFH parameters ------------------------------------------------------------------
+  if (lane < SB2_SFH_ROW) prow[lane] = (lane < P.sfh_stride) ? P.sfh_rows[g * P.sfh_stride + lane] : 0.0;
+  __syncwarp();
+  double mn = prow[0], mx = prow[1];
+  if (P.max_age_from_z) {
+    double age_gyr = hermite_lut(M.age, M.dage, M.cosmo_ds, M.cosmo_n, s);
+    mx = (age_gyr - P.age_zmax_gyr) * 1.0e9;
+    if (lane < SB2_SFH_ROW - 2 && ((P.norm_mask >> lane) & 1u)) prow[2 + lane] *= mx;
+    __syncwarp();
+  }
+  const double* p = prow + 2;
+
+  double part = 0.0;
+  for (int a = lane; a < M.n_age; a += 32) {
+    double m = 0.0;
+    if (a < M.n_age - 1) {  // the last age bin receives no mass (A2)
+      double e_lo = M.edges[a], e_hi = M.edges[a + 1];
+      double lo = fmin(fmax(e_lo, mn), mx), hi = fmin(fmax(e_hi, mn), mx);
+      m = sfh_bin_mass(P.sfh_type, p, mn, mx, lo, hi, e_lo, e_hi);
+    }
+    sf[a] = m;
+    part += m;
+  }
+  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+  const double inv_sf = 1.0 / part;
+
+  // ---- metallicity weights ---------------------------------------------------------------
+  const double zv = P.zd_value[g];
+  const double zs = P.zd_sigma ? P.zd_sigma[g] : 0.0;
+  const bool logz = (P.zd_type == SB2_ZD_DELTA_LOG10 || P.zd_type == SB2_ZD_NORMAL_LOG10);
+  const double* zx = logz ? M.log10zmet : M.zmet;
+  double zpart = 0.0;
+  if (P.zd_type == SB2_ZD_DELTA_LINEAR || P.zd_type == SB2_ZD_DELTA_LOG10) {
+    int j = 0;  // largest j with zx[j] <= zv
+    for (int i = 1; i < M.n_z; ++i) j = (zx[i] <= zv) ? i : j;
+    double f = 0.0;
+    if (zv <= zx[0]) { j = 0; f = 0.0; }
+    else if (zv >= zx[M.n_z - 1]) { j = M.n_z - 1; f = 0.0; }
+    else f = (zv - zx[j]) / (zx[j + 1] - zx[j]);
+    for (int i = lane; i < M.n_z; i += 32) zd[i] = (i == j) ? 1.0 - f : ((i == j + 1) ? f : 0.0);
+    zpart = 1.0;
+  } else {
+    for (int i = lane; i < M.n_z; i += 32) {
+      double u = (zx[i] - zv) / zs;
+      double w = exp(-0.5 * u * u);
+      zd[i] = w;
+      zpart += w;
+    }
+    for (int o = 16; o; o >>= 1) zpart += __shfl_xor_sync(FULL, zpart, o);
+  }
+  __syncwarp();
+  const double inv = inv_sf / zpart;
+
+  // ---- weights row (TF32 hi/lo split, K index = iz*n_age + ia) -----------------------------
+  for (int k = lane; k < M.k_pad; k += 32) {
+    double w = 0.0;
+    if (k < M.K) w = sf[k % M.n_age] * zd[k / M.n_age] * inv;
+    float hi = to_tf32_rna((float)w);
+    float lo = to_tf32_rna((float)(w - (double)hi));
+    O.w_hi[t * M.k_pad + k] = hi;
+    O.w_lo[t * M.k_pad + k] = lo;
+    if (O.w_f64 && k < M.K) O.w_f64[g * M.K + k] = w;
+  }
+
+  // ---- per-galaxy scalars -------------------------------------------------------------------
+  const double tq = s / M.ln_q;
+  const int m = (int)floor(tq);
+  const double r = exp(s - (double)m * M.ln_q);  // (1+z)/q^m in [1, q)
+  const double beta = (M.variant == 0) ? (1.0 - 1.0 / r) / (1.0 - 1.0 / M.q) : (r - 1.0) / (M.q - 1.0);
+  unsigned trunc = 0u;
+  if (lane < M.n_filt) {
+    int i_first = M.filt_lo[lane] - 1 - m, i_last = M.filt_hi[lane] - m;
+    trunc = (i_first < 0 || i_last > M.n_lam - 1) ? 1u : 0u;
+  }
+  trunc = __ballot_sync(FULL, trunc != 0u);
+  if (lane == 0) {
+    const double dc = hermite_lut(M.dc, M.ddc, M.cosmo_ds, M.cosmo_n, s);
+    const double dl_cm = zp * dc * 3.0856775814913673e24;
+    const double scale = M.grid_scale * M.base_mass * zp / (4.0 * 3.14159265358979323846 * dl_cm * dl_cm) * 1.0e32;
+    O.g_m[t] = m;
+    O.g_beta[t] = (float)beta;
+    O.g_taut[t] = (float)((P.tau_v ? P.tau_v[g] : 0.0) * 1.44269504088896340736);
+    O.g_scale[t] = (float)scale;
+    O.g_ca[t] = (float)(P.coef_att ? P.coef_att[g] : 1.0);
+    O.g_cb[t] = (float)(P.coef_unatt ? P.coef_unatt[g] : 1.0);
+    O.g_orig[t] = (int)g;
+    O.g_mscale[t] = P.log_mass ? pow(10.0, P.log_mass[g]) / M.base_mass : 1.0;
+    O.g_trunc[t] = trunc;
+  }
+
+  // ---- Inoue+14 transmission for the bins blueward of Ly-alpha ---------------------------------
+  if (!M.igm_on) return;
+  // (1+z)^p for p in (1.2, 2.1, 3.7, 5.5, -0.3, 2, 3, -0.9, 1.6, 3.4, 2.3, 3.3): lane l computes one
+  const double zpw_exp[12] = {1.2, 2.1, 3.7, 5.5, -0.3, 2.0, 3.0, -0.9, 1.6, 3.4, 2.3, 3.3};
+  double mine = (lane < 12) ? pow(zp, zpw_exp[lane]) : 0.0;
+  double Z[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) Z[i] = __shfl_sync(FULL, mine, i);
+  const int nb = M.n_blue;
+  const int np1 = M.n_lines + 1;
+  for (int i = lane; i < nb; i += 32) {
+    const double b12 = M.bin_pow[0 * nb + i] * Z[0], b21 = M.bin_pow[1 * nb + i] * Z[1];
+    const double b37 = M.bin_pow[2 * nb + i] * Z[2], b55 = M.bin_pow[3 * nb + i] * Z[3];
+    const double bm3 = M.bin_pow[4 * nb + i] * Z[4], b2 = M.bin_pow[5 * nb + i] * Z[5];
+    const double b3 = M.bin_pow[6 * nb + i] * Z[6];
+    const double xl = M.bin_pow[7 * nb + i] * zp;  // lam_obs / 911.8
+    int n1 = 0, n2 = 0, nd = 0;  // leading lines (largest lam_j) still in the low-z regimes
+#pragma unroll
+    for (int step = 32; step; step >>= 1) {
+      if (M.thr[0 * 64 + n1 + step - 1] > xl) n1 += step;
+      if (M.thr[1 * 64 + n2 + step - 1] > xl) n2 += step;
+      if (M.thr[2 * 64 + nd + step - 1] > xl) nd += step;
+    }
+    const int J = M.nline[i];
+    const int a = min(J, n1), b = min(J, n2), c = min(J, nd);
+    double tau = b12 * M.pre[0 * np1 + a] + b37 * (M.pre[1 * np1 + b] - M.pre[1 * np1 + a]) +
+                 b55 * (M.pre[2 * np1 + J] - M.pre[2 * np1 + b]) + b2 * M.pre[3 * np1 + c] +
+                 b3 * (M.pre[4 * np1 + J] - M.pre[4 * np1 + c]);
+    if (M.lc_on[i]) {
+      // Lyman continuum, DLA component
+      if (z < 2.0) tau += 0.2113 * Z[5] - 0.07661 * Z[10] * bm3 - 0.1347 * b2;
+      else if (xl >= 3.0) tau += 0.04696 * Z[6] - 0.01779 * Z[11] * bm3 - 0.02916 * b3;
+      else tau += 0.6340 + 0.04696 * Z[6] - 0.01779 * Z[11] * bm3 - 0.1347 * b2 - 0.2905 * bm3;
+      // Lyman continuum, LAF component
+      if (z < 1.2) tau += 0.3248 * (b12 - Z[7] * b21);
+      else if (z < 4.7) {
+        if (xl >= 2.2) tau += 2.545e-2 * (Z[8] * b21 - b37);
+        else tau += 2.545e-2 * Z[8] * b21 + 0.3248 * b12 - 0.2496 * b21;
+      } else {
+        if (xl > 5.7) tau += 5.221e-4 * (Z[9] * b21 - b55);
+        else if (xl >= 2.2 && xl < 5.7) tau += 5.221e-4 * Z[9] * b21 + 0.2182 * b21 - 2.545e-2 * b37;
+        else if (xl < 2.2) tau += 5.221e-4 * Z[9] * b21 + 0.3248 * b12 - 3.140e-2 * b21;
+      }
+    }
+    O.igm[((t >> 7) * nb + i) * 128 + (t & 127)] = (float)exp(-tau);
+  }
+}
+
+}  // namespace sb2

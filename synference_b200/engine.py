@@ -1,0 +1,379 @@
+"""Host side of the CUDA hot path: lowers a (grid, emission model, filters, cosmology) model to
+device tables once, then runs batches of galaxy parameters through the C ABI.
+
+What this replaces in the reference: the per-batch ``Pipeline(...)`` set-up and ``run()`` of
+``GalaxyBasis.process_galaxies`` (``library.py:2571-2619``) and the single-galaxy chain of
+``GalaxySimulator.simulate`` (``library.py:5711-5772``).  PyTorch is used only for device
+memory and streams when the caller keeps data on the GPU; the host-buffer entry point needs
+no torch at all.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _capi, igm as _igm
+from .cosmology import Planck18
+from .parametric import (EmissionModel, FilterCollection, Grid, SFH_MAX_PARAMS, ZD_NORMAL_LINEAR,
+                         pack_sfh, pack_zdist)
+from .units import strip_units
+
+CHUNK_COLS = 256
+
+
+def tf32_split(x64: np.ndarray):
+    """(hi, lo) float32 arrays with hi = tf32_rna(x), lo = tf32_rna(x - hi)  (3xTF32 operands)."""
+    def rna(a32):
+        bits = a32.view(np.uint32)
+        return ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    hi = rna(np.ascontiguousarray(x64, dtype=np.float32))
+    lo = rna(np.ascontiguousarray(x64 - hi.astype(np.float64), dtype=np.float32))
+    return hi, lo
+
+
+@dataclass
+class GalaxyParams:
+    """Struct-of-arrays parameter block for a population (float64, one entry per galaxy)."""
+
+    redshift: np.ndarray
+    sfh_type: int
+    sfh_rows: np.ndarray                 # (N, stride) [min_age, max_age, p0, ...] in yr
+    zd_type: int
+    zd_value: np.ndarray
+    zd_sigma: Optional[np.ndarray] = None
+    log_mass: Optional[np.ndarray] = None
+    tau_v: Optional[np.ndarray] = None
+    coef_att: Optional[np.ndarray] = None
+    coef_unatt: Optional[np.ndarray] = None
+    max_age_from_z: bool = False
+    norm_mask: int = 0
+    age_zmax_gyr: float = 0.0
+    extra: dict = field(default_factory=dict)
+
+    def __len__(self):
+        return int(np.asarray(self.redshift).shape[0])
+
+    @classmethod
+    def from_objects(cls, redshifts, sfhs, metal_dists, log_mass=None, tau_v=None, **kw):
+        """Lower the reference-style per-galaxy object lists once (``library.py:2168-2261``)."""
+        sfh_type, rows = pack_sfh(sfhs)
+        zd_type, zv, zs = pack_zdist(metal_dists)
+        n = len(np.atleast_1d(redshifts))
+        bc = lambda a: None if a is None else np.broadcast_to(  # noqa: E731
+            np.asarray(strip_units(a), dtype=np.float64), (n,)).copy()
+        if rows.shape[0] == 1 and n > 1:
+            rows = np.repeat(rows, n, axis=0)
+        used = max(2, int(np.max(np.nonzero(np.abs(rows).sum(0))[0], initial=1)) + 1)
+        return cls(redshift=bc(redshifts), sfh_type=sfh_type, sfh_rows=np.ascontiguousarray(rows[:, :used]),
+                   zd_type=zd_type, zd_value=bc(zv), zd_sigma=bc(zs) if zd_type >= ZD_NORMAL_LINEAR else None,
+                   log_mass=bc(log_mass), tau_v=bc(tau_v), **kw)
+
+    def slice(self, sl):
+        g = lambda a: None if a is None else a[sl]  # noqa: E731
+        return GalaxyParams(self.redshift[sl], self.sfh_type, self.sfh_rows[sl], self.zd_type,
+                            self.zd_value[sl], g(self.zd_sigma), g(self.log_mass), g(self.tau_v),
+                            g(self.coef_att), g(self.coef_unatt), self.max_age_from_z, self.norm_mask,
+                            self.age_zmax_gyr)
+
+
+def geometric_ratio(lam):
+    lam = np.asarray(lam, dtype=np.float64)
+    r = lam[1:] / lam[:-1]
+    q = float(np.exp(np.log(lam[-1] / lam[0]) / (len(lam) - 1)))
+    if np.max(np.abs(r / q - 1.0)) > 1e-9:
+        raise ValueError(
+            "the CUDA path needs grid and filters on one shared constant-R wavelength axis "
+            "(generate_constant_R, as every production script of the reference builds); resample the "
+            "Grid and FilterCollection with new_lam=... first")
+    return q
+
+
+def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, filters: FilterCollection,
+                 cosmo=Planck18, igm=True, variant="nu", z_table_max=100.0):
+    """All float64 host-side derivations behind ``sb2_model_desc`` (kept as numpy arrays)."""
+    lam = np.asarray(grid.lam, dtype=np.float64)
+    n_lam = lam.size
+    q = geometric_ratio(lam)
+    att, un = emission_model.recipe(emission_key)
+    has_att, has_un = bool(np.any(att != 0)), bool(np.any(un != 0))
+    dust = emission_model.dust_curve
+    if has_att and dust is None:
+        raise ValueError(f"spectrum '{emission_key}' is dust attenuated but the emission model has no dust_curve")
+    if has_att and has_un:
+        comps, kappa = [att, un], dust.get_tau(lam)
+    elif has_att:
+        comps, kappa = [att], dust.get_tau(lam)
+    else:
+        comps, kappa = [un], None
+    n_comp = len(comps)
+    na, nz = grid.log10ages.size, grid.metallicity.size
+    k = na * nz
+    k_pad = (k + 31) // 32 * 32
+    lch = CHUNK_COLS // n_comp
+    n_chunk = (n_lam + lch - 1) // lch
+    grid_scale = float(max(c.max() for c in comps))
+    if not np.isfinite(grid_scale) or grid_scale <= 0:
+        raise ValueError("grid spectra must be finite and not all zero")
+    gt = np.zeros((n_chunk, n_comp, lch, k_pad), dtype=np.float64)
+    for ci, comp in enumerate(comps):
+        # (age, Z, lam) -> (lam, Z, age) -> rows lam, columns k = iz*n_age + ia
+        flat = np.transpose(comp, (2, 1, 0)).reshape(n_lam, k) / grid_scale
+        pad = np.zeros((n_chunk * lch, k))
+        pad[:n_lam] = flat
+        gt[:, ci, :, :k] = pad.reshape(n_chunk, lch, k)
+    gt = gt.reshape(n_chunk * CHUNK_COLS, k_pad)
+    gt_hi, gt_lo = tf32_split(gt)
+    kap = None
+    if kappa is not None:
+        kap = np.zeros(n_chunk * lch, dtype=np.float32)
+        kap[:n_lam] = kappa
+    # ---- filters on the shared axis -> (U, DV) weight pairs (SURVEY A9 on a geometric grid)
+    if variant not in ("nu", "lam"):
+        raise ValueError("variant must be 'nu' or 'lam'")
+    c_left, c_right = ((q - 1) / 2, (1 - 1 / q) / 2) if variant == "nu" else ((1 - 1 / q) / 2, (q - 1) / 2)
+    lo_l, hi_l, off_l, su_l, sdv_l, uv = [], [], [], [], [], []
+    for f in filters:
+        if f.lam.shape != lam.shape or np.max(np.abs(f.lam / lam - 1)) > 1e-12:
+            raise ValueError(f"filter {f.filter_code} is not tabulated on the grid's wavelength axis; "
+                             "use FilterCollection.resample_filters(new_lam=grid.lam)")
+        nzi = np.nonzero(f.t > 0)[0]
+        if nzi.size < 2:
+            raise ValueError(f"filter {f.filter_code} has fewer than two in-band samples on this grid")
+        lo, hi = int(nzi[0]), int(nzi[-1])
+        if nzi.size != hi - lo + 1:
+            raise ValueError(f"filter {f.filter_code} has interior zeros; not supported by the batched path")
+        if lo < 1 or hi > n_lam - 2:
+            raise ValueError(f"filter {f.filter_code} is truncated by the wavelength grid")
+        n = np.arange(lo - 2, hi + 2)                 # table index k -> n = lo - 2 + k
+        tpad = np.concatenate([[0.0, 0.0], f.t, [0.0, 0.0]])
+        t_n, t_n1 = tpad[n + 2], tpad[n + 3]
+        w = np.where((n >= lo) & (n <= hi - 1), c_left + c_right, 0.0)
+        w = np.where(n == lo - 1, c_right, w)
+        w = np.where(n == hi, c_left, w)
+        u, v = w * t_n, w * t_n1
+        lo_l.append(lo); hi_l.append(hi); off_l.append(sum(len(x) for x in uv))
+        su_l.append(u.sum()); sdv_l.append((v - u).sum())
+        uv.append(np.stack([u, v - u], 1))
+    uv = np.concatenate(uv, 0).astype(np.float32)
+    tables = dict(
+        n_age=na, n_z=nz, n_lam=n_lam, n_comp=n_comp, n_filt=len(lo_l), k_pad=k_pad, n_chunk=n_chunk,
+        log10ages=np.ascontiguousarray(grid.log10ages, dtype=np.float64),
+        metallicities=np.ascontiguousarray(grid.metallicity, dtype=np.float64),
+        gt_hi=gt_hi, gt_lo=gt_lo, grid_scale=grid_scale, kappa=kap, lam0=float(lam[0]), q=q,
+        interp_variant=0 if variant == "nu" else 1,
+        filt_lo=np.array(lo_l, dtype=np.int32), filt_hi=np.array(hi_l, dtype=np.int32),
+        filt_off=np.array(off_l, dtype=np.int32), filt_uv=np.ascontiguousarray(uv),
+        filt_su=np.array(su_l, dtype=np.float64), filt_sdv=np.array(sdv_l, dtype=np.float64),
+    )
+    if igm:
+        laf, dla = (igm if isinstance(igm, tuple) else (_igm.INOUE14_LAF, _igm.INOUE14_DLA))
+        tables["igm"] = _igm.device_tables(lam, laf, dla)
+    else:
+        tables["igm"] = None
+    tab = cosmo.table(z_max=z_table_max)
+    tables["cosmo"] = tab
+    return tables
+
+
+class SynthEngine:
+    """Device-resident model + batched synthesis (one instance per GPU / process)."""
+
+    def __init__(self, grid: Grid, emission_model: EmissionModel, emission_key: str,
+                 filters: FilterCollection, cosmo=Planck18, igm=True, variant="nu", base_mass=1.0e9,
+                 max_batch=1 << 20, device=0):
+        self.lib = _capi.load()
+        if self.lib.sb2_device_count() < 1:
+            raise RuntimeError("synference_b200: no CUDA device visible; the hot path has no CPU fallback")
+        self.tables = t = build_tables(grid, emission_model, emission_key, filters, cosmo, igm, variant)
+        self.filter_codes = list(filters.filter_codes)
+        self.n_filt, self.n_lam, self.n_comp = t["n_filt"], t["n_lam"], t["n_comp"]
+        self.k = t["n_age"] * t["n_z"]
+        self.k_pad = t["k_pad"]
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        self.base_mass = float(base_mass)
+        self.cosmo = cosmo
+        d = _capi.ModelDesc()
+        keep = []
+
+        def ptr(a, ctype):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a)
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(ctype))
+
+        for name in ("n_age", "n_z", "n_lam", "n_comp", "n_filt", "k_pad", "n_chunk", "interp_variant"):
+            setattr(d, name, int(t[name]))
+        d.log10ages, d.metallicities = ptr(t["log10ages"], C.c_double), ptr(t["metallicities"], C.c_double)
+        d.gt_hi, d.gt_lo = ptr(t["gt_hi"], C.c_float), ptr(t["gt_lo"], C.c_float)
+        d.grid_scale, d.lam0, d.q = t["grid_scale"], t["lam0"], t["q"]
+        d.kappa = ptr(t["kappa"], C.c_float)
+        d.filt_lo, d.filt_hi = ptr(t["filt_lo"], C.c_int32), ptr(t["filt_hi"], C.c_int32)
+        d.filt_off, d.filt_uv = ptr(t["filt_off"], C.c_int32), ptr(t["filt_uv"], C.c_float)
+        d.filt_uv_len = int(t["filt_uv"].shape[0])
+        d.filt_su, d.filt_sdv = ptr(t["filt_su"], C.c_double), ptr(t["filt_sdv"], C.c_double)
+        ig = t["igm"]
+        if ig is not None and ig["n_blue"] > 0:
+            d.n_blue, d.n_lines = int(ig["n_blue"]), int(ig["n_lines"])
+            d.igm_bin_pow = ptr(ig["bin_pow"], C.c_double)
+            d.igm_nline, d.igm_lc_on = ptr(ig["nline"], C.c_int32), ptr(ig["lc_on"], C.c_int32)
+            d.igm_thr, d.igm_pre = ptr(ig["thr"], C.c_double), ptr(ig["pre"], C.c_double)
+        cz = t["cosmo"]
+        d.cosmo_n, d.cosmo_smax = int(cz.n_cells), float(cz.s_max)
+        d.cosmo_dc, d.cosmo_ddc = ptr(cz.dc, C.c_double), ptr(cz.ddc, C.c_double)
+        d.cosmo_age, d.cosmo_dage = ptr(cz.age, C.c_double), ptr(cz.dage, C.c_double)
+        d.base_mass, d.max_batch = self.base_mass, self.max_batch
+        handle = C.c_void_p()
+        _capi.check(self.lib.sb2_model_create(C.byref(d), self.device, C.byref(handle)), "sb2_model_create")
+        self._h = handle
+        del keep
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.sb2_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameter marshalling ------------------------------------------------------------
+    @staticmethod
+    def _fill(p: GalaxyParams, get_ptr):
+        s = _capi.Params()
+        s.n = len(p)
+        s.redshift, s.log_mass, s.tau_v = get_ptr(p.redshift), get_ptr(p.log_mass), get_ptr(p.tau_v)
+        s.sfh_type, s.sfh_stride, s.sfh_rows = int(p.sfh_type), int(p.sfh_rows.shape[1]), get_ptr(p.sfh_rows)
+        s.max_age_from_z, s.norm_mask, s.age_zmax_gyr = int(p.max_age_from_z), int(p.norm_mask), float(p.age_zmax_gyr)
+        s.zd_type, s.zd_value, s.zd_sigma = int(p.zd_type), get_ptr(p.zd_value), get_ptr(p.zd_sigma)
+        s.coef_att, s.coef_unatt = get_ptr(p.coef_att), get_ptr(p.coef_unatt)
+        return s
+
+    @staticmethod
+    def _host_ptr_factory(keep):
+        def get(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            return a.ctypes.data
+        return get
+
+    # ---- host-buffer entry (what a drop-in caller uses) --------------------------------------
+    def photometry(self, params: GalaxyParams, scaled=True, out=None):
+        """Fluxes [nJy] as a host array ``(N, n_filt)``: float64 scaled by stellar mass
+        (``float32(base) * 10**log_mass / base_mass``, ``library.py:4588-4609``) or float32 at base mass."""
+        n = len(params)
+        res = out if out is not None else np.empty((n, self.n_filt), dtype=np.float64 if scaled else np.float32)
+        for a in range(0, n, self.max_batch):
+            b = min(n, a + self.max_batch)
+            keep = []
+            s = self._fill(params.slice(slice(a, b)), self._host_ptr_factory(keep))
+            dst = res[a:b]
+            assert dst.flags.c_contiguous
+            if scaled:
+                rc = self.lib.sb2_synth_photometry_host(self._h, C.byref(s), None, dst.ctypes.data, None)
+            else:
+                rc = self.lib.sb2_synth_photometry_host(self._h, C.byref(s), dst.ctypes.data, None, None)
+            _capi.check(rc, "sb2_synth_photometry_host")
+        return res
+
+    # ---- device entry (torch tensors stay on the GPU) ------------------------------------------
+    def to_device(self, params: GalaxyParams):
+        import torch
+        dev = torch.device("cuda", self.device)
+        mv = lambda a: None if a is None else torch.as_tensor(  # noqa: E731
+            np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        return DeviceParams(params, {k: mv(getattr(params, k)) for k in
+                                     ("redshift", "log_mass", "tau_v", "sfh_rows", "zd_value", "zd_sigma",
+                                      "coef_att", "coef_unatt")})
+
+    def photometry_device(self, dparams: "DeviceParams", flux_base=None, flux_scaled=None, spectra=None):
+        """Run one batch whose parameters are already in HBM; outputs are caller-provided torch tensors."""
+        import torch
+        p = dparams.host
+        t = dparams.tensors
+        s = self._fill(p, lambda a: None)
+        for k2, v in t.items():
+            setattr(s, k2, None if v is None else v.data_ptr())
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        dp = lambda x: None if x is None else x.data_ptr()  # noqa: E731
+        rc = self.lib.sb2_synth_photometry(self._h, C.byref(s), dp(flux_base), dp(flux_scaled), dp(spectra), st)
+        _capi.check(rc, "sb2_synth_photometry")
+
+    def spectra(self, params: GalaxyParams):
+        """Observed-frame f_nu [nJy] at base mass on the rest-frame axis, ``(N, n_lam)`` float32 (host)."""
+        import torch
+        n = len(params)
+        out = np.empty((n, self.n_lam), dtype=np.float32)
+        dev = torch.device("cuda", self.device)
+        for a in range(0, n, self.max_batch):
+            b = min(n, a + self.max_batch)
+            dpar = self.to_device(params.slice(slice(a, b)))
+            spec = torch.empty((b - a, self.n_lam), dtype=torch.float32, device=dev)
+            flux = torch.empty((b - a, self.n_filt), dtype=torch.float32, device=dev)
+            self.photometry_device(dpar, flux_base=flux, spectra=spec)
+            out[a:b] = spec.cpu().numpy()
+        return out
+
+    def weights(self, params: GalaxyParams):
+        """SFZH weights ``(N, n_age*n_z)`` float64, k = iz*n_age + ia (parity hook)."""
+        import torch
+        n = len(params)
+        dev = torch.device("cuda", self.device)
+        out = np.empty((n, self.k), dtype=np.float64)
+        for a in range(0, n, self.max_batch):
+            b = min(n, a + self.max_batch)
+            dpar = self.to_device(params.slice(slice(a, b)))
+            s = self._fill(dpar.host, lambda x: None)
+            for k2, v in dpar.tensors.items():
+                setattr(s, k2, None if v is None else v.data_ptr())
+            w = torch.empty((b - a, self.k), dtype=torch.float64, device=dev)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _capi.check(self.lib.sb2_build_weights(self._h, C.byref(s), w.data_ptr(), st), "sb2_build_weights")
+            out[a:b] = w.cpu().numpy()
+        return out
+
+
+@dataclass
+class DeviceParams:
+    host: GalaxyParams
+    tensors: dict
+
+
+def depth_noise_features(flux, sigma, n_scatter=1, normals=None, seed=0, epoch=0, norm_mag_limit=50.0,
+                         min_flux_pc_error=0.0, want_flux=True, want_features=True, device=0):
+    """Depth scatter + AB feature rows on the GPU (``sb2_depth_noise_features``).
+
+    flux ``(n_gal, n_filt)`` nJy (numpy or CUDA torch tensor), sigma ``(n_filt,)`` nJy.
+    Returns ``(noisy_flux (n_filt, n_rows) f64 | None, sigma (n_filt, n_rows) f64 | None,
+    features (n_rows, 2 n_filt) f32 | None)`` as torch CUDA tensors.
+    """
+    import torch
+    lib = _capi.load()
+    dev = torch.device("cuda", device)
+    fl = torch.as_tensor(flux, dtype=torch.float64).to(dev).contiguous()
+    n_gal, n_filt = fl.shape
+    sg = torch.as_tensor(np.asarray(sigma, dtype=np.float64)).to(dev).contiguous()
+    n_rows = n_gal * int(n_scatter)
+    nz = None
+    if normals is not None:
+        nz = torch.as_tensor(normals, dtype=torch.float64).to(dev).contiguous()
+        assert tuple(nz.shape) == (n_filt, n_rows), "normals must be (n_filt, n_gal*n_scatter)"
+    of = torch.empty((n_filt, n_rows), dtype=torch.float64, device=dev) if want_flux else None
+    osig = torch.empty((n_filt, n_rows), dtype=torch.float64, device=dev) if want_flux else None
+    feat = torch.empty((n_rows, 2 * n_filt), dtype=torch.float32, device=dev) if want_features else None
+    dp = lambda x: None if x is None else x.data_ptr()  # noqa: E731
+    st = torch.cuda.current_stream(device).cuda_stream
+    rc = lib.sb2_depth_noise_features(fl.data_ptr(), n_gal, n_filt, int(n_scatter), sg.data_ptr(),
+                                      float(min_flux_pc_error), dp(nz), int(seed), int(epoch),
+                                      float(norm_mag_limit), dp(of), dp(osig), dp(feat), st)
+    _capi.check(rc, "sb2_depth_noise_features")
+    return of, osig, feat

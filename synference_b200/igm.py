@@ -113,7 +113,7 @@ INOUE14_DLA = np.array([
 Z1_LAF, Z2_LAF, Z1_DLA = 1.2, 4.7, 2.0
 
 # exponents of the per-bin power table, in the order the kernel indexes them
-BIN_POWERS = (1.2, 2.1, 3.7, 5.5, -0.3, 2.0, 3.0)
+BIN_POWERS = (1.2, 2.1, 3.7, 5.5, -0.3, 2.0, 3.0, 1.0)
 # exponents of the per-galaxy (1+z) power vector
 Z_POWERS = (1.2, 2.1, 3.7, 5.5, -0.3, 2.0, 3.0, -0.9, 1.6, 3.4, 2.3, 3.3)
 
@@ -185,7 +185,7 @@ def device_tables(lam, laf=INOUE14_LAF, dla=INOUE14_DLA):
 
     Returns a dict of float64/int32 arrays:
       n_blue            number of bins with lam_i < lam_Lyalpha (others have T=1)
-      bin_pow[7, n_blue] (lam_i/LAM_L)**p for p in BIN_POWERS
+      bin_pow[8, n_blue] (lam_i/LAM_L)**p for p in BIN_POWERS
       nline[n_blue]     J_i = #{j : lam_j > lam_i}
       lc_on[n_blue]     1 where lam_i < LAM_L (Lyman continuum applies)
       thr[3, 64]        regime thresholds c*lam_j/LAM_L for c in (2.2, 5.7, 3.0), padded with -1
@@ -198,7 +198,7 @@ def device_tables(lam, laf=INOUE14_LAF, dla=INOUE14_DLA):
     nl = len(lj)
     n_blue = int(np.searchsorted(lam, lj[0], side="left"))  # lam_i < 1215.67
     lb = lam[:n_blue]
-    bin_pow = np.stack([(lb / LAM_L) ** p for p in BIN_POWERS]) if n_blue else np.zeros((7, 0))
+    bin_pow = np.stack([(lb / LAM_L) ** p for p in BIN_POWERS]) if n_blue else np.zeros((len(BIN_POWERS), 0))
     nline = (lj[None, :] > lb[:, None]).sum(1).astype(np.int32)
     lc_on = (lb < LAM_L).astype(np.int32)
     thr = -np.ones((3, 64))
