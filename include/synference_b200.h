@@ -133,6 +133,12 @@ int sb2_build_weights(sb2_model* m, const sb2_params* params, double* w_out, voi
 int sb2_synth_photometry(sb2_model* m, const sb2_params* params, float* flux_base, double* flux_scaled,
                          float* spec_out, void* stream);
 
+/* Device time of the stages of the most recent sb2_synth_photometry call on this model, from CUDA
+ * events recorded on its stream: out3 = {sort [ms], weight/IGM kernel [ms], contraction kernel [ms]}.
+ * Blocks until that call has finished.  (Measurement hook; no reference counterpart beyond the
+ * wall-clock `pipeline_time` attribute, library.py:2617-2622.)                                   */
+int sb2_last_stage_ms(sb2_model* m, float* out3);
+
 /* Same, with HOST buffers: copies parameters in, runs, copies results out (synchronous). */
 int sb2_synth_photometry_host(sb2_model* m, const sb2_params* params, float* flux_base, double* flux_scaled,
                               float* spec_out);

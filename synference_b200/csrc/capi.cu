@@ -111,6 +111,8 @@ struct sb2_model {
   double* stage_flux64 = nullptr;
   CUtensorMap tm_w_hi, tm_w_lo, tm_g_hi, tm_g_lo;
   size_t smem_bytes = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start | sorted | weights built | synthesised
+  bool ev_valid = false;
 };
 
 extern "C" {
@@ -133,6 +135,8 @@ int sb2_model_destroy(sb2_model* m) {
                   m->stage_flux, m->stage_flux64};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (cudaEvent_t e : m->ev)
+    if (e) cudaEventDestroy(e);
   delete m;
   return SB2_OK;
 }
@@ -236,6 +240,12 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
     return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to the operand pipeline (" +
                                      std::to_string(m->smem_bytes) + " B needed)");
   }
+  for (int i = 0; i < 4; ++i) {
+    if (cudaEventCreate(&m->ev[i]) != cudaSuccess) {
+      sb2_model_destroy(m);
+      return fail(SB2_ERR_CUDA, "cudaEventCreate failed");
+    }
+  }
   *out = m;
   return SB2_OK;
 }
@@ -308,6 +318,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, cuda
   const long long n = p->n;
   const long long n_pad = (n + 127) / 128 * 128;
   const int* perm = nullptr;
+  cudaEventRecord(m->ev[0], st);
   if (sorted) {
     const int tb = 256;
     sort_keys_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(p->redshift, m->keys, m->idx, n);
@@ -316,6 +327,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, cuda
     CU_TRY(cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)n, 0, 32, st));
     perm = m->perm;
   }
+  cudaEventRecord(m->ev[1], st);
   sb2::PrepModel M = prep_model(m);
   sb2::PrepParams P = prep_params(p);
   sb2::PrepOut O{};
@@ -326,6 +338,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, cuda
   const unsigned blocks = (unsigned)((n_pad + sb2::kPrepWarps - 1) / sb2::kPrepWarps);
   sb2::prep_kernel<<<blocks, sb2::kPrepWarps * 32, sh, st>>>(M, P, O, perm, n_pad);
   CU_TRY(cudaGetLastError());
+  cudaEventRecord(m->ev[2], st);
   return SB2_OK;
 }
 
@@ -364,7 +377,18 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
     a.filt_su[f] = m->h_su[f]; a.filt_sdv[f] = m->h_sdv[f];
   }
   const int grid = a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm;
-  return launch_synth(m, a, grid, st);
+  rc = launch_synth(m, a, grid, st);
+  cudaEventRecord(m->ev[3], st);
+  m->ev_valid = (rc == SB2_OK);
+  return rc;
+}
+
+int sb2_last_stage_ms(sb2_model* m, float* out3) {
+  if (!m || !out3) return fail(SB2_ERR_INVALID, "null argument");
+  if (!m->ev_valid) return fail(SB2_ERR_INVALID, "no completed sb2_synth_photometry call to time");
+  CU_TRY(cudaEventSynchronize(m->ev[3]));
+  for (int i = 0; i < 3; ++i) CU_TRY(cudaEventElapsedTime(&out3[i], m->ev[i], m->ev[i + 1]));
+  return SB2_OK;
 }
 
 int sb2_synth_photometry_host(sb2_model* m, const sb2_params* p, float* flux_base, double* flux_scaled,
