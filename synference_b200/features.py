@@ -1,0 +1,155 @@
+"""Training-row builder: depth scatter + flux -> magnitude features on the GPU.
+
+Mirrors the part of ``SBI_Fitter.create_feature_array_from_raw_photometry``
+(``src/synference/sbi_runner.py:1429-2219``) that sits on the hot path: ``_apply_depths``
+(:580-691), the AB conversion and error propagation (:1698-1716), the ``norm_mag_limit`` clip
+(:1927-1932), optional normalisation by one band (:1781-1830), error columns, removal of
+non-finite rows (:2083-2087), float32 ``(N_rows, N_feat)`` output (:2150) and the matching
+``np.repeat`` of the parameter rows (``update_parameter_array``, :476-578).
+
+The reference scatters once with ``N_scatters`` static replicas; :class:`ResampledFeatures` adds the
+per-epoch resampling of BASELINE config 4 behind the same call (Philox counter = epoch), without the
+table leaving HBM.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+from .engine import depth_noise_features
+from .units import Unit, has_units, strip_units
+
+_TO_NJY = {"nJy": 1.0, "uJy": 1e3, "mJy": 1e6, "Jy": 1e9}
+
+
+def depths_to_sigma_njy(depths, depth_sigma=5.0, n_filt=None):
+    """sigma [nJy] per filter from 5-sigma depths given in AB magnitudes (bare numbers) or flux units."""
+    if has_units(depths):
+        d = np.asarray(strip_units(depths, "nJy"), dtype=np.float64)
+    else:
+        d = 10 ** ((np.asarray(depths, dtype=np.float64) - 23.9) / -2.5) * 1e3  # AB -> uJy -> nJy
+    d = np.atleast_1d(d)
+    if n_filt is not None and d.size == 1:
+        d = np.full(n_filt, d[0])
+    return d / depth_sigma
+
+
+def create_feature_array_from_raw_photometry(
+        phot_grid, raw_observation_names: List[str], raw_observation_units: str = "nJy",
+        normalize_method: Optional[str] = None, normed_flux_units: str = "AB", scatter_fluxes=False,
+        depths=None, depth_sigma: float = 5.0, include_errors_in_feature_array: bool = False,
+        min_flux_pc_error: float = 0.0, norm_mag_limit: float = 50.0, remove_nan_inf: bool = True,
+        photometry_to_remove: Optional[list] = None, drop_dropouts: bool = False,
+        drop_dropout_fraction: float = 1.0, parameter_array=None, normals=None, seed: int = 0,
+        epoch: int = 0, device: int = 0, return_torch: bool = False):
+    """``(N_filters, N_gal)`` library photometry -> ``(feature_array (N_rows, N_feat) float32,
+    feature_names, parameter_array (N_rows, N_par) | None)``.
+
+    ``scatter_fluxes`` is the number of noisy replicas per galaxy (0/False: no scatter, one row per
+    galaxy).  With ``normals`` (``(N_filters, N_rows)`` float64) the scatter is bit-exact with numpy's
+    ``flux + np.random.normal(0, sigma)`` for the same draws; otherwise Philox4x32-10(seed, epoch).
+    """
+    import torch
+    if normed_flux_units != "AB":
+        raise NotImplementedError("the device feature builder implements normed_flux_units='AB' "
+                                  "(asinh / linear features: SURVEY 8f-3)")
+    names = list(raw_observation_names)
+    dev = torch.device("cuda", device)
+    grid = phot_grid if isinstance(phot_grid, torch.Tensor) else torch.as_tensor(np.asarray(phot_grid, dtype=np.float64))
+    grid = grid.to(dev, dtype=torch.float64)
+    assert grid.shape[0] == len(names), "phot_grid must be (N_filters, N_gal)"
+    if photometry_to_remove:
+        keep = [i for i, n in enumerate(names) if n not in set(photometry_to_remove)]
+        if len(keep) == len(names):
+            raise ValueError(f"No matching photometry filters found in the raw photometry names: {photometry_to_remove}")
+        if not keep:
+            raise ValueError("No photometry filters left after removing the specified ones.")
+        grid, names = grid[keep], [names[i] for i in keep]
+    grid = grid * _TO_NJY[str(raw_observation_units)]
+    n_filt, n_gal = grid.shape
+    n_sc = int(scatter_fluxes) if scatter_fluxes else 1
+    if scatter_fluxes:
+        assert depths is not None, "If scattering fluxes, depths or empirical noise models must be provided."
+        if isinstance(depths, dict):  # keyed by filter name (sbi_runner.py:1639-1645)
+            vals = [depths[n] for n in names]
+            if has_units(vals[0]):
+                sigma = np.array([float(strip_units(v, "nJy")) for v in vals]) / depth_sigma
+            else:
+                sigma = depths_to_sigma_njy(np.array(vals, dtype=float), depth_sigma)
+        else:
+            sigma = depths_to_sigma_njy(depths, depth_sigma, n_filt)
+        if sigma.shape[0] != n_filt:
+            raise ValueError(f"Mismatch in dimensions: photometry_array has {n_filt} rows but depths has "
+                             f"{sigma.shape[0]} elements")
+    else:
+        sigma = np.zeros(n_filt)
+        normals = torch.zeros((n_filt, n_gal), dtype=torch.float64, device=dev)
+    flux_gf = grid.t().contiguous()                                   # (n_gal, n_filt), kernel layout
+    _, _, feat = depth_noise_features(flux_gf, sigma, n_scatter=n_sc, normals=normals, seed=seed, epoch=epoch,
+                                      norm_mag_limit=norm_mag_limit, min_flux_pc_error=min_flux_pc_error,
+                                      want_flux=False, want_features=True, device=device)
+    mags, errs = feat[:, :n_filt], feat[:, n_filt:]
+    feature_names = list(names)
+    if normalize_method is not None:
+        if normalize_method not in names:
+            raise NotImplementedError("normalisation by a parameter is not part of the device path; "
+                                      "use a filter name")
+        j = names.index(normalize_method)
+        norm = mags[:, j:j + 1]
+        others = [i for i in range(n_filt) if i != j]
+        mags = torch.clamp(mags[:, others] - norm, max=norm_mag_limit)
+        errs = errs[:, others]
+        feature_names = [names[i] for i in others]
+        cols = [mags] + ([errs] if include_errors_in_feature_array and scatter_fluxes else []) + [norm]
+        tail = [f"norm_{normalize_method}"]
+    else:
+        cols = [mags] + ([errs] if include_errors_in_feature_array and scatter_fluxes else [])
+        tail = []
+    if include_errors_in_feature_array and scatter_fluxes:
+        feature_names = feature_names + [f"unc_{n}" for n in feature_names]
+    feature_names = feature_names + tail
+    out = torch.cat(cols, 1) if len(cols) > 1 else cols[0]
+    keep_rows = torch.ones(out.shape[0], dtype=torch.bool, device=dev)
+    if remove_nan_inf:
+        keep_rows &= torch.isfinite(out).all(1)
+    if drop_dropouts:
+        nb = mags.shape[1]
+        keep_rows &= ~((out[:, :nb].abs() >= norm_mag_limit).sum(1) >= nb * drop_dropout_fraction)
+    params = None
+    if parameter_array is not None:
+        params = torch.as_tensor(np.asarray(parameter_array, dtype=np.float32)).to(dev)
+        params = params.repeat_interleave(n_sc, dim=0)                # update_parameter_array (np.repeat)
+    if not bool(keep_rows.all()):
+        out = out[keep_rows]
+        params = params[keep_rows] if params is not None else None
+    if out.shape[0] == 0:
+        raise ValueError("All rows in the feature array were deleted. Please check the input parameters.")
+    out = out.contiguous().to(torch.float32)
+    if return_torch:
+        return out, feature_names, params
+    return out.cpu().numpy(), feature_names, (None if params is None else params.cpu().numpy())
+
+
+class ResampledFeatures:
+    """Library photometry resident in HBM; a fresh noise realisation of every row per epoch.
+
+    ``epoch(e)`` returns ``(features (N_gal*n_scatter, N_feat) float32 CUDA tensor, params)`` for epoch
+    ``e``; the Philox counter is (row, filter) and the key (seed, epoch), so epochs are reproducible and
+    independent of the world size.
+    """
+
+    def __init__(self, phot_grid, names, depths, parameter_array=None, n_scatter=1, seed=42, device=0, **kw):
+        import torch
+        self.dev = device
+        self.grid = torch.as_tensor(np.asarray(phot_grid, dtype=np.float64)).to(torch.device("cuda", device))
+        self.names, self.depths, self.n_scatter, self.seed, self.kw = list(names), depths, n_scatter, seed, kw
+        self.params = parameter_array
+
+    def epoch(self, e: int):
+        f, names, p = create_feature_array_from_raw_photometry(
+            self.grid, self.names, scatter_fluxes=self.n_scatter, depths=self.depths, seed=self.seed, epoch=e,
+            parameter_array=self.params, device=self.dev, return_torch=True, **self.kw)
+        self.feature_names = names
+        return f, p

@@ -1,0 +1,952 @@
+"""Library builders and on-the-fly simulator with the reference's public names and file contract.
+
+Mirrors (paths relative to the reference repository, ``src/synference/library.py``):
+  ``create_galaxy``                       :1340-1424
+  ``GalaxyBasis``                         :1497-3183  (``process_galaxies`` :2447, ``create_mock_library`` :3022)
+  ``CombinedBasis``                       :3185-4919  (``process_bases`` :3291, ``load_bases`` :3385,
+                                          ``create_full_library`` :4435, ``save_library`` :4031,
+                                          ``_validate_library`` :3976, ``create_spectral_grid`` :4887)
+  ``GalaxySimulator``                     :4922-6001  (``simulate`` :5553, ``_scatter`` :5906, ``_normalize`` :5866)
+
+What is different by design: no per-galaxy Python objects and no Synthesizer ``Pipeline``.  A basis
+is lowered once to a struct-of-arrays :class:`GalaxyParams`; every batch goes through one call of the
+CUDA path (:class:`synference_b200.engine.SynthEngine`); the per-galaxy Python loops of
+``create_full_library`` are array expressions.  Galaxies are sharded contiguously over ranks with the
+reference's rule (``library.py:3127-3138``).
+"""
+
+from __future__ import annotations
+
+import copy
+import os
+from datetime import datetime
+from typing import Dict, List, Optional, Union
+
+import numpy as np
+
+from . import distributed as _dist
+from .cosmology import Planck18
+from .engine import GalaxyParams, SynthEngine
+from .igm import Inoue14
+from .parametric import (EmissionModel, Grid, Instrument, SFHArray, ZDistArray, _SFHCommon, _ZDistCommon,
+                         pack_sfh, pack_zdist)
+from .sampling import draw_from_hypercube, generate_sfh_basis  # noqa: F401  (re-exported)
+from .units import Quantity, has_units, strip_units
+from .utils import logger, read_container, write_container
+
+library_folder = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libraries")
+
+UNIT_DICT = {
+    "log10metallicity": "log10(Zmet)", "metallicity": "Zmet", "av": "mag", "tau_v": "mag",
+    "tau_v_ism": "mag", "tau_v_birth": "mag", "weight_fraction": "dimensionless",
+    "log_sfr": "log10(Msun/yr)", "sfr": "Msun/yr", "log_stellar_mass": "log10(Msun)",
+    "log_surviving_mass": "log10(Msun)", "stellar_mass": "Msun",
+}
+
+# emitter parameters that change the spectrum and are understood by the CUDA path
+_SPECTRAL_EMITTER_PARAMS = ("tau_v",)
+# emitter parameters of the reference scripts that would change the spectrum but are not implemented
+_UNSUPPORTED_EMITTER_PARAMS = ("slope", "fesc", "fesc_lya", "fesc_ly_alpha", "dust_bump_amplitude",
+                               "tau_v_ism", "tau_v_birth")
+
+
+def create_galaxy(sfh, redshift, metal_dist, grid, log_stellar_masses=9, **galaxy_kwargs):
+    """A single-galaxy description (``library.py:1340-1424``); a plain record, not a Synthesizer object."""
+    assert not has_units(log_stellar_masses), \
+        "log_stellar_masses must be a float or list of floats, not a unyt array"
+    return {"sfh": sfh, "redshift": float(redshift), "metal_dist": metal_dist,
+            "log_stellar_mass": log_stellar_masses, "params": dict(galaxy_kwargs)}
+
+
+def _rank_size(multi_node):
+    return _dist.rank_world() if multi_node else (0, 1)
+
+
+class GalaxyBasis:
+    """A population of model galaxies sharing one grid / emission model / instrument."""
+
+    def __init__(self, model_name: str, redshifts, grid: Grid, emission_model: EmissionModel, sfhs,
+                 metal_dists, log_stellar_masses=None, galaxy_params: dict = None,
+                 alt_parametrizations: Dict[str, tuple] = None, cosmo=Planck18, instrument: Instrument = None,
+                 redshift_dependent_sfh: bool = False, params_to_ignore: List[str] = None,
+                 build_library: bool = False) -> None:
+        galaxy_params = {} if galaxy_params is None else galaxy_params
+        self.model_name = model_name
+        self.grid = grid
+        self.emission_model = emission_model
+        self.galaxy_params = galaxy_params
+        self.alt_parametrizations = alt_parametrizations or {}
+        self.cosmo = cosmo
+        self.instrument = instrument
+        self.redshift_dependent_sfh = redshift_dependent_sfh
+        self.log_stellar_masses = log_stellar_masses
+        self.params_to_ignore = params_to_ignore or []
+        self.build_library = build_library
+        self.galaxies = []
+        self.per_particle = False
+        if isinstance(sfhs, _SFHCommon):
+            sfhs = [sfhs]
+        if isinstance(metal_dists, _ZDistCommon):
+            metal_dists = [metal_dists]
+        if isinstance(redshifts, (float, int)) and not build_library:
+            redshifts = np.full(len(sfhs), redshifts)
+        self.sfhs, self.metal_dists = sfhs, metal_dists
+        self.redshifts = np.asarray(strip_units(redshifts), dtype=np.float64)
+        for key in list(galaxy_params.keys()):
+            value = galaxy_params[key]
+            if isinstance(value, dict):
+                if key in ("bh", "gas"):
+                    raise NotImplementedError("black-hole / gas emitters are outside the stellar hot path")
+                self.galaxy_params[key] = self.process_priors(value)
+        for key in galaxy_params:
+            if key in _UNSUPPORTED_EMITTER_PARAMS:
+                raise NotImplementedError(
+                    f"per-galaxy emitter parameter '{key}' is not implemented in the CUDA path yet "
+                    "(SURVEY 8f-1); only 'tau_v' varies per galaxy")
+        if not build_library:
+            logger.info("Generating library directly from provided parameter samples.")
+        elif redshift_dependent_sfh:
+            for sfh in self.sfhs:
+                if not hasattr(sfh, "redshift"):
+                    raise ValueError("SFH must have a redshift attr if redshift_dependent_sfh==True")
+                if sfh.redshift not in self.redshifts:
+                    raise ValueError(f"SFH redshift {sfh.redshift} not in redshifts array")
+        self.params: Optional[GalaxyParams] = None
+        self.all_parameters: Dict[str, np.ndarray] = {}
+        self.varying_param_names: List[str] = []
+        self.fixed_param_names: List[str] = []
+        self.fixed_param_values: list = []
+        self.fixed_param_units: List[str] = []
+        self._engines: Dict[str, SynthEngine] = {}
+
+    # ---------------------------------------------------------------------------------------
+    def process_priors(self, prior_dict):
+        """Draw a per-galaxy parameter from a scipy.stats prior description (``library.py:1653-1692``)."""
+        assert isinstance(prior_dict, dict) and "prior" in prior_dict and "size" in prior_dict
+        kw = {k: v for k, v in prior_dict.items() if k not in ("prior", "size", "units", "name")}
+        values = prior_dict["prior"].rvs(size=int(prior_dict["size"]), **kw)
+        if prior_dict.get("units") is not None:
+            values = Quantity(values, str(prior_dict["units"]))
+        return values
+
+    @staticmethod
+    def _sfh_param_table(sfhs, n):
+        """``{name: (N,) array}`` of the SFH constructor parameters (what ``sfh.parameters`` holds)."""
+        sfh_type, rows = pack_sfh(sfhs)
+        if rows.shape[0] == 1 and n > 1:
+            rows = np.repeat(rows, n, axis=0)
+        cls = sfhs.sfh_type if isinstance(sfhs, SFHArray) else type(list(sfhs)[0])
+        out = {"max_age": rows[:, 1]}
+        if np.any(rows[:, 0] != 0):
+            out["min_age"] = rows[:, 0]
+        for j, name in enumerate(getattr(cls, "param_names", ())):
+            out[name] = rows[:, 2 + j]
+        if cls.__name__ == "_Continuity":
+            nb = int(rows[0, 2])
+            for j in range(nb - 1):
+                out[f"logsfr_ratio_{j}"] = rows[:, 3 + nb + 1 + j]
+        return out
+
+    def _finalise_parameters(self, table: Dict[str, np.ndarray]):
+        """Split parameters into varying / fixed exactly like ``library.py:2382-2441``."""
+        for key, (new_key, func) in self.alt_parametrizations.items():
+            if key in table:
+                if isinstance(new_key, str):
+                    table[new_key] = np.asarray(func(table))
+                else:
+                    for k in new_key:
+                        table[k] = np.asarray(func(k, table))
+                table.pop(key)
+        self.all_parameters = table
+        self.varying_param_names, self.fixed_param_names = [], []
+        self.fixed_param_values, self.fixed_param_units = [], []
+        for key, value in table.items():
+            if key in self.params_to_ignore:
+                continue
+            v = np.asarray(strip_units(value), dtype=float)
+            if np.unique(v).size == 1:
+                self.fixed_param_names.append(key)
+                self.fixed_param_values.append(float(v.flat[0]))
+                self.fixed_param_units.append(str(value.units) if has_units(value) else "")
+            else:
+                self.varying_param_names.append(key)
+
+    def _lower(self, redshifts, sfhs, metal_dists, galaxy_params: Dict[str, np.ndarray], log_mass=None):
+        n = len(redshifts)
+        tau_v = galaxy_params.get("tau_v")
+        self.params = GalaxyParams.from_objects(redshifts, sfhs, metal_dists, log_mass=log_mass, tau_v=tau_v)
+        table = {k: np.broadcast_to(np.asarray(strip_units(v), dtype=float), (n,)).copy()
+                 for k, v in galaxy_params.items()}
+        table["redshift"] = np.asarray(redshifts, dtype=float)
+        table.update(self._sfh_param_table(sfhs, n))
+        zt, zv, zs = pack_zdist(metal_dists)
+        zv = np.broadcast_to(zv, (n,)).copy()
+        if zt == 0:
+            table["metallicity"] = zv
+        elif zt == 1:
+            table["log10metallicity"] = zv
+        else:
+            table["mean"], table["sigma"] = zv, np.broadcast_to(zs, (n,)).copy()
+        self._finalise_parameters(table)
+        self.galaxies = _LazyGalaxyList(self)
+        return self.galaxies
+
+    def _create_matched_galaxies(self, log_base_masses=9, galaxies_mask=None, n_proc: int = 1):
+        """One galaxy per (SFH, redshift, metallicity distribution) triple (``library.py:2263-2445``)."""
+        n = len(self.sfhs)
+        if len(self.metal_dists) == 1 and n > 1:
+            md = self.metal_dists if isinstance(self.metal_dists, ZDistArray) else \
+                [self.metal_dists[0]] * n
+            self.metal_dists = md if not isinstance(md, ZDistArray) else ZDistArray(
+                md.type_id, np.repeat(md.value, n), np.repeat(md.sigma, n))
+        assert n == len(self.redshifts), \
+            f"If iterate_redshifts is False, sfhs and redshifts must be the same length, got {n} and {len(self.redshifts)}"
+        assert n == len(self.metal_dists), \
+            f"sfhs and metal_dists must be the same length, got {n} and {len(self.metal_dists)}"
+        gp = {}
+        for k, v in self.galaxy_params.items():
+            if isinstance(v, (list, np.ndarray)) or has_units(v) and np.ndim(v) > 0:
+                assert len(v) == n, f"All varying parameters must be the same length, got {n} and {len(v)}"
+            gp[k] = v
+        sel = slice(None) if galaxies_mask is None else np.asarray(galaxies_mask, dtype=bool)
+        if galaxies_mask is not None:
+            assert len(galaxies_mask) == n, "galaxies_mask must be the same length as sfhs"
+            gp = {k: (np.asarray(strip_units(v))[sel] if np.ndim(v) > 0 else v) for k, v in gp.items()}
+        sfhs = self.sfhs[sel] if isinstance(self.sfhs, (SFHArray, np.ndarray)) else \
+            [s for s, m in zip(self.sfhs, np.ones(n, bool) if galaxies_mask is None else sel) if m]
+        zds = self.metal_dists[sel] if isinstance(self.metal_dists, (ZDistArray, np.ndarray)) else \
+            [s for s, m in zip(self.metal_dists, np.ones(n, bool) if galaxies_mask is None else sel) if m]
+        return self._lower(self.redshifts[sel], sfhs, zds, gp)
+
+    def _create_galaxies(self, log_base_masses=9):
+        """Every combination of redshift x SFH x metallicity distribution x varying galaxy parameters,
+        in the loop order of ``library.py:1694-1873``."""
+        if not self.build_library:
+            raise ValueError("You probably meant to call_create_matched_galaxies instead.")
+        varying = {k: np.asarray(strip_units(v), dtype=float) for k, v in self.galaxy_params.items()
+                   if isinstance(v, (list, np.ndarray))}
+        fixed = {k: v for k, v in self.galaxy_params.items() if k not in varying}
+        if varying:
+            combos = np.array(np.meshgrid(*varying.values())).T.reshape(-1, len(varying))
+        else:
+            combos = np.zeros((1, 0))
+        sfh_list = list(self.sfhs)
+        zd_list = list(self.metal_dists)
+        zs, sf, zd, cm = [], [], [], []
+        for z in self.redshifts:
+            for s in (sfh_list if not self.redshift_dependent_sfh else
+                      [x for x in sfh_list if x.redshift == z]):
+                for d in zd_list:
+                    for row in combos:
+                        zs.append(z); sf.append(s); zd.append(d); cm.append(row)
+        cm = np.array(cm).reshape(len(zs), len(varying))
+        gp = {k: cm[:, j] for j, k in enumerate(varying)}
+        gp.update(fixed)
+        out = self._lower(np.array(zs), sf, zd, gp)
+        # varying-parameter combinations must be unique (library.py:1842-1858)
+        if self.varying_param_names:
+            mat = np.stack([np.asarray(strip_units(self.all_parameters[k]), float) for k in self.varying_param_names], 1)
+            if np.unique(mat, axis=0).shape[0] != mat.shape[0]:
+                raise ValueError("Varying parameters are not unique across galaxies. Check your input parameters.")
+        return out
+
+    def create_galaxies_optimized(self, galaxies_mask=None, varying_param_names=None, log_base_masses=9,
+                                  fixed_params=None, n_proc=1):
+        return self._create_matched_galaxies(log_base_masses, galaxies_mask, n_proc)
+
+    # ---------------------------------------------------------------------------------------
+    def _engine(self, emission_key, igm=Inoue14, max_batch=40_000) -> SynthEngine:
+        tag = f"{emission_key}|{bool(igm)}|{max_batch}"
+        if tag not in self._engines:
+            for e in self._engines.values():
+                e.close()
+            self._engines.clear()
+            self._engines[tag] = SynthEngine(self.grid, self.emission_model, emission_key,
+                                             self.instrument.filters, cosmo=self.cosmo, igm=bool(igm),
+                                             max_batch=max_batch, device=_dist.local_device())
+        return self._engines[tag]
+
+    def process_galaxies(self, galaxies=None, out_name: str = "auto", out_dir: str = "internal", n_proc: int = 4,
+                         verbose: int = 1, save: bool = True, emission_model_keys=None,
+                         batch_galaxies: bool = True, batch_size: int = 40_000, overwrite: bool = False,
+                         multi_node: bool = False, spectra_to_save: list = None, em_lines_to_save: list = None,
+                         igm=Inoue14, **extra_analysis_functions):
+        """Synthesise the basis in batches and write the pipeline files (``library.py:2447-2694``).
+
+        Returns the dict ``{"photometry": {key: (N, n_filt)}, "spectra": {...}}`` of what was computed.
+        Each batch is one pass of the CUDA path at the base mass; per-batch files are the resume unit:
+        an existing ``<out_name>_<i>.hdf5`` is skipped unless ``overwrite``.
+        """
+        if extra_analysis_functions:
+            raise NotImplementedError(
+                "supplementary analysis callbacks operate on Synthesizer objects and are outside the hot "
+                f"path (SURVEY 2 row 12): {list(extra_analysis_functions)}")
+        if em_lines_to_save:
+            raise NotImplementedError("emission-line outputs are outside the hot path")
+        if self.params is None:
+            raise ValueError("create the galaxies first (_create_matched_galaxies / _create_galaxies)")
+        self.emission_model.set_per_particle(self.per_particle)
+        keys = list(emission_model_keys) if emission_model_keys is not None else ["total"]
+        if emission_model_keys is not None:
+            self.emission_model.save_spectra(*keys, *(spectra_to_save or []))
+        n_gal = len(self.params)
+        if not batch_galaxies:
+            batch_size = n_gal
+        n_batches = int(np.ceil(n_gal / batch_size))
+        if out_dir == "internal":
+            out_dir = library_folder
+        if out_name == "auto":
+            out_name = self.model_name
+        if not out_name.endswith(".hdf5"):
+            out_name += ".hdf5"
+        fullpath = os.path.join(out_dir, out_name)
+        if save:
+            os.makedirs(out_dir, exist_ok=True)
+        spectra_keys = set(spectra_to_save or [])
+        results = {"photometry": {k: [] for k in keys}, "spectra": {k: [] for k in keys if k in spectra_keys}}
+        rank, size = _rank_size(multi_node)
+        for batch_i in range(n_batches):
+            sl = slice(batch_i * batch_size, min(n_gal, (batch_i + 1) * batch_size))
+            final = fullpath if n_batches == 1 else fullpath.replace(".hdf5", f"_{batch_i + 1}.hdf5")
+            if multi_node and size > 1:
+                final = final.replace(".hdf5", f"_rank{rank}.hdf5")
+            if save and os.path.exists(final) and not overwrite:
+                logger.warning(f"Skipping batch {batch_i + 1} as {final} already exists.")
+                continue
+            start = datetime.now()
+            p = self.params.slice(sl)
+            # the pipeline always runs at the base mass (library.py:3217): no mass scaling here
+            p.log_mass = None
+            datasets = {}
+            for key in keys:
+                eng = self._engine(key, igm=igm, max_batch=max(batch_size, 1))
+                flux = eng.photometry(p, scaled=False)
+                results["photometry"][key].append(flux)
+                label = self.instrument.label
+                for j, code in enumerate(eng.filter_codes):
+                    datasets[f"Galaxies/Stars/Photometry/Fluxes/{key}/{label}/{code}"] = flux[:, j].astype(np.float64)
+                if key in spectra_keys:
+                    spec = eng.spectra(p)
+                    results["spectra"][key].append(spec)
+                    datasets[f"Galaxies/Stars/Spectra/SpectralFluxDensities/{key}"] = spec
+            elapsed = datetime.now() - start
+            logger.info(f"Pipeline (CUDA) took {elapsed} for {sl.stop - sl.start} galaxies.")
+            if save:
+                for name, arr in self.all_parameters.items():
+                    datasets[f"Galaxies/{name}"] = np.asarray(strip_units(arr), dtype=float)[sl]
+                datasets["Galaxies/mass"] = np.full(sl.stop - sl.start, 10.0 ** 9)
+                datasets["Wavelengths"] = np.asarray(self.grid.lam)
+                attrs = {"varying_param_names": list(self.varying_param_names),
+                         "fixed_param_names": list(self.fixed_param_names),
+                         "fixed_param_values": list(self.fixed_param_values),
+                         "fixed_param_units": list(self.fixed_param_units),
+                         "model_name": self.model_name, "grid_name": self.grid.grid_name,
+                         "grid_dir": str(self.grid.grid_dir), "date_created": str(datetime.now()),
+                         "pipeline_time": str(elapsed), "WavelengthUnits": "Angstrom",
+                         "FilterCodes": list(self.instrument.filters.filter_codes),
+                         "InstrumentLabel": self.instrument.label, "batch": batch_i + 1, "n_batches": n_batches,
+                         "rank": rank, "world_size": size, "galaxy_start": sl.start, "galaxy_stop": sl.stop}
+                write_container(final, datasets, attrs, compress=False)
+                logger.info(f"Written pipeline to disk at {final}.")
+        return {k: {kk: (np.concatenate(vv) if vv else None) for kk, vv in v.items()} for k, v in results.items()}
+
+    def process_base(self, out_name, log_stellar_masses=9, emission_model_key="total", out_dir=library_folder,
+                     n_proc=6, overwrite=False, verbose=False, batch_size=40_000, multi_node=False, **kw):
+        """Create the galaxies of this basis and run them (``library.py:2939-3020``)."""
+        if self.build_library:
+            self._create_galaxies(log_stellar_masses)
+        else:
+            self._create_matched_galaxies(log_stellar_masses)
+        return self.process_galaxies(out_name=out_name, out_dir=out_dir, overwrite=overwrite,
+                                     emission_model_keys=[emission_model_key], batch_size=batch_size,
+                                     multi_node=multi_node, **kw)
+
+    def create_mock_library(self, out_name, log_stellar_masses=None, emission_model_key: str = "total",
+                            out_dir: str = library_folder, n_proc: int = 6, overwrite=False, verbose=False,
+                            batch_size: int = 40_000, parameter_transforms_to_save=None, cat_type="photometry",
+                            compile_grid: bool = True, multi_node: bool = False, spectra_to_save=None,
+                            em_lines_to_save=None, **extra_analysis_functions):
+        """Convenience wrapper: basis -> CombinedBasis -> process -> compile -> store model
+        (``library.py:3022-3183``)."""
+        if log_stellar_masses is None:
+            assert self.log_stellar_masses is not None, \
+                "log_stellar_masses must be provided or set in the GalaxyBasis"
+            log_stellar_masses = self.log_stellar_masses
+        assert not has_units(log_stellar_masses), "log_stellar_masses must be not be a unyt_array"
+        combined = CombinedBasis(bases=[self], log_stellar_masses=log_stellar_masses, redshifts=self.redshifts,
+                                 base_emission_model_keys=[emission_model_key], combination_weights=None,
+                                 out_name=out_name, out_dir=out_dir, draw_parameter_combinations=False)
+        galaxy_mask = None
+        if multi_node:
+            rank, size = _dist.rank_world()
+            total = len(combined.redshifts)
+            start, end = _dist.shard_bounds(total, rank, size)
+            galaxy_mask = np.zeros(total, dtype=bool)
+            galaxy_mask[start:end] = True
+            logger.info(f"Node {rank} processing galaxies from {start} to {end}.")
+        if cat_type not in ("photometry", "spectra"):
+            raise ValueError(f"Unknown catalog type: {cat_type}. Use 'photometry' or 'spectra'.")
+        if cat_type == "spectra" and not spectra_to_save:
+            spectra_to_save = [emission_model_key]
+        combined.process_bases(n_proc=n_proc, overwrite=overwrite, verbose=verbose, batch_size=batch_size,
+                               multi_node=multi_node, galaxies_mask=galaxy_mask, spectra_to_save=spectra_to_save,
+                               em_lines_to_save=em_lines_to_save, **extra_analysis_functions)
+        if compile_grid:
+            logger.info("Compiling the library after processing bases.")
+            if cat_type == "photometry":
+                combined.create_library(overwrite=overwrite)
+            else:
+                combined.create_spectral_grid(overwrite=overwrite)
+            out_path = os.path.join(combined.out_dir, combined.out_name)
+            if not out_path.endswith(".hdf5"):
+                out_path += ".hdf5"
+            self._store_model(out_path, other_info={"emission_model_key": emission_model_key,
+                                                    "timestamp": datetime.now().isoformat(), "cat_type": cat_type},
+                              parameter_transforms_to_save=parameter_transforms_to_save)
+            logger.info("Processed the bases and saved the output.")
+            return combined
+
+    def _store_model(self, model_path, other_info=None, parameter_transforms_to_save=None):
+        """Record what is needed to rebuild the simulator next to the library (``library.py:2017-2132``)."""
+        em = self.emission_model
+        dust = em.dust_curve
+        info = {
+            "Model/grid_name": self.grid.grid_name, "Model/grid_dir": str(self.grid.grid_dir),
+            "Model/emission_model": type(em).__name__, "Model/fesc": float(em.fesc),
+            "Model/fesc_ly_alpha": float(em.fesc_ly_alpha),
+            "Model/dust_law": None if dust is None else dust.name,
+            "Model/dust_params": None if dust is None else dict(dust.params),
+            "Model/cosmology": repr(self.cosmo), "Model/instrument": self.instrument.label,
+            "Model/filter_codes": list(self.instrument.filters.filter_codes),
+            "Model/sfh_type": self.params and int(self.params.sfh_type),
+            "Model/zd_type": self.params and int(self.params.zd_type),
+            "Model/varying_param_names": list(self.varying_param_names),
+            "Model/fixed_param_names": list(self.fixed_param_names),
+            "Model/fixed_param_values": list(self.fixed_param_values),
+        }
+        info.update({f"Model/{k}": v for k, v in (other_info or {}).items()})
+        if parameter_transforms_to_save:
+            info["Model/parameter_transforms"] = sorted(str(k) for k in parameter_transforms_to_save)
+        if os.path.exists(model_path):
+            data, attrs = read_container(model_path)
+            attrs.update(info)
+            write_container(model_path, data, attrs)
+
+    def plot_galaxy(self, *a, **k):
+        raise NotImplementedError("plotting helpers are outside the hot path (SURVEY 2 row 13)")
+
+
+class _LazyGalaxyList:
+    """``basis.galaxies``: indexable records without materialising N Python objects."""
+
+    def __init__(self, basis: GalaxyBasis):
+        self._b = basis
+
+    def __len__(self):
+        return len(self._b.params)
+
+    def __getitem__(self, i):
+        b = self._b
+        return {"redshift": float(b.params.redshift[i]),
+                "all_params": {k: np.asarray(strip_units(v))[i] for k, v in b.all_parameters.items()}}
+
+
+class CombinedBasis:
+    """Turns processed bases into the photometry library the trainer reads."""
+
+    def __init__(self, bases: List[GalaxyBasis], log_stellar_masses, redshifts, base_emission_model_keys: List[str],
+                 combination_weights, out_name: str = "combined_basis", out_dir: str = library_folder,
+                 log_base_masses=9, draw_parameter_combinations: bool = False) -> None:
+        self.bases = bases
+        self.log_stellar_masses = log_stellar_masses
+        self.redshifts = redshifts
+        self.combination_weights = combination_weights
+        self.out_name, self.out_dir = out_name, out_dir
+        self.log_base_masses = log_base_masses
+        self.base_emission_model_keys = base_emission_model_keys
+        self.draw_parameter_combinations = draw_parameter_combinations
+        if isinstance(redshifts, (int, float)):
+            self.redshifts = np.full(len(self.log_stellar_masses), redshifts)
+        if self.combination_weights is None:
+            assert len(self.bases) == 1
+            self.combination_weights = np.ones((len(self.redshifts), 1))
+        self._mask = None
+        self._multi_node = False
+
+    def process_bases(self, n_proc=6, overwrite: Union[bool, List[bool]] = False, verbose=False,
+                      batch_size=40_000, multi_node=False, galaxies_mask=None, spectra_to_save=None,
+                      em_lines_to_save=None, **extra_analysis_functions):
+        """Create and run every basis (``library.py:3291-3383``)."""
+        if not isinstance(overwrite, (list, tuple, np.ndarray)):
+            overwrite = [overwrite] * len(self.bases)
+        self._mask, self._multi_node = galaxies_mask, multi_node
+        for i, base in enumerate(self.bases):
+            if base.build_library:
+                base._create_galaxies(self.log_base_masses)
+            else:
+                base._create_matched_galaxies(self.log_base_masses, galaxies_mask=galaxies_mask)
+            base.process_galaxies(out_name=base.model_name, out_dir=self.out_dir, n_proc=n_proc, verbose=verbose,
+                                  save=True, overwrite=overwrite[i], multi_node=multi_node,
+                                  emission_model_keys=[self.base_emission_model_keys[i]], batch_size=batch_size,
+                                  spectra_to_save=spectra_to_save, em_lines_to_save=em_lines_to_save,
+                                  **extra_analysis_functions)
+        if multi_node:
+            _dist.barrier()
+
+    def load_bases(self, load_spectra=False) -> dict:
+        """Read the pipeline files back and concatenate batches / rank shards (``library.py:3385-3642``)."""
+        out = {}
+        for i, base in enumerate(self.bases):
+            stem = os.path.join(self.out_dir, base.model_name)
+            files = [f for f in sorted(os.listdir(self.out_dir))
+                     if f.startswith(base.model_name) and f.endswith(".hdf5")
+                     and (f == base.model_name + ".hdf5" or f[len(base.model_name)] == "_")]
+            if not files:
+                raise FileNotFoundError(f"No pipeline output for base {base.model_name} in {self.out_dir}")
+            parts = []
+            for f in files:
+                data, attrs = read_container(os.path.join(self.out_dir, f))
+                parts.append((int(attrs.get("galaxy_start", 0)), int(attrs.get("rank", 0)), data, attrs))
+            parts.sort(key=lambda t: (t[1], t[0]))
+            key = self.base_emission_model_keys[i]
+            label = parts[0][3].get("InstrumentLabel", base.instrument.label)
+            codes = list(parts[0][3].get("FilterCodes", base.instrument.filters.filter_codes))
+            props = {}
+            for name in parts[0][2]:
+                if name.startswith("Galaxies/") and name.count("/") == 1:
+                    props[name.split("/", 1)[1]] = np.concatenate([p[2][name] for p in parts])
+            phot = {c: np.concatenate([p[2][f"Galaxies/Stars/Photometry/Fluxes/{key}/{label}/{c}"] for p in parts])
+                    for c in codes}
+            entry = {"properties": props, "observed_photometry": phot, "supp_properties": {},
+                     "wavelengths": parts[0][2]["Wavelengths"], "filter_codes": codes, "stem": stem}
+            skey = f"Galaxies/Stars/Spectra/SpectralFluxDensities/{key}"
+            if load_spectra:
+                if skey not in parts[0][2]:
+                    raise KeyError(f"No spectra stored for {base.model_name}; pass spectra_to_save")
+                entry["observed_spectra"] = np.concatenate([p[2][skey] for p in parts])
+            out[base.model_name] = entry
+        return out
+
+    # ---------------------------------------------------------------------------------------
+    def create_library(self, override_instrument=None, save=True, overload_out_name="", overwrite=False):
+        if not self.draw_parameter_combinations:
+            return self.create_full_library(override_instrument, overwrite=overwrite, save=save,
+                                            overload_out_name=overload_out_name)
+        raise NotImplementedError("meshgrid mode (draw_parameter_combinations=True, library.py:3644-3974) is not "
+                                  "part of the batched path; draw the combinations up front instead")
+
+    def create_spectral_grid(self, override_instrument=None, save=True, overload_out_name="", overwrite=False):
+        return self.create_full_library(override_instrument, save=save, overload_out_name=overload_out_name,
+                                        overwrite=overwrite, spectral_mode=True)
+
+    def create_full_library(self, override_instrument=None, save: bool = True, overload_out_name: str = "",
+                            overwrite: bool = False, spectral_mode=False):
+        """Scale base-mass outputs to each galaxy's stellar mass and assemble the parameter table
+        (``library.py:4435-4885``).  Photometry is cast to float32 before the float64 mass ratio is
+        applied (``:4588-4609``); multi-base libraries add the weighted contributions (``:4739-4742``)."""
+        if self.draw_parameter_combinations:
+            raise AssertionError("Cannot create full grid with draw_parameter_combinations set to True. "
+                                 "Set to False to create full grid.")
+        outputs = self.load_bases(load_spectra=spectral_mode)
+        base_filters = outputs[self.bases[0].model_name]["filter_codes"]
+        for b in self.bases[1:]:
+            if outputs[b.model_name]["filter_codes"] != base_filters:
+                raise ValueError("All bases must share the same filters")
+        if override_instrument is not None:
+            for code in override_instrument.filters.filter_codes:
+                if code not in base_filters:
+                    raise ValueError(f"Filter {code} not found in base filters. Cannot override instrument.")
+            filter_codes = list(override_instrument.filters.filter_codes)
+        else:
+            filter_codes = list(base_filters)
+        sel = slice(None) if self._mask is None else np.asarray(self._mask, dtype=bool)
+        redshift = np.broadcast_to(np.asarray(strip_units(self.redshifts), dtype=float),
+                                   (len(self.log_stellar_masses),))[sel]
+        log_mass = np.asarray(self.log_stellar_masses, dtype=float)[sel]
+        weights = np.asarray(self.combination_weights, dtype=float)
+        weights = weights.reshape(len(weights), -1)[sel]
+        multi = len(self.bases) > 1
+        param_columns = ["redshift", "log_mass"] + (["weight_fraction"] if multi else [])
+        param_units = ["dimensionless", "log10_Msun"] + (["dimensionless"] if multi else [])
+        rows = [redshift, log_mass] + ([weights[:, 0]] if multi else [])
+        total = None
+        for i, base in enumerate(self.bases):
+            o = outputs[base.model_name]
+            mass = o["properties"]["mass"]
+            if len(mass) != len(log_mass):
+                raise ValueError(f"base {base.model_name} has {len(mass)} galaxies, expected {len(log_mass)}")
+            scale = (weights[:, i] if multi else 1.0) * 10.0 ** log_mass / mass
+            if spectral_mode:
+                contrib = o["observed_spectra"].astype(np.float32) * scale[:, None]
+            else:
+                phot = np.stack([o["observed_photometry"][c] for c in filter_codes], 1).astype(np.float32)
+                contrib = phot * scale[:, None]
+            total = contrib if total is None else total + contrib
+            for name in base.varying_param_names:
+                if name == "redshift":
+                    continue
+                col = f"{base.model_name}/{name}" if multi else name
+                param_columns.append(col)
+                rows.append(np.asarray(o["properties"][name], dtype=float))
+                short = name.lower()
+                src = base.all_parameters.get(name)
+                param_units.append(UNIT_DICT.get(short, str(src.units) if has_units(src) else "dimensionless"))
+        combined_outputs = np.ascontiguousarray(total.T)          # (n_filters | n_lam, n_gal)
+        combined_params = np.stack(rows, 0)                        # (n_params, n_gal)
+        supp = np.zeros((0, combined_params.shape[1]))
+        out = {"parameters": combined_params, "parameter_names": param_columns,
+               "supplementary_parameters": supp, "supplementary_parameter_names": [],
+               "supplementary_parameter_units": [], "parameter_units": param_units}
+        if spectral_mode:
+            out["spectra"] = combined_outputs
+            self.library_spectra = combined_outputs
+            self.library_filter_codes = (outputs[self.bases[0].model_name]["wavelengths"] * 1e-4).tolist()
+        else:
+            out["photometry"] = combined_outputs
+            self.library_photometry = combined_outputs
+            self.library_filter_codes = filter_codes
+        out["filter_codes"] = self.library_filter_codes
+        self.library_parameters = combined_params
+        self.library_parameter_names = param_columns
+        self.library_parameter_units = param_units
+        self.library_supplementary_parameters = supp
+        self.library_supplementary_parameter_names = []
+        self.library_supplementary_parameter_units = []
+        logger.info(f"Combined outputs shape: {combined_outputs.shape}; parameters {combined_params.shape}")
+        if save:
+            self.save_library(out, overload_out_name=overload_out_name, overwrite=overwrite)
+        return out
+
+    def _validate_library(self, library_dict, check_type="photometry"):
+        """NaN / Inf / shape validation (``library.py:3976-4029``)."""
+        for req in (check_type, "parameters", "parameter_names", "filter_codes"):
+            if req not in library_dict:
+                raise ValueError(f"library dictionary is missing '{req}'")
+        phot, par = library_dict[check_type], library_dict["parameters"]
+        if phot.ndim != 2 or par.ndim != 2 or phot.shape[1] != par.shape[1]:
+            raise ValueError(f"{check_type} {phot.shape} and parameters {par.shape} must share their last axis")
+        if len(library_dict["parameter_names"]) != par.shape[0]:
+            raise ValueError("parameter_names does not match the parameter array")
+        for name, arr in ((check_type, phot), ("parameters", par)):
+            if np.isnan(arr).any():
+                raise ValueError(f"{name} array contains NaN values.")
+            if np.isinf(arr).any():
+                raise ValueError(f"{name} array contains infinite values.")
+        return True
+
+    def save_library(self, library_dict: dict, overload_out_name: str = "", overwrite: bool = False,
+                     library_params_to_save=("model_name",)) -> None:
+        """Write ``Grid/Photometry`` (or ``Grid/Spectra``), ``Grid/Parameters``,
+        ``Grid/SupplementaryParameters`` and the attribute block (``library.py:4031-4153``)."""
+        check_type = "photometry" if "photometry" in library_dict else "spectra"
+        self._validate_library(library_dict, check_type=check_type)
+        os.makedirs(self.out_dir, exist_ok=True)
+        out_name = overload_out_name or self.out_name
+        if not out_name.endswith(".hdf5"):
+            out_name = f"{out_name}.hdf5"
+        rank, size = _rank_size(self._multi_node)
+        if size > 1:
+            out_name = out_name.replace(".hdf5", f"_{rank}.hdf5")  # one shard per rank (utils.py:2288-2299)
+        path = os.path.join(self.out_dir, out_name)
+        if os.path.exists(path) and not overwrite:
+            logger.warning(f"File {path} already exists. Skipping.")
+            return
+        if os.path.exists(path):
+            logger.warning(f"File {path} already exists. Overwriting.")
+            os.remove(path)
+        datasets = {"Grid/Parameters": library_dict["parameters"]}
+        if "photometry" in library_dict:
+            datasets["Grid/Photometry"] = library_dict["photometry"]
+        if "spectra" in library_dict:
+            datasets["Grid/Spectra"] = library_dict["spectra"]
+        if "supplementary_parameters" in library_dict:
+            datasets["Grid/SupplementaryParameters"] = library_dict["supplementary_parameters"]
+        attrs = {"ParameterNames": list(library_dict["parameter_names"]),
+                 "FilterCodes": list(library_dict["filter_codes"]), "PhotometryUnits": "nJy",
+                 "SupplementaryParameterNames": list(library_dict.get("supplementary_parameter_names", [])),
+                 "SupplementaryParameterUnits": list(library_dict.get("supplementary_parameter_units", [])),
+                 "ParameterUnits": list(library_dict.get("parameter_units", [])),
+                 "Grids": [b.grid.grid_name for b in self.bases],
+                 "CreationDT": datetime.now().strftime("%Y%m%d_%H%M%S"), "rank": rank, "world_size": size}
+        for param in library_params_to_save:
+            attrs[param] = [str(getattr(b, param)) for b in self.bases]
+        write_container(path, datasets, attrs)
+        self.library_path = path
+
+    def load_library_from_file(self, file_path: str):
+        from .utils import load_library_from_hdf5
+        lib = load_library_from_hdf5(file_path)
+        self.library_photometry = lib.get("photometry")
+        self.library_parameters = lib["parameters"]
+        self.library_parameter_names = lib["parameter_names"]
+        self.library_filter_codes = lib["filter_codes"]
+        return lib
+
+
+class GalaxySimulator:
+    """On-the-fly simulator: parameter vector(s) -> photometry (``library.py:4922-6001``).
+
+    Unlike the reference (one galaxy per call, ~ms-100 ms of Python/unyt overhead each), ``simulate``
+    also accepts a 2-D array / tensor of N parameter vectors and synthesises them in one CUDA pass.
+    """
+
+    def __init__(self, sfh_model, zdist_model, grid: Grid, instrument: Instrument, emission_model: EmissionModel,
+                 emission_model_key: str, emitter_params: dict = None, cosmo=Planck18, param_order=None,
+                 param_units: dict = None, param_transforms: dict = None, out_flux_unit: str = "nJy",
+                 required_keys=("redshift", "log_mass"), extra_functions=None, normalize_method=None,
+                 output_type="photo_fnu", include_phot_errors: bool = False, depths=None, depth_sigma: int = 5,
+                 noise_models=None, fixed_params: dict = None, photometry_to_remove=None, ignore_params=None,
+                 ignore_scatter: bool = False, return_type: str = "array", device="cpu", max_batch=1 << 16) -> None:
+        assert isinstance(grid, Grid), f"Grid must be a subclass of Grid. Got {type(grid)} instead."
+        assert isinstance(instrument, Instrument), "Instrument must be an Instrument"
+        assert isinstance(emission_model, EmissionModel), "Emission model must be an EmissionModel"
+        assert return_type in ("array", "tensor")
+        if extra_functions:
+            raise NotImplementedError("extra_functions operate on Synthesizer objects; not in the batched path")
+        self.sfh_model, self.zdist_model = sfh_model, zdist_model
+        self.grid, self.instrument, self.emission_model = grid, instrument, emission_model
+        self.emission_model_key = emission_model_key
+        self.emitter_params = emitter_params or {"stellar": ["tau_v"], "galaxy": []}
+        self.cosmo = cosmo
+        self.param_order = list(param_order) if param_order is not None else None
+        self.param_units = param_units or {}
+        self.param_transforms = param_transforms or {}
+        self.out_flux_unit = out_flux_unit
+        self.required_keys = list(required_keys)
+        self.normalize_method = normalize_method
+        self.output_type = [output_type] if isinstance(output_type, str) else list(output_type)
+        self.include_phot_errors = include_phot_errors
+        self.depths, self.depth_sigma = depths, depth_sigma
+        self.noise_models = noise_models
+        self.fixed_params = fixed_params or {}
+        self.ignore_params = ignore_params or []
+        self.ignore_scatter = ignore_scatter
+        self.return_type, self.device = return_type, device
+        self.unused_params, self.reported_unused = [], False
+        if photometry_to_remove:
+            self.update_photo_filters(photometry_to_remove=photometry_to_remove)
+        if depths is not None:
+            assert len(depths) == len(self.instrument.filters.filter_codes), \
+                "depths must have one entry per filter"
+        if noise_models is not None:
+            assert isinstance(noise_models, dict), "noise_models must be a dict keyed by filter code"
+            missing = [c for c in self.instrument.filters.filter_codes if c not in noise_models]
+            assert not missing, f"no noise model for filters {missing}"
+        import inspect
+        self.sfh_params = [p for p in inspect.signature(sfh_model.__init__).parameters
+                           if p not in ("self", "min_age")]
+        self.optional_sfh_params = ["min_age"]
+        self.zdist_params = list(getattr(zdist_model, "required", ())) or self._zdist_names(zdist_model)
+        self.optional_zdist_params = []
+        self.total_possible_keys = set(self.sfh_params + self.zdist_params + self.required_keys + ["min_age"])
+        self._max_batch = int(max_batch)
+        self._engine: Optional[SynthEngine] = None
+
+    @staticmethod
+    def _zdist_names(zdist_model):
+        name = zdist_model.__name__
+        return ["log10metallicity"] if name == "_DeltaConstant" else ["mean", "sigma"]
+
+    def update_photo_filters(self, photometry_to_remove=None, photometry_to_add=None):
+        """Restrict / extend the filter set (``library.py:5180-5216``); rebuilds the device tables lazily."""
+        from .parametric import FilterCollection
+        filters = list(self.instrument.filters.filters)
+        if photometry_to_remove:
+            filters = [f for f in filters if f.filter_code not in set(photometry_to_remove)]
+        if photometry_to_add:
+            raise NotImplementedError("adding filters needs curves on the shared wavelength axis")
+        fc = FilterCollection(filters=filters)
+        fc.lam = self.instrument.filters.lam
+        self.instrument = Instrument(self.instrument.label, filters=fc)
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+    def _get_engine(self):
+        if self._engine is None:
+            self._engine = SynthEngine(self.grid, self.emission_model, self.emission_model_key,
+                                       self.instrument.filters, cosmo=self.cosmo, igm=True,
+                                       max_batch=self._max_batch, device=_dist.local_device())
+        return self._engine
+
+    # ---------------------------------------------------------------------------------------
+    def _params_to_dict(self, params):
+        try:
+            import torch
+            if isinstance(params, torch.Tensor):
+                params = params.detach().cpu().numpy()
+        except ImportError:
+            pass
+        params = copy.deepcopy(params)
+        if not isinstance(params, dict):
+            if self.param_order is None:
+                raise ValueError("simulate() input requires a dictionary unless param_order is set. "
+                                 "Cannot create photometry.")
+            arr = np.asarray(params, dtype=float)
+            if arr.ndim == 2 and arr.shape[0] == 1 and arr.shape[1] == len(self.param_order):
+                arr = arr[0]
+            assert arr.shape[-1] == len(self.param_order), \
+                f"Parameter array length {arr.shape[-1]} does not match parameter order length " \
+                f"{len(self.param_order)}. Cannot create photometry."
+            params = {k: arr[..., j] for j, k in enumerate(self.param_order)}
+        params.update(self.fixed_params)
+        for key in self.required_keys:
+            if key not in params:
+                raise ValueError(f"Missing required parameter {key}. Cannot create photometry.")
+        for key in params:
+            if key in self.param_units:
+                params[key] = params[key] * self.param_units[key]
+        for key, value in self.param_transforms.items():
+            if isinstance(key, tuple):
+                name, func = value
+                params[name] = func(**{k: params[k] for k in key if k in params})
+            elif isinstance(value, tuple):
+                name, func = value
+                params[name] = func(params[key]) if key in params else func(params)
+            elif callable(value):
+                params[key] = value(params[key]) if key in params else value(params)
+        for key in self.sfh_params + self.zdist_params:
+            if key not in params:
+                raise ValueError(f"Missing required parameter {key} for SFH or ZDist. Cannot create photometry.")
+        return params
+
+    def _lower(self, params: dict) -> GalaxyParams:
+        n = int(np.max([np.size(strip_units(v)) for v in params.values()]))
+        bc = lambda v: np.broadcast_to(np.asarray(strip_units(v), dtype=float).reshape(-1), (n,))  # noqa: E731
+        from .parametric import SFH_MAX_PARAMS, ZD_DELTA_LINEAR, ZD_DELTA_LOG10, ZD_NORMAL_LOG10
+        cls = self.sfh_model
+        rows = np.zeros((n, SFH_MAX_PARAMS))
+        to_yr = lambda v: bc(v) * (v.units.factor if has_units(v) else 1.0)  # noqa: E731
+        rows[:, 1] = to_yr(params["max_age"])
+        if "min_age" in params:
+            rows[:, 0] = to_yr(params["min_age"])
+        for j, name in enumerate(cls.param_names):
+            rows[:, 2 + j] = to_yr(params[name]) if name in cls.time_params else bc(params[name])
+        if self.zdist_model.__name__ == "_DeltaConstant":
+            if "log10metallicity" in params:
+                zd = ZDistArray(ZD_DELTA_LOG10, bc(params["log10metallicity"]))
+            else:
+                zd = ZDistArray(ZD_DELTA_LINEAR, bc(params["metallicity"]))
+        else:
+            zd = ZDistArray(ZD_NORMAL_LOG10, bc(params["mean"]), bc(params["sigma"]))
+        tau_v = bc(params["tau_v"]) if "tau_v" in params else None
+        used = [k for k in params if k not in self.total_possible_keys and k != "tau_v"
+                and k not in self.ignore_params and k not in cls.param_names]
+        for k in used:
+            if k not in self.unused_params:
+                self.unused_params.append(k)
+        if self.unused_params and not self.reported_unused:
+            logger.warning(f"The following parameters are not used by the simulator: {self.unused_params}")
+            self.reported_unused = True
+        return GalaxyParams.from_objects(bc(params["redshift"]), SFHArray(cls, rows), zd,
+                                         log_mass=bc(params["log_mass"]), tau_v=tau_v)
+
+    def simulate(self, params):
+        """Photometry (and/or spectra) for one parameter vector or a batch of them."""
+        batched = not isinstance(params, dict) and np.ndim(params) == 2 and np.shape(params)[0] > 1
+        p = self._lower(self._params_to_dict(params))
+        eng = self._get_engine()
+        outputs = {}
+        if "photo_fnu" in self.output_type:
+            outputs["photo_fnu"] = eng.photometry(p, scaled=True)             # nJy
+            outputs["photo_wav"] = self.instrument.filters.pivot_lams
+        if "fnu" in self.output_type:
+            spec = eng.spectra(p).astype(np.float64) * (10.0 ** p.log_mass / eng.base_mass)[:, None]
+            outputs["fnu"] = spec
+            outputs["fnu_wav"] = np.asarray(self.grid.lam)[None, :] * (1.0 + p.redshift)[:, None]
+        for t in self.output_type:
+            if t not in ("photo_fnu", "fnu"):
+                raise NotImplementedError(f"output_type '{t}' is not available in the batched path")
+        conv = {"nJy": 1.0, "uJy": 1e-3, "mJy": 1e-6, "Jy": 1e-9}
+        for k in ("photo_fnu", "fnu"):
+            if k not in outputs:
+                continue
+            if self.out_flux_unit == "AB":
+                with np.errstate(all="ignore"):
+                    outputs[k] = -2.5 * np.log10(outputs[k] * 1e-9) + 8.9
+                if k == "fnu":
+                    outputs[k][np.isinf(outputs[k])] = 99
+            elif self.out_flux_unit == "asinh":
+                raise NotImplementedError("asinh fluxes not implemented yet. Please use AB or Jy units.")
+            elif self.out_flux_unit in conv:
+                outputs[k] = outputs[k] * conv[self.out_flux_unit]
+            else:
+                raise ValueError(f"unknown out_flux_unit {self.out_flux_unit}")
+        if len(self.output_type) > 1:
+            outputs["filters"] = self.instrument.filters
+            return outputs
+        fluxes = outputs[self.output_type[0]]
+        rows = []
+        for g in range(fluxes.shape[0]):
+            f, errors = self._scatter(fluxes[g], flux_units=self.out_flux_unit)
+            if self.normalize_method is not None:
+                f = self._normalize(f, method=self.normalize_method, norm_unit=self.out_flux_unit)
+            if self.include_phot_errors:
+                f = np.concatenate((f, errors))
+            rows.append(f)
+        out = np.stack(rows) if batched else rows[0]
+        if self.return_type == "tensor":
+            import torch
+            out = torch.tensor(np.atleast_2d(out), device=self.device)
+        return out
+
+    def _normalize(self, fluxes, method=None, norm_unit="AB", add_norm_pos=-1):
+        if method is None:
+            return fluxes
+        func = np.subtract if norm_unit == "AB" else np.divide
+        if isinstance(method, str):
+            codes = self.instrument.filters.filter_codes
+            if method not in codes:
+                raise ValueError(f"Filter {method} not found in filter codes. Cannot normalize photometry.")
+            norm = fluxes[codes.index(method)]
+        elif has_units(method):
+            norm = -2.5 * np.log10(float(strip_units(method, "Jy"))) + 8.9 if norm_unit == "AB" else \
+                float(strip_units(method, norm_unit))
+        elif callable(method):
+            norm = method(fluxes)
+        else:
+            norm = method
+        fluxes = func(fluxes, norm)
+        if add_norm_pos is not None:
+            fluxes = np.append(fluxes, norm) if add_norm_pos == -1 else np.insert(fluxes, add_norm_pos, norm)
+        return fluxes
+
+    def _scatter(self, fluxes: np.ndarray, flux_units: str = "nJy"):
+        """Depth or noise-model scatter of one galaxy's photometry (``library.py:5906-5997``), including
+        its quirks: depth errors are returned in uJy, and the AB-mode error carries a minus sign."""
+        if self.ignore_scatter:
+            return fluxes, None
+        to_ujy = {"nJy": 1e-3, "uJy": 1.0, "mJy": 1e3, "Jy": 1e6}
+        if self.depths is not None:
+            depths = self.depths
+            if flux_units == "AB":
+                f_ujy = 10 ** ((fluxes - 23.9) / -2.5)
+            else:
+                f_ujy = fluxes * to_ujy[flux_units]
+            if self.out_flux_unit == "AB" and not has_units(depths):
+                depths_std = 10 ** ((np.asarray(depths, dtype=float) - 23.9) / -2.5) / self.depth_sigma
+            else:
+                depths_std = strip_units(depths, "uJy") / self.depth_sigma
+            noisy = f_ujy + np.random.normal(loc=0, scale=depths_std, size=fluxes.shape)
+            errors = depths_std
+            if flux_units == "AB":
+                with np.errstate(all="ignore"):
+                    out = -2.5 * np.log10(noisy * 1e-6) + 8.9
+                errors = -2.5 * depths_std / (np.log(10) * f_ujy)
+            else:
+                out = noisy / to_ujy[flux_units]
+            return out, errors
+        if self.noise_models is not None:
+            scattered = np.zeros_like(fluxes, dtype=float)
+            errors = np.zeros_like(fluxes, dtype=float)
+            for i, code in enumerate(self.instrument.filters.filter_codes):
+                model = self.noise_models.get(code)
+                model.return_noise = True
+                sf, sig = model.apply_noise(flux=np.atleast_1d(fluxes[i]), true_flux_units=flux_units,
+                                            out_units=self.out_flux_unit)
+                scattered[i], errors[i] = np.asarray(sf).reshape(-1)[0], np.asarray(sig).reshape(-1)[0]
+            return scattered, errors
+        return fluxes, None
+
+    def __call__(self, params):
+        return self.simulate(params)

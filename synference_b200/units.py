@@ -48,10 +48,10 @@ class Unit:
 
     # value * Unit  /  Unit * value
     def __rmul__(self, other):
-        return Quantity(np.asarray(other, dtype=float), self)
+        return Quantity(other, self)
 
     def __mul__(self, other):
-        return Quantity(np.asarray(other, dtype=float), self)
+        return Quantity(other, self)
 
     def __eq__(self, other):
         try:
@@ -76,7 +76,10 @@ class Quantity(np.ndarray):
     def __new__(cls, value, units="dimensionless"):
         if isinstance(value, Quantity) and units is None:
             units = value.units
-        obj = np.asarray(value, dtype=float).view(cls)
+        arr = np.asarray(value)
+        if arr.dtype.kind != "f":
+            arr = arr.astype(float)
+        obj = arr.view(cls)
         obj.units = units if isinstance(units, Unit) else Unit(units)
         return obj
 
@@ -87,7 +90,7 @@ class Quantity(np.ndarray):
 
     @property
     def value(self):
-        return np.asarray(self).view(np.ndarray).copy() if self.ndim else float(np.asarray(self))
+        return np.asarray(self).view(np.ndarray).copy() if self.ndim else np.float64(np.asarray(self))
 
     @property
     def v(self):

@@ -1,0 +1,141 @@
+"""Generate golden vectors by RUNNING THE REFERENCE'S OWN CODE (where it can run offline).
+
+``/root/reference/src/synference/{utils,noise_models}.py`` are pure numpy/scipy apart from their
+imports of unyt / h5py / matplotlib / astropy, none of which is installed here.  This script loads
+those two files by path with stub modules for the missing imports (``unyt`` is served by
+``synference_b200.units``, which implements the calls these files make) and records their outputs for
+fixed, seeded inputs.  The vectors pin the synference-side half of the oracle and of the product
+(unit converters, depth model, asinh magnitudes, constant-R grid, empirical-model binning); the
+Synthesizer-side half stays unpinned (see oracle/oracle.py).
+
+Run in the build container only:  python tests/golden/make_golden_from_reference.py
+"""
+
+import importlib.util
+import os
+import sys
+import types
+from unittest import mock
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/src/synference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_noise_golden.npz")
+
+
+def load_reference():
+    from synference_b200 import units as shim
+    unyt = types.ModuleType("unyt")
+    for name in ("Jy", "nJy", "uJy", "Angstrom", "Unit", "unyt_array", "unyt_quantity", "Myr", "yr", "Msun"):
+        setattr(unyt, name, getattr(shim, name))
+    unyt.unyt_array = unyt.unyt_quantity = shim.Quantity  # must be classes (used in annotations)
+    sys.modules["unyt"] = unyt
+    for name in ("h5py", "matplotlib", "matplotlib.pyplot", "astropy", "astropy.table", "numba", "spectres",
+                 "synthesizer", "plotext"):
+        sys.modules.setdefault(name, mock.MagicMock())
+    pkg = types.ModuleType("synference")
+    pkg.__path__ = [REF]
+    sys.modules["synference"] = pkg
+    mods = {}
+    for name in ("utils", "noise_models"):
+        spec = importlib.util.spec_from_file_location(f"synference.{name}", os.path.join(REF, f"{name}.py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"synference.{name}"] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods["utils"], mods["noise_models"], shim
+
+
+def main():
+    U, NM, shim = load_reference()
+    g = {}
+    mags = np.array([18.0, 23.9, 25.0, 29.3, 31.4])
+    fj = np.asarray(NM.UncertaintyModel.ab_to_jy(mags))
+    g["conv_mags"], g["conv_ab_to_jy"] = mags, fj
+    g["conv_jy_to_ab"] = np.asarray(NM.UncertaintyModel.jy_to_ab(shim.Quantity(fj, "Jy")))
+    merr = np.array([0.01, 0.1, 0.2, 0.5, 1.0])
+    ferr = np.asarray(NM.UncertaintyModel.ab_err_to_jy(merr, shim.Quantity(fj, "Jy")))
+    g["conv_merr"], g["conv_ab_err_to_jy"] = merr, ferr
+    g["conv_jy_err_to_ab"] = np.asarray(NM.UncertaintyModel.jy_err_to_ab(shim.Quantity(ferr, "Jy"), shim.Quantity(fj, "Jy")))
+
+    model = NM.DepthUncertaintyModel(depth_ab=29.0, depth_sigma_level=5, return_noise=True)
+    g["depth_sigma_jy"] = np.asarray(model.sigma)
+    flux_ujy = np.linspace(-0.002, 0.05, 64)
+    np.random.seed(1234)
+    g["depth_z"] = np.random.normal(size=64)                      # the draws numpy will hand out next
+    np.random.seed(1234)
+    noisy, unc = model.apply_noise(shim.Quantity(flux_ujy, "uJy"))
+    g["depth_flux_ujy"], g["depth_noisy_jy"], g["depth_unc_jy"] = flux_ujy, np.asarray(noisy), np.asarray(unc)
+    np.random.seed(1234)
+    noisy_ab, unc_ab = model.apply_noise(flux_ujy * 1e3, true_flux_units="nJy", out_units="AB")
+    g["depth_noisy_ab"], g["depth_unc_ab"] = np.asarray(noisy_ab), np.asarray(unc_ab)
+
+    f = shim.Quantity(np.array([-3e-9, 0.0, 2e-9, 5e-8, 1e-6]), "Jy")
+    e = shim.Quantity(np.array([1e-9, 1e-9, 2e-9, 3e-9, 1e-8]), "Jy")
+    b = shim.Quantity(5e-9, "Jy")
+    g["asinh_f"], g["asinh_e"], g["asinh_b"] = np.asarray(f), np.asarray(e), np.asarray(b)
+    g["asinh_mag"] = np.asarray(U.f_jy_to_asinh(f, b))
+    g["asinh_err"] = np.asarray(U.f_jy_err_to_asinh(f, e, b))
+    g["asinh_back"] = np.asarray(U.asinh_to_f_jy(g["asinh_mag"], b))
+
+    g["const_r_300"] = np.asarray(U.generate_constant_R(R=300, start=shim.Quantity(1000.0, "Angstrom"),
+                                                        end=shim.Quantity(1100.0, "Angstrom")))
+
+    rng = np.random.default_rng(7)
+    true_ab = np.linspace(20, 28, 4000)
+    err_ab = 0.05 + np.exp((true_ab - 26) / 1.5) + rng.normal(0, 0.02, true_ab.size)
+    obs_ab = true_ab + rng.normal(0, 0.01, true_ab.size)
+    gm = NM.GeneralEmpiricalUncertaintyModel(obs_ab, err_ab, flux_unit="AB", log_bins=False, num_bins=16)
+    g["emp_obs"], g["emp_err"] = obs_ab, err_ab
+    g["emp_centers"], g["emp_median"], g["emp_std"] = gm.bin_centers, gm.median_error_in_bin, gm.std_error_in_bin
+    probe = np.linspace(19.0, 29.0, 41)
+    g["emp_probe"], g["emp_mu"] = probe, gm._mu_sigma_interpolator(probe)
+    g["emp_sig"] = gm._sigma_sigma_interpolator(probe)
+    # ---- functions lifted out of modules that cannot be imported offline (AST extraction, no edits)
+    import ast
+    import inspect as _inspect
+    import logging
+    from scipy.stats import qmc
+
+    def lift(path, func_name, class_name=None, extra=None):
+        tree = ast.parse(open(path).read())
+        body = tree.body
+        if class_name:
+            body = next(n for n in body if isinstance(n, ast.ClassDef) and n.name == class_name).body
+        fn = next(n for n in body if isinstance(n, ast.FunctionDef) and n.name == func_name)
+        fn.decorator_list = []
+        for a in fn.args.args + fn.args.kwonlyargs:
+            a.annotation = None
+        fn.returns = None
+        ns = {"np": np, "logger": logging.getLogger("ref"), "unyt_array": shim.Quantity,
+              "unyt_quantity": shim.Quantity, "qmc": qmc, "inspect": _inspect}
+        ns.update(extra or {})
+        exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+        return ns[func_name]
+
+    apply_depths = lift(os.path.join(REF, "sbi_runner.py"), "_apply_depths", "SBI_Fitter")
+    phot = shim.Quantity(np.abs(np.random.default_rng(3).normal(50, 30, size=(4, 6))), "nJy")
+    depths = shim.Quantity(np.array([5.0, 10.0, 20.0, 40.0]), "nJy")
+    np.random.seed(99)
+    g["ad_z"] = np.random.normal(size=(4, 18))
+    np.random.seed(99)
+    out, err = apply_depths(None, depths, phot, N_scatters=3, depth_sigma=5, return_errors=True)
+    g["ad_phot"], g["ad_depths"], g["ad_out"], g["ad_err"] = np.asarray(phot), np.asarray(depths), np.asarray(out), np.asarray(err)
+    np.random.seed(99)
+    out2, err2 = apply_depths(None, depths, phot, N_scatters=3, depth_sigma=5, return_errors=True, min_flux_pc_error=10.0)
+    g["ad_out_pc"], g["ad_err_pc"] = np.asarray(out2), np.asarray(err2)
+
+    draw = lift(os.path.join(REF, "library.py"), "draw_from_hypercube")
+    pr = {"redshift": (0.01, 10), "masses": (5, 11), "tau_v": (0, 2), "peak_age": (0, 0.99), "tau": (0.1, 1.5),
+          "log_zmet": (-3, -1.39)}   # tests/conftest.py:139-147
+    d = draw(pr, N=100, rng=42, unlog_keys=["masses"])
+    for k, v in d.items():
+        g[f"lhc_{k}"] = np.asarray(v)
+    np.savez(OUT, **g)
+    print("wrote", OUT, {k: np.shape(v) for k, v in g.items()})
+
+
+if __name__ == "__main__":
+    main()

