@@ -60,14 +60,14 @@ typedef struct sb2_model_desc {
   const float* kappa; /* [n_chunk*256/n_comp] tau(lambda)/tau_V, zero padded (NULL: no dust) */
   double lam0, q;     /* geometric wavelength axis lam_i = lam0*q^i [Angstrom]              */
   int32_t interp_variant; /* 0: filters interpolated/integrated in nu, 1: in lambda (A9)    */
-  /* filters on the shared axis: band [filt_lo, filt_hi], packed (U, DV) weight pairs       */
+  /* filters on the shared axis: band [filt_lo, filt_hi], packed (U, V) weight pairs        */
   const int32_t* filt_lo;
   const int32_t* filt_hi;
   const int32_t* filt_off;
   const float* filt_uv; /* float2[filt_uv_len]                                              */
   int32_t filt_uv_len;
-  const double* filt_su;  /* [n_filt] denominator = su + beta*sdv                           */
-  const double* filt_sdv; /* [n_filt]                                                       */
+  const double* filt_su;  /* [n_filt] sum(U): denominator = (1-beta)*su + beta*sdv          */
+  const double* filt_sdv; /* [n_filt] sum(V)                                                */
   /* Inoue+14 tables (NULL igm_bin_pow: no IGM)                                             */
   int32_t n_blue, n_lines;
   const double* igm_bin_pow; /* [8][n_blue] */

@@ -99,7 +99,7 @@ struct sb2_model {
   // workspace
   float *w_hi = nullptr, *w_lo = nullptr, *igm = nullptr;
   int *g_m = nullptr, *g_orig = nullptr, *perm = nullptr, *idx = nullptr;
-  float *g_beta = nullptr, *g_taut = nullptr, *g_scale = nullptr, *g_ca = nullptr, *g_cb = nullptr;
+  float *g_beta = nullptr, *g_gamma = nullptr, *g_taut = nullptr, *g_scale = nullptr, *g_ca = nullptr, *g_cb = nullptr;
   float *keys = nullptr, *keys_sorted = nullptr;
   double* g_mscale = nullptr;
   unsigned* g_trunc = nullptr;
@@ -130,7 +130,7 @@ int sb2_model_destroy(sb2_model* m) {
   cudaSetDevice(m->device);
   void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->filt_uv, m->filt_lo,
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage,
-                  m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_taut, m->g_scale,
+                  m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
                   m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->g_mscale, m->g_trunc, m->cub_tmp, m->stage_params,
                   m->stage_flux, m->stage_flux64};
   for (void* p : ptrs)
@@ -217,7 +217,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(w_lo, np * d->k_pad * 4);
   AL(igm, (np / 128) * (size_t)(m->d.n_blue > 0 ? m->d.n_blue : 1) * 128 * 4);
   AL(g_m, np * 4); AL(g_orig, np * 4); AL(perm, np * 4); AL(idx, np * 4);
-  AL(g_beta, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
+  AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
   AL(keys, np * 4); AL(keys_sorted, np * 4);
   AL(g_mscale, np * 8); AL(g_trunc, np * 4);
   m->cub_bytes = 0;
@@ -331,7 +331,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, cuda
   sb2::PrepModel M = prep_model(m);
   sb2::PrepParams P = prep_params(p);
   sb2::PrepOut O{};
-  O.w_hi = m->w_hi; O.w_lo = m->w_lo; O.w_f64 = w_f64; O.igm = m->igm; O.g_m = m->g_m; O.g_beta = m->g_beta;
+  O.w_hi = m->w_hi; O.w_lo = m->w_lo; O.w_f64 = w_f64; O.igm = m->igm; O.g_m = m->g_m; O.g_beta = m->g_beta; O.g_gamma = m->g_gamma;
   O.g_taut = m->g_taut; O.g_scale = m->g_scale; O.g_ca = m->g_ca; O.g_cb = m->g_cb; O.g_orig = m->g_orig;
   O.g_mscale = m->g_mscale; O.g_trunc = m->g_trunc;
   const size_t sh = (size_t)sb2::kPrepWarps * (M.n_age + M.n_z + SB2_SFH_ROW) * sizeof(double);
@@ -369,7 +369,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.n_chunk = d.n_chunk; a.n_kb = d.k_pad / sb2::kBK; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
   a.n_blue = d.n_blue; a.uv_len = d.filt_uv_len;
   a.kappa = m->kappa; a.filt_uv = reinterpret_cast<const float2*>(m->filt_uv); a.igm = m->igm;
-  a.g_m = m->g_m; a.g_beta = m->g_beta; a.g_taut = m->g_taut; a.g_scale = m->g_scale; a.g_ca = m->g_ca;
+  a.g_m = m->g_m; a.g_beta = m->g_beta; a.g_gamma = m->g_gamma; a.g_taut = m->g_taut; a.g_scale = m->g_scale; a.g_ca = m->g_ca;
   a.g_cb = m->g_cb; a.g_orig = m->g_orig; a.g_mscale = m->g_mscale; a.g_trunc = m->g_trunc;
   a.out_base = flux_base; a.out_scaled = flux_scaled; a.out_spec = spec_out;
   for (int f = 0; f < d.n_filt; ++f) {

@@ -62,6 +62,7 @@ struct PrepOut {
   float* igm;       // [n_tiles][n_blue][128]
   int* g_m;         // [n_pad]
   float* g_beta;    // [n_pad]
+  float* g_gamma;   // [n_pad] 1 - beta
   float* g_taut;    // [n_pad]
   float* g_scale;   // [n_pad]
   float* g_ca;      // [n_pad]
@@ -157,7 +158,7 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
       for (int i = lane; i < M.n_blue; i += 32)
         O.igm[((t >> 7) * M.n_blue + i) * 128 + (t & 127)] = 1.f;
     if (lane == 0) {
-      O.g_m[t] = 0; O.g_beta[t] = 0.5f; O.g_taut[t] = 0.f; O.g_scale[t] = 0.f; O.g_ca[t] = 0.f;
+      O.g_m[t] = 0; O.g_beta[t] = 0.5f; O.g_gamma[t] = 0.5f; O.g_taut[t] = 0.f; O.g_scale[t] = 0.f; O.g_ca[t] = 0.f;
       O.g_cb[t] = 0.f; O.g_orig[t] = -1; O.g_mscale[t] = 0.0; O.g_trunc[t] = 0u;
     }
     return;
@@ -249,6 +250,7 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
     const double scale = M.grid_scale * M.base_mass * zp / (4.0 * 3.14159265358979323846 * dl_cm * dl_cm) * 1.0e32;
     O.g_m[t] = m;
     O.g_beta[t] = (float)beta;
+    O.g_gamma[t] = (float)((M.variant == 0) ? (1.0 / r - 1.0 / M.q) / (1.0 - 1.0 / M.q) : (M.q - r) / (M.q - 1.0));
     O.g_taut[t] = (float)((P.tau_v ? P.tau_v[g] : 0.0) * 1.44269504088896340736);
     O.g_scale[t] = (float)scale;
     O.g_ca[t] = (float)(P.coef_att ? P.coef_att[g] : 1.0);

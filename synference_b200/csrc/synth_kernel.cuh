@@ -43,7 +43,8 @@ struct SynthArgs {
   const float2* filt_uv;
   const float* igm;     // [n_tiles][n_blue][128]
   const int* g_m;
-  const float* g_beta;
+  const float* g_beta;   // blend weight of the filter sample n+1
+  const float* g_gamma;  // 1 - beta, rounded from float64 (no cancellation at the band edges)
   const float* g_taut;
   const float* g_scale;
   const float* g_ca;
@@ -155,7 +156,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
     for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
       const int row = tile * kBM + et;
       const int m = A.g_m[row];
-      const float beta = A.g_beta[row], taut = A.g_taut[row], ca = A.g_ca[row], cb = A.g_cb[row];
+      const float beta = A.g_beta[row], gamma = A.g_gamma[row], taut = A.g_taut[row], ca = A.g_ca[row], cb = A.g_cb[row];
       const int orig = A.g_orig[row];
       const float scale = A.g_scale[row];
       int mmin = m, mmax = m;
@@ -215,7 +216,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
             for (int j = 0; j < 32; ++j)
               if (i0 + j < A.n_lam) A.out_spec[(size_t)orig * A.n_lam + i0 + j] = s[j] * scale;
           }
-          // filter numerators: num_f += s_i * (U_f[n] + beta * DV_f[n]),  n = i + m
+          // filter numerators: num_f += s_i * (gamma * U_f[n] + beta * V_f[n]),  n = i + m
 #pragma unroll
           for (int f = 0; f < kNF; ++f) {
             if (f < A.n_filt) {
@@ -228,7 +229,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                   const float2 uv = tab[min(max(k0 + j, 0), kmax)];
-                  a = fmaf(s[j], fmaf(beta, uv.y, uv.x), a);
+                  a = fmaf(s[j], fmaf(beta, uv.y, gamma * uv.x), a);
                 }
                 acc[f] = a;
               }
@@ -237,14 +238,14 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
           if (last_sub) break;
         }
       }
-      // ---- finalize: flux_f = num_f / den_f * scale ; den_f = su_f + beta * sdv_f
+      // ---- finalize: flux_f = num_f / den_f * scale ; den_f = gamma * su_f + beta * sv_f
       if (orig >= 0) {
         const unsigned trunc = A.g_trunc[row];
         const double mscale = A.g_mscale[row];
 #pragma unroll
         for (int f = 0; f < kNF; ++f) {
           if (f < A.n_filt) {
-            float flux = acc[f] / fmaf(beta, A.filt_sdv[f], A.filt_su[f]) * scale;
+            float flux = acc[f] / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * scale;
             if ((trunc >> f) & 1u) flux = __int_as_float(0x7fc00000);
             if (A.out_base) A.out_base[(size_t)orig * A.n_filt + f] = flux;
             if (A.out_scaled) A.out_scaled[(size_t)orig * A.n_filt + f] = (double)flux * mscale;

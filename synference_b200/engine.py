@@ -131,7 +131,8 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
     if kappa is not None:
         kap = np.zeros(n_chunk * lch, dtype=np.float32)
         kap[:n_lam] = kappa
-    # ---- filters on the shared axis -> (U, DV) weight pairs (SURVEY A9 on a geometric grid)
+    # ---- filters on the shared axis -> (U, V) weight pairs (SURVEY A9 on a geometric grid):
+    #      sample weight = (1-beta) U[n] + beta V[n], denominator = (1-beta) sum(U) + beta sum(V)
     if variant not in ("nu", "lam"):
         raise ValueError("variant must be 'nu' or 'lam'")
     c_left, c_right = ((q - 1) / 2, (1 - 1 / q) / 2) if variant == "nu" else ((1 - 1 / q) / 2, (q - 1) / 2)
@@ -156,8 +157,8 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         w = np.where(n == hi, c_left, w)
         u, v = w * t_n, w * t_n1
         lo_l.append(lo); hi_l.append(hi); off_l.append(sum(len(x) for x in uv))
-        su_l.append(u.sum()); sdv_l.append((v - u).sum())
-        uv.append(np.stack([u, v - u], 1))
+        su_l.append(u.sum()); sdv_l.append(v.sum())
+        uv.append(np.stack([u, v], 1))
     uv = np.concatenate(uv, 0).astype(np.float32)
     tables = dict(
         n_age=na, n_z=nz, n_lam=n_lam, n_comp=n_comp, n_filt=len(lo_l), k_pad=k_pad, n_chunk=n_chunk,

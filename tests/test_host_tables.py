@@ -61,8 +61,8 @@ def emulate_filters(t, spec, z):
         lo, hi, off = int(t["filt_lo"][f]), int(t["filt_hi"][f]), int(t["filt_off"][f])
         k = np.clip(i + m - (lo - 2), 0, hi - lo + 3)
         uv = t["filt_uv"][off + k].astype(np.float64)
-        num = np.sum(spec * (uv[:, 0] + beta * uv[:, 1]))
-        out[f] = num / (t["filt_su"][f] + beta * t["filt_sdv"][f])
+        num = np.sum(spec * ((1 - beta) * uv[:, 0] + beta * uv[:, 1]))
+        out[f] = num / ((1 - beta) * t["filt_su"][f] + beta * t["filt_sdv"][f])
     return out
 
 
