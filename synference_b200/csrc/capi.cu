@@ -102,6 +102,7 @@ struct sb2_model {
   float *g_beta = nullptr, *g_gamma = nullptr, *g_taut = nullptr, *g_scale = nullptr, *g_ca = nullptr, *g_cb = nullptr;
   float *keys = nullptr, *keys_sorted = nullptr;
   double* g_mscale = nullptr;
+  double* zpow = nullptr;
   unsigned* g_trunc = nullptr;
   void* cub_tmp = nullptr;
   size_t cub_bytes = 0;
@@ -131,7 +132,7 @@ int sb2_model_destroy(sb2_model* m) {
   void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->filt_uv, m->filt_lo,
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
-                  m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->g_mscale, m->g_trunc, m->cub_tmp, m->stage_params,
+                  m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params,
                   m->stage_flux, m->stage_flux64};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -219,7 +220,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(g_m, np * 4); AL(g_orig, np * 4); AL(perm, np * 4); AL(idx, np * 4);
   AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
   AL(keys, np * 4); AL(keys_sorted, np * 4);
-  AL(g_mscale, np * 8); AL(g_trunc, np * 4);
+  AL(g_mscale, np * 8); AL(g_trunc, np * 4); AL(zpow, np * 13 * 8);
   m->cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)m->cap);
   AL(cub_tmp, m->cub_bytes + 16);
@@ -333,11 +334,16 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, cuda
   sb2::PrepOut O{};
   O.w_hi = m->w_hi; O.w_lo = m->w_lo; O.w_f64 = w_f64; O.igm = m->igm; O.g_m = m->g_m; O.g_beta = m->g_beta; O.g_gamma = m->g_gamma;
   O.g_taut = m->g_taut; O.g_scale = m->g_scale; O.g_ca = m->g_ca; O.g_cb = m->g_cb; O.g_orig = m->g_orig;
-  O.g_mscale = m->g_mscale; O.g_trunc = m->g_trunc;
+  O.g_mscale = m->g_mscale; O.g_trunc = m->g_trunc; O.zpow = m->zpow;
   const size_t sh = (size_t)sb2::kPrepWarps * (M.n_age + M.n_z + SB2_SFH_ROW) * sizeof(double);
   const unsigned blocks = (unsigned)((n_pad + sb2::kPrepWarps - 1) / sb2::kPrepWarps);
   sb2::prep_kernel<<<blocks, sb2::kPrepWarps * 32, sh, st>>>(M, P, O, perm, n_pad);
   CU_TRY(cudaGetLastError());
+  if (M.igm_on && !w_f64) {
+    dim3 grid((unsigned)(n_pad / 128), (unsigned)((M.n_blue + sb2::kIgmStrip - 1) / sb2::kIgmStrip));
+    sb2::igm_kernel<<<grid, 128, 0, st>>>(M, m->zpow, m->igm, n_pad);
+    CU_TRY(cudaGetLastError());
+  }
   cudaEventRecord(m->ev[2], st);
   return SB2_OK;
 }

@@ -59,7 +59,8 @@ struct PrepOut {
   float* w_hi;      // [n_pad][k_pad]
   float* w_lo;      // [n_pad][k_pad]
   double* w_f64;    // optional [n][K] in ORIGINAL order (parity hook), else nullptr
-  float* igm;       // [n_tiles][n_blue][128]
+  float* igm;       // [n_tiles][n_blue][128]   (written by igm_kernel)
+  double* zpow;     // [13][n_pad] powers of (1+z) for igm_kernel, then z
   int* g_m;         // [n_pad]
   float* g_beta;    // [n_pad]
   float* g_gamma;   // [n_pad] 1 - beta
@@ -154,9 +155,7 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
       O.w_hi[t * M.k_pad + k] = 0.f;
       O.w_lo[t * M.k_pad + k] = 0.f;
     }
-    if (M.igm_on)
-      for (int i = lane; i < M.n_blue; i += 32)
-        O.igm[((t >> 7) * M.n_blue + i) * 128 + (t & 127)] = 1.f;
+    if (M.igm_on && lane < 13) O.zpow[(size_t)lane * n_pad + t] = (lane < 12) ? 1.0 : 0.0;
     if (lane == 0) {
       O.g_m[t] = 0; O.g_beta[t] = 0.5f; O.g_gamma[t] = 0.5f; O.g_taut[t] = 0.f; O.g_scale[t] = 0.f; O.g_ca[t] = 0.f;
       O.g_cb[t] = 0.f; O.g_orig[t] = -1; O.g_mscale[t] = 0.0; O.g_trunc[t] = 0u;
@@ -223,14 +222,20 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
   const double inv = inv_sf / zpart;
 
   // ---- weights row (TF32 hi/lo split, K index = iz*n_age + ia) -----------------------------
-  for (int k = lane; k < M.k_pad; k += 32) {
-    double w = 0.0;
-    if (k < M.K) w = sf[k % M.n_age] * zd[k / M.n_age] * inv;
-    float hi = to_tf32_rna((float)w);
-    float lo = to_tf32_rna((float)(w - (double)hi));
-    O.w_hi[t * M.k_pad + k] = hi;
-    O.w_lo[t * M.k_pad + k] = lo;
-    if (O.w_f64 && k < M.K) O.w_f64[g * M.K + k] = w;
+  for (int iz = 0; iz < M.n_z; ++iz) {
+    const double zw = zd[iz] * inv;
+    for (int a = lane; a < M.n_age; a += 32) {
+      const int k = iz * M.n_age + a;
+      const double w = sf[a] * zw;
+      const float hi = to_tf32_rna((float)w);
+      O.w_hi[t * M.k_pad + k] = hi;
+      O.w_lo[t * M.k_pad + k] = to_tf32_rna((float)(w - (double)hi));
+      if (O.w_f64) O.w_f64[g * M.K + k] = w;
+    }
+  }
+  for (int k = M.K + lane; k < M.k_pad; k += 32) {
+    O.w_hi[t * M.k_pad + k] = 0.f;
+    O.w_lo[t * M.k_pad + k] = 0.f;
   }
 
   // ---- per-galaxy scalars -------------------------------------------------------------------
@@ -260,35 +265,67 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
     O.g_trunc[t] = trunc;
   }
 
-  // ---- Inoue+14 transmission for the bins blueward of Ly-alpha ---------------------------------
-  if (!M.igm_on) return;
-  // (1+z)^p for p in (1.2, 2.1, 3.7, 5.5, -0.3, 2, 3, -0.9, 1.6, 3.4, 2.3, 3.3): lane l computes one
-  const double zpw_exp[12] = {1.2, 2.1, 3.7, 5.5, -0.3, 2.0, 3.0, -0.9, 1.6, 3.4, 2.3, 3.3};
-  double mine = (lane < 12) ? pow(zp, zpw_exp[lane]) : 0.0;
+  // ---- (1+z)^p for the IGM kernel: p in (1.2, 2.1, 3.7, 5.5, -0.3, 2, 3, -0.9, 1.6, 3.4, 2.3, 3.3), then z
+  if (M.igm_on) {
+    const double zpw_exp[12] = {1.2, 2.1, 3.7, 5.5, -0.3, 2.0, 3.0, -0.9, 1.6, 3.4, 2.3, 3.3};
+    if (lane < 12) O.zpow[(size_t)lane * n_pad + t] = pow(zp, zpw_exp[lane]);
+    if (lane == 12) O.zpow[(size_t)12 * n_pad + t] = z;
+  }
+}
+
+// Inoue+14 transmission exp(-tau(z, lam_i (1+z))) for the bins blueward of Ly-alpha.
+// Block = one 128-galaxy tile x one strip of 64 wavelength bins; thread = galaxy, so the per-bin tables are
+// warp-uniform loads, the (redshift-sorted) galaxies of a warp take the same branches, and the store of
+// 128 consecutive floats per bin is coalesced in the tile-blocked layout the contraction epilogue reads.
+// No pow(): every term is coef * (lam_i/911.8)^p * (1+z)^p with host-tabulated bin powers and the
+// per-galaxy z powers from prep_kernel; "lines in regime k" are prefixes of the wavelength-sorted
+// line list, tracked by pointers that only move down as the bin index grows.
+constexpr int kIgmStrip = 64;
+
+__global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __restrict__ zpow, float* __restrict__ igm,
+                                                  long long n_pad) {
+  __shared__ double s_thr[3 * 64];
+  __shared__ double s_pre[5 * 64];
+  const int np1 = M.n_lines + 1;
+  for (int i = threadIdx.x; i < 3 * 64; i += 128) s_thr[i] = M.thr[i];
+  for (int i = threadIdx.x; i < 5 * np1; i += 128) s_pre[(i / np1) * 64 + (i % np1)] = M.pre[i];
+  __syncthreads();
+  const int nb = M.n_blue;
+  const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
   double Z[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) Z[i] = __shfl_sync(FULL, mine, i);
-  const int nb = M.n_blue;
-  const int np1 = M.n_lines + 1;
-  for (int i = lane; i < nb; i += 32) {
-    const double b12 = M.bin_pow[0 * nb + i] * Z[0], b21 = M.bin_pow[1 * nb + i] * Z[1];
-    const double b37 = M.bin_pow[2 * nb + i] * Z[2], b55 = M.bin_pow[3 * nb + i] * Z[3];
-    const double bm3 = M.bin_pow[4 * nb + i] * Z[4], b2 = M.bin_pow[5 * nb + i] * Z[5];
-    const double b3 = M.bin_pow[6 * nb + i] * Z[6];
-    const double xl = M.bin_pow[7 * nb + i] * zp;  // lam_obs / 911.8
-    int n1 = 0, n2 = 0, nd = 0;  // leading lines (largest lam_j) still in the low-z regimes
+  for (int p = 0; p < 12; ++p) Z[p] = zpow[(size_t)p * n_pad + t];
+  const double z = zpow[(size_t)12 * n_pad + t];
+  const double zp = 1.0 + z;
+  const int i0 = blockIdx.y * kIgmStrip;
+  const int i1 = min(nb, i0 + kIgmStrip);
+  // lines (sorted by decreasing wavelength) still below the regime thresholds at the strip's first bin
+  int n1 = 0, n2 = 0, nd = 0;
+  {
+    const double xl = __ldg(M.bin_pow + 7 * nb + i0) * zp;
 #pragma unroll
     for (int step = 32; step; step >>= 1) {
-      if (M.thr[0 * 64 + n1 + step - 1] > xl) n1 += step;
-      if (M.thr[1 * 64 + n2 + step - 1] > xl) n2 += step;
-      if (M.thr[2 * 64 + nd + step - 1] > xl) nd += step;
+      if (s_thr[0 * 64 + n1 + step - 1] > xl) n1 += step;
+      if (s_thr[1 * 64 + n2 + step - 1] > xl) n2 += step;
+      if (s_thr[2 * 64 + nd + step - 1] > xl) nd += step;
     }
-    const int J = M.nline[i];
+  }
+  float* out = igm + ((size_t)blockIdx.x * nb) * 128 + threadIdx.x;
+  for (int i = i0; i < i1; ++i) {
+    const double xl = __ldg(M.bin_pow + 7 * nb + i) * zp;  // lam_obs / 911.8
+    while (n1 > 0 && !(s_thr[0 * 64 + n1 - 1] > xl)) --n1;
+    while (n2 > 0 && !(s_thr[1 * 64 + n2 - 1] > xl)) --n2;
+    while (nd > 0 && !(s_thr[2 * 64 + nd - 1] > xl)) --nd;
+    const double b12 = __ldg(M.bin_pow + 0 * nb + i) * Z[0], b37 = __ldg(M.bin_pow + 2 * nb + i) * Z[2];
+    const double b55 = __ldg(M.bin_pow + 3 * nb + i) * Z[3];
+    const double b2 = xl * xl, b3 = b2 * xl;
+    const int J = __ldg(M.nline + i);
     const int a = min(J, n1), b = min(J, n2), c = min(J, nd);
-    double tau = b12 * M.pre[0 * np1 + a] + b37 * (M.pre[1 * np1 + b] - M.pre[1 * np1 + a]) +
-                 b55 * (M.pre[2 * np1 + J] - M.pre[2 * np1 + b]) + b2 * M.pre[3 * np1 + c] +
-                 b3 * (M.pre[4 * np1 + J] - M.pre[4 * np1 + c]);
-    if (M.lc_on[i]) {
+    double tau = b12 * s_pre[0 * 64 + a] + b37 * (s_pre[1 * 64 + b] - s_pre[1 * 64 + a]) +
+                 b55 * (s_pre[2 * 64 + J] - s_pre[2 * 64 + b]) + b2 * s_pre[3 * 64 + c] +
+                 b3 * (s_pre[4 * 64 + J] - s_pre[4 * 64 + c]);
+    if (__ldg(M.lc_on + i)) {
+      const double b21 = __ldg(M.bin_pow + 1 * nb + i) * Z[1], bm3 = __ldg(M.bin_pow + 4 * nb + i) * Z[4];
       // Lyman continuum, DLA component
       if (z < 2.0) tau += 0.2113 * Z[5] - 0.07661 * Z[10] * bm3 - 0.1347 * b2;
       else if (xl >= 3.0) tau += 0.04696 * Z[6] - 0.01779 * Z[11] * bm3 - 0.02916 * b3;
@@ -304,7 +341,7 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
         else if (xl < 2.2) tau += 5.221e-4 * Z[9] * b21 + 0.3248 * b12 - 3.140e-2 * b21;
       }
     }
-    O.igm[((t >> 7) * nb + i) * 128 + (t & 127)] = (float)exp(-tau);
+    out[(size_t)i * 128] = (float)exp(-tau);
   }
 }
 
