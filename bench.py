@@ -248,8 +248,13 @@ def main():
         peaks, peak_src = read_peaks()
         t = eng.tables
         k_alg = t["n_age"] * t["n_z"]
-        flops_alg = 2.0 * k_alg * t["n_lam"] * t["n_comp"] * n          # 2 K N_lam C per galaxy
-        flops_exec = 3.0 * 2.0 * t["k_pad"] * (t["n_chunk"] * 256) * ((n + 127) // 128 * 128)  # 3xTF32, padded
+        # DeltaConstant batches are grouped by metallicity bracket and multiply only the two grid
+        # metallicities they can touch: K_exec = 2 n_age (report K_exec, count executed flops)
+        delta = w.params.zd_type in (0, 1) and t["n_z"] >= 2
+        k_exec = 2 * t["n_age"] if delta else k_alg
+        k_mma = 2 * t["n_age_pad"] if delta else t["k_pad"]
+        flops_alg = 2.0 * k_exec * t["n_lam"] * t["n_comp"] * n          # 2 K_exec N_lam C per galaxy
+        flops_exec = 3.0 * 2.0 * k_mma * (t["n_chunk"] * 256) * ((n + 127) // 128 * 128)  # 3xTF32, padded
         achieved = flops_alg / (synth_ms_avg * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -257,9 +262,11 @@ def main():
                     "kernel": "synth_kernel (3xTF32 tcgen05 contraction + fused epilogue)",
                     "kernel_ms": synth_ms_avg, "peak_source": f"{peak_src} bf16 sustained (MEASURED_PEAKS.json)",
                     "executed_tflops": flops_exec / (synth_ms_avg * 1e-3) / 1e12,
-                    "note": "achieved counts ALGORITHMIC flops 2*K*N_lam*C per galaxy; the kernel executes 3x "
-                            "that on the TF32 pipe (3xTF32 for the 1e-5 tolerance), whose dense peak is half "
-                            "the bf16 peak, so frac <= 1/6 by construction",
+                    "k_exec": k_exec, "k_dense": k_alg,
+                    "note": "achieved counts ALGORITHMIC flops 2*K_exec*N_lam*C per galaxy (K_exec = 2*n_age for "
+                            "DeltaConstant batches grouped by metallicity bracket, n_age*n_z otherwise); the kernel "
+                            "executes 3x that on the TF32 pipe (3xTF32 for the 1e-5 tolerance), whose dense peak is "
+                            "half the bf16 peak, so frac <= 1/6 by construction",
                     "stage_ms": {"sort": float(np.mean([s[0] for s in stages])),
                                  "weights_igm": float(np.mean([s[1] for s in stages])),
                                  "contraction_epilogue": synth_ms_avg}}
@@ -278,9 +285,11 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 accumulate); weights/IGM in f64",
             "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "galaxies_per_gpu_per_step": n,
-                       "n_lam": t["n_lam"], "n_filt": t["n_filt"], "k": k_alg, "n_comp": t["n_comp"],
-                       "l2": "per-step working set (TF32 hi/lo weights, %.1f GB) >> 126 MB L2; no explicit flush"
-                             % (2 * 4 * t["k_pad"] * n / 1e9)},
+                       "n_lam": t["n_lam"], "n_filt": t["n_filt"], "k": k_alg, "k_exec": k_exec,
+                       "n_comp": t["n_comp"],
+                       "l2": "per-step working set (TF32 hi/lo weights %.2f GB + parameters + IGM rows %.2f GB) "
+                             ">> 126 MB L2; no explicit flush"
+                             % (2 * 4 * k_mma * n / 1e9, 4.0 * (t["igm"]["n_blue"] if t["igm"] else 0) * n / 1e9)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "SynthEngine.photometry (sb2_synth_photometry_host), pinned host buffers"},
             "gpu_launches": 3 * args.steps,

@@ -48,12 +48,14 @@ enum { SB2_ZD_DELTA_LINEAR = 0, SB2_ZD_DELTA_LOG10 = 1, SB2_ZD_NORMAL_LINEAR = 2
  * sb2_model_create time.                                                                  */
 typedef struct sb2_model_desc {
   int32_t n_age, n_z, n_lam, n_comp, n_filt;
-  int32_t k_pad;   /* n_age*n_z rounded up to a multiple of 32                              */
+  int32_t n_age_pad; /* n_age rounded up to a multiple of 4: grid column of (iz, ia) is iz*n_age_pad + ia,
+                      * so every metallicity's columns start 16-byte aligned (TMA box origin)        */
+  int32_t k_pad;   /* n_age_pad*n_z rounded up to a multiple of 32                          */
   int32_t n_chunk; /* wavelength chunks of 256/n_comp bins                                  */
   const double* log10ages;     /* [n_age]                                                   */
   const double* metallicities; /* [n_z]                                                     */
   /* Transposed, TF32 hi/lo-split grid in internal units, K-major:
-   * row = chunk*256 + comp*(256/n_comp) + bin_in_chunk ; column k = iz*n_age + ia          */
+   * row = chunk*256 + comp*(256/n_comp) + bin_in_chunk ; column k = iz*n_age_pad + ia      */
   const float* gt_hi; /* [n_chunk*256][k_pad]                                               */
   const float* gt_lo; /* [n_chunk*256][k_pad]                                               */
   double grid_scale;  /* erg/s/Hz/Msun per internal unit                                    */

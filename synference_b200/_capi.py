@@ -28,7 +28,7 @@ _ip = C.POINTER(C.c_int32)
 class ModelDesc(C.Structure):
     _fields_ = [
         ("n_age", C.c_int32), ("n_z", C.c_int32), ("n_lam", C.c_int32), ("n_comp", C.c_int32),
-        ("n_filt", C.c_int32), ("k_pad", C.c_int32), ("n_chunk", C.c_int32),
+        ("n_filt", C.c_int32), ("n_age_pad", C.c_int32), ("k_pad", C.c_int32), ("n_chunk", C.c_int32),
         ("log10ages", _dp), ("metallicities", _dp),
         ("gt_hi", _fp), ("gt_lo", _fp), ("grid_scale", C.c_double),
         ("kappa", _fp), ("lam0", C.c_double), ("q", C.c_double), ("interp_variant", C.c_int32),

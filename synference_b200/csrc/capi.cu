@@ -1,5 +1,6 @@
 // C ABI of the B200-native mock-library hot path (see include/synference_b200.h).
 // Owns the device-resident model, the per-batch workspace, the TMA descriptors and the launches.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,6 +31,22 @@ int fail(int code, const std::string& msg) {
     cudaError_t e_ = (expr);                                                                 \
     if (e_ != cudaSuccess)                                                                   \
       return fail(SB2_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+// SB2_DEBUG_SYNC=1: synchronise after every launch and name the stage that failed.
+bool debug_sync() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SB2_DEBUG_SYNC");
+    v = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+#define STAGE_CHECK(name, st)                                                                  \
+  do {                                                                                         \
+    cudaError_t e_ = cudaGetLastError();                                                       \
+    if (e_ == cudaSuccess && debug_sync()) e_ = cudaStreamSynchronize(st);                     \
+    if (e_ != cudaSuccess) return fail(SB2_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
 template <class T>
@@ -72,11 +89,67 @@ int make_tmap(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, 
   return SB2_OK;
 }
 
-__global__ void sort_keys_kernel(const double* z, float* keys, int* idx, long long n) {
+// Grouping keys: (metallicity bracket, redshift).  Tiles of the contraction kernel hold galaxies of ONE
+// bracket (so a DeltaConstant batch multiplies only the 2*n_age grid columns it can touch) in redshift
+// order (so the filter windows of a warp's galaxies coincide).  Dense batches use bracket 0 for everyone.
+constexpr int kMaxGroups = 64;
+constexpr int kKeyShift = 26;  // key = bracket << 26 | float_bits(z) >> 6
+
+__global__ void group_keys_kernel(const double* __restrict__ z, const double* __restrict__ zv,
+                                  const double* __restrict__ zx, int n_z, int delta, unsigned* keys, int* idx,
+                                  int* counts, long long n) {
+  __shared__ int h[kMaxGroups];
+  if (threadIdx.x < kMaxGroups) h[threadIdx.x] = 0;
+  __syncthreads();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    keys[i] = (float)z[i];
+    int j = 0;
+    if (delta) {
+      double f;
+      j = sb2::delta_bracket(zx, n_z, zv[i], &f);
+    }
+    const float zf = fmaxf((float)z[i], 0.f);
+    keys[i] = ((unsigned)j << kKeyShift) | (__float_as_uint(zf) >> (32 - kKeyShift));
     idx[i] = (int)i;
+    atomicAdd(&h[j], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxGroups && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+
+// counts -> first sorted position (cum) and first padded row (pad_start) of every group, the tile count and
+// each tile's first grid column.
+__global__ void group_layout_kernel(const int* __restrict__ counts, int n_groups, int cols_per_group, int* cum,
+                                    int* pad_start, int* tile_k0, int* n_tiles_out, int max_tiles) {
+  __shared__ int s_first[kMaxGroups + 1];
+  if (threadIdx.x == 0) {
+    int c = 0, t = 0;
+    for (int j = 0; j < n_groups; ++j) {
+      cum[j] = c;
+      pad_start[j] = t * 128;
+      s_first[j] = t;
+      c += counts[j];
+      t += (counts[j] + 127) / 128;
+    }
+    s_first[n_groups] = t;
+    *n_tiles_out = t;
+  }
+  __syncthreads();
+  const int total = min(s_first[n_groups], max_tiles);
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    int j = 0;
+    while (j + 1 < n_groups && s_first[j + 1] <= t) ++j;
+    tile_k0[t] = j * cols_per_group;
+  }
+}
+
+__global__ void group_scatter_kernel(const unsigned* __restrict__ keys_sorted, const int* __restrict__ perm_sorted,
+                                     const int* __restrict__ cum, const int* __restrict__ pad_start, int* perm_pad,
+                                     long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int j = (int)(keys_sorted[i] >> kKeyShift);
+    perm_pad[pad_start[j] + (int)(i - cum[j])] = perm_sorted[i];
   }
 }
 
@@ -100,7 +173,13 @@ struct sb2_model {
   float *w_hi = nullptr, *w_lo = nullptr, *igm = nullptr;
   int *g_m = nullptr, *g_orig = nullptr, *perm = nullptr, *idx = nullptr;
   float *g_beta = nullptr, *g_gamma = nullptr, *g_taut = nullptr, *g_scale = nullptr, *g_ca = nullptr, *g_cb = nullptr;
-  float *keys = nullptr, *keys_sorted = nullptr;
+  unsigned *keys = nullptr, *keys_sorted = nullptr;
+  int *perm_pad = nullptr, *grp = nullptr, *tile_k0 = nullptr;  // grp: counts[64] | cum[64] | pad_start[64] | n_tiles
+  int uv_len = 0;      // entries of the padded (U, V) tables
+  int n_blue_pad = 0;  // IGM rows per tile (n_blue rounded up to 32; the extra rows hold 1)
+  int2* tile_range = nullptr;
+  int wd_stride = 0;  // floats per weights row in DeltaConstant (bracket-grouped) mode; 0: mode unavailable
+  CUtensorMap tm_wd_hi, tm_wd_lo;
   double* g_mscale = nullptr;
   double* zpow = nullptr;
   unsigned* g_trunc = nullptr;
@@ -132,7 +211,7 @@ int sb2_model_destroy(sb2_model* m) {
   void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->filt_uv, m->filt_lo,
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
-                  m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params,
+                  m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params,
                   m->stage_flux, m->stage_flux64};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -147,7 +226,8 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   *out = nullptr;
   if (d->n_comp != 1 && d->n_comp != 2) return fail(SB2_ERR_INVALID, "n_comp must be 1 or 2");
   if (d->n_filt < 1 || d->n_filt > sb2::kMaxFilt) return fail(SB2_ERR_INVALID, "n_filt must be in [1, 32]");
-  if (d->k_pad % 32 != 0 || d->k_pad < d->n_age * d->n_z) return fail(SB2_ERR_INVALID, "bad k_pad");
+  if (d->n_age_pad < d->n_age || d->n_age_pad % 4 != 0) return fail(SB2_ERR_INVALID, "n_age_pad must be a multiple of 4 >= n_age");
+  if (d->k_pad % 32 != 0 || d->k_pad < d->n_age_pad * d->n_z) return fail(SB2_ERR_INVALID, "bad k_pad");
   const int lch = sb2::kBN / d->n_comp;
   if (d->n_chunk != (d->n_lam + lch - 1) / lch) return fail(SB2_ERR_INVALID, "bad n_chunk");
   if (d->max_batch < 1) return fail(SB2_ERR_INVALID, "max_batch must be positive");
@@ -184,12 +264,28 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
     if (d->kappa) std::memcpy(kap.data(), d->kappa, kap.size() * sizeof(float));
     UP(kappa, kap.data(), kap.size());
   }
-  UP(filt_uv, d->filt_uv, (size_t)d->filt_uv_len * 2);
+  {
+    // (U, V) tables with kUvPad zero entries on both sides of every filter, so the epilogue's shifted reads
+    // need no index clamps (synth_kernel.cuh, fast path)
+    std::vector<float> uvp;
+    for (int f = 0; f < d->n_filt; ++f) {
+      const int len = d->filt_hi[f] - d->filt_lo[f] + 4;
+      if (len < 4 || d->filt_off[f] < 0 || d->filt_off[f] + len > d->filt_uv_len) {
+        sb2_model_destroy(m);
+        return fail(SB2_ERR_INVALID, "filter table offsets inconsistent with filt_lo/filt_hi");
+      }
+      m->h_off.push_back((int)(uvp.size() / 2));
+      uvp.insert(uvp.end(), (size_t)2 * sb2::kUvPad, 0.f);
+      uvp.insert(uvp.end(), d->filt_uv + (size_t)2 * d->filt_off[f], d->filt_uv + (size_t)2 * (d->filt_off[f] + len));
+      uvp.insert(uvp.end(), (size_t)2 * sb2::kUvPad, 0.f);
+    }
+    m->uv_len = (int)(uvp.size() / 2);
+    UP(filt_uv, uvp.data(), uvp.size());
+  }
   UP(filt_lo, d->filt_lo, d->n_filt);
   UP(filt_hi, d->filt_hi, d->n_filt);
   m->h_lo.assign(d->filt_lo, d->filt_lo + d->n_filt);
   m->h_hi.assign(d->filt_hi, d->filt_hi + d->n_filt);
-  m->h_off.assign(d->filt_off, d->filt_off + d->n_filt);
   for (int f = 0; f < d->n_filt; ++f) {
     m->h_su.push_back((float)d->filt_su[f]);
     m->h_sdv.push_back((float)d->filt_sdv[f]);
@@ -203,6 +299,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   } else {
     m->d.n_blue = 0;
   }
+  m->n_blue_pad = (m->d.n_blue + 31) / 32 * 32;
   UP(dc, d->cosmo_dc, d->cosmo_n + 1);
   UP(ddc, d->cosmo_ddc, d->cosmo_n + 1);
   UP(age, d->cosmo_age, d->cosmo_n + 1);
@@ -210,16 +307,20 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
 #undef UP
   // workspace
   m->cap = d->max_batch;
-  m->cap_pad = (m->cap + 127) / 128 * 128;
+  m->cap_pad = (m->cap + 127) / 128 * 128 + 128 * (long long)(d->n_z > 1 ? d->n_z - 1 : 1);
+  // bracket-grouped (DeltaConstant) mode: a tile's grid columns start at bracket*n_age_pad -- TMA needs that
+  // start 16-byte aligned, hence n_age_pad % 4 == 0 -- and span two metallicities
+  m->wd_stride = (d->n_z >= 2 && d->n_z <= kMaxGroups) ? 2 * d->n_age_pad : 0;
   const size_t np = (size_t)m->cap_pad;
 #define AL(ptr, bytes) { cudaError_t e_ = cudaMalloc(reinterpret_cast<void**>(&m->ptr), (bytes)); \
     if (e_ != cudaSuccess) { sb2_model_destroy(m); return fail(SB2_ERR_CUDA, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_)); } }
   AL(w_hi, np * d->k_pad * 4);
   AL(w_lo, np * d->k_pad * 4);
-  AL(igm, (np / 128) * (size_t)(m->d.n_blue > 0 ? m->d.n_blue : 1) * 128 * 4);
+  AL(igm, (np / 128) * (size_t)(m->n_blue_pad > 0 ? m->n_blue_pad : 1) * 128 * 4);
+  AL(tile_range, (np / 128) * sizeof(int2));
   AL(g_m, np * 4); AL(g_orig, np * 4); AL(perm, np * 4); AL(idx, np * 4);
   AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
-  AL(keys, np * 4); AL(keys_sorted, np * 4);
+  AL(keys, np * 4); AL(keys_sorted, np * 4); AL(perm_pad, np * 4); AL(tile_k0, (np / 128) * 4); AL(grp, (3 * kMaxGroups + 1) * 4);
   AL(g_mscale, np * 8); AL(g_trunc, np * 4); AL(zpow, np * 13 * 8);
   m->cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)m->cap);
@@ -230,12 +331,14 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
 #undef AL
   if ((rc = make_tmap(&m->tm_w_hi, m->w_hi, np, d->k_pad, sb2::kBM)) != SB2_OK ||
       (rc = make_tmap(&m->tm_w_lo, m->w_lo, np, d->k_pad, sb2::kBM)) != SB2_OK ||
+      (m->wd_stride && (rc = make_tmap(&m->tm_wd_hi, m->w_hi, np, m->wd_stride, sb2::kBM)) != SB2_OK) ||
+      (m->wd_stride && (rc = make_tmap(&m->tm_wd_lo, m->w_lo, np, m->wd_stride, sb2::kBM)) != SB2_OK) ||
       (rc = make_tmap(&m->tm_g_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK) {
     sb2_model_destroy(m);
     return rc;
   }
-  m->smem_bytes = 1024 + (size_t)sb2::kStages * sb2::kStageBytes + (((size_t)d->filt_uv_len * 8 + 15) & ~size_t(15)) + 128;
+  m->smem_bytes = 1024 + (size_t)sb2::kStages * sb2::kStageBytes + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 128;
   if (m->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
     sb2_model_destroy(m);
     return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to the operand pipeline (" +
@@ -255,31 +358,39 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
 
 namespace {
 
-template <int C, int NF>
-int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
-  auto k = sb2::synth_kernel<C, NF>;
+template <int C, int NF, bool SPEC>
+int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
+  auto k = sb2::synth_kernel<C, NF, SPEC>;
   CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes));
-  k<<<grid, sb2::kSynthThreads, m->smem_bytes, st>>>(m->tm_w_hi, m->tm_w_lo, m->tm_g_hi, m->tm_g_lo, a);
-  CU_TRY(cudaGetLastError());
+  k<<<grid, sb2::kSynthThreads, m->smem_bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo,
+                                                     m->tm_g_hi, m->tm_g_lo, a);
+  STAGE_CHECK("synth_kernel", st);
   return SB2_OK;
 }
 
-int launch_synth(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
+int launch_synth(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
   const int nf = m->d.n_filt, c = m->d.n_comp;
+  const bool spec = a.out_spec != nullptr;
+#define SB2_PICK(C, NF) (spec ? launch_synth_t<C, NF, true>(m, a, grid, delta, st) : launch_synth_t<C, NF, false>(m, a, grid, delta, st))
   if (c == 1) {
-    if (nf <= 8) return launch_synth_t<1, 8>(m, a, grid, st);
-    if (nf <= 24) return launch_synth_t<1, 24>(m, a, grid, st);
-    return launch_synth_t<1, 32>(m, a, grid, st);
+    if (nf <= 8) return SB2_PICK(1, 8);
+    if (nf <= 24) return SB2_PICK(1, 24);
+    return SB2_PICK(1, 32);
   }
-  if (nf <= 8) return launch_synth_t<2, 8>(m, a, grid, st);
-  if (nf <= 24) return launch_synth_t<2, 24>(m, a, grid, st);
-  return launch_synth_t<2, 32>(m, a, grid, st);
+  if (nf <= 8) return SB2_PICK(2, 8);
+  if (nf <= 24) return SB2_PICK(2, 24);
+  return SB2_PICK(2, 32);
+#undef SB2_PICK
+}
+
+bool delta_mode(const sb2_model* m, const sb2_params* p) {
+  return m->wd_stride > 0 && (p->zd_type == SB2_ZD_DELTA_LINEAR || p->zd_type == SB2_ZD_DELTA_LOG10);
 }
 
 sb2::PrepModel prep_model(const sb2_model* m) {
   sb2::PrepModel M{};
   const sb2_model_desc& d = m->d;
-  M.n_age = d.n_age; M.n_z = d.n_z; M.K = d.n_age * d.n_z; M.k_pad = d.k_pad; M.n_lam = d.n_lam;
+  M.n_age = d.n_age; M.n_z = d.n_z; M.na_pad = d.n_age_pad; M.K = d.n_age * d.n_z; M.k_pad = d.k_pad; M.n_lam = d.n_lam;
   M.n_filt = d.n_filt; M.n_blue = d.n_blue; M.n_lines = d.n_lines; M.variant = d.interp_variant;
   M.igm_on = d.n_blue > 0;
   M.ages = m->ages; M.edges = m->edges; M.zmet = m->zmet; M.log10zmet = m->log10zmet;
@@ -314,22 +425,42 @@ int check_params(const sb2_model* m, const sb2_params* p) {
   return SB2_OK;
 }
 
-// sort by redshift -> perm ; prep kernel
+// Rows the grouped layout of a batch of n galaxies can occupy (every group is padded to whole tiles).
+long long padded_rows(const sb2_model* m, long long n, bool delta) {
+  return (n + 127) / 128 * 128 + (delta ? 128LL * (m->d.n_z - 1) : 0);
+}
+
+// group by (metallicity bracket, redshift) -> perm_pad ; prep kernel
 int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, cudaStream_t st) {
   const long long n = p->n;
-  const long long n_pad = (n + 127) / 128 * 128;
+  const bool delta = sorted && delta_mode(m, p);
+  const long long n_pad = padded_rows(m, n, delta);
   const int* perm = nullptr;
   cudaEventRecord(m->ev[0], st);
   if (sorted) {
     const int tb = 256;
-    sort_keys_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(p->redshift, m->keys, m->idx, n);
-    CU_TRY(cudaGetLastError());
+    const int n_groups = delta ? m->d.n_z - 1 : 1;
+    const bool logz = p->zd_type == SB2_ZD_DELTA_LOG10;
+    CU_TRY(cudaMemsetAsync(m->grp, 0, (3 * kMaxGroups + 1) * 4, st));
+    CU_TRY(cudaMemsetAsync(m->perm_pad, 0xFF, (size_t)n_pad * 4, st));
+    group_keys_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(p->redshift, p->zd_value, logz ? m->log10zmet : m->zmet,
+                                                                   m->d.n_z, delta ? 1 : 0, m->keys, m->idx, m->grp, n);
+    STAGE_CHECK("group_keys_kernel", st);
     size_t bytes = m->cub_bytes;
     CU_TRY(cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)n, 0, 32, st));
-    perm = m->perm;
+    STAGE_CHECK("radix sort", st);
+    group_layout_kernel<<<1, 256, 0, st>>>(m->grp, n_groups, m->d.n_age_pad, m->grp + kMaxGroups, m->grp + 2 * kMaxGroups,
+                                           m->tile_k0, m->grp + 3 * kMaxGroups, (int)(n_pad / 128));
+    STAGE_CHECK("group_layout_kernel", st);
+    group_scatter_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(m->keys_sorted, m->perm, m->grp + kMaxGroups,
+                                                                      m->grp + 2 * kMaxGroups, m->perm_pad, n);
+    STAGE_CHECK("group_scatter_kernel", st);
+    perm = m->perm_pad;
   }
   cudaEventRecord(m->ev[1], st);
   sb2::PrepModel M = prep_model(m);
+  M.delta = delta ? 1 : 0;
+  M.w_stride = delta ? m->wd_stride : m->d.k_pad;
   sb2::PrepParams P = prep_params(p);
   sb2::PrepOut O{};
   O.w_hi = m->w_hi; O.w_lo = m->w_lo; O.w_f64 = w_f64; O.igm = m->igm; O.g_m = m->g_m; O.g_beta = m->g_beta; O.g_gamma = m->g_gamma;
@@ -338,11 +469,11 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, cuda
   const size_t sh = (size_t)sb2::kPrepWarps * (M.n_age + M.n_z + SB2_SFH_ROW) * sizeof(double);
   const unsigned blocks = (unsigned)((n_pad + sb2::kPrepWarps - 1) / sb2::kPrepWarps);
   sb2::prep_kernel<<<blocks, sb2::kPrepWarps * 32, sh, st>>>(M, P, O, perm, n_pad);
-  CU_TRY(cudaGetLastError());
+  STAGE_CHECK("prep_kernel", st);
   if (M.igm_on && !w_f64) {
-    dim3 grid((unsigned)(n_pad / 128), (unsigned)((M.n_blue + sb2::kIgmStrip - 1) / sb2::kIgmStrip));
-    sb2::igm_kernel<<<grid, 128, 0, st>>>(M, m->zpow, m->igm, n_pad);
-    CU_TRY(cudaGetLastError());
+    dim3 grid((unsigned)(n_pad / 128), (unsigned)((m->n_blue_pad + sb2::kIgmStrip - 1) / sb2::kIgmStrip));
+    sb2::igm_kernel<<<grid, 128, 0, st>>>(M, m->zpow, m->igm, m->n_blue_pad, n_pad);
+    STAGE_CHECK("igm_kernel", st);
   }
   cudaEventRecord(m->ev[2], st);
   return SB2_OK;
@@ -370,10 +501,23 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   if ((rc = run_prep(m, p, nullptr, true, st)) != SB2_OK) return rc;
   const sb2_model_desc& d = m->d;
   sb2::SynthArgs a{};
+  const bool delta = delta_mode(m, p);
   a.n_gal = (int)p->n;
-  a.n_tiles = (int)((p->n + 127) / 128);
-  a.n_chunk = d.n_chunk; a.n_kb = d.k_pad / sb2::kBK; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
-  a.n_blue = d.n_blue; a.uv_len = d.filt_uv_len;
+  a.n_tiles = (int)(padded_rows(m, p->n, delta) / 128);
+  a.n_tiles_dev = m->grp + 3 * kMaxGroups;
+  a.tile_k0 = m->tile_k0;
+  a.k8_total = (delta ? m->wd_stride : d.k_pad) / 8;
+  a.n_chunk = d.n_chunk; a.n_kb = (a.k8_total + 3) / 4; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
+  a.n_blue = d.n_blue; a.n_blue_pad = m->n_blue_pad; a.uv_len = m->uv_len;
+  {
+    int lo_min = m->h_lo[0], hi_max = m->h_hi[0];
+    for (int f = 1; f < d.n_filt; ++f) { lo_min = std::min(lo_min, m->h_lo[f]); hi_max = std::max(hi_max, m->h_hi[f]); }
+    const int wpb = 8;
+    sb2::tile_range_kernel<<<(a.n_tiles + wpb - 1) / wpb, wpb * 32, 0, st>>>(m->g_m, m->g_orig, a.n_tiles, lo_min, hi_max, d.n_lam,
+                                                                           sb2::kBN / d.n_comp, spec_out ? 1 : 0, m->tile_range);
+    STAGE_CHECK("tile_range_kernel", st);
+    a.tile_range = m->tile_range;
+  }
   a.kappa = m->kappa; a.filt_uv = reinterpret_cast<const float2*>(m->filt_uv); a.igm = m->igm;
   a.g_m = m->g_m; a.g_beta = m->g_beta; a.g_gamma = m->g_gamma; a.g_taut = m->g_taut; a.g_scale = m->g_scale; a.g_ca = m->g_ca;
   a.g_cb = m->g_cb; a.g_orig = m->g_orig; a.g_mscale = m->g_mscale; a.g_trunc = m->g_trunc;
@@ -383,7 +527,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
     a.filt_su[f] = m->h_su[f]; a.filt_sdv[f] = m->h_sdv[f];
   }
   const int grid = a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm;
-  rc = launch_synth(m, a, grid, st);
+  rc = launch_synth(m, a, grid, delta, st);
   cudaEventRecord(m->ev[3], st);
   m->ev_valid = (rc == SB2_OK);
   return rc;

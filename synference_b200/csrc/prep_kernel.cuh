@@ -14,7 +14,10 @@
 namespace sb2 {
 
 struct PrepModel {
-  int n_age, n_z, K, k_pad, n_lam, n_filt, n_blue, n_lines, variant, igm_on;
+  int n_age, na_pad, n_z, K, k_pad, n_lam, n_filt, n_blue, n_lines, variant, igm_on;
+  int delta;     // 1: DeltaConstant batch grouped by metallicity bracket -> weights row holds only the
+                 //    two bracketing grid metallicities: [sf*(1-f) (na_pad) | sf*f (na_pad)], stride w_stride
+  int w_stride;  // floats per weights row (k_pad, or 2*na_pad in delta mode)
   const double* ages;      // [n_age] yr
   const double* edges;     // [n_age] e_0..e_{n_age-1} (bin a spans [e_a, e_{a+1}], a < n_age-1)
   const double* zmet;      // [n_z]
@@ -84,6 +87,20 @@ __device__ __forceinline__ double hermite_lut(const double* y, const double* dy,
   return h00 * y[k] + h10 * ds * dy[k] + h01 * y[k + 1] + h11 * ds * dy[k + 1];
 }
 
+// DeltaConstant: all mass is shared between the two bracketing grid metallicities.
+// Returns the bracket j in [0, n_z-2] and the weight f of metallicity j+1 (1-f goes to j); values
+// outside the grid clamp to the end bin.  Used by the grouping keys and by prep_kernel (same result).
+__device__ __forceinline__ int delta_bracket(const double* __restrict__ zx, int n_z, double zv, double* f_out) {
+  int j = 0;  // largest j with zx[j] <= zv
+  for (int i = 1; i < n_z; ++i) j = (zx[i] <= zv) ? i : j;
+  double f;
+  if (zv <= zx[0]) { j = 0; f = 0.0; }
+  else if (zv >= zx[n_z - 1]) { j = n_z - 2; f = 1.0; }
+  else f = (zv - zx[j]) / (zx[j + 1] - zx[j]);
+  *f_out = f;
+  return j;
+}
+
 // Phi(uh) - Phi(ul) evaluated in whichever tail avoids cancellation.
 __device__ __forceinline__ double phi_diff(double ul, double uh) {
   const double r = 0.70710678118654752440;
@@ -150,10 +167,11 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
   double* prow = zd + M.n_z;
   const unsigned FULL = 0xffffffffu;
 
-  if (t >= P.n) {  // padding row of the last tile
-    for (int k = lane; k < M.k_pad; k += 32) {
-      O.w_hi[t * M.k_pad + k] = 0.f;
-      O.w_lo[t * M.k_pad + k] = 0.f;
+  const long long g = perm ? (long long)perm[t] : (t < P.n ? t : -1);
+  if (g < 0) {  // padding row (end of a tile / of a metallicity group)
+    for (int k = lane; k < M.w_stride; k += 32) {
+      O.w_hi[t * M.w_stride + k] = 0.f;
+      O.w_lo[t * M.w_stride + k] = 0.f;
     }
     if (M.igm_on && lane < 13) O.zpow[(size_t)lane * n_pad + t] = (lane < 12) ? 1.0 : 0.0;
     if (lane == 0) {
@@ -163,7 +181,6 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
     return;
   }
 
-  const long long g = perm ? (long long)perm[t] : t;
   const double z = P.redshift[g];
   const double zp = 1.0 + z;
   const double s = log1p(z);
@@ -200,14 +217,11 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
   const bool logz = (P.zd_type == SB2_ZD_DELTA_LOG10 || P.zd_type == SB2_ZD_NORMAL_LOG10);
   const double* zx = logz ? M.log10zmet : M.zmet;
   double zpart = 0.0;
+  int zj = 0;
+  double zf = 0.0;
   if (P.zd_type == SB2_ZD_DELTA_LINEAR || P.zd_type == SB2_ZD_DELTA_LOG10) {
-    int j = 0;  // largest j with zx[j] <= zv
-    for (int i = 1; i < M.n_z; ++i) j = (zx[i] <= zv) ? i : j;
-    double f = 0.0;
-    if (zv <= zx[0]) { j = 0; f = 0.0; }
-    else if (zv >= zx[M.n_z - 1]) { j = M.n_z - 1; f = 0.0; }
-    else f = (zv - zx[j]) / (zx[j + 1] - zx[j]);
-    for (int i = lane; i < M.n_z; i += 32) zd[i] = (i == j) ? 1.0 - f : ((i == j + 1) ? f : 0.0);
+    if (M.n_z >= 2) zj = delta_bracket(zx, M.n_z, zv, &zf);
+    for (int i = lane; i < M.n_z; i += 32) zd[i] = (i == zj) ? 1.0 - zf : ((i == zj + 1) ? zf : 0.0);
     zpart = 1.0;
   } else {
     for (int i = lane; i < M.n_z; i += 32) {
@@ -221,21 +235,32 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
   __syncwarp();
   const double inv = inv_sf / zpart;
 
-  // ---- weights row (TF32 hi/lo split, K index = iz*n_age + ia) -----------------------------
-  for (int iz = 0; iz < M.n_z; ++iz) {
+  // ---- weights row (TF32 hi/lo split) ------------------------------------------------------
+  if (M.delta) {  // columns [0, na_pad): metallicity zj, [na_pad, 2 na_pad): zj+1 (grid columns zj*na_pad + k)
+    for (int k = lane; k < M.w_stride; k += 32) {
+      double w = 0.0;
+      if (k < M.n_age) w = sf[k] * ((1.0 - zf) * inv);
+      else if (k >= M.na_pad && k - M.na_pad < M.n_age) w = sf[k - M.na_pad] * (zf * inv);
+      const float hi = to_tf32_rna((float)w);
+      O.w_hi[t * M.w_stride + k] = hi;
+      O.w_lo[t * M.w_stride + k] = to_tf32_rna((float)(w - (double)hi));
+    }
+  } else {
+  for (int iz = 0; iz < M.n_z; ++iz) {  // column k = iz*na_pad + ia
     const double zw = zd[iz] * inv;
-    for (int a = lane; a < M.n_age; a += 32) {
-      const int k = iz * M.n_age + a;
-      const double w = sf[a] * zw;
+    for (int a = lane; a < M.na_pad; a += 32) {
+      const int k = iz * M.na_pad + a;
+      const double w = (a < M.n_age) ? sf[a] * zw : 0.0;
       const float hi = to_tf32_rna((float)w);
       O.w_hi[t * M.k_pad + k] = hi;
       O.w_lo[t * M.k_pad + k] = to_tf32_rna((float)(w - (double)hi));
-      if (O.w_f64) O.w_f64[g * M.K + k] = w;
+      if (O.w_f64 && a < M.n_age) O.w_f64[g * M.K + iz * M.n_age + a] = w;
     }
   }
-  for (int k = M.K + lane; k < M.k_pad; k += 32) {
+  for (int k = M.n_z * M.na_pad + lane; k < M.k_pad; k += 32) {
     O.w_hi[t * M.k_pad + k] = 0.f;
     O.w_lo[t * M.k_pad + k] = 0.f;
+  }
   }
 
   // ---- per-galaxy scalars -------------------------------------------------------------------
@@ -283,7 +308,7 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
 constexpr int kIgmStrip = 64;
 
 __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __restrict__ zpow, float* __restrict__ igm,
-                                                  long long n_pad) {
+                                                  int nb_pad, long long n_pad) {
   __shared__ double s_thr[3 * 64];
   __shared__ double s_pre[5 * 64];
   const int np1 = M.n_lines + 1;
@@ -299,6 +324,9 @@ __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __r
   const double zp = 1.0 + z;
   const int i0 = blockIdx.y * kIgmStrip;
   const int i1 = min(nb, i0 + kIgmStrip);
+  float* out = igm + ((size_t)blockIdx.x * nb_pad) * 128 + threadIdx.x;
+  for (int i = max(i0, nb); i < min(nb_pad, i0 + kIgmStrip); ++i) out[(size_t)i * 128] = 1.f;  // padding rows
+  if (i0 >= nb) return;
   // lines (sorted by decreasing wavelength) still below the regime thresholds at the strip's first bin
   int n1 = 0, n2 = 0, nd = 0;
   {
@@ -310,7 +338,6 @@ __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __r
       if (s_thr[2 * 64 + nd + step - 1] > xl) nd += step;
     }
   }
-  float* out = igm + ((size_t)blockIdx.x * nb) * 128 + threadIdx.x;
   for (int i = i0; i < i1; ++i) {
     const double xl = __ldg(M.bin_pow + 7 * nb + i) * zp;  // lam_obs / 911.8
     while (n1 > 0 && !(s_thr[0 * 64 + n1 - 1] > xl)) --n1;

@@ -1,6 +1,6 @@
 // Contraction + fused epilogue kernel (the hot path of the hot path).
 //
-//   S[g, lam] = sum_k W[g, k] * G[k, lam]      (N_gal x K) . (K x N_lam), K = n_age*n_z
+//   S[g, lam] = sum_k W[g, k] * G[k, lam]      (N_gal x K) . (K x N_lam)
 //
 // is the one dense contraction of the reference path (grid-weighted spectral sum, SURVEY A4;
 // Pipeline.run at library.py:2619).  It runs on the 5th-gen tensor cores as 3xTF32
@@ -21,8 +21,12 @@
 //
 // A wavelength chunk is 256 accumulator columns: 256 wavelengths for one spectral component, or
 // 128 wavelengths x 2 components (attenuated | unattenuated) when the emission recipe needs both.
-// Galaxies arrive sorted by redshift so the filter windows of a warp's 32 galaxies nearly coincide.
+// Tiles hold galaxies of one metallicity bracket in redshift order (capi.cu: group_*_kernel), so
+//   * a DeltaConstant tile multiplies only the 2*n_age_pad grid columns it can touch (tile_k0),
+//   * the filter windows of a warp's 32 galaxies coincide (warp-uniform window tests), and
+//   * wavelength chunks no filter of the tile reaches are skipped altogether (tile_range).
 #pragma once
+#include <climits>
 #include "ptx.cuh"
 
 namespace sb2 {
@@ -36,12 +40,18 @@ constexpr int kBBytes = kBN * kBK * 4;         // 32 KiB
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // hi + lo of both operands = 96 KiB
 constexpr int kSynthThreads = 256;
 constexpr int kMaxFilt = 32;
+constexpr int kUvPad = 32;       // zero entries on both sides of every filter's (U, V) table
+constexpr int kFastSpread = 2;   // max (m_max - m_min) within a warp for the unclamped table reads
 
 struct SynthArgs {
-  int n_gal, n_tiles, n_chunk, n_kb, n_lam, n_filt, n_blue, uv_len;
-  const float* kappa;   // [n_chunk * lam_per_chunk], zero padded
-  const float2* filt_uv;
-  const float* igm;     // [n_tiles][n_blue][128]
+  int n_gal, n_tiles, n_chunk, n_kb, n_lam, n_filt, n_blue, n_blue_pad, uv_len;
+  int k8_total;              // K/8 MMA steps actually needed (the last k-block may be partial)
+  const int* n_tiles_dev;    // actual tile count (<= n_tiles) when the batch was grouped on device, else nullptr
+  const int* tile_k0;        // [n_tiles] first grid column (k) of each tile's weights, nullptr: 0
+  const int2* tile_range;    // [n_tiles] first / last wavelength chunk any filter of the tile needs, nullptr: all
+  const float* kappa;        // [n_chunk * lam_per_chunk], zero padded
+  const float2* filt_uv;     // padded tables, uv_len entries
+  const float* igm;          // [n_tiles][n_blue_pad][128]
   const int* g_m;
   const float* g_beta;   // blend weight of the filter sample n+1
   const float* g_gamma;  // 1 - beta, rounded from float64 (no cancellation at the band edges)
@@ -55,16 +65,32 @@ struct SynthArgs {
   float* out_base;
   double* out_scaled;
   float* out_spec;
-  int filt_lo[kMaxFilt], filt_hi[kMaxFilt], filt_off[kMaxFilt];
+  int filt_lo[kMaxFilt], filt_hi[kMaxFilt], filt_off[kMaxFilt];  // filt_off: start of the PADDED table
   float filt_su[kMaxFilt], filt_sdv[kMaxFilt];
 };
 
-template <int kComp, int kNF>
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 r;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+  return r;
+}
+// acc.{x,y} += s * uv.{x,y}   (one FFMA2 on sm_100)
+__device__ __forceinline__ void ffma2_bcast(float2& acc, float s, float2 uv) {
+  uint64_t a, b, c;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(uv.x), "f"(uv.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(c) : "l"(a), "l"(b), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
+}
+
+template <int kComp, int kNF, bool kSpec>
 __global__ void __launch_bounds__(kSynthThreads, 1)
 synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
              const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo,
              const __grid_constant__ SynthArgs A) {
   constexpr int kLch = kBN / kComp;  // wavelengths per chunk
+  constexpr int kSub = kLch / 32;    // 32-wavelength sub-chunks per chunk
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [stages][W_hi | W_lo | G_hi | G_lo], filter table, barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -95,21 +121,25 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = A.n_tiles_dev ? min(A.n_tiles, __ldg(A.n_tiles_dev)) : A.n_tiles;
+  const int c_all_last = A.n_chunk - 1;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < A.n_chunk; ++c) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int k0 = A.tile_k0 ? __ldg(A.tile_k0 + tile) : 0;
+        const int2 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int2(0, c_all_last);
+        for (int c = cr.x; c <= cr.y; ++c) {
           for (int kb = 0; kb < A.n_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * kStageBytes;
             mbar_expect_tx(&full_bar[stage], kStageBytes);
             tma_load_2d(st, &tm_w_hi, &full_bar[stage], kb * kBK, tile * kBM, kEvictNormal);
             tma_load_2d(st + kABytes, &tm_w_lo, &full_bar[stage], kb * kBK, tile * kBM, kEvictNormal);
-            tma_load_2d(st + 2 * kABytes, &tm_g_hi, &full_bar[stage], kb * kBK, c * kBN, kEvictLast);
-            tma_load_2d(st + 2 * kABytes + kBBytes, &tm_g_lo, &full_bar[stage], kb * kBK, c * kBN, kEvictLast);
+            tma_load_2d(st + 2 * kABytes, &tm_g_hi, &full_bar[stage], k0 + kb * kBK, c * kBN, kEvictLast);
+            tma_load_2d(st + 2 * kABytes + kBBytes, &tm_g_lo, &full_bar[stage], k0 + kb * kBK, c * kBN, kEvictLast);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -120,8 +150,9 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(kBM, kBN);
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < A.n_chunk; ++c, ++it) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int2 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int2(0, c_all_last);
+        for (int c = cr.x; c <= cr.y; ++c, ++it) {
           const uint32_t buf = it & 1u;
           mbar_wait(&tempty_bar[buf], ((it >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
           tc_fence_after();
@@ -130,8 +161,10 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(smem + stage * kStageBytes);
+            const int k4n = min(kBK / 8, A.k8_total - kb * (kBK / 8));
 #pragma unroll
             for (int k4 = 0; k4 < kBK / 8; ++k4) {
+              if (k4 >= k4n) break;
               const uint64_t a_hi = make_kmajor_sw128_desc(st + k4 * 32);
               const uint64_t a_lo = make_kmajor_sw128_desc(st + kABytes + k4 * 32);
               const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * kABytes + k4 * 32);
@@ -151,53 +184,70 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
     // ===================================================================== fused epilogue
     const int et = threadIdx.x - 128;            // galaxy within tile == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t uv_base = smem_u32(s_uv);
     const unsigned FULL = 0xffffffffu;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int2 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int2(0, c_all_last);
       const int row = tile * kBM + et;
-      const int m = A.g_m[row];
-      const float beta = A.g_beta[row], gamma = A.g_gamma[row], taut = A.g_taut[row], ca = A.g_ca[row], cb = A.g_cb[row];
       const int orig = A.g_orig[row];
+      int m = A.g_m[row];
+      const float beta = A.g_beta[row], gamma = A.g_gamma[row], ntaut = -A.g_taut[row];
+      const float ca = A.g_ca[row], cb = A.g_cb[row];
       const float scale = A.g_scale[row];
-      int mmin = m, mmax = m;
+      // redshift-shift range of this warp's real galaxies (padding rows follow the others)
+      int mmin = orig >= 0 ? m : INT_MAX, mmax = orig >= 0 ? m : INT_MIN;
 #pragma unroll
       for (int o = 16; o; o >>= 1) {
         mmin = min(mmin, __shfl_xor_sync(FULL, mmin, o));
         mmax = max(mmax, __shfl_xor_sync(FULL, mmax, o));
       }
-      float acc[kNF];
+      if (mmin > mmax) mmin = mmax = 0;
+      if (orig < 0) m = mmin;
+      const bool fast = (mmax - mmin) <= kFastSpread;
+      float2 acc[kNF];
 #pragma unroll
-      for (int f = 0; f < kNF; ++f) acc[f] = 0.f;
+      for (int f = 0; f < kNF; ++f) acc[f] = make_float2(0.f, 0.f);
 
-      for (int c = 0; c < A.n_chunk; ++c, ++it) {
+      for (int c = cr.x; c <= cr.y; ++c, ++it) {
+        // which filters overlap which 32-wavelength sub-chunk of this chunk: lane `sub` works it out for sub-chunk `sub`
+        unsigned cmask = 0u;
+        {
+          const int i0s = c * kLch + (lane & (kSub - 1)) * 32;
+#pragma unroll
+          for (int f = 0; f < kNF; ++f)
+            if (f < A.n_filt && i0s + mmin <= A.filt_hi[f] && i0s + 31 + mmax >= A.filt_lo[f] - 1) cmask |= 1u << f;
+        }
         const uint32_t buf = it & 1u;
         mbar_wait(&tfull_bar[buf], (it >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_acc = tmem_base + lane_base + buf * kBN;
 #pragma unroll 1
-        for (int sub = 0; sub < kLch / 32; ++sub) {
+        for (int sub = 0; sub < kSub; ++sub) {
           const int i0 = c * kLch + sub * 32;
-          const bool last_sub = (sub == kLch / 32 - 1) || (i0 + 32 >= A.n_lam);
+          const bool last_sub = (sub == kSub - 1) || (i0 + 32 >= A.n_lam);
           float s[32];
           {
             uint32_t v[32];
             tmem_ld_32x32b_x32(t_acc + sub * 32, v);
+            float kk[32];
+            const float4* kp = reinterpret_cast<const float4*>(A.kappa + i0);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 k4 = __ldg(kp + j4);
+              kk[4 * j4] = k4.x; kk[4 * j4 + 1] = k4.y; kk[4 * j4 + 2] = k4.z; kk[4 * j4 + 3] = k4.w;
+            }
             if constexpr (kComp == 2) {
               uint32_t u[32];
               tmem_ld_32x32b_x32(t_acc + kLch + sub * 32, u);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float att = ex2_approx(-taut * __ldg(A.kappa + i0 + j));
-                s[j] = ca * (__uint_as_float(v[j]) * att) + cb * __uint_as_float(u[j]);
-              }
+              for (int j = 0; j < 32; ++j)
+                s[j] = ca * (__uint_as_float(v[j]) * ex2_approx(ntaut * kk[j])) + cb * __uint_as_float(u[j]);
             } else {
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float att = ex2_approx(-taut * __ldg(A.kappa + i0 + j));
-                s[j] = ca * (__uint_as_float(v[j]) * att);
-              }
+              for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]) * ex2_approx(ntaut * kk[j]);  // ca goes into the final scale
             }
           }
           if (last_sub) {  // all TMEM reads of this accumulator are done: hand it back to the MMA warp
@@ -205,47 +255,69 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
           }
-          if (i0 < A.n_blue) {
-            const float* ig = A.igm + ((size_t)tile * A.n_blue + i0) * 128 + et;
+          if (i0 < A.n_blue) {  // rows [n_blue, n_blue_pad) of the table hold 1
+            const float* ig = A.igm + ((size_t)tile * A.n_blue_pad + i0) * 128 + et;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (i0 + j < A.n_blue) s[j] *= __ldg(ig + j * 128);
+            for (int j = 0; j < 32; ++j) s[j] *= __ldg(ig + j * 128);
           }
-          if (A.out_spec != nullptr && orig >= 0) {
+          if constexpr (kSpec) {
+            if (A.out_spec != nullptr && orig >= 0) {
+              const float sc = (kComp == 1) ? scale * ca : scale;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (i0 + j < A.n_lam) A.out_spec[(size_t)orig * A.n_lam + i0 + j] = s[j] * scale;
+              for (int j = 0; j < 32; ++j)
+                if (i0 + j < A.n_lam) A.out_spec[(size_t)orig * A.n_lam + i0 + j] = s[j] * sc;
+            }
           }
-          // filter numerators: num_f += s_i * (gamma * U_f[n] + beta * V_f[n]),  n = i + m
+          // filter numerators: (numU_f, numV_f) += s_i * (U_f[n], V_f[n]),  n = i + m
+          const unsigned fm = __shfl_sync(FULL, cmask, sub);
+          if (fm != 0u) {
+            if (fast) {
 #pragma unroll
-          for (int f = 0; f < kNF; ++f) {
-            if (f < A.n_filt) {
-              const int lo = A.filt_lo[f], hi = A.filt_hi[f];
-              if (i0 + mmin <= hi && i0 + 31 + mmax >= lo - 1) {  // warp-uniform
-                const float2* tab = s_uv + A.filt_off[f];
-                const int kmax = hi - lo + 3;
-                const int k0 = i0 + m - (lo - 2);
-                float a = acc[f];
+              for (int f = 0; f < kNF; ++f) {
+                if ((fm >> f) & 1u) {
+                  // padded table entry p <-> n = filt_lo - 2 - kUvPad + p ; all 32 reads stay inside the padding
+                  const uint32_t addr = uv_base + (uint32_t)(A.filt_off[f] + kUvPad + i0 + m - (A.filt_lo[f] - 2)) * 8u;
+                  float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float2 uv = tab[min(max(k0 + j, 0), kmax)];
-                  a = fmaf(s[j], fmaf(beta, uv.y, gamma * uv.x), a);
+                  for (int j = 0; j < 32; j += 2) {
+                    ffma2_bcast(t0, s[j], lds_f2(addr + j * 8));
+                    ffma2_bcast(t1, s[j + 1], lds_f2(addr + j * 8 + 8));
+                  }
+                  acc[f].x += t0.x + t1.x;
+                  acc[f].y += t0.y + t1.y;
                 }
-                acc[f] = a;
+              }
+            } else {
+#pragma unroll
+              for (int f = 0; f < kNF; ++f) {
+                if ((fm >> f) & 1u) {
+                  const int pmax = A.filt_hi[f] - A.filt_lo[f] + 3 + 2 * kUvPad;
+                  const int p0 = kUvPad + i0 + m - (A.filt_lo[f] - 2);
+                  const uint32_t tab = uv_base + (uint32_t)A.filt_off[f] * 8u;
+                  float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);  // same association as the fast path
+#pragma unroll
+                  for (int j = 0; j < 32; j += 2) {
+                    ffma2_bcast(t0, s[j], lds_f2(tab + (uint32_t)min(max(p0 + j, 0), pmax) * 8u));
+                    ffma2_bcast(t1, s[j + 1], lds_f2(tab + (uint32_t)min(max(p0 + j + 1, 0), pmax) * 8u));
+                  }
+                  acc[f].x += t0.x + t1.x;
+                  acc[f].y += t0.y + t1.y;
+                }
               }
             }
           }
           if (last_sub) break;
         }
       }
-      // ---- finalize: flux_f = num_f / den_f * scale ; den_f = gamma * su_f + beta * sv_f
+      // ---- finalize: flux_f = (gamma numU + beta numV) / (gamma su_f + beta sv_f) * scale
       if (orig >= 0) {
         const unsigned trunc = A.g_trunc[row];
         const double mscale = A.g_mscale[row];
+        const float sc = (kComp == 1) ? scale * ca : scale;
 #pragma unroll
         for (int f = 0; f < kNF; ++f) {
           if (f < A.n_filt) {
-            float flux = acc[f] / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * scale;
+            float flux = fmaf(beta, acc[f].y, gamma * acc[f].x) / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * sc;
             if ((trunc >> f) & 1u) flux = __int_as_float(0x7fc00000);
             if (A.out_base) A.out_base[(size_t)orig * A.n_filt + f] = flux;
             if (A.out_scaled) A.out_scaled[(size_t)orig * A.n_filt + f] = (double)flux * mscale;
@@ -260,6 +332,35 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// First / last wavelength chunk that any filter of a tile's galaxies can reach (one warp per tile).
+__global__ void tile_range_kernel(const int* __restrict__ g_m, const int* __restrict__ g_orig, int n_tiles,
+                                  int lo_min, int hi_max, int n_lam, int lam_per_chunk, int all, int2* out) {
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  int mmin = INT_MAX, mmax = INT_MIN;
+  for (int r = lane; r < kBM; r += 32) {
+    const int row = tile * kBM + r;
+    if (g_orig[row] >= 0) {
+      mmin = min(mmin, g_m[row]);
+      mmax = max(mmax, g_m[row]);
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    mmin = min(mmin, __shfl_xor_sync(0xffffffffu, mmin, o));
+    mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+  }
+  if (lane == 0) {
+    int2 r;
+    if (mmin > mmax) r = make_int2(0, -1);  // padding only
+    else if (all) r = make_int2(0, (n_lam - 1) / lam_per_chunk);
+    else {
+      const int i_lo = max(0, lo_min - 1 - mmax), i_hi = min(n_lam - 1, hi_max - mmin);
+      r = (i_hi < i_lo) ? make_int2(0, -1) : make_int2(i_lo / lam_per_chunk, i_hi / lam_per_chunk);
+    }
+    out[tile] = r;
   }
 }
 

@@ -112,7 +112,8 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
     n_comp = len(comps)
     na, nz = grid.log10ages.size, grid.metallicity.size
     k = na * nz
-    k_pad = (k + 31) // 32 * 32
+    na_pad = (na + 3) // 4 * 4          # every metallicity's columns start 16-byte aligned (TMA box origin)
+    k_pad = (na_pad * nz + 31) // 32 * 32
     lch = CHUNK_COLS // n_comp
     n_chunk = (n_lam + lch - 1) // lch
     grid_scale = float(max(c.max() for c in comps))
@@ -120,11 +121,10 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         raise ValueError("grid spectra must be finite and not all zero")
     gt = np.zeros((n_chunk, n_comp, lch, k_pad), dtype=np.float64)
     for ci, comp in enumerate(comps):
-        # (age, Z, lam) -> (lam, Z, age) -> rows lam, columns k = iz*n_age + ia
-        flat = np.transpose(comp, (2, 1, 0)).reshape(n_lam, k) / grid_scale
-        pad = np.zeros((n_chunk * lch, k))
-        pad[:n_lam] = flat
-        gt[:, ci, :, :k] = pad.reshape(n_chunk, lch, k)
+        # (age, Z, lam) -> (lam, Z, age) -> rows lam, columns k = iz*na_pad + ia
+        pad = np.zeros((n_chunk * lch, nz, na_pad))
+        pad[:n_lam, :, :na] = np.transpose(comp, (2, 1, 0)) / grid_scale
+        gt[:, ci, :, :nz * na_pad] = pad.reshape(n_chunk, lch, nz * na_pad)
     gt = gt.reshape(n_chunk * CHUNK_COLS, k_pad)
     gt_hi, gt_lo = tf32_split(gt)
     kap = None
@@ -161,7 +161,7 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         uv.append(np.stack([u, v], 1))
     uv = np.concatenate(uv, 0).astype(np.float32)
     tables = dict(
-        n_age=na, n_z=nz, n_lam=n_lam, n_comp=n_comp, n_filt=len(lo_l), k_pad=k_pad, n_chunk=n_chunk,
+        n_age=na, n_z=nz, n_lam=n_lam, n_comp=n_comp, n_filt=len(lo_l), n_age_pad=na_pad, k_pad=k_pad, n_chunk=n_chunk,
         log10ages=np.ascontiguousarray(grid.log10ages, dtype=np.float64),
         metallicities=np.ascontiguousarray(grid.metallicity, dtype=np.float64),
         gt_hi=gt_hi, gt_lo=gt_lo, grid_scale=grid_scale, kappa=kap, lam0=float(lam[0]), q=q,
@@ -208,7 +208,7 @@ class SynthEngine:
             keep.append(a)
             return a.ctypes.data_as(C.POINTER(ctype))
 
-        for name in ("n_age", "n_z", "n_lam", "n_comp", "n_filt", "k_pad", "n_chunk", "interp_variant"):
+        for name in ("n_age", "n_z", "n_lam", "n_comp", "n_filt", "n_age_pad", "k_pad", "n_chunk", "interp_variant"):
             setattr(d, name, int(t[name]))
         d.log10ages, d.metallicities = ptr(t["log10ages"], C.c_double), ptr(t["metallicities"], C.c_double)
         d.gt_hi, d.gt_lo = ptr(t["gt_hi"], C.c_float), ptr(t["gt_lo"], C.c_float)
