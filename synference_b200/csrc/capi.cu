@@ -177,7 +177,7 @@ struct sb2_model {
   int *perm_pad = nullptr, *grp = nullptr, *tile_k0 = nullptr;  // grp: counts[64] | cum[64] | pad_start[64] | n_tiles
   int uv_len = 0;      // entries of the padded (U, V) tables
   int n_blue_pad = 0;  // IGM rows per tile (n_blue rounded up to 32; the extra rows hold 1)
-  int2* tile_range = nullptr;
+  int4* tile_range = nullptr;
   int wd_stride = 0;  // floats per weights row in DeltaConstant (bracket-grouped) mode; 0: mode unavailable
   CUtensorMap tm_wd_hi, tm_wd_lo;
   double* g_mscale = nullptr;
@@ -317,7 +317,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(w_hi, np * d->k_pad * 4);
   AL(w_lo, np * d->k_pad * 4);
   AL(igm, (np / 128) * (size_t)(m->n_blue_pad > 0 ? m->n_blue_pad : 1) * 128 * 4);
-  AL(tile_range, (np / 128) * sizeof(int2));
+  AL(tile_range, (np / 128) * sizeof(int4));
   AL(g_m, np * 4); AL(g_orig, np * 4); AL(perm, np * 4); AL(idx, np * 4);
   AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
   AL(keys, np * 4); AL(keys_sorted, np * 4); AL(perm_pad, np * 4); AL(tile_k0, (np / 128) * 4); AL(grp, (3 * kMaxGroups + 1) * 4);
@@ -431,7 +431,7 @@ long long padded_rows(const sb2_model* m, long long n, bool delta) {
 }
 
 // group by (metallicity bracket, redshift) -> perm_pad ; prep kernel
-int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, cudaStream_t st) {
+int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool all_lam, cudaStream_t st) {
   const long long n = p->n;
   const bool delta = sorted && delta_mode(m, p);
   const long long n_pad = padded_rows(m, n, delta);
@@ -466,13 +466,24 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, cuda
   O.w_hi = m->w_hi; O.w_lo = m->w_lo; O.w_f64 = w_f64; O.igm = m->igm; O.g_m = m->g_m; O.g_beta = m->g_beta; O.g_gamma = m->g_gamma;
   O.g_taut = m->g_taut; O.g_scale = m->g_scale; O.g_ca = m->g_ca; O.g_cb = m->g_cb; O.g_orig = m->g_orig;
   O.g_mscale = m->g_mscale; O.g_trunc = m->g_trunc; O.zpow = m->zpow;
-  const size_t sh = (size_t)sb2::kPrepWarps * (M.n_age + M.n_z + SB2_SFH_ROW) * sizeof(double);
-  const unsigned blocks = (unsigned)((n_pad + sb2::kPrepWarps - 1) / sb2::kPrepWarps);
-  sb2::prep_kernel<<<blocks, sb2::kPrepWarps * 32, sh, st>>>(M, P, O, perm, n_pad);
-  STAGE_CHECK("prep_kernel", st);
+  if (!w_f64) {  // the parity hook (sb2_build_weights) needs the weights only
+    sb2::scalars_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(M, P, O, perm, n_pad);
+    STAGE_CHECK("scalars_kernel", st);
+    const sb2_model_desc& d = m->d;
+    int lo_min = m->h_lo[0], hi_max = m->h_hi[0];
+    for (int f = 1; f < d.n_filt; ++f) { lo_min = std::min(lo_min, m->h_lo[f]); hi_max = std::max(hi_max, m->h_hi[f]); }
+    const int wpb = 8, n_tiles = (int)(n_pad / 128);
+    sb2::tile_range_kernel<<<(n_tiles + wpb - 1) / wpb, wpb * 32, 0, st>>>(m->g_m, m->g_orig, n_tiles, lo_min, hi_max, d.n_lam,
+                                                                         sb2::kBN / d.n_comp, all_lam ? 1 : 0, m->tile_range);
+    STAGE_CHECK("tile_range_kernel", st);
+  }
+  const size_t sh = sb2::weights_smem_doubles(M.n_age, M.n_z) * sizeof(double);
+  const unsigned blocks = (unsigned)((n_pad + sb2::kWGal - 1) / sb2::kWGal);
+  sb2::weights_kernel<<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, P, O, perm, n_pad);
+  STAGE_CHECK("weights_kernel", st);
   if (M.igm_on && !w_f64) {
     dim3 grid((unsigned)(n_pad / 128), (unsigned)((m->n_blue_pad + sb2::kIgmStrip - 1) / sb2::kIgmStrip));
-    sb2::igm_kernel<<<grid, 128, 0, st>>>(M, m->zpow, m->igm, m->n_blue_pad, n_pad);
+    sb2::igm_kernel<<<grid, 128, 0, st>>>(M, m->zpow, m->igm, m->tile_range, m->n_blue_pad, n_pad);
     STAGE_CHECK("igm_kernel", st);
   }
   cudaEventRecord(m->ev[2], st);
@@ -488,7 +499,7 @@ int sb2_build_weights(sb2_model* m, const sb2_params* p, double* w_out, void* st
   if (rc != SB2_OK) return rc;
   if (!w_out) return fail(SB2_ERR_INVALID, "w_out is null");
   CU_TRY(cudaSetDevice(m->device));
-  return run_prep(m, p, w_out, false, (cudaStream_t)stream);
+  return run_prep(m, p, w_out, false, false, (cudaStream_t)stream);
 }
 
 int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, double* flux_scaled,
@@ -498,7 +509,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   if (!flux_base && !flux_scaled && !spec_out) return fail(SB2_ERR_INVALID, "no output requested");
   CU_TRY(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = run_prep(m, p, nullptr, true, st)) != SB2_OK) return rc;
+  if ((rc = run_prep(m, p, nullptr, true, spec_out != nullptr, st)) != SB2_OK) return rc;
   const sb2_model_desc& d = m->d;
   sb2::SynthArgs a{};
   const bool delta = delta_mode(m, p);
@@ -509,15 +520,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.k8_total = (delta ? m->wd_stride : d.k_pad) / 8;
   a.n_chunk = d.n_chunk; a.n_kb = (a.k8_total + 3) / 4; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
   a.n_blue = d.n_blue; a.n_blue_pad = m->n_blue_pad; a.uv_len = m->uv_len;
-  {
-    int lo_min = m->h_lo[0], hi_max = m->h_hi[0];
-    for (int f = 1; f < d.n_filt; ++f) { lo_min = std::min(lo_min, m->h_lo[f]); hi_max = std::max(hi_max, m->h_hi[f]); }
-    const int wpb = 8;
-    sb2::tile_range_kernel<<<(a.n_tiles + wpb - 1) / wpb, wpb * 32, 0, st>>>(m->g_m, m->g_orig, a.n_tiles, lo_min, hi_max, d.n_lam,
-                                                                           sb2::kBN / d.n_comp, spec_out ? 1 : 0, m->tile_range);
-    STAGE_CHECK("tile_range_kernel", st);
-    a.tile_range = m->tile_range;
-  }
+  a.tile_range = m->tile_range;
   a.kappa = m->kappa; a.filt_uv = reinterpret_cast<const float2*>(m->filt_uv); a.igm = m->igm;
   a.g_m = m->g_m; a.g_beta = m->g_beta; a.g_gamma = m->g_gamma; a.g_taut = m->g_taut; a.g_scale = m->g_scale; a.g_ca = m->g_ca;
   a.g_cb = m->g_cb; a.g_orig = m->g_orig; a.g_mscale = m->g_mscale; a.g_trunc = m->g_trunc;

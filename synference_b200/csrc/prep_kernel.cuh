@@ -1,6 +1,7 @@
-// Weight construction ("prep") kernel: one warp per galaxy, float64.
+// Weight construction ("prep") kernels, float64: scalars_kernel (one thread per galaxy), weights_kernel
+// (one thread per (galaxy, age-bin edge)), igm_kernel (one thread per galaxy, strips of wavelength bins).
 //
-// For the galaxy in sorted slot t it produces everything the contraction kernel needs:
+// For the galaxy in grouped slot t they produce everything the contraction kernel needs:
 //   * SFZH weights  w[iz*n_age + ia] = sf[ia] * zd[iz]  (Stars.__init__ in the
 //     reference, library.py:1372-1379), written as a TF32 hi/lo pair (3xTF32 operand A);
 //   * the Inoue+14 transmission row exp(-tau(z, lam_i (1+z))) for the bins blueward of Ly-alpha;
@@ -8,6 +9,7 @@
 //     dust exponent scale, flux scale (1+z)/(4 pi d_L^2) from the cosmology table, mass scale.
 // HBM-bound by design: algorithmic bytes per galaxy = 2 * 4 * k_pad (weights) + 4 * n_blue (IGM).
 #pragma once
+#include <climits>
 #include "ptx.cuh"
 #include "../../include/synference_b200.h"
 
@@ -108,193 +110,310 @@ __device__ __forceinline__ double phi_diff(double ul, double uh) {
   return 0.5 * (erfc(-uh * r) - erfc(-ul * r));
 }
 
-// Mass formed between lookback ages [lo, hi] (already clipped to [min_age, max_age]).
-__device__ double sfh_bin_mass(int type, const double* p, double mn, double mx, double lo, double hi,
-                               double e_lo, double e_hi) {
-  if (type == SB2_SFH_CONTINUITY) {
-    const int nb = (int)p[0];
-    const double* edges = p + 1;
-    const double* ratios = p + 1 + nb + 1;
-    double sfr = 1.0, m = 0.0;
-    for (int j = 0; j < nb; ++j) {
-      if (j > 0) sfr *= pow(10.0, -ratios[j - 1]);
-      double ov = fmin(e_hi, edges[j + 1]) - fmax(e_lo, edges[j]);
-      if (ov > 0.0) m += sfr * ov;
-    }
-    return m;
-  }
-  if (!(hi > lo)) return 0.0;
+// ---- SFH bin masses from per-edge values ---------------------------------------------------------
+// Every family's bin mass is F(e_{a+1}) - F(e_a) for an antiderivative F evaluated at the bin edges
+// clipped to [min_age, max_age] (closed forms instead of scipy.quad), so each of the n_age
+// edges is evaluated ONCE by its own thread and neighbouring threads difference them.  The normal-CDF
+// families keep the small tail c = erfc(|u|/sqrt2)/2 and u itself, so the difference is formed in
+// whichever tail avoids cancellation.
+struct EdgeVal { double a, b; };
+
+__device__ __forceinline__ EdgeVal sfh_edge(int type, const double* __restrict__ p, const double* __restrict__ gc,
+                                            double mn, double mx, double e_raw) {
+  const double r = 0.70710678118654752440;
+  const double t = fmin(fmax(e_raw, mn), mx);
+  EdgeVal v{0.0, 0.0};
   switch (type) {
     case SB2_SFH_CONSTANT:
-      return hi - lo;
+      v.a = t;
+      break;
     case SB2_SFH_GAUSSIAN: {
-      double pk = p[0], s = p[1];
-      return s * 2.50662827463100050242 * phi_diff((lo - pk) / s, (hi - pk) / s);
+      const double u = (t - p[0]) / p[1];
+      v.a = 0.5 * erfc(fabs(u) * r);
+      v.b = u;
+      break;
     }
     case SB2_SFH_EXPONENTIAL:
     case SB2_SFH_DECLINING_EXP: {
-      double tau = (type == SB2_SFH_EXPONENTIAL) ? p[0] : -p[0];
-      double shift = tau > 0.0 ? (mx - mn) / tau : 0.0;
-      return tau * (exp((mx - lo) / tau - shift) - exp((mx - hi) / tau - shift));
+      const double tau = (type == SB2_SFH_EXPONENTIAL) ? p[0] : -p[0];
+      const double shift = tau > 0.0 ? (mx - mn) / tau : 0.0;
+      v.a = -tau * exp((mx - t) / tau - shift);
+      break;
     }
     case SB2_SFH_DELAYED_EXP: {
-      double tau = p[0];
-      double t1 = mx - lo, t2 = mx - hi;
-      return -tau * (t1 + tau) * exp(-t1 / tau) + tau * (t2 + tau) * exp(-t2 / tau);
+      const double tau = p[0], T = mx - t;
+      v.a = tau * (T + tau) * exp(-T / tau);
+      break;
     }
-    case SB2_SFH_LOGNORMAL: {
-      double tau = p[0], pk = p[1];
-      double t0 = log(mx - pk) + tau * tau;
-      double u_hi = (log(fmax(mx - hi, 1e-300)) - t0) / tau;
-      double u_lo = (log(fmax(mx - lo, 1e-300)) - t0) / tau;
-      return tau * 2.50662827463100050242 * phi_diff(u_hi, u_lo);
+    case SB2_SFH_LOGNORMAL: {  // gc[0] = ln(max_age - peak_age) + tau^2
+      const double u = (log(fmax(mx - t, 1e-300)) - gc[0]) / p[0];
+      v.a = 0.5 * erfc(fabs(u) * r);
+      v.b = u;
+      break;
+    }
+    case SB2_SFH_CONTINUITY: {  // gc[j] = SFR of bin j; piecewise-constant SFR, edges not clipped
+      const int nb = (int)p[0];
+      const double* edges = p + 1;
+      double F = 0.0;
+      for (int j = 0; j < nb; ++j) {
+        const double ov = fmin(e_raw, edges[j + 1]) - edges[j];
+        if (ov > 0.0) F += gc[j] * ov;
+      }
+      v.a = F;
+      break;
     }
     default:
-      return nan("");
+      v.a = nan("");
+  }
+  return v;
+}
+
+// Phi(u_hi) - Phi(u_lo) from the tails c = 1 - Phi(|u|)
+__device__ __forceinline__ double phi_between(EdgeVal lo, EdgeVal hi) {
+  const bool pl = lo.b > 0.0, ph = hi.b > 0.0;
+  if (pl && ph) return lo.a - hi.a;
+  if (!pl && !ph) return hi.a - lo.a;
+  if (!pl && ph) return 1.0 - hi.a - lo.a;
+  return -(1.0 - lo.a - hi.a);
+}
+
+__device__ __forceinline__ double sfh_mass_from_edges(int type, const double* __restrict__ p, EdgeVal lo, EdgeVal hi) {
+  const double s2pi = 2.50662827463100050242;
+  switch (type) {
+    case SB2_SFH_GAUSSIAN:
+      return p[1] * s2pi * phi_between(lo, hi);
+    case SB2_SFH_LOGNORMAL:
+      return -p[0] * s2pi * phi_between(lo, hi);  // u decreases with lookback age
+    default:
+      return hi.a - lo.a;
   }
 }
 
-constexpr int kPrepWarps = 8;
-
-__global__ void __launch_bounds__(kPrepWarps * 32)
-prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, long long n_pad) {
-  extern __shared__ double prep_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long t = (long long)blockIdx.x * kPrepWarps + warp;
+// ---- per-galaxy scalars: one THREAD per (padded, grouped) row ------------------------------------
+__global__ void __launch_bounds__(256)
+scalars_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, long long n_pad) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_pad) return;
-  double* sf = prep_smem + (size_t)warp * (M.n_age + M.n_z + SB2_SFH_ROW);
-  double* zd = sf + M.n_age;
-  double* prow = zd + M.n_z;
-  const unsigned FULL = 0xffffffffu;
-
   const long long g = perm ? (long long)perm[t] : (t < P.n ? t : -1);
   if (g < 0) {  // padding row (end of a tile / of a metallicity group)
-    for (int k = lane; k < M.w_stride; k += 32) {
-      O.w_hi[t * M.w_stride + k] = 0.f;
-      O.w_lo[t * M.w_stride + k] = 0.f;
+    if (M.igm_on) {
+      for (int p = 0; p < 12; ++p) O.zpow[(size_t)p * n_pad + t] = 1.0;
+      O.zpow[(size_t)12 * n_pad + t] = 0.0;
     }
-    if (M.igm_on && lane < 13) O.zpow[(size_t)lane * n_pad + t] = (lane < 12) ? 1.0 : 0.0;
-    if (lane == 0) {
-      O.g_m[t] = 0; O.g_beta[t] = 0.5f; O.g_gamma[t] = 0.5f; O.g_taut[t] = 0.f; O.g_scale[t] = 0.f; O.g_ca[t] = 0.f;
-      O.g_cb[t] = 0.f; O.g_orig[t] = -1; O.g_mscale[t] = 0.0; O.g_trunc[t] = 0u;
-    }
+    O.g_m[t] = 0; O.g_beta[t] = 0.5f; O.g_gamma[t] = 0.5f; O.g_taut[t] = 0.f; O.g_scale[t] = 0.f; O.g_ca[t] = 0.f;
+    O.g_cb[t] = 0.f; O.g_orig[t] = -1; O.g_mscale[t] = 0.0; O.g_trunc[t] = 0u;
     return;
   }
-
   const double z = P.redshift[g];
   const double zp = 1.0 + z;
   const double s = log1p(z);
-
-  // ---- SFH parameters ------------------------------------------------------------------
-  if (lane < SB2_SFH_ROW) prow[lane] = (lane < P.sfh_stride) ? P.sfh_rows[g * P.sfh_stride + lane] : 0.0;
-  __syncwarp();
-  double mn = prow[0], mx = prow[1];
-  if (P.max_age_from_z) {
-    double age_gyr = hermite_lut(M.age, M.dage, M.cosmo_ds, M.cosmo_n, s);
-    mx = (age_gyr - P.age_zmax_gyr) * 1.0e9;
-    if (lane < SB2_SFH_ROW - 2 && ((P.norm_mask >> lane) & 1u)) prow[2 + lane] *= mx;
-    __syncwarp();
-  }
-  const double* p = prow + 2;
-
-  double part = 0.0;
-  for (int a = lane; a < M.n_age; a += 32) {
-    double m = 0.0;
-    if (a < M.n_age - 1) {  // the last age bin receives no mass (A2)
-      double e_lo = M.edges[a], e_hi = M.edges[a + 1];
-      double lo = fmin(fmax(e_lo, mn), mx), hi = fmin(fmax(e_hi, mn), mx);
-      m = sfh_bin_mass(P.sfh_type, p, mn, mx, lo, hi, e_lo, e_hi);
-    }
-    sf[a] = m;
-    part += m;
-  }
-  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-  const double inv_sf = 1.0 / part;
-
-  // ---- metallicity weights ---------------------------------------------------------------
-  const double zv = P.zd_value[g];
-  const double zs = P.zd_sigma ? P.zd_sigma[g] : 0.0;
-  const bool logz = (P.zd_type == SB2_ZD_DELTA_LOG10 || P.zd_type == SB2_ZD_NORMAL_LOG10);
-  const double* zx = logz ? M.log10zmet : M.zmet;
-  double zpart = 0.0;
-  int zj = 0;
-  double zf = 0.0;
-  if (P.zd_type == SB2_ZD_DELTA_LINEAR || P.zd_type == SB2_ZD_DELTA_LOG10) {
-    if (M.n_z >= 2) zj = delta_bracket(zx, M.n_z, zv, &zf);
-    for (int i = lane; i < M.n_z; i += 32) zd[i] = (i == zj) ? 1.0 - zf : ((i == zj + 1) ? zf : 0.0);
-    zpart = 1.0;
-  } else {
-    for (int i = lane; i < M.n_z; i += 32) {
-      double u = (zx[i] - zv) / zs;
-      double w = exp(-0.5 * u * u);
-      zd[i] = w;
-      zpart += w;
-    }
-    for (int o = 16; o; o >>= 1) zpart += __shfl_xor_sync(FULL, zpart, o);
-  }
-  __syncwarp();
-  const double inv = inv_sf / zpart;
-
-  // ---- weights row (TF32 hi/lo split) ------------------------------------------------------
-  if (M.delta) {  // columns [0, na_pad): metallicity zj, [na_pad, 2 na_pad): zj+1 (grid columns zj*na_pad + k)
-    for (int k = lane; k < M.w_stride; k += 32) {
-      double w = 0.0;
-      if (k < M.n_age) w = sf[k] * ((1.0 - zf) * inv);
-      else if (k >= M.na_pad && k - M.na_pad < M.n_age) w = sf[k - M.na_pad] * (zf * inv);
-      const float hi = to_tf32_rna((float)w);
-      O.w_hi[t * M.w_stride + k] = hi;
-      O.w_lo[t * M.w_stride + k] = to_tf32_rna((float)(w - (double)hi));
-    }
-  } else {
-  for (int iz = 0; iz < M.n_z; ++iz) {  // column k = iz*na_pad + ia
-    const double zw = zd[iz] * inv;
-    for (int a = lane; a < M.na_pad; a += 32) {
-      const int k = iz * M.na_pad + a;
-      const double w = (a < M.n_age) ? sf[a] * zw : 0.0;
-      const float hi = to_tf32_rna((float)w);
-      O.w_hi[t * M.k_pad + k] = hi;
-      O.w_lo[t * M.k_pad + k] = to_tf32_rna((float)(w - (double)hi));
-      if (O.w_f64 && a < M.n_age) O.w_f64[g * M.K + iz * M.n_age + a] = w;
-    }
-  }
-  for (int k = M.n_z * M.na_pad + lane; k < M.k_pad; k += 32) {
-    O.w_hi[t * M.k_pad + k] = 0.f;
-    O.w_lo[t * M.k_pad + k] = 0.f;
-  }
-  }
-
-  // ---- per-galaxy scalars -------------------------------------------------------------------
   const double tq = s / M.ln_q;
   const int m = (int)floor(tq);
   const double r = exp(s - (double)m * M.ln_q);  // (1+z)/q^m in [1, q)
   const double beta = (M.variant == 0) ? (1.0 - 1.0 / r) / (1.0 - 1.0 / M.q) : (r - 1.0) / (M.q - 1.0);
   unsigned trunc = 0u;
-  if (lane < M.n_filt) {
-    int i_first = M.filt_lo[lane] - 1 - m, i_last = M.filt_hi[lane] - m;
-    trunc = (i_first < 0 || i_last > M.n_lam - 1) ? 1u : 0u;
+  for (int f = 0; f < M.n_filt; ++f) {
+    const int i_first = __ldg(M.filt_lo + f) - 1 - m, i_last = __ldg(M.filt_hi + f) - m;
+    if (i_first < 0 || i_last > M.n_lam - 1) trunc |= 1u << f;
   }
-  trunc = __ballot_sync(FULL, trunc != 0u);
-  if (lane == 0) {
-    const double dc = hermite_lut(M.dc, M.ddc, M.cosmo_ds, M.cosmo_n, s);
-    const double dl_cm = zp * dc * 3.0856775814913673e24;
-    const double scale = M.grid_scale * M.base_mass * zp / (4.0 * 3.14159265358979323846 * dl_cm * dl_cm) * 1.0e32;
-    O.g_m[t] = m;
-    O.g_beta[t] = (float)beta;
-    O.g_gamma[t] = (float)((M.variant == 0) ? (1.0 / r - 1.0 / M.q) / (1.0 - 1.0 / M.q) : (M.q - r) / (M.q - 1.0));
-    O.g_taut[t] = (float)((P.tau_v ? P.tau_v[g] : 0.0) * 1.44269504088896340736);
-    O.g_scale[t] = (float)scale;
-    O.g_ca[t] = (float)(P.coef_att ? P.coef_att[g] : 1.0);
-    O.g_cb[t] = (float)(P.coef_unatt ? P.coef_unatt[g] : 1.0);
-    O.g_orig[t] = (int)g;
-    O.g_mscale[t] = P.log_mass ? pow(10.0, P.log_mass[g]) / M.base_mass : 1.0;
-    O.g_trunc[t] = trunc;
-  }
-
-  // ---- (1+z)^p for the IGM kernel: p in (1.2, 2.1, 3.7, 5.5, -0.3, 2, 3, -0.9, 1.6, 3.4, 2.3, 3.3), then z
+  const double dc = hermite_lut(M.dc, M.ddc, M.cosmo_ds, M.cosmo_n, s);
+  const double dl_cm = zp * dc * 3.0856775814913673e24;
+  const double scale = M.grid_scale * M.base_mass * zp / (4.0 * 3.14159265358979323846 * dl_cm * dl_cm) * 1.0e32;
+  O.g_m[t] = m;
+  O.g_beta[t] = (float)beta;
+  O.g_gamma[t] = (float)((M.variant == 0) ? (1.0 / r - 1.0 / M.q) / (1.0 - 1.0 / M.q) : (M.q - r) / (M.q - 1.0));
+  O.g_taut[t] = (float)((P.tau_v ? P.tau_v[g] : 0.0) * 1.44269504088896340736);
+  O.g_scale[t] = (float)scale;
+  O.g_ca[t] = (float)(P.coef_att ? P.coef_att[g] : 1.0);
+  O.g_cb[t] = (float)(P.coef_unatt ? P.coef_unatt[g] : 1.0);
+  O.g_orig[t] = (int)g;
+  O.g_mscale[t] = P.log_mass ? pow(10.0, P.log_mass[g]) / M.base_mass : 1.0;
+  O.g_trunc[t] = trunc;
+  // (1+z)^p for the IGM kernel: p in (1.2, 2.1, 3.7, 5.5, -0.3, 2, 3, -0.9, 1.6, 3.4, 2.3, 3.3), then z
   if (M.igm_on) {
     const double zpw_exp[12] = {1.2, 2.1, 3.7, 5.5, -0.3, 2.0, 3.0, -0.9, 1.6, 3.4, 2.3, 3.3};
-    if (lane < 12) O.zpow[(size_t)lane * n_pad + t] = pow(zp, zpw_exp[lane]);
-    if (lane == 12) O.zpow[(size_t)12 * n_pad + t] = z;
+#pragma unroll
+    for (int p = 0; p < 12; ++p) O.zpow[(size_t)p * n_pad + t] = exp(zpw_exp[p] * s);
+    O.zpow[(size_t)12 * n_pad + t] = z;
+  }
+}
+
+// ---- SFZH weights: block = kWGal galaxies x 64 slots; thread (galaxy, edge) -------------------------
+constexpr int kWGal = 4;
+constexpr int kWSlots = 64;
+constexpr int kGConst = 24;  // per-galaxy constants (ln-normal t0, continuity bin SFRs)
+
+__host__ __device__ inline size_t weights_smem_doubles(int n_age, int n_z) {
+  return (size_t)kWGal * (3 * (size_t)n_age + n_z + SB2_SFH_ROW + kGConst + 8);
+}
+
+__global__ void __launch_bounds__(kWGal * kWSlots)
+weights_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, long long n_pad) {
+  extern __shared__ double prep_smem[];
+  const int gq = threadIdx.x / kWSlots, slot = threadIdx.x % kWSlots;
+  const long long t = (long long)blockIdx.x * kWGal + gq;
+  double* base = prep_smem + (size_t)gq * (3 * M.n_age + M.n_z + SB2_SFH_ROW + kGConst + 8);
+  double* eA = base;                  // [n_age] edge values
+  double* eB = eA + M.n_age;
+  double* sf = eB + M.n_age;          // [n_age] bin masses
+  double* zd = sf + M.n_age;          // [n_z]
+  double* prow = zd + M.n_z;          // [SB2_SFH_ROW]
+  double* gc = prow + SB2_SFH_ROW;    // [kGConst]
+  double* red = gc + kGConst;         // [8] reductions / scalars
+  const unsigned FULL = 0xffffffffu;
+  const bool in_range = t < n_pad;
+  const long long g = !in_range ? -1 : (perm ? (long long)perm[t] : (t < P.n ? t : -1));
+  const bool valid = g >= 0;
+
+  // ---- SFH parameter row (+ max_age from redshift, *_norm scaling: library.py:1206, :1287-1289)
+  if (valid && slot < SB2_SFH_ROW) prow[slot] = (slot < P.sfh_stride) ? P.sfh_rows[g * P.sfh_stride + slot] : 0.0;
+  __syncthreads();
+  if (valid && P.max_age_from_z) {
+    if (slot == 0) {
+      const double s = log1p(P.redshift[g]);
+      red[0] = (hermite_lut(M.age, M.dage, M.cosmo_ds, M.cosmo_n, s) - P.age_zmax_gyr) * 1.0e9;
+    }
+  }
+  __syncthreads();
+  if (valid && P.max_age_from_z) {
+    const double mxz = red[0];
+    __syncwarp();
+    if (slot < SB2_SFH_ROW - 2 && ((P.norm_mask >> slot) & 1u)) prow[2 + slot] *= mxz;
+    if (slot == 0) prow[1] = mxz;
+  }
+  __syncthreads();
+  const double mn = prow[0], mx = prow[1];
+  const double* p = prow + 2;
+  // ---- per-galaxy constants
+  if (valid) {
+    if (P.sfh_type == SB2_SFH_LOGNORMAL) {
+      if (slot == 0) gc[0] = log(mx - p[1]) + p[0] * p[0];
+    } else if (P.sfh_type == SB2_SFH_CONTINUITY) {
+      const int nb = (int)p[0];
+      const double* ratios = p + 1 + nb + 1;
+      if (slot > 0 && slot < nb && slot < kGConst) gc[slot] = pow(10.0, -ratios[slot - 1]);
+    }
+  }
+  __syncthreads();
+  if (valid && P.sfh_type == SB2_SFH_CONTINUITY && slot == 0) {
+    const int nb = min((int)p[0], kGConst);
+    double sfr = 1.0;
+    gc[0] = 1.0;
+    for (int j = 1; j < nb; ++j) { sfr *= gc[j]; gc[j] = sfr; }
+  }
+  __syncthreads();
+  // ---- edge values, bin masses (the last age bin receives no mass, A2)
+  if (valid)
+    for (int e = slot; e < M.n_age; e += kWSlots) {
+      const EdgeVal v = sfh_edge(P.sfh_type, p, gc, mn, mx, M.edges[e]);
+      eA[e] = v.a; eB[e] = v.b;
+    }
+  __syncthreads();
+  double part = 0.0;
+  if (valid)
+    for (int a = slot; a < M.n_age; a += kWSlots) {
+      double mass = 0.0;
+      if (a < M.n_age - 1) mass = sfh_mass_from_edges(P.sfh_type, p, EdgeVal{eA[a], eB[a]}, EdgeVal{eA[a + 1], eB[a + 1]});
+      sf[a] = mass;
+      part += mass;
+    }
+  // ---- metallicity weights
+  const bool logz = (P.zd_type == SB2_ZD_DELTA_LOG10 || P.zd_type == SB2_ZD_NORMAL_LOG10);
+  const double* zx = logz ? M.log10zmet : M.zmet;
+  const bool zdelta = (P.zd_type == SB2_ZD_DELTA_LINEAR || P.zd_type == SB2_ZD_DELTA_LOG10);
+  double zpart = 0.0;
+  if (valid) {
+    const double zv = P.zd_value[g];
+    if (zdelta) {
+      if (slot == 0) {
+        double zf = 0.0;
+        int zj = 0;
+        if (M.n_z >= 2) zj = delta_bracket(zx, M.n_z, zv, &zf);
+        red[4] = (double)zj; red[5] = zf;
+      }
+    } else {
+      const double zs = P.zd_sigma[g];
+      for (int i = slot; i < M.n_z; i += kWSlots) {
+        const double u = (zx[i] - zv) / zs;
+        const double w = exp(-0.5 * u * u);
+        zd[i] = w;
+        zpart += w;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    part += __shfl_xor_sync(FULL, part, o);
+    zpart += __shfl_xor_sync(FULL, zpart, o);
+  }
+  if ((slot & 31) == 0) { red[slot >> 5] = part; red[2 + (slot >> 5)] = zpart; }
+  __syncthreads();
+  if (!valid) {
+    if (in_range)
+      for (int k = slot; k < M.w_stride; k += kWSlots) {
+        O.w_hi[t * M.w_stride + k] = 0.f;
+        O.w_lo[t * M.w_stride + k] = 0.f;
+      }
+    return;
+  }
+  const double inv_sf = 1.0 / (red[0] + red[1]);
+  // ---- weights row (TF32 hi/lo split)
+  if (M.delta) {  // columns [0, na_pad): metallicity zj, [na_pad, 2 na_pad): zj+1 (grid columns zj*na_pad + k)
+    const double zf = red[5];
+    for (int k = slot; k < M.w_stride; k += kWSlots) {
+      double w = 0.0;
+      if (k < M.n_age) w = sf[k] * ((1.0 - zf) * inv_sf);
+      else if (k >= M.na_pad && k - M.na_pad < M.n_age) w = sf[k - M.na_pad] * (zf * inv_sf);
+      const float hi = to_tf32_rna((float)w);
+      O.w_hi[t * M.w_stride + k] = hi;
+      O.w_lo[t * M.w_stride + k] = to_tf32_rna((float)(w - (double)hi));
+    }
+    return;
+  }
+  if (zdelta) {
+    const int zj = (int)red[4];
+    const double zf = red[5];
+    for (int i = slot; i < M.n_z; i += kWSlots) zd[i] = (i == zj) ? 1.0 - zf : ((i == zj + 1) ? zf : 0.0);
+  }
+  const double inv = inv_sf / (zdelta ? 1.0 : red[2] + red[3]);
+  __syncthreads();
+  for (int k = slot; k < M.k_pad; k += kWSlots) {  // column k = iz*na_pad + ia
+    const int iz = k / M.na_pad, a = k - iz * M.na_pad;
+    const double w = (iz < M.n_z && a < M.n_age) ? sf[a] * (zd[iz] * inv) : 0.0;
+    const float hi = to_tf32_rna((float)w);
+    O.w_hi[t * M.k_pad + k] = hi;
+    O.w_lo[t * M.k_pad + k] = to_tf32_rna((float)(w - (double)hi));
+    if (O.w_f64 && iz < M.n_z && a < M.n_age) O.w_f64[g * M.K + iz * M.n_age + a] = w;
+  }
+}
+
+// First / last wavelength chunk (and bin) that any filter of a tile's galaxies can reach; one warp per tile.
+// Chunks outside the range are skipped by the contraction kernel, IGM bins below it are not evaluated.
+__global__ void tile_range_kernel(const int* __restrict__ g_m, const int* __restrict__ g_orig, int n_tiles,
+                                  int lo_min, int hi_max, int n_lam, int lam_per_chunk, int all, int4* out) {
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  int mmin = INT_MAX, mmax = INT_MIN;
+  for (int r = lane; r < 128; r += 32) {
+    const int row = tile * 128 + r;
+    if (g_orig[row] >= 0) {
+      mmin = min(mmin, g_m[row]);
+      mmax = max(mmax, g_m[row]);
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    mmin = min(mmin, __shfl_xor_sync(0xffffffffu, mmin, o));
+    mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+  }
+  if (lane == 0) {
+    int4 r;
+    if (mmin > mmax) r = make_int4(0, -1, n_lam, -1);  // padding only
+    else if (all) r = make_int4(0, (n_lam - 1) / lam_per_chunk, 0, n_lam - 1);
+    else {
+      const int i_lo = max(0, lo_min - 1 - mmax), i_hi = min(n_lam - 1, hi_max - mmin);
+      r = (i_hi < i_lo) ? make_int4(0, -1, n_lam, -1) : make_int4(i_lo / lam_per_chunk, i_hi / lam_per_chunk, i_lo & ~31, i_hi);
+    }
+    out[tile] = r;
   }
 }
 
@@ -308,7 +427,9 @@ prep_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, 
 constexpr int kIgmStrip = 64;
 
 __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __restrict__ zpow, float* __restrict__ igm,
-                                                  int nb_pad, long long n_pad) {
+                                                  const int4* __restrict__ tile_range, int nb_pad, long long n_pad) {
+  const int first_bin = tile_range ? tile_range[blockIdx.x].z : 0;  // bins below it are never integrated (warp-uniform)
+  if ((int)(blockIdx.y + 1) * kIgmStrip <= first_bin) return;
   __shared__ double s_thr[3 * 64];
   __shared__ double s_pre[5 * 64];
   const int np1 = M.n_lines + 1;
@@ -322,10 +443,10 @@ __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __r
   for (int p = 0; p < 12; ++p) Z[p] = zpow[(size_t)p * n_pad + t];
   const double z = zpow[(size_t)12 * n_pad + t];
   const double zp = 1.0 + z;
-  const int i0 = blockIdx.y * kIgmStrip;
-  const int i1 = min(nb, i0 + kIgmStrip);
+  const int i0 = max((int)blockIdx.y * kIgmStrip, first_bin);
+  const int i1 = min(nb, (int)(blockIdx.y + 1) * kIgmStrip);
   float* out = igm + ((size_t)blockIdx.x * nb_pad) * 128 + threadIdx.x;
-  for (int i = max(i0, nb); i < min(nb_pad, i0 + kIgmStrip); ++i) out[(size_t)i * 128] = 1.f;  // padding rows
+  for (int i = max(i0, nb); i < min(nb_pad, (int)(blockIdx.y + 1) * kIgmStrip); ++i) out[(size_t)i * 128] = 1.f;  // padding rows
   if (i0 >= nb) return;
   // lines (sorted by decreasing wavelength) still below the regime thresholds at the strip's first bin
   int n1 = 0, n2 = 0, nd = 0;
@@ -368,7 +489,11 @@ __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __r
         else if (xl < 2.2) tau += 5.221e-4 * Z[9] * b21 + 0.3248 * b12 - 3.140e-2 * b21;
       }
     }
-    out[(size_t)i * 128] = (float)exp(-tau);
+    // exp(-tau) = 2^n * 2^f with the split done in float64 and only 2^f (|f| <= 1/2) in float32
+    const double y = -tau * 1.44269504088896340736;
+    const double yn = rint(fmin(fmax(y, -200.0), 100.0));
+    const int ex = (int)yn + 127;
+    out[(size_t)i * 128] = ex > 0 ? __int_as_float(ex << 23) * exp2f((float)(y - yn)) : 0.f;
   }
 }
 

@@ -48,7 +48,7 @@ struct SynthArgs {
   int k8_total;              // K/8 MMA steps actually needed (the last k-block may be partial)
   const int* n_tiles_dev;    // actual tile count (<= n_tiles) when the batch was grouped on device, else nullptr
   const int* tile_k0;        // [n_tiles] first grid column (k) of each tile's weights, nullptr: 0
-  const int2* tile_range;    // [n_tiles] first / last wavelength chunk any filter of the tile needs, nullptr: all
+  const int4* tile_range;    // [n_tiles] {first, last wavelength chunk any filter of the tile needs, first bin & ~31, last bin}; nullptr: all
   const float* kappa;        // [n_chunk * lam_per_chunk], zero padded
   const float2* filt_uv;     // padded tables, uv_len entries
   const float* igm;          // [n_tiles][n_blue_pad][128]
@@ -130,7 +130,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int k0 = A.tile_k0 ? __ldg(A.tile_k0 + tile) : 0;
-        const int2 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int2(0, c_all_last);
+        const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
         for (int c = cr.x; c <= cr.y; ++c) {
           for (int kb = 0; kb < A.n_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -151,7 +151,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_tf32(kBM, kBN);
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int2 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int2(0, c_all_last);
+        const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
         for (int c = cr.x; c <= cr.y; ++c, ++it) {
           const uint32_t buf = it & 1u;
           mbar_wait(&tempty_bar[buf], ((it >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
@@ -188,7 +188,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
     const unsigned FULL = 0xffffffffu;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int2 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int2(0, c_all_last);
+      const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
       const int row = tile * kBM + et;
       const int orig = A.g_orig[row];
       int m = A.g_m[row];
@@ -332,35 +332,6 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
-  }
-}
-
-// First / last wavelength chunk that any filter of a tile's galaxies can reach (one warp per tile).
-__global__ void tile_range_kernel(const int* __restrict__ g_m, const int* __restrict__ g_orig, int n_tiles,
-                                  int lo_min, int hi_max, int n_lam, int lam_per_chunk, int all, int2* out) {
-  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (tile >= n_tiles) return;
-  int mmin = INT_MAX, mmax = INT_MIN;
-  for (int r = lane; r < kBM; r += 32) {
-    const int row = tile * kBM + r;
-    if (g_orig[row] >= 0) {
-      mmin = min(mmin, g_m[row]);
-      mmax = max(mmax, g_m[row]);
-    }
-  }
-  for (int o = 16; o; o >>= 1) {
-    mmin = min(mmin, __shfl_xor_sync(0xffffffffu, mmin, o));
-    mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
-  }
-  if (lane == 0) {
-    int2 r;
-    if (mmin > mmax) r = make_int2(0, -1);  // padding only
-    else if (all) r = make_int2(0, (n_lam - 1) / lam_per_chunk);
-    else {
-      const int i_lo = max(0, lo_min - 1 - mmax), i_hi = min(n_lam - 1, hi_max - mmin);
-      r = (i_hi < i_lo) ? make_int2(0, -1) : make_int2(i_lo / lam_per_chunk, i_hi / lam_per_chunk);
-    }
-    out[tile] = r;
   }
 }
 
