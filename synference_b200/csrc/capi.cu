@@ -178,6 +178,7 @@ struct sb2_model {
   int uv_len = 0;      // entries of the padded (U, V) tables
   int n_blue_pad = 0;  // IGM rows per tile (n_blue rounded up to 32; the extra rows hold 1)
   int4* tile_range = nullptr;
+  float2* part = nullptr;  // [2][n_filt][cap_pad] partial filter numerators of the two epilogue groups
   int wd_stride = 0;  // floats per weights row in DeltaConstant (bracket-grouped) mode; 0: mode unavailable
   CUtensorMap tm_wd_hi, tm_wd_lo;
   double* g_mscale = nullptr;
@@ -211,7 +212,7 @@ int sb2_model_destroy(sb2_model* m) {
   void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->filt_uv, m->filt_lo,
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
-                  m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params,
+                  m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params,
                   m->stage_flux, m->stage_flux64};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -318,6 +319,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(w_lo, np * d->k_pad * 4);
   AL(igm, (np / 128) * (size_t)(m->n_blue_pad > 0 ? m->n_blue_pad : 1) * 128 * 4);
   AL(tile_range, (np / 128) * sizeof(int4));
+  AL(part, (size_t)2 * d->n_filt * np * sizeof(float2));
   AL(g_m, np * 4); AL(g_orig, np * 4); AL(perm, np * 4); AL(idx, np * 4);
   AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
   AL(keys, np * 4); AL(keys_sorted, np * 4); AL(perm_pad, np * 4); AL(tile_k0, (np / 128) * 4); AL(grp, (3 * kMaxGroups + 1) * 4);
@@ -530,7 +532,20 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
     a.filt_su[f] = m->h_su[f]; a.filt_sdv[f] = m->h_sdv[f];
   }
   const int grid = a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm;
+  a.part = m->part;
+  a.n_rows = (long long)a.n_tiles * 128;
   rc = launch_synth(m, a, grid, delta, st);
+  if (rc == SB2_OK) {
+    sb2::FinalizeArgs fa{};
+    fa.part = m->part; fa.n_rows = a.n_rows; fa.n_filt = d.n_filt; fa.n_comp = d.n_comp;
+    fa.g_beta = m->g_beta; fa.g_gamma = m->g_gamma; fa.g_scale = m->g_scale; fa.g_ca = m->g_ca; fa.g_orig = m->g_orig;
+    fa.g_mscale = m->g_mscale; fa.g_trunc = m->g_trunc; fa.out_base = flux_base; fa.out_scaled = flux_scaled;
+    for (int f = 0; f < d.n_filt; ++f) { fa.filt_su[f] = m->h_su[f]; fa.filt_sdv[f] = m->h_sdv[f]; }
+    if (flux_base || flux_scaled) {
+      sb2::finalize_kernel<<<(unsigned)((a.n_rows + 255) / 256), 256, 0, st>>>(fa, a.n_tiles_dev);
+      STAGE_CHECK("finalize_kernel", st);
+    }
+  }
   cudaEventRecord(m->ev[3], st);
   m->ev_valid = (rc == SB2_OK);
   return rc;

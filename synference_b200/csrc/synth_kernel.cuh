@@ -12,12 +12,15 @@
 //   warp 1      MMA issuer     : 12 tcgen05.mma (M128 N256 K8, kind::tf32) per stage into one of
 //                                two 256-column TMEM accumulators
 //   warp 2      TMEM allocator
-//   warps 4-7   fused epilogue : thread t owns galaxy t of the tile (= TMEM lane t); it streams its
+//   warps 4-11  fused epilogue : two warpgroups, one per TMEM accumulator (even / odd chunks), so each
+//                                scheduler has two warps to hide TMEM / L1 / MUFU latency.  Thread t of
+//                                a group owns galaxy t of the tile (= TMEM lane t); it streams its
 //                                spectrum out of TMEM 32 wavelengths at a time and applies dust
-//                                attenuation exp(-tau_V kappa), component mixing, the IGM row,
-//                                and accumulates the trapezoidal filter numerators with the
-//                                per-galaxy (m, beta) shift of the filter tables -- the spectrum
-//                                never goes to shared or global memory.
+//                                attenuation exp(-tau_V kappa), component mixing, the IGM row, and
+//                                accumulates the trapezoidal filter numerators with the per-galaxy
+//                                (m, beta) shift of the filter tables -- the spectrum never goes to
+//                                shared or global memory.  Each group writes its partial numerators
+//                                (numU, numV per filter); finalize_kernel adds the two and scales.
 //
 // A wavelength chunk is 256 accumulator columns: 256 wavelengths for one spectral component, or
 // 128 wavelengths x 2 components (attenuated | unattenuated) when the emission recipe needs both.
@@ -38,7 +41,7 @@ constexpr int kStages = 2;
 constexpr int kABytes = kBM * kBK * 4;         // 16 KiB
 constexpr int kBBytes = kBN * kBK * 4;         // 32 KiB
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // hi + lo of both operands = 96 KiB
-constexpr int kSynthThreads = 256;
+constexpr int kSynthThreads = 384;             // 4 control warps + 2 epilogue warpgroups
 constexpr int kMaxFilt = 32;
 constexpr int kUvPad = 32;       // zero entries on both sides of every filter's (U, V) table
 constexpr int kFastSpread = 2;   // max (m_max - m_min) within a warp for the unclamped table reads
@@ -62,6 +65,8 @@ struct SynthArgs {
   const int* g_orig;
   const double* g_mscale;
   const unsigned* g_trunc;
+  float2* part;          // [2][n_filt][n_rows] partial filter numerators of the two epilogue groups
+  long long n_rows;      // padded rows (n_tiles * 128)
   float* out_base;
   double* out_scaled;
   float* out_spec;
@@ -109,7 +114,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }  // 4 warps per epilogue group
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -182,7 +187,8 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================================================================== fused epilogue
-    const int et = threadIdx.x - 128;            // galaxy within tile == TMEM lane
+    const uint32_t grp = (uint32_t)(warp - 4) >> 2;            // owns TMEM accumulator `grp` = chunks with (it & 1) == grp
+    const int et = (threadIdx.x - 128) & 127;                  // galaxy within tile == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t uv_base = smem_u32(s_uv);
     const unsigned FULL = 0xffffffffu;
@@ -192,9 +198,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
       const int row = tile * kBM + et;
       const int orig = A.g_orig[row];
       int m = A.g_m[row];
-      const float beta = A.g_beta[row], gamma = A.g_gamma[row], ntaut = -A.g_taut[row];
-      const float ca = A.g_ca[row], cb = A.g_cb[row];
-      const float scale = A.g_scale[row];
+      const float ntaut = -A.g_taut[row];
       // redshift-shift range of this warp's real galaxies (padding rows follow the others)
       int mmin = orig >= 0 ? m : INT_MAX, mmax = orig >= 0 ? m : INT_MIN;
 #pragma unroll
@@ -210,18 +214,17 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
       for (int f = 0; f < kNF; ++f) acc[f] = make_float2(0.f, 0.f);
 
       for (int c = cr.x; c <= cr.y; ++c, ++it) {
+        if ((it & 1u) != grp) continue;
         // which filters overlap which 32-wavelength sub-chunk of this chunk: lane `sub` works it out for sub-chunk `sub`
         unsigned cmask = 0u;
         {
           const int i0s = c * kLch + (lane & (kSub - 1)) * 32;
-#pragma unroll
-          for (int f = 0; f < kNF; ++f)
-            if (f < A.n_filt && i0s + mmin <= A.filt_hi[f] && i0s + 31 + mmax >= A.filt_lo[f] - 1) cmask |= 1u << f;
+          for (int f = 0; f < A.n_filt; ++f)
+            if (i0s + mmin <= A.filt_hi[f] && i0s + 31 + mmax >= A.filt_lo[f] - 1) cmask |= 1u << f;
         }
-        const uint32_t buf = it & 1u;
-        mbar_wait(&tfull_bar[buf], (it >> 1) & 1u);
+        mbar_wait(&tfull_bar[grp], (it >> 1) & 1u);
         tc_fence_after();
-        const uint32_t t_acc = tmem_base + lane_base + buf * kBN;
+        const uint32_t t_acc = tmem_base + lane_base + grp * kBN;
 #pragma unroll 1
         for (int sub = 0; sub < kSub; ++sub) {
           const int i0 = c * kLch + sub * 32;
@@ -230,30 +233,36 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
           {
             uint32_t v[32];
             tmem_ld_32x32b_x32(t_acc + sub * 32, v);
-            float kk[32];
             const float4* kp = reinterpret_cast<const float4*>(A.kappa + i0);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 k4 = __ldg(kp + j4);
-              kk[4 * j4] = k4.x; kk[4 * j4 + 1] = k4.y; kk[4 * j4 + 2] = k4.z; kk[4 * j4 + 3] = k4.w;
-            }
             if constexpr (kComp == 2) {
+              const float ca = A.g_ca[row], cb = A.g_cb[row];
               uint32_t u[32];
               tmem_ld_32x32b_x32(t_acc + kLch + sub * 32, u);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                s[j] = ca * (__uint_as_float(v[j]) * ex2_approx(ntaut * kk[j])) + cb * __uint_as_float(u[j]);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 k4 = __ldg(kp + j4);
+                s[4 * j4 + 0] = ca * (__uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x)) + cb * __uint_as_float(u[4 * j4 + 0]);
+                s[4 * j4 + 1] = ca * (__uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y)) + cb * __uint_as_float(u[4 * j4 + 1]);
+                s[4 * j4 + 2] = ca * (__uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z)) + cb * __uint_as_float(u[4 * j4 + 2]);
+                s[4 * j4 + 3] = ca * (__uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w)) + cb * __uint_as_float(u[4 * j4 + 3]);
+              }
             } else {
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]) * ex2_approx(ntaut * kk[j]);  // ca goes into the final scale
+              for (int j4 = 0; j4 < 8; ++j4) {  // ca goes into the final scale
+                const float4 k4 = __ldg(kp + j4);
+                s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x);
+                s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y);
+                s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z);
+                s[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w);
+              }
             }
           }
           if (last_sub) {  // all TMEM reads of this accumulator are done: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (lane == 0) mbar_arrive(&tempty_bar[grp]);
           }
           if (i0 < A.n_blue) {  // rows [n_blue, n_blue_pad) of the table hold 1
             const float* ig = A.igm + ((size_t)tile * A.n_blue_pad + i0) * 128 + et;
@@ -262,68 +271,57 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
           }
           if constexpr (kSpec) {
             if (A.out_spec != nullptr && orig >= 0) {
-              const float sc = (kComp == 1) ? scale * ca : scale;
+              const float sc = (kComp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row];
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (i0 + j < A.n_lam) A.out_spec[(size_t)orig * A.n_lam + i0 + j] = s[j] * sc;
             }
           }
-          // filter numerators: (numU_f, numV_f) += s_i * (U_f[n], V_f[n]),  n = i + m
-          const unsigned fm = __shfl_sync(FULL, cmask, sub);
-          if (fm != 0u) {
-            if (fast) {
+          // filter numerators: (numU_f, numV_f) += s_i * (U_f[n], V_f[n]),  n = i + m ; loop over the filters whose
+          // window overlaps this sub-chunk (warp-uniform), compact code: one body, accumulator picked by a switch
+          unsigned fm = __shfl_sync(FULL, cmask, sub);
+#pragma unroll 1
+          while (fm != 0u) {
+            const int f = __ffs(fm) - 1;
+            fm &= fm - 1u;
+            float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
+            // padded table entry p <-> n = filt_lo - 2 - kUvPad + p
+            const int p0 = kUvPad + i0 + m - (A.filt_lo[f] - 2);
+            const uint32_t tab = uv_base + (uint32_t)A.filt_off[f] * 8u;
+            if (fast) {  // all 32 reads stay inside the zero padding
+              const uint32_t addr = tab + (uint32_t)p0 * 8u;
 #pragma unroll
-              for (int f = 0; f < kNF; ++f) {
-                if ((fm >> f) & 1u) {
-                  // padded table entry p <-> n = filt_lo - 2 - kUvPad + p ; all 32 reads stay inside the padding
-                  const uint32_t addr = uv_base + (uint32_t)(A.filt_off[f] + kUvPad + i0 + m - (A.filt_lo[f] - 2)) * 8u;
-                  float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
-#pragma unroll
-                  for (int j = 0; j < 32; j += 2) {
-                    ffma2_bcast(t0, s[j], lds_f2(addr + j * 8));
-                    ffma2_bcast(t1, s[j + 1], lds_f2(addr + j * 8 + 8));
-                  }
-                  acc[f].x += t0.x + t1.x;
-                  acc[f].y += t0.y + t1.y;
-                }
+              for (int j = 0; j < 32; j += 2) {
+                ffma2_bcast(t0, s[j], lds_f2(addr + j * 8));
+                ffma2_bcast(t1, s[j + 1], lds_f2(addr + j * 8 + 8));
               }
-            } else {
+            } else {     // same association as the fast path, indices clamped into the padding
+              const int pmax = A.filt_hi[f] - A.filt_lo[f] + 3 + 2 * kUvPad;
 #pragma unroll
-              for (int f = 0; f < kNF; ++f) {
-                if ((fm >> f) & 1u) {
-                  const int pmax = A.filt_hi[f] - A.filt_lo[f] + 3 + 2 * kUvPad;
-                  const int p0 = kUvPad + i0 + m - (A.filt_lo[f] - 2);
-                  const uint32_t tab = uv_base + (uint32_t)A.filt_off[f] * 8u;
-                  float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);  // same association as the fast path
-#pragma unroll
-                  for (int j = 0; j < 32; j += 2) {
-                    ffma2_bcast(t0, s[j], lds_f2(tab + (uint32_t)min(max(p0 + j, 0), pmax) * 8u));
-                    ffma2_bcast(t1, s[j + 1], lds_f2(tab + (uint32_t)min(max(p0 + j + 1, 0), pmax) * 8u));
-                  }
-                  acc[f].x += t0.x + t1.x;
-                  acc[f].y += t0.y + t1.y;
-                }
+              for (int j = 0; j < 32; j += 2) {
+                ffma2_bcast(t0, s[j], lds_f2(tab + (uint32_t)min(max(p0 + j, 0), pmax) * 8u));
+                ffma2_bcast(t1, s[j + 1], lds_f2(tab + (uint32_t)min(max(p0 + j + 1, 0), pmax) * 8u));
               }
+            }
+            t0.x += t1.x;
+            t0.y += t1.y;
+            switch (f) {
+#define SB2_ACC(i) case i: if (i < kNF) { acc[i < kNF ? i : 0].x += t0.x; acc[i < kNF ? i : 0].y += t0.y; } break;
+              SB2_ACC(0) SB2_ACC(1) SB2_ACC(2) SB2_ACC(3) SB2_ACC(4) SB2_ACC(5) SB2_ACC(6) SB2_ACC(7)
+              SB2_ACC(8) SB2_ACC(9) SB2_ACC(10) SB2_ACC(11) SB2_ACC(12) SB2_ACC(13) SB2_ACC(14) SB2_ACC(15)
+              SB2_ACC(16) SB2_ACC(17) SB2_ACC(18) SB2_ACC(19) SB2_ACC(20) SB2_ACC(21) SB2_ACC(22) SB2_ACC(23)
+              SB2_ACC(24) SB2_ACC(25) SB2_ACC(26) SB2_ACC(27) SB2_ACC(28) SB2_ACC(29) SB2_ACC(30) SB2_ACC(31)
+#undef SB2_ACC
+              default: break;
             }
           }
           if (last_sub) break;
         }
       }
-      // ---- finalize: flux_f = (gamma numU + beta numV) / (gamma su_f + beta sv_f) * scale
-      if (orig >= 0) {
-        const unsigned trunc = A.g_trunc[row];
-        const double mscale = A.g_mscale[row];
-        const float sc = (kComp == 1) ? scale * ca : scale;
+      // ---- this group's partial numerators (finalize_kernel adds the two groups and scales)
 #pragma unroll
-        for (int f = 0; f < kNF; ++f) {
-          if (f < A.n_filt) {
-            float flux = fmaf(beta, acc[f].y, gamma * acc[f].x) / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * sc;
-            if ((trunc >> f) & 1u) flux = __int_as_float(0x7fc00000);
-            if (A.out_base) A.out_base[(size_t)orig * A.n_filt + f] = flux;
-            if (A.out_scaled) A.out_scaled[(size_t)orig * A.n_filt + f] = (double)flux * mscale;
-          }
-        }
-      }
+      for (int f = 0; f < kNF; ++f)
+        if (f < A.n_filt) A.part[((size_t)grp * A.n_filt + f) * A.n_rows + row] = acc[f];
     }
   }
 
@@ -332,6 +330,41 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// flux_f = (gamma numU + beta numV) / (gamma su_f + beta sv_f) * scale, numerators = sum of the two epilogue
+// groups' partials; one thread per (padded) row, results scattered back to the caller's galaxy order.
+struct FinalizeArgs {
+  const float2* part;
+  long long n_rows;
+  int n_filt, n_comp;
+  const float *g_beta, *g_gamma, *g_scale, *g_ca;
+  const int* g_orig;
+  const double* g_mscale;
+  const unsigned* g_trunc;
+  float* out_base;
+  double* out_scaled;
+  float filt_su[kMaxFilt], filt_sdv[kMaxFilt];
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs A, const int* __restrict__ n_tiles_dev) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long rows = n_tiles_dev ? min(A.n_rows, (long long)__ldg(n_tiles_dev) * kBM) : A.n_rows;
+  if (row >= rows) return;
+  const int orig = A.g_orig[row];
+  if (orig < 0) return;
+  const float beta = A.g_beta[row], gamma = A.g_gamma[row];
+  const float sc = (A.n_comp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row];
+  const unsigned trunc = A.g_trunc[row];
+  const double mscale = A.g_mscale[row];
+  for (int f = 0; f < A.n_filt; ++f) {
+    const float2 a = A.part[(size_t)f * A.n_rows + row], b = A.part[((size_t)A.n_filt + f) * A.n_rows + row];
+    const float nu = a.x + b.x, nv = a.y + b.y;
+    float flux = fmaf(beta, nv, gamma * nu) / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * sc;
+    if ((trunc >> f) & 1u) flux = __int_as_float(0x7fc00000);
+    if (A.out_base) A.out_base[(size_t)orig * A.n_filt + f] = flux;
+    if (A.out_scaled) A.out_scaled[(size_t)orig * A.n_filt + f] = (double)flux * mscale;
   }
 }
 
