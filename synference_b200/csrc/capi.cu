@@ -117,19 +117,19 @@ __global__ void group_keys_kernel(const double* __restrict__ z, const double* __
   if (threadIdx.x < kMaxGroups && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
 }
 
-// counts -> first sorted position (cum) and first padded row (pad_start) of every group, the tile count and
-// each tile's first grid column.
-__global__ void group_layout_kernel(const int* __restrict__ counts, int n_groups, int cols_per_group, int* cum,
-                                    int* pad_start, int* tile_k0, int* n_tiles_out, int max_tiles) {
+// counts -> first sorted position (cum) and first padded row (pad_start) of every group, the number of units
+// (a unit = one tile of 128 rows, or a pair of tiles for the CTA-pair kernel) and each unit's first grid column.
+__global__ void group_layout_kernel(const int* __restrict__ counts, int n_groups, int cols_per_group, int rows_per_unit,
+                                    int* cum, int* pad_start, int* tile_k0, int* n_tiles_out, int max_tiles) {
   __shared__ int s_first[kMaxGroups + 1];
   if (threadIdx.x == 0) {
     int c = 0, t = 0;
     for (int j = 0; j < n_groups; ++j) {
       cum[j] = c;
-      pad_start[j] = t * 128;
+      pad_start[j] = t * rows_per_unit;
       s_first[j] = t;
       c += counts[j];
-      t += (counts[j] + 127) / 128;
+      t += (counts[j] + rows_per_unit - 1) / rows_per_unit;
     }
     s_first[n_groups] = t;
     *n_tiles_out = t;
@@ -180,7 +180,8 @@ struct sb2_model {
   int4* tile_range = nullptr;
   float2* part = nullptr;  // [2][n_filt][cap_pad] partial filter numerators of the two epilogue groups
   int wd_stride = 0;  // floats per weights row in DeltaConstant (bracket-grouped) mode; 0: mode unavailable
-  CUtensorMap tm_wd_hi, tm_wd_lo;
+  CUtensorMap tm_wd_hi, tm_wd_lo, tm_g2_hi, tm_g2_lo;  // g2: 128-row boxes (one CTA's half of a chunk)
+  size_t smem2_bytes = 0;
   double* g_mscale = nullptr;
   double* zpow = nullptr;
   unsigned* g_trunc = nullptr;
@@ -308,7 +309,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
 #undef UP
   // workspace
   m->cap = d->max_batch;
-  m->cap_pad = (m->cap + 127) / 128 * 128 + 128 * (long long)(d->n_z > 1 ? d->n_z - 1 : 1);
+  m->cap_pad = (m->cap + 255) / 256 * 256 + 256 * (long long)(d->n_z > 1 ? d->n_z - 1 : 1);
   // bracket-grouped (DeltaConstant) mode: a tile's grid columns start at bracket*n_age_pad -- TMA needs that
   // start 16-byte aligned, hence n_age_pad % 4 == 0 -- and span two metallicities
   m->wd_stride = (d->n_z >= 2 && d->n_z <= kMaxGroups) ? 2 * d->n_age_pad : 0;
@@ -335,12 +336,16 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
       (rc = make_tmap(&m->tm_w_lo, m->w_lo, np, d->k_pad, sb2::kBM)) != SB2_OK ||
       (m->wd_stride && (rc = make_tmap(&m->tm_wd_hi, m->w_hi, np, m->wd_stride, sb2::kBM)) != SB2_OK) ||
       (m->wd_stride && (rc = make_tmap(&m->tm_wd_lo, m->w_lo, np, m->wd_stride, sb2::kBM)) != SB2_OK) ||
+      (rc = make_tmap(&m->tm_g2_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN / 2)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g2_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN / 2)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK) {
     sb2_model_destroy(m);
     return rc;
   }
   m->smem_bytes = 1024 + (size_t)sb2::kStages * sb2::kStageBytes + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 128;
+  m->smem2_bytes = 1024 + (size_t)sb2::kW2Bytes + (size_t)sb2::kG2Slots * sb2::kG2Slot + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 128;
+  if (m->smem2_bytes > (size_t)prop.sharedMemPerBlockOptin || m->wd_stride > sb2::kW2Kb * sb2::kBK || (m->n_sm & 1)) m->smem2_bytes = 0;  // CTA-pair kernel unavailable
   if (m->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
     sb2_model_destroy(m);
     return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to the operand pipeline (" +
@@ -368,6 +373,40 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
                                                      m->tm_g_hi, m->tm_g_lo, a);
   STAGE_CHECK("synth_kernel", st);
   return SB2_OK;
+}
+
+template <int C, int NF, bool SPEC>
+int launch_synth2_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
+  auto k = sb2::synth2_kernel<C, NF, SPEC>;
+  CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem2_bytes));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(sb2::kSynthThreads);
+  cfg.dynamicSmemBytes = m->smem2_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU_TRY(cudaLaunchKernelEx(&cfg, k, m->tm_wd_hi, m->tm_wd_lo, m->tm_g2_hi, m->tm_g2_lo, a));
+  STAGE_CHECK("synth2_kernel", st);
+  return SB2_OK;
+}
+
+int launch_synth2(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
+  const int nf = m->d.n_filt, c = m->d.n_comp;
+  const bool spec = a.out_spec != nullptr;
+#define SB2_PICK(C, NF) (spec ? launch_synth2_t<C, NF, true>(m, a, grid, st) : launch_synth2_t<C, NF, false>(m, a, grid, st))
+  if (c == 1) {
+    if (nf <= 8) return SB2_PICK(1, 8);
+    if (nf <= 24) return SB2_PICK(1, 24);
+    return SB2_PICK(1, 32);
+  }
+  if (nf <= 8) return SB2_PICK(2, 8);
+  if (nf <= 24) return SB2_PICK(2, 24);
+  return SB2_PICK(2, 32);
+#undef SB2_PICK
 }
 
 int launch_synth(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
@@ -427,9 +466,15 @@ int check_params(const sb2_model* m, const sb2_params* p) {
   return SB2_OK;
 }
 
-// Rows the grouped layout of a batch of n galaxies can occupy (every group is padded to whole tiles).
+// A unit of work of the contraction kernel: one 128-galaxy tile, or a PAIR of tiles for the CTA-pair kernel
+// (bracket-grouped batches).
+int rows_per_unit(const sb2_model* m, bool delta) {
+  return (delta && m->smem2_bytes > 0 && !std::getenv("SB2_NO_CTA_PAIR")) ? 256 : 128;
+}
+// Rows the grouped layout of a batch of n galaxies can occupy (every group is padded to whole units).
 long long padded_rows(const sb2_model* m, long long n, bool delta) {
-  return (n + 127) / 128 * 128 + (delta ? 128LL * (m->d.n_z - 1) : 0);
+  const long long rpu = rows_per_unit(m, delta);
+  return (n + rpu - 1) / rpu * rpu + (delta ? rpu * (m->d.n_z - 1) : 0);
 }
 
 // group by (metallicity bracket, redshift) -> perm_pad ; prep kernel
@@ -437,6 +482,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   const long long n = p->n;
   const bool delta = sorted && delta_mode(m, p);
   const long long n_pad = padded_rows(m, n, delta);
+  const int rpu = rows_per_unit(m, delta);
   const int* perm = nullptr;
   cudaEventRecord(m->ev[0], st);
   if (sorted) {
@@ -451,8 +497,8 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
     size_t bytes = m->cub_bytes;
     CU_TRY(cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)n, 0, 32, st));
     STAGE_CHECK("radix sort", st);
-    group_layout_kernel<<<1, 256, 0, st>>>(m->grp, n_groups, m->d.n_age_pad, m->grp + kMaxGroups, m->grp + 2 * kMaxGroups,
-                                           m->tile_k0, m->grp + 3 * kMaxGroups, (int)(n_pad / 128));
+    group_layout_kernel<<<1, 256, 0, st>>>(m->grp, n_groups, m->d.n_age_pad, rpu, m->grp + kMaxGroups, m->grp + 2 * kMaxGroups,
+                                           m->tile_k0, m->grp + 3 * kMaxGroups, (int)(n_pad / rpu));
     STAGE_CHECK("group_layout_kernel", st);
     group_scatter_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, st>>>(m->keys_sorted, m->perm, m->grp + kMaxGroups,
                                                                       m->grp + 2 * kMaxGroups, m->perm_pad, n);
@@ -474,8 +520,8 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
     const sb2_model_desc& d = m->d;
     int lo_min = m->h_lo[0], hi_max = m->h_hi[0];
     for (int f = 1; f < d.n_filt; ++f) { lo_min = std::min(lo_min, m->h_lo[f]); hi_max = std::max(hi_max, m->h_hi[f]); }
-    const int wpb = 8, n_tiles = (int)(n_pad / 128);
-    sb2::tile_range_kernel<<<(n_tiles + wpb - 1) / wpb, wpb * 32, 0, st>>>(m->g_m, m->g_orig, n_tiles, lo_min, hi_max, d.n_lam,
+    const int wpb = 8, n_units = (int)(n_pad / rpu);
+    sb2::tile_range_kernel<<<(n_units + wpb - 1) / wpb, wpb * 32, 0, st>>>(m->g_m, m->g_orig, n_units, rpu, lo_min, hi_max, d.n_lam,
                                                                          sb2::kBN / d.n_comp, all_lam ? 1 : 0, m->tile_range);
     STAGE_CHECK("tile_range_kernel", st);
   }
@@ -485,7 +531,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   STAGE_CHECK("weights_kernel", st);
   if (M.igm_on && !w_f64) {
     dim3 grid((unsigned)(n_pad / 128), (unsigned)((m->n_blue_pad + sb2::kIgmStrip - 1) / sb2::kIgmStrip));
-    sb2::igm_kernel<<<grid, 128, 0, st>>>(M, m->zpow, m->igm, m->tile_range, m->n_blue_pad, n_pad);
+    sb2::igm_kernel<<<grid, 128, 0, st>>>(M, m->zpow, m->igm, m->tile_range, rpu == 256 ? 1 : 0, m->n_blue_pad, n_pad);
     STAGE_CHECK("igm_kernel", st);
   }
   cudaEventRecord(m->ev[2], st);
@@ -516,7 +562,8 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   sb2::SynthArgs a{};
   const bool delta = delta_mode(m, p);
   a.n_gal = (int)p->n;
-  a.n_tiles = (int)(padded_rows(m, p->n, delta) / 128);
+  const int rpu = rows_per_unit(m, delta);
+  a.n_tiles = (int)(padded_rows(m, p->n, delta) / rpu);  // units
   a.n_tiles_dev = m->grp + 3 * kMaxGroups;
   a.tile_k0 = m->tile_k0;
   a.k8_total = (delta ? m->wd_stride : d.k_pad) / 8;
@@ -531,10 +578,15 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
     a.filt_lo[f] = m->h_lo[f]; a.filt_hi[f] = m->h_hi[f]; a.filt_off[f] = m->h_off[f];
     a.filt_su[f] = m->h_su[f]; a.filt_sdv[f] = m->h_sdv[f];
   }
-  const int grid = a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm;
   a.part = m->part;
-  a.n_rows = (long long)a.n_tiles * 128;
-  rc = launch_synth(m, a, grid, delta, st);
+  a.n_rows = (long long)a.n_tiles * rpu;
+  if (rpu == 256) {
+    const int grid = 2 * std::min(a.n_tiles, m->n_sm / 2);
+    rc = launch_synth2(m, a, grid, st);
+  } else {
+    const int grid = a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm;
+    rc = launch_synth(m, a, grid, delta, st);
+  }
   if (rc == SB2_OK) {
     sb2::FinalizeArgs fa{};
     fa.part = m->part; fa.n_rows = a.n_rows; fa.n_filt = d.n_filt; fa.n_comp = d.n_comp;
@@ -542,7 +594,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
     fa.g_mscale = m->g_mscale; fa.g_trunc = m->g_trunc; fa.out_base = flux_base; fa.out_scaled = flux_scaled;
     for (int f = 0; f < d.n_filt; ++f) { fa.filt_su[f] = m->h_su[f]; fa.filt_sdv[f] = m->h_sdv[f]; }
     if (flux_base || flux_scaled) {
-      sb2::finalize_kernel<<<(unsigned)((a.n_rows + 255) / 256), 256, 0, st>>>(fa, a.n_tiles_dev);
+      sb2::finalize_kernel<<<(unsigned)((a.n_rows + 255) / 256), 256, 0, st>>>(fa, a.n_tiles_dev, rpu);
       STAGE_CHECK("finalize_kernel", st);
     }
   }

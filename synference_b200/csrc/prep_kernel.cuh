@@ -387,15 +387,16 @@ weights_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ per
   }
 }
 
-// First / last wavelength chunk (and bin) that any filter of a tile's galaxies can reach; one warp per tile.
+// First / last wavelength chunk (and bin) that any filter of a unit's galaxies can reach; one warp per unit
+// (a tile of 128 rows, or a pair of tiles).
 // Chunks outside the range are skipped by the contraction kernel, IGM bins below it are not evaluated.
-__global__ void tile_range_kernel(const int* __restrict__ g_m, const int* __restrict__ g_orig, int n_tiles,
+__global__ void tile_range_kernel(const int* __restrict__ g_m, const int* __restrict__ g_orig, int n_tiles, int rows_per_unit,
                                   int lo_min, int hi_max, int n_lam, int lam_per_chunk, int all, int4* out) {
   const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (tile >= n_tiles) return;
   int mmin = INT_MAX, mmax = INT_MIN;
-  for (int r = lane; r < 128; r += 32) {
-    const int row = tile * 128 + r;
+  for (int r = lane; r < rows_per_unit; r += 32) {
+    const int row = tile * rows_per_unit + r;
     if (g_orig[row] >= 0) {
       mmin = min(mmin, g_m[row]);
       mmax = max(mmax, g_m[row]);
@@ -427,8 +428,9 @@ __global__ void tile_range_kernel(const int* __restrict__ g_m, const int* __rest
 constexpr int kIgmStrip = 64;
 
 __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __restrict__ zpow, float* __restrict__ igm,
-                                                  const int4* __restrict__ tile_range, int nb_pad, long long n_pad) {
-  const int first_bin = tile_range ? tile_range[blockIdx.x].z : 0;  // bins below it are never integrated (warp-uniform)
+                                                  const int4* __restrict__ tile_range, int range_shift, int nb_pad,
+                                                  long long n_pad) {
+  const int first_bin = tile_range ? tile_range[blockIdx.x >> range_shift].z : 0;  // bins below it are never integrated (warp-uniform)
   if ((int)(blockIdx.y + 1) * kIgmStrip <= first_bin) return;
   __shared__ double s_thr[3 * 64];
   __shared__ double s_pre[5 * 64];

@@ -89,6 +89,161 @@ __device__ __forceinline__ void ffma2_bcast(float2& acc, float s, float2 uv) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
 }
 
+// Fused epilogue of one CTA (warps 4-11): see the header comment.  kCta = 2: the CTA is one half of a pair that
+// shares the MMA (cta_group::2); `unit` is then a pair of tiles, this CTA owns tile 2*unit + rank and hands its
+// accumulators back through the LEADER's tempty barriers (tempty_addr, shared::cluster).
+template <int kComp, int kNF, bool kSpec, int kCta>
+__device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* s_uv, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                              uint32_t tempty_addr, uint32_t tmem_base, int unit0, int unit_stride,
+                                              int n_units, uint32_t cta_rank) {
+  constexpr int kLch = kBN / kComp;
+  constexpr int kSub = kLch / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c_all_last = A.n_chunk - 1;
+  {
+    const uint32_t grp = (uint32_t)(warp - 4) >> 2;            // owns TMEM accumulator `grp` = chunks with (it & 1) == grp
+    const int et = (threadIdx.x - 128) & 127;                  // galaxy within tile == TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t uv_base = smem_u32(s_uv);
+    const unsigned FULL = 0xffffffffu;
+    uint32_t it = 0;
+    for (int unit = unit0; unit < n_units; unit += unit_stride) {
+      const int tile = unit * kCta + (int)cta_rank;
+      const int4 cr = A.tile_range ? __ldg(A.tile_range + unit) : make_int4(0, c_all_last, 0, 0);
+      const int row = tile * kBM + et;
+      const int orig = A.g_orig[row];
+      int m = A.g_m[row];
+      const float ntaut = -A.g_taut[row];
+      // redshift-shift range of this warp's real galaxies (padding rows follow the others)
+      int mmin = orig >= 0 ? m : INT_MAX, mmax = orig >= 0 ? m : INT_MIN;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        mmin = min(mmin, __shfl_xor_sync(FULL, mmin, o));
+        mmax = max(mmax, __shfl_xor_sync(FULL, mmax, o));
+      }
+      if (mmin > mmax) mmin = mmax = 0;
+      if (orig < 0) m = mmin;
+      const bool fast = (mmax - mmin) <= kFastSpread;
+      float2 acc[kNF];
+#pragma unroll
+      for (int f = 0; f < kNF; ++f) acc[f] = make_float2(0.f, 0.f);
+
+      for (int c = cr.x; c <= cr.y; ++c, ++it) {
+        if ((it & 1u) != grp) continue;
+        // which filters overlap which 32-wavelength sub-chunk of this chunk: lane `sub` works it out for sub-chunk `sub`
+        unsigned cmask = 0u;
+        {
+          const int i0s = c * kLch + (lane & (kSub - 1)) * 32;
+          for (int f = 0; f < A.n_filt; ++f)
+            if (i0s + mmin <= A.filt_hi[f] && i0s + 31 + mmax >= A.filt_lo[f] - 1) cmask |= 1u << f;
+        }
+        mbar_wait(&tfull_bar[grp], (it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + lane_base + grp * kBN;
+#pragma unroll 1
+        for (int sub = 0; sub < kSub; ++sub) {
+          const int i0 = c * kLch + sub * 32;
+          const bool last_sub = (sub == kSub - 1) || (i0 + 32 >= A.n_lam);
+          float s[32];
+          {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_acc + sub * 32, v);
+            const float4* kp = reinterpret_cast<const float4*>(A.kappa + i0);
+            if constexpr (kComp == 2) {
+              const float ca = A.g_ca[row], cb = A.g_cb[row];
+              uint32_t u[32];
+              tmem_ld_32x32b_x32(t_acc + kLch + sub * 32, u);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 k4 = __ldg(kp + j4);
+                s[4 * j4 + 0] = ca * (__uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x)) + cb * __uint_as_float(u[4 * j4 + 0]);
+                s[4 * j4 + 1] = ca * (__uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y)) + cb * __uint_as_float(u[4 * j4 + 1]);
+                s[4 * j4 + 2] = ca * (__uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z)) + cb * __uint_as_float(u[4 * j4 + 2]);
+                s[4 * j4 + 3] = ca * (__uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w)) + cb * __uint_as_float(u[4 * j4 + 3]);
+              }
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {  // ca goes into the final scale
+                const float4 k4 = __ldg(kp + j4);
+                s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x);
+                s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y);
+                s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z);
+                s[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w);
+              }
+            }
+          }
+          if (last_sub) {  // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (kCta == 2) mbar_arrive_cluster(tempty_addr + grp * 8u);   // the leader CTA's barrier
+              else mbar_arrive(tempty_bar + grp);
+            }
+          }
+          if (i0 < A.n_blue) {  // rows [n_blue, n_blue_pad) of the table hold 1
+            const float* ig = A.igm + ((size_t)tile * A.n_blue_pad + i0) * 128 + et;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s[j] *= __ldg(ig + j * 128);
+          }
+          if constexpr (kSpec) {
+            if (A.out_spec != nullptr && orig >= 0) {
+              const float sc = (kComp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (i0 + j < A.n_lam) A.out_spec[(size_t)orig * A.n_lam + i0 + j] = s[j] * sc;
+            }
+          }
+          // filter numerators: (numU_f, numV_f) += s_i * (U_f[n], V_f[n]),  n = i + m ; loop over the filters whose
+          // window overlaps this sub-chunk (warp-uniform), compact code: one body, accumulator picked by a switch
+          unsigned fm = __shfl_sync(FULL, cmask, sub);
+#pragma unroll 1
+          while (fm != 0u) {
+            const int f = __ffs(fm) - 1;
+            fm &= fm - 1u;
+            float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
+            // padded table entry p <-> n = filt_lo - 2 - kUvPad + p
+            const int p0 = kUvPad + i0 + m - (A.filt_lo[f] - 2);
+            const uint32_t tab = uv_base + (uint32_t)A.filt_off[f] * 8u;
+            if (fast) {  // all 32 reads stay inside the zero padding
+              const uint32_t addr = tab + (uint32_t)p0 * 8u;
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                ffma2_bcast(t0, s[j], lds_f2(addr + j * 8));
+                ffma2_bcast(t1, s[j + 1], lds_f2(addr + j * 8 + 8));
+              }
+            } else {     // same association as the fast path, indices clamped into the padding
+              const int pmax = A.filt_hi[f] - A.filt_lo[f] + 3 + 2 * kUvPad;
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                ffma2_bcast(t0, s[j], lds_f2(tab + (uint32_t)min(max(p0 + j, 0), pmax) * 8u));
+                ffma2_bcast(t1, s[j + 1], lds_f2(tab + (uint32_t)min(max(p0 + j + 1, 0), pmax) * 8u));
+              }
+            }
+            t0.x += t1.x;
+            t0.y += t1.y;
+            switch (f) {
+#define SB2_ACC(i) case i: if (i < kNF) { acc[i < kNF ? i : 0].x += t0.x; acc[i < kNF ? i : 0].y += t0.y; } break;
+              SB2_ACC(0) SB2_ACC(1) SB2_ACC(2) SB2_ACC(3) SB2_ACC(4) SB2_ACC(5) SB2_ACC(6) SB2_ACC(7)
+              SB2_ACC(8) SB2_ACC(9) SB2_ACC(10) SB2_ACC(11) SB2_ACC(12) SB2_ACC(13) SB2_ACC(14) SB2_ACC(15)
+              SB2_ACC(16) SB2_ACC(17) SB2_ACC(18) SB2_ACC(19) SB2_ACC(20) SB2_ACC(21) SB2_ACC(22) SB2_ACC(23)
+              SB2_ACC(24) SB2_ACC(25) SB2_ACC(26) SB2_ACC(27) SB2_ACC(28) SB2_ACC(29) SB2_ACC(30) SB2_ACC(31)
+#undef SB2_ACC
+              default: break;
+            }
+          }
+          if (last_sub) break;
+        }
+      }
+      // ---- this group's partial numerators (finalize_kernel adds the two groups and scales)
+#pragma unroll
+      for (int f = 0; f < kNF; ++f)
+        if (f < A.n_filt) A.part[((size_t)grp * A.n_filt + f) * A.n_rows + row] = acc[f];
+    }
+  }
+}
+
 template <int kComp, int kNF, bool kSpec>
 __global__ void __launch_bounds__(kSynthThreads, 1)
 synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -186,143 +341,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===================================================================== fused epilogue
-    const uint32_t grp = (uint32_t)(warp - 4) >> 2;            // owns TMEM accumulator `grp` = chunks with (it & 1) == grp
-    const int et = (threadIdx.x - 128) & 127;                  // galaxy within tile == TMEM lane
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t uv_base = smem_u32(s_uv);
-    const unsigned FULL = 0xffffffffu;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
-      const int row = tile * kBM + et;
-      const int orig = A.g_orig[row];
-      int m = A.g_m[row];
-      const float ntaut = -A.g_taut[row];
-      // redshift-shift range of this warp's real galaxies (padding rows follow the others)
-      int mmin = orig >= 0 ? m : INT_MAX, mmax = orig >= 0 ? m : INT_MIN;
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        mmin = min(mmin, __shfl_xor_sync(FULL, mmin, o));
-        mmax = max(mmax, __shfl_xor_sync(FULL, mmax, o));
-      }
-      if (mmin > mmax) mmin = mmax = 0;
-      if (orig < 0) m = mmin;
-      const bool fast = (mmax - mmin) <= kFastSpread;
-      float2 acc[kNF];
-#pragma unroll
-      for (int f = 0; f < kNF; ++f) acc[f] = make_float2(0.f, 0.f);
-
-      for (int c = cr.x; c <= cr.y; ++c, ++it) {
-        if ((it & 1u) != grp) continue;
-        // which filters overlap which 32-wavelength sub-chunk of this chunk: lane `sub` works it out for sub-chunk `sub`
-        unsigned cmask = 0u;
-        {
-          const int i0s = c * kLch + (lane & (kSub - 1)) * 32;
-          for (int f = 0; f < A.n_filt; ++f)
-            if (i0s + mmin <= A.filt_hi[f] && i0s + 31 + mmax >= A.filt_lo[f] - 1) cmask |= 1u << f;
-        }
-        mbar_wait(&tfull_bar[grp], (it >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t t_acc = tmem_base + lane_base + grp * kBN;
-#pragma unroll 1
-        for (int sub = 0; sub < kSub; ++sub) {
-          const int i0 = c * kLch + sub * 32;
-          const bool last_sub = (sub == kSub - 1) || (i0 + 32 >= A.n_lam);
-          float s[32];
-          {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_acc + sub * 32, v);
-            const float4* kp = reinterpret_cast<const float4*>(A.kappa + i0);
-            if constexpr (kComp == 2) {
-              const float ca = A.g_ca[row], cb = A.g_cb[row];
-              uint32_t u[32];
-              tmem_ld_32x32b_x32(t_acc + kLch + sub * 32, u);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 k4 = __ldg(kp + j4);
-                s[4 * j4 + 0] = ca * (__uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x)) + cb * __uint_as_float(u[4 * j4 + 0]);
-                s[4 * j4 + 1] = ca * (__uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y)) + cb * __uint_as_float(u[4 * j4 + 1]);
-                s[4 * j4 + 2] = ca * (__uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z)) + cb * __uint_as_float(u[4 * j4 + 2]);
-                s[4 * j4 + 3] = ca * (__uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w)) + cb * __uint_as_float(u[4 * j4 + 3]);
-              }
-            } else {
-              tmem_ld_wait();
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {  // ca goes into the final scale
-                const float4 k4 = __ldg(kp + j4);
-                s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x);
-                s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y);
-                s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z);
-                s[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w);
-              }
-            }
-          }
-          if (last_sub) {  // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[grp]);
-          }
-          if (i0 < A.n_blue) {  // rows [n_blue, n_blue_pad) of the table hold 1
-            const float* ig = A.igm + ((size_t)tile * A.n_blue_pad + i0) * 128 + et;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s[j] *= __ldg(ig + j * 128);
-          }
-          if constexpr (kSpec) {
-            if (A.out_spec != nullptr && orig >= 0) {
-              const float sc = (kComp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row];
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (i0 + j < A.n_lam) A.out_spec[(size_t)orig * A.n_lam + i0 + j] = s[j] * sc;
-            }
-          }
-          // filter numerators: (numU_f, numV_f) += s_i * (U_f[n], V_f[n]),  n = i + m ; loop over the filters whose
-          // window overlaps this sub-chunk (warp-uniform), compact code: one body, accumulator picked by a switch
-          unsigned fm = __shfl_sync(FULL, cmask, sub);
-#pragma unroll 1
-          while (fm != 0u) {
-            const int f = __ffs(fm) - 1;
-            fm &= fm - 1u;
-            float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
-            // padded table entry p <-> n = filt_lo - 2 - kUvPad + p
-            const int p0 = kUvPad + i0 + m - (A.filt_lo[f] - 2);
-            const uint32_t tab = uv_base + (uint32_t)A.filt_off[f] * 8u;
-            if (fast) {  // all 32 reads stay inside the zero padding
-              const uint32_t addr = tab + (uint32_t)p0 * 8u;
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                ffma2_bcast(t0, s[j], lds_f2(addr + j * 8));
-                ffma2_bcast(t1, s[j + 1], lds_f2(addr + j * 8 + 8));
-              }
-            } else {     // same association as the fast path, indices clamped into the padding
-              const int pmax = A.filt_hi[f] - A.filt_lo[f] + 3 + 2 * kUvPad;
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                ffma2_bcast(t0, s[j], lds_f2(tab + (uint32_t)min(max(p0 + j, 0), pmax) * 8u));
-                ffma2_bcast(t1, s[j + 1], lds_f2(tab + (uint32_t)min(max(p0 + j + 1, 0), pmax) * 8u));
-              }
-            }
-            t0.x += t1.x;
-            t0.y += t1.y;
-            switch (f) {
-#define SB2_ACC(i) case i: if (i < kNF) { acc[i < kNF ? i : 0].x += t0.x; acc[i < kNF ? i : 0].y += t0.y; } break;
-              SB2_ACC(0) SB2_ACC(1) SB2_ACC(2) SB2_ACC(3) SB2_ACC(4) SB2_ACC(5) SB2_ACC(6) SB2_ACC(7)
-              SB2_ACC(8) SB2_ACC(9) SB2_ACC(10) SB2_ACC(11) SB2_ACC(12) SB2_ACC(13) SB2_ACC(14) SB2_ACC(15)
-              SB2_ACC(16) SB2_ACC(17) SB2_ACC(18) SB2_ACC(19) SB2_ACC(20) SB2_ACC(21) SB2_ACC(22) SB2_ACC(23)
-              SB2_ACC(24) SB2_ACC(25) SB2_ACC(26) SB2_ACC(27) SB2_ACC(28) SB2_ACC(29) SB2_ACC(30) SB2_ACC(31)
-#undef SB2_ACC
-              default: break;
-            }
-          }
-          if (last_sub) break;
-        }
-      }
-      // ---- this group's partial numerators (finalize_kernel adds the two groups and scales)
-#pragma unroll
-      for (int f = 0; f < kNF; ++f)
-        if (f < A.n_filt) A.part[((size_t)grp * A.n_filt + f) * A.n_rows + row] = acc[f];
-    }
+    epilogue_loop<kComp, kNF, kSpec, 1>(A, s_uv, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
   }
 
   tc_fence_before();
@@ -330,6 +349,150 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// CTA-pair variant for bracket-grouped (DeltaConstant) batches: K = 2*n_age_pad <= 128.
+//
+// A cluster of two CTAs works on a PAIR of tiles (256 galaxies of one metallicity bracket) with
+// tcgen05.mma.cta_group::2 (M = 256 over the pair, N = 256): each CTA keeps the hi/lo weights of ITS 128
+// galaxies resident in shared memory for the whole pair (loaded once instead of once per chunk) and streams
+// only ITS half (128 rows) of every G k-block, so the L2 -> SM traffic per flop is a third of the
+// single-CTA kernel's, which was L2-bandwidth bound.  The leader CTA issues all MMAs; completion is
+// multicast to both CTAs' barriers; both CTAs run the fused epilogue on their own 128 TMEM lanes.
+constexpr int kW2Kb = 4;                          // resident k-blocks (K <= 128)
+constexpr int kW2Bytes = kW2Kb * 2 * kABytes;     // [kb][hi | lo] x 16 KiB = 128 KiB
+constexpr int kG2Half = (kBN / 2) * kBK * 4;      // 16 KiB: this CTA's 128 rows of one G k-block
+constexpr int kG2Slot = 2 * kG2Half;              // lo | hi
+constexpr int kG2Slots = 2;
+
+template <int kComp, int kNF, bool kSpec>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynthThreads, 1)
+synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+              const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo,
+              const __grid_constant__ SynthArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w = smem;                              // resident weights
+  uint8_t* s_g = smem + kW2Bytes;                   // G ring
+  float2* s_uv = reinterpret_cast<float2*>(s_g + kG2Slots * kG2Slot);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_uv) + ((A.uv_len * 8 + 15) & ~15));
+  uint64_t* full_bar = bars;                        // [kG2Slots] TMA (both CTAs) -> MMA   (leader's copy is used)
+  uint64_t* empty_bar = bars + kG2Slots;            // [kG2Slots] MMA -> TMA               (multicast to both)
+  uint64_t* tfull_bar = bars + 2 * kG2Slots;        // [2]        MMA -> epilogue          (multicast to both)
+  uint64_t* tempty_bar = bars + 2 * kG2Slots + 2;   // [2]        epilogues of both CTAs -> MMA (leader's copy)
+  uint64_t* wfull_bar = bars + 2 * kG2Slots + 4;    //            weights landed (both CTAs) -> MMA (leader's copy)
+  uint64_t* wempty_bar = bars + 2 * kG2Slots + 5;   //            MMA -> TMA: weights buffer free (multicast)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kG2Slots + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo); prefetch_tmap(&tm_g_hi); prefetch_tmap(&tm_g_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kG2Slots; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }  // 4 warps x 2 CTAs
+    mbar_init(wfull_bar, 2);
+    mbar_init(wempty_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm<512>(tmem_slot);
+    tmem_relinquish_2sm();
+  }
+  for (int i = threadIdx.x; i < A.uv_len; i += kSynthThreads) s_uv[i] = A.filt_uv[i];
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_units = A.n_tiles_dev ? min(A.n_tiles, __ldg(A.n_tiles_dev)) : A.n_tiles;  // units = tile pairs
+  const int unit0 = (int)(blockIdx.x >> 1), unit_stride = (int)(gridDim.x >> 1);
+  const int c_all_last = A.n_chunk - 1;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      const uint32_t wfull_l = mapa_u32(smem_u32(wfull_bar), 0);
+      uint32_t full_l[kG2Slots];
+      for (int s = 0; s < kG2Slots; ++s) full_l[s] = mapa_u32(smem_u32(&full_bar[s]), 0);
+      int slot = 0; uint32_t phase = 0, wphase = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_stride) {
+        const int tile = unit * 2 + (int)rank;
+        const int k0 = A.tile_k0 ? __ldg(A.tile_k0 + unit) : 0;
+        const int4 cr = A.tile_range ? __ldg(A.tile_range + unit) : make_int4(0, c_all_last, 0, 0);
+        // this CTA's weights, resident for the whole unit
+        mbar_wait(wempty_bar, wphase ^ 1);
+        if (rank == 0) mbar_expect_tx(wfull_bar, 2 * kW2Bytes); else mbar_arrive_cluster(wfull_l);
+        for (int kb = 0; kb < kW2Kb; ++kb) {
+          tma_load_2d_2sm(s_w + kb * 2 * kABytes, &tm_w_hi, wfull_l, kb * kBK, tile * kBM, kEvictFirst);
+          tma_load_2d_2sm(s_w + kb * 2 * kABytes + kABytes, &tm_w_lo, wfull_l, kb * kBK, tile * kBM, kEvictFirst);
+        }
+        wphase ^= 1;
+        for (int c = cr.x; c <= cr.y; ++c) {
+          for (int kb = 0; kb < A.n_kb; ++kb) {
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&full_bar[slot], 2 * kG2Slot); else mbar_arrive_cluster(full_l[slot]);
+            uint8_t* st = s_g + slot * kG2Slot;
+            tma_load_2d_2sm(st, &tm_g_lo, full_l[slot], k0 + kb * kBK, c * kBN + (int)rank * (kBN / 2), kEvictLast);
+            tma_load_2d_2sm(st + kG2Half, &tm_g_hi, full_l[slot], k0 + kb * kBK, c * kBN + (int)rank * (kBN / 2), kEvictLast);
+            if (++slot == kG2Slots) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(2 * kBM, kBN);
+      const uint32_t w_base = smem_u32(s_w), g_base = smem_u32(s_g);
+      int slot = 0; uint32_t phase = 0, wphase = 0, it = 0;
+      for (int unit = unit0; unit < n_units; unit += unit_stride) {
+        const int4 cr = A.tile_range ? __ldg(A.tile_range + unit) : make_int4(0, c_all_last, 0, 0);
+        mbar_wait(wfull_bar, wphase);
+        wphase ^= 1;
+        tc_fence_after();
+        for (int c = cr.x; c <= cr.y; ++c, ++it) {
+          const uint32_t buf = it & 1u;
+          mbar_wait(&tempty_bar[buf], ((it >> 1) & 1u) ^ 1u);  // both CTAs' epilogues have drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kBN;
+          for (int kb = 0; kb < A.n_kb; ++kb) {
+            mbar_wait(&full_bar[slot], phase);
+            tc_fence_after();
+            const uint32_t sa = w_base + kb * 2 * kABytes, sb = g_base + slot * kG2Slot;
+            const int k4n = min(kBK / 8, A.k8_total - kb * (kBK / 8));
+#pragma unroll
+            for (int k4 = 0; k4 < kBK / 8; ++k4) {
+              if (k4 >= k4n) break;
+              const uint64_t a_hi = make_kmajor_sw128_desc(sa + k4 * 32);
+              const uint64_t a_lo = make_kmajor_sw128_desc(sa + kABytes + k4 * 32);
+              const uint64_t b_lo = make_kmajor_sw128_desc(sb + k4 * 32);
+              const uint64_t b_hi = make_kmajor_sw128_desc(sb + kG2Half + k4 * 32);
+              umma_tf32_2sm(d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
+              umma_tf32_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_tf32_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+            umma_commit_2sm(&empty_bar[slot], 3);   // ring slot reusable in both CTAs
+            if (++slot == kG2Slots) { slot = 0; phase ^= 1; }
+          }
+          umma_commit_2sm(&tfull_bar[buf], 3);      // accumulator complete in both CTAs
+        }
+        umma_commit_2sm(wempty_bar, 3);             // weights buffers reusable in both CTAs
+      }
+    }
+  } else if (warp >= 4) {
+    epilogue_loop<kComp, kNF, kSpec, 2>(A, s_uv, tfull_bar, tempty_bar, mapa_u32(smem_u32(tempty_bar), 0), tmem_base, unit0,
+                                        unit_stride, n_units, rank);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
   }
 }
 
@@ -348,9 +511,10 @@ struct FinalizeArgs {
   float filt_su[kMaxFilt], filt_sdv[kMaxFilt];
 };
 
-__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs A, const int* __restrict__ n_tiles_dev) {
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs A, const int* __restrict__ n_units_dev,
+                                                       int rows_per_unit) {
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long rows = n_tiles_dev ? min(A.n_rows, (long long)__ldg(n_tiles_dev) * kBM) : A.n_rows;
+  const long long rows = n_units_dev ? min(A.n_rows, (long long)__ldg(n_units_dev) * rows_per_unit) : A.n_rows;
   if (row >= rows) return;
   const int orig = A.g_orig[row];
   if (orig < 0) return;
