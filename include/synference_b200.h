@@ -120,6 +120,9 @@ int sb2_device_count(void);
 int sb2_model_create(const sb2_model_desc* desc, int device, sb2_model** out);
 int sb2_model_destroy(sb2_model* m);
 
+/* Diagnostics: which in-kernel barrier waits timed out in the last failed launch ("" if none). */
+const char* sb2_wait_debug(sb2_model* m);
+
 /* SFZH weights only (parity hook for Stars.__init__ -> _get_sfzh, library.py:1372-1379).
  * params: DEVICE pointers. w_out: device float64 [n][n_age*n_z] (k = iz*n_age + ia).       */
 int sb2_build_weights(sb2_model* m, const sb2_params* params, double* w_out, void* stream);

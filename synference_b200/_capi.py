@@ -11,13 +11,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsynference_b200.so")
+LIB_PATH = os.environ.get("SB2_LIB") or os.path.join(_HERE, "csrc", "libsynference_b200.so")  # SB2_LIB: A/B builds
 
 SFH_ROW = 24
 
 EXPORTED_SYMBOLS = (
     "sb2_last_error", "sb2_device_count", "sb2_model_create", "sb2_model_destroy", "sb2_build_weights",
-    "sb2_synth_photometry", "sb2_synth_photometry_host", "sb2_depth_noise_features", "sb2_last_stage_ms",
+    "sb2_synth_photometry", "sb2_synth_photometry_host", "sb2_depth_noise_features", "sb2_last_stage_ms", "sb2_wait_debug",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -74,6 +74,8 @@ def load():
     lib.sb2_device_count.restype = C.c_int
     lib.sb2_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_void_p)]
     lib.sb2_model_destroy.argtypes = [C.c_void_p]
+    lib.sb2_wait_debug.argtypes = [C.c_void_p]
+    lib.sb2_wait_debug.restype = C.c_char_p
     lib.sb2_build_weights.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
     lib.sb2_synth_photometry.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]

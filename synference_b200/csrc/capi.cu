@@ -193,6 +193,7 @@ struct sb2_model {
   double* stage_flux64 = nullptr;
   CUtensorMap tm_w_hi, tm_w_lo, tm_g_hi, tm_g_lo;
   size_t smem_bytes = 0;
+  unsigned int* wait_dbg = nullptr;  // host-mapped: who timed out in an mbarrier wait (protocol-bug watchdog)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start | sorted | weights built | synthesised
   bool ev_valid = false;
 };
@@ -200,6 +201,21 @@ struct sb2_model {
 extern "C" {
 
 const char* sb2_last_error(void) { return g_err.c_str(); }
+
+/* Watchdog record of the most recent mbarrier-wait timeout (diagnostics; empty string if none). */
+const char* sb2_wait_debug(sb2_model* m) {
+  static thread_local std::string out;
+  out.clear();
+  if (!m || !m->wait_dbg) return out.c_str();
+  const unsigned n = m->wait_dbg[0] < 63u ? m->wait_dbg[0] : 63u;
+  for (unsigned i = 0; i < n; ++i) {
+    const unsigned int* e = m->wait_dbg + 4 + i * 4;
+    char buf[128];
+    std::snprintf(buf, sizeof buf, "id=0x%x block=%u thread=%u parity=%u; ", e[0], e[1], e[2], e[3]);
+    out += buf;
+  }
+  return out.c_str();
+}
 
 int sb2_device_count(void) {
   int n = 0;
@@ -320,7 +336,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(w_lo, np * d->k_pad * 4);
   AL(igm, (np / 128) * (size_t)(m->n_blue_pad > 0 ? m->n_blue_pad : 1) * 128 * 4);
   AL(tile_range, (np / 128) * sizeof(int4));
-  AL(part, (size_t)2 * d->n_filt * np * sizeof(float2));
+  AL(part, (size_t)sb2::kMaxGroups * d->n_filt * np * sizeof(float2));
   AL(g_m, np * 4); AL(g_orig, np * 4); AL(perm, np * 4); AL(idx, np * 4);
   AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
   AL(keys, np * 4); AL(keys_sorted, np * 4); AL(perm_pad, np * 4); AL(tile_k0, (np / 128) * 4); AL(grp, (3 * kMaxGroups + 1) * 4);
@@ -336,20 +352,26 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
       (rc = make_tmap(&m->tm_w_lo, m->w_lo, np, d->k_pad, sb2::kBM)) != SB2_OK ||
       (m->wd_stride && (rc = make_tmap(&m->tm_wd_hi, m->w_hi, np, m->wd_stride, sb2::kBM)) != SB2_OK) ||
       (m->wd_stride && (rc = make_tmap(&m->tm_wd_lo, m->w_lo, np, m->wd_stride, sb2::kBM)) != SB2_OK) ||
-      (rc = make_tmap(&m->tm_g2_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN / 2)) != SB2_OK ||
-      (rc = make_tmap(&m->tm_g2_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN / 2)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g2_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN2 / 2)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g2_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN2 / 2)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK) {
     sb2_model_destroy(m);
     return rc;
   }
-  m->smem_bytes = 1024 + (size_t)sb2::kStages * sb2::kStageBytes + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 128;
-  m->smem2_bytes = 1024 + (size_t)sb2::kW2Bytes + (size_t)sb2::kG2Slots * sb2::kG2Slot + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 128;
+  m->smem_bytes = 1024 + (size_t)sb2::kStages * sb2::kStageBytes + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 256;
+  m->smem2_bytes = 1024 + (size_t)sb2::kW2Bytes + (size_t)sb2::kG2Slots * sb2::kG2Slot + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 256;
   if (m->smem2_bytes > (size_t)prop.sharedMemPerBlockOptin || m->wd_stride > sb2::kW2Kb * sb2::kBK || (m->n_sm & 1)) m->smem2_bytes = 0;  // CTA-pair kernel unavailable
   if (m->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
     sb2_model_destroy(m);
     return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to the operand pipeline (" +
                                      std::to_string(m->smem_bytes) + " B needed)");
+  }
+  if (cudaHostAlloc(reinterpret_cast<void**>(&m->wait_dbg), 260 * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess) {
+    std::memset(m->wait_dbg, 0, 260 * sizeof(unsigned int));
+    unsigned int* dptr = nullptr;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), m->wait_dbg, 0) == cudaSuccess)
+      cudaMemcpyToSymbol(sb2::g_wait_dbg, &dptr, sizeof(dptr));
   }
   for (int i = 0; i < 4; ++i) {
     if (cudaEventCreate(&m->ev[i]) != cudaSuccess) {
@@ -522,7 +544,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
     for (int f = 1; f < d.n_filt; ++f) { lo_min = std::min(lo_min, m->h_lo[f]); hi_max = std::max(hi_max, m->h_hi[f]); }
     const int wpb = 8, n_units = (int)(n_pad / rpu);
     sb2::tile_range_kernel<<<(n_units + wpb - 1) / wpb, wpb * 32, 0, st>>>(m->g_m, m->g_orig, n_units, rpu, lo_min, hi_max, d.n_lam,
-                                                                         sb2::kBN / d.n_comp, all_lam ? 1 : 0, m->tile_range);
+                                                                         (rpu == 256 ? sb2::kBN2 : sb2::kBN) / d.n_comp, all_lam ? 1 : 0, m->tile_range);
     STAGE_CHECK("tile_range_kernel", st);
   }
   const size_t sh = sb2::weights_smem_doubles(M.n_age, M.n_z) * sizeof(double);
@@ -567,6 +589,8 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.n_tiles_dev = m->grp + 3 * kMaxGroups;
   a.tile_k0 = m->tile_k0;
   a.k8_total = (delta ? m->wd_stride : d.k_pad) / 8;
+  a.dbg = std::getenv("SB2_DBG") ? std::atoi(std::getenv("SB2_DBG")) : 0;
+  a.two_pass = (!delta && !std::getenv("SB2_ONE_PASS")) ? 1 : 0;
   a.n_chunk = d.n_chunk; a.n_kb = (a.k8_total + 3) / 4; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
   a.n_blue = d.n_blue; a.n_blue_pad = m->n_blue_pad; a.uv_len = m->uv_len;
   a.tile_range = m->tile_range;
@@ -589,7 +613,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   }
   if (rc == SB2_OK) {
     sb2::FinalizeArgs fa{};
-    fa.part = m->part; fa.n_rows = a.n_rows; fa.n_filt = d.n_filt; fa.n_comp = d.n_comp;
+    fa.part = m->part; fa.n_rows = a.n_rows; fa.n_filt = d.n_filt; fa.n_comp = d.n_comp; fa.n_groups = (rpu == 256 && sb2::kT2Buf >= 3) ? 3 : 2;
     fa.g_beta = m->g_beta; fa.g_gamma = m->g_gamma; fa.g_scale = m->g_scale; fa.g_ca = m->g_ca; fa.g_orig = m->g_orig;
     fa.g_mscale = m->g_mscale; fa.g_trunc = m->g_trunc; fa.out_base = flux_base; fa.out_scaled = flux_scaled;
     for (int f = 0; f < d.n_filt; ++f) { fa.filt_su[f] = m->h_su[f]; fa.filt_sdv[f] = m->h_sdv[f]; }

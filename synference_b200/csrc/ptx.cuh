@@ -49,11 +49,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a watchdog: a protocol bug traps instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Spin with a watchdog: a protocol bug traps instead of hanging the GPU box.  Before trapping, the waiter
+// records who it is in a host-mapped buffer (g_wait_dbg, set by the host; readable after the context died).
+__device__ unsigned int* g_wait_dbg = nullptr;
+__device__ __noinline__ void mbar_timeout(uint32_t id, uint32_t parity) {
+  if (g_wait_dbg && (threadIdx.x & 31u) == 0u) {
+    const unsigned slot = atomicAdd(g_wait_dbg, 1u);
+    if (slot < 63u) {
+      unsigned int* e = g_wait_dbg + 4 + slot * 4;
+      e[0] = id; e[1] = blockIdx.x; e[2] = threadIdx.x; e[3] = parity;
+    }
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t id = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 27)) __trap();
+    if (++spins > (1u << 22)) mbar_timeout(id, parity);   // ~10-20 s of polling
   }
 }
 
@@ -203,6 +216,87 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, 
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-uniform issue: every lane of the MMA warp executes these with identical operands; `elected` is 1 in
+// exactly one lane (elect_one()), which is the lane that issues.  Keeping the issue loop free of divergent
+// branches lets ptxas hold descriptors in uniform registers instead of broadcasting them for every MMA.
+__device__ __forceinline__ void umma_tf32_e(uint32_t elected, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm_e(uint32_t elected, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t elected, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_e(uint32_t elected, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(mask), "r"(elected)
+      : "memory");
+}
+// Elected-lane forms of the producer's operations (same warp-uniform scheme as the MMA issue).
+__device__ __forceinline__ void mbar_expect_tx_e(uint32_t elected, uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_e(uint32_t elected, uint32_t cluster_addr) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n\t}" ::"r"(cluster_addr),
+      "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_e(uint32_t elected, uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_addr,
+                                              int c0, int c1, uint64_t cache_hint) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;\n\t}"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "l"(cache_hint), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_e(uint32_t elected, uint32_t smem_dst, const CUtensorMap* m,
+                                                  uint32_t bar_cluster_addr, int c0, int c1, uint64_t cache_hint) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;\n\t}"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(cache_hint),
+        "r"(elected)
+      : "memory");
+}
+// Tell the compiler a value is the same in every lane of the (converged) warp.
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // Arrive (once all previously issued MMAs completed) on the mbarrier at this smem offset in every CTA of `mask`.
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
   asm volatile(

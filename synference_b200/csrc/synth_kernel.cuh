@@ -41,14 +41,18 @@ constexpr int kStages = 2;
 constexpr int kABytes = kBM * kBK * 4;         // 16 KiB
 constexpr int kBBytes = kBN * kBK * 4;         // 32 KiB
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // hi + lo of both operands = 96 KiB
-constexpr int kSynthThreads = 384;             // 4 control warps + 2 epilogue warpgroups
+constexpr int kSynthThreads = 480;             // 3 control warps + 3 epilogue warpgroups
+constexpr int kEpiWarp0 = 3;                   // first epilogue warp
+constexpr int kMaxGroups = 3;                  // epilogue warpgroups in the CTA (partial-numerator planes)
 constexpr int kMaxFilt = 32;
-constexpr int kUvPad = 32;       // zero entries on both sides of every filter's (U, V) table
-constexpr int kFastSpread = 2;   // max (m_max - m_min) within a warp for the unclamped table reads
+constexpr int kUvPad = 40;       // zero entries on both sides of every filter's (U, V) table
+constexpr int kFastSpread = 10;  // max (m_max - m_min) within a warp for the unclamped table reads
 
 struct SynthArgs {
   int n_gal, n_tiles, n_chunk, n_kb, n_lam, n_filt, n_blue, n_blue_pad, uv_len;
   int k8_total;              // K/8 MMA steps actually needed (the last k-block may be partial)
+  int dbg;                   // experiments only (SB2_DBG): 1 skip filter sums, 2 skip dust exp, 4 two ring slots
+  int two_pass;              // 1: long K, cross terms summed before the hi*hi terms (single-CTA kernel only)
   const int* n_tiles_dev;    // actual tile count (<= n_tiles) when the batch was grouped on device, else nullptr
   const int* tile_k0;        // [n_tiles] first grid column (k) of each tile's weights, nullptr: 0
   const int4* tile_range;    // [n_tiles] {first, last wavelength chunk any filter of the tile needs, first bin & ~31, last bin}; nullptr: all
@@ -65,7 +69,7 @@ struct SynthArgs {
   const int* g_orig;
   const double* g_mscale;
   const unsigned* g_trunc;
-  float2* part;          // [2][n_filt][n_rows] partial filter numerators of the two epilogue groups
+  float2* part;          // [kMaxGroups][n_filt][n_rows] partial filter numerators of the epilogue groups
   long long n_rows;      // padded rows (n_tiles * 128)
   float* out_base;
   double* out_scaled;
@@ -89,24 +93,33 @@ __device__ __forceinline__ void ffma2_bcast(float2& acc, float s, float2 uv) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
 }
 
-// Fused epilogue of one CTA (warps 4-11): see the header comment.  kCta = 2: the CTA is one half of a pair that
+// Fused epilogue of one CTA (warps 3-14): see the header comment.  kCta = 2: the CTA is one half of a pair that
 // shares the MMA (cta_group::2); `unit` is then a pair of tiles, this CTA owns tile 2*unit + rank and hands its
 // accumulators back through the LEADER's tempty barriers (tempty_addr, shared::cluster).
-template <int kComp, int kNF, bool kSpec, int kCta>
+// Work split: warpgroup g takes the wavelength chunks with c % kGroups == g (a fixed function of the chunk, so a
+// galaxy's partial sums do not depend on what else is in the batch); the chunk's accumulator is TMEM buffer it % kBuf.
+// "Accumulator ready" barriers are PER GROUP (tfull_bar[2 g + (k & 1)] for the group's k-th chunk): an mbarrier
+// wait only carries one parity bit, so a waiter must see every phase of a barrier in order -- which a group does
+// for its own pair, but would not for per-buffer barriers that other groups also consume.
+template <int kComp, int kNF, bool kSpec, int kCta, int kN, int kGroups>
 __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* s_uv, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                               uint32_t tempty_addr, uint32_t tmem_base, int unit0, int unit_stride,
                                               int n_units, uint32_t cta_rank) {
-  constexpr int kLch = kBN / kComp;
-  constexpr int kSub = kLch / 32;
+  constexpr int kLch = kN / kComp;      // wavelengths per chunk
+  constexpr int kSub = kLch / 32;       // 32-wavelength sub-chunks per chunk
+  constexpr uint32_t kBuf = 512 / kN;   // TMEM accumulators (2 x 256 or 4 x 128 columns)
+  static_assert(kGroups <= (int)kBuf && kGroups <= kMaxGroups, "a group must own a whole accumulator while it drains it");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c_all_last = A.n_chunk - 1;
+  const int c_all_last = A.n_chunk * (kBN / kN) - 1;
+  const uint32_t grp = (uint32_t)(warp - kEpiWarp0) >> 2;
+  if (grp >= (uint32_t)kGroups) return;
   {
-    const uint32_t grp = (uint32_t)(warp - 4) >> 2;            // owns TMEM accumulator `grp` = chunks with (it & 1) == grp
-    const int et = (threadIdx.x - 128) & 127;                  // galaxy within tile == TMEM lane
+    const int et = (warp & 3) * 32 + lane;                     // galaxy within tile == TMEM lane (a warp may only touch
+                                                               // the TMEM lane quarter warp % 4)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t uv_base = smem_u32(s_uv);
     const unsigned FULL = 0xffffffffu;
-    uint32_t it = 0;
+    uint32_t it = 0, gk = 0;   // chunks seen by the CTA / chunks taken by this group
     for (int unit = unit0; unit < n_units; unit += unit_stride) {
       const int tile = unit * kCta + (int)cta_rank;
       const int4 cr = A.tile_range ? __ldg(A.tile_range + unit) : make_int4(0, c_all_last, 0, 0);
@@ -128,18 +141,17 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
 #pragma unroll
       for (int f = 0; f < kNF; ++f) acc[f] = make_float2(0.f, 0.f);
 
+      // lane f looks after filter f: sub-chunk starting at i0 overlaps its shifted window iff
+      // lo_f - 32 - mmax <= i0 <= hi_f - mmin  (warp-uniform bounds)
+      const int w_lo = (lane < A.n_filt ? A.filt_lo[lane < kMaxFilt ? lane : 0] : INT_MAX / 2) - 32 - mmax;
+      const int w_hi = (lane < A.n_filt ? A.filt_hi[lane < kMaxFilt ? lane : 0] : -1) - mmin;
       for (int c = cr.x; c <= cr.y; ++c, ++it) {
-        if ((it & 1u) != grp) continue;
-        // which filters overlap which 32-wavelength sub-chunk of this chunk: lane `sub` works it out for sub-chunk `sub`
-        unsigned cmask = 0u;
-        {
-          const int i0s = c * kLch + (lane & (kSub - 1)) * 32;
-          for (int f = 0; f < A.n_filt; ++f)
-            if (i0s + mmin <= A.filt_hi[f] && i0s + 31 + mmax >= A.filt_lo[f] - 1) cmask |= 1u << f;
-        }
-        mbar_wait(&tfull_bar[grp], (it >> 1) & 1u);
+        if ((uint32_t)c % (uint32_t)kGroups != grp) continue;
+        const uint32_t buf = it % kBuf;
+        mbar_wait(&tfull_bar[2 * grp + (gk & 1u)], (gk >> 1) & 1u, 0x600u + (it << 12));
+        ++gk;
         tc_fence_after();
-        const uint32_t t_acc = tmem_base + lane_base + grp * kBN;
+        const uint32_t t_acc = tmem_base + lane_base + buf * kN;
 #pragma unroll 1
         for (int sub = 0; sub < kSub; ++sub) {
           const int i0 = c * kLch + sub * 32;
@@ -147,6 +159,10 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
           float s[32];
           {
             uint32_t v[32];
+            if (A.dbg & 16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0x3f800000u;
+            } else
             tmem_ld_32x32b_x32(t_acc + sub * 32, v);
             const float4* kp = reinterpret_cast<const float4*>(A.kappa + i0);
             if constexpr (kComp == 2) {
@@ -165,6 +181,11 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
             } else {
               tmem_ld_wait();
 #pragma unroll
+              if (A.dbg & 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
+              } else
+#pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {  // ca goes into the final scale
                 const float4 k4 = __ldg(kp + j4);
                 s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x);
@@ -178,11 +199,11 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if constexpr (kCta == 2) mbar_arrive_cluster(tempty_addr + grp * 8u);   // the leader CTA's barrier
-              else mbar_arrive(tempty_bar + grp);
+              if constexpr (kCta == 2) mbar_arrive_cluster(tempty_addr + buf * 8u);   // the leader CTA's barrier
+              else mbar_arrive(tempty_bar + buf);
             }
           }
-          if (i0 < A.n_blue) {  // rows [n_blue, n_blue_pad) of the table hold 1
+          if (i0 < A.n_blue && !(A.dbg & 8)) {  // rows [n_blue, n_blue_pad) of the table hold 1
             const float* ig = A.igm + ((size_t)tile * A.n_blue_pad + i0) * 128 + et;
 #pragma unroll
             for (int j = 0; j < 32; ++j) s[j] *= __ldg(ig + j * 128);
@@ -197,7 +218,8 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
           }
           // filter numerators: (numU_f, numV_f) += s_i * (U_f[n], V_f[n]),  n = i + m ; loop over the filters whose
           // window overlaps this sub-chunk (warp-uniform), compact code: one body, accumulator picked by a switch
-          unsigned fm = __shfl_sync(FULL, cmask, sub);
+          unsigned fm = __ballot_sync(FULL, i0 >= w_lo && i0 <= w_hi);
+          if (A.dbg & 1) fm = 0u;
 #pragma unroll 1
           while (fm != 0u) {
             const int f = __ffs(fm) - 1;
@@ -258,9 +280,9 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + ((A.uv_len * 8 + 15) & ~15));
   uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * kStages;     // [2]        MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * kStages + 2;// [2]        epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* tfull_bar = bars + 2 * kStages;                       // [2 * kMaxGroups] MMA -> epilogue group (see epilogue_loop)
+  uint64_t* tempty_bar = bars + 2 * kStages + 2 * kMaxGroups;     // [2]              epilogue -> MMA, per TMEM accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kMaxGroups + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -269,7 +291,8 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }  // 4 warps per epilogue group
+    for (int b = 0; b < 2 * kMaxGroups; ++b) mbar_init(&tfull_bar[b], 1);
+    for (int b = 0; b < 2; ++b) mbar_init(&tempty_bar[b], 4);  // 4 warps per epilogue group
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -286,62 +309,88 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (see ptx.cuh).  two_pass (dense K): pass 0 streams all four
+    // operand tiles of a k-block for the two small cross terms, pass 1 streams the hi tiles again for hi*hi.
+    {
+      const uint32_t elected = elect_one() ? 1u : 0u;
+      const uint32_t s_addr = smem_u32(smem), full0 = smem_u32(full_bar);
+      const int n_tiles_u = warp_uniform(n_tiles), n_kb = A.n_kb, n_pass = A.two_pass ? 2 : 1;
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int k0 = A.tile_k0 ? __ldg(A.tile_k0 + tile) : 0;
+      for (int tile = blockIdx.x; tile < n_tiles_u; tile += gridDim.x) {
+        const int k0 = warp_uniform(A.tile_k0 ? __ldg(A.tile_k0 + tile) : 0);
         const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
-        for (int c = cr.x; c <= cr.y; ++c) {
-          for (int kb = 0; kb < A.n_kb; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * kStageBytes;
-            mbar_expect_tx(&full_bar[stage], kStageBytes);
-            tma_load_2d(st, &tm_w_hi, &full_bar[stage], kb * kBK, tile * kBM, kEvictNormal);
-            tma_load_2d(st + kABytes, &tm_w_lo, &full_bar[stage], kb * kBK, tile * kBM, kEvictNormal);
-            tma_load_2d(st + 2 * kABytes, &tm_g_hi, &full_bar[stage], k0 + kb * kBK, c * kBN, kEvictLast);
-            tma_load_2d(st + 2 * kABytes + kBBytes, &tm_g_lo, &full_bar[stage], k0 + kb * kBK, c * kBN, kEvictLast);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
+        for (int c = c_first; c <= c_last; ++c) {
+          for (int pass = 0; pass < n_pass; ++pass) {
+            const bool lo_tiles = (pass == 0);   // single pass: everything in pass 0
+            for (int kb = 0; kb < n_kb; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              const uint32_t st = s_addr + (uint32_t)stage * kStageBytes, fb = full0 + (uint32_t)stage * 8u;
+              mbar_expect_tx_e(elected, &full_bar[stage], lo_tiles ? kStageBytes : kABytes + kBBytes);
+              tma_load_2d_e(elected, st, &tm_w_hi, fb, kb * kBK, tile * kBM, kEvictNormal);
+              tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, c * kBN, kEvictLast);
+              if (lo_tiles) {
+                tma_load_2d_e(elected, st + kABytes, &tm_w_lo, fb, kb * kBK, tile * kBM, kEvictNormal);
+                tma_load_2d_e(elected, st + 2 * kABytes + kBBytes, &tm_g_lo, fb, k0 + kb * kBK, c * kBN, kEvictLast);
+              }
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // FP32 accumulation in the tensor core truncates, so the error grows with the number of accumulations made
+    // onto the (large) running sum: with a long K the small cross terms W_lo*G_hi + W_hi*G_lo are summed FIRST
+    // (two_pass), while the accumulator is still small, and the W_hi*G_hi terms after.
+    {
       constexpr uint32_t idesc = make_idesc_tf32(kBM, kBN);
+      const uint32_t elected = elect_one() ? 1u : 0u;
+      const uint32_t s_addr = smem_u32(smem);
+      const uint64_t desc0 = make_kmajor_sw128_desc(0);
+      const uint32_t tmem_u = (uint32_t)warp_uniform((int)tmem_base);
+      const int n_tiles_u = warp_uniform(n_tiles), n_kb = A.n_kb, k8_total = A.k8_total, two_pass = A.two_pass;
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      uint32_t gk0 = 0, gk1 = 0;   // chunks handed to epilogue group 0 / 1 so far
+      for (int tile = blockIdx.x; tile < n_tiles_u; tile += gridDim.x) {
         const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
-        for (int c = cr.x; c <= cr.y; ++c, ++it) {
+        const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
+        for (int c = c_first; c <= c_last; ++c, ++it) {
           const uint32_t buf = it & 1u;
           mbar_wait(&tempty_bar[buf], ((it >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * kBN;
-          for (int kb = 0; kb < A.n_kb; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t st = smem_u32(smem + stage * kStageBytes);
-            const int k4n = min(kBK / 8, A.k8_total - kb * (kBK / 8));
+          const uint32_t d_tmem = tmem_u + buf * kBN;
+          for (int pass = 0; pass <= two_pass; ++pass) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint64_t da = desc0 + (uint64_t)(((s_addr + stage * kStageBytes) & 0x3FFFF) >> 4);
+              const uint64_t db = da + (uint64_t)((2 * kABytes) >> 4);
+              const int k4n = min(kBK / 8, k8_total - kb * (kBK / 8));
 #pragma unroll
-            for (int k4 = 0; k4 < kBK / 8; ++k4) {
-              if (k4 >= k4n) break;
-              const uint64_t a_hi = make_kmajor_sw128_desc(st + k4 * 32);
-              const uint64_t a_lo = make_kmajor_sw128_desc(st + kABytes + k4 * 32);
-              const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * kABytes + k4 * 32);
-              const uint64_t b_lo = make_kmajor_sw128_desc(st + 2 * kABytes + kBBytes + k4 * 32);
-              umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
-              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+              for (int k4 = 0; k4 < kBK / 8; ++k4) {
+                if (k4 < k4n) {
+                  const uint64_t a_hi = da + (uint64_t)(k4 * 2), a_lo = da + (uint64_t)((kABytes >> 4) + k4 * 2);
+                  const uint64_t b_hi = db + (uint64_t)(k4 * 2), b_lo = db + (uint64_t)((kBBytes >> 4) + k4 * 2);
+                  if (pass == 0) {
+                    umma_tf32_e(elected, d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
+                    umma_tf32_e(elected, d_tmem, a_hi, b_lo, idesc, 1u);
+                  }
+                  if (pass == two_pass) umma_tf32_e(elected, d_tmem, a_hi, b_hi, idesc, 1u);
+                }
+              }
+              umma_commit_e(elected, &empty_bar[stage]);  // smem slot reusable once these MMAs retire
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull_bar[buf]);      // accumulator complete
+          if ((c & 1) == 0) { umma_commit_e(elected, &tfull_bar[0 + (gk0 & 1u)]); ++gk0; }   // accumulator complete:
+          else              { umma_commit_e(elected, &tfull_bar[2 + (gk1 & 1u)]); ++gk1; }   // wake the group that owns chunk c
         }
       }
     }
-  } else if (warp >= 4) {
-    epilogue_loop<kComp, kNF, kSpec, 1>(A, s_uv, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
+  } else if (warp >= kEpiWarp0) {
+    epilogue_loop<kComp, kNF, kSpec, 1, kBN, 2>(A, s_uv, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
   }
 
   tc_fence_before();
@@ -356,16 +405,22 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
 // CTA-pair variant for bracket-grouped (DeltaConstant) batches: K = 2*n_age_pad <= 128.
 //
 // A cluster of two CTAs works on a PAIR of tiles (256 galaxies of one metallicity bracket) with
-// tcgen05.mma.cta_group::2 (M = 256 over the pair, N = 256): each CTA keeps the hi/lo weights of ITS 128
+// tcgen05.mma.cta_group::2 (M = 256 over the pair, N = 128): each CTA keeps the hi/lo weights of ITS 128
 // galaxies resident in shared memory for the whole pair (loaded once instead of once per chunk) and streams
-// only ITS half (128 rows) of every G k-block, so the L2 -> SM traffic per flop is a third of the
+// only ITS half (64 rows) of every G k-block, so the L2 -> SM traffic per flop is a third of the
 // single-CTA kernel's, which was L2-bandwidth bound.  The leader CTA issues all MMAs; completion is
 // multicast to both CTAs' barriers; both CTAs run the fused epilogue on their own 128 TMEM lanes.
+#ifndef SB2_BN2
+#define SB2_BN2 128
+#endif
 constexpr int kW2Kb = 4;                          // resident k-blocks (K <= 128)
 constexpr int kW2Bytes = kW2Kb * 2 * kABytes;     // [kb][hi | lo] x 16 KiB = 128 KiB
-constexpr int kG2Half = (kBN / 2) * kBK * 4;      // 16 KiB: this CTA's 128 rows of one G k-block
+constexpr int kBN2 = SB2_BN2;                         // accumulator columns per chunk: 4 TMEM accumulators, two per epilogue
+                                                  // group, so the MMA of a group's next chunk overlaps its current one
+constexpr int kG2Half = (kBN2 / 2) * kBK * 4;     // 8 KiB: this CTA's 64 rows of one G k-block
 constexpr int kG2Slot = 2 * kG2Half;              // lo | hi
-constexpr int kG2Slots = 2;
+constexpr int kG2Slots = 512 / kBN2;        // 64 KiB ring either way
+constexpr int kT2Buf = 512 / kBN2;
 
 template <int kComp, int kNF, bool kSpec>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynthThreads, 1)
@@ -380,11 +435,11 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_uv) + ((A.uv_len * 8 + 15) & ~15));
   uint64_t* full_bar = bars;                        // [kG2Slots] TMA (both CTAs) -> MMA   (leader's copy is used)
   uint64_t* empty_bar = bars + kG2Slots;            // [kG2Slots] MMA -> TMA               (multicast to both)
-  uint64_t* tfull_bar = bars + 2 * kG2Slots;        // [2]        MMA -> epilogue          (multicast to both)
-  uint64_t* tempty_bar = bars + 2 * kG2Slots + 2;   // [2]        epilogues of both CTAs -> MMA (leader's copy)
-  uint64_t* wfull_bar = bars + 2 * kG2Slots + 4;    //            weights landed (both CTAs) -> MMA (leader's copy)
-  uint64_t* wempty_bar = bars + 2 * kG2Slots + 5;   //            MMA -> TMA: weights buffer free (multicast)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kG2Slots + 6);
+  uint64_t* tfull_bar = bars + 2 * kG2Slots;                            // [2 kMaxGroups] MMA -> epilogue group (multicast to both)
+  uint64_t* tempty_bar = tfull_bar + 2 * kMaxGroups;                    // [kT2Buf] epilogues of both CTAs -> MMA (leader's copy)
+  uint64_t* wfull_bar = tempty_bar + kT2Buf;                            //          weights landed (both CTAs) -> MMA (leader's copy)
+  uint64_t* wempty_bar = wfull_bar + 1;                                 //          MMA -> TMA: weights buffer free (multicast)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wempty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -394,7 +449,8 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kG2Slots; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }  // 4 warps x 2 CTAs
+    for (int b = 0; b < 2 * kMaxGroups; ++b) mbar_init(&tfull_bar[b], 1);
+    for (int b = 0; b < kT2Buf; ++b) mbar_init(&tempty_bar[b], 8);  // 4 warps x 2 CTAs
     mbar_init(wfull_bar, 2);
     mbar_init(wempty_bar, 1);
     fence_barrier_init();
@@ -410,81 +466,108 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   const int n_units = A.n_tiles_dev ? min(A.n_tiles, __ldg(A.n_tiles_dev)) : A.n_tiles;  // units = tile pairs
   const int unit0 = (int)(blockIdx.x >> 1), unit_stride = (int)(gridDim.x >> 1);
-  const int c_all_last = A.n_chunk - 1;
+  const int n_slots = (A.dbg & 4) ? 2 : kG2Slots;
+  const int c_all_last = A.n_chunk * (kBN / kBN2) - 1;   // tile_range counts 128-column chunks for this kernel
 
   if (warp == 0) {
     // ===================================================================== TMA producer (both CTAs)
-    if (lane == 0) {
-      const uint32_t wfull_l = mapa_u32(smem_u32(wfull_bar), 0);
-      uint32_t full_l[kG2Slots];
-      for (int s = 0; s < kG2Slots; ++s) full_l[s] = mapa_u32(smem_u32(&full_bar[s]), 0);
+    // warp-uniform loop, one elected lane issues (see ptx.cuh)
+    {
+      const uint32_t elected = elect_one() ? 1u : 0u;
+      const uint32_t rk = (uint32_t)warp_uniform((int)rank);
+      const uint32_t wfull_l = (uint32_t)warp_uniform((int)mapa_u32(smem_u32(wfull_bar), 0));
+      const uint32_t full_l0 = (uint32_t)warp_uniform((int)mapa_u32(smem_u32(full_bar), 0));
+      const uint32_t w_addr = smem_u32(s_w), g_addr = smem_u32(s_g);
+      const int n_units_u = warp_uniform(n_units), n_kb = A.n_kb;
       int slot = 0; uint32_t phase = 0, wphase = 0;
-      for (int unit = unit0; unit < n_units; unit += unit_stride) {
-        const int tile = unit * 2 + (int)rank;
-        const int k0 = A.tile_k0 ? __ldg(A.tile_k0 + unit) : 0;
+      for (int unit = unit0; unit < n_units_u; unit += unit_stride) {
+        const int tile = unit * 2 + (int)rk;
+        const int k0 = warp_uniform(A.tile_k0 ? __ldg(A.tile_k0 + unit) : 0);
         const int4 cr = A.tile_range ? __ldg(A.tile_range + unit) : make_int4(0, c_all_last, 0, 0);
+        const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
         // this CTA's weights, resident for the whole unit
-        mbar_wait(wempty_bar, wphase ^ 1);
-        if (rank == 0) mbar_expect_tx(wfull_bar, 2 * kW2Bytes); else mbar_arrive_cluster(wfull_l);
+        mbar_wait(wempty_bar, wphase ^ 1, 0x100u + (uint32_t)unit);
+        if (rk == 0) mbar_expect_tx_e(elected, wfull_bar, 2 * kW2Bytes); else mbar_arrive_cluster_e(elected, wfull_l);
+#pragma unroll
         for (int kb = 0; kb < kW2Kb; ++kb) {
-          tma_load_2d_2sm(s_w + kb * 2 * kABytes, &tm_w_hi, wfull_l, kb * kBK, tile * kBM, kEvictFirst);
-          tma_load_2d_2sm(s_w + kb * 2 * kABytes + kABytes, &tm_w_lo, wfull_l, kb * kBK, tile * kBM, kEvictFirst);
+          tma_load_2d_2sm_e(elected, w_addr + kb * 2 * kABytes, &tm_w_hi, wfull_l, kb * kBK, tile * kBM, kEvictFirst);
+          tma_load_2d_2sm_e(elected, w_addr + kb * 2 * kABytes + kABytes, &tm_w_lo, wfull_l, kb * kBK, tile * kBM, kEvictFirst);
         }
         wphase ^= 1;
-        for (int c = cr.x; c <= cr.y; ++c) {
-          for (int kb = 0; kb < A.n_kb; ++kb) {
-            mbar_wait(&empty_bar[slot], phase ^ 1);
-            if (rank == 0) mbar_expect_tx(&full_bar[slot], 2 * kG2Slot); else mbar_arrive_cluster(full_l[slot]);
-            uint8_t* st = s_g + slot * kG2Slot;
-            tma_load_2d_2sm(st, &tm_g_lo, full_l[slot], k0 + kb * kBK, c * kBN + (int)rank * (kBN / 2), kEvictLast);
-            tma_load_2d_2sm(st + kG2Half, &tm_g_hi, full_l[slot], k0 + kb * kBK, c * kBN + (int)rank * (kBN / 2), kEvictLast);
-            if (++slot == kG2Slots) { slot = 0; phase ^= 1; }
+        for (int c = c_first; c <= c_last; ++c) {
+          // this CTA's 64 rows of the chunk's G^T block.  The grid is laid out in 256-row blocks
+          // [comp][256/comp wavelengths]; accumulator columns are [rank 0 rows | rank 1 rows]
+          const int g_row = (kComp == 1) ? c * kBN2 + (int)rk * (kBN2 / 2)
+                                         : (c >> 1) * kBN + (int)rk * (kBN / 2) + (c & 1) * (kBN2 / 2);
+          for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(&empty_bar[slot], phase ^ 1, 0x200u + (uint32_t)slot);
+            const uint32_t fl = full_l0 + (uint32_t)slot * 8u;
+            if (rk == 0) mbar_expect_tx_e(elected, &full_bar[slot], 2 * kG2Slot); else mbar_arrive_cluster_e(elected, fl);
+            const uint32_t st = g_addr + (uint32_t)slot * kG2Slot;
+            tma_load_2d_2sm_e(elected, st, &tm_g_lo, fl, k0 + kb * kBK, g_row, kEvictLast);
+            tma_load_2d_2sm_e(elected, st + kG2Half, &tm_g_hi, fl, k0 + kb * kBK, g_row, kEvictLast);
+            if (++slot == n_slots) { slot = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(2 * kBM, kBN);
+    // The whole warp runs this loop with warp-uniform values; one elected lane issues (see umma_tf32_2sm_e).
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(2 * kBM, kBN2);
+      const uint32_t elected = elect_one() ? 1u : 0u;
       const uint32_t w_base = smem_u32(s_w), g_base = smem_u32(s_g);
+      const uint64_t desc0 = make_kmajor_sw128_desc(0);
+      const int n_kb = A.n_kb, k8_total = A.k8_total;
+      const uint32_t tmem_u = (uint32_t)warp_uniform((int)tmem_base);
+      const int n_units_u = warp_uniform(n_units);
       int slot = 0; uint32_t phase = 0, wphase = 0, it = 0;
-      for (int unit = unit0; unit < n_units; unit += unit_stride) {
-        const int4 cr = A.tile_range ? __ldg(A.tile_range + unit) : make_int4(0, c_all_last, 0, 0);
-        mbar_wait(wfull_bar, wphase);
+      constexpr int kG = (kT2Buf >= 3 ? 3 : 2);   // epilogue groups (must match the epilogue_loop instantiation below)
+      uint32_t gk0 = 0, gk1 = 0, gk2 = 0;         // chunks handed to each epilogue group so far
+      for (int unit = unit0; unit < n_units_u; unit += unit_stride) {
+        int4 cr = A.tile_range ? __ldg(A.tile_range + unit) : make_int4(0, c_all_last, 0, 0);
+        const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
+        mbar_wait(wfull_bar, wphase, 0x300u + (uint32_t)unit);
         wphase ^= 1;
         tc_fence_after();
-        for (int c = cr.x; c <= cr.y; ++c, ++it) {
-          const uint32_t buf = it & 1u;
-          mbar_wait(&tempty_bar[buf], ((it >> 1) & 1u) ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        for (int c = c_first; c <= c_last; ++c, ++it) {
+          const uint32_t buf = it % kT2Buf;
+          mbar_wait(&tempty_bar[buf], ((it / kT2Buf) & 1u) ^ 1u, 0x400u + (it << 12));  // both CTAs' epilogues have drained this accumulator
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * kBN;
-          for (int kb = 0; kb < A.n_kb; ++kb) {
-            mbar_wait(&full_bar[slot], phase);
+          const uint32_t d_tmem = tmem_u + buf * kBN2;
+          for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(&full_bar[slot], phase, 0x500u + (uint32_t)slot + (it << 12));
             tc_fence_after();
-            const uint32_t sa = w_base + kb * 2 * kABytes, sb = g_base + slot * kG2Slot;
-            const int k4n = min(kBK / 8, A.k8_total - kb * (kBK / 8));
+            // descriptors differ only in the 14-bit start-address field (bytes >> 4)
+            const uint64_t da = desc0 + (uint64_t)(((w_base + kb * 2 * kABytes) & 0x3FFFF) >> 4);
+            const uint64_t db = desc0 + (uint64_t)(((g_base + slot * kG2Slot) & 0x3FFFF) >> 4);
+            const int k4n = min(kBK / 8, k8_total - kb * (kBK / 8));
 #pragma unroll
             for (int k4 = 0; k4 < kBK / 8; ++k4) {
-              if (k4 >= k4n) break;
-              const uint64_t a_hi = make_kmajor_sw128_desc(sa + k4 * 32);
-              const uint64_t a_lo = make_kmajor_sw128_desc(sa + kABytes + k4 * 32);
-              const uint64_t b_lo = make_kmajor_sw128_desc(sb + k4 * 32);
-              const uint64_t b_hi = make_kmajor_sw128_desc(sb + kG2Half + k4 * 32);
-              umma_tf32_2sm(d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
-              umma_tf32_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_tf32_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+              if (k4 < k4n) {
+                const uint64_t a_hi = da + (uint64_t)(k4 * 2), a_lo = da + (uint64_t)((kABytes >> 4) + k4 * 2);
+                const uint64_t b_lo = db + (uint64_t)(k4 * 2), b_hi = db + (uint64_t)((kG2Half >> 4) + k4 * 2);
+                if (!(A.dbg & 32)) {
+                umma_tf32_2sm_e(elected, d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
+                umma_tf32_2sm_e(elected, d_tmem, a_hi, b_lo, idesc, 1u);
+                umma_tf32_2sm_e(elected, d_tmem, a_hi, b_hi, idesc, 1u);
+                }
+              }
             }
-            umma_commit_2sm(&empty_bar[slot], 3);   // ring slot reusable in both CTAs
-            if (++slot == kG2Slots) { slot = 0; phase ^= 1; }
+            umma_commit_2sm_e(elected, &empty_bar[slot], 3);   // ring slot reusable in both CTAs
+            if (++slot == n_slots) { slot = 0; phase ^= 1; }
           }
-          umma_commit_2sm(&tfull_bar[buf], 3);      // accumulator complete in both CTAs
+          const int g = c % kG;                                // accumulator complete in both CTAs: wake the owners of chunk c
+          if (g == 0)      { umma_commit_2sm_e(elected, &tfull_bar[0 + (gk0 & 1u)], 3); ++gk0; }
+          else if (g == 1) { umma_commit_2sm_e(elected, &tfull_bar[2 + (gk1 & 1u)], 3); ++gk1; }
+          else             { umma_commit_2sm_e(elected, &tfull_bar[4 + (gk2 & 1u)], 3); ++gk2; }
         }
-        umma_commit_2sm(wempty_bar, 3);             // weights buffers reusable in both CTAs
+        umma_commit_2sm_e(elected, wempty_bar, 3);             // weights buffers reusable in both CTAs
       }
     }
-  } else if (warp >= 4) {
-    epilogue_loop<kComp, kNF, kSpec, 2>(A, s_uv, tfull_bar, tempty_bar, mapa_u32(smem_u32(tempty_bar), 0), tmem_base, unit0,
+  } else if (warp >= kEpiWarp0) {
+    epilogue_loop<kComp, kNF, kSpec, 2, kBN2, (kT2Buf >= 3 ? 3 : 2)>(A, s_uv, tfull_bar, tempty_bar, mapa_u32(smem_u32(tempty_bar), 0), tmem_base, unit0,
                                         unit_stride, n_units, rank);
   }
 
@@ -501,7 +584,7 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
 struct FinalizeArgs {
   const float2* part;
   long long n_rows;
-  int n_filt, n_comp;
+  int n_filt, n_comp, n_groups;
   const float *g_beta, *g_gamma, *g_scale, *g_ca;
   const int* g_orig;
   const double* g_mscale;
@@ -523,8 +606,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   const unsigned trunc = A.g_trunc[row];
   const double mscale = A.g_mscale[row];
   for (int f = 0; f < A.n_filt; ++f) {
-    const float2 a = A.part[(size_t)f * A.n_rows + row], b = A.part[((size_t)A.n_filt + f) * A.n_rows + row];
-    const float nu = a.x + b.x, nv = a.y + b.y;
+    float nu = 0.f, nv = 0.f;
+    for (int g = 0; g < A.n_groups; ++g) {   // fixed order: plane g holds the chunks with c % n_groups == g
+      const float2 a = A.part[((size_t)g * A.n_filt + f) * A.n_rows + row];
+      nu += a.x; nv += a.y;
+    }
     float flux = fmaf(beta, nv, gamma * nu) / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * sc;
     if ((trunc >> f) & 1u) flux = __int_as_float(0x7fc00000);
     if (A.out_base) A.out_base[(size_t)orig * A.n_filt + f] = flux;

@@ -35,16 +35,21 @@ for r in rows[2:]:
             print(f"  {k:85s} {d[k]:>16s} {u[k]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-h = None; data = []; seen = set()
+sections = []  # (kernel name, header index map, rows)
+name = "?"
 for r in rows:
-    if r and r[0] == "Address":
-        h = {x: i for i, x in enumerate(r)}; continue
-    if h and r and r[0].startswith("0x") and len(r) > h["# Samples"] and r[0] not in seen:
-        seen.add(r[0]); data.append(r)
-if data:
+    if r and r[0] == "Kernel Name":
+        name = r[1] if len(r) > 1 else "?"
+    elif r and r[0] == "Address":
+        sections.append((name, {x: i for i, x in enumerate(r)}, []))
+    elif sections and r and r[0].startswith("0x"):
+        sections[-1][2].append(r)
+for name, h, data in sections:
+    if not re.search(pat, name) or not data:
+        continue
     S, E, SRC = h["# Samples"], h["Instructions Executed"], h["Source"]
     tot = sum(int(r[S]) for r in data); ti = sum(int(r[E]) for r in data)
-    print(f"-- source page: {len(data)} SASS lines, {tot} samples, {ti} warp instructions executed")
+    print(f"-- source page of {name[:80]}: {len(data)} SASS lines, {tot} samples, {ti} warp instructions executed")
     for r in sorted(data, key=lambda r: -int(r[S]))[:25]:
         print(f"  {int(r[S]):8d} {100*int(r[S])/max(tot,1):5.1f}%  exec {int(r[E]):10d}  {r[SRC][:90]}")
     c = Counter(); cs = Counter()
