@@ -48,8 +48,9 @@ enum { SB2_ZD_DELTA_LINEAR = 0, SB2_ZD_DELTA_LOG10 = 1, SB2_ZD_NORMAL_LINEAR = 2
  * sb2_model_create time.                                                                  */
 typedef struct sb2_model_desc {
   int32_t n_age, n_z, n_lam, n_comp, n_filt;
-  int32_t n_age_pad; /* n_age rounded up to a multiple of 4: grid column of (iz, ia) is iz*n_age_pad + ia,
-                      * so every metallicity's columns start 16-byte aligned (TMA box origin)        */
+  int32_t n_age_pad; /* n_age rounded up to a multiple of 4 (8 recommended): grid column of (iz, ia) is
+                      * iz*n_age_pad + ia, so every metallicity's columns start 16-byte (32-byte) aligned,
+                      * which the TMA box origin of a bracket-grouped tile needs                        */
   int32_t k_pad;   /* n_age_pad*n_z rounded up to a multiple of 32                          */
   int32_t n_chunk; /* wavelength chunks of 256/n_comp bins                                  */
   const double* log10ages;     /* [n_age]                                                   */

@@ -193,6 +193,9 @@ struct sb2_model {
   double* stage_flux64 = nullptr;
   CUtensorMap tm_w_hi, tm_w_lo, tm_g_hi, tm_g_lo;
   size_t smem_bytes = 0;
+  // host entry point: copy-in / compute / copy-out streams and per-slice events (slices are pipelined)
+  cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
+  cudaEvent_t ev_in[8] = {}, ev_done[8] = {};
   unsigned int* wait_dbg = nullptr;  // host-mapped: who timed out in an mbarrier wait (protocol-bug watchdog)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start | sorted | weights built | synthesised
   bool ev_valid = false;
@@ -235,6 +238,14 @@ int sb2_model_destroy(sb2_model* m) {
     if (p) cudaFree(p);
   for (cudaEvent_t e : m->ev)
     if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 8; ++i) {
+    if (m->ev_in[i]) cudaEventDestroy(m->ev_in[i]);
+    if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+  }
+  if (m->st_h2d) cudaStreamDestroy(m->st_h2d);
+  if (m->st_comp) cudaStreamDestroy(m->st_comp);
+  if (m->st_d2h) cudaStreamDestroy(m->st_d2h);
+  if (m->wait_dbg) cudaFreeHost(m->wait_dbg);
   delete m;
   return SB2_OK;
 }
@@ -373,6 +384,16 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
     if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), m->wait_dbg, 0) == cudaSuccess)
       cudaMemcpyToSymbol(sb2::g_wait_dbg, &dptr, sizeof(dptr));
   }
+  bool ok = cudaStreamCreateWithFlags(&m->st_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&m->st_comp, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&m->st_d2h, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 8 && ok; ++i)
+    ok = cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    sb2_model_destroy(m);
+    return fail(SB2_ERR_CUDA, "stream / event creation failed");
+  }
   for (int i = 0; i < 4; ++i) {
     if (cudaEventCreate(&m->ev[i]) != cudaSuccess) {
       sb2_model_destroy(m);
@@ -491,7 +512,9 @@ int check_params(const sb2_model* m, const sb2_params* p) {
 // A unit of work of the contraction kernel: one 128-galaxy tile, or a PAIR of tiles for the CTA-pair kernel
 // (bracket-grouped batches).
 int rows_per_unit(const sb2_model* m, bool delta) {
-  return (delta && m->smem2_bytes > 0 && !std::getenv("SB2_NO_CTA_PAIR")) ? 256 : 128;
+  // The CTA-pair kernel (synth2_kernel) is parity-tested but not yet faster than the single-CTA kernel on B200
+  // (both sit on the same synchronisation/epilogue floor); it is opt-in: SB2_CTA_PAIR=1.
+  return (delta && m->smem2_bytes > 0 && std::getenv("SB2_CTA_PAIR")) ? 256 : 128;
 }
 // Rows the grouped layout of a batch of n galaxies can occupy (every group is padded to whole units).
 long long padded_rows(const sb2_model* m, long long n, bool delta) {
@@ -590,6 +613,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.tile_k0 = m->tile_k0;
   a.k8_total = (delta ? m->wd_stride : d.k_pad) / 8;
   a.dbg = std::getenv("SB2_DBG") ? std::atoi(std::getenv("SB2_DBG")) : 0;
+  if (a.dbg & 256) a.n_kb = 1;   // experiment: one k-block per chunk
   a.two_pass = (!delta && !std::getenv("SB2_ONE_PASS")) ? 1 : 0;
   a.n_chunk = d.n_chunk; a.n_kb = (a.k8_total + 3) / 4; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
   a.n_blue = d.n_blue; a.n_blue_pad = m->n_blue_pad; a.uv_len = m->uv_len;
@@ -613,7 +637,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   }
   if (rc == SB2_OK) {
     sb2::FinalizeArgs fa{};
-    fa.part = m->part; fa.n_rows = a.n_rows; fa.n_filt = d.n_filt; fa.n_comp = d.n_comp; fa.n_groups = (rpu == 256 && sb2::kT2Buf >= 3) ? 3 : 2;
+    fa.part = m->part; fa.n_rows = a.n_rows; fa.n_filt = d.n_filt; fa.n_comp = d.n_comp; fa.n_groups = (rpu == 256 && sb2::kT2Buf >= 3 && sb2::kMaxGroups >= 3) ? 3 : 2;
     fa.g_beta = m->g_beta; fa.g_gamma = m->g_gamma; fa.g_scale = m->g_scale; fa.g_ca = m->g_ca; fa.g_orig = m->g_orig;
     fa.g_mscale = m->g_mscale; fa.g_trunc = m->g_trunc; fa.out_base = flux_base; fa.out_scaled = flux_scaled;
     for (int f = 0; f < d.n_filt; ++f) { fa.filt_su[f] = m->h_su[f]; fa.filt_sdv[f] = m->h_sdv[f]; }
@@ -642,30 +666,53 @@ int sb2_synth_photometry_host(sb2_model* m, const sb2_params* p, float* flux_bas
   if (spec_out) return fail(SB2_ERR_INVALID, "spec_out is only supported through the device entry point");
   CU_TRY(cudaSetDevice(m->device));
   const size_t n = (size_t)p->n;
-  double* s = m->stage_params;
-  sb2_params dp = *p;
-  auto put = [&](const double* src, size_t count, const double** dst) -> cudaError_t {
-    *dst = nullptr;
-    if (!src) return cudaSuccess;
-    cudaError_t e = cudaMemcpyAsync(s, src, count * sizeof(double), cudaMemcpyHostToDevice, 0);
-    *dst = s;
-    s += count;
-    return e;
-  };
-  CU_TRY(put(p->redshift, n, &dp.redshift));
-  CU_TRY(put(p->log_mass, n, &dp.log_mass));
-  CU_TRY(put(p->tau_v, n, &dp.tau_v));
-  CU_TRY(put(p->zd_value, n, &dp.zd_value));
-  CU_TRY(put(p->zd_sigma, n, &dp.zd_sigma));
-  CU_TRY(put(p->coef_att, n, &dp.coef_att));
-  CU_TRY(put(p->coef_unatt, n, &dp.coef_unatt));
-  CU_TRY(put(p->sfh_rows, n * p->sfh_stride, &dp.sfh_rows));
-  rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux : nullptr, flux_scaled ? m->stage_flux64 : nullptr,
-                            nullptr, nullptr);
-  if (rc != SB2_OK) return rc;
-  if (flux_base) CU_TRY(cudaMemcpyAsync(flux_base, m->stage_flux, n * m->d.n_filt * 4, cudaMemcpyDeviceToHost, 0));
-  if (flux_scaled) CU_TRY(cudaMemcpyAsync(flux_scaled, m->stage_flux64, n * m->d.n_filt * 8, cudaMemcpyDeviceToHost, 0));
-  CU_TRY(cudaStreamSynchronize(0));
+  const int nf = m->d.n_filt;
+  // Device layout of the staged parameters: one full-length array per field; slices [a, b) of the batch are
+  // copied in on st_h2d, synthesised on st_comp and copied out on st_d2h, so the PCIe copies of one slice
+  // overlap the kernels of its neighbours (pinned host buffers are needed for the overlap, not for correctness).
+  double* base = m->stage_params;
+  const double* src[8] = {p->redshift, p->log_mass, p->tau_v, p->zd_value, p->zd_sigma, p->coef_att, p->coef_unatt, p->sfh_rows};
+  double* dev[8];
+  for (int i = 0; i < 8; ++i) {
+    const size_t w = (i == 7) ? (size_t)p->sfh_stride : 1;
+    dev[i] = src[i] ? base : nullptr;
+    if (src[i]) base += n * w;
+  }
+  int n_slice = 1;
+  {
+    const char* e = std::getenv("SB2_HOST_SLICES");
+    const long long want = e ? std::atoll(e) : (long long)(n / 400000);  // measured best on B200: 2 slices per 1M galaxies
+    n_slice = (int)std::min<long long>(8, std::max<long long>(1, want));
+  }
+  const size_t per = ((n + n_slice - 1) / n_slice + 255) / 256 * 256;
+  for (int sl = 0; sl < n_slice; ++sl) {
+    const size_t a = (size_t)sl * per, b = std::min(n, a + per);
+    if (a >= b) break;
+    for (int i = 0; i < 8; ++i) {
+      if (!src[i]) continue;
+      const size_t w = (i == 7) ? (size_t)p->sfh_stride : 1;
+      CU_TRY(cudaMemcpyAsync(dev[i] + a * w, src[i] + a * w, (b - a) * w * sizeof(double), cudaMemcpyHostToDevice, m->st_h2d));
+    }
+    CU_TRY(cudaEventRecord(m->ev_in[sl], m->st_h2d));
+    CU_TRY(cudaStreamWaitEvent(m->st_comp, m->ev_in[sl], 0));
+    sb2_params dp = *p;
+    dp.n = (int64_t)(b - a);
+    dp.redshift = dev[0] + a; dp.log_mass = dev[1] ? dev[1] + a : nullptr; dp.tau_v = dev[2] ? dev[2] + a : nullptr;
+    dp.zd_value = dev[3] + a; dp.zd_sigma = dev[4] ? dev[4] + a : nullptr;
+    dp.coef_att = dev[5] ? dev[5] + a : nullptr; dp.coef_unatt = dev[6] ? dev[6] + a : nullptr;
+    dp.sfh_rows = dev[7] + a * p->sfh_stride;
+    rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux + a * nf : nullptr,
+                              flux_scaled ? m->stage_flux64 + a * nf : nullptr, nullptr, m->st_comp);
+    if (rc != SB2_OK) return rc;
+    CU_TRY(cudaEventRecord(m->ev_done[sl], m->st_comp));
+    CU_TRY(cudaStreamWaitEvent(m->st_d2h, m->ev_done[sl], 0));
+    if (flux_base)
+      CU_TRY(cudaMemcpyAsync(flux_base + a * nf, m->stage_flux + a * nf, (b - a) * nf * 4, cudaMemcpyDeviceToHost, m->st_d2h));
+    if (flux_scaled)
+      CU_TRY(cudaMemcpyAsync(flux_scaled + a * nf, m->stage_flux64 + a * nf, (b - a) * nf * 8, cudaMemcpyDeviceToHost, m->st_d2h));
+  }
+  CU_TRY(cudaStreamSynchronize(m->st_d2h));
+  CU_TRY(cudaStreamSynchronize(m->st_comp));
   return SB2_OK;
 }
 

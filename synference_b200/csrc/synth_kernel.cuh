@@ -41,9 +41,23 @@ constexpr int kStages = 2;
 constexpr int kABytes = kBM * kBK * 4;         // 16 KiB
 constexpr int kBBytes = kBN * kBK * 4;         // 32 KiB
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // hi + lo of both operands = 96 KiB
-constexpr int kSynthThreads = 480;             // 3 control warps + 3 epilogue warpgroups
-constexpr int kEpiWarp0 = 3;                   // first epilogue warp
-constexpr int kMaxGroups = 3;                  // epilogue warpgroups in the CTA (partial-numerator planes)
+// Bottleneck experiments (skip filter sums / dust exp / IGM / TMEM loads / MMAs / G or W traffic): compiled in only
+// with -DSB2_EXPERIMENTS, selected at run time with the SB2_DBG bit mask.
+#ifdef SB2_EXPERIMENTS
+#define SB2_DBG_BITS(A) ((A).dbg)
+#else
+#define SB2_DBG_BITS(A) 0
+#endif
+
+#ifndef SB2_GROUPS
+#define SB2_GROUPS 2
+#endif
+constexpr int kMaxGroups = SB2_GROUPS;         // epilogue warpgroups in the CTA (partial-numerator planes)
+constexpr int kEpiWarp0 = 3;                   // first epilogue warp (warps 0-2: TMA producer, MMA issuer, TMEM allocator)
+constexpr int kSynthThreads = 32 * kEpiWarp0 + 128 * kMaxGroups;
+constexpr int kTfPerGroup = 4;                 // "accumulator ready" barriers per epilogue group: one per chunk that can be
+                                               // outstanding (<= number of TMEM accumulators), so no barrier is ever committed
+                                               // twice before its group has seen the first completion
 constexpr int kMaxFilt = 32;
 constexpr int kUvPad = 40;       // zero entries on both sides of every filter's (U, V) table
 constexpr int kFastSpread = 10;  // max (m_max - m_min) within a warp for the unclamped table reads
@@ -93,12 +107,22 @@ __device__ __forceinline__ void ffma2_bcast(float2& acc, float s, float2 uv) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
 }
 
+// Chunk visiting order.  Every CTA (pair) walks the chunks of a unit cyclically from a different start: units that are
+// neighbours in the (bracket, redshift) order need the SAME G^T tiles, and with one common order all 148 SMs request the
+// same few L2 lines at the same moment (measured: per-chunk time independent of bytes, MMAs and epilogue work).
+__device__ __forceinline__ int chunk_at(int c_first, int n_c, int rot, int j) {
+  int c = j + rot;
+  if (c >= n_c) c -= n_c;
+  return c_first + c;
+}
+__device__ __forceinline__ int chunk_rot(int n_c, unsigned who) { return n_c > 0 ? (int)((who * 5u) % (unsigned)n_c) : 0; }
+
 // Fused epilogue of one CTA (warps 3-14): see the header comment.  kCta = 2: the CTA is one half of a pair that
 // shares the MMA (cta_group::2); `unit` is then a pair of tiles, this CTA owns tile 2*unit + rank and hands its
 // accumulators back through the LEADER's tempty barriers (tempty_addr, shared::cluster).
 // Work split: warpgroup g takes the wavelength chunks with c % kGroups == g (a fixed function of the chunk, so a
 // galaxy's partial sums do not depend on what else is in the batch); the chunk's accumulator is TMEM buffer it % kBuf.
-// "Accumulator ready" barriers are PER GROUP (tfull_bar[2 g + (k & 1)] for the group's k-th chunk): an mbarrier
+// "Accumulator ready" barriers are PER GROUP (tfull_bar[kTfPerGroup g + k % kTfPerGroup] for the group's k-th chunk): an mbarrier
 // wait only carries one parity bit, so a waiter must see every phase of a barrier in order -- which a group does
 // for its own pair, but would not for per-buffer barriers that other groups also consume.
 template <int kComp, int kNF, bool kSpec, int kCta, int kN, int kGroups>
@@ -108,7 +132,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
   constexpr int kLch = kN / kComp;      // wavelengths per chunk
   constexpr int kSub = kLch / 32;       // 32-wavelength sub-chunks per chunk
   constexpr uint32_t kBuf = 512 / kN;   // TMEM accumulators (2 x 256 or 4 x 128 columns)
-  static_assert(kGroups <= (int)kBuf && kGroups <= kMaxGroups, "a group must own a whole accumulator while it drains it");
+  static_assert((int)kBuf <= kTfPerGroup && kGroups <= (int)kBuf && kGroups <= kMaxGroups, "a group must own a whole accumulator while it drains it");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c_all_last = A.n_chunk * (kBN / kN) - 1;
   const uint32_t grp = (uint32_t)(warp - kEpiWarp0) >> 2;
@@ -145,10 +169,12 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
       // lo_f - 32 - mmax <= i0 <= hi_f - mmin  (warp-uniform bounds)
       const int w_lo = (lane < A.n_filt ? A.filt_lo[lane < kMaxFilt ? lane : 0] : INT_MAX / 2) - 32 - mmax;
       const int w_hi = (lane < A.n_filt ? A.filt_hi[lane < kMaxFilt ? lane : 0] : -1) - mmin;
-      for (int c = cr.x; c <= cr.y; ++c, ++it) {
+      const int n_c = cr.y - cr.x + 1, rot = chunk_rot(n_c, blockIdx.x / kCta);
+      for (int j = 0; j < n_c; ++j, ++it) {
+        const int c = chunk_at(cr.x, n_c, rot, j);
         if ((uint32_t)c % (uint32_t)kGroups != grp) continue;
         const uint32_t buf = it % kBuf;
-        mbar_wait(&tfull_bar[2 * grp + (gk & 1u)], (gk >> 1) & 1u, 0x600u + (it << 12));
+        mbar_wait(&tfull_bar[kTfPerGroup * grp + (gk % kTfPerGroup)], (gk / kTfPerGroup) & 1u, 0x600u + (it << 12));
         ++gk;
         tc_fence_after();
         const uint32_t t_acc = tmem_base + lane_base + buf * kN;
@@ -159,7 +185,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
           float s[32];
           {
             uint32_t v[32];
-            if (A.dbg & 16) {
+            if (SB2_DBG_BITS(A) & 16) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0x3f800000u;
             } else
@@ -181,7 +207,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
             } else {
               tmem_ld_wait();
 #pragma unroll
-              if (A.dbg & 2) {
+              if (SB2_DBG_BITS(A) & 2) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
               } else
@@ -203,7 +229,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               else mbar_arrive(tempty_bar + buf);
             }
           }
-          if (i0 < A.n_blue && !(A.dbg & 8)) {  // rows [n_blue, n_blue_pad) of the table hold 1
+          if (i0 < A.n_blue && !(SB2_DBG_BITS(A) & 8)) {  // rows [n_blue, n_blue_pad) of the table hold 1
             const float* ig = A.igm + ((size_t)tile * A.n_blue_pad + i0) * 128 + et;
 #pragma unroll
             for (int j = 0; j < 32; ++j) s[j] *= __ldg(ig + j * 128);
@@ -219,7 +245,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
           // filter numerators: (numU_f, numV_f) += s_i * (U_f[n], V_f[n]),  n = i + m ; loop over the filters whose
           // window overlaps this sub-chunk (warp-uniform), compact code: one body, accumulator picked by a switch
           unsigned fm = __ballot_sync(FULL, i0 >= w_lo && i0 <= w_hi);
-          if (A.dbg & 1) fm = 0u;
+          if (SB2_DBG_BITS(A) & 1) fm = 0u;
 #pragma unroll 1
           while (fm != 0u) {
             const int f = __ffs(fm) - 1;
@@ -280,9 +306,9 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + ((A.uv_len * 8 + 15) & ~15));
   uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * kStages;                       // [2 * kMaxGroups] MMA -> epilogue group (see epilogue_loop)
-  uint64_t* tempty_bar = bars + 2 * kStages + 2 * kMaxGroups;     // [2]              epilogue -> MMA, per TMEM accumulator
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kMaxGroups + 2);
+  uint64_t* tfull_bar = bars + 2 * kStages;                       // [kTfPerGroup * kMaxGroups] MMA -> epilogue group (see epilogue_loop)
+  uint64_t* tempty_bar = tfull_bar + kTfPerGroup * kMaxGroups;    // [2]              epilogue -> MMA, per TMEM accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -291,7 +317,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2 * kMaxGroups; ++b) mbar_init(&tfull_bar[b], 1);
+    for (int b = 0; b < kTfPerGroup * kMaxGroups; ++b) mbar_init(&tfull_bar[b], 1);
     for (int b = 0; b < 2; ++b) mbar_init(&tempty_bar[b], 4);  // 4 warps per epilogue group
     fence_barrier_init();
   }
@@ -320,7 +346,9 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
         const int k0 = warp_uniform(A.tile_k0 ? __ldg(A.tile_k0 + tile) : 0);
         const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
         const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
-        for (int c = c_first; c <= c_last; ++c) {
+        const int n_c = c_last - c_first + 1, rot = chunk_rot(n_c, blockIdx.x);
+        for (int j = 0; j < n_c; ++j) {
+          const int c = chunk_at(c_first, n_c, rot, j);
           for (int pass = 0; pass < n_pass; ++pass) {
             const bool lo_tiles = (pass == 0);   // single pass: everything in pass 0
             for (int kb = 0; kb < n_kb; ++kb) {
@@ -356,7 +384,9 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
       for (int tile = blockIdx.x; tile < n_tiles_u; tile += gridDim.x) {
         const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
         const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
-        for (int c = c_first; c <= c_last; ++c, ++it) {
+        const int n_c = c_last - c_first + 1, rot = chunk_rot(n_c, blockIdx.x);
+        for (int j = 0; j < n_c; ++j, ++it) {
+          const int c = chunk_at(c_first, n_c, rot, j);
           const uint32_t buf = it & 1u;
           mbar_wait(&tempty_bar[buf], ((it >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
           tc_fence_after();
@@ -384,8 +414,8 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
-          if ((c & 1) == 0) { umma_commit_e(elected, &tfull_bar[0 + (gk0 & 1u)]); ++gk0; }   // accumulator complete:
-          else              { umma_commit_e(elected, &tfull_bar[2 + (gk1 & 1u)]); ++gk1; }   // wake the group that owns chunk c
+          if ((c & 1) == 0) { umma_commit_e(elected, &tfull_bar[gk0 % kTfPerGroup]); ++gk0; }                 // accumulator complete:
+          else              { umma_commit_e(elected, &tfull_bar[kTfPerGroup + gk1 % kTfPerGroup]); ++gk1; }   // wake the group that owns chunk c
         }
       }
     }
@@ -435,8 +465,8 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_uv) + ((A.uv_len * 8 + 15) & ~15));
   uint64_t* full_bar = bars;                        // [kG2Slots] TMA (both CTAs) -> MMA   (leader's copy is used)
   uint64_t* empty_bar = bars + kG2Slots;            // [kG2Slots] MMA -> TMA               (multicast to both)
-  uint64_t* tfull_bar = bars + 2 * kG2Slots;                            // [2 kMaxGroups] MMA -> epilogue group (multicast to both)
-  uint64_t* tempty_bar = tfull_bar + 2 * kMaxGroups;                    // [kT2Buf] epilogues of both CTAs -> MMA (leader's copy)
+  uint64_t* tfull_bar = bars + 2 * kG2Slots;                            // [kTfPerGroup kMaxGroups] MMA -> epilogue group (multicast to both)
+  uint64_t* tempty_bar = tfull_bar + kTfPerGroup * kMaxGroups;          // [kT2Buf] epilogues of both CTAs -> MMA (leader's copy)
   uint64_t* wfull_bar = tempty_bar + kT2Buf;                            //          weights landed (both CTAs) -> MMA (leader's copy)
   uint64_t* wempty_bar = wfull_bar + 1;                                 //          MMA -> TMA: weights buffer free (multicast)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wempty_bar + 1);
@@ -449,7 +479,7 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kG2Slots; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2 * kMaxGroups; ++b) mbar_init(&tfull_bar[b], 1);
+    for (int b = 0; b < kTfPerGroup * kMaxGroups; ++b) mbar_init(&tfull_bar[b], 1);
     for (int b = 0; b < kT2Buf; ++b) mbar_init(&tempty_bar[b], 8);  // 4 warps x 2 CTAs
     mbar_init(wfull_bar, 2);
     mbar_init(wempty_bar, 1);
@@ -466,7 +496,7 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   const int n_units = A.n_tiles_dev ? min(A.n_tiles, __ldg(A.n_tiles_dev)) : A.n_tiles;  // units = tile pairs
   const int unit0 = (int)(blockIdx.x >> 1), unit_stride = (int)(gridDim.x >> 1);
-  const int n_slots = (A.dbg & 4) ? 2 : kG2Slots;
+  const int n_slots = (SB2_DBG_BITS(A) & 4) ? 2 : kG2Slots;
   const int c_all_last = A.n_chunk * (kBN / kBN2) - 1;   // tile_range counts 128-column chunks for this kernel
 
   if (warp == 0) {
@@ -487,14 +517,17 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
         const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
         // this CTA's weights, resident for the whole unit
         mbar_wait(wempty_bar, wphase ^ 1, 0x100u + (uint32_t)unit);
-        if (rk == 0) mbar_expect_tx_e(elected, wfull_bar, 2 * kW2Bytes); else mbar_arrive_cluster_e(elected, wfull_l);
+        if (rk == 0) mbar_expect_tx_e(elected, wfull_bar, (SB2_DBG_BITS(A) & 128) ? 0 : 2 * kW2Bytes); else mbar_arrive_cluster_e(elected, wfull_l);
+        if (!(SB2_DBG_BITS(A) & 128))
 #pragma unroll
         for (int kb = 0; kb < kW2Kb; ++kb) {
           tma_load_2d_2sm_e(elected, w_addr + kb * 2 * kABytes, &tm_w_hi, wfull_l, kb * kBK, tile * kBM, kEvictFirst);
           tma_load_2d_2sm_e(elected, w_addr + kb * 2 * kABytes + kABytes, &tm_w_lo, wfull_l, kb * kBK, tile * kBM, kEvictFirst);
         }
         wphase ^= 1;
-        for (int c = c_first; c <= c_last; ++c) {
+        const int n_c = c_last - c_first + 1, rot = chunk_rot(n_c, blockIdx.x >> 1);
+        for (int j = 0; j < n_c; ++j) {
+          const int c = chunk_at(c_first, n_c, rot, j);
           // this CTA's 64 rows of the chunk's G^T block.  The grid is laid out in 256-row blocks
           // [comp][256/comp wavelengths]; accumulator columns are [rank 0 rows | rank 1 rows]
           const int g_row = (kComp == 1) ? c * kBN2 + (int)rk * (kBN2 / 2)
@@ -502,10 +535,14 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(&empty_bar[slot], phase ^ 1, 0x200u + (uint32_t)slot);
             const uint32_t fl = full_l0 + (uint32_t)slot * 8u;
-            if (rk == 0) mbar_expect_tx_e(elected, &full_bar[slot], 2 * kG2Slot); else mbar_arrive_cluster_e(elected, fl);
             const uint32_t st = g_addr + (uint32_t)slot * kG2Slot;
+            if (SB2_DBG_BITS(A) & 64) {   // experiment: no G traffic
+              if (rk == 0) mbar_expect_tx_e(elected, &full_bar[slot], 0); else mbar_arrive_cluster_e(elected, fl);
+            } else {
+            if (rk == 0) mbar_expect_tx_e(elected, &full_bar[slot], 2 * kG2Slot); else mbar_arrive_cluster_e(elected, fl);
             tma_load_2d_2sm_e(elected, st, &tm_g_lo, fl, k0 + kb * kBK, g_row, kEvictLast);
             tma_load_2d_2sm_e(elected, st + kG2Half, &tm_g_hi, fl, k0 + kb * kBK, g_row, kEvictLast);
+            }
             if (++slot == n_slots) { slot = 0; phase ^= 1; }
           }
         }
@@ -523,7 +560,7 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
       const uint32_t tmem_u = (uint32_t)warp_uniform((int)tmem_base);
       const int n_units_u = warp_uniform(n_units);
       int slot = 0; uint32_t phase = 0, wphase = 0, it = 0;
-      constexpr int kG = (kT2Buf >= 3 ? 3 : 2);   // epilogue groups (must match the epilogue_loop instantiation below)
+      constexpr int kG = (kT2Buf >= 3 && kMaxGroups >= 3 ? 3 : 2);   // epilogue groups (must match the epilogue_loop instantiation below)
       uint32_t gk0 = 0, gk1 = 0, gk2 = 0;         // chunks handed to each epilogue group so far
       for (int unit = unit0; unit < n_units_u; unit += unit_stride) {
         int4 cr = A.tile_range ? __ldg(A.tile_range + unit) : make_int4(0, c_all_last, 0, 0);
@@ -531,7 +568,9 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
         mbar_wait(wfull_bar, wphase, 0x300u + (uint32_t)unit);
         wphase ^= 1;
         tc_fence_after();
-        for (int c = c_first; c <= c_last; ++c, ++it) {
+        const int n_c = c_last - c_first + 1, rot = chunk_rot(n_c, blockIdx.x >> 1);
+        for (int j = 0; j < n_c; ++j, ++it) {
+          const int c = chunk_at(c_first, n_c, rot, j);
           const uint32_t buf = it % kT2Buf;
           mbar_wait(&tempty_bar[buf], ((it / kT2Buf) & 1u) ^ 1u, 0x400u + (it << 12));  // both CTAs' epilogues have drained this accumulator
           tc_fence_after();
@@ -548,7 +587,7 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
               if (k4 < k4n) {
                 const uint64_t a_hi = da + (uint64_t)(k4 * 2), a_lo = da + (uint64_t)((kABytes >> 4) + k4 * 2);
                 const uint64_t b_lo = db + (uint64_t)(k4 * 2), b_hi = db + (uint64_t)((kG2Half >> 4) + k4 * 2);
-                if (!(A.dbg & 32)) {
+                if (!(SB2_DBG_BITS(A) & 32)) {
                 umma_tf32_2sm_e(elected, d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
                 umma_tf32_2sm_e(elected, d_tmem, a_hi, b_lo, idesc, 1u);
                 umma_tf32_2sm_e(elected, d_tmem, a_hi, b_hi, idesc, 1u);
@@ -559,15 +598,15 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
             if (++slot == n_slots) { slot = 0; phase ^= 1; }
           }
           const int g = c % kG;                                // accumulator complete in both CTAs: wake the owners of chunk c
-          if (g == 0)      { umma_commit_2sm_e(elected, &tfull_bar[0 + (gk0 & 1u)], 3); ++gk0; }
-          else if (g == 1) { umma_commit_2sm_e(elected, &tfull_bar[2 + (gk1 & 1u)], 3); ++gk1; }
-          else             { umma_commit_2sm_e(elected, &tfull_bar[4 + (gk2 & 1u)], 3); ++gk2; }
+          if (g == 0)      { umma_commit_2sm_e(elected, &tfull_bar[gk0 % kTfPerGroup], 3); ++gk0; }
+          else if (g == 1) { umma_commit_2sm_e(elected, &tfull_bar[kTfPerGroup + gk1 % kTfPerGroup], 3); ++gk1; }
+          else             { umma_commit_2sm_e(elected, &tfull_bar[(kMaxGroups >= 3 ? 2 * kTfPerGroup : 0) + gk2 % kTfPerGroup], 3); ++gk2; }
         }
         umma_commit_2sm_e(elected, wempty_bar, 3);             // weights buffers reusable in both CTAs
       }
     }
   } else if (warp >= kEpiWarp0) {
-    epilogue_loop<kComp, kNF, kSpec, 2, kBN2, (kT2Buf >= 3 ? 3 : 2)>(A, s_uv, tfull_bar, tempty_bar, mapa_u32(smem_u32(tempty_bar), 0), tmem_base, unit0,
+    epilogue_loop<kComp, kNF, kSpec, 2, kBN2, (kT2Buf >= 3 && kMaxGroups >= 3 ? 3 : 2)>(A, s_uv, tfull_bar, tempty_bar, mapa_u32(smem_u32(tempty_bar), 0), tmem_base, unit0,
                                         unit_stride, n_units, rank);
   }
 

@@ -112,7 +112,9 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
     n_comp = len(comps)
     na, nz = grid.log10ages.size, grid.metallicity.size
     k = na * nz
-    na_pad = (na + 3) // 4 * 4          # every metallicity's columns start 16-byte aligned (TMA box origin)
+    # every metallicity's columns start 32-byte aligned: TMA needs a 16-byte aligned box origin, and measured on
+    # B200 a 32-byte aligned origin streams ~5% faster than a 16-byte aligned one (no further gain at 128 B)
+    na_pad = (na + 7) // 8 * 8
     k_pad = (na_pad * nz + 31) // 32 * 32
     lch = CHUNK_COLS // n_comp
     n_chunk = (n_lam + lch - 1) // lch

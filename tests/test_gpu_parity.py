@@ -210,3 +210,76 @@ def test_invalid_arguments_raise(engines):
     big = make_workload("cfg1", (1 << 15) + 1)
     out = eng.photometry(big.params, scaled=False)        # larger than max_batch: split into batches
     assert out.shape == ((1 << 15) + 1, 8) and np.isfinite(out).all()
+
+
+# ---- bracket-grouped layout, CTA-pair kernel, pipelined host entry ------------------------------------
+
+def _delta_linear_params(w, n, seed=3):
+    """DeltaConstant by (linear) metallicity, including values below / above / exactly on the grid."""
+    p = w.params.slice(slice(0, n))
+    zgrid = np.asarray(w.grid.metallicity)
+    rng = np.random.default_rng(seed)
+    zv = 10.0 ** rng.uniform(np.log10(zgrid[0]) - 0.3, np.log10(zgrid[-1]) + 0.2, n)
+    zv[:13] = zgrid                        # exactly on every grid point
+    zv[13], zv[14] = zgrid[0] * 0.1, zgrid[-1] * 3.0
+    return GalaxyParams(p.redshift, p.sfh_type, p.sfh_rows, 0, zv, None, p.log_mass, p.tau_v)
+
+
+def test_delta_linear_brackets_and_clamps(engines):
+    """Every metallicity bracket, both clamps and on-grid values, through the grouped layout."""
+    w, eng = engines("cfg2", 600)
+    q = _delta_linear_params(w, 600)
+    W = eng.weights(q)
+    np.testing.assert_allclose(W, A.weights_matrix(q, w.grid.log10ages, w.grid.metallicity), rtol=0, atol=1e-13)
+    assert_flux_close(eng.photometry(q, scaled=False), oracle_flux(w, params=q, c=True))
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 129])
+def test_tiny_batches_one_bracket(engines, n):
+    """A handful of galaxies in ONE bracket: eleven empty groups, one partly filled tile."""
+    w, eng = engines("cfg2", 200)
+    p = w.params.slice(slice(0, n))
+    q = GalaxyParams(p.redshift, p.sfh_type, p.sfh_rows, p.zd_type, np.full(n, -2.05), None, p.log_mass, p.tau_v)
+    assert_flux_close(eng.photometry(q, scaled=False), oracle_flux(w, params=q, c=True))
+
+
+def test_results_do_not_depend_on_batch_composition(engines):
+    """Chunks are handed to epilogue groups by chunk index, partial sums are added in a fixed order, and the
+    host entry's slices are independent batches: a galaxy's fluxes are bit-identical alone, in a batch, and
+    under any slicing of the batch."""
+    import os
+    w, eng = engines("cfg2", 3000)
+    full = eng.photometry(w.params, scaled=False)
+    for sl in (slice(7, 8), slice(1000, 1300), slice(2990, 3000)):
+        assert np.array_equal(eng.photometry(w.params.slice(sl), scaled=False), full[sl])
+    os.environ["SB2_HOST_SLICES"] = "3"
+    try:
+        assert np.array_equal(eng.photometry(w.params, scaled=False), full)
+    finally:
+        del os.environ["SB2_HOST_SLICES"]
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_cta_pair_kernel_matches_oracle_and_single_cta(engines, name):
+    """synth2_kernel (cta_group::2, weights resident in shared memory) is opt-in; it must agree with the oracle
+    and, since both kernels multiply the same operands in the same order, bit for bit with the default kernel."""
+    import os
+    w, eng = engines(name, 2500)
+    single = eng.photometry(w.params, scaled=False)
+    os.environ["SB2_CTA_PAIR"] = "1"
+    try:
+        pair = eng.photometry(w.params, scaled=False)
+        spec = eng.spectra(w.params.slice(slice(0, 300)))
+    finally:
+        del os.environ["SB2_CTA_PAIR"]
+    want, spec_want = oracle_flux(w, params=w.params.slice(slice(0, 300)), spectra=True)
+    assert_flux_close(pair[:300], want)
+    big = spec_want > 1e-25 * spec_want.max(axis=1, keepdims=True)
+    assert (np.abs(spec[big] - spec_want[big]) / spec_want[big]).max() < FLUX_RTOL
+    np.testing.assert_allclose(pair, single, rtol=3e-6)
+
+
+def test_watchdog_record_is_empty_after_good_runs(engines):
+    w, eng = engines("cfg1", 64)
+    eng.photometry(w.params, scaled=False)
+    assert eng.lib.sb2_wait_debug(eng._h) == b""

@@ -110,14 +110,18 @@ def test_tf32_split_properties():
 def test_grid_layout_and_scaling():
     w = make_workload("cfg2", 4)
     t = build_tables(w.grid, w.emission_model, w.emission_key, w.filters)
-    na, nz, nl = t["n_age"], t["n_z"], t["n_lam"]
-    assert t["k_pad"] % 32 == 0 and t["k_pad"] >= na * nz and t["n_chunk"] * 256 // t["n_comp"] >= nl
+    na, nz, nl, nap = t["n_age"], t["n_z"], t["n_lam"], t["n_age_pad"]
+    # every metallicity's block of columns starts 32-byte aligned (TMA box origin of a bracket-grouped tile)
+    assert nap % 8 == 0 and nap >= na
+    assert t["k_pad"] % 32 == 0 and t["k_pad"] >= nap * nz and t["n_chunk"] * 256 // t["n_comp"] >= nl
     att, un = w.emission_model.recipe(w.emission_key)
     comp = att if att.any() else un
     g = (t["gt_hi"].astype(np.float64) + t["gt_lo"]) * t["grid_scale"]
     for (ia, iz, il) in ((0, 0, 0), (50, 12, nl - 1), (17, 5, 1234), (3, 9, 255), (3, 9, 256)):
-        assert g[il, iz * na + ia] == pytest.approx(comp[ia, iz, il], rel=1e-6)
-    assert np.all(g[nl:] == 0) and np.all(g[:, na * nz:] == 0)
+        assert g[il, iz * nap + ia] == pytest.approx(comp[ia, iz, il], rel=1e-6)
+    assert np.all(g[nl:] == 0) and np.all(g[:, nap * nz:] == 0)
+    pad_cols = np.concatenate([np.arange(iz * nap + na, (iz + 1) * nap) for iz in range(nz)])
+    assert np.all(g[:, pad_cols] == 0)
 
 
 def test_two_component_layout():
@@ -127,12 +131,12 @@ def test_two_component_layout():
     t = build_tables(w.grid, em, "emergent", w.filters)
     assert t["n_comp"] == 2
     att, un = em.recipe("emergent")
-    na = t["n_age"]
+    nap = t["n_age_pad"]
     g = (t["gt_hi"].astype(np.float64) + t["gt_lo"]) * t["grid_scale"]
     il, ia, iz = 700, 20, 4
     chunk, j = divmod(il, 128)
-    assert g[chunk * 256 + j, iz * na + ia] == pytest.approx(att[ia, iz, il], rel=1e-6)
-    assert g[chunk * 256 + 128 + j, iz * na + ia] == pytest.approx(un[ia, iz, il], rel=1e-6)
+    assert g[chunk * 256 + j, iz * nap + ia] == pytest.approx(att[ia, iz, il], rel=1e-6)
+    assert g[chunk * 256 + 128 + j, iz * nap + ia] == pytest.approx(un[ia, iz, il], rel=1e-6)
     # Ly-alpha escape applies to the single bin nearest 1215.67 A only (A5)
     lam = np.asarray(w.grid.lam)
     jl = int(np.argmin(np.abs(lam - 1215.67)))
