@@ -149,6 +149,15 @@ int sb2_last_stage_ms(sb2_model* m, float* out3);
 int sb2_synth_photometry_host(sb2_model* m, const sb2_params* params, float* flux_base, double* flux_scaled,
                               float* spec_out);
 
+/* Asynchronous form for streams of batches (a library is generated batch by batch, library.py:2447-2694
+ * `batch_size`): submit() enqueues copy-in, kernels and copy-out of one batch on the model's three streams using
+ * staging slot 0 or 1 and returns; wait() blocks until that slot's results are in the caller's host buffers.
+ * Alternating the slots overlaps the PCIe copies of one batch with the kernels of the next.  The host buffers
+ * (pinned for real overlap) must stay valid and untouched until wait(); one model serves one host thread. */
+int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* params, float* flux_base, double* flux_scaled,
+                                     int slot);
+int sb2_synth_photometry_host_wait(sb2_model* m, int slot);
+
 /* Depth-based scatter + flux->AB feature rows on DEVICE buffers.
  * Replaces SBI_Fitter._apply_depths (sbi_runner.py:580-691) and the AB branch of
  * create_feature_array_from_raw_photometry (sbi_runner.py:1698-1716, 1927-1932).

@@ -18,6 +18,7 @@ SFH_ROW = 24
 EXPORTED_SYMBOLS = (
     "sb2_last_error", "sb2_device_count", "sb2_model_create", "sb2_model_destroy", "sb2_build_weights",
     "sb2_synth_photometry", "sb2_synth_photometry_host", "sb2_depth_noise_features", "sb2_last_stage_ms", "sb2_wait_debug",
+    "sb2_synth_photometry_host_submit", "sb2_synth_photometry_host_wait",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -80,6 +81,8 @@ def load():
     lib.sb2_synth_photometry.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]
     lib.sb2_synth_photometry_host.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sb2_synth_photometry_host_submit.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int]
+    lib.sb2_synth_photometry_host_wait.argtypes = [C.c_void_p, C.c_int]
     lib.sb2_last_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.sb2_depth_noise_features.argtypes = [
         C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_uint64,

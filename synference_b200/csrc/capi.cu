@@ -188,9 +188,12 @@ struct sb2_model {
   void* cub_tmp = nullptr;
   size_t cub_bytes = 0;
   // host-entry staging (device side)
-  double* stage_params = nullptr;  // redshift | log_mass | tau_v | zd_value | zd_sigma | ca | cb | sfh rows
-  float* stage_flux = nullptr;
-  double* stage_flux64 = nullptr;
+  // two staging slots, so the copies of one batch overlap the kernels of the next (sb2_synth_photometry_host_submit)
+  double* stage_params[2] = {nullptr, nullptr};  // redshift | log_mass | tau_v | zd_value | zd_sigma | ca | cb | sfh rows
+  float* stage_flux[2] = {nullptr, nullptr};
+  double* stage_flux64[2] = {nullptr, nullptr};
+  cudaEvent_t ev_slot[2] = {nullptr, nullptr};   // slot's results are on the host
+  bool slot_busy[2] = {false, false};
   CUtensorMap tm_w_hi, tm_w_lo, tm_g_hi, tm_g_lo;
   size_t smem_bytes = 0;
   // host entry point: copy-in / compute / copy-out streams and per-slice events (slices are pipelined)
@@ -232,12 +235,14 @@ int sb2_model_destroy(sb2_model* m) {
   void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->filt_uv, m->filt_lo,
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
-                  m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params,
-                  m->stage_flux, m->stage_flux64};
+                  m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params[0],
+                  m->stage_params[1], m->stage_flux[0], m->stage_flux[1], m->stage_flux64[0], m->stage_flux64[1]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : m->ev)
     if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i)
+    if (m->ev_slot[i]) cudaEventDestroy(m->ev_slot[i]);
   for (int i = 0; i < 8; ++i) {
     if (m->ev_in[i]) cudaEventDestroy(m->ev_in[i]);
     if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
@@ -355,9 +360,11 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   m->cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)m->cap);
   AL(cub_tmp, m->cub_bytes + 16);
-  AL(stage_params, (size_t)m->cap * (7 + SB2_SFH_ROW) * 8);
-  AL(stage_flux, (size_t)m->cap * d->n_filt * 4);
-  AL(stage_flux64, (size_t)m->cap * d->n_filt * 8);
+  for (int sl = 0; sl < 2; ++sl) {
+    AL(stage_params[sl], (size_t)m->cap * (7 + SB2_SFH_ROW) * 8);
+    AL(stage_flux[sl], (size_t)m->cap * d->n_filt * 4);
+    AL(stage_flux64[sl], (size_t)m->cap * d->n_filt * 8);
+  }
 #undef AL
   if ((rc = make_tmap(&m->tm_w_hi, m->w_hi, np, d->k_pad, sb2::kBM)) != SB2_OK ||
       (rc = make_tmap(&m->tm_w_lo, m->w_lo, np, d->k_pad, sb2::kBM)) != SB2_OK ||
@@ -390,6 +397,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   for (int i = 0; i < 8 && ok; ++i)
     ok = cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreateWithFlags(&m->ev_slot[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     sb2_model_destroy(m);
     return fail(SB2_ERR_CUDA, "stream / event creation failed");
@@ -659,18 +667,39 @@ int sb2_last_stage_ms(sb2_model* m, float* out3) {
   return SB2_OK;
 }
 
+int sb2_synth_photometry_host_wait(sb2_model* m, int slot) {
+  if (!m || slot < 0 || slot > 1) return fail(SB2_ERR_INVALID, "bad slot");
+  if (!m->slot_busy[slot]) return SB2_OK;
+  CU_TRY(cudaSetDevice(m->device));
+  CU_TRY(cudaEventSynchronize(m->ev_slot[slot]));
+  m->slot_busy[slot] = false;
+  return SB2_OK;
+}
+
 int sb2_synth_photometry_host(sb2_model* m, const sb2_params* p, float* flux_base, double* flux_scaled,
                               float* spec_out) {
+  if (spec_out) return fail(SB2_ERR_INVALID, "spec_out is only supported through the device entry point");
+  int rc = sb2_synth_photometry_host_submit(m, p, flux_base, flux_scaled, 0);
+  if (rc != SB2_OK) return rc;
+  return sb2_synth_photometry_host_wait(m, 0);
+}
+
+int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* flux_base, double* flux_scaled, int slot) {
   int rc = check_params(m, p);
   if (rc != SB2_OK) return rc;
-  if (spec_out) return fail(SB2_ERR_INVALID, "spec_out is only supported through the device entry point");
+  if (slot < 0 || slot > 1) return fail(SB2_ERR_INVALID, "slot must be 0 or 1");
+  if (!flux_base && !flux_scaled) return fail(SB2_ERR_INVALID, "no output requested");
   CU_TRY(cudaSetDevice(m->device));
+  if (m->slot_busy[slot]) {   // the slot's staging buffers are still in use by an unfinished submit
+    rc = sb2_synth_photometry_host_wait(m, slot);
+    if (rc != SB2_OK) return rc;
+  }
   const size_t n = (size_t)p->n;
   const int nf = m->d.n_filt;
   // Device layout of the staged parameters: one full-length array per field; slices [a, b) of the batch are
   // copied in on st_h2d, synthesised on st_comp and copied out on st_d2h, so the PCIe copies of one slice
   // overlap the kernels of its neighbours (pinned host buffers are needed for the overlap, not for correctness).
-  double* base = m->stage_params;
+  double* base = m->stage_params[slot];
   const double* src[8] = {p->redshift, p->log_mass, p->tau_v, p->zd_value, p->zd_sigma, p->coef_att, p->coef_unatt, p->sfh_rows};
   double* dev[8];
   for (int i = 0; i < 8; ++i) {
@@ -681,10 +710,20 @@ int sb2_synth_photometry_host(sb2_model* m, const sb2_params* p, float* flux_bas
   int n_slice = 1;
   {
     const char* e = std::getenv("SB2_HOST_SLICES");
-    const long long want = e ? std::atoll(e) : (long long)(n / 400000);  // measured best on B200: 2 slices per 1M galaxies
+    // measured on B200: each extra slice costs ~0.3 ms of per-launch overhead, 2 slices per 1M galaxies is best for a
+    // lone batch; when the other slot is in flight the neighbouring batch already provides the overlap
+    const long long want = e ? std::atoll(e) : (m->slot_busy[slot ^ 1] ? 1 : (long long)(n / 400000));
     n_slice = (int)std::min<long long>(8, std::max<long long>(1, want));
   }
   const size_t per = ((n + n_slice - 1) / n_slice + 255) / 256 * 256;
+  const bool trace = std::getenv("SB2_TRACE") != nullptr;   // per-slice timeline on stderr (diagnostics)
+  cudaEvent_t tr[1 + 8 * 4] = {};
+  if (trace) {
+    for (auto& e : tr) cudaEventCreate(&e);
+    cudaEventRecord(tr[0], m->st_h2d);
+    cudaStreamWaitEvent(m->st_comp, tr[0], 0);
+    cudaStreamWaitEvent(m->st_d2h, tr[0], 0);
+  }
   for (int sl = 0; sl < n_slice; ++sl) {
     const size_t a = (size_t)sl * per, b = std::min(n, a + per);
     if (a >= b) break;
@@ -694,25 +733,38 @@ int sb2_synth_photometry_host(sb2_model* m, const sb2_params* p, float* flux_bas
       CU_TRY(cudaMemcpyAsync(dev[i] + a * w, src[i] + a * w, (b - a) * w * sizeof(double), cudaMemcpyHostToDevice, m->st_h2d));
     }
     CU_TRY(cudaEventRecord(m->ev_in[sl], m->st_h2d));
+    if (trace) cudaEventRecord(tr[1 + sl * 4 + 0], m->st_h2d);
     CU_TRY(cudaStreamWaitEvent(m->st_comp, m->ev_in[sl], 0));
+    if (trace) cudaEventRecord(tr[1 + sl * 4 + 1], m->st_comp);
     sb2_params dp = *p;
     dp.n = (int64_t)(b - a);
     dp.redshift = dev[0] + a; dp.log_mass = dev[1] ? dev[1] + a : nullptr; dp.tau_v = dev[2] ? dev[2] + a : nullptr;
     dp.zd_value = dev[3] + a; dp.zd_sigma = dev[4] ? dev[4] + a : nullptr;
     dp.coef_att = dev[5] ? dev[5] + a : nullptr; dp.coef_unatt = dev[6] ? dev[6] + a : nullptr;
     dp.sfh_rows = dev[7] + a * p->sfh_stride;
-    rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux + a * nf : nullptr,
-                              flux_scaled ? m->stage_flux64 + a * nf : nullptr, nullptr, m->st_comp);
+    rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux[slot] + a * nf : nullptr,
+                              flux_scaled ? m->stage_flux64[slot] + a * nf : nullptr, nullptr, m->st_comp);
     if (rc != SB2_OK) return rc;
     CU_TRY(cudaEventRecord(m->ev_done[sl], m->st_comp));
+    if (trace) cudaEventRecord(tr[1 + sl * 4 + 2], m->st_comp);
     CU_TRY(cudaStreamWaitEvent(m->st_d2h, m->ev_done[sl], 0));
     if (flux_base)
-      CU_TRY(cudaMemcpyAsync(flux_base + a * nf, m->stage_flux + a * nf, (b - a) * nf * 4, cudaMemcpyDeviceToHost, m->st_d2h));
+      CU_TRY(cudaMemcpyAsync(flux_base + a * nf, m->stage_flux[slot] + a * nf, (b - a) * nf * 4, cudaMemcpyDeviceToHost, m->st_d2h));
     if (flux_scaled)
-      CU_TRY(cudaMemcpyAsync(flux_scaled + a * nf, m->stage_flux64 + a * nf, (b - a) * nf * 8, cudaMemcpyDeviceToHost, m->st_d2h));
+      CU_TRY(cudaMemcpyAsync(flux_scaled + a * nf, m->stage_flux64[slot] + a * nf, (b - a) * nf * 8, cudaMemcpyDeviceToHost, m->st_d2h));
+    if (trace) cudaEventRecord(tr[1 + sl * 4 + 3], m->st_d2h);
   }
-  CU_TRY(cudaStreamSynchronize(m->st_d2h));
-  CU_TRY(cudaStreamSynchronize(m->st_comp));
+  CU_TRY(cudaEventRecord(m->ev_slot[slot], m->st_d2h));
+  m->slot_busy[slot] = true;
+  if (trace) {
+    cudaEventSynchronize(m->ev_slot[slot]);
+    for (int sl = 0; sl < n_slice && (size_t)sl * per < n; ++sl) {
+      float t[4];
+      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tr[0], tr[1 + sl * 4 + k]);
+      std::fprintf(stderr, "[sb2 trace] slice %d: h2d done %.3f ms | kernels %.3f -> %.3f ms | d2h done %.3f ms\n", sl, t[0], t[1], t[2], t[3]);
+    }
+    for (auto& e : tr) cudaEventDestroy(e);
+  }
   return SB2_OK;
 }
 

@@ -272,21 +272,36 @@ class SynthEngine:
     # ---- host-buffer entry (what a drop-in caller uses) --------------------------------------
     def photometry(self, params: GalaxyParams, scaled=True, out=None):
         """Fluxes [nJy] as a host array ``(N, n_filt)``: float64 scaled by stellar mass
-        (``float32(base) * 10**log_mass / base_mass``, ``library.py:4588-4609``) or float32 at base mass."""
+        (``float32(base) * 10**log_mass / base_mass``, ``library.py:4588-4609``) or float32 at base mass.
+
+        Populations larger than ``max_batch`` run batch by batch through the two staging slots of the C ABI, so
+        the copies of one batch overlap the kernels of the next."""
         n = len(params)
         res = out if out is not None else np.empty((n, self.n_filt), dtype=np.float64 if scaled else np.float32)
-        for a in range(0, n, self.max_batch):
+        pending = []
+        for i, a in enumerate(range(0, n, self.max_batch)):
             b = min(n, a + self.max_batch)
-            keep = []
-            s = self._fill(params.slice(slice(a, b)), self._host_ptr_factory(keep))
-            dst = res[a:b]
-            assert dst.flags.c_contiguous
-            if scaled:
-                rc = self.lib.sb2_synth_photometry_host(self._h, C.byref(s), None, dst.ctypes.data, None)
-            else:
-                rc = self.lib.sb2_synth_photometry_host(self._h, C.byref(s), dst.ctypes.data, None, None)
-            _capi.check(rc, "sb2_synth_photometry_host")
+            if len(pending) == 2:
+                self.wait(pending.pop(0))
+            pending.append(self.submit(params.slice(slice(a, b)), res[a:b], scaled=scaled, slot=i & 1))
+        for t in pending:
+            self.wait(t)
         return res
+
+    def submit(self, params: GalaxyParams, out, scaled=True, slot=0):
+        """Enqueue one batch (``len(params) <= max_batch``) and return a ticket for :meth:`wait`; ``out`` is the
+        host array the results land in (pinned memory gives real copy/compute overlap)."""
+        assert out.flags.c_contiguous and out.shape == (len(params), self.n_filt)
+        assert out.dtype == (np.float64 if scaled else np.float32)
+        keep = [out]
+        s = self._fill(params, self._host_ptr_factory(keep))
+        rc = self.lib.sb2_synth_photometry_host_submit(self._h, C.byref(s), None if scaled else out.ctypes.data,
+                                                       out.ctypes.data if scaled else None, int(slot))
+        _capi.check(rc, "sb2_synth_photometry_host_submit")
+        return (int(slot), keep)
+
+    def wait(self, ticket):
+        _capi.check(self.lib.sb2_synth_photometry_host_wait(self._h, ticket[0]), "sb2_synth_photometry_host_wait")
 
     # ---- device entry (torch tensors stay on the GPU) ------------------------------------------
     def to_device(self, params: GalaxyParams):
