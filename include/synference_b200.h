@@ -87,6 +87,15 @@ typedef struct sb2_model_desc {
   const double* cosmo_dage; /* d/ds                    */
   double base_mass;         /* Msun the base photometry is quoted at (1e9, library.py:3217) */
   int64_t max_batch;        /* workspace capacity in galaxies                               */
+  /* Optional tables for the weight builder's float64 special functions (normal-CDF tail, log, exp); NULL: the
+   * CUDA math library is used instead (slower, same results to ~1e-12).  Built by synference_b200/fastmath.py:
+   * fm_log_tab [256][2] = ln(m0), 1/m0 ; fm_exp_tab [64] = 2^(j/64) ; fm_tail_tab [fm_tail_n][8] = local
+   * degree-7 polynomials of exp(u^2/2) Q(u) on intervals of width fm_tail_w.                              */
+  const double* fm_log_tab;
+  const double* fm_exp_tab;
+  const double* fm_tail_tab;
+  int32_t fm_tail_n;
+  double fm_tail_w;
 } sb2_model_desc;
 
 /* Per-galaxy parameters, struct of arrays (float64).  Replaces the per-galaxy object lists

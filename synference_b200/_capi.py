@@ -40,6 +40,7 @@ class ModelDesc(C.Structure):
         ("cosmo_n", C.c_int32), ("cosmo_smax", C.c_double),
         ("cosmo_dc", _dp), ("cosmo_ddc", _dp), ("cosmo_age", _dp), ("cosmo_dage", _dp),
         ("base_mass", C.c_double), ("max_batch", C.c_int64),
+        ("fm_log_tab", _dp), ("fm_exp_tab", _dp), ("fm_tail_tab", _dp), ("fm_tail_n", C.c_int32), ("fm_tail_w", C.c_double),
     ]
 
 

@@ -167,6 +167,7 @@ struct sb2_model {
   double *bin_pow = nullptr, *thr = nullptr, *pre = nullptr;
   int *nline = nullptr, *lc_on = nullptr;
   double *dc = nullptr, *ddc = nullptr, *age = nullptr, *dage = nullptr;
+  double *fm_log = nullptr, *fm_exp = nullptr, *fm_tail = nullptr;   // weight builder's special-function tables (optional)
   std::vector<int> h_lo, h_hi, h_off;
   std::vector<float> h_su, h_sdv;
   // workspace
@@ -233,7 +234,7 @@ int sb2_model_destroy(sb2_model* m) {
   if (!m) return SB2_OK;
   cudaSetDevice(m->device);
   void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->filt_uv, m->filt_lo,
-                  m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage,
+                  m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage, m->fm_log, m->fm_exp, m->fm_tail,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
                   m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params[0],
                   m->stage_params[1], m->stage_flux[0], m->stage_flux[1], m->stage_flux64[0], m->stage_flux64[1]};
@@ -338,6 +339,11 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   UP(ddc, d->cosmo_ddc, d->cosmo_n + 1);
   UP(age, d->cosmo_age, d->cosmo_n + 1);
   UP(dage, d->cosmo_dage, d->cosmo_n + 1);
+  if (d->fm_log_tab && d->fm_exp_tab && d->fm_tail_tab && d->fm_tail_n > 0 && d->fm_tail_w > 0.0) {
+    UP(fm_log, d->fm_log_tab, 512);
+    UP(fm_exp, d->fm_exp_tab, 64);
+    UP(fm_tail, d->fm_tail_tab, (size_t)8 * d->fm_tail_n);
+  }
 #undef UP
   // workspace
   m->cap = d->max_batch;
@@ -580,7 +586,15 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   }
   const size_t sh = sb2::weights_smem_doubles(M.n_age, M.n_z) * sizeof(double);
   const unsigned blocks = (unsigned)((n_pad + sb2::kWGal - 1) / sb2::kWGal);
-  sb2::weights_kernel<<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, P, O, perm, n_pad);
+  sb2::FastMath F{};
+  if (m->fm_tail && !std::getenv("SB2_LIBM")) {
+    F.log_tab = reinterpret_cast<const double2*>(m->fm_log); F.exp_tab = m->fm_exp;
+    F.tail_tab = reinterpret_cast<const double2*>(m->fm_tail);
+    F.tail_w = m->d.fm_tail_w; F.tail_inv_w = 1.0 / m->d.fm_tail_w; F.tail_n = m->d.fm_tail_n;
+    sb2::weights_kernel<true><<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, F, P, O, perm, n_pad);
+  } else {
+    sb2::weights_kernel<false><<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, F, P, O, perm, n_pad);
+  }
   STAGE_CHECK("weights_kernel", st);
   if (M.igm_on && !w_f64) {
     dim3 grid((unsigned)(n_pad / 128), (unsigned)((m->n_blue_pad + sb2::kIgmStrip - 1) / sb2::kIgmStrip));

@@ -42,6 +42,66 @@ struct PrepModel {
   const double* dage;
 };
 
+// Table-driven float64 log / exp / normal tail for weights_kernel (tables: synference_b200/fastmath.py, which also
+// restates these functions in numpy for the CPU accuracy test).  The CUDA math library's erfc / log / exp cost ~5x
+// the instructions (branchy range reduction, constants assembled from 32-bit immediates) and the kernel is
+// instruction-issue bound.
+struct FastMath {
+  const double2* log_tab;   // [256] (ln m0, 1/m0)
+  const double* exp_tab;    // [64]  2^(j/64)
+  const double2* tail_tab;  // [tail_n][4] = 8 polynomial coefficients per interval
+  double tail_w, tail_inv_w;
+  int tail_n;
+};
+
+__device__ __forceinline__ double fm_log(const FastMath& F, double x) {   // x positive and normal
+  const long long b = __double_as_longlong(x);
+  const int e = (int)(b >> 52) - 1023;
+  const double m = __longlong_as_double((b & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL);
+  const double2 t = __ldg(F.log_tab + ((int)(b >> 44) & 0xFF));
+  const double r = fma(m, t.y, -1.0);                    // |r| <= 2^-9
+  double p = 0.2;
+  p = fma(p, r, -0.25);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  p = fma(p, r, 1.0);
+  return fma((double)e, 0.6931471805599453, fma(r, p, t.x));
+}
+
+__device__ __forceinline__ double fm_exp(const FastMath& F, double y) {   // y <= ~0; underflow flushes to 0
+  const double kf = rint(y * 92.33248261689366);         // 64 / ln 2
+  const double r = fma(-kf, 2.531013593154441e-13, fma(-kf, 0.010830424695996044, y));   // Cody-Waite, ln2/64 = hi + lo
+  const int k = (int)kf;
+  const int e = k >> 6;
+  double p = 1.0 / 120.0;
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double v = __ldg(F.exp_tab + (k & 63)) * p;      // in [1, 2]
+  if (e < -1021) return 0.0;
+  return __longlong_as_double(__double_as_longlong(v) + ((long long)e << 52));
+}
+
+// Q(u) = 1 - Phi(u), u >= 0:  exp(-u^2/2) * g(u), g from a local degree-7 polynomial
+__device__ __forceinline__ double fm_tail(const FastMath& F, double u) {
+  if (!(u < F.tail_w * (double)F.tail_n)) return 0.0;
+  const int j = min((int)(u * F.tail_inv_w), F.tail_n - 1);
+  const double s = u - ((double)j + 0.5) * F.tail_w;
+  const double2* c = F.tail_tab + 4 * j;
+  const double2 c01 = __ldg(c), c23 = __ldg(c + 1), c45 = __ldg(c + 2), c67 = __ldg(c + 3);
+  double g = c67.y;
+  g = fma(g, s, c67.x);
+  g = fma(g, s, c45.y);
+  g = fma(g, s, c45.x);
+  g = fma(g, s, c23.y);
+  g = fma(g, s, c23.x);
+  g = fma(g, s, c01.y);
+  g = fma(g, s, c01.x);
+  return fm_exp(F, -0.5 * u * u) * g;
+}
+
 struct PrepParams {  // device pointers (sb2_params with device arrays)
   long long n;
   const double* redshift;
@@ -118,8 +178,9 @@ __device__ __forceinline__ double phi_diff(double ul, double uh) {
 // whichever tail avoids cancellation.
 struct EdgeVal { double a, b; };
 
-__device__ __forceinline__ EdgeVal sfh_edge(int type, const double* __restrict__ p, const double* __restrict__ gc,
-                                            double mn, double mx, double e_raw) {
+template <bool kFast>
+__device__ __forceinline__ EdgeVal sfh_edge(const FastMath& F, int type, const double* __restrict__ p,
+                                            const double* __restrict__ gc, double mn, double mx, double e_raw) {
   const double r = 0.70710678118654752440;
   const double t = fmin(fmax(e_raw, mn), mx);
   EdgeVal v{0.0, 0.0};
@@ -129,7 +190,7 @@ __device__ __forceinline__ EdgeVal sfh_edge(int type, const double* __restrict__
       break;
     case SB2_SFH_GAUSSIAN: {
       const double u = (t - p[0]) / p[1];
-      v.a = 0.5 * erfc(fabs(u) * r);
+      v.a = kFast ? fm_tail(F, fabs(u)) : 0.5 * erfc(fabs(u) * r);
       v.b = u;
       break;
     }
@@ -137,17 +198,20 @@ __device__ __forceinline__ EdgeVal sfh_edge(int type, const double* __restrict__
     case SB2_SFH_DECLINING_EXP: {
       const double tau = (type == SB2_SFH_EXPONENTIAL) ? p[0] : -p[0];
       const double shift = tau > 0.0 ? (mx - mn) / tau : 0.0;
-      v.a = -tau * exp((mx - t) / tau - shift);
+      const double arg = (mx - t) / tau - shift;
+      v.a = -tau * ((kFast && arg <= 0.0) ? fm_exp(F, arg) : exp(arg));
       break;
     }
     case SB2_SFH_DELAYED_EXP: {
       const double tau = p[0], T = mx - t;
-      v.a = tau * (T + tau) * exp(-T / tau);
+      const double arg = -T / tau;
+      v.a = tau * (T + tau) * ((kFast && arg <= 0.0) ? fm_exp(F, arg) : exp(arg));
       break;
     }
     case SB2_SFH_LOGNORMAL: {  // gc[0] = ln(max_age - peak_age) + tau^2
-      const double u = (log(fmax(mx - t, 1e-300)) - gc[0]) / p[0];
-      v.a = 0.5 * erfc(fabs(u) * r);
+      const double x = fmax(mx - t, 1e-300);
+      const double u = ((kFast ? fm_log(F, x) : log(x)) - gc[0]) / p[0];
+      v.a = kFast ? fm_tail(F, fabs(u)) : 0.5 * erfc(fabs(u) * r);
       v.b = u;
       break;
     }
@@ -247,8 +311,9 @@ __host__ __device__ inline size_t weights_smem_doubles(int n_age, int n_z) {
   return (size_t)kWGal * (3 * (size_t)n_age + n_z + SB2_SFH_ROW + kGConst + 8);
 }
 
+template <bool kFast>
 __global__ void __launch_bounds__(kWGal * kWSlots)
-weights_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ perm, long long n_pad) {
+weights_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __restrict__ perm, long long n_pad) {
   extern __shared__ double prep_smem[];
   const int gq = threadIdx.x / kWSlots, slot = threadIdx.x % kWSlots;
   const long long t = (long long)blockIdx.x * kWGal + gq;
@@ -305,7 +370,7 @@ weights_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ per
   // ---- edge values, bin masses (the last age bin receives no mass, A2)
   if (valid)
     for (int e = slot; e < M.n_age; e += kWSlots) {
-      const EdgeVal v = sfh_edge(P.sfh_type, p, gc, mn, mx, M.edges[e]);
+      const EdgeVal v = sfh_edge<kFast>(F, P.sfh_type, p, gc, mn, mx, M.edges[e]);
       eA[e] = v.a; eB[e] = v.b;
     }
   __syncthreads();

@@ -42,7 +42,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -63,10 +63,23 @@ __device__ __noinline__ void mbar_timeout(uint32_t id, uint32_t parity) {
   }
   __trap();
 }
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// try_wait suspends the warp in hardware for a while (it does not burn the issue slots the epilogue warps of the
+// same scheduler need); the watchdog is wall-clock based: no legitimate wait of these kernels lasts 2 s.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t id = 0) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) mbar_timeout(id, parity);   // ~10-20 s of polling
+    if ((++spins & 0x3FFu) == 0u) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) mbar_timeout(id, parity);
+    }
   }
 }
 

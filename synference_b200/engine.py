@@ -16,7 +16,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import _capi, igm as _igm
+from . import _capi, fastmath as _fm, igm as _igm
 from .cosmology import Planck18
 from .parametric import (EmissionModel, FilterCollection, Grid, SFH_MAX_PARAMS, ZD_NORMAL_LINEAR,
                          pack_sfh, pack_zdist)
@@ -187,7 +187,7 @@ class SynthEngine:
 
     def __init__(self, grid: Grid, emission_model: EmissionModel, emission_key: str,
                  filters: FilterCollection, cosmo=Planck18, igm=True, variant="nu", base_mass=1.0e9,
-                 max_batch=1 << 20, device=0):
+                 max_batch=1 << 20, device=0, fast_math=True):
         self.lib = _capi.load()
         if self.lib.sb2_device_count() < 1:
             raise RuntimeError("synference_b200: no CUDA device visible; the hot path has no CPU fallback")
@@ -231,6 +231,10 @@ class SynthEngine:
         d.cosmo_dc, d.cosmo_ddc = ptr(cz.dc, C.c_double), ptr(cz.ddc, C.c_double)
         d.cosmo_age, d.cosmo_dage = ptr(cz.age, C.c_double), ptr(cz.dage, C.c_double)
         d.base_mass, d.max_batch = self.base_mass, self.max_batch
+        if fast_math:
+            fm = _fm.build_tables()
+            d.fm_log_tab, d.fm_exp_tab = ptr(fm["log_tab"], C.c_double), ptr(fm["exp_tab"], C.c_double)
+            d.fm_tail_tab, d.fm_tail_n, d.fm_tail_w = ptr(fm["tail_tab"], C.c_double), int(fm["tail_n"]), float(fm["tail_w"])
         handle = C.c_void_p()
         _capi.check(self.lib.sb2_model_create(C.byref(d), self.device, C.byref(handle)), "sb2_model_create")
         self._h = handle

@@ -56,8 +56,15 @@ def test_weights_match_oracle(engines, name):
     w, eng = engines(name, 300)
     W = eng.weights(w.params)
     Wo = A.weights_matrix(w.params, w.grid.log10ages, w.grid.metallicity)
-    np.testing.assert_allclose(W, Wo, rtol=0, atol=1e-13)
+    # weights sum to 1; the table-driven normal tail / log / exp of the kernel are good to ~1e-12 relative
+    np.testing.assert_allclose(W, Wo, rtol=0, atol=2e-12)
     np.testing.assert_allclose(W.sum(1), 1.0, rtol=0, atol=1e-12)
+    import os
+    os.environ["SB2_LIBM"] = "1"          # same kernel with the CUDA math library's erfc / log / exp
+    try:
+        np.testing.assert_allclose(eng.weights(w.params), Wo, rtol=0, atol=1e-13)
+    finally:
+        del os.environ["SB2_LIBM"]
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
@@ -230,7 +237,7 @@ def test_delta_linear_brackets_and_clamps(engines):
     w, eng = engines("cfg2", 600)
     q = _delta_linear_params(w, 600)
     W = eng.weights(q)
-    np.testing.assert_allclose(W, A.weights_matrix(q, w.grid.log10ages, w.grid.metallicity), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(W, A.weights_matrix(q, w.grid.log10ages, w.grid.metallicity), rtol=0, atol=2e-12)
     assert_flux_close(eng.photometry(q, scaled=False), oracle_flux(w, params=q, c=True))
 
 
