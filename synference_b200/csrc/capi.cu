@@ -587,10 +587,17 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   const size_t sh = sb2::weights_smem_doubles(M.n_age, M.n_z) * sizeof(double);
   const unsigned blocks = (unsigned)((n_pad + sb2::kWGal - 1) / sb2::kWGal);
   sb2::FastMath F{};
-  if (m->fm_tail && !std::getenv("SB2_LIBM")) {
+  const bool fast = m->fm_tail && !std::getenv("SB2_LIBM");
+  if (fast) {
     F.log_tab = reinterpret_cast<const double2*>(m->fm_log); F.exp_tab = m->fm_exp;
     F.tail_tab = reinterpret_cast<const double2*>(m->fm_tail);
     F.tail_w = m->d.fm_tail_w; F.tail_inv_w = 1.0 / m->d.fm_tail_w; F.tail_n = m->d.fm_tail_n;
+  }
+  if (M.n_age <= 64 && M.n_z <= 64 && !std::getenv("SB2_WEIGHTS_V1")) {   // half-warp per galaxy
+    const unsigned blocks2 = (unsigned)((n_pad + sb2::kW2Gal - 1) / sb2::kW2Gal);
+    if (fast) sb2::weights2_kernel<true><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+    else sb2::weights2_kernel<false><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+  } else if (fast) {
     sb2::weights_kernel<true><<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, F, P, O, perm, n_pad);
   } else {
     sb2::weights_kernel<false><<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, F, P, O, perm, n_pad);

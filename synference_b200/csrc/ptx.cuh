@@ -153,6 +153,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld for a load issued EARLIER (prefetch): the registers only hold the data after the wait, so every later
+// use must be ordered behind it -- the empty asm makes the compiler treat them as rewritten here.
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  asm volatile(""
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
 
 // K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B (what TMA wrote):
 // 8-row groups are 1024 B apart (SBO); LBO is unused for swizzled K-major layouts.

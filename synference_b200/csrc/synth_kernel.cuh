@@ -184,12 +184,15 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
           const bool last_sub = (sub == kSub - 1) || (i0 + 32 >= A.n_lam);
           float s[32];
           {
+            // (prefetching the next sub-chunk's TMEM columns behind the filter work was measured 6% SLOWER: the
+            //  tcgen05.ld latency is already covered by the other epilogue group on the same scheduler)
             uint32_t v[32];
             if (SB2_DBG_BITS(A) & 16) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0x3f800000u;
-            } else
-            tmem_ld_32x32b_x32(t_acc + sub * 32, v);
+            } else {
+              tmem_ld_32x32b_x32(t_acc + sub * 32, v);
+            }
             const float4* kp = reinterpret_cast<const float4*>(A.kappa + i0);
             if constexpr (kComp == 2) {
               const float ca = A.g_ca[row], cb = A.g_cb[row];
@@ -206,7 +209,6 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               }
             } else {
               tmem_ld_wait();
-#pragma unroll
               if (SB2_DBG_BITS(A) & 2) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
@@ -354,12 +356,16 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
             for (int kb = 0; kb < n_kb; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               const uint32_t st = s_addr + (uint32_t)stage * kStageBytes, fb = full0 + (uint32_t)stage * 8u;
+              if (SB2_DBG_BITS(A) & 64) {   // experiment: no operand traffic
+                mbar_expect_tx_e(elected, &full_bar[stage], 0);
+              } else {
               mbar_expect_tx_e(elected, &full_bar[stage], lo_tiles ? kStageBytes : kABytes + kBBytes);
               tma_load_2d_e(elected, st, &tm_w_hi, fb, kb * kBK, tile * kBM, kEvictNormal);
               tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, c * kBN, kEvictLast);
               if (lo_tiles) {
                 tma_load_2d_e(elected, st + kABytes, &tm_w_lo, fb, kb * kBK, tile * kBM, kEvictNormal);
                 tma_load_2d_e(elected, st + 2 * kABytes + kBBytes, &tm_g_lo, fb, k0 + kb * kBK, c * kBN, kEvictLast);
+              }
               }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
@@ -403,11 +409,13 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
                 if (k4 < k4n) {
                   const uint64_t a_hi = da + (uint64_t)(k4 * 2), a_lo = da + (uint64_t)((kABytes >> 4) + k4 * 2);
                   const uint64_t b_hi = db + (uint64_t)(k4 * 2), b_lo = db + (uint64_t)((kBBytes >> 4) + k4 * 2);
+                  if (!(SB2_DBG_BITS(A) & 32)) {
                   if (pass == 0) {
                     umma_tf32_e(elected, d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
                     umma_tf32_e(elected, d_tmem, a_hi, b_lo, idesc, 1u);
                   }
                   if (pass == two_pass) umma_tf32_e(elected, d_tmem, a_hi, b_hi, idesc, 1u);
+                  }
                 }
               }
               umma_commit_e(elected, &empty_bar[stage]);  // smem slot reusable once these MMAs retire
