@@ -145,8 +145,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--galaxies", type=int, default=1_000_000, help="galaxies per GPU per step")
-    ap.add_argument("--ref-sample", type=int, default=20000, help="galaxies per CPU step")
-    ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--ref-sample", type=int, default=150000, help="galaxies per CPU step")
+    ap.add_argument("--cpu-sample", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per contraction launch, if known")
     args = ap.parse_args()

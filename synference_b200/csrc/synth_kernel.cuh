@@ -652,16 +652,41 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   const float sc = (A.n_comp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row];
   const unsigned trunc = A.g_trunc[row];
   const double mscale = A.g_mscale[row];
-  for (int f = 0; f < A.n_filt; ++f) {
-    float nu = 0.f, nv = 0.f;
-    for (int g = 0; g < A.n_groups; ++g) {   // fixed order: plane g holds the chunks with c % n_groups == g
-      const float2 a = A.part[((size_t)g * A.n_filt + f) * A.n_rows + row];
-      nu += a.x; nv += a.y;
+  // a galaxy's n_filt fluxes are contiguous in the output: build them four at a time and store 16 bytes at once
+  // (the rows land in the caller's galaxy order, i.e. scattered -- scalar stores would touch each 32-byte sector 8x)
+  const bool vec = (A.n_filt % 4) == 0 && ((reinterpret_cast<uintptr_t>(A.out_base) | reinterpret_cast<uintptr_t>(A.out_scaled)) & 15) == 0;
+  for (int f0 = 0; f0 < A.n_filt; f0 += 4) {
+    float fl[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int f = f0 + q;
+      fl[q] = 0.f;
+      if (f < A.n_filt) {
+        float nu = 0.f, nv = 0.f;
+        for (int g = 0; g < A.n_groups; ++g) {   // fixed order: plane g holds the chunks with c % n_groups == g
+          const float2 a = A.part[((size_t)g * A.n_filt + f) * A.n_rows + row];
+          nu += a.x; nv += a.y;
+        }
+        float flux = fmaf(beta, nv, gamma * nu) / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * sc;
+        if ((trunc >> f) & 1u) flux = __int_as_float(0x7fc00000);
+        fl[q] = flux;
+      }
     }
-    float flux = fmaf(beta, nv, gamma * nu) / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * sc;
-    if ((trunc >> f) & 1u) flux = __int_as_float(0x7fc00000);
-    if (A.out_base) A.out_base[(size_t)orig * A.n_filt + f] = flux;
-    if (A.out_scaled) A.out_scaled[(size_t)orig * A.n_filt + f] = (double)flux * mscale;
+    if (vec) {
+      if (A.out_base) *reinterpret_cast<float4*>(A.out_base + (size_t)orig * A.n_filt + f0) = make_float4(fl[0], fl[1], fl[2], fl[3]);
+      if (A.out_scaled) {
+        double2* o = reinterpret_cast<double2*>(A.out_scaled + (size_t)orig * A.n_filt + f0);
+        o[0] = make_double2((double)fl[0] * mscale, (double)fl[1] * mscale);
+        o[1] = make_double2((double)fl[2] * mscale, (double)fl[3] * mscale);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (f0 + q < A.n_filt) {
+          if (A.out_base) A.out_base[(size_t)orig * A.n_filt + f0 + q] = fl[q];
+          if (A.out_scaled) A.out_scaled[(size_t)orig * A.n_filt + f0 + q] = (double)fl[q] * mscale;
+        }
+    }
   }
 }
 
