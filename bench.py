@@ -4,8 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # the CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement on the host cores
 
-One "step" = one pass of the hot path (sort by z, weight/IGM kernel, tcgen05 contraction + fused
-epilogue) over one batch of synthetic galaxies.  At N=1 the workload is BASELINE configs[1]
+One "step" = one pass of the hot path (group by metallicity bracket and redshift, weight and IGM kernels,
+tcgen05 contraction + fused epilogue, finalize) over one batch of synthetic galaxies.  At N=1 the workload is BASELINE configs[1]
 (1M galaxies, LogNormal SFH + Calzetti dust screen, z 0-10 with IGM, 20 NIRCam+MIRI filters).
 For N>1 every rank processes its own batch of the same size (weak scaling, no data-path collective);
 time is the max over ranks of the CUDA-event time of the K steps.
@@ -273,9 +273,17 @@ def main():
         flops_alg = 2.0 * k_exec * t["n_lam"] * t["n_comp"] * n          # 2 K_exec N_lam C per galaxy
         flops_exec = 3.0 * 2.0 * k_mma * (t["n_chunk"] * 256) * ((n + 127) // 128 * 128)  # 3xTF32, padded
         achieved = flops_alg / (synth_ms_avg * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum of the contraction kernel from the committed ncu capture
+        # (profiles/r01_final_ncu_summary.txt: 1.892 GB + 0.315 GB per launch at 1M cfg2 galaxies), scaled to this batch
+        if args.traffic is not None:
+            traffic, traffic_src = args.traffic, "--traffic"
+        elif args.workload == "cfg2":
+            traffic, traffic_src = 2.207e9 * n / 1e6, "ncu --set full, profiles/r01_final_ncu_summary.txt, scaled by batch size"
+        else:
+            traffic, traffic_src = None, None
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": args.traffic,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "kernel": "synth_kernel (3xTF32 tcgen05 contraction + fused epilogue)",
                     "kernel_ms": synth_ms_avg, "peak_source": f"{peak_src} bf16 sustained (MEASURED_PEAKS.json)",
                     "executed_tflops": flops_exec / (synth_ms_avg * 1e-3) / 1e12,
@@ -313,7 +321,7 @@ def main():
                            "slots, pinned host buffers",
                     "blocking_call_value": world * n * e2e_steps / (e2e_sync_ms * 1e-3),
                     "blocking_call_api": "SynthEngine.photometry (sb2_synth_photometry_host), one blocking call per step"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": 15 * args.steps,   # per step: 9 kernels of this repo + 6 of CUB's radix sort
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -101,12 +101,14 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
     att, un = emission_model.recipe(emission_key)
     has_att, has_un = bool(np.any(att != 0)), bool(np.any(un != 0))
     dust = emission_model.dust_curve
-    if has_att and dust is None:
+    dust_free = bool(getattr(emission_model, "dust_free", lambda k: False)(emission_key))
+    if has_att and dust is None and not dust_free:
         raise ValueError(f"spectrum '{emission_key}' is dust attenuated but the emission model has no dust_curve")
+    screen = (lambda: np.zeros_like(lam)) if dust_free else (lambda: dust.get_tau(lam))
     if has_att and has_un:
-        comps, kappa = [att, un], dust.get_tau(lam)
+        comps, kappa = [att, un], screen()
     elif has_att:
-        comps, kappa = [att], dust.get_tau(lam)
+        comps, kappa = [att], screen()
     else:
         comps, kappa = [un], None
     n_comp = len(comps)
@@ -171,6 +173,9 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         filt_lo=np.array(lo_l, dtype=np.int32), filt_hi=np.array(hi_l, dtype=np.int32),
         filt_off=np.array(off_l, dtype=np.int32), filt_uv=np.ascontiguousarray(uv),
         filt_su=np.array(su_l, dtype=np.float64), filt_sdv=np.array(sdv_l, dtype=np.float64),
+        # a lone component is the kernel's component A whichever grid it came from: its per-galaxy coefficient
+        # travels as coef_att (SynthEngine._fill)
+        single_is_unatt=(n_comp == 1 and not has_att),
     )
     if igm:
         laf, dla = (igm if isinstance(igm, tuple) else (_igm.INOUE14_LAF, _igm.INOUE14_DLA))
@@ -252,15 +257,17 @@ class SynthEngine:
             pass
 
     # ---- parameter marshalling ------------------------------------------------------------
-    @staticmethod
-    def _fill(p: GalaxyParams, get_ptr):
+    def _fill(self, p: GalaxyParams, get_ptr):
         s = _capi.Params()
         s.n = len(p)
         s.redshift, s.log_mass, s.tau_v = get_ptr(p.redshift), get_ptr(p.log_mass), get_ptr(p.tau_v)
         s.sfh_type, s.sfh_stride, s.sfh_rows = int(p.sfh_type), int(p.sfh_rows.shape[1]), get_ptr(p.sfh_rows)
         s.max_age_from_z, s.norm_mask, s.age_zmax_gyr = int(p.max_age_from_z), int(p.norm_mask), float(p.age_zmax_gyr)
         s.zd_type, s.zd_value, s.zd_sigma = int(p.zd_type), get_ptr(p.zd_value), get_ptr(p.zd_sigma)
-        s.coef_att, s.coef_unatt = get_ptr(p.coef_att), get_ptr(p.coef_unatt)
+        if self.tables["single_is_unatt"]:
+            s.coef_att, s.coef_unatt = get_ptr(p.coef_unatt), None
+        else:
+            s.coef_att, s.coef_unatt = get_ptr(p.coef_att), get_ptr(p.coef_unatt)
         return s
 
     @staticmethod
@@ -317,14 +324,22 @@ class SynthEngine:
                                      ("redshift", "log_mass", "tau_v", "sfh_rows", "zd_value", "zd_sigma",
                                       "coef_att", "coef_unatt")})
 
+    def _set_device_ptrs(self, s, tensors):
+        ptr = lambda k: None if tensors.get(k) is None else tensors[k].data_ptr()  # noqa: E731
+        for k in ("redshift", "log_mass", "tau_v", "sfh_rows", "zd_value", "zd_sigma"):
+            setattr(s, k, ptr(k))
+        if self.tables["single_is_unatt"]:
+            s.coef_att, s.coef_unatt = ptr("coef_unatt"), None
+        else:
+            s.coef_att, s.coef_unatt = ptr("coef_att"), ptr("coef_unatt")
+
     def photometry_device(self, dparams: "DeviceParams", flux_base=None, flux_scaled=None, spectra=None):
         """Run one batch whose parameters are already in HBM; outputs are caller-provided torch tensors."""
         import torch
         p = dparams.host
         t = dparams.tensors
         s = self._fill(p, lambda a: None)
-        for k2, v in t.items():
-            setattr(s, k2, None if v is None else v.data_ptr())
+        self._set_device_ptrs(s, t)
         st = torch.cuda.current_stream(self.device).cuda_stream
         dp = lambda x: None if x is None else x.data_ptr()  # noqa: E731
         rc = self.lib.sb2_synth_photometry(self._h, C.byref(s), dp(flux_base), dp(flux_scaled), dp(spectra), st)
@@ -355,8 +370,7 @@ class SynthEngine:
             b = min(n, a + self.max_batch)
             dpar = self.to_device(params.slice(slice(a, b)))
             s = self._fill(dpar.host, lambda x: None)
-            for k2, v in dpar.tensors.items():
-                setattr(s, k2, None if v is None else v.data_ptr())
+            self._set_device_ptrs(s, dpar.tensors)
             w = torch.empty((b - a, self.k), dtype=torch.float64, device=dev)
             st = torch.cuda.current_stream(self.device).cuda_stream
             _capi.check(self.lib.sb2_build_weights(self._h, C.byref(s), w.data_ptr(), st), "sb2_build_weights")

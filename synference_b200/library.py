@@ -44,9 +44,9 @@ UNIT_DICT = {
 }
 
 # emitter parameters that change the spectrum and are understood by the CUDA path
-_SPECTRAL_EMITTER_PARAMS = ("tau_v",)
+_SPECTRAL_EMITTER_PARAMS = ("tau_v", "fesc")
 # emitter parameters of the reference scripts that would change the spectrum but are not implemented
-_UNSUPPORTED_EMITTER_PARAMS = ("slope", "fesc", "fesc_lya", "fesc_ly_alpha", "dust_bump_amplitude",
+_UNSUPPORTED_EMITTER_PARAMS = ("slope", "fesc_lya", "fesc_ly_alpha", "dust_bump_amplitude",
                                "tau_v_ism", "tau_v_birth")
 
 
@@ -102,7 +102,14 @@ class GalaxyBasis:
             if key in _UNSUPPORTED_EMITTER_PARAMS:
                 raise NotImplementedError(
                     f"per-galaxy emitter parameter '{key}' is not implemented in the CUDA path yet "
-                    "(SURVEY 8f-1); only 'tau_v' varies per galaxy")
+                    "(SURVEY 8f-1); 'tau_v' and 'fesc' vary per galaxy")
+        per_gal = getattr(emission_model, "fesc_per_galaxy", False)
+        if per_gal and emission_model.fesc_name not in galaxy_params:
+            raise ValueError(f"the emission model reads fesc from the per-galaxy parameter "
+                             f"'{emission_model.fesc_name}', which galaxy_params does not provide")
+        if not per_gal and "fesc" in galaxy_params:
+            raise ValueError("galaxy_params has 'fesc' but the emission model uses a global fesc; construct it with "
+                             "fesc='fesc' (the reference's string convention for per-emitter parameters)")
         if not build_library:
             logger.info("Generating library directly from provided parameter samples.")
         elif redshift_dependent_sfh:
@@ -320,6 +327,9 @@ class GalaxyBasis:
             datasets = {}
             for key in keys:
                 eng = self._engine(key, igm=igm, max_batch=max(batch_size, 1))
+                if getattr(self.emission_model, "fesc_per_galaxy", False):
+                    fesc = np.asarray(strip_units(self.all_parameters[self.emission_model.fesc_name]), dtype=float)[sl]
+                    p.coef_att, p.coef_unatt = self.emission_model.coefficients(key, fesc)
                 flux = eng.photometry(p, scaled=False)
                 results["photometry"][key].append(flux)
                 label = self.instrument.label
@@ -830,7 +840,8 @@ class GalaxySimulator:
         else:
             zd = ZDistArray(ZD_NORMAL_LOG10, bc(params["mean"]), bc(params["sigma"]))
         tau_v = bc(params["tau_v"]) if "tau_v" in params else None
-        used = [k for k in params if k not in self.total_possible_keys and k != "tau_v"
+        fesc_name = getattr(self.emission_model, "fesc_name", None)
+        used = [k for k in params if k not in self.total_possible_keys and k not in ("tau_v", fesc_name)
                 and k not in self.ignore_params and k not in cls.param_names]
         for k in used:
             if k not in self.unused_params:
@@ -838,8 +849,13 @@ class GalaxySimulator:
         if self.unused_params and not self.reported_unused:
             logger.warning(f"The following parameters are not used by the simulator: {self.unused_params}")
             self.reported_unused = True
-        return GalaxyParams.from_objects(bc(params["redshift"]), SFHArray(cls, rows), zd,
-                                         log_mass=bc(params["log_mass"]), tau_v=tau_v)
+        gp = GalaxyParams.from_objects(bc(params["redshift"]), SFHArray(cls, rows), zd,
+                                       log_mass=bc(params["log_mass"]), tau_v=tau_v)
+        if fesc_name is not None:   # per-galaxy escape fraction (emission model built with fesc="<name>")
+            if fesc_name not in params:
+                raise ValueError(f"Missing required parameter '{fesc_name}' (per-galaxy escape fraction of the emission model)")
+            gp.coef_att, gp.coef_unatt = self.emission_model.coefficients(self.emission_model_key, bc(params[fesc_name]))
+        return gp
 
     def simulate(self, params):
         """Photometry (and/or spectra) for one parameter vector or a batch of them."""

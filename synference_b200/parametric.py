@@ -601,6 +601,13 @@ class EmissionModel:
     spectrum ``key`` that passes through the dust screen and the part that does
     not, already combined over grid components with the *global* ``fesc`` /
     ``fesc_ly_alpha``.  Per-galaxy ``tau_v`` is an emitter parameter supplied at run time.
+
+    ``fesc`` may instead name a per-galaxy emitter attribute (``fesc="fesc"``, the string
+    convention of the reference's emission models, SURVEY A5;
+    ``docs/source/library_gen/complex_library_generation.ipynb:357,398``): the two grids are then
+    built for fesc = 0 and fesc enters as per-galaxy coefficients ``(1 - fesc, fesc)`` on them
+    (:meth:`coefficients`) -- the contraction kernel's two-component form
+    ``c_att * dust(att) + c_un * un``.
     """
 
     label = "emission"
@@ -616,10 +623,11 @@ class EmissionModel:
         self.dust_emission = dust_emission
         self.per_particle = False
         self.saved_spectra = None
-        for name, v in (("fesc", fesc), ("fesc_ly_alpha", fesc_ly_alpha)):
-            if isinstance(v, str):
-                raise NotImplementedError(
-                    f"per-galaxy '{name}' (string-named emitter attribute) is not in the batched path yet")
+        self.fesc_per_galaxy = isinstance(fesc, str)
+        self.fesc_name = fesc if self.fesc_per_galaxy else None
+        if isinstance(fesc_ly_alpha, str):
+            raise NotImplementedError(
+                "per-galaxy 'fesc_ly_alpha' (string-named emitter attribute) is not in the batched path yet")
         if dust_emission is not None:
             raise NotImplementedError("dust emission / energy balance is not in the batched path yet")
 
@@ -640,11 +648,44 @@ class EmissionModel:
             return sp["incident"]
         raise KeyError(f"grid has no '{name}' spectra")
 
+    # which per-galaxy factor multiplies the (dust-screened, unscreened) grid of each spectrum when fesc is per galaxy
+    _PER_GALAXY = {"incident": (None, "one"), "transmitted": (None, "1-f"), "nebular": (None, "1-f"),
+                   "reprocessed": (None, "1-f"), "escaped": (None, "f"), "intrinsic": ("1-f", "f"),
+                   "attenuated": ("1-f", None), "emergent": ("1-f", "f"), "total": ("1-f", "f")}
+
+    def dust_free(self, key):
+        """True when the first grid of ``recipe(key)`` must NOT be attenuated (per-galaxy fesc, 'intrinsic':
+        reprocessed and escaped light need different coefficients but neither sees the screen)."""
+        return self.fesc_per_galaxy and key == "intrinsic"
+
+    def coefficients(self, key, fesc_values):
+        """Per-galaxy factors ``(c_first, c_second)`` on the two grids of ``recipe(key)``; ``None`` = 1."""
+        if not self.fesc_per_galaxy:
+            return None, None
+        f = np.asarray(fesc_values, dtype=np.float64)
+        if np.any((f < 0) | (f > 1)) or not np.all(np.isfinite(f)):
+            raise ValueError("fesc must lie in [0, 1]")
+        pick = {"1-f": 1.0 - f, "f": f, "one": None, None: None}
+        a, b = self._PER_GALAXY[key]
+        return pick[a], pick[b]
+
     def recipe(self, key):
         if key not in self.available:
             raise ValueError(f"Emission model {type(self).__name__} has no spectrum '{key}'")
         lam = np.asarray(self.grid.lam)
-        fesc, flya = float(self.fesc), float(self.fesc_ly_alpha)
+        flya = float(self.fesc_ly_alpha)
+        if self.fesc_per_galaxy:
+            inc = self._component("incident")
+            zero = np.zeros_like(inc)
+            line = self._component("linecont").copy()
+            line[..., int(np.argmin(np.abs(lam - LYA)))] *= flya
+            trans, neb = self._component("transmitted"), line + self._component("nebular_continuum")
+            repro = trans + neb
+            table = {"incident": (zero, inc), "transmitted": (zero, trans), "nebular": (zero, neb),
+                     "reprocessed": (zero, repro), "escaped": (zero, inc), "intrinsic": (repro, inc),
+                     "attenuated": (repro, zero), "emergent": (repro, inc), "total": (repro, inc)}
+            return table[key]
+        fesc = float(self.fesc)
         inc = self._component("incident")
         zero = np.zeros_like(inc)
         if key == "incident":

@@ -208,3 +208,34 @@ def test_galaxy_simulator_single_and_batched(tmp_path):
     np.random.seed(1)
     noisy = sim(params)
     assert noisy.shape == (7,) and not np.array_equal(noisy, one)
+
+
+def test_library_and_simulator_with_per_galaxy_fesc(tmp_path):
+    """galaxy_params={"fesc": ...} with an emission model built with fesc="fesc" (the reference's
+    complex_library_generation notebook, cell 398): library photometry equals the global-fesc library of each galaxy's
+    own value, 'fesc' is a library parameter, and the simulator accepts it as an input."""
+    n = 24
+    basis, d, grid, inst, _ = _small_basis(n, tmp_path)
+    fesc = np.tile([0.0, 0.3, 0.9], n // 3)
+    em = S.PacmanEmission(grid=grid, fesc="fesc", fesc_ly_alpha=0.1, dust_curve=S.Calzetti2000())
+    per = S.GalaxyBasis("per_fesc", d["redshift"], grid, em, basis.sfhs, basis.metal_dists,
+                        galaxy_params={"tau_v": d["tau_v"], "fesc": fesc}, instrument=inst, build_library=False)
+    per._create_matched_galaxies(log_base_masses=9)
+    got = per.process_galaxies(save=False, emission_model_keys=["emergent"])["photometry"]["emergent"]
+    assert "fesc" in per.varying_param_names
+    for f in (0.0, 0.3, 0.9):
+        emg = S.PacmanEmission(grid=grid, fesc=f, fesc_ly_alpha=0.1, dust_curve=S.Calzetti2000())
+        ref = S.GalaxyBasis("glob", d["redshift"], grid, emg, basis.sfhs, basis.metal_dists,
+                            galaxy_params={"tau_v": d["tau_v"]}, instrument=inst, build_library=False)
+        ref._create_matched_galaxies(log_base_masses=9)
+        want = ref.process_galaxies(save=False, emission_model_keys=["emergent"])["photometry"]["emergent"]
+        sel = fesc == f
+        np.testing.assert_allclose(got[sel], want[sel], rtol=3e-6)
+    sim = S.GalaxySimulator(sfh_model=S.SFH.LogNormal, zdist_model=S.ZDist.DeltaConstant, grid=grid, instrument=inst,
+                            emission_model=em, emission_model_key="emergent", out_flux_unit="nJy", ignore_scatter=True,
+                            param_units={"peak_age": S.Myr, "max_age": S.Myr})
+    base = {"redshift": 3.0, "log_mass": 9.0, "tau": 0.5, "peak_age": 100.0, "max_age": 300.0, "log10metallicity": -2.0, "tau_v": 0.4}
+    lo, hi = sim(dict(base, fesc=0.0)), sim(dict(base, fesc=1.0))
+    assert np.all(np.isfinite(lo)) and not np.allclose(lo, hi)
+    with pytest.raises(ValueError):
+        sim(base)                                    # fesc is required once the model reads it per galaxy

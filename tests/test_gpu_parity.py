@@ -290,3 +290,31 @@ def test_watchdog_record_is_empty_after_good_runs(engines):
     w, eng = engines("cfg1", 64)
     eng.photometry(w.params, scaled=False)
     assert eng.lib.sb2_wait_debug(eng._h) == b""
+
+
+# ---- per-galaxy escape fraction ------------------------------------------------------------
+
+@pytest.mark.parametrize("key", ["emergent", "intrinsic", "attenuated", "reprocessed", "escaped"])
+def test_per_galaxy_fesc_matches_oracle(key):
+    """fesc="fesc" (the reference's string convention for per-emitter parameters): every galaxy gets its own
+    escape fraction through the kernel's two-component form; the oracle evaluates the tree galaxy by galaxy."""
+    from synference_b200.parametric import Calzetti2000, PacmanEmission
+    n = 200
+    w = make_workload("cfg2", n)
+    em = PacmanEmission(grid=w.grid, fesc="fesc", fesc_ly_alpha=0.3, dust_curve=Calzetti2000())
+    fesc = np.random.default_rng(5).uniform(0.0, 1.0, n)
+    fesc[:3] = (0.0, 1.0, 0.5)
+    eng = SynthEngine(w.grid, em, key, w.filters, max_batch=4096)
+    p = w.params.slice(slice(0, n))
+    if key in ("intrinsic", "reprocessed", "escaped"):
+        p.tau_v = None
+    p.coef_att, p.coef_unatt = em.coefficients(key, fesc)
+    got = eng.photometry(p, scaled=False)
+    gals = A.galaxies_from_params(p)
+    for g, f in zip(gals, fesc):
+        g["fesc"] = float(f)
+    lam = np.asarray(w.grid.lam)
+    want = O.synthesize(gals, w.grid.log10ages, w.grid.metallicity, lam, w.grid.spectra, [(f.lam, f.t) for f in w.filters],
+                        key=key, fesc_ly_alpha=0.3, dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA))
+    assert_flux_close(got, want)
+    eng.close()

@@ -119,7 +119,14 @@ def test_unsupported_features_fail_loudly():
         S.GalaxyBasis("x", b.redshifts, b.grid, b.emission_model, b.sfhs, b.metal_dists,
                       galaxy_params={"slope": np.zeros(4)}, instrument=b.instrument)
     with pytest.raises(NotImplementedError):
-        S.PacmanEmission(grid=b.grid, fesc="fesc", dust_curve=S.Calzetti2000())
+        S.PacmanEmission(grid=b.grid, fesc=0.1, fesc_ly_alpha="fesc_lya", dust_curve=S.Calzetti2000())
+    per = S.PacmanEmission(grid=b.grid, fesc="fesc", dust_curve=S.Calzetti2000())     # per-galaxy fesc IS supported ...
+    with pytest.raises(ValueError):                                                  # ... but must then be provided
+        S.GalaxyBasis("x", b.redshifts, b.grid, per, b.sfhs, b.metal_dists, galaxy_params={"tau_v": np.ones(4)},
+                      instrument=b.instrument)
+    with pytest.raises(ValueError):                                                  # and not with a global-fesc model
+        S.GalaxyBasis("x", b.redshifts, b.grid, b.emission_model, b.sfhs, b.metal_dists,
+                      galaxy_params={"fesc": np.full(4, 0.2)}, instrument=b.instrument)
     with pytest.raises(ValueError):
         b.emission_model.recipe("nonsense")
     with pytest.raises(ValueError):
@@ -199,3 +206,32 @@ def test_shard_bounds_follow_reference_rule():
     from synference_b200.distributed import shard_bounds, shard_counts
     assert [shard_bounds(10, r, 3) for r in range(3)] == [(0, 3), (3, 6), (6, 10)]   # library.py:3130-3137
     assert sum(shard_counts(1_000_003, 8)) == 1_000_003
+
+
+def test_per_galaxy_fesc_recipe_and_coefficients():
+    """fesc="fesc": grids are built for fesc = 0 and (1 - fesc, fesc) become per-galaxy coefficients; summing
+    coefficient * grid reproduces the global-fesc recipe for every spectrum of the tree."""
+    import numpy as np
+    from synference_b200.configs import make_workload
+    from synference_b200.parametric import Calzetti2000, PacmanEmission
+    w = make_workload("cfg1", 4)
+    per = PacmanEmission(grid=w.grid, fesc="fesc", fesc_ly_alpha=0.4, dust_curve=Calzetti2000())
+    assert per.fesc_per_galaxy and per.fesc_name == "fesc"
+    for f in (0.0, 0.25, 1.0):
+        glob = PacmanEmission(grid=w.grid, fesc=f, fesc_ly_alpha=0.4, dust_curve=Calzetti2000())
+        for key in ("incident", "transmitted", "nebular", "reprocessed", "escaped", "intrinsic", "attenuated", "emergent", "total"):
+            a, u = per.recipe(key)
+            ca, cu = per.coefficients(key, np.array([f]))
+            ca = 1.0 if ca is None else ca[0]
+            cu = 1.0 if cu is None else cu[0]
+            ga, gu = glob.recipe(key)
+            if per.dust_free(key):          # both grids bypass the screen: compare the sum
+                np.testing.assert_allclose(ca * a + cu * u, ga + gu, rtol=1e-14, atol=0)
+            else:
+                np.testing.assert_allclose(ca * a, ga, rtol=1e-14, atol=0)
+                np.testing.assert_allclose(cu * u, gu, rtol=1e-14, atol=0)
+    import pytest
+    with pytest.raises(ValueError):
+        per.coefficients("emergent", np.array([1.2]))
+    with pytest.raises(NotImplementedError):
+        PacmanEmission(grid=w.grid, fesc=0.1, fesc_ly_alpha="fesc_lya")
