@@ -806,7 +806,15 @@ int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, 
   long long blocks = (rows + 255) / 256;
   const long long cap = (long long)n_sm * 16;
   if (blocks > cap) blocks = cap;
-  sb2::depth_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  if (!normals && !out_flux && !out_sigma && out_feat && (reinterpret_cast<uintptr_t>(flux) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out_feat) & 7) == 0 && !std::getenv("SB2_NOISE_V1")) {
+    const long long pairs = rows * ((n_filt + 1) / 2);
+    long long b2 = (pairs + 255) / 256;
+    if (b2 > (long long)n_sm * 32) b2 = (long long)n_sm * 32;
+    sb2::depth_noise_feat_kernel<<<(unsigned)b2, 256, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    sb2::depth_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  }
   CU_TRY(cudaGetLastError());
   return SB2_OK;
 }

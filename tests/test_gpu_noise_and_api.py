@@ -239,3 +239,23 @@ def test_library_and_simulator_with_per_galaxy_fesc(tmp_path):
     assert np.all(np.isfinite(lo)) and not np.allclose(lo, hi)
     with pytest.raises(ValueError):
         sim(base)                                    # fesc is required once the model reads it per galaxy
+
+
+def test_feature_only_philox_kernel_matches_general_kernel():
+    """The feature-rows-only kernel (one thread per filter pair, float32 log10) draws the same Philox normals as the
+    general kernel and agrees with it to 3 float32 ulp (6e-6 mag; tolerance of the path: 1e-4 mag); odd filter counts and n_scatter > 1 included."""
+    import os
+    rng = np.random.default_rng(9)
+    for n_filt, n_sc in ((20, 1), (7, 3)):
+        flux = np.abs(rng.normal(40.0, 60.0, (30000, n_filt))) + 0.5
+        sigma = depths_to_sigma_njy(np.full(n_filt, 28.5))
+        _, _, fast = depth_noise_features(flux, sigma, n_scatter=n_sc, seed=3, epoch=5, want_flux=False)
+        os.environ["SB2_NOISE_V1"] = "1"
+        try:
+            _, _, ref = depth_noise_features(flux, sigma, n_scatter=n_sc, seed=3, epoch=5, want_flux=False)
+        finally:
+            del os.environ["SB2_NOISE_V1"]
+        fast, ref = fast.cpu().numpy(), ref.cpu().numpy()
+        assert fast.shape == (30000 * n_sc, 2 * n_filt)
+        np.testing.assert_allclose(fast[:, :n_filt], ref[:, :n_filt], atol=6e-6, rtol=0)     # <= 3 ulp of a float32 magnitude
+        np.testing.assert_allclose(fast[:, n_filt:], ref[:, n_filt:], rtol=2e-6, atol=1e-7)
