@@ -108,7 +108,7 @@ __global__ void group_keys_kernel(const double* __restrict__ z, const double* __
       double f;
       j = sb2::delta_bracket(zx, n_z, zv[i], &f);
     }
-    const float zf = fmaxf((float)z[i], 0.f);
+    const float zf = (z[i] >= 0.0 && z[i] <= 1.0e6) ? (float)z[i] : 0.f;   // unusable redshifts sort first (scalars_kernel flags them)
     keys[i] = ((unsigned)j << kKeyShift) | (__float_as_uint(zf) >> (32 - kKeyShift));
     idx[i] = (int)i;
     atomicAdd(&h[j], 1);

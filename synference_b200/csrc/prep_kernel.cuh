@@ -268,14 +268,18 @@ scalars_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ per
     O.g_cb[t] = 0.f; O.g_orig[t] = -1; O.g_mscale[t] = 0.0; O.g_trunc[t] = 0u;
     return;
   }
-  const double z = P.redshift[g];
+  double z = P.redshift[g];
+  // a redshift that is not a finite number >= 0 cannot be placed on the wavelength axis: the galaxy gets NaN fluxes
+  // (every filter flagged) and a harmless shift, instead of indexing the filter tables with garbage
+  const bool z_ok = (z >= 0.0) && (z <= 1.0e6);
+  if (!z_ok) z = 0.0;
   const double zp = 1.0 + z;
   const double s = log1p(z);
   const double tq = s / M.ln_q;
   const int m = (int)floor(tq);
   const double r = exp(s - (double)m * M.ln_q);  // (1+z)/q^m in [1, q)
   const double beta = (M.variant == 0) ? (1.0 - 1.0 / r) / (1.0 - 1.0 / M.q) : (r - 1.0) / (M.q - 1.0);
-  unsigned trunc = 0u;
+  unsigned trunc = z_ok ? 0u : 0xffffffffu;
   for (int f = 0; f < M.n_filt; ++f) {
     const int i_first = __ldg(M.filt_lo + f) - 1 - m, i_last = __ldg(M.filt_hi + f) - m;
     if (i_first < 0 || i_last > M.n_lam - 1) trunc |= 1u << f;

@@ -318,3 +318,17 @@ def test_per_galaxy_fesc_matches_oracle(key):
                         key=key, fesc_ly_alpha=0.3, dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA))
     assert_flux_close(got, want)
     eng.close()
+
+
+def test_unusable_redshifts_give_nan_rows_not_faults(engines):
+    """NaN / negative / infinite redshifts: that galaxy's fluxes are NaN, its neighbours are untouched."""
+    w, eng = engines("cfg2", 300)
+    good = eng.photometry(w.params, scaled=False)
+    p = w.params.slice(slice(0, 300))
+    p.redshift = p.redshift.copy()
+    bad = [3, 77, 150, 299]
+    p.redshift[bad] = [np.nan, -0.5, np.inf, -np.inf]
+    got = eng.photometry(p, scaled=False)
+    assert np.isnan(got[bad]).all()
+    ok = np.setdiff1d(np.arange(300), bad)
+    assert np.array_equal(got[ok], good[ok])
