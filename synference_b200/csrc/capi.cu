@@ -181,7 +181,8 @@ struct sb2_model {
   int4* tile_range = nullptr;
   float2* part = nullptr;  // [2][n_filt][cap_pad] partial filter numerators of the two epilogue groups
   int wd_stride = 0;  // floats per weights row in DeltaConstant (bracket-grouped) mode; 0: mode unavailable
-  CUtensorMap tm_wd_hi, tm_wd_lo, tm_g2_hi, tm_g2_lo;  // g2: 128-row boxes (one CTA's half of a chunk)
+  CUtensorMap tm_wd_hi, tm_wd_lo, tm_g2_hi, tm_g2_lo, tm_g160_hi, tm_g160_lo;  // g160: 160-row boxes (three-accumulator variant)
+  size_t smem160_bytes = 0;  // g2: 128-row boxes (one CTA's half of a chunk)
   size_t smem2_bytes = 0;
   double* g_mscale = nullptr;
   double* zpow = nullptr;
@@ -378,12 +379,15 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
       (m->wd_stride && (rc = make_tmap(&m->tm_wd_lo, m->w_lo, np, m->wd_stride, sb2::kBM)) != SB2_OK) ||
       (rc = make_tmap(&m->tm_g2_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN2 / 2)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g2_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN2 / 2)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g160_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 160)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g160_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 160)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK) {
     sb2_model_destroy(m);
     return rc;
   }
   m->smem_bytes = 1024 + (size_t)sb2::kStages * sb2::kStageBytes + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 256;
+  m->smem160_bytes = 1024 + (size_t)sb2::kStages * sb2::SynthCfg<160>::kStageBytesN + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 256;
   m->smem2_bytes = 1024 + (size_t)sb2::kW2Bytes + (size_t)sb2::kG2Slots * sb2::kG2Slot + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 256;
   if (m->smem2_bytes > (size_t)prop.sharedMemPerBlockOptin || m->wd_stride > sb2::kW2Kb * sb2::kBK || (m->n_sm & 1)) m->smem2_bytes = 0;  // CTA-pair kernel unavailable
   if (m->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
@@ -422,9 +426,22 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
 
 namespace {
 
+// One spectral component: chunks of 160 columns and three TMEM accumulators (unless SB2_N256 asks for the two-accumulator form)
+bool use_n160(const sb2_model* m) { return m->d.n_comp == 1 && !std::getenv("SB2_N256"); }
+
 template <int C, int NF, bool SPEC>
 int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
-  auto k = sb2::synth_kernel<C, NF, SPEC>;
+  if constexpr (C == 1) {
+    if (use_n160(m)) {
+      auto k = sb2::synth_kernel<C, NF, SPEC, 160>;
+      CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem160_bytes));
+      k<<<grid, sb2::kSynthThreads, m->smem160_bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo,
+                                                            m->tm_g160_hi, m->tm_g160_lo, a);
+      STAGE_CHECK("synth_kernel", st);
+      return SB2_OK;
+    }
+  }
+  auto k = sb2::synth_kernel<C, NF, SPEC, sb2::kBN>;
   CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes));
   k<<<grid, sb2::kSynthThreads, m->smem_bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo,
                                                      m->tm_g_hi, m->tm_g_lo, a);
@@ -581,7 +598,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
     for (int f = 1; f < d.n_filt; ++f) { lo_min = std::min(lo_min, m->h_lo[f]); hi_max = std::max(hi_max, m->h_hi[f]); }
     const int wpb = 8, n_units = (int)(n_pad / rpu);
     sb2::tile_range_kernel<<<(n_units + wpb - 1) / wpb, wpb * 32, 0, st>>>(m->g_m, m->g_orig, n_units, rpu, lo_min, hi_max, d.n_lam,
-                                                                         (rpu == 256 ? sb2::kBN2 : sb2::kBN) / d.n_comp, all_lam ? 1 : 0, m->tile_range);
+                                                                         (rpu == 256 ? sb2::kBN2 : (use_n160(m) ? 160 : sb2::kBN)) / d.n_comp, all_lam ? 1 : 0, m->tile_range);
     STAGE_CHECK("tile_range_kernel", st);
   }
   const size_t sh = sb2::weights_smem_doubles(M.n_age, M.n_z) * sizeof(double);

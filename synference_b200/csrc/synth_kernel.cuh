@@ -134,7 +134,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
   constexpr uint32_t kBuf = 512 / kN;   // TMEM accumulators (2 x 256 or 4 x 128 columns)
   static_assert((int)kBuf <= kTfPerGroup && kGroups <= (int)kBuf && kGroups <= kMaxGroups, "a group must own a whole accumulator while it drains it");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c_all_last = A.n_chunk * (kBN / kN) - 1;
+  const int c_all_last = (A.n_chunk * kBN / kComp + kLch - 1) / kLch - 1;   // last chunk of kLch wavelengths on the padded axis
   const uint32_t grp = (uint32_t)(warp - kEpiWarp0) >> 2;
   if (grp >= (uint32_t)kGroups) return;
   {
@@ -294,12 +294,26 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
   }
 }
 
-template <int kComp, int kNF, bool kSpec>
+// kN = accumulator columns per chunk: 256 (two TMEM accumulators) or, for one spectral component, 160 (THREE
+// accumulators: the MMA warp always has a free one, so an epilogue group that hands an accumulator back finds its next
+// chunk already multiplied instead of waiting one MMA time for it).
+template <int kN>
+struct SynthCfg {
+  static constexpr int kBBytesN = kN * kBK * 4;
+  static constexpr int kStageBytesN = 2 * kABytes + 2 * kBBytesN;
+  static constexpr int kBufN = 512 / kN;
+};
+
+template <int kComp, int kNF, bool kSpec, int kN>
 __global__ void __launch_bounds__(kSynthThreads, 1)
 synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
              const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo,
              const __grid_constant__ SynthArgs A) {
-  constexpr int kLch = kBN / kComp;  // wavelengths per chunk
+  static_assert(kN == kBN || kComp == 1, "the grid's two-component row layout is built for 256-column chunks");
+  constexpr int kBBytes = SynthCfg<kN>::kBBytesN;
+  constexpr int kStageBytes = SynthCfg<kN>::kStageBytesN;
+  constexpr uint32_t kBuf = SynthCfg<kN>::kBufN;
+  constexpr int kLch = kN / kComp;  // wavelengths per chunk
   constexpr int kSub = kLch / 32;    // 32-wavelength sub-chunks per chunk
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [stages][W_hi | W_lo | G_hi | G_lo], filter table, barriers
@@ -309,8 +323,8 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kStages;                       // [kTfPerGroup * kMaxGroups] MMA -> epilogue group (see epilogue_loop)
-  uint64_t* tempty_bar = tfull_bar + kTfPerGroup * kMaxGroups;    // [2]              epilogue -> MMA, per TMEM accumulator
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + kTfPerGroup * kMaxGroups;    // [kBuf]           epilogue -> MMA, per TMEM accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -320,7 +334,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < kTfPerGroup * kMaxGroups; ++b) mbar_init(&tfull_bar[b], 1);
-    for (int b = 0; b < 2; ++b) mbar_init(&tempty_bar[b], 4);  // 4 warps per epilogue group
+    for (int b = 0; b < (int)kBuf; ++b) mbar_init(&tempty_bar[b], 4);  // 4 warps per epilogue group
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -333,7 +347,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_tiles = A.n_tiles_dev ? min(A.n_tiles, __ldg(A.n_tiles_dev)) : A.n_tiles;
-  const int c_all_last = A.n_chunk - 1;
+  const int c_all_last = (A.n_chunk * kBN / kComp + kLch - 1) / kLch - 1;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -361,10 +375,10 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
               } else {
               mbar_expect_tx_e(elected, &full_bar[stage], lo_tiles ? kStageBytes : kABytes + kBBytes);
               tma_load_2d_e(elected, st, &tm_w_hi, fb, kb * kBK, tile * kBM, kEvictNormal);
-              tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, c * kBN, kEvictLast);
+              tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, c * kN, kEvictLast);
               if (lo_tiles) {
                 tma_load_2d_e(elected, st + kABytes, &tm_w_lo, fb, kb * kBK, tile * kBM, kEvictNormal);
-                tma_load_2d_e(elected, st + 2 * kABytes + kBBytes, &tm_g_lo, fb, k0 + kb * kBK, c * kBN, kEvictLast);
+                tma_load_2d_e(elected, st + 2 * kABytes + kBBytes, &tm_g_lo, fb, k0 + kb * kBK, c * kN, kEvictLast);
               }
               }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -379,7 +393,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
     // onto the (large) running sum: with a long K the small cross terms W_lo*G_hi + W_hi*G_lo are summed FIRST
     // (two_pass), while the accumulator is still small, and the W_hi*G_hi terms after.
     {
-      constexpr uint32_t idesc = make_idesc_tf32(kBM, kBN);
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, kN);
       const uint32_t elected = elect_one() ? 1u : 0u;
       const uint32_t s_addr = smem_u32(smem);
       const uint64_t desc0 = make_kmajor_sw128_desc(0);
@@ -393,10 +407,10 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
         const int n_c = c_last - c_first + 1, rot = chunk_rot(n_c, blockIdx.x);
         for (int j = 0; j < n_c; ++j, ++it) {
           const int c = chunk_at(c_first, n_c, rot, j);
-          const uint32_t buf = it & 1u;
-          mbar_wait(&tempty_bar[buf], ((it >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+          const uint32_t buf = it % kBuf;
+          mbar_wait(&tempty_bar[buf], ((it / kBuf) & 1u) ^ 1u);  // epilogue has drained this accumulator
           tc_fence_after();
-          const uint32_t d_tmem = tmem_u + buf * kBN;
+          const uint32_t d_tmem = tmem_u + buf * kN;
           for (int pass = 0; pass <= two_pass; ++pass) {
             for (int kb = 0; kb < n_kb; ++kb) {
               mbar_wait(&full_bar[stage], phase);
@@ -428,7 +442,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
       }
     }
   } else if (warp >= kEpiWarp0) {
-    epilogue_loop<kComp, kNF, kSpec, 1, kBN, 2>(A, s_uv, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
+    epilogue_loop<kComp, kNF, kSpec, 1, kN, 2>(A, s_uv, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
   }
 
   tc_fence_before();
