@@ -182,7 +182,7 @@ struct sb2_model {
   float2* part = nullptr;  // [2][n_filt][cap_pad] partial filter numerators of the two epilogue groups
   int wd_stride = 0;  // floats per weights row in DeltaConstant (bracket-grouped) mode; 0: mode unavailable
   CUtensorMap tm_wd_hi, tm_wd_lo, tm_g2_hi, tm_g2_lo, tm_g160_hi, tm_g160_lo;  // g160: 160-row boxes (three-accumulator variant)
-  size_t smem160_bytes = 0;  // g2: 128-row boxes (one CTA's half of a chunk)
+  size_t smem160_bytes = 0, smem_optin = 0;  // g2: 128-row boxes (one CTA's half of a chunk)
   size_t smem2_bytes = 0;
   double* g_mscale = nullptr;
   double* zpow = nullptr;
@@ -386,9 +386,10 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
     sb2_model_destroy(m);
     return rc;
   }
-  m->smem_bytes = 1024 + (size_t)sb2::kStages * sb2::kStageBytes + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 256;
-  m->smem160_bytes = 1024 + (size_t)sb2::kStages * sb2::SynthCfg<160>::kStageBytesN + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 256;
-  m->smem2_bytes = 1024 + (size_t)sb2::kW2Bytes + (size_t)sb2::kG2Slots * sb2::kG2Slot + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + 256;
+  m->smem_bytes = 1024 + (size_t)sb2::kStages * sb2::kStageBytes + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + sb2::kBarBytes;
+  m->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+  m->smem160_bytes = 1024 + (size_t)sb2::kStages * sb2::SynthCfg<160>::kStageBytesN + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + sb2::kBarBytes;
+  m->smem2_bytes = 1024 + (size_t)sb2::kW2Bytes + (size_t)sb2::kG2Slots * sb2::kG2Slot + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + sb2::kBarBytes;
   if (m->smem2_bytes > (size_t)prop.sharedMemPerBlockOptin || m->wd_stride > sb2::kW2Kb * sb2::kBK || (m->n_sm & 1)) m->smem2_bytes = 0;  // CTA-pair kernel unavailable
   if (m->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
     sb2_model_destroy(m);
@@ -434,9 +435,15 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
   if constexpr (C == 1) {
     if (use_n160(m)) {
       auto k = sb2::synth_kernel<C, NF, SPEC, 160>;
-      CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem160_bytes));
-      k<<<grid, sb2::kSynthThreads, m->smem160_bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo,
-                                                            m->tm_g160_hi, m->tm_g160_lo, a);
+      sb2::SynthArgs a2 = a;
+      size_t bytes = m->smem160_bytes;
+      if (SPEC && bytes + sb2::kSpecSmemBytes <= m->smem_optin) {   // room for the spectra transpose tiles
+        bytes += sb2::kSpecSmemBytes;
+        a2.spec_smem = 1;
+      }
+      CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      k<<<grid, sb2::kSynthThreads, bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo,
+                                                 m->tm_g160_hi, m->tm_g160_lo, a2);
       STAGE_CHECK("synth_kernel", st);
       return SB2_OK;
     }

@@ -55,6 +55,8 @@ constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // hi + lo of both opera
 constexpr int kMaxGroups = SB2_GROUPS;         // epilogue warpgroups in the CTA (partial-numerator planes)
 constexpr int kEpiWarp0 = 3;                   // first epilogue warp (warps 0-2: TMA producer, MMA issuer, TMEM allocator)
 constexpr int kSynthThreads = 32 * kEpiWarp0 + 128 * kMaxGroups;
+constexpr int kSpecSmemBytes = 8 * kMaxGroups / 2 * 32 * 33 * 4;   // one 32 x 33 float tile per epilogue warp
+constexpr int kBarBytes = 256;                 // barriers + TMEM slot
 constexpr int kTfPerGroup = 4;                 // "accumulator ready" barriers per epilogue group: one per chunk that can be
                                                // outstanding (<= number of TMEM accumulators), so no barrier is ever committed
                                                // twice before its group has seen the first completion
@@ -88,6 +90,7 @@ struct SynthArgs {
   float* out_base;
   double* out_scaled;
   float* out_spec;
+  int spec_smem;         // 1: the launch reserved kSpecSmemBytes after the barriers for the spectra transpose tiles
   int filt_lo[kMaxFilt], filt_hi[kMaxFilt], filt_off[kMaxFilt];  // filt_off: start of the PADDED table
   float filt_su[kMaxFilt], filt_sdv[kMaxFilt];
 };
@@ -126,8 +129,8 @@ __device__ __forceinline__ int chunk_rot(int n_c, unsigned who) { return n_c > 0
 // wait only carries one parity bit, so a waiter must see every phase of a barrier in order -- which a group does
 // for its own pair, but would not for per-buffer barriers that other groups also consume.
 template <int kComp, int kNF, bool kSpec, int kCta, int kN, int kGroups>
-__device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* s_uv, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                              uint32_t tempty_addr, uint32_t tmem_base, int unit0, int unit_stride,
+__device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* s_uv, float* s_spec, uint64_t* tfull_bar,
+                                              uint64_t* tempty_bar, uint32_t tempty_addr, uint32_t tmem_base, int unit0, int unit_stride,
                                               int n_units, uint32_t cta_rank) {
   constexpr int kLch = kN / kComp;      // wavelengths per chunk
   constexpr int kSub = kLch / 32;       // 32-wavelength sub-chunks per chunk
@@ -237,11 +240,27 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
             for (int j = 0; j < 32; ++j) s[j] *= __ldg(ig + j * 128);
           }
           if constexpr (kSpec) {
-            if (A.out_spec != nullptr && orig >= 0) {
-              const float sc = (kComp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row];
+            if (A.out_spec != nullptr) {
+              const float sc = orig < 0 ? 0.f : ((kComp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row]);
+              if (s_spec != nullptr) {
+                // a thread holds 32 wavelengths of ONE galaxy; transposed through a 32 x 33 tile so that each store
+                // instruction writes 128 contiguous bytes of one output row (per-thread stores reached 2 % of HBM)
+                float* tile = s_spec + (warp - kEpiWarp0) * (32 * 33);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (i0 + j < A.n_lam) A.out_spec[(size_t)orig * A.n_lam + i0 + j] = s[j] * sc;
+                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = s[j] * sc;
+                __syncwarp();
+                const bool in_lam = i0 + lane < A.n_lam;
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                  const int o = __shfl_sync(FULL, orig, r);
+                  if (o >= 0 && in_lam) A.out_spec[(size_t)o * A.n_lam + i0 + lane] = tile[r * 33 + lane];
+                }
+                __syncwarp();
+              } else if (orig >= 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (i0 + j < A.n_lam) A.out_spec[(size_t)orig * A.n_lam + i0 + j] = s[j] * sc;
+              }
             }
           }
           // filter numerators: (numU_f, numV_f) += s_i * (U_f[n], V_f[n]),  n = i + m ; loop over the filters whose
@@ -442,7 +461,8 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
       }
     }
   } else if (warp >= kEpiWarp0) {
-    epilogue_loop<kComp, kNF, kSpec, 1, kN, 2>(A, s_uv, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
+    float* s_spec = (kSpec && A.spec_smem) ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes) : nullptr;
+    epilogue_loop<kComp, kNF, kSpec, 1, kN, 2>(A, s_uv, s_spec, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
   }
 
   tc_fence_before();
@@ -628,7 +648,7 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
       }
     }
   } else if (warp >= kEpiWarp0) {
-    epilogue_loop<kComp, kNF, kSpec, 2, kBN2, (kT2Buf >= 3 && kMaxGroups >= 3 ? 3 : 2)>(A, s_uv, tfull_bar, tempty_bar, mapa_u32(smem_u32(tempty_bar), 0), tmem_base, unit0,
+    epilogue_loop<kComp, kNF, kSpec, 2, kBN2, (kT2Buf >= 3 && kMaxGroups >= 3 ? 3 : 2)>(A, s_uv, nullptr, tfull_bar, tempty_bar, mapa_u32(smem_u32(tempty_bar), 0), tmem_base, unit0,
                                         unit_stride, n_units, rank);
   }
 
