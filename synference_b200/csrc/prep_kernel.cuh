@@ -640,26 +640,39 @@ __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __r
   if ((int)(blockIdx.y + 1) * kIgmStrip <= first_bin) return;
   __shared__ double s_thr[3 * 64];
   __shared__ double s_pre[5 * 64];
+  __shared__ __align__(16) double s_bin[kIgmStrip * 8];   // per bin: x^1.2, x^2.1, x^3.7, x^5.5, x^-0.3, x, nline, lc_on
   const int np1 = M.n_lines + 1;
+  const int nb = M.n_blue;
+  const int strip0 = (int)blockIdx.y * kIgmStrip;
   for (int i = threadIdx.x; i < 3 * 64; i += 128) s_thr[i] = M.thr[i];
   for (int i = threadIdx.x; i < 5 * np1; i += 128) s_pre[(i / np1) * 64 + (i % np1)] = M.pre[i];
+  for (int i = threadIdx.x; i < kIgmStrip * 8; i += 128) {
+    const int b = strip0 + (i >> 3), k = i & 7;
+    double v = 0.0;
+    if (b < nb) {
+      if (k < 5) v = M.bin_pow[k * nb + b];
+      else if (k == 5) v = M.bin_pow[7 * nb + b];
+      else if (k == 6) v = (double)M.nline[b];
+      else v = (double)M.lc_on[b];
+    }
+    s_bin[i] = v;
+  }
   __syncthreads();
-  const int nb = M.n_blue;
   const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
   double Z[12];
 #pragma unroll
   for (int p = 0; p < 12; ++p) Z[p] = zpow[(size_t)p * n_pad + t];
   const double z = zpow[(size_t)12 * n_pad + t];
   const double zp = 1.0 + z;
-  const int i0 = max((int)blockIdx.y * kIgmStrip, first_bin);
-  const int i1 = min(nb, (int)(blockIdx.y + 1) * kIgmStrip);
+  const int i0 = max(strip0, first_bin);
+  const int i1 = min(nb, strip0 + kIgmStrip);
   float* out = igm + ((size_t)blockIdx.x * nb_pad) * 128 + threadIdx.x;
-  for (int i = max(i0, nb); i < min(nb_pad, (int)(blockIdx.y + 1) * kIgmStrip); ++i) out[(size_t)i * 128] = 1.f;  // padding rows
+  for (int i = max(i0, nb); i < min(nb_pad, strip0 + kIgmStrip); ++i) out[(size_t)i * 128] = 1.f;  // padding rows
   if (i0 >= nb) return;
   // lines (sorted by decreasing wavelength) still below the regime thresholds at the strip's first bin
   int n1 = 0, n2 = 0, nd = 0;
   {
-    const double xl = __ldg(M.bin_pow + 7 * nb + i0) * zp;
+    const double xl = s_bin[(i0 - strip0) * 8 + 5] * zp;
 #pragma unroll
     for (int step = 32; step; step >>= 1) {
       if (s_thr[0 * 64 + n1 + step - 1] > xl) n1 += step;
@@ -667,28 +680,32 @@ __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __r
       if (s_thr[2 * 64 + nd + step - 1] > xl) nd += step;
     }
   }
-  for (int i = i0; i < i1; ++i) {
-    const double xl = __ldg(M.bin_pow + 7 * nb + i) * zp;  // lam_obs / 911.8
+  // regime flags that depend on the galaxy only
+  const bool dla_lo = z < 2.0, laf_a = z < 1.2, laf_b = z < 4.7;
+  const double2* bp = reinterpret_cast<const double2*>(s_bin + (i0 - strip0) * 8);
+  float* op = out + (size_t)i0 * 128;
+  for (int i = i0; i < i1; ++i, bp += 4, op += 128) {
+    const double2 q01 = bp[0], q23 = bp[1], q45 = bp[2], q67 = bp[3];
+    const double xl = q45.y * zp;  // lam_obs / 911.8
     while (n1 > 0 && !(s_thr[0 * 64 + n1 - 1] > xl)) --n1;
     while (n2 > 0 && !(s_thr[1 * 64 + n2 - 1] > xl)) --n2;
     while (nd > 0 && !(s_thr[2 * 64 + nd - 1] > xl)) --nd;
-    const double b12 = __ldg(M.bin_pow + 0 * nb + i) * Z[0], b37 = __ldg(M.bin_pow + 2 * nb + i) * Z[2];
-    const double b55 = __ldg(M.bin_pow + 3 * nb + i) * Z[3];
+    const double b12 = q01.x * Z[0], b37 = q23.x * Z[2], b55 = q23.y * Z[3];
     const double b2 = xl * xl, b3 = b2 * xl;
-    const int J = __ldg(M.nline + i);
+    const int J = (int)q67.x;
     const int a = min(J, n1), b = min(J, n2), c = min(J, nd);
     double tau = b12 * s_pre[0 * 64 + a] + b37 * (s_pre[1 * 64 + b] - s_pre[1 * 64 + a]) +
                  b55 * (s_pre[2 * 64 + J] - s_pre[2 * 64 + b]) + b2 * s_pre[3 * 64 + c] +
                  b3 * (s_pre[4 * 64 + J] - s_pre[4 * 64 + c]);
-    if (__ldg(M.lc_on + i)) {
-      const double b21 = __ldg(M.bin_pow + 1 * nb + i) * Z[1], bm3 = __ldg(M.bin_pow + 4 * nb + i) * Z[4];
+    if (q67.y != 0.0) {
+      const double b21 = q01.y * Z[1], bm3 = q45.x * Z[4];
       // Lyman continuum, DLA component
-      if (z < 2.0) tau += 0.2113 * Z[5] - 0.07661 * Z[10] * bm3 - 0.1347 * b2;
+      if (dla_lo) tau += 0.2113 * Z[5] - 0.07661 * Z[10] * bm3 - 0.1347 * b2;
       else if (xl >= 3.0) tau += 0.04696 * Z[6] - 0.01779 * Z[11] * bm3 - 0.02916 * b3;
       else tau += 0.6340 + 0.04696 * Z[6] - 0.01779 * Z[11] * bm3 - 0.1347 * b2 - 0.2905 * bm3;
       // Lyman continuum, LAF component
-      if (z < 1.2) tau += 0.3248 * (b12 - Z[7] * b21);
-      else if (z < 4.7) {
+      if (laf_a) tau += 0.3248 * (b12 - Z[7] * b21);
+      else if (laf_b) {
         if (xl >= 2.2) tau += 2.545e-2 * (Z[8] * b21 - b37);
         else tau += 2.545e-2 * Z[8] * b21 + 0.3248 * b12 - 0.2496 * b21;
       } else {
@@ -701,7 +718,7 @@ __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __r
     const double y = -tau * 1.44269504088896340736;
     const double yn = rint(fmin(fmax(y, -200.0), 100.0));
     const int ex = (int)yn + 127;
-    out[(size_t)i * 128] = ex > 0 ? __int_as_float(ex << 23) * exp2f((float)(y - yn)) : 0.f;
+    *op = ex > 0 ? __int_as_float(ex << 23) * exp2f((float)(y - yn)) : 0.f;
   }
 }
 
