@@ -34,6 +34,7 @@ typedef enum sb2_status {
  * src/synference/library.py:1313). Row layout of sb2_params.sfh_rows:
  *   [0]=min_age [1]=max_age (yr, lookback) then
  *   GAUSSIAN: peak_age, sigma | EXPONENTIAL/DECLINING/DELAYED: tau | LOGNORMAL: tau, peak_age
+ *   DOUBLE_POWERLAW: peak_age, alpha, beta (bins integrated by 16-point Gauss-Legendre)
  *   CONTINUITY: n_bins, edges[n_bins+1] (yr), logsfr_ratios[n_bins-1]                        */
 enum { SB2_SFH_CONSTANT = 0, SB2_SFH_GAUSSIAN = 1, SB2_SFH_EXPONENTIAL = 2, SB2_SFH_DECLINING_EXP = 3,
        SB2_SFH_DELAYED_EXP = 4, SB2_SFH_LOGNORMAL = 5, SB2_SFH_DOUBLE_POWERLAW = 6, SB2_SFH_CONTINUITY = 7 };

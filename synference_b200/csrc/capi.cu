@@ -540,7 +540,7 @@ int check_params(const sb2_model* m, const sb2_params* p) {
   if (p->n > m->cap) return fail(SB2_ERR_CAPACITY, "batch of " + std::to_string(p->n) + " exceeds max_batch " + std::to_string(m->cap));
   if (!p->redshift || !p->sfh_rows || !p->zd_value) return fail(SB2_ERR_INVALID, "redshift, sfh_rows and zd_value are required");
   if (p->sfh_stride < 2 || p->sfh_stride > SB2_SFH_ROW) return fail(SB2_ERR_INVALID, "sfh_stride out of range");
-  if (p->sfh_type < 0 || p->sfh_type > SB2_SFH_CONTINUITY || p->sfh_type == SB2_SFH_DOUBLE_POWERLAW)
+  if (p->sfh_type < 0 || p->sfh_type > SB2_SFH_CONTINUITY)
     return fail(SB2_ERR_INVALID, "unsupported sfh_type");
   if (p->zd_type < 0 || p->zd_type > SB2_ZD_NORMAL_LOG10) return fail(SB2_ERR_INVALID, "bad zd_type");
   if (p->zd_type >= SB2_ZD_NORMAL_LINEAR && !p->zd_sigma) return fail(SB2_ERR_INVALID, "zd_sigma required for Normal");

@@ -186,6 +186,7 @@ __device__ __forceinline__ EdgeVal sfh_edge(const FastMath& F, int type, const d
   EdgeVal v{0.0, 0.0};
   switch (type) {
     case SB2_SFH_CONSTANT:
+    case SB2_SFH_DOUBLE_POWERLAW:   // no antiderivative: the clipped edge itself, the bin is integrated numerically
       v.a = t;
       break;
     case SB2_SFH_GAUSSIAN: {
@@ -241,9 +242,32 @@ __device__ __forceinline__ double phi_between(EdgeVal lo, EdgeVal hi) {
   return -(1.0 - lo.a - hi.a);
 }
 
+// DoublePowerLaw sfr(t) = 1 / ((t/peak)^alpha + (t/peak)^beta) over [lo, hi]: 16-point Gauss-Legendre (the reference
+// integrates every bin with scipy.quad; a 0.1-dex age bin of this smooth integrand converges to ~1e-12)
+__device__ __noinline__ double dpl_bin_mass(const double* __restrict__ p, double lo, double hi) {
+  if (!(hi > lo)) return 0.0;
+  const double x[8] = {0.0950125098376374, 0.2816035507792589, 0.4580167776572274, 0.6178762444026438,
+                       0.7554044083550030, 0.8656312023878318, 0.9445750230732326, 0.9894009349916499};
+  const double w[8] = {0.1894506104550685, 0.1826034150449236, 0.1691565193950025, 0.1495959888165767,
+                       0.1246289712555339, 0.0951585116824928, 0.0622535239386479, 0.0271524594117541};
+  const double mid = 0.5 * (lo + hi), half = 0.5 * (hi - lo), inv_pk = 1.0 / p[0];
+  double acc = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int sgn = -1; sgn <= 1; sgn += 2) {
+      const double l = log((mid + sgn * half * x[i]) * inv_pk);
+      acc += w[i] / (exp(p[1] * l) + exp(p[2] * l));
+    }
+  }
+  return acc * half;
+}
+
 __device__ __forceinline__ double sfh_mass_from_edges(int type, const double* __restrict__ p, EdgeVal lo, EdgeVal hi) {
   const double s2pi = 2.50662827463100050242;
   switch (type) {
+    case SB2_SFH_DOUBLE_POWERLAW:
+      return dpl_bin_mass(p, lo.a, hi.a);
     case SB2_SFH_GAUSSIAN:
       return p[1] * s2pi * phi_between(lo, hi);
     case SB2_SFH_LOGNORMAL:

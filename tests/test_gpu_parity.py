@@ -142,6 +142,21 @@ def test_every_sfh_family(engines, sfh_type):
     assert_flux_close(eng.photometry(q, scaled=False), oracle_flux(w, params=q, c=True))
 
 
+def test_double_power_law_sfh(engines):
+    """DoublePowerLaw has no antiderivative: the kernel integrates each age bin with 16-point Gauss-Legendre, the
+    oracle with scipy.quad (the reference's own method)."""
+    w, eng = engines("cfg2", 48)
+    p = w.params
+    mx = p.sfh_rows[:, 1]
+    rng = np.random.default_rng(4)
+    rows = np.stack([np.zeros_like(mx), mx, rng.uniform(0.1, 0.8, mx.size) * mx, rng.uniform(1.0, 8.0, mx.size),
+                     -rng.uniform(0.5, 6.0, mx.size)], 1)
+    q = GalaxyParams(p.redshift, 6, np.ascontiguousarray(rows), p.zd_type, p.zd_value, None, p.log_mass, p.tau_v)
+    W, Wo = eng.weights(q), A.weights_matrix(q, w.grid.log10ages, w.grid.metallicity)
+    np.testing.assert_allclose(W, Wo, rtol=0, atol=2e-8)          # quad's default tolerance is 1.49e-8
+    assert_flux_close(eng.photometry(q, scaled=False), oracle_flux(w, params=q))
+
+
 def test_metallicity_edge_cases(engines):
     w, eng = engines("cfg2", 64)
     p = w.params
@@ -211,7 +226,7 @@ def test_invalid_arguments_raise(engines):
     w, eng = engines("cfg1", 16)
     p = w.params
     with pytest.raises(ValueError):
-        eng.photometry(GalaxyParams(p.redshift, 6, p.sfh_rows, p.zd_type, p.zd_value, None, p.log_mass, None))
+        eng.photometry(GalaxyParams(p.redshift, 8, p.sfh_rows, p.zd_type, p.zd_value, None, p.log_mass, None))
     with pytest.raises(ValueError):
         eng.photometry(GalaxyParams(p.redshift, p.sfh_type, p.sfh_rows, 3, p.zd_value, None, p.log_mass, None))
     big = make_workload("cfg1", (1 << 15) + 1)
