@@ -92,6 +92,12 @@ typedef struct sb2_model_desc {
    * CUDA math library is used instead (slower, same results to ~1e-12).  Built by synference_b200/fastmath.py:
    * fm_log_tab [256][2] = ln(m0), 1/m0 ; fm_exp_tab [64] = 2^(j/64) ; fm_tail_tab [fm_tail_n][8] = local
    * degree-7 polynomials of exp(u^2/2) Q(u) on intervals of width fm_tail_w.                              */
+  /* Optional per-galaxy dust-curve shape (Calzetti2000(slope="...", ampl="...") of the reference's production script,
+   * final_library_generation_multinode.py:496): tau(lambda)/tau_V = (kappa + ampl_g * dust_d0) * 2^(slope_g * dust_l2),
+   * with `kappa` then holding the curve at slope = 0, ampl = 0; dust_d0 = bump profile / k(0.55 um) and
+   * dust_l2 = log2(lambda / 0.55 um) on the same padded axis as kappa.  NULL: the curve is global (kappa only).   */
+  const float* dust_d0;
+  const float* dust_l2;
   const double* fm_log_tab;
   const double* fm_exp_tab;
   const double* fm_tail_tab;
@@ -120,6 +126,8 @@ typedef struct sb2_params {
   const double* zd_sigma; /* [n] (NULL for delta) */
   const double* coef_att;   /* [n] optional per-galaxy factor on the attenuated component   */
   const double* coef_unatt; /* [n] optional per-galaxy factor on the unattenuated component */
+  const double* dust_slope; /* [n] per-galaxy power-law slope delta of the dust curve (requires dust_d0/dust_l2)  */
+  const double* dust_ampl;  /* [n] per-galaxy UV-bump amplitude                       (requires dust_d0/dust_l2)  */
 } sb2_params;
 
 typedef struct sb2_model sb2_model;

@@ -352,7 +352,8 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
 
     galaxies : list of dicts with redshift, tau_v, sfh_kind, sfh (dict, ages in yr),
                zd_kind, zd_value, zd_sigma and optionally fesc (per-galaxy escape fraction: the emission tree
-               of SURVEY A5 is then evaluated with that galaxy's value instead of the global ``fesc``)
+               of SURVEY A5 is then evaluated with that galaxy's value instead of the global ``fesc``) and
+               dust_slope / dust_ampl (per-galaxy shape of the attenuation curve)
     filters  : list of (lam_table [A], transmission) on each filter's own axis
     dust     : None or dict(curve=..., slope=..., ampl=...)  ;  igm : None or (laf, dla)
     """
@@ -371,7 +372,13 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
         lnu = w @ g_un2  # A4: grid-weighted sum, erg/s/Hz per Msun
         att = w @ g_att2
         if kappa is not None:
-            att = att * np.exp(-gal.get("tau_v", 0.0) * kappa)
+            kap = kappa
+            if "dust_slope" in gal or "dust_ampl" in gal:
+                dd = dict(dust)
+                dd["slope"] = float(gal.get("dust_slope", dd.get("slope", 0.0)))
+                dd["ampl"] = float(gal.get("dust_ampl", dd.get("ampl", 0.0)))
+                kap = dust_kappa(lam, **dd)
+            att = att * np.exp(-gal.get("tau_v", 0.0) * kap)
         lnu = (lnu + att) * base_mass
         z = float(gal["redshift"])
         dl = luminosity_distance_cm(z) if dl_cm is None else dl_cm[g]

@@ -163,6 +163,7 @@ struct sb2_model {
   // model tables
   double *ages = nullptr, *edges = nullptr, *zmet = nullptr, *log10zmet = nullptr;
   float *gt_hi = nullptr, *gt_lo = nullptr, *kappa = nullptr, *filt_uv = nullptr;
+  float *dust_d0 = nullptr, *dust_l2 = nullptr, *g_slope = nullptr, *g_ampl = nullptr;   // per-galaxy dust shape (optional)
   int *filt_lo = nullptr, *filt_hi = nullptr;
   double *bin_pow = nullptr, *thr = nullptr, *pre = nullptr;
   int *nline = nullptr, *lc_on = nullptr;
@@ -234,7 +235,7 @@ int sb2_device_count(void) {
 int sb2_model_destroy(sb2_model* m) {
   if (!m) return SB2_OK;
   cudaSetDevice(m->device);
-  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->filt_uv, m->filt_lo,
+  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->dust_d0, m->dust_l2, m->g_slope, m->g_ampl, m->filt_uv, m->filt_lo,
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage, m->fm_log, m->fm_exp, m->fm_tail,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
                   m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params[0],
@@ -299,6 +300,14 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
     std::vector<float> kap((size_t)d->n_chunk * lch, 0.f);
     if (d->kappa) std::memcpy(kap.data(), d->kappa, kap.size() * sizeof(float));
     UP(kappa, kap.data(), kap.size());
+    if (d->dust_d0 && d->dust_l2) {
+      if (!d->kappa) { sb2_model_destroy(m); return fail(SB2_ERR_INVALID, "dust_d0/dust_l2 need kappa"); }
+      std::vector<float> t0(kap.size(), 0.f), t1(kap.size(), 0.f);
+      std::memcpy(t0.data(), d->dust_d0, t0.size() * sizeof(float));
+      std::memcpy(t1.data(), d->dust_l2, t1.size() * sizeof(float));
+      UP(dust_d0, t0.data(), t0.size());
+      UP(dust_l2, t1.data(), t1.size());
+    }
   }
   {
     // (U, V) tables with kUvPad zero entries on both sides of every filter, so the epilogue's shifted reads
@@ -361,6 +370,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(tile_range, (np / 128) * sizeof(int4));
   AL(part, (size_t)sb2::kMaxGroups * d->n_filt * np * sizeof(float2));
   AL(g_m, np * 4); AL(g_orig, np * 4); AL(perm, np * 4); AL(idx, np * 4);
+  if (m->dust_d0) { AL(g_slope, np * 4); AL(g_ampl, np * 4); }
   AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
   AL(keys, np * 4); AL(keys_sorted, np * 4); AL(perm_pad, np * 4); AL(tile_k0, (np / 128) * 4); AL(grp, (3 * kMaxGroups + 1) * 4);
   AL(g_mscale, np * 8); AL(g_trunc, np * 4); AL(zpow, np * 13 * 8);
@@ -368,7 +378,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)m->cap);
   AL(cub_tmp, m->cub_bytes + 16);
   for (int sl = 0; sl < 2; ++sl) {
-    AL(stage_params[sl], (size_t)m->cap * (7 + SB2_SFH_ROW) * 8);
+    AL(stage_params[sl], (size_t)m->cap * (9 + SB2_SFH_ROW) * 8);
     AL(stage_flux[sl], (size_t)m->cap * d->n_filt * 4);
     AL(stage_flux64[sl], (size_t)m->cap * d->n_filt * 8);
   }
@@ -530,7 +540,7 @@ sb2::PrepParams prep_params(const sb2_params* p) {
   P.sfh_type = p->sfh_type; P.sfh_stride = p->sfh_stride; P.sfh_rows = p->sfh_rows;
   P.max_age_from_z = p->max_age_from_z; P.norm_mask = p->norm_mask; P.age_zmax_gyr = p->age_zmax_gyr;
   P.zd_type = p->zd_type; P.zd_value = p->zd_value; P.zd_sigma = p->zd_sigma;
-  P.coef_att = p->coef_att; P.coef_unatt = p->coef_unatt;
+  P.coef_att = p->coef_att; P.coef_unatt = p->coef_unatt; P.dust_slope = p->dust_slope; P.dust_ampl = p->dust_ampl;
   return P;
 }
 
@@ -544,6 +554,8 @@ int check_params(const sb2_model* m, const sb2_params* p) {
     return fail(SB2_ERR_INVALID, "unsupported sfh_type");
   if (p->zd_type < 0 || p->zd_type > SB2_ZD_NORMAL_LOG10) return fail(SB2_ERR_INVALID, "bad zd_type");
   if (p->zd_type >= SB2_ZD_NORMAL_LINEAR && !p->zd_sigma) return fail(SB2_ERR_INVALID, "zd_sigma required for Normal");
+  if ((p->dust_slope || p->dust_ampl) && !m->dust_d0)
+    return fail(SB2_ERR_INVALID, "per-galaxy dust_slope / dust_ampl need a model created with dust_d0 and dust_l2");
   return SB2_OK;
 }
 
@@ -596,6 +608,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   sb2::PrepOut O{};
   O.w_hi = m->w_hi; O.w_lo = m->w_lo; O.w_f64 = w_f64; O.igm = m->igm; O.g_m = m->g_m; O.g_beta = m->g_beta; O.g_gamma = m->g_gamma;
   O.g_taut = m->g_taut; O.g_scale = m->g_scale; O.g_ca = m->g_ca; O.g_cb = m->g_cb; O.g_orig = m->g_orig;
+  O.g_slope = m->g_slope; O.g_ampl = m->g_ampl;
   O.g_mscale = m->g_mscale; O.g_trunc = m->g_trunc; O.zpow = m->zpow;
   if (!w_f64) {  // the parity hook (sb2_build_weights) needs the weights only
     sb2::scalars_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(M, P, O, perm, n_pad);
@@ -671,6 +684,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.n_chunk = d.n_chunk; a.n_kb = (a.k8_total + 3) / 4; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
   a.n_blue = d.n_blue; a.n_blue_pad = m->n_blue_pad; a.uv_len = m->uv_len;
   a.tile_range = m->tile_range;
+  a.dust_d0 = m->dust_d0; a.dust_l2 = m->dust_l2; a.g_slope = m->g_slope; a.g_ampl = m->g_ampl;
   a.kappa = m->kappa; a.filt_uv = reinterpret_cast<const float2*>(m->filt_uv); a.igm = m->igm;
   a.g_m = m->g_m; a.g_beta = m->g_beta; a.g_gamma = m->g_gamma; a.g_taut = m->g_taut; a.g_scale = m->g_scale; a.g_ca = m->g_ca;
   a.g_cb = m->g_cb; a.g_orig = m->g_orig; a.g_mscale = m->g_mscale; a.g_trunc = m->g_trunc;
@@ -745,10 +759,12 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
   // copied in on st_h2d, synthesised on st_comp and copied out on st_d2h, so the PCIe copies of one slice
   // overlap the kernels of its neighbours (pinned host buffers are needed for the overlap, not for correctness).
   double* base = m->stage_params[slot];
-  const double* src[8] = {p->redshift, p->log_mass, p->tau_v, p->zd_value, p->zd_sigma, p->coef_att, p->coef_unatt, p->sfh_rows};
-  double* dev[8];
-  for (int i = 0; i < 8; ++i) {
-    const size_t w = (i == 7) ? (size_t)p->sfh_stride : 1;
+  constexpr int kNA = 10;   // staged arrays; the last one is the SFH row table
+  const double* src[kNA] = {p->redshift, p->log_mass, p->tau_v, p->zd_value, p->zd_sigma, p->coef_att, p->coef_unatt,
+                            p->dust_slope, p->dust_ampl, p->sfh_rows};
+  double* dev[kNA];
+  for (int i = 0; i < kNA; ++i) {
+    const size_t w = (i == kNA - 1) ? (size_t)p->sfh_stride : 1;
     dev[i] = src[i] ? base : nullptr;
     if (src[i]) base += n * w;
   }
@@ -772,9 +788,9 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
   for (int sl = 0; sl < n_slice; ++sl) {
     const size_t a = (size_t)sl * per, b = std::min(n, a + per);
     if (a >= b) break;
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kNA; ++i) {
       if (!src[i]) continue;
-      const size_t w = (i == 7) ? (size_t)p->sfh_stride : 1;
+      const size_t w = (i == kNA - 1) ? (size_t)p->sfh_stride : 1;
       CU_TRY(cudaMemcpyAsync(dev[i] + a * w, src[i] + a * w, (b - a) * w * sizeof(double), cudaMemcpyHostToDevice, m->st_h2d));
     }
     CU_TRY(cudaEventRecord(m->ev_in[sl], m->st_h2d));
@@ -786,7 +802,8 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
     dp.redshift = dev[0] + a; dp.log_mass = dev[1] ? dev[1] + a : nullptr; dp.tau_v = dev[2] ? dev[2] + a : nullptr;
     dp.zd_value = dev[3] + a; dp.zd_sigma = dev[4] ? dev[4] + a : nullptr;
     dp.coef_att = dev[5] ? dev[5] + a : nullptr; dp.coef_unatt = dev[6] ? dev[6] + a : nullptr;
-    dp.sfh_rows = dev[7] + a * p->sfh_stride;
+    dp.dust_slope = dev[7] ? dev[7] + a : nullptr; dp.dust_ampl = dev[8] ? dev[8] + a : nullptr;
+    dp.sfh_rows = dev[9] + a * p->sfh_stride;
     rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux[slot] + a * nf : nullptr,
                               flux_scaled ? m->stage_flux64[slot] + a * nf : nullptr, nullptr, m->st_comp);
     if (rc != SB2_OK) return rc;

@@ -118,6 +118,8 @@ struct PrepParams {  // device pointers (sb2_params with device arrays)
   const double* zd_sigma;
   const double* coef_att;
   const double* coef_unatt;
+  const double* dust_slope;
+  const double* dust_ampl;
 };
 
 struct PrepOut {
@@ -133,6 +135,8 @@ struct PrepOut {
   float* g_scale;   // [n_pad]
   float* g_ca;      // [n_pad]
   float* g_cb;      // [n_pad]
+  float* g_slope;   // [n_pad] per-galaxy dust slope / bump amplitude (nullptr: global curve)
+  float* g_ampl;    // [n_pad]
   int* g_orig;      // [n_pad]  original index, -1 for padding rows
   double* g_mscale; // [n_pad]
   unsigned* g_trunc;// [n_pad]  bit f set: filter f not fully covered by the grid at this z
@@ -290,6 +294,7 @@ scalars_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ per
     }
     O.g_m[t] = 0; O.g_beta[t] = 0.5f; O.g_gamma[t] = 0.5f; O.g_taut[t] = 0.f; O.g_scale[t] = 0.f; O.g_ca[t] = 0.f;
     O.g_cb[t] = 0.f; O.g_orig[t] = -1; O.g_mscale[t] = 0.0; O.g_trunc[t] = 0u;
+    if (O.g_slope) { O.g_slope[t] = 0.f; O.g_ampl[t] = 0.f; }
     return;
   }
   double z = P.redshift[g];
@@ -318,6 +323,10 @@ scalars_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ per
   O.g_scale[t] = (float)scale;
   O.g_ca[t] = (float)(P.coef_att ? P.coef_att[g] : 1.0);
   O.g_cb[t] = (float)(P.coef_unatt ? P.coef_unatt[g] : 1.0);
+  if (O.g_slope) {
+    O.g_slope[t] = (float)(P.dust_slope ? P.dust_slope[g] : 0.0);
+    O.g_ampl[t] = (float)(P.dust_ampl ? P.dust_ampl[g] : 0.0);
+  }
   O.g_orig[t] = (int)g;
   O.g_mscale[t] = P.log_mass ? pow(10.0, P.log_mass[g]) / M.base_mass : 1.0;
   O.g_trunc[t] = trunc;

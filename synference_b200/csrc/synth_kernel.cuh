@@ -73,6 +73,10 @@ struct SynthArgs {
   const int* tile_k0;        // [n_tiles] first grid column (k) of each tile's weights, nullptr: 0
   const int4* tile_range;    // [n_tiles] {first, last wavelength chunk any filter of the tile needs, first bin & ~31, last bin}; nullptr: all
   const float* kappa;        // [n_chunk * lam_per_chunk], zero padded
+  const float* dust_d0;      // per-galaxy dust shape: tau/tau_V = (kappa + ampl_g dust_d0) 2^(slope_g dust_l2); nullptr: global
+  const float* dust_l2;
+  const float* g_slope;
+  const float* g_ampl;
   const float2* filt_uv;     // padded tables, uv_len entries
   const float* igm;          // [n_tiles][n_blue_pad][128]
   const int* g_m;
@@ -108,6 +112,13 @@ __device__ __forceinline__ void ffma2_bcast(float2& acc, float s, float2 uv) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(c) : "l"(a), "l"(b), "l"(c));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
+}
+
+// tau(lambda)/tau_V of a galaxy with its own slope and bump amplitude (Noll+09 form): the helper curve is
+// linear in the amplitude, the slope is a power law in lambda / 0.55 um.
+__device__ __forceinline__ float4 dust_shape(float4 k, float4 d, float4 l, float slope, float ampl) {
+  return make_float4(fmaf(ampl, d.x, k.x) * ex2_approx(slope * l.x), fmaf(ampl, d.y, k.y) * ex2_approx(slope * l.y),
+                     fmaf(ampl, d.z, k.z) * ex2_approx(slope * l.z), fmaf(ampl, d.w, k.w) * ex2_approx(slope * l.w));
 }
 
 // Chunk visiting order.  Every CTA (pair) walks the chunks of a unit cyclically from a different start: units that are
@@ -154,6 +165,8 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
       const int orig = A.g_orig[row];
       int m = A.g_m[row];
       const float ntaut = -A.g_taut[row];
+      const bool pg_dust = A.dust_d0 != nullptr;                // warp-uniform
+      const float slope = pg_dust ? A.g_slope[row] : 0.f, ampl = pg_dust ? A.g_ampl[row] : 0.f;
       // redshift-shift range of this warp's real galaxies (padding rows follow the others)
       int mmin = orig >= 0 ? m : INT_MAX, mmax = orig >= 0 ? m : INT_MIN;
 #pragma unroll
@@ -204,7 +217,9 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               tmem_ld_wait();
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 k4 = __ldg(kp + j4);
+                float4 k4 = __ldg(kp + j4);
+                if (pg_dust) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
+                                             __ldg(reinterpret_cast<const float4*>(A.dust_l2 + i0) + j4), slope, ampl);
                 s[4 * j4 + 0] = ca * (__uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x)) + cb * __uint_as_float(u[4 * j4 + 0]);
                 s[4 * j4 + 1] = ca * (__uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y)) + cb * __uint_as_float(u[4 * j4 + 1]);
                 s[4 * j4 + 2] = ca * (__uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z)) + cb * __uint_as_float(u[4 * j4 + 2]);
@@ -218,7 +233,9 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               } else
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {  // ca goes into the final scale
-                const float4 k4 = __ldg(kp + j4);
+                float4 k4 = __ldg(kp + j4);
+                if (pg_dust) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
+                                             __ldg(reinterpret_cast<const float4*>(A.dust_l2 + i0) + j4), slope, ampl);
                 s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x);
                 s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y);
                 s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z);

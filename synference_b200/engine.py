@@ -49,6 +49,8 @@ class GalaxyParams:
     tau_v: Optional[np.ndarray] = None
     coef_att: Optional[np.ndarray] = None
     coef_unatt: Optional[np.ndarray] = None
+    dust_slope: Optional[np.ndarray] = None     # per-galaxy dust-curve slope / bump amplitude (models built with
+    dust_ampl: Optional[np.ndarray] = None      # Calzetti2000(slope="...", ampl="..."))
     max_age_from_z: bool = False
     norm_mask: int = 0
     age_zmax_gyr: float = 0.0
@@ -76,8 +78,8 @@ class GalaxyParams:
         g = lambda a: None if a is None else a[sl]  # noqa: E731
         return GalaxyParams(self.redshift[sl], self.sfh_type, self.sfh_rows[sl], self.zd_type,
                             self.zd_value[sl], g(self.zd_sigma), g(self.log_mass), g(self.tau_v),
-                            g(self.coef_att), g(self.coef_unatt), self.max_age_from_z, self.norm_mask,
-                            self.age_zmax_gyr)
+                            g(self.coef_att), g(self.coef_unatt), g(self.dust_slope), g(self.dust_ampl),
+                            self.max_age_from_z, self.norm_mask, self.age_zmax_gyr)
 
 
 def geometric_ratio(lam):
@@ -131,10 +133,18 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         gt[:, ci, :, :nz * na_pad] = pad.reshape(n_chunk, lch, nz * na_pad)
     gt = gt.reshape(n_chunk * CHUNK_COLS, k_pad)
     gt_hi, gt_lo = tf32_split(gt)
-    kap = None
+    kap = d0 = l2 = None
     if kappa is not None:
         kap = np.zeros(n_chunk * lch, dtype=np.float32)
         kap[:n_lam] = kappa
+        if getattr(dust, "per_galaxy", False) and not dust_free:
+            # per-galaxy slope / bump amplitude: kappa holds the curve at slope = 0, ampl = 0 (get_tau already used 0 for
+            # the string-named ones; a numeric one is broadcast to every galaxy by SynthEngine._fill)
+            k0, dd, ll = dust.components(lam)
+            kap[:n_lam] = k0
+            d0 = np.zeros_like(kap)
+            l2 = np.zeros_like(kap)
+            d0[:n_lam], l2[:n_lam] = dd, ll
     # ---- filters on the shared axis -> (U, V) weight pairs (SURVEY A9 on a geometric grid):
     #      sample weight = (1-beta) U[n] + beta V[n], denominator = (1-beta) sum(U) + beta sum(V)
     if variant not in ("nu", "lam"):
@@ -168,7 +178,9 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         n_age=na, n_z=nz, n_lam=n_lam, n_comp=n_comp, n_filt=len(lo_l), n_age_pad=na_pad, k_pad=k_pad, n_chunk=n_chunk,
         log10ages=np.ascontiguousarray(grid.log10ages, dtype=np.float64),
         metallicities=np.ascontiguousarray(grid.metallicity, dtype=np.float64),
-        gt_hi=gt_hi, gt_lo=gt_lo, grid_scale=grid_scale, kappa=kap, lam0=float(lam[0]), q=q,
+        gt_hi=gt_hi, gt_lo=gt_lo, grid_scale=grid_scale, kappa=kap, dust_d0=d0, dust_l2=l2,
+        dust_global=(float(getattr(dust, "slope", 0.0)), float(getattr(dust, "ampl", 0.0))) if d0 is not None else None,
+        lam0=float(lam[0]), q=q,
         interp_variant=0 if variant == "nu" else 1,
         filt_lo=np.array(lo_l, dtype=np.int32), filt_hi=np.array(hi_l, dtype=np.int32),
         filt_off=np.array(off_l, dtype=np.int32), filt_uv=np.ascontiguousarray(uv),
@@ -221,6 +233,7 @@ class SynthEngine:
         d.gt_hi, d.gt_lo = ptr(t["gt_hi"], C.c_float), ptr(t["gt_lo"], C.c_float)
         d.grid_scale, d.lam0, d.q = t["grid_scale"], t["lam0"], t["q"]
         d.kappa = ptr(t["kappa"], C.c_float)
+        d.dust_d0, d.dust_l2 = ptr(t["dust_d0"], C.c_float), ptr(t["dust_l2"], C.c_float)
         d.filt_lo, d.filt_hi = ptr(t["filt_lo"], C.c_int32), ptr(t["filt_hi"], C.c_int32)
         d.filt_off, d.filt_uv = ptr(t["filt_off"], C.c_int32), ptr(t["filt_uv"], C.c_float)
         d.filt_uv_len = int(t["filt_uv"].shape[0])
@@ -268,7 +281,21 @@ class SynthEngine:
             s.coef_att, s.coef_unatt = get_ptr(p.coef_unatt), None
         else:
             s.coef_att, s.coef_unatt = get_ptr(p.coef_att), get_ptr(p.coef_unatt)
+        s.dust_slope, s.dust_ampl = self._dust_arrays(p, get_ptr)
         return s
+
+    def _dust_arrays(self, p: GalaxyParams, get_ptr):
+        """Per-galaxy dust slope / amplitude pointers; a parameter the curve holds as a number is broadcast."""
+        glob = self.tables.get("dust_global")
+        if glob is None:
+            if p.dust_slope is not None or p.dust_ampl is not None:
+                raise ValueError("per-galaxy dust slope / amplitude given, but the model's dust curve has numeric parameters; "
+                                 "build it with Calzetti2000(slope='slope', ampl='dust_bump_amplitude')")
+            return None, None
+        n = len(p)
+        sl = p.dust_slope if p.dust_slope is not None else np.full(n, glob[0])
+        am = p.dust_ampl if p.dust_ampl is not None else np.full(n, glob[1])
+        return get_ptr(sl), get_ptr(am)
 
     @staticmethod
     def _host_ptr_factory(keep):
@@ -320,9 +347,12 @@ class SynthEngine:
         dev = torch.device("cuda", self.device)
         mv = lambda a: None if a is None else torch.as_tensor(  # noqa: E731
             np.ascontiguousarray(a, dtype=np.float64)).to(dev)
-        return DeviceParams(params, {k: mv(getattr(params, k)) for k in
-                                     ("redshift", "log_mass", "tau_v", "sfh_rows", "zd_value", "zd_sigma",
-                                      "coef_att", "coef_unatt")})
+        tensors = {k: mv(getattr(params, k)) for k in ("redshift", "log_mass", "tau_v", "sfh_rows", "zd_value", "zd_sigma",
+                                                       "coef_att", "coef_unatt")}
+        keep = []
+        sl, am = self._dust_arrays(params, lambda a: (keep.append(np.ascontiguousarray(a, dtype=np.float64)), keep[-1])[1])
+        tensors["dust_slope"], tensors["dust_ampl"] = mv(sl), mv(am)
+        return DeviceParams(params, tensors)
 
     def _set_device_ptrs(self, s, tensors):
         ptr = lambda k: None if tensors.get(k) is None else tensors[k].data_ptr()  # noqa: E731
@@ -332,6 +362,7 @@ class SynthEngine:
             s.coef_att, s.coef_unatt = ptr("coef_unatt"), None
         else:
             s.coef_att, s.coef_unatt = ptr("coef_att"), ptr("coef_unatt")
+        s.dust_slope, s.dust_ampl = ptr("dust_slope"), ptr("dust_ampl")
 
     def photometry_device(self, dparams: "DeviceParams", flux_base=None, flux_scaled=None, spectra=None):
         """Run one batch whose parameters are already in HBM; outputs are caller-provided torch tensors."""

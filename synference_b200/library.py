@@ -98,11 +98,16 @@ class GalaxyBasis:
                 if key in ("bh", "gas"):
                     raise NotImplementedError("black-hole / gas emitters are outside the stellar hot path")
                 self.galaxy_params[key] = self.process_priors(value)
+        dust = getattr(emission_model, "dust_curve", None)
+        dust_names = {getattr(dust, "slope_name", None), getattr(dust, "ampl_name", None)} - {None}
+        for name in dust_names:
+            if name not in galaxy_params:
+                raise ValueError(f"the dust curve reads '{name}' per galaxy, but galaxy_params does not provide it")
         for key in galaxy_params:
-            if key in _UNSUPPORTED_EMITTER_PARAMS:
+            if key in _UNSUPPORTED_EMITTER_PARAMS and key not in dust_names:
                 raise NotImplementedError(
                     f"per-galaxy emitter parameter '{key}' is not implemented in the CUDA path yet "
-                    "(SURVEY 8f-1); 'tau_v' and 'fesc' vary per galaxy")
+                    "(SURVEY 8f-1); 'tau_v', 'fesc' and the dust curve's named slope / bump amplitude vary per galaxy")
         per_gal = getattr(emission_model, "fesc_per_galaxy", False)
         if per_gal and emission_model.fesc_name not in galaxy_params:
             raise ValueError(f"the emission model reads fesc from the per-galaxy parameter "
@@ -330,6 +335,10 @@ class GalaxyBasis:
                 if getattr(self.emission_model, "fesc_per_galaxy", False):
                     fesc = np.asarray(strip_units(self.all_parameters[self.emission_model.fesc_name]), dtype=float)[sl]
                     p.coef_att, p.coef_unatt = self.emission_model.coefficients(key, fesc)
+                dust = getattr(self.emission_model, "dust_curve", None)
+                for attr, name in (("dust_slope", getattr(dust, "slope_name", None)), ("dust_ampl", getattr(dust, "ampl_name", None))):
+                    if name is not None:
+                        setattr(p, attr, np.asarray(strip_units(self.all_parameters[name]), dtype=float)[sl])
                 flux = eng.photometry(p, scaled=False)
                 results["photometry"][key].append(flux)
                 label = self.instrument.label
@@ -841,7 +850,9 @@ class GalaxySimulator:
             zd = ZDistArray(ZD_NORMAL_LOG10, bc(params["mean"]), bc(params["sigma"]))
         tau_v = bc(params["tau_v"]) if "tau_v" in params else None
         fesc_name = getattr(self.emission_model, "fesc_name", None)
-        used = [k for k in params if k not in self.total_possible_keys and k not in ("tau_v", fesc_name)
+        dust = getattr(self.emission_model, "dust_curve", None)
+        slope_name, ampl_name = getattr(dust, "slope_name", None), getattr(dust, "ampl_name", None)
+        used = [k for k in params if k not in self.total_possible_keys and k not in ("tau_v", fesc_name, slope_name, ampl_name)
                 and k not in self.ignore_params and k not in cls.param_names]
         for k in used:
             if k not in self.unused_params:
@@ -855,6 +866,11 @@ class GalaxySimulator:
             if fesc_name not in params:
                 raise ValueError(f"Missing required parameter '{fesc_name}' (per-galaxy escape fraction of the emission model)")
             gp.coef_att, gp.coef_unatt = self.emission_model.coefficients(self.emission_model_key, bc(params[fesc_name]))
+        for attr, name in (("dust_slope", slope_name), ("dust_ampl", ampl_name)):
+            if name is not None:
+                if name not in params:
+                    raise ValueError(f"Missing required parameter '{name}' (read per galaxy by the dust curve)")
+                setattr(gp, attr, np.array(bc(params[name]), dtype=float))
         return gp
 
     def simulate(self, params):

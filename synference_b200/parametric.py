@@ -394,15 +394,29 @@ class PowerLaw:
 
 
 class Calzetti2000:
-    """Calzetti (2000) with the Noll+09 slope/bump modification."""
+    """Calzetti (2000) with the Noll+09 slope/bump modification.
+
+    ``slope`` and/or ``ampl`` may name a per-galaxy emitter attribute instead of being numbers
+    (``Calzetti2000(slope="slope", ampl="dust_bump_amplitude")``,
+    ``final_library_generation_multinode.py:496``): the curve is then
+    ``(K0 + ampl_g * D0) * (lam / 0.55um)**slope_g`` with the per-galaxy values supplied at run time
+    (:meth:`components`).
+    """
 
     def __init__(self, slope=0.0, cent_lam=0.2175, ampl=0.0, gamma=0.035):
-        self.slope, self.ampl = float(strip_units(slope)), float(strip_units(ampl))
+        self.slope_name = slope if isinstance(slope, str) else None
+        self.ampl_name = ampl if isinstance(ampl, str) else None
+        self.slope = 0.0 if self.slope_name else float(strip_units(slope))
+        self.ampl = 0.0 if self.ampl_name else float(strip_units(ampl))
         self.cent_lam = float(strip_units(cent_lam, "um")) if has_units(cent_lam) else float(cent_lam)
         self.gamma = float(strip_units(gamma, "um")) if has_units(gamma) else float(gamma)
         self.name = "Calzetti2000"
         self.params = {"slope": self.slope, "cent_lam": self.cent_lam, "ampl": self.ampl,
                        "gamma": self.gamma}
+
+    @property
+    def per_galaxy(self):
+        return self.slope_name is not None or self.ampl_name is not None
 
     @staticmethod
     def _k(x):
@@ -411,19 +425,35 @@ class Calzetti2000:
         red = -1.857 + 1.040 / x
         return 4.05 + 2.659 * np.where(x < 0.63, blue, red)
 
-    def get_tau(self, lam):
-        lam_um = strip_units(lam, "Angstrom") * 1.0e-4
-        x = np.arange(0.12, 2.2, 0.001)
-        k = self._k(x)
-        bump = self.ampl * (x * self.gamma) ** 2 / ((x**2 - self.cent_lam**2) ** 2 + (x * self.gamma) ** 2)
-        helper = (k + bump) / self._k(0.55)
+    @staticmethod
+    def _interp_extrap(lam_um, x, helper):
         # linear interpolation with linear extrapolation beyond the helper range
         y = np.interp(lam_um, x, helper)
         lo = lam_um < x[0]
         hi = lam_um > x[-1]
         y = np.where(lo, helper[0] + (lam_um - x[0]) * (helper[1] - helper[0]) / (x[1] - x[0]), y)
-        y = np.where(hi, helper[-1] + (lam_um - x[-1]) * (helper[-1] - helper[-2]) / (x[-1] - x[-2]), y)
-        return y * (lam_um / 0.55) ** self.slope
+        return np.where(hi, helper[-1] + (lam_um - x[-1]) * (helper[-1] - helper[-2]) / (x[-1] - x[-2]), y)
+
+    def components(self, lam):
+        """``(K0, D0, L2)``: curve at slope = 0, ampl = 0; bump profile per unit amplitude (both / k(0.55 um), on the
+        helper grid, interpolated -- the helper curve is linear in the amplitude); log2(lam / 0.55 um)."""
+        lam_um = strip_units(lam, "Angstrom") * 1.0e-4
+        x = np.arange(0.12, 2.2, 0.001)
+        k55 = self._k(0.55)
+        bump1 = (x * self.gamma) ** 2 / ((x**2 - self.cent_lam**2) ** 2 + (x * self.gamma) ** 2)
+        return (self._interp_extrap(lam_um, x, self._k(x) / k55), self._interp_extrap(lam_um, x, bump1 / k55),
+                np.log2(lam_um / 0.55))
+
+    def get_tau(self, lam, slope=None, ampl=None):
+        """tau(lam)/tau_V for the global parameters, or for explicit ``slope`` / ``ampl`` scalars."""
+        lam_um = strip_units(lam, "Angstrom") * 1.0e-4
+        slope = self.slope if slope is None else float(slope)
+        ampl = self.ampl if ampl is None else float(ampl)
+        x = np.arange(0.12, 2.2, 0.001)
+        k = self._k(x)
+        bump = ampl * (x * self.gamma) ** 2 / ((x**2 - self.cent_lam**2) ** 2 + (x * self.gamma) ** 2)
+        helper = (k + bump) / self._k(0.55)
+        return self._interp_extrap(lam_um, x, helper) * (lam_um / 0.55) ** slope
 
 
 # --------------------------------------------------------------------------

@@ -347,3 +347,35 @@ def test_unusable_redshifts_give_nan_rows_not_faults(engines):
     assert np.isnan(got[bad]).all()
     ok = np.setdiff1d(np.arange(300), bad)
     assert np.array_equal(got[ok], good[ok])
+
+
+@pytest.mark.parametrize("key", ["emergent", "attenuated"])
+def test_per_galaxy_dust_slope_and_bump(key):
+    """Calzetti2000(slope="slope", ampl="dust_bump_amplitude") (final_library_generation_multinode.py:496): every galaxy has
+    its own attenuation-curve shape; one- and two-component recipes, against the oracle's per-galaxy curve."""
+    from synference_b200.parametric import Calzetti2000, PacmanEmission
+    n = 160
+    w = make_workload("cfg2", n)
+    em = PacmanEmission(grid=w.grid, fesc=0.15, fesc_ly_alpha=0.5, dust_curve=Calzetti2000(slope="slope", ampl="dust_bump_amplitude"))
+    rng = np.random.default_rng(8)
+    slope, ampl = rng.uniform(-1.0, 0.4, n), rng.uniform(0.0, 5.0, n)
+    slope[:2], ampl[:2] = 0.0, 0.0
+    eng = SynthEngine(w.grid, em, key, w.filters, max_batch=4096)
+    p = w.params.slice(slice(0, n))
+    p.dust_slope, p.dust_ampl = slope, ampl
+    got = eng.photometry(p, scaled=False)
+    gals = A.galaxies_from_params(p)
+    for g, sl, am in zip(gals, slope, ampl):
+        g["dust_slope"], g["dust_ampl"] = float(sl), float(am)
+    lam = np.asarray(w.grid.lam)
+    want = O.synthesize(gals, w.grid.log10ages, w.grid.metallicity, lam, w.grid.spectra, [(f.lam, f.t) for f in w.filters],
+                        key=key, fesc=0.15, fesc_ly_alpha=0.5, dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA))
+    assert_flux_close(got, want)
+    # the first two galaxies have slope = ampl = 0: identical to the plain Calzetti model
+    plain = SynthEngine(w.grid, PacmanEmission(grid=w.grid, fesc=0.15, fesc_ly_alpha=0.5, dust_curve=Calzetti2000()), key,
+                        w.filters, max_batch=4096)
+    q = w.params.slice(slice(0, 2))
+    np.testing.assert_allclose(got[:2], plain.photometry(q, scaled=False), rtol=2e-6)
+    with pytest.raises(ValueError):
+        plain.photometry(p, scaled=False)          # per-galaxy values need a curve built with named parameters
+    eng.close(); plain.close()
