@@ -440,11 +440,11 @@ namespace {
 // One spectral component: chunks of 160 columns and three TMEM accumulators (unless SB2_N256 asks for the two-accumulator form)
 bool use_n160(const sb2_model* m) { return m->d.n_comp == 1 && !std::getenv("SB2_N256"); }
 
-template <int C, int NF, bool SPEC>
+template <int C, int NF, bool SPEC, bool PG>
 int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
   if constexpr (C == 1) {
     if (use_n160(m)) {
-      auto k = sb2::synth_kernel<C, NF, SPEC, 160>;
+      auto k = sb2::synth_kernel<C, NF, SPEC, 160, PG>;
       sb2::SynthArgs a2 = a;
       size_t bytes = m->smem160_bytes;
       if (SPEC && bytes + sb2::kSpecSmemBytes <= m->smem_optin) {   // room for the spectra transpose tiles
@@ -458,7 +458,7 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
       return SB2_OK;
     }
   }
-  auto k = sb2::synth_kernel<C, NF, SPEC, sb2::kBN>;
+  auto k = sb2::synth_kernel<C, NF, SPEC, sb2::kBN, PG>;
   CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes));
   k<<<grid, sb2::kSynthThreads, m->smem_bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo,
                                                      m->tm_g_hi, m->tm_g_lo, a);
@@ -503,7 +503,10 @@ int launch_synth2(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t 
 int launch_synth(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
   const int nf = m->d.n_filt, c = m->d.n_comp;
   const bool spec = a.out_spec != nullptr;
-#define SB2_PICK(C, NF) (spec ? launch_synth_t<C, NF, true>(m, a, grid, delta, st) : launch_synth_t<C, NF, false>(m, a, grid, delta, st))
+  const bool pg = a.dust_d0 != nullptr;   // per-galaxy dust-curve shape: its own instantiation
+#define SB2_PICK(C, NF)                                                                                             \
+  (pg ? (spec ? launch_synth_t<C, NF, true, true>(m, a, grid, delta, st) : launch_synth_t<C, NF, false, true>(m, a, grid, delta, st)) \
+      : (spec ? launch_synth_t<C, NF, true, false>(m, a, grid, delta, st) : launch_synth_t<C, NF, false, false>(m, a, grid, delta, st)))
   if (c == 1) {
     if (nf <= 8) return SB2_PICK(1, 8);
     if (nf <= 24) return SB2_PICK(1, 24);
@@ -564,7 +567,7 @@ int check_params(const sb2_model* m, const sb2_params* p) {
 int rows_per_unit(const sb2_model* m, bool delta) {
   // The CTA-pair kernel (synth2_kernel) is parity-tested but not yet faster than the single-CTA kernel on B200
   // (both sit on the same synchronisation/epilogue floor); it is opt-in: SB2_CTA_PAIR=1.
-  return (delta && m->smem2_bytes > 0 && std::getenv("SB2_CTA_PAIR")) ? 256 : 128;
+  return (delta && m->smem2_bytes > 0 && !m->dust_d0 && std::getenv("SB2_CTA_PAIR")) ? 256 : 128;
 }
 // Rows the grouped layout of a batch of n galaxies can occupy (every group is padded to whole units).
 long long padded_rows(const sb2_model* m, long long n, bool delta) {
@@ -630,14 +633,18 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
     F.tail_tab = reinterpret_cast<const double2*>(m->fm_tail);
     F.tail_w = m->d.fm_tail_w; F.tail_inv_w = 1.0 / m->d.fm_tail_w; F.tail_n = m->d.fm_tail_n;
   }
+  const bool dpl = p->sfh_type == SB2_SFH_DOUBLE_POWERLAW;
   if (M.n_age <= 64 && M.n_z <= 64 && !std::getenv("SB2_WEIGHTS_V1")) {   // half-warp per galaxy
     const unsigned blocks2 = (unsigned)((n_pad + sb2::kW2Gal - 1) / sb2::kW2Gal);
-    if (fast) sb2::weights2_kernel<true><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
-    else sb2::weights2_kernel<false><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+    if (dpl) sb2::weights2_kernel<false, true><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+    else if (fast) sb2::weights2_kernel<true, false><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+    else sb2::weights2_kernel<false, false><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+  } else if (dpl) {
+    sb2::weights_kernel<false, true><<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, F, P, O, perm, n_pad);
   } else if (fast) {
-    sb2::weights_kernel<true><<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, F, P, O, perm, n_pad);
+    sb2::weights_kernel<true, false><<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, F, P, O, perm, n_pad);
   } else {
-    sb2::weights_kernel<false><<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, F, P, O, perm, n_pad);
+    sb2::weights_kernel<false, false><<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, F, P, O, perm, n_pad);
   }
   STAGE_CHECK("weights_kernel", st);
   if (M.igm_on && !w_f64) {

@@ -267,11 +267,13 @@ __device__ __noinline__ double dpl_bin_mass(const double* __restrict__ p, double
   return acc * half;
 }
 
+// kDpl: the DoublePowerLaw quadrature is an out-of-line call; kernels for the other families are compiled without it (its
+// mere presence cost the half-warp weight builder 12 %)
+template <bool kDpl>
 __device__ __forceinline__ double sfh_mass_from_edges(int type, const double* __restrict__ p, EdgeVal lo, EdgeVal hi) {
   const double s2pi = 2.50662827463100050242;
+  if constexpr (kDpl) return dpl_bin_mass(p, lo.a, hi.a);
   switch (type) {
-    case SB2_SFH_DOUBLE_POWERLAW:
-      return dpl_bin_mass(p, lo.a, hi.a);
     case SB2_SFH_GAUSSIAN:
       return p[1] * s2pi * phi_between(lo, hi);
     case SB2_SFH_LOGNORMAL:
@@ -348,7 +350,7 @@ __host__ __device__ inline size_t weights_smem_doubles(int n_age, int n_z) {
   return (size_t)kWGal * (3 * (size_t)n_age + n_z + SB2_SFH_ROW + kGConst + 8);
 }
 
-template <bool kFast>
+template <bool kFast, bool kDpl>
 __global__ void __launch_bounds__(kWGal * kWSlots)
 weights_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __restrict__ perm, long long n_pad) {
   extern __shared__ double prep_smem[];
@@ -415,7 +417,7 @@ weights_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __re
   if (valid)
     for (int a = slot; a < M.n_age; a += kWSlots) {
       double mass = 0.0;
-      if (a < M.n_age - 1) mass = sfh_mass_from_edges(P.sfh_type, p, EdgeVal{eA[a], eB[a]}, EdgeVal{eA[a + 1], eB[a + 1]});
+      if (a < M.n_age - 1) mass = sfh_mass_from_edges<kDpl>(P.sfh_type, p, EdgeVal{eA[a], eB[a]}, EdgeVal{eA[a + 1], eB[a + 1]});
       sf[a] = mass;
       part += mass;
     }
@@ -500,7 +502,7 @@ constexpr int kW2Smem = 64 + 64 + SB2_SFH_ROW + kGConst;   // doubles per galaxy
 __device__ __forceinline__ double shfl_down16(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d, 16); }
 __device__ __forceinline__ double shfl_xor16(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 16); }
 
-template <bool kFast>
+template <bool kFast, bool kDpl>
 __global__ void __launch_bounds__(kW2Gal * 16)
 weights2_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __restrict__ perm, long long n_pad) {
   __shared__ double sm[kW2Gal * kW2Smem];
@@ -558,7 +560,7 @@ weights2_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __r
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int a = 4 * hl + q;
-    const double mass = (a < M.n_age - 1) ? sfh_mass_from_edges(P.sfh_type, p, ev[q], ev[q + 1]) : 0.0;
+    const double mass = (a < M.n_age - 1) ? sfh_mass_from_edges<kDpl>(P.sfh_type, p, ev[q], ev[q + 1]) : 0.0;
     sf[a] = mass;
     part += mass;
   }

@@ -139,7 +139,7 @@ __device__ __forceinline__ int chunk_rot(int n_c, unsigned who) { return n_c > 0
 // "Accumulator ready" barriers are PER GROUP (tfull_bar[kTfPerGroup g + k % kTfPerGroup] for the group's k-th chunk): an mbarrier
 // wait only carries one parity bit, so a waiter must see every phase of a barrier in order -- which a group does
 // for its own pair, but would not for per-buffer barriers that other groups also consume.
-template <int kComp, int kNF, bool kSpec, int kCta, int kN, int kGroups>
+template <int kComp, int kNF, bool kSpec, int kCta, int kN, int kGroups, bool kPgDust>
 __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* s_uv, float* s_spec, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tempty_addr, uint32_t tmem_base, int unit0, int unit_stride,
                                               int n_units, uint32_t cta_rank) {
@@ -165,7 +165,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
       const int orig = A.g_orig[row];
       int m = A.g_m[row];
       const float ntaut = -A.g_taut[row];
-      const bool pg_dust = A.dust_d0 != nullptr;                // warp-uniform
+      constexpr bool pg_dust = kPgDust;   // compile-time: a run-time test here cost 10 % of the kernel (register pressure)
       const float slope = pg_dust ? A.g_slope[row] : 0.f, ampl = pg_dust ? A.g_ampl[row] : 0.f;
       // redshift-shift range of this warp's real galaxies (padding rows follow the others)
       int mmin = orig >= 0 ? m : INT_MAX, mmax = orig >= 0 ? m : INT_MIN;
@@ -340,7 +340,7 @@ struct SynthCfg {
   static constexpr int kBufN = 512 / kN;
 };
 
-template <int kComp, int kNF, bool kSpec, int kN>
+template <int kComp, int kNF, bool kSpec, int kN, bool kPgDust>
 __global__ void __launch_bounds__(kSynthThreads, 1)
 synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
              const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo,
@@ -479,7 +479,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
     }
   } else if (warp >= kEpiWarp0) {
     float* s_spec = (kSpec && A.spec_smem) ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes) : nullptr;
-    epilogue_loop<kComp, kNF, kSpec, 1, kN, 2>(A, s_uv, s_spec, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
+    epilogue_loop<kComp, kNF, kSpec, 1, kN, 2, kPgDust>(A, s_uv, s_spec, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
   }
 
   tc_fence_before();
@@ -665,7 +665,7 @@ synth2_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant
       }
     }
   } else if (warp >= kEpiWarp0) {
-    epilogue_loop<kComp, kNF, kSpec, 2, kBN2, (kT2Buf >= 3 && kMaxGroups >= 3 ? 3 : 2)>(A, s_uv, nullptr, tfull_bar, tempty_bar, mapa_u32(smem_u32(tempty_bar), 0), tmem_base, unit0,
+    epilogue_loop<kComp, kNF, kSpec, 2, kBN2, (kT2Buf >= 3 && kMaxGroups >= 3 ? 3 : 2), false>(A, s_uv, nullptr, tfull_bar, tempty_bar, mapa_u32(smem_u32(tempty_bar), 0), tmem_base, unit0,
                                         unit_stride, n_units, rank);
   }
 
