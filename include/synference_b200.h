@@ -98,6 +98,12 @@ typedef struct sb2_model_desc {
    * dust_l2 = log2(lambda / 0.55 um) on the same padded axis as kappa.  NULL: the curve is global (kappa only).   */
   const float* dust_d0;
   const float* dust_l2;
+  /* Optional per-galaxy Lyman-alpha escape fraction (fesc_ly_alpha="fesc_lya" in the reference's production script): the
+   * grids are then lowered WITHOUT the line-continuum value of the one bin nearest 1216 A (lya_bin), lya_line[iz*n_age+ia]
+   * holds that value (internal units, times (1 - fesc) when fesc is global), and the kernel adds
+   * fesc_lya_g * sum_k w_k lya_line[k] to the first component at that bin.  NULL: fesc_ly_alpha is global.          */
+  const double* lya_line;
+  int32_t lya_bin;
   const double* fm_log_tab;
   const double* fm_exp_tab;
   const double* fm_tail_tab;
@@ -128,6 +134,7 @@ typedef struct sb2_params {
   const double* coef_unatt; /* [n] optional per-galaxy factor on the unattenuated component */
   const double* dust_slope; /* [n] per-galaxy power-law slope delta of the dust curve (requires dust_d0/dust_l2)  */
   const double* dust_ampl;  /* [n] per-galaxy UV-bump amplitude                       (requires dust_d0/dust_l2)  */
+  const double* fesc_lya;   /* [n] per-galaxy Lyman-alpha escape fraction             (requires lya_line)         */
 } sb2_params;
 
 typedef struct sb2_model sb2_model;

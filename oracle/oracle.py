@@ -352,7 +352,8 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
 
     galaxies : list of dicts with redshift, tau_v, sfh_kind, sfh (dict, ages in yr),
                zd_kind, zd_value, zd_sigma and optionally fesc (per-galaxy escape fraction: the emission tree
-               of SURVEY A5 is then evaluated with that galaxy's value instead of the global ``fesc``) and
+               of SURVEY A5 is then evaluated with that galaxy's value instead of the global ``fesc``; likewise
+               fesc_ly_alpha) and
                dust_slope / dust_ampl (per-galaxy shape of the attenuation curve)
     filters  : list of (lam_table [A], transmission) on each filter's own axis
     dust     : None or dict(curve=..., slope=..., ampl=...)  ;  igm : None or (laf, dla)
@@ -366,8 +367,9 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
     spectra = np.zeros((len(galaxies), len(lam))) if return_spectra else None
     for g, gal in enumerate(galaxies):
         w = weights_for(gal, log10ages, metallicities).reshape(-1)
-        if "fesc" in gal:
-            ga, gu = emission_parts(components, lam, key, float(gal["fesc"]), fesc_ly_alpha)
+        if "fesc" in gal or "fesc_ly_alpha" in gal:
+            ga, gu = emission_parts(components, lam, key, float(gal.get("fesc", fesc)),
+                                    float(gal.get("fesc_ly_alpha", fesc_ly_alpha)))
             g_att2, g_un2 = ga.reshape(na * nz, -1), gu.reshape(na * nz, -1)
         lnu = w @ g_un2  # A4: grid-weighted sum, erg/s/Hz per Msun
         att = w @ g_att2

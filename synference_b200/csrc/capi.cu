@@ -164,6 +164,8 @@ struct sb2_model {
   double *ages = nullptr, *edges = nullptr, *zmet = nullptr, *log10zmet = nullptr;
   float *gt_hi = nullptr, *gt_lo = nullptr, *kappa = nullptr, *filt_uv = nullptr;
   float *dust_d0 = nullptr, *dust_l2 = nullptr, *g_slope = nullptr, *g_ampl = nullptr;   // per-galaxy dust shape (optional)
+  double* lya_line = nullptr;   // per-galaxy Lyman-alpha escape (optional)
+  float* g_lya = nullptr;
   int *filt_lo = nullptr, *filt_hi = nullptr;
   double *bin_pow = nullptr, *thr = nullptr, *pre = nullptr;
   int *nline = nullptr, *lc_on = nullptr;
@@ -235,7 +237,7 @@ int sb2_device_count(void) {
 int sb2_model_destroy(sb2_model* m) {
   if (!m) return SB2_OK;
   cudaSetDevice(m->device);
-  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->dust_d0, m->dust_l2, m->g_slope, m->g_ampl, m->filt_uv, m->filt_lo,
+  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->dust_d0, m->dust_l2, m->g_slope, m->g_ampl, m->lya_line, m->g_lya, m->filt_uv, m->filt_lo,
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage, m->fm_log, m->fm_exp, m->fm_tail,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
                   m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params[0],
@@ -349,6 +351,10 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   UP(ddc, d->cosmo_ddc, d->cosmo_n + 1);
   UP(age, d->cosmo_age, d->cosmo_n + 1);
   UP(dage, d->cosmo_dage, d->cosmo_n + 1);
+  if (d->lya_line) {
+    if (d->lya_bin < 0 || d->lya_bin >= d->n_lam) { sb2_model_destroy(m); return fail(SB2_ERR_INVALID, "lya_bin out of range"); }
+    UP(lya_line, d->lya_line, (size_t)d->n_age * d->n_z);
+  }
   if (d->fm_log_tab && d->fm_exp_tab && d->fm_tail_tab && d->fm_tail_n > 0 && d->fm_tail_w > 0.0) {
     UP(fm_log, d->fm_log_tab, 512);
     UP(fm_exp, d->fm_exp_tab, 64);
@@ -371,6 +377,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(part, (size_t)sb2::kMaxGroups * d->n_filt * np * sizeof(float2));
   AL(g_m, np * 4); AL(g_orig, np * 4); AL(perm, np * 4); AL(idx, np * 4);
   if (m->dust_d0) { AL(g_slope, np * 4); AL(g_ampl, np * 4); }
+  if (m->lya_line) { AL(g_lya, np * 4); }
   AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
   AL(keys, np * 4); AL(keys_sorted, np * 4); AL(perm_pad, np * 4); AL(tile_k0, (np / 128) * 4); AL(grp, (3 * kMaxGroups + 1) * 4);
   AL(g_mscale, np * 8); AL(g_trunc, np * 4); AL(zpow, np * 13 * 8);
@@ -378,7 +385,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)m->cap);
   AL(cub_tmp, m->cub_bytes + 16);
   for (int sl = 0; sl < 2; ++sl) {
-    AL(stage_params[sl], (size_t)m->cap * (9 + SB2_SFH_ROW) * 8);
+    AL(stage_params[sl], (size_t)m->cap * (10 + SB2_SFH_ROW) * 8);
     AL(stage_flux[sl], (size_t)m->cap * d->n_filt * 4);
     AL(stage_flux64[sl], (size_t)m->cap * d->n_filt * 8);
   }
@@ -503,7 +510,7 @@ int launch_synth2(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t 
 int launch_synth(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
   const int nf = m->d.n_filt, c = m->d.n_comp;
   const bool spec = a.out_spec != nullptr;
-  const bool pg = a.dust_d0 != nullptr;   // per-galaxy dust-curve shape: its own instantiation
+  const bool pg = a.dust_d0 != nullptr || a.g_lya != nullptr;   // per-galaxy emission extras: their own instantiation
 #define SB2_PICK(C, NF)                                                                                             \
   (pg ? (spec ? launch_synth_t<C, NF, true, true>(m, a, grid, delta, st) : launch_synth_t<C, NF, false, true>(m, a, grid, delta, st)) \
       : (spec ? launch_synth_t<C, NF, true, false>(m, a, grid, delta, st) : launch_synth_t<C, NF, false, false>(m, a, grid, delta, st)))
@@ -533,7 +540,7 @@ sb2::PrepModel prep_model(const sb2_model* m) {
   M.filt_lo = m->filt_lo; M.filt_hi = m->filt_hi;
   M.bin_pow = m->bin_pow; M.nline = m->nline; M.lc_on = m->lc_on; M.thr = m->thr; M.pre = m->pre;
   M.cosmo_n = d.cosmo_n; M.cosmo_ds = d.cosmo_smax / d.cosmo_n;
-  M.dc = m->dc; M.ddc = m->ddc; M.age = m->age; M.dage = m->dage;
+  M.dc = m->dc; M.ddc = m->ddc; M.age = m->age; M.dage = m->dage; M.lya_line = m->lya_line;
   return M;
 }
 
@@ -543,7 +550,7 @@ sb2::PrepParams prep_params(const sb2_params* p) {
   P.sfh_type = p->sfh_type; P.sfh_stride = p->sfh_stride; P.sfh_rows = p->sfh_rows;
   P.max_age_from_z = p->max_age_from_z; P.norm_mask = p->norm_mask; P.age_zmax_gyr = p->age_zmax_gyr;
   P.zd_type = p->zd_type; P.zd_value = p->zd_value; P.zd_sigma = p->zd_sigma;
-  P.coef_att = p->coef_att; P.coef_unatt = p->coef_unatt; P.dust_slope = p->dust_slope; P.dust_ampl = p->dust_ampl;
+  P.coef_att = p->coef_att; P.coef_unatt = p->coef_unatt; P.dust_slope = p->dust_slope; P.dust_ampl = p->dust_ampl; P.fesc_lya = p->fesc_lya;
   return P;
 }
 
@@ -559,6 +566,9 @@ int check_params(const sb2_model* m, const sb2_params* p) {
   if (p->zd_type >= SB2_ZD_NORMAL_LINEAR && !p->zd_sigma) return fail(SB2_ERR_INVALID, "zd_sigma required for Normal");
   if ((p->dust_slope || p->dust_ampl) && !m->dust_d0)
     return fail(SB2_ERR_INVALID, "per-galaxy dust_slope / dust_ampl need a model created with dust_d0 and dust_l2");
+  if (p->fesc_lya && !m->lya_line) return fail(SB2_ERR_INVALID, "per-galaxy fesc_lya needs a model created with lya_line");
+  if (m->lya_line && !p->fesc_lya) return fail(SB2_ERR_INVALID, "this model reads fesc_lya per galaxy: params.fesc_lya is required");
+  if (p->fesc_lya && (m->d.n_age > 64 || m->d.n_z > 64)) return fail(SB2_ERR_INVALID, "per-galaxy fesc_lya supports n_age, n_z <= 64");
   return SB2_OK;
 }
 
@@ -567,7 +577,7 @@ int check_params(const sb2_model* m, const sb2_params* p) {
 int rows_per_unit(const sb2_model* m, bool delta) {
   // The CTA-pair kernel (synth2_kernel) is parity-tested but not yet faster than the single-CTA kernel on B200
   // (both sit on the same synchronisation/epilogue floor); it is opt-in: SB2_CTA_PAIR=1.
-  return (delta && m->smem2_bytes > 0 && !m->dust_d0 && std::getenv("SB2_CTA_PAIR")) ? 256 : 128;
+  return (delta && m->smem2_bytes > 0 && !m->dust_d0 && !m->lya_line && std::getenv("SB2_CTA_PAIR")) ? 256 : 128;
 }
 // Rows the grouped layout of a batch of n galaxies can occupy (every group is padded to whole units).
 long long padded_rows(const sb2_model* m, long long n, bool delta) {
@@ -611,7 +621,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   sb2::PrepOut O{};
   O.w_hi = m->w_hi; O.w_lo = m->w_lo; O.w_f64 = w_f64; O.igm = m->igm; O.g_m = m->g_m; O.g_beta = m->g_beta; O.g_gamma = m->g_gamma;
   O.g_taut = m->g_taut; O.g_scale = m->g_scale; O.g_ca = m->g_ca; O.g_cb = m->g_cb; O.g_orig = m->g_orig;
-  O.g_slope = m->g_slope; O.g_ampl = m->g_ampl;
+  O.g_slope = m->g_slope; O.g_ampl = m->g_ampl; O.g_lya = m->g_lya;
   O.g_mscale = m->g_mscale; O.g_trunc = m->g_trunc; O.zpow = m->zpow;
   if (!w_f64) {  // the parity hook (sb2_build_weights) needs the weights only
     sb2::scalars_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(M, P, O, perm, n_pad);
@@ -636,9 +646,13 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   const bool dpl = p->sfh_type == SB2_SFH_DOUBLE_POWERLAW;
   if (M.n_age <= 64 && M.n_z <= 64 && !std::getenv("SB2_WEIGHTS_V1")) {   // half-warp per galaxy
     const unsigned blocks2 = (unsigned)((n_pad + sb2::kW2Gal - 1) / sb2::kW2Gal);
-    if (dpl) sb2::weights2_kernel<false, true><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
-    else if (fast) sb2::weights2_kernel<true, false><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
-    else sb2::weights2_kernel<false, false><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+    const bool lya = p->fesc_lya != nullptr && !w_f64;
+    if (dpl && lya) sb2::weights2_kernel<false, true, true><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+    else if (dpl) sb2::weights2_kernel<false, true, false><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+    else if (fast && lya) sb2::weights2_kernel<true, false, true><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+    else if (fast) sb2::weights2_kernel<true, false, false><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+    else if (lya) sb2::weights2_kernel<false, false, true><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
+    else sb2::weights2_kernel<false, false, false><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
   } else if (dpl) {
     sb2::weights_kernel<false, true><<<blocks, sb2::kWGal * sb2::kWSlots, sh, st>>>(M, F, P, O, perm, n_pad);
   } else if (fast) {
@@ -692,6 +706,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.n_blue = d.n_blue; a.n_blue_pad = m->n_blue_pad; a.uv_len = m->uv_len;
   a.tile_range = m->tile_range;
   a.dust_d0 = m->dust_d0; a.dust_l2 = m->dust_l2; a.g_slope = m->g_slope; a.g_ampl = m->g_ampl;
+  a.g_lya = m->g_lya; a.lya_bin = d.lya_bin;
   a.kappa = m->kappa; a.filt_uv = reinterpret_cast<const float2*>(m->filt_uv); a.igm = m->igm;
   a.g_m = m->g_m; a.g_beta = m->g_beta; a.g_gamma = m->g_gamma; a.g_taut = m->g_taut; a.g_scale = m->g_scale; a.g_ca = m->g_ca;
   a.g_cb = m->g_cb; a.g_orig = m->g_orig; a.g_mscale = m->g_mscale; a.g_trunc = m->g_trunc;
@@ -766,9 +781,9 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
   // copied in on st_h2d, synthesised on st_comp and copied out on st_d2h, so the PCIe copies of one slice
   // overlap the kernels of its neighbours (pinned host buffers are needed for the overlap, not for correctness).
   double* base = m->stage_params[slot];
-  constexpr int kNA = 10;   // staged arrays; the last one is the SFH row table
+  constexpr int kNA = 11;   // staged arrays; the last one is the SFH row table
   const double* src[kNA] = {p->redshift, p->log_mass, p->tau_v, p->zd_value, p->zd_sigma, p->coef_att, p->coef_unatt,
-                            p->dust_slope, p->dust_ampl, p->sfh_rows};
+                            p->dust_slope, p->dust_ampl, p->fesc_lya, p->sfh_rows};
   double* dev[kNA];
   for (int i = 0; i < kNA; ++i) {
     const size_t w = (i == kNA - 1) ? (size_t)p->sfh_stride : 1;
@@ -810,7 +825,8 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
     dp.zd_value = dev[3] + a; dp.zd_sigma = dev[4] ? dev[4] + a : nullptr;
     dp.coef_att = dev[5] ? dev[5] + a : nullptr; dp.coef_unatt = dev[6] ? dev[6] + a : nullptr;
     dp.dust_slope = dev[7] ? dev[7] + a : nullptr; dp.dust_ampl = dev[8] ? dev[8] + a : nullptr;
-    dp.sfh_rows = dev[9] + a * p->sfh_stride;
+    dp.fesc_lya = dev[9] ? dev[9] + a : nullptr;
+    dp.sfh_rows = dev[10] + a * p->sfh_stride;
     rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux[slot] + a * nf : nullptr,
                               flux_scaled ? m->stage_flux64[slot] + a * nf : nullptr, nullptr, m->st_comp);
     if (rc != SB2_OK) return rc;

@@ -40,6 +40,7 @@ struct PrepModel {
   const double* ddc;
   const double* age;
   const double* dage;
+  const double* lya_line;  // [n_z][n_age] line-continuum value of the Lyman-alpha bin (optional)
 };
 
 // Table-driven float64 log / exp / normal tail for weights_kernel (tables: synference_b200/fastmath.py, which also
@@ -120,6 +121,7 @@ struct PrepParams {  // device pointers (sb2_params with device arrays)
   const double* coef_unatt;
   const double* dust_slope;
   const double* dust_ampl;
+  const double* fesc_lya;
 };
 
 struct PrepOut {
@@ -137,6 +139,7 @@ struct PrepOut {
   float* g_cb;      // [n_pad]
   float* g_slope;   // [n_pad] per-galaxy dust slope / bump amplitude (nullptr: global curve)
   float* g_ampl;    // [n_pad]
+  float* g_lya;     // [n_pad] fesc_lya_g * sum_k w_k lya_line[k] (nullptr: global Lyman-alpha escape fraction)
   int* g_orig;      // [n_pad]  original index, -1 for padding rows
   double* g_mscale; // [n_pad]
   unsigned* g_trunc;// [n_pad]  bit f set: filter f not fully covered by the grid at this z
@@ -502,7 +505,7 @@ constexpr int kW2Smem = 64 + 64 + SB2_SFH_ROW + kGConst;   // doubles per galaxy
 __device__ __forceinline__ double shfl_down16(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d, 16); }
 __device__ __forceinline__ double shfl_xor16(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 16); }
 
-template <bool kFast, bool kDpl>
+template <bool kFast, bool kDpl, bool kLya>
 __global__ void __launch_bounds__(kW2Gal * 16)
 weights2_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __restrict__ perm, long long n_pad) {
   __shared__ double sm[kW2Gal * kW2Smem];
@@ -591,6 +594,28 @@ weights2_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __r
     zinv = 1.0 / zpart;
   }
   __syncwarp();
+  if constexpr (kLya) {
+    // per-galaxy Lyman-alpha line: the weighted sum of the line-continuum value of that one bin (a dot product over the
+    // (age, Z) cells), times this galaxy's escape fraction; the contraction kernel adds it at the Lyman-alpha bin
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int a = 4 * hl + q;
+      if (a < M.n_age) {
+        double lz;
+        if (zdelta) {
+          lz = (1.0 - zf) * M.lya_line[zj * M.n_age + a] + (M.n_z >= 2 ? zf * M.lya_line[(zj + 1) * M.n_age + a] : 0.0);
+        } else {
+          lz = 0.0;
+          for (int iz = 0; iz < M.n_z; ++iz) lz += zd[iz] * zinv * M.lya_line[iz * M.n_age + a];
+        }
+        acc += sf[a] * lz;
+      }
+    }
+#pragma unroll
+    for (int o = 8; o; o >>= 1) acc += shfl_xor16(acc, o);
+    if (hl == 0 && in_range) O.g_lya[t] = valid ? (float)(P.fesc_lya[gs] * acc * inv_sf) : 0.f;
+  }
   if (!in_range) return;
 
   // ---- weights row (TF32 hi/lo split)

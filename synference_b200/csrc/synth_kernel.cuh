@@ -77,6 +77,8 @@ struct SynthArgs {
   const float* dust_l2;
   const float* g_slope;
   const float* g_ampl;
+  const float* g_lya;        // per-galaxy Lyman-alpha line term, added to the first component at bin lya_bin; nullptr: none
+  int lya_bin;
   const float2* filt_uv;     // padded tables, uv_len entries
   const float* igm;          // [n_tiles][n_blue_pad][128]
   const int* g_m;
@@ -166,7 +168,10 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
       int m = A.g_m[row];
       const float ntaut = -A.g_taut[row];
       constexpr bool pg_dust = kPgDust;   // compile-time: a run-time test here cost 10 % of the kernel (register pressure)
-      const float slope = pg_dust ? A.g_slope[row] : 0.f, ampl = pg_dust ? A.g_ampl[row] : 0.f;
+      // (kPgDust instantiations carry all per-galaxy emission extras: dust-curve shape and/or the Lyman-alpha line)
+      const bool dust_pg = pg_dust && A.dust_d0 != nullptr;
+      const float slope = dust_pg ? A.g_slope[row] : 0.f, ampl = dust_pg ? A.g_ampl[row] : 0.f;
+      const float lya = (pg_dust && A.g_lya != nullptr) ? A.g_lya[row] : 0.f;
       // redshift-shift range of this warp's real galaxies (padding rows follow the others)
       int mmin = orig >= 0 ? m : INT_MAX, mmax = orig >= 0 ? m : INT_MIN;
 #pragma unroll
@@ -215,10 +220,15 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               uint32_t u[32];
               tmem_ld_32x32b_x32(t_acc + kLch + sub * 32, u);
               tmem_ld_wait();
+              if (pg_dust && A.g_lya != nullptr && A.lya_bin >= i0 && A.lya_bin < i0 + 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (i0 + j == A.lya_bin) v[j] = __float_as_uint(__uint_as_float(v[j]) + lya);
+              }
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 float4 k4 = __ldg(kp + j4);
-                if (pg_dust) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
+                if (pg_dust && dust_pg) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
                                              __ldg(reinterpret_cast<const float4*>(A.dust_l2 + i0) + j4), slope, ampl);
                 s[4 * j4 + 0] = ca * (__uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x)) + cb * __uint_as_float(u[4 * j4 + 0]);
                 s[4 * j4 + 1] = ca * (__uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y)) + cb * __uint_as_float(u[4 * j4 + 1]);
@@ -227,6 +237,11 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               }
             } else {
               tmem_ld_wait();
+              if (pg_dust && A.g_lya != nullptr && A.lya_bin >= i0 && A.lya_bin < i0 + 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (i0 + j == A.lya_bin) v[j] = __float_as_uint(__uint_as_float(v[j]) + lya);
+              }
               if (SB2_DBG_BITS(A) & 2) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
@@ -234,7 +249,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {  // ca goes into the final scale
                 float4 k4 = __ldg(kp + j4);
-                if (pg_dust) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
+                if (pg_dust && dust_pg) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
                                              __ldg(reinterpret_cast<const float4*>(A.dust_l2 + i0) + j4), slope, ampl);
                 s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x);
                 s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y);

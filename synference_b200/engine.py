@@ -51,6 +51,7 @@ class GalaxyParams:
     coef_unatt: Optional[np.ndarray] = None
     dust_slope: Optional[np.ndarray] = None     # per-galaxy dust-curve slope / bump amplitude (models built with
     dust_ampl: Optional[np.ndarray] = None      # Calzetti2000(slope="...", ampl="..."))
+    fesc_lya: Optional[np.ndarray] = None       # per-galaxy Lyman-alpha escape fraction (fesc_ly_alpha="<name>" models)
     max_age_from_z: bool = False
     norm_mask: int = 0
     age_zmax_gyr: float = 0.0
@@ -78,7 +79,7 @@ class GalaxyParams:
         g = lambda a: None if a is None else a[sl]  # noqa: E731
         return GalaxyParams(self.redshift[sl], self.sfh_type, self.sfh_rows[sl], self.zd_type,
                             self.zd_value[sl], g(self.zd_sigma), g(self.log_mass), g(self.tau_v),
-                            g(self.coef_att), g(self.coef_unatt), g(self.dust_slope), g(self.dust_ampl),
+                            g(self.coef_att), g(self.coef_unatt), g(self.dust_slope), g(self.dust_ampl), g(self.fesc_lya),
                             self.max_age_from_z, self.norm_mask, self.age_zmax_gyr)
 
 
@@ -189,6 +190,15 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         # travels as coef_att (SynthEngine._fill)
         single_is_unatt=(n_comp == 1 and not has_att),
     )
+    lya = getattr(emission_model, "lya_line", lambda k: None)(emission_key)
+    if lya is not None:
+        # the line sits in the first grid of every recipe, i.e. in the kernel's component A, except when that grid is
+        # all zero and the lone component is the second one -- also component A
+        vals, lya_bin = lya
+        tables["lya_line"] = np.ascontiguousarray(np.asarray(vals, dtype=np.float64).T / grid_scale)   # [iz][ia]
+        tables["lya_bin"] = int(lya_bin)
+    else:
+        tables["lya_line"], tables["lya_bin"] = None, 0
     if igm:
         laf, dla = (igm if isinstance(igm, tuple) else (_igm.INOUE14_LAF, _igm.INOUE14_DLA))
         tables["igm"] = _igm.device_tables(lam, laf, dla)
@@ -234,6 +244,7 @@ class SynthEngine:
         d.grid_scale, d.lam0, d.q = t["grid_scale"], t["lam0"], t["q"]
         d.kappa = ptr(t["kappa"], C.c_float)
         d.dust_d0, d.dust_l2 = ptr(t["dust_d0"], C.c_float), ptr(t["dust_l2"], C.c_float)
+        d.lya_line, d.lya_bin = ptr(t["lya_line"], C.c_double), int(t["lya_bin"])
         d.filt_lo, d.filt_hi = ptr(t["filt_lo"], C.c_int32), ptr(t["filt_hi"], C.c_int32)
         d.filt_off, d.filt_uv = ptr(t["filt_off"], C.c_int32), ptr(t["filt_uv"], C.c_float)
         d.filt_uv_len = int(t["filt_uv"].shape[0])
@@ -282,6 +293,12 @@ class SynthEngine:
         else:
             s.coef_att, s.coef_unatt = get_ptr(p.coef_att), get_ptr(p.coef_unatt)
         s.dust_slope, s.dust_ampl = self._dust_arrays(p, get_ptr)
+        if self.tables["lya_line"] is not None and p.fesc_lya is None:
+            raise ValueError("the emission model reads fesc_ly_alpha per galaxy: GalaxyParams.fesc_lya is required")
+        if self.tables["lya_line"] is None and p.fesc_lya is not None:
+            raise ValueError("per-galaxy fesc_lya given, but the emission model has a numeric fesc_ly_alpha (or the spectrum "
+                             "has no nebular part); build it with fesc_ly_alpha='fesc_lya'")
+        s.fesc_lya = get_ptr(p.fesc_lya)
         return s
 
     def _dust_arrays(self, p: GalaxyParams, get_ptr):
@@ -352,6 +369,7 @@ class SynthEngine:
         keep = []
         sl, am = self._dust_arrays(params, lambda a: (keep.append(np.ascontiguousarray(a, dtype=np.float64)), keep[-1])[1])
         tensors["dust_slope"], tensors["dust_ampl"] = mv(sl), mv(am)
+        tensors["fesc_lya"] = mv(params.fesc_lya)
         return DeviceParams(params, tensors)
 
     def _set_device_ptrs(self, s, tensors):
@@ -363,6 +381,7 @@ class SynthEngine:
         else:
             s.coef_att, s.coef_unatt = ptr("coef_att"), ptr("coef_unatt")
         s.dust_slope, s.dust_ampl = ptr("dust_slope"), ptr("dust_ampl")
+        s.fesc_lya = ptr("fesc_lya")
 
     def photometry_device(self, dparams: "DeviceParams", flux_base=None, flux_scaled=None, spectra=None):
         """Run one batch whose parameters are already in HBM; outputs are caller-provided torch tensors."""

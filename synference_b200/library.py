@@ -47,7 +47,7 @@ UNIT_DICT = {
 _SPECTRAL_EMITTER_PARAMS = ("tau_v", "fesc")
 # emitter parameters of the reference scripts that would change the spectrum but are not implemented
 _UNSUPPORTED_EMITTER_PARAMS = ("slope", "fesc_lya", "fesc_ly_alpha", "dust_bump_amplitude",
-                               "tau_v_ism", "tau_v_birth")
+                               "tau_v_ism", "tau_v_birth")   # ... unless the emission model / dust curve names them
 
 
 def create_galaxy(sfh, redshift, metal_dist, grid, log_stellar_masses=9, **galaxy_kwargs):
@@ -99,10 +99,11 @@ class GalaxyBasis:
                     raise NotImplementedError("black-hole / gas emitters are outside the stellar hot path")
                 self.galaxy_params[key] = self.process_priors(value)
         dust = getattr(emission_model, "dust_curve", None)
-        dust_names = {getattr(dust, "slope_name", None), getattr(dust, "ampl_name", None)} - {None}
+        dust_names = {getattr(dust, "slope_name", None), getattr(dust, "ampl_name", None),
+                      getattr(emission_model, "lya_name", None)} - {None}
         for name in dust_names:
             if name not in galaxy_params:
-                raise ValueError(f"the dust curve reads '{name}' per galaxy, but galaxy_params does not provide it")
+                raise ValueError(f"the emission model reads '{name}' per galaxy, but galaxy_params does not provide it")
         for key in galaxy_params:
             if key in _UNSUPPORTED_EMITTER_PARAMS and key not in dust_names:
                 raise NotImplementedError(
@@ -339,6 +340,10 @@ class GalaxyBasis:
                 for attr, name in (("dust_slope", getattr(dust, "slope_name", None)), ("dust_ampl", getattr(dust, "ampl_name", None))):
                     if name is not None:
                         setattr(p, attr, np.asarray(strip_units(self.all_parameters[name]), dtype=float)[sl])
+                lya_name = getattr(self.emission_model, "lya_name", None)
+                p.fesc_lya = None
+                if lya_name is not None and self.emission_model.lya_line(key) is not None:
+                    p.fesc_lya = np.asarray(strip_units(self.all_parameters[lya_name]), dtype=float)[sl]
                 flux = eng.photometry(p, scaled=False)
                 results["photometry"][key].append(flux)
                 label = self.instrument.label
@@ -852,7 +857,8 @@ class GalaxySimulator:
         fesc_name = getattr(self.emission_model, "fesc_name", None)
         dust = getattr(self.emission_model, "dust_curve", None)
         slope_name, ampl_name = getattr(dust, "slope_name", None), getattr(dust, "ampl_name", None)
-        used = [k for k in params if k not in self.total_possible_keys and k not in ("tau_v", fesc_name, slope_name, ampl_name)
+        lya_name = getattr(self.emission_model, "lya_name", None)
+        used = [k for k in params if k not in self.total_possible_keys and k not in ("tau_v", fesc_name, slope_name, ampl_name, lya_name)
                 and k not in self.ignore_params and k not in cls.param_names]
         for k in used:
             if k not in self.unused_params:
@@ -871,6 +877,10 @@ class GalaxySimulator:
                 if name not in params:
                     raise ValueError(f"Missing required parameter '{name}' (read per galaxy by the dust curve)")
                 setattr(gp, attr, np.array(bc(params[name]), dtype=float))
+        if lya_name is not None and self.emission_model.lya_line(self.emission_model_key) is not None:
+            if lya_name not in params:
+                raise ValueError(f"Missing required parameter '{lya_name}' (per-galaxy Lyman-alpha escape fraction)")
+            gp.fesc_lya = np.array(bc(params[lya_name]), dtype=float)
         return gp
 
     def simulate(self, params):

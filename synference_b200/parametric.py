@@ -655,9 +655,10 @@ class EmissionModel:
         self.saved_spectra = None
         self.fesc_per_galaxy = isinstance(fesc, str)
         self.fesc_name = fesc if self.fesc_per_galaxy else None
-        if isinstance(fesc_ly_alpha, str):
-            raise NotImplementedError(
-                "per-galaxy 'fesc_ly_alpha' (string-named emitter attribute) is not in the batched path yet")
+        # fesc_ly_alpha="fesc_lya" (final_library_generation_multinode.py:499): the line-continuum value of the ONE bin
+        # nearest 1216 A is scaled per galaxy; grids are lowered without it and lya_line() hands the kernel that value
+        self.lya_per_galaxy = isinstance(fesc_ly_alpha, str)
+        self.lya_name = fesc_ly_alpha if self.lya_per_galaxy else None
         if dust_emission is not None:
             raise NotImplementedError("dust emission / energy balance is not in the batched path yet")
 
@@ -699,11 +700,21 @@ class EmissionModel:
         a, b = self._PER_GALAXY[key]
         return pick[a], pick[b]
 
+    def lya_line(self, key):
+        """``(values (N_age, N_Z), bin)`` of the Lyman-alpha line term that a per-galaxy ``fesc_ly_alpha`` multiplies in
+        spectrum ``key`` (it always lives in the first grid of ``recipe(key)``), or ``None``."""
+        if not self.lya_per_galaxy or key in ("incident", "transmitted", "escaped"):
+            return None
+        lam = np.asarray(self.grid.lam)
+        i = int(np.argmin(np.abs(lam - LYA)))
+        scale = 1.0 if self.fesc_per_galaxy else 1.0 - float(self.fesc)
+        return scale * self._component("linecont")[..., i], i
+
     def recipe(self, key):
         if key not in self.available:
             raise ValueError(f"Emission model {type(self).__name__} has no spectrum '{key}'")
         lam = np.asarray(self.grid.lam)
-        flya = float(self.fesc_ly_alpha)
+        flya = 0.0 if self.lya_per_galaxy else float(self.fesc_ly_alpha)
         if self.fesc_per_galaxy:
             inc = self._component("incident")
             zero = np.zeros_like(inc)

@@ -379,3 +379,44 @@ def test_per_galaxy_dust_slope_and_bump(key):
     with pytest.raises(ValueError):
         plain.photometry(p, scaled=False)          # per-galaxy values need a curve built with named parameters
     eng.close(); plain.close()
+
+
+@pytest.mark.parametrize("key,per_fesc", [("emergent", False), ("emergent", True), ("reprocessed", False)])
+def test_per_galaxy_lyman_alpha_escape(key, per_fesc):
+    """fesc_ly_alpha="fesc_lya" (final_library_generation_multinode.py:499): the Lyman-alpha line bin is scaled per galaxy.
+    The kernel adds fesc_lya_g * (weighted line value) at that one bin; the oracle rebuilds the tree per galaxy.  The filter
+    set is given a narrow band on the line so that the term matters."""
+    from synference_b200.parametric import Calzetti2000, PacmanEmission
+    n = 120
+    w = make_workload("cfg2", n)
+    em = PacmanEmission(grid=w.grid, fesc=("fesc" if per_fesc else 0.2), fesc_ly_alpha="fesc_lya", dust_curve=Calzetti2000())
+    rng = np.random.default_rng(12)
+    flya = rng.uniform(0.0, 1.0, n)
+    flya[:2] = (0.0, 1.0)
+    fesc = rng.uniform(0.0, 0.6, n)
+    eng = SynthEngine(w.grid, em, key, w.filters, max_batch=4096)
+    p = w.params.slice(slice(0, n))
+    if key == "reprocessed":
+        p.tau_v = None
+    p.fesc_lya = flya
+    if per_fesc:
+        p.coef_att, p.coef_unatt = em.coefficients(key, fesc)
+    got = eng.photometry(p, scaled=False)
+    spec = eng.spectra(p)
+    gals = A.galaxies_from_params(p)
+    for i, g in enumerate(gals):
+        g["fesc_ly_alpha"] = float(flya[i])
+        if per_fesc:
+            g["fesc"] = float(fesc[i])
+    lam = np.asarray(w.grid.lam)
+    want, spec_want = O.synthesize(gals, w.grid.log10ages, w.grid.metallicity, lam, w.grid.spectra,
+                                   [(f.lam, f.t) for f in w.filters], key=key, fesc=0.2, dust=dict(curve="Calzetti2000"),
+                                   igm=(I.INOUE14_LAF, I.INOUE14_DLA), return_spectra=True)
+    assert_flux_close(got, want)
+    i_lya = int(np.argmin(np.abs(lam - 1215.67)))
+    col, col_want = spec[:, i_lya].astype(np.float64), spec_want[:, i_lya]
+    ok = col_want > 1e-25 * spec_want.max(axis=1)
+    assert ok.sum() > 20 and np.max(np.abs(col[ok] - col_want[ok]) / col_want[ok]) < FLUX_RTOL   # the line bin itself
+    with pytest.raises(ValueError):
+        eng.photometry(w.params.slice(slice(0, 4)), scaled=False)       # fesc_lya missing
+    eng.close()

@@ -118,8 +118,8 @@ def test_unsupported_features_fail_loudly():
     with pytest.raises(NotImplementedError):
         S.GalaxyBasis("x", b.redshifts, b.grid, b.emission_model, b.sfhs, b.metal_dists,
                       galaxy_params={"slope": np.zeros(4)}, instrument=b.instrument)
-    with pytest.raises(NotImplementedError):
-        S.PacmanEmission(grid=b.grid, fesc=0.1, fesc_ly_alpha="fesc_lya", dust_curve=S.Calzetti2000())
+    lya = S.PacmanEmission(grid=b.grid, fesc=0.1, fesc_ly_alpha="fesc_lya", dust_curve=S.Calzetti2000())
+    assert lya.lya_per_galaxy and lya.lya_line("emergent") is not None and lya.lya_line("incident") is None
     per = S.PacmanEmission(grid=b.grid, fesc="fesc", dust_curve=S.Calzetti2000())     # per-galaxy fesc IS supported ...
     with pytest.raises(ValueError):                                                  # ... but must then be provided
         S.GalaxyBasis("x", b.redshifts, b.grid, per, b.sfhs, b.metal_dists, galaxy_params={"tau_v": np.ones(4)},
@@ -233,5 +233,12 @@ def test_per_galaxy_fesc_recipe_and_coefficients():
     import pytest
     with pytest.raises(ValueError):
         per.coefficients("emergent", np.array([1.2]))
-    with pytest.raises(NotImplementedError):
-        PacmanEmission(grid=w.grid, fesc=0.1, fesc_ly_alpha="fesc_lya")
+    # per-galaxy Lyman-alpha escape: grids are lowered without the line bin, lya_line() carries it
+    lya = PacmanEmission(grid=w.grid, fesc=0.25, fesc_ly_alpha="fesc_lya", dust_curve=Calzetti2000())
+    full = PacmanEmission(grid=w.grid, fesc=0.25, fesc_ly_alpha=1.0, dust_curve=Calzetti2000())
+    vals, i = lya.lya_line("emergent")
+    a0, _ = lya.recipe("emergent")
+    a1, _ = full.recipe("emergent")
+    rebuilt = a0.copy()
+    rebuilt[..., i] += vals
+    np.testing.assert_allclose(rebuilt, a1, rtol=1e-14, atol=0)
