@@ -259,3 +259,33 @@ def test_feature_only_philox_kernel_matches_general_kernel():
         assert fast.shape == (30000 * n_sc, 2 * n_filt)
         np.testing.assert_allclose(fast[:, :n_filt], ref[:, :n_filt], atol=6e-6, rtol=0)     # <= 3 ulp of a float32 magnitude
         np.testing.assert_allclose(fast[:, n_filt:], ref[:, n_filt:], rtol=2e-6, atol=1e-7)
+
+
+def test_production_script_emission_model_through_the_api(tmp_path):
+    """The emission model of final_library_generation_multinode.py:493-510 -- Calzetti2000(slope="slope",
+    ampl="dust_bump_amplitude"), fesc_ly_alpha="fesc_lya", per-galaxy tau_v -- through GalaxyBasis, against the oracle
+    evaluated galaxy by galaxy."""
+    from oracle import adapter as A
+    n = 40
+    basis, d, grid, inst, _ = _small_basis(n, tmp_path)
+    rng = np.random.default_rng(21)
+    gp = {"tau_v": np.asarray(d["tau_v"], dtype=float), "slope": rng.uniform(-0.8, 0.3, n),
+          "fesc_lya": rng.uniform(0, 1, n), "dust_bump_amplitude": rng.uniform(0, 4, n)}
+    em = S.PacmanEmission(grid=grid, tau_v="tau_v", dust_curve=S.Calzetti2000(slope="slope", ampl="dust_bump_amplitude"),
+                          fesc=0.0, fesc_ly_alpha="fesc_lya")
+    b = S.GalaxyBasis("prod", d["redshift"], grid, em, basis.sfhs, basis.metal_dists, galaxy_params=gp, instrument=inst,
+                      build_library=False)
+    b._create_matched_galaxies(log_base_masses=9)
+    got = b.process_galaxies(save=False, emission_model_keys=["emergent"])["photometry"]["emergent"]
+    assert {"slope", "fesc_lya", "dust_bump_amplitude", "tau_v"} <= set(b.varying_param_names)
+    gals = A.galaxies_from_params(b.params)
+    for i, g in enumerate(gals):
+        g.update(dust_slope=float(gp["slope"][i]), dust_ampl=float(gp["dust_bump_amplitude"][i]),
+                 fesc_ly_alpha=float(gp["fesc_lya"][i]))
+    want = O.synthesize(gals, grid.log10ages, grid.metallicity, np.asarray(grid.lam), grid.spectra,
+                        [(f.lam, f.t) for f in inst.filters], key="emergent", fesc=0.0, dust=dict(curve="Calzetti2000"),
+                        igm=(I.INOUE14_LAF, I.INOUE14_DLA))
+    assert_flux_close(got, want)
+    with pytest.raises(ValueError):      # a named parameter the galaxies do not provide
+        S.GalaxyBasis("bad", d["redshift"], grid, em, basis.sfhs, basis.metal_dists, galaxy_params={"tau_v": gp["tau_v"]},
+                      instrument=inst, build_library=False)
