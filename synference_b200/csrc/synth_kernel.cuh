@@ -123,15 +123,12 @@ __device__ __forceinline__ float4 dust_shape(float4 k, float4 d, float4 l, float
                      fmaf(ampl, d.z, k.z) * ex2_approx(slope * l.z), fmaf(ampl, d.w, k.w) * ex2_approx(slope * l.w));
 }
 
-// Chunk visiting order.  Every CTA (pair) walks the chunks of a unit cyclically from a different start: units that are
-// neighbours in the (bracket, redshift) order need the SAME G^T tiles, and with one common order all 148 SMs request the
-// same few L2 lines at the same moment (measured: per-chunk time independent of bytes, MMAs and epilogue work).
-__device__ __forceinline__ int chunk_at(int c_first, int n_c, int rot, int j) {
-  int c = j + rot;
-  if (c >= n_c) c -= n_c;
-  return c_first + c;
-}
-__device__ __forceinline__ int chunk_rot(int n_c, unsigned who) { return n_c > 0 ? (int)((who * 5u) % (unsigned)n_c) : 0; }
+// Chunk visiting order: ascending.  (Walking the chunks cyclically from a different start per CTA, to keep SMs that work
+// on neighbouring tiles off the same L2 lines, was tried: no measurable gain, and it makes the order in which a galaxy's
+// chunks are summed depend on which CTA it landed on -- results would no longer be bit-identical across batch
+// compositions.)
+__device__ __forceinline__ int chunk_at(int c_first, int n_c, int rot, int j) { return c_first + j; }
+__device__ __forceinline__ int chunk_rot(int n_c, unsigned who) { return 0; }
 
 // Fused epilogue of one CTA (warps 3-14): see the header comment.  kCta = 2: the CTA is one half of a pair that
 // shares the MMA (cta_group::2); `unit` is then a pair of tiles, this CTA owns tile 2*unit + rank and hands its

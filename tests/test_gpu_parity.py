@@ -420,3 +420,17 @@ def test_per_galaxy_lyman_alpha_escape(key, per_fesc):
     with pytest.raises(ValueError):
         eng.photometry(w.params.slice(slice(0, 4)), scaled=False)       # fesc_lya missing
     eng.close()
+
+
+def test_populations_larger_than_max_batch_stream_through_both_slots():
+    """SynthEngine.photometry walks a population batch by batch through the two staging slots (submit / wait): the
+    result is bit-identical to one big batch, for both output types."""
+    n = 70_000
+    w = make_workload("cfg2", n)
+    big = SynthEngine(w.grid, w.emission_model, w.emission_key, w.filters, max_batch=n)
+    small = SynthEngine(w.grid, w.emission_model, w.emission_key, w.filters, max_batch=16_384)     # 5 batches, ragged tail
+    for scaled in (False, True):
+        a = big.photometry(w.params, scaled=scaled)
+        b = small.photometry(w.params, scaled=scaled)
+        assert np.array_equal(a, b)
+    big.close(); small.close()
