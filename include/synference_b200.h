@@ -104,6 +104,11 @@ typedef struct sb2_model_desc {
    * fesc_lya_g * sum_k w_k lya_line[k] to the first component at that bin.  NULL: fesc_ly_alpha is global.          */
   const double* lya_line;
   int32_t lya_bin;
+  /* Optional second dust screen (BimodalPacmanEmission of the reference's scripts, generate_library_full.py:221-231):
+   * with n_comp = 2 the two grid components are then the YOUNG and the OLD stellar populations (split at age_pivot),
+   * both attenuated: young by exp(-tau_v_birth * kappa_birth - tau_v * kappa), old by exp(-tau_v * kappa).
+   * kappa_birth is on the same padded axis as kappa.  NULL: component 2 is unattenuated (escaped light).          */
+  const float* kappa_birth;
   const double* fm_log_tab;
   const double* fm_exp_tab;
   const double* fm_tail_tab;
@@ -135,6 +140,7 @@ typedef struct sb2_params {
   const double* dust_slope; /* [n] per-galaxy power-law slope delta of the dust curve (requires dust_d0/dust_l2)  */
   const double* dust_ampl;  /* [n] per-galaxy UV-bump amplitude                       (requires dust_d0/dust_l2)  */
   const double* fesc_lya;   /* [n] per-galaxy Lyman-alpha escape fraction             (requires lya_line)         */
+  const double* tau_v_birth;/* [n] birth-cloud optical depth of the young population (requires kappa_birth; tau_v = ISM) */
 } sb2_params;
 
 typedef struct sb2_model sb2_model;

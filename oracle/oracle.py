@@ -347,7 +347,7 @@ def weights_for(gal, log10ages, metallicities):
 
 def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, key="intrinsic",
                fesc=0.0, fesc_ly_alpha=1.0, dust=None, igm=None, variant="nu", base_mass=1e9,
-               return_spectra=False, dl_cm=None):
+               return_spectra=False, dl_cm=None, two_screens=None):
     """Fluxes [nJy] of every galaxy through every filter at ``base_mass`` Msun.
 
     galaxies : list of dicts with redshift, tau_v, sfh_kind, sfh (dict, ages in yr),
@@ -357,12 +357,17 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
                dust_slope / dust_ampl (per-galaxy shape of the attenuation curve)
     filters  : list of (lam_table [A], transmission) on each filter's own axis
     dust     : None or dict(curve=..., slope=..., ampl=...)  ;  igm : None or (laf, dla)
+    two_screens : None or dict(age_pivot=log10 yr, dust_birth=dict(...)): stars with log10age < age_pivot are attenuated by
+               exp(-tau_v_birth kappa_birth - tau_v kappa), the others by exp(-tau_v kappa) (galaxy key tau_v_birth)
     """
     lam = np.asarray(lam, dtype=float)
     g_att, g_un = emission_parts(components, lam, key, fesc, fesc_ly_alpha)
     na, nz = len(log10ages), len(metallicities)
     g_att2, g_un2 = g_att.reshape(na * nz, -1), g_un.reshape(na * nz, -1)
     kappa = dust_kappa(lam, **dust) if dust is not None else None
+    if two_screens is not None:
+        kappa_birth = dust_kappa(lam, **two_screens["dust_birth"])
+        young = (np.repeat(np.asarray(log10ages)[:, None], nz, 1) < two_screens["age_pivot"]).reshape(-1)
     out = np.zeros((len(galaxies), len(filters)))
     spectra = np.zeros((len(galaxies), len(lam))) if return_spectra else None
     for g, gal in enumerate(galaxies):
@@ -380,7 +385,11 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
                 dd["slope"] = float(gal.get("dust_slope", dd.get("slope", 0.0)))
                 dd["ampl"] = float(gal.get("dust_ampl", dd.get("ampl", 0.0)))
                 kap = dust_kappa(lam, **dd)
-            att = att * np.exp(-gal.get("tau_v", 0.0) * kap)
+            if two_screens is not None:
+                att = (w * young) @ g_att2 * np.exp(-gal.get("tau_v_birth", 0.0) * kappa_birth - gal.get("tau_v", 0.0) * kap) \
+                    + (w * ~young) @ g_att2 * np.exp(-gal.get("tau_v", 0.0) * kap)
+            else:
+                att = att * np.exp(-gal.get("tau_v", 0.0) * kap)
         lnu = (lnu + att) * base_mass
         z = float(gal["redshift"])
         dl = luminosity_distance_cm(z) if dl_cm is None else dl_cm[g]

@@ -9,7 +9,7 @@ from .units import (Angstrom, Gyr, Jy, Msun, Myr, Quantity, Unit, mJy, nJy, uJy,
                     unyt_quantity, yr)
 from .cosmology import FlatLambdaCDM, Planck18  # noqa: F401
 from .parametric import (SFH, Calzetti2000, EmergentEmission, EmissionModel, Filter, FilterCollection,  # noqa: F401
-                         Grid, IncidentEmission, Instrument, IntrinsicEmission, PacmanEmission, PowerLaw,
+                         Grid, IncidentEmission, Instrument, IntrinsicEmission, PacmanEmission, BimodalPacmanEmission, PowerLaw,
                          SFHArray, TotalEmission, ZDist, ZDistArray)
 from .igm import Inoue14  # noqa: F401
 from .sampling import (continuity_sfh_array, draw_from_hypercube, generate_metallicity_distribution,  # noqa: F401

@@ -41,7 +41,7 @@ class ModelDesc(C.Structure):
         ("cosmo_dc", _dp), ("cosmo_ddc", _dp), ("cosmo_age", _dp), ("cosmo_dage", _dp),
         ("base_mass", C.c_double), ("max_batch", C.c_int64),
         ("dust_d0", _fp), ("dust_l2", _fp),
-        ("lya_line", _dp), ("lya_bin", C.c_int32),
+        ("lya_line", _dp), ("lya_bin", C.c_int32), ("kappa_birth", _fp),
         ("fm_log_tab", _dp), ("fm_exp_tab", _dp), ("fm_tail_tab", _dp), ("fm_tail_n", C.c_int32), ("fm_tail_w", C.c_double),
     ]
 
@@ -55,6 +55,7 @@ class Params(C.Structure):
         ("zd_type", C.c_int32), ("zd_value", C.c_void_p), ("zd_sigma", C.c_void_p),
         ("coef_att", C.c_void_p), ("coef_unatt", C.c_void_p),
         ("dust_slope", C.c_void_p), ("dust_ampl", C.c_void_p), ("fesc_lya", C.c_void_p),
+        ("tau_v_birth", C.c_void_p),
     ]
 
 

@@ -166,6 +166,7 @@ struct sb2_model {
   float *dust_d0 = nullptr, *dust_l2 = nullptr, *g_slope = nullptr, *g_ampl = nullptr;   // per-galaxy dust shape (optional)
   double* lya_line = nullptr;   // per-galaxy Lyman-alpha escape (optional)
   float* g_lya = nullptr;
+  float *kappa_birth = nullptr, *g_taub = nullptr;   // second dust screen (optional)
   int *filt_lo = nullptr, *filt_hi = nullptr;
   double *bin_pow = nullptr, *thr = nullptr, *pre = nullptr;
   int *nline = nullptr, *lc_on = nullptr;
@@ -237,7 +238,7 @@ int sb2_device_count(void) {
 int sb2_model_destroy(sb2_model* m) {
   if (!m) return SB2_OK;
   cudaSetDevice(m->device);
-  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->dust_d0, m->dust_l2, m->g_slope, m->g_ampl, m->lya_line, m->g_lya, m->filt_uv, m->filt_lo,
+  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->dust_d0, m->dust_l2, m->g_slope, m->g_ampl, m->lya_line, m->g_lya, m->kappa_birth, m->g_taub, m->filt_uv, m->filt_lo,
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage, m->fm_log, m->fm_exp, m->fm_tail,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
                   m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params[0],
@@ -302,6 +303,12 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
     std::vector<float> kap((size_t)d->n_chunk * lch, 0.f);
     if (d->kappa) std::memcpy(kap.data(), d->kappa, kap.size() * sizeof(float));
     UP(kappa, kap.data(), kap.size());
+    if (d->kappa_birth) {
+      if (!d->kappa || d->n_comp != 2) { sb2_model_destroy(m); return fail(SB2_ERR_INVALID, "kappa_birth needs kappa and n_comp = 2"); }
+      std::vector<float> tb(kap.size(), 0.f);
+      std::memcpy(tb.data(), d->kappa_birth, tb.size() * sizeof(float));
+      UP(kappa_birth, tb.data(), tb.size());
+    }
     if (d->dust_d0 && d->dust_l2) {
       if (!d->kappa) { sb2_model_destroy(m); return fail(SB2_ERR_INVALID, "dust_d0/dust_l2 need kappa"); }
       std::vector<float> t0(kap.size(), 0.f), t1(kap.size(), 0.f);
@@ -378,6 +385,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(g_m, np * 4); AL(g_orig, np * 4); AL(perm, np * 4); AL(idx, np * 4);
   if (m->dust_d0) { AL(g_slope, np * 4); AL(g_ampl, np * 4); }
   if (m->lya_line) { AL(g_lya, np * 4); }
+  if (m->kappa_birth) { AL(g_taub, np * 4); }
   AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
   AL(keys, np * 4); AL(keys_sorted, np * 4); AL(perm_pad, np * 4); AL(tile_k0, (np / 128) * 4); AL(grp, (3 * kMaxGroups + 1) * 4);
   AL(g_mscale, np * 8); AL(g_trunc, np * 4); AL(zpow, np * 13 * 8);
@@ -385,7 +393,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)m->cap);
   AL(cub_tmp, m->cub_bytes + 16);
   for (int sl = 0; sl < 2; ++sl) {
-    AL(stage_params[sl], (size_t)m->cap * (10 + SB2_SFH_ROW) * 8);
+    AL(stage_params[sl], (size_t)m->cap * (11 + SB2_SFH_ROW) * 8);
     AL(stage_flux[sl], (size_t)m->cap * d->n_filt * 4);
     AL(stage_flux64[sl], (size_t)m->cap * d->n_filt * 8);
   }
@@ -510,7 +518,7 @@ int launch_synth2(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t 
 int launch_synth(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
   const int nf = m->d.n_filt, c = m->d.n_comp;
   const bool spec = a.out_spec != nullptr;
-  const bool pg = a.dust_d0 != nullptr || a.g_lya != nullptr;   // per-galaxy emission extras: their own instantiation
+  const bool pg = a.dust_d0 != nullptr || a.g_lya != nullptr || a.kappa_birth != nullptr;   // per-galaxy emission extras: their own instantiation
 #define SB2_PICK(C, NF)                                                                                             \
   (pg ? (spec ? launch_synth_t<C, NF, true, true>(m, a, grid, delta, st) : launch_synth_t<C, NF, false, true>(m, a, grid, delta, st)) \
       : (spec ? launch_synth_t<C, NF, true, false>(m, a, grid, delta, st) : launch_synth_t<C, NF, false, false>(m, a, grid, delta, st)))
@@ -550,7 +558,7 @@ sb2::PrepParams prep_params(const sb2_params* p) {
   P.sfh_type = p->sfh_type; P.sfh_stride = p->sfh_stride; P.sfh_rows = p->sfh_rows;
   P.max_age_from_z = p->max_age_from_z; P.norm_mask = p->norm_mask; P.age_zmax_gyr = p->age_zmax_gyr;
   P.zd_type = p->zd_type; P.zd_value = p->zd_value; P.zd_sigma = p->zd_sigma;
-  P.coef_att = p->coef_att; P.coef_unatt = p->coef_unatt; P.dust_slope = p->dust_slope; P.dust_ampl = p->dust_ampl; P.fesc_lya = p->fesc_lya;
+  P.coef_att = p->coef_att; P.coef_unatt = p->coef_unatt; P.dust_slope = p->dust_slope; P.dust_ampl = p->dust_ampl; P.fesc_lya = p->fesc_lya; P.tau_v_birth = p->tau_v_birth;
   return P;
 }
 
@@ -566,6 +574,7 @@ int check_params(const sb2_model* m, const sb2_params* p) {
   if (p->zd_type >= SB2_ZD_NORMAL_LINEAR && !p->zd_sigma) return fail(SB2_ERR_INVALID, "zd_sigma required for Normal");
   if ((p->dust_slope || p->dust_ampl) && !m->dust_d0)
     return fail(SB2_ERR_INVALID, "per-galaxy dust_slope / dust_ampl need a model created with dust_d0 and dust_l2");
+  if (p->tau_v_birth && !m->kappa_birth) return fail(SB2_ERR_INVALID, "tau_v_birth needs a model created with kappa_birth");
   if (p->fesc_lya && !m->lya_line) return fail(SB2_ERR_INVALID, "per-galaxy fesc_lya needs a model created with lya_line");
   if (m->lya_line && !p->fesc_lya) return fail(SB2_ERR_INVALID, "this model reads fesc_lya per galaxy: params.fesc_lya is required");
   if (p->fesc_lya && (m->d.n_age > 64 || m->d.n_z > 64)) return fail(SB2_ERR_INVALID, "per-galaxy fesc_lya supports n_age, n_z <= 64");
@@ -577,7 +586,7 @@ int check_params(const sb2_model* m, const sb2_params* p) {
 int rows_per_unit(const sb2_model* m, bool delta) {
   // The CTA-pair kernel (synth2_kernel) is parity-tested but not yet faster than the single-CTA kernel on B200
   // (both sit on the same synchronisation/epilogue floor); it is opt-in: SB2_CTA_PAIR=1.
-  return (delta && m->smem2_bytes > 0 && !m->dust_d0 && !m->lya_line && std::getenv("SB2_CTA_PAIR")) ? 256 : 128;
+  return (delta && m->smem2_bytes > 0 && !m->dust_d0 && !m->lya_line && !m->kappa_birth && std::getenv("SB2_CTA_PAIR")) ? 256 : 128;
 }
 // Rows the grouped layout of a batch of n galaxies can occupy (every group is padded to whole units).
 long long padded_rows(const sb2_model* m, long long n, bool delta) {
@@ -621,7 +630,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   sb2::PrepOut O{};
   O.w_hi = m->w_hi; O.w_lo = m->w_lo; O.w_f64 = w_f64; O.igm = m->igm; O.g_m = m->g_m; O.g_beta = m->g_beta; O.g_gamma = m->g_gamma;
   O.g_taut = m->g_taut; O.g_scale = m->g_scale; O.g_ca = m->g_ca; O.g_cb = m->g_cb; O.g_orig = m->g_orig;
-  O.g_slope = m->g_slope; O.g_ampl = m->g_ampl; O.g_lya = m->g_lya;
+  O.g_slope = m->g_slope; O.g_ampl = m->g_ampl; O.g_lya = m->g_lya; O.g_taub = m->g_taub;
   O.g_mscale = m->g_mscale; O.g_trunc = m->g_trunc; O.zpow = m->zpow;
   if (!w_f64) {  // the parity hook (sb2_build_weights) needs the weights only
     sb2::scalars_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(M, P, O, perm, n_pad);
@@ -706,7 +715,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.n_blue = d.n_blue; a.n_blue_pad = m->n_blue_pad; a.uv_len = m->uv_len;
   a.tile_range = m->tile_range;
   a.dust_d0 = m->dust_d0; a.dust_l2 = m->dust_l2; a.g_slope = m->g_slope; a.g_ampl = m->g_ampl;
-  a.g_lya = m->g_lya; a.lya_bin = d.lya_bin;
+  a.g_lya = m->g_lya; a.lya_bin = d.lya_bin; a.kappa_birth = m->kappa_birth; a.g_taub = m->g_taub;
   a.kappa = m->kappa; a.filt_uv = reinterpret_cast<const float2*>(m->filt_uv); a.igm = m->igm;
   a.g_m = m->g_m; a.g_beta = m->g_beta; a.g_gamma = m->g_gamma; a.g_taut = m->g_taut; a.g_scale = m->g_scale; a.g_ca = m->g_ca;
   a.g_cb = m->g_cb; a.g_orig = m->g_orig; a.g_mscale = m->g_mscale; a.g_trunc = m->g_trunc;
@@ -781,9 +790,9 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
   // copied in on st_h2d, synthesised on st_comp and copied out on st_d2h, so the PCIe copies of one slice
   // overlap the kernels of its neighbours (pinned host buffers are needed for the overlap, not for correctness).
   double* base = m->stage_params[slot];
-  constexpr int kNA = 11;   // staged arrays; the last one is the SFH row table
+  constexpr int kNA = 12;   // staged arrays; the last one is the SFH row table
   const double* src[kNA] = {p->redshift, p->log_mass, p->tau_v, p->zd_value, p->zd_sigma, p->coef_att, p->coef_unatt,
-                            p->dust_slope, p->dust_ampl, p->fesc_lya, p->sfh_rows};
+                            p->dust_slope, p->dust_ampl, p->fesc_lya, p->tau_v_birth, p->sfh_rows};
   double* dev[kNA];
   for (int i = 0; i < kNA; ++i) {
     const size_t w = (i == kNA - 1) ? (size_t)p->sfh_stride : 1;
@@ -826,7 +835,8 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
     dp.coef_att = dev[5] ? dev[5] + a : nullptr; dp.coef_unatt = dev[6] ? dev[6] + a : nullptr;
     dp.dust_slope = dev[7] ? dev[7] + a : nullptr; dp.dust_ampl = dev[8] ? dev[8] + a : nullptr;
     dp.fesc_lya = dev[9] ? dev[9] + a : nullptr;
-    dp.sfh_rows = dev[10] + a * p->sfh_stride;
+    dp.tau_v_birth = dev[10] ? dev[10] + a : nullptr;
+    dp.sfh_rows = dev[11] + a * p->sfh_stride;
     rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux[slot] + a * nf : nullptr,
                               flux_scaled ? m->stage_flux64[slot] + a * nf : nullptr, nullptr, m->st_comp);
     if (rc != SB2_OK) return rc;

@@ -122,6 +122,7 @@ struct PrepParams {  // device pointers (sb2_params with device arrays)
   const double* dust_slope;
   const double* dust_ampl;
   const double* fesc_lya;
+  const double* tau_v_birth;
 };
 
 struct PrepOut {
@@ -139,6 +140,7 @@ struct PrepOut {
   float* g_cb;      // [n_pad]
   float* g_slope;   // [n_pad] per-galaxy dust slope / bump amplitude (nullptr: global curve)
   float* g_ampl;    // [n_pad]
+  float* g_taub;    // [n_pad] birth-cloud tau_V * log2(e) (nullptr: single screen)
   float* g_lya;     // [n_pad] fesc_lya_g * sum_k w_k lya_line[k] (nullptr: global Lyman-alpha escape fraction)
   int* g_orig;      // [n_pad]  original index, -1 for padding rows
   double* g_mscale; // [n_pad]
@@ -300,6 +302,7 @@ scalars_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ per
     O.g_m[t] = 0; O.g_beta[t] = 0.5f; O.g_gamma[t] = 0.5f; O.g_taut[t] = 0.f; O.g_scale[t] = 0.f; O.g_ca[t] = 0.f;
     O.g_cb[t] = 0.f; O.g_orig[t] = -1; O.g_mscale[t] = 0.0; O.g_trunc[t] = 0u;
     if (O.g_slope) { O.g_slope[t] = 0.f; O.g_ampl[t] = 0.f; }
+    if (O.g_taub) O.g_taub[t] = 0.f;
     return;
   }
   double z = P.redshift[g];
@@ -328,6 +331,7 @@ scalars_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ per
   O.g_scale[t] = (float)scale;
   O.g_ca[t] = (float)(P.coef_att ? P.coef_att[g] : 1.0);
   O.g_cb[t] = (float)(P.coef_unatt ? P.coef_unatt[g] : 1.0);
+  if (O.g_taub) O.g_taub[t] = (float)((P.tau_v_birth ? P.tau_v_birth[g] : 0.0) * 1.44269504088896340736);
   if (O.g_slope) {
     O.g_slope[t] = (float)(P.dust_slope ? P.dust_slope[g] : 0.0);
     O.g_ampl[t] = (float)(P.dust_ampl ? P.dust_ampl[g] : 0.0);

@@ -77,6 +77,8 @@ struct SynthArgs {
   const float* dust_l2;
   const float* g_slope;
   const float* g_ampl;
+  const float* kappa_birth;  // second screen (young population): nullptr = component 2 is unattenuated
+  const float* g_taub;
   const float* g_lya;        // per-galaxy Lyman-alpha line term, added to the first component at bin lya_bin; nullptr: none
   int lya_bin;
   const float2* filt_uv;     // padded tables, uv_len entries
@@ -169,6 +171,8 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
       const bool dust_pg = pg_dust && A.dust_d0 != nullptr;
       const float slope = dust_pg ? A.g_slope[row] : 0.f, ampl = dust_pg ? A.g_ampl[row] : 0.f;
       const float lya = (pg_dust && A.g_lya != nullptr) ? A.g_lya[row] : 0.f;
+      const bool two_screens = pg_dust && kComp == 2 && A.kappa_birth != nullptr;
+      const float ntaub = two_screens ? -A.g_taub[row] : 0.f;
       // redshift-shift range of this warp's real galaxies (padding rows follow the others)
       int mmin = orig >= 0 ? m : INT_MAX, mmax = orig >= 0 ? m : INT_MIN;
 #pragma unroll
@@ -227,6 +231,14 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
                 float4 k4 = __ldg(kp + j4);
                 if (pg_dust && dust_pg) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
                                              __ldg(reinterpret_cast<const float4*>(A.dust_l2 + i0) + j4), slope, ampl);
+                if (two_screens) {   // young: birth cloud + ISM, old: ISM only (both components are attenuated)
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(A.kappa_birth + i0) + j4);
+                  s[4 * j4 + 0] = ca * (__uint_as_float(v[4 * j4 + 0]) * ex2_approx(fmaf(ntaub, b4.x, ntaut * k4.x))) + cb * (__uint_as_float(u[4 * j4 + 0]) * ex2_approx(ntaut * k4.x));
+                  s[4 * j4 + 1] = ca * (__uint_as_float(v[4 * j4 + 1]) * ex2_approx(fmaf(ntaub, b4.y, ntaut * k4.y))) + cb * (__uint_as_float(u[4 * j4 + 1]) * ex2_approx(ntaut * k4.y));
+                  s[4 * j4 + 2] = ca * (__uint_as_float(v[4 * j4 + 2]) * ex2_approx(fmaf(ntaub, b4.z, ntaut * k4.z))) + cb * (__uint_as_float(u[4 * j4 + 2]) * ex2_approx(ntaut * k4.z));
+                  s[4 * j4 + 3] = ca * (__uint_as_float(v[4 * j4 + 3]) * ex2_approx(fmaf(ntaub, b4.w, ntaut * k4.w))) + cb * (__uint_as_float(u[4 * j4 + 3]) * ex2_approx(ntaut * k4.w));
+                  continue;
+                }
                 s[4 * j4 + 0] = ca * (__uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x)) + cb * __uint_as_float(u[4 * j4 + 0]);
                 s[4 * j4 + 1] = ca * (__uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y)) + cb * __uint_as_float(u[4 * j4 + 1]);
                 s[4 * j4 + 2] = ca * (__uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z)) + cb * __uint_as_float(u[4 * j4 + 2]);

@@ -52,6 +52,7 @@ class GalaxyParams:
     dust_slope: Optional[np.ndarray] = None     # per-galaxy dust-curve slope / bump amplitude (models built with
     dust_ampl: Optional[np.ndarray] = None      # Calzetti2000(slope="...", ampl="..."))
     fesc_lya: Optional[np.ndarray] = None       # per-galaxy Lyman-alpha escape fraction (fesc_ly_alpha="<name>" models)
+    tau_v_birth: Optional[np.ndarray] = None    # birth-cloud optical depth (BimodalPacmanEmission; tau_v is then the ISM's)
     max_age_from_z: bool = False
     norm_mask: int = 0
     age_zmax_gyr: float = 0.0
@@ -80,7 +81,7 @@ class GalaxyParams:
         return GalaxyParams(self.redshift[sl], self.sfh_type, self.sfh_rows[sl], self.zd_type,
                             self.zd_value[sl], g(self.zd_sigma), g(self.log_mass), g(self.tau_v),
                             g(self.coef_att), g(self.coef_unatt), g(self.dust_slope), g(self.dust_ampl), g(self.fesc_lya),
-                            self.max_age_from_z, self.norm_mask, self.age_zmax_gyr)
+                            g(self.tau_v_birth), self.max_age_from_z, self.norm_mask, self.age_zmax_gyr)
 
 
 def geometric_ratio(lam):
@@ -105,10 +106,14 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
     has_att, has_un = bool(np.any(att != 0)), bool(np.any(un != 0))
     dust = emission_model.dust_curve
     dust_free = bool(getattr(emission_model, "dust_free", lambda k: False)(emission_key))
+    two_screens = bool(getattr(emission_model, "two_screens", lambda k: False)(emission_key))
     if has_att and dust is None and not dust_free:
         raise ValueError(f"spectrum '{emission_key}' is dust attenuated but the emission model has no dust_curve")
     screen = (lambda: np.zeros_like(lam)) if dust_free else (lambda: dust.get_tau(lam))
-    if has_att and has_un:
+    if two_screens:           # (young, old) reprocessed light, both attenuated: always two components
+        comps, kappa = [att, un], screen()
+        has_att = has_un = True
+    elif has_att and has_un:
         comps, kappa = [att, un], screen()
     elif has_att:
         comps, kappa = [att], screen()
@@ -134,10 +139,13 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         gt[:, ci, :, :nz * na_pad] = pad.reshape(n_chunk, lch, nz * na_pad)
     gt = gt.reshape(n_chunk * CHUNK_COLS, k_pad)
     gt_hi, gt_lo = tf32_split(gt)
-    kap = d0 = l2 = None
+    kap = d0 = l2 = kap_birth = None
     if kappa is not None:
         kap = np.zeros(n_chunk * lch, dtype=np.float32)
         kap[:n_lam] = kappa
+        if two_screens:
+            kap_birth = np.zeros_like(kap)
+            kap_birth[:n_lam] = emission_model.dust_curve_birth.get_tau(lam)
         if getattr(dust, "per_galaxy", False) and not dust_free:
             # per-galaxy slope / bump amplitude: kappa holds the curve at slope = 0, ampl = 0 (get_tau already used 0 for
             # the string-named ones; a numeric one is broadcast to every galaxy by SynthEngine._fill)
@@ -179,7 +187,7 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         n_age=na, n_z=nz, n_lam=n_lam, n_comp=n_comp, n_filt=len(lo_l), n_age_pad=na_pad, k_pad=k_pad, n_chunk=n_chunk,
         log10ages=np.ascontiguousarray(grid.log10ages, dtype=np.float64),
         metallicities=np.ascontiguousarray(grid.metallicity, dtype=np.float64),
-        gt_hi=gt_hi, gt_lo=gt_lo, grid_scale=grid_scale, kappa=kap, dust_d0=d0, dust_l2=l2,
+        gt_hi=gt_hi, gt_lo=gt_lo, grid_scale=grid_scale, kappa=kap, dust_d0=d0, dust_l2=l2, kappa_birth=kap_birth,
         dust_global=(float(getattr(dust, "slope", 0.0)), float(getattr(dust, "ampl", 0.0))) if d0 is not None else None,
         lam0=float(lam[0]), q=q,
         interp_variant=0 if variant == "nu" else 1,
@@ -245,6 +253,7 @@ class SynthEngine:
         d.kappa = ptr(t["kappa"], C.c_float)
         d.dust_d0, d.dust_l2 = ptr(t["dust_d0"], C.c_float), ptr(t["dust_l2"], C.c_float)
         d.lya_line, d.lya_bin = ptr(t["lya_line"], C.c_double), int(t["lya_bin"])
+        d.kappa_birth = ptr(t["kappa_birth"], C.c_float)
         d.filt_lo, d.filt_hi = ptr(t["filt_lo"], C.c_int32), ptr(t["filt_hi"], C.c_int32)
         d.filt_off, d.filt_uv = ptr(t["filt_off"], C.c_int32), ptr(t["filt_uv"], C.c_float)
         d.filt_uv_len = int(t["filt_uv"].shape[0])
@@ -299,6 +308,11 @@ class SynthEngine:
             raise ValueError("per-galaxy fesc_lya given, but the emission model has a numeric fesc_ly_alpha (or the spectrum "
                              "has no nebular part); build it with fesc_ly_alpha='fesc_lya'")
         s.fesc_lya = get_ptr(p.fesc_lya)
+        if p.tau_v_birth is not None and self.tables["kappa_birth"] is None:
+            raise ValueError("tau_v_birth given, but this spectrum / emission model has a single dust screen")
+        if p.tau_v_birth is None and self.tables["kappa_birth"] is not None:
+            raise ValueError("the emission model has two dust screens: GalaxyParams.tau_v_birth is required")
+        s.tau_v_birth = get_ptr(p.tau_v_birth)
         return s
 
     def _dust_arrays(self, p: GalaxyParams, get_ptr):
@@ -370,6 +384,7 @@ class SynthEngine:
         sl, am = self._dust_arrays(params, lambda a: (keep.append(np.ascontiguousarray(a, dtype=np.float64)), keep[-1])[1])
         tensors["dust_slope"], tensors["dust_ampl"] = mv(sl), mv(am)
         tensors["fesc_lya"] = mv(params.fesc_lya)
+        tensors["tau_v_birth"] = mv(params.tau_v_birth)
         return DeviceParams(params, tensors)
 
     def _set_device_ptrs(self, s, tensors):
@@ -382,6 +397,7 @@ class SynthEngine:
             s.coef_att, s.coef_unatt = ptr("coef_att"), ptr("coef_unatt")
         s.dust_slope, s.dust_ampl = ptr("dust_slope"), ptr("dust_ampl")
         s.fesc_lya = ptr("fesc_lya")
+        s.tau_v_birth = ptr("tau_v_birth")
 
     def photometry_device(self, dparams: "DeviceParams", flux_base=None, flux_scaled=None, spectra=None):
         """Run one batch whose parameters are already in HBM; outputs are caller-provided torch tensors."""

@@ -100,7 +100,8 @@ class GalaxyBasis:
                 self.galaxy_params[key] = self.process_priors(value)
         dust = getattr(emission_model, "dust_curve", None)
         dust_names = {getattr(dust, "slope_name", None), getattr(dust, "ampl_name", None),
-                      getattr(emission_model, "lya_name", None)} - {None}
+                      getattr(emission_model, "lya_name", None), getattr(emission_model, "tau_v_ism_name", None),
+                      getattr(emission_model, "tau_v_birth_name", None)} - {None}
         for name in dust_names:
             if name not in galaxy_params:
                 raise ValueError(f"the emission model reads '{name}' per galaxy, but galaxy_params does not provide it")
@@ -186,7 +187,7 @@ class GalaxyBasis:
 
     def _lower(self, redshifts, sfhs, metal_dists, galaxy_params: Dict[str, np.ndarray], log_mass=None):
         n = len(redshifts)
-        tau_v = galaxy_params.get("tau_v")
+        tau_v = galaxy_params.get(getattr(self.emission_model, "tau_v_ism_name", None) or "tau_v")
         self.params = GalaxyParams.from_objects(redshifts, sfhs, metal_dists, log_mass=log_mass, tau_v=tau_v)
         table = {k: np.broadcast_to(np.asarray(strip_units(v), dtype=float), (n,)).copy()
                  for k, v in galaxy_params.items()}
@@ -340,6 +341,10 @@ class GalaxyBasis:
                 for attr, name in (("dust_slope", getattr(dust, "slope_name", None)), ("dust_ampl", getattr(dust, "ampl_name", None))):
                     if name is not None:
                         setattr(p, attr, np.asarray(strip_units(self.all_parameters[name]), dtype=float)[sl])
+                birth = getattr(self.emission_model, "tau_v_birth_name", None)
+                p.tau_v_birth = None
+                if birth is not None and self.emission_model.two_screens(key):
+                    p.tau_v_birth = np.asarray(strip_units(self.all_parameters[birth]), dtype=float)[sl]
                 lya_name = getattr(self.emission_model, "lya_name", None)
                 p.fesc_lya = None
                 if lya_name is not None and self.emission_model.lya_line(key) is not None:
@@ -853,12 +858,14 @@ class GalaxySimulator:
                 zd = ZDistArray(ZD_DELTA_LINEAR, bc(params["metallicity"]))
         else:
             zd = ZDistArray(ZD_NORMAL_LOG10, bc(params["mean"]), bc(params["sigma"]))
-        tau_v = bc(params["tau_v"]) if "tau_v" in params else None
+        ism_name = getattr(self.emission_model, "tau_v_ism_name", None) or "tau_v"
+        birth_name = getattr(self.emission_model, "tau_v_birth_name", None)
+        tau_v = bc(params[ism_name]) if ism_name in params else None
         fesc_name = getattr(self.emission_model, "fesc_name", None)
         dust = getattr(self.emission_model, "dust_curve", None)
         slope_name, ampl_name = getattr(dust, "slope_name", None), getattr(dust, "ampl_name", None)
         lya_name = getattr(self.emission_model, "lya_name", None)
-        used = [k for k in params if k not in self.total_possible_keys and k not in ("tau_v", fesc_name, slope_name, ampl_name, lya_name)
+        used = [k for k in params if k not in self.total_possible_keys and k not in (ism_name, birth_name, fesc_name, slope_name, ampl_name, lya_name)
                 and k not in self.ignore_params and k not in cls.param_names]
         for k in used:
             if k not in self.unused_params:
@@ -881,6 +888,11 @@ class GalaxySimulator:
             if lya_name not in params:
                 raise ValueError(f"Missing required parameter '{lya_name}' (per-galaxy Lyman-alpha escape fraction)")
             gp.fesc_lya = np.array(bc(params[lya_name]), dtype=float)
+        if birth_name is not None and self.emission_model.two_screens(self.emission_model_key):
+            for name in (ism_name, birth_name):
+                if name not in params:
+                    raise ValueError(f"Missing required parameter '{name}' (optical depth of one of the two dust screens)")
+            gp.tau_v_birth = np.array(bc(params[birth_name]), dtype=float)
         return gp
 
     def simulate(self, params):

@@ -755,6 +755,43 @@ class PacmanEmission(EmissionModel):
     pass
 
 
+class BimodalPacmanEmission(EmissionModel):
+    """Charlot & Fall style two-screen attenuation (``generate_library_full.py:221-231``,
+    ``generate_spectral_library.py:329-340``): stars younger than ``age_pivot`` (log10 yr, ``log10ages < age_pivot``) sit
+    behind their birth cloud AND the ISM, older stars behind the ISM only.  ``tau_v_ism`` / ``tau_v_birth`` name per-galaxy
+    emitter attributes.  Lowered as two grid components (young, old reprocessed light) that are BOTH attenuated
+    (``two_screens``); an escape fraction would need a third, unscreened component and is not supported."""
+
+    def __init__(self, grid, tau_v_ism="tau_v_ism", tau_v_birth="tau_v_birth", dust_curve_ism=None, dust_curve_birth=None,
+                 age_pivot=7.0, dust_emission_ism=None, dust_emission_birth=None, fesc=0.0, fesc_ly_alpha=1.0, **kwargs):
+        if dust_curve_ism is None or dust_curve_birth is None:
+            raise ValueError("BimodalPacmanEmission needs dust_curve_ism and dust_curve_birth")
+        if isinstance(fesc, str) or float(fesc) != 0.0:
+            raise NotImplementedError("BimodalPacmanEmission with a non-zero escape fraction needs a third (unscreened) "
+                                      "component; not in the batched path yet")
+        for c in (dust_curve_ism, dust_curve_birth):
+            if getattr(c, "per_galaxy", False):
+                raise NotImplementedError("per-galaxy dust-curve shape together with two screens is not in the batched path yet")
+        super().__init__(grid, fesc=0.0, fesc_ly_alpha=fesc_ly_alpha, dust_curve=dust_curve_ism, tau_v=tau_v_ism, **kwargs)
+        self.dust_curve_birth = dust_curve_birth
+        self.tau_v_ism_name, self.tau_v_birth_name = tau_v_ism, tau_v_birth
+        self.age_pivot = float(strip_units(age_pivot))
+        # dust emission is accepted and ignored up to 'emergent'; 'total' (which adds it) is refused in recipe()
+        self._has_dust_emission = dust_emission_ism is not None or dust_emission_birth is not None
+
+    def two_screens(self, key):
+        return key in ("attenuated", "emergent", "total")
+
+    def recipe(self, key):
+        if key == "total" and self._has_dust_emission:
+            raise NotImplementedError("dust emission / energy balance is not in the batched path yet; use 'emergent'")
+        att, un = super().recipe(key)
+        if not self.two_screens(key):
+            return att, un
+        young = (np.asarray(self.grid.log10ages) < self.age_pivot)[:, None, None]
+        return np.where(young, att, 0.0), np.where(young, 0.0, att)       # (young, old), both behind dust
+
+
 class TotalEmission(EmissionModel):
     def __init__(self, grid, dust_curve=None, tau_v="tau_v", dust_emission_model=None, **kw):
         super().__init__(grid, dust_curve=dust_curve, tau_v=tau_v, dust_emission=dust_emission_model, **kw)

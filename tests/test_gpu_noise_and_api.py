@@ -289,3 +289,29 @@ def test_production_script_emission_model_through_the_api(tmp_path):
     with pytest.raises(ValueError):      # a named parameter the galaxies do not provide
         S.GalaxyBasis("bad", d["redshift"], grid, em, basis.sfhs, basis.metal_dists, galaxy_params={"tau_v": gp["tau_v"]},
                       instrument=inst, build_library=False)
+
+
+def test_bimodal_emission_model_through_the_api(tmp_path):
+    """The emission model of generate_library_full.py:221-231 (BimodalPacmanEmission with tau_v_ism / tau_v_birth per galaxy,
+    age_pivot 7) through GalaxyBasis and GalaxySimulator, against the oracle's two-screen form."""
+    from oracle import adapter as A
+    n = 40
+    basis, d, grid, inst, _ = _small_basis(n, tmp_path)
+    rng = np.random.default_rng(33)
+    gp = {"tau_v_ism": np.asarray(d["tau_v"], dtype=float), "tau_v_birth": rng.uniform(0, 2.5, n)}
+    em = S.BimodalPacmanEmission(grid=grid, tau_v_ism="tau_v_ism", tau_v_birth="tau_v_birth", dust_curve_ism=S.Calzetti2000(),
+                                 dust_curve_birth=S.Calzetti2000(), age_pivot=7.0)
+    b = S.GalaxyBasis("bimodal", d["redshift"], grid, em, basis.sfhs, basis.metal_dists, galaxy_params=gp, instrument=inst,
+                      build_library=False)
+    b._create_matched_galaxies(log_base_masses=9)
+    got = b.process_galaxies(save=False, emission_model_keys=["emergent"])["photometry"]["emergent"]
+    assert {"tau_v_ism", "tau_v_birth"} <= set(b.varying_param_names)
+    gals = A.galaxies_from_params(b.params)
+    for i, g in enumerate(gals):
+        assert g["tau_v"] == pytest.approx(gp["tau_v_ism"][i])
+        g["tau_v_birth"] = float(gp["tau_v_birth"][i])
+    want = O.synthesize(gals, grid.log10ages, grid.metallicity, np.asarray(grid.lam), grid.spectra,
+                        [(f.lam, f.t) for f in inst.filters], key="emergent", dust=dict(curve="Calzetti2000"),
+                        igm=(I.INOUE14_LAF, I.INOUE14_DLA),
+                        two_screens=dict(age_pivot=7.0, dust_birth=dict(curve="Calzetti2000")))
+    assert_flux_close(got, want)

@@ -422,6 +422,45 @@ def test_per_galaxy_lyman_alpha_escape(key, per_fesc):
     eng.close()
 
 
+@pytest.mark.parametrize("key", ["emergent", "attenuated"])
+def test_two_screen_birth_cloud_and_ism_attenuation(key):
+    """BimodalPacmanEmission (generate_library_full.py:221-231): stars younger than age_pivot behind birth cloud + ISM, the rest
+    behind the ISM only, each with its own curve and per-galaxy optical depths; spectra and photometry against the oracle."""
+    from synference_b200.parametric import BimodalPacmanEmission, Calzetti2000, PacmanEmission
+    n = 180
+    w = make_workload("cfg2", n)
+    em = BimodalPacmanEmission(grid=w.grid, tau_v_ism="tau_v_ism", tau_v_birth="tau_v_birth", dust_curve_ism=Calzetti2000(),
+                               dust_curve_birth=Calzetti2000(slope=-0.7), age_pivot=7.0, fesc_ly_alpha=0.4)
+    rng = np.random.default_rng(21)
+    tau_b = rng.uniform(0.0, 3.0, n)
+    tau_b[:2] = 0.0
+    eng = SynthEngine(w.grid, em, key, w.filters, max_batch=4096)
+    p = w.params.slice(slice(0, n))
+    p.tau_v_birth = tau_b
+    got = eng.photometry(p, scaled=False)
+    spec = eng.spectra(p).astype(np.float64)
+    gals = A.galaxies_from_params(p)
+    for g, tb in zip(gals, tau_b):
+        g["tau_v_birth"] = float(tb)
+    lam = np.asarray(w.grid.lam)
+    want, spec_want = O.synthesize(gals, w.grid.log10ages, w.grid.metallicity, lam, w.grid.spectra,
+                                   [(f.lam, f.t) for f in w.filters], key=key, fesc_ly_alpha=0.4, dust=dict(curve="Calzetti2000"),
+                                   igm=(I.INOUE14_LAF, I.INOUE14_DLA), return_spectra=True,
+                                   two_screens=dict(age_pivot=7.0, dust_birth=dict(curve="Calzetti2000", slope=-0.7)))
+    assert_flux_close(got, want)
+    ok = spec_want > 1e-25 * spec_want.max(axis=1, keepdims=True)
+    assert np.max(np.abs(spec[ok] - spec_want[ok]) / spec_want[ok]) < FLUX_RTOL
+    # a galaxy without birth-cloud dust is the single-screen model
+    plain = SynthEngine(w.grid, PacmanEmission(grid=w.grid, fesc=0.0, fesc_ly_alpha=0.4, dust_curve=Calzetti2000()), key,
+                        w.filters, max_batch=4096)
+    np.testing.assert_allclose(got[:2], plain.photometry(w.params.slice(slice(0, 2)), scaled=False), rtol=3e-6)
+    with pytest.raises(ValueError):
+        plain.photometry(p, scaled=False)                            # tau_v_birth needs the two-screen model
+    with pytest.raises(ValueError):
+        eng.photometry(w.params.slice(slice(0, 4)), scaled=False)    # ... and the two-screen model needs tau_v_birth
+    eng.close(); plain.close()
+
+
 def test_populations_larger_than_max_batch_stream_through_both_slots():
     """SynthEngine.photometry walks a population batch by batch through the two staging slots (submit / wait): the
     result is bit-identical to one big batch, for both output types."""

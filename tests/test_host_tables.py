@@ -148,6 +148,31 @@ def test_two_component_layout():
     assert list(diff) == [jl]
 
 
+def test_two_screen_layout():
+    """BimodalPacmanEmission lowers to (young, old) reprocessed components split at age_pivot, plus a second kappa table."""
+    from synference_b200.parametric import BimodalPacmanEmission, Calzetti2000, PacmanEmission
+    w = make_workload("cfg2", 4)
+    em = BimodalPacmanEmission(grid=w.grid, dust_curve_ism=Calzetti2000(), dust_curve_birth=Calzetti2000(slope=-0.7),
+                               age_pivot=7.0, fesc_ly_alpha=0.4)
+    t = build_tables(w.grid, em, "emergent", w.filters)
+    assert t["n_comp"] == 2 and t["kappa_birth"] is not None and t["kappa"] is not None
+    lam = np.asarray(w.grid.lam)
+    nl = len(lam)
+    np.testing.assert_allclose(t["kappa"][:nl], O.dust_kappa(lam, curve="Calzetti2000"), rtol=1e-6)
+    np.testing.assert_allclose(t["kappa_birth"][:nl], O.dust_kappa(lam, curve="Calzetti2000", slope=-0.7), rtol=1e-6)
+    assert np.all(t["kappa_birth"][nl:] == 0)
+    young, old = em.recipe("emergent")
+    whole = PacmanEmission(grid=w.grid, fesc=0.0, fesc_ly_alpha=0.4, dust_curve=Calzetti2000()).recipe("emergent")[0]
+    np.testing.assert_array_equal(young + old, whole)
+    is_young = np.asarray(w.grid.log10ages) < 7.0
+    assert is_young.any() and (~is_young).any()
+    assert np.all(young[~is_young] == 0) and np.all(old[is_young] == 0)
+    # keys without dust keep the single-sum form
+    assert build_tables(w.grid, em, "reprocessed", w.filters)["kappa_birth"] is None
+    with pytest.raises(NotImplementedError):
+        BimodalPacmanEmission(grid=w.grid, dust_curve_ism=Calzetti2000(), dust_curve_birth=Calzetti2000(), fesc=0.1)
+
+
 def test_non_geometric_axis_is_rejected():
     with pytest.raises(ValueError, match="constant-R"):
         geometric_ratio(np.linspace(1000.0, 2000.0, 100))
