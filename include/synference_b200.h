@@ -109,6 +109,17 @@ typedef struct sb2_model_desc {
    * both attenuated: young by exp(-tau_v_birth * kappa_birth - tau_v * kappa), old by exp(-tau_v * kappa).
    * kappa_birth is on the same padded axis as kappa.  NULL: component 2 is unattenuated (escaped light).          */
   const float* kappa_birth;
+  /* Optional dust emission with energy balance (spectrum "total" of PacmanEmission / TotalEmission / BimodalPacmanEmission
+   * with a Greybody / Blackbody generator: min_example.py:110-120, final_library_generation_multinode.py:489-497):
+   *   L_total(nu) = L_emergent(nu) + E_abs * g(nu),  E_abs = trapezoid over nu of (unattenuated - attenuated) light.
+   * dust_wnu: the trapezoid weights (Hz / 1e14) on the same padded axis as kappa; dust_g: g(nu) * 1e14 on the n_lam axis (it
+   * must vanish where the IGM acts); dust_duv[m][f] = sum_i dust_g[i] * (U_f, V_f)[i + m] for every integer redshift shift
+   * m < dust_m_len: the emission's contribution to the filter numerators per unit E_abs.  With dust emission every
+   * wavelength chunk is multiplied (the reduction needs the whole axis).  NULL: none.                                   */
+  const float* dust_wnu;
+  const float* dust_g;
+  const float* dust_duv;
+  int32_t dust_m_len;
   const double* fm_log_tab;
   const double* fm_exp_tab;
   const double* fm_tail_tab;

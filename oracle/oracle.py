@@ -345,9 +345,23 @@ def weights_for(gal, log10ages, metallicities):
     return sfzh_weights(sf, zd)
 
 
+def dust_emission_shape(lam, kind="Greybody", temperature=40.0, emissivity=1.5):
+    """A5 pin: the generator's L_nu, nu^beta B_nu(T) (beta = 0 for a Blackbody), normalised to unit integral over all
+    frequencies -- here by numerical quadrature in x = h nu / k T (the product uses the closed form Gamma * zeta)."""
+    from scipy.integrate import quad
+    beta = 0.0 if kind == "Blackbody" else float(emissivity)
+    h_over_k = 6.62607015e-34 / 1.380649e-23
+    nu = 2.99792458e18 / np.asarray(lam, dtype=float)
+    x = h_over_k * nu / float(temperature)
+    with np.errstate(over="ignore", under="ignore"):
+        f = x ** (3.0 + beta) / np.expm1(x)
+    norm = quad(lambda t: t ** (3.0 + beta) / math.expm1(t) if t < 700 else 0.0, 0.0, 700.0, epsabs=0, epsrel=1e-12, limit=400)[0]
+    return f / norm * (h_over_k / float(temperature))
+
+
 def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, key="intrinsic",
                fesc=0.0, fesc_ly_alpha=1.0, dust=None, igm=None, variant="nu", base_mass=1e9,
-               return_spectra=False, dl_cm=None, two_screens=None):
+               return_spectra=False, dl_cm=None, two_screens=None, dust_emission=None):
     """Fluxes [nJy] of every galaxy through every filter at ``base_mass`` Msun.
 
     galaxies : list of dicts with redshift, tau_v, sfh_kind, sfh (dict, ages in yr),
@@ -359,6 +373,8 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
     dust     : None or dict(curve=..., slope=..., ampl=...)  ;  igm : None or (laf, dla)
     two_screens : None or dict(age_pivot=log10 yr, dust_birth=dict(...)): stars with log10age < age_pivot are attenuated by
                exp(-tau_v_birth kappa_birth - tau_v kappa), the others by exp(-tau_v kappa) (galaxy key tau_v_birth)
+    dust_emission : None or dict(kind=, temperature=, emissivity=): adds E_abs * shape(nu), E_abs = trapezoid over nu of the
+               light the screen(s) removed (energy balance, A5 'total')
     """
     lam = np.asarray(lam, dtype=float)
     g_att, g_un = emission_parts(components, lam, key, fesc, fesc_ly_alpha)
@@ -368,6 +384,8 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
     if two_screens is not None:
         kappa_birth = dust_kappa(lam, **two_screens["dust_birth"])
         young = (np.repeat(np.asarray(log10ages)[:, None], nz, 1) < two_screens["age_pivot"]).reshape(-1)
+    dust_shape = dust_emission_shape(lam, **dust_emission) if dust_emission is not None else None
+    nu_rest = 2.99792458e18 / lam
     out = np.zeros((len(galaxies), len(filters)))
     spectra = np.zeros((len(galaxies), len(lam))) if return_spectra else None
     for g, gal in enumerate(galaxies):
@@ -378,6 +396,7 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
             g_att2, g_un2 = ga.reshape(na * nz, -1), gu.reshape(na * nz, -1)
         lnu = w @ g_un2  # A4: grid-weighted sum, erg/s/Hz per Msun
         att = w @ g_att2
+        before_dust = att
         if kappa is not None:
             kap = kappa
             if "dust_slope" in gal or "dust_ampl" in gal:
@@ -390,6 +409,9 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
                     + (w * ~young) @ g_att2 * np.exp(-gal.get("tau_v", 0.0) * kap)
             else:
                 att = att * np.exp(-gal.get("tau_v", 0.0) * kap)
+        if dust_shape is not None and kappa is not None:
+            e_abs = -np.trapezoid(before_dust - att, nu_rest)          # nu decreases along the axis
+            att = att + e_abs * dust_shape
         lnu = (lnu + att) * base_mass
         z = float(gal["redshift"])
         dl = luminosity_distance_cm(z) if dl_cm is None else dl_cm[g]

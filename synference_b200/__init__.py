@@ -8,7 +8,7 @@ the inference / training half of the reference is out of scope and not re-export
 from .units import (Angstrom, Gyr, Jy, Msun, Myr, Quantity, Unit, mJy, nJy, uJy, um, unyt_array,  # noqa: F401
                     unyt_quantity, yr)
 from .cosmology import FlatLambdaCDM, Planck18  # noqa: F401
-from .parametric import (SFH, Calzetti2000, EmergentEmission, EmissionModel, Filter, FilterCollection,  # noqa: F401
+from .parametric import (SFH, Blackbody, Calzetti2000, Greybody, EmergentEmission, EmissionModel, Filter, FilterCollection,  # noqa: F401
                          Grid, IncidentEmission, Instrument, IntrinsicEmission, PacmanEmission, BimodalPacmanEmission, PowerLaw,
                          SFHArray, TotalEmission, ZDist, ZDistArray)
 from .igm import Inoue14  # noqa: F401

@@ -42,6 +42,7 @@ class ModelDesc(C.Structure):
         ("base_mass", C.c_double), ("max_batch", C.c_int64),
         ("dust_d0", _fp), ("dust_l2", _fp),
         ("lya_line", _dp), ("lya_bin", C.c_int32), ("kappa_birth", _fp),
+        ("dust_wnu", _fp), ("dust_g", _fp), ("dust_duv", _fp), ("dust_m_len", C.c_int32),
         ("fm_log_tab", _dp), ("fm_exp_tab", _dp), ("fm_tail_tab", _dp), ("fm_tail_n", C.c_int32), ("fm_tail_w", C.c_double),
     ]
 

@@ -167,6 +167,7 @@ struct sb2_model {
   double* lya_line = nullptr;   // per-galaxy Lyman-alpha escape (optional)
   float* g_lya = nullptr;
   float *kappa_birth = nullptr, *g_taub = nullptr;   // second dust screen (optional)
+  float *dust_wnu = nullptr, *dust_g = nullptr, *dust_duv = nullptr, *e_part = nullptr;   // dust emission (optional)
   int *filt_lo = nullptr, *filt_hi = nullptr;
   double *bin_pow = nullptr, *thr = nullptr, *pre = nullptr;
   int *nline = nullptr, *lc_on = nullptr;
@@ -238,7 +239,7 @@ int sb2_device_count(void) {
 int sb2_model_destroy(sb2_model* m) {
   if (!m) return SB2_OK;
   cudaSetDevice(m->device);
-  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->dust_d0, m->dust_l2, m->g_slope, m->g_ampl, m->lya_line, m->g_lya, m->kappa_birth, m->g_taub, m->filt_uv, m->filt_lo,
+  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->dust_d0, m->dust_l2, m->g_slope, m->g_ampl, m->lya_line, m->g_lya, m->kappa_birth, m->g_taub, m->dust_wnu, m->dust_g, m->dust_duv, m->e_part, m->filt_uv, m->filt_lo,
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage, m->fm_log, m->fm_exp, m->fm_tail,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
                   m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params[0],
@@ -308,6 +309,15 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
       std::vector<float> tb(kap.size(), 0.f);
       std::memcpy(tb.data(), d->kappa_birth, tb.size() * sizeof(float));
       UP(kappa_birth, tb.data(), tb.size());
+    }
+    if (d->dust_wnu) {
+      if (!d->kappa || !d->dust_g || !d->dust_duv || d->dust_m_len < 1) {
+        sb2_model_destroy(m);
+        return fail(SB2_ERR_INVALID, "dust_wnu needs kappa, dust_g, dust_duv and dust_m_len");
+      }
+      UP(dust_wnu, d->dust_wnu, kap.size());
+      UP(dust_g, d->dust_g, (size_t)d->n_lam);
+      UP(dust_duv, d->dust_duv, (size_t)d->dust_m_len * d->n_filt * 2);
     }
     if (d->dust_d0 && d->dust_l2) {
       if (!d->kappa) { sb2_model_destroy(m); return fail(SB2_ERR_INVALID, "dust_d0/dust_l2 need kappa"); }
@@ -386,6 +396,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   if (m->dust_d0) { AL(g_slope, np * 4); AL(g_ampl, np * 4); }
   if (m->lya_line) { AL(g_lya, np * 4); }
   if (m->kappa_birth) { AL(g_taub, np * 4); }
+  if (m->dust_wnu) { AL(e_part, (size_t)sb2::kMaxGroups * np * 4); }
   AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
   AL(keys, np * 4); AL(keys_sorted, np * 4); AL(perm_pad, np * 4); AL(tile_k0, (np / 128) * 4); AL(grp, (3 * kMaxGroups + 1) * 4);
   AL(g_mscale, np * 8); AL(g_trunc, np * 4); AL(zpow, np * 13 * 8);
@@ -518,7 +529,7 @@ int launch_synth2(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t 
 int launch_synth(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
   const int nf = m->d.n_filt, c = m->d.n_comp;
   const bool spec = a.out_spec != nullptr;
-  const bool pg = a.dust_d0 != nullptr || a.g_lya != nullptr || a.kappa_birth != nullptr;   // per-galaxy emission extras: their own instantiation
+  const bool pg = a.dust_d0 != nullptr || a.g_lya != nullptr || a.kappa_birth != nullptr || a.wnu != nullptr;   // per-galaxy emission extras: their own instantiation
 #define SB2_PICK(C, NF)                                                                                             \
   (pg ? (spec ? launch_synth_t<C, NF, true, true>(m, a, grid, delta, st) : launch_synth_t<C, NF, false, true>(m, a, grid, delta, st)) \
       : (spec ? launch_synth_t<C, NF, true, false>(m, a, grid, delta, st) : launch_synth_t<C, NF, false, false>(m, a, grid, delta, st)))
@@ -586,7 +597,7 @@ int check_params(const sb2_model* m, const sb2_params* p) {
 int rows_per_unit(const sb2_model* m, bool delta) {
   // The CTA-pair kernel (synth2_kernel) is parity-tested but not yet faster than the single-CTA kernel on B200
   // (both sit on the same synchronisation/epilogue floor); it is opt-in: SB2_CTA_PAIR=1.
-  return (delta && m->smem2_bytes > 0 && !m->dust_d0 && !m->lya_line && !m->kappa_birth && std::getenv("SB2_CTA_PAIR")) ? 256 : 128;
+  return (delta && m->smem2_bytes > 0 && !m->dust_d0 && !m->lya_line && !m->kappa_birth && !m->dust_wnu && std::getenv("SB2_CTA_PAIR")) ? 256 : 128;
 }
 // Rows the grouped layout of a batch of n galaxies can occupy (every group is padded to whole units).
 long long padded_rows(const sb2_model* m, long long n, bool delta) {
@@ -698,7 +709,8 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   if (!flux_base && !flux_scaled && !spec_out) return fail(SB2_ERR_INVALID, "no output requested");
   CU_TRY(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = run_prep(m, p, nullptr, true, spec_out != nullptr, st)) != SB2_OK) return rc;
+  // (spectra and the absorbed-energy sum of the dust emission need every wavelength chunk, not just the filters')
+  if ((rc = run_prep(m, p, nullptr, true, spec_out != nullptr || m->dust_wnu != nullptr, st)) != SB2_OK) return rc;
   const sb2_model_desc& d = m->d;
   sb2::SynthArgs a{};
   const bool delta = delta_mode(m, p);
@@ -716,6 +728,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.tile_range = m->tile_range;
   a.dust_d0 = m->dust_d0; a.dust_l2 = m->dust_l2; a.g_slope = m->g_slope; a.g_ampl = m->g_ampl;
   a.g_lya = m->g_lya; a.lya_bin = d.lya_bin; a.kappa_birth = m->kappa_birth; a.g_taub = m->g_taub;
+  a.wnu = m->dust_wnu; a.e_part = m->e_part;
   a.kappa = m->kappa; a.filt_uv = reinterpret_cast<const float2*>(m->filt_uv); a.igm = m->igm;
   a.g_m = m->g_m; a.g_beta = m->g_beta; a.g_gamma = m->g_gamma; a.g_taut = m->g_taut; a.g_scale = m->g_scale; a.g_ca = m->g_ca;
   a.g_cb = m->g_cb; a.g_orig = m->g_orig; a.g_mscale = m->g_mscale; a.g_trunc = m->g_trunc;
@@ -739,6 +752,12 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
     fa.g_beta = m->g_beta; fa.g_gamma = m->g_gamma; fa.g_scale = m->g_scale; fa.g_ca = m->g_ca; fa.g_orig = m->g_orig;
     fa.g_mscale = m->g_mscale; fa.g_trunc = m->g_trunc; fa.out_base = flux_base; fa.out_scaled = flux_scaled;
     for (int f = 0; f < d.n_filt; ++f) { fa.filt_su[f] = m->h_su[f]; fa.filt_sdv[f] = m->h_sdv[f]; }
+    fa.e_part = m->dust_wnu ? m->e_part : nullptr; fa.dust_duv = reinterpret_cast<const float2*>(m->dust_duv); fa.dust_g = m->dust_g;
+    fa.g_m = m->g_m; fa.dust_m_len = d.dust_m_len; fa.n_lam = d.n_lam; fa.out_spec = spec_out;
+    if (spec_out && fa.e_part) {
+      sb2::dust_spec_kernel<<<(unsigned)((a.n_rows + 7) / 8), 256, 0, st>>>(fa, a.n_tiles_dev, rpu);
+      STAGE_CHECK("dust_spec_kernel", st);
+    }
     if (flux_base || flux_scaled) {
       sb2::finalize_kernel<<<(unsigned)((a.n_rows + 255) / 256), 256, 0, st>>>(fa, a.n_tiles_dev, rpu);
       STAGE_CHECK("finalize_kernel", st);

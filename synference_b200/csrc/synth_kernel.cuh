@@ -79,6 +79,8 @@ struct SynthArgs {
   const float* g_ampl;
   const float* kappa_birth;  // second screen (young population): nullptr = component 2 is unattenuated
   const float* g_taub;
+  const float* wnu;          // dust emission: trapezoid weights in frequency for the absorbed-energy sum; nullptr: none
+  float* e_part;             // [kMaxGroups][n_rows] each epilogue group's share of sum_i (unattenuated - attenuated)_i wnu_i
   const float* g_lya;        // per-galaxy Lyman-alpha line term, added to the first component at bin lya_bin; nullptr: none
   int lya_bin;
   const float2* filt_uv;     // padded tables, uv_len entries
@@ -123,6 +125,21 @@ __device__ __forceinline__ void ffma2_bcast(float2& acc, float s, float2 uv) {
 __device__ __forceinline__ float4 dust_shape(float4 k, float4 d, float4 l, float slope, float ampl) {
   return make_float4(fmaf(ampl, d.x, k.x) * ex2_approx(slope * l.x), fmaf(ampl, d.y, k.y) * ex2_approx(slope * l.y),
                      fmaf(ampl, d.z, k.z) * ex2_approx(slope * l.z), fmaf(ampl, d.w, k.w) * ex2_approx(slope * l.w));
+}
+
+// 1 - 2^y given T = ex2(y): the series where 1 - T would cancel (small optical depths), so that the absorbed energy of a
+// nearly transparent galaxy keeps float32 relative accuracy.  (y > 0 happens: the pinned Calzetti curve is extrapolated
+// linearly beyond 2.2 um and goes negative there, SURVEY A6 -- "absorption" is then negative, as in the reference.)
+__device__ __forceinline__ float one_minus_ex2(float y, float T) {
+  const float t = y * 0.6931471805599453f;
+  float p = fmaf(t, 2.48015873e-5f, 1.98412698e-4f);
+  p = fmaf(p, t, 1.38888889e-3f);
+  p = fmaf(p, t, 8.33333333e-3f);
+  p = fmaf(p, t, 4.16666667e-2f);
+  p = fmaf(p, t, 1.66666667e-1f);
+  p = fmaf(p, t, 0.5f);
+  p = fmaf(p, t, 1.f);
+  return fabsf(y) < 1.f ? -t * p : 1.f - T;
 }
 
 // Chunk visiting order: ascending.  (Walking the chunks cyclically from a different start per CTA, to keep SMs that work
@@ -173,6 +190,8 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
       const float lya = (pg_dust && A.g_lya != nullptr) ? A.g_lya[row] : 0.f;
       const bool two_screens = pg_dust && kComp == 2 && A.kappa_birth != nullptr;
       const float ntaub = two_screens ? -A.g_taub[row] : 0.f;
+      const bool absorbed = pg_dust && A.wnu != nullptr;   // energy balance: what the dust removes, summed over the axis
+      float e_abs = 0.f;
       // redshift-shift range of this warp's real galaxies (padding rows follow the others)
       int mmin = orig >= 0 ? m : INT_MAX, mmax = orig >= 0 ? m : INT_MIN;
 #pragma unroll
@@ -205,6 +224,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
           const int i0 = c * kLch + sub * 32;
           const bool last_sub = (sub == kSub - 1) || (i0 + 32 >= A.n_lam);
           float s[32];
+          float e_sub = 0.f;   // absorbed energy of this sub-chunk (blocked summation: 4 -> 32 -> axis)
           {
             // (prefetching the next sub-chunk's TMEM columns behind the filter work was measured 6% SLOWER: the
             //  tcgen05.ld latency is already covered by the other epilogue group on the same scheduler)
@@ -233,16 +253,29 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
                                              __ldg(reinterpret_cast<const float4*>(A.dust_l2 + i0) + j4), slope, ampl);
                 if (two_screens) {   // young: birth cloud + ISM, old: ISM only (both components are attenuated)
                   const float4 b4 = __ldg(reinterpret_cast<const float4*>(A.kappa_birth + i0) + j4);
-                  s[4 * j4 + 0] = ca * (__uint_as_float(v[4 * j4 + 0]) * ex2_approx(fmaf(ntaub, b4.x, ntaut * k4.x))) + cb * (__uint_as_float(u[4 * j4 + 0]) * ex2_approx(ntaut * k4.x));
-                  s[4 * j4 + 1] = ca * (__uint_as_float(v[4 * j4 + 1]) * ex2_approx(fmaf(ntaub, b4.y, ntaut * k4.y))) + cb * (__uint_as_float(u[4 * j4 + 1]) * ex2_approx(ntaut * k4.y));
-                  s[4 * j4 + 2] = ca * (__uint_as_float(v[4 * j4 + 2]) * ex2_approx(fmaf(ntaub, b4.z, ntaut * k4.z))) + cb * (__uint_as_float(u[4 * j4 + 2]) * ex2_approx(ntaut * k4.z));
-                  s[4 * j4 + 3] = ca * (__uint_as_float(v[4 * j4 + 3]) * ex2_approx(fmaf(ntaub, b4.w, ntaut * k4.w))) + cb * (__uint_as_float(u[4 * j4 + 3]) * ex2_approx(ntaut * k4.w));
+                  const float4 w4 = absorbed ? __ldg(reinterpret_cast<const float4*>(A.wnu + i0) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  float e4 = 0.f;
+#define SB2_TS(q, K, B, W) { const float yo = ntaut * (K), yy = fmaf(ntaub, (B), yo), To = ex2_approx(yo), Ty = ex2_approx(yy); \
+                             const float vy = ca * __uint_as_float(v[4 * j4 + q]), vo = cb * __uint_as_float(u[4 * j4 + q]); \
+                             s[4 * j4 + q] = vy * Ty + vo * To; \
+                             if (absorbed) e4 = fmaf(fmaf(vy, one_minus_ex2(yy, Ty), vo * one_minus_ex2(yo, To)), (W), e4); }
+                  SB2_TS(0, k4.x, b4.x, w4.x) SB2_TS(1, k4.y, b4.y, w4.y) SB2_TS(2, k4.z, b4.z, w4.z) SB2_TS(3, k4.w, b4.w, w4.w)
+#undef SB2_TS
+                  e_sub += e4;
                   continue;
                 }
                 s[4 * j4 + 0] = ca * (__uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x)) + cb * __uint_as_float(u[4 * j4 + 0]);
                 s[4 * j4 + 1] = ca * (__uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y)) + cb * __uint_as_float(u[4 * j4 + 1]);
                 s[4 * j4 + 2] = ca * (__uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z)) + cb * __uint_as_float(u[4 * j4 + 2]);
                 s[4 * j4 + 3] = ca * (__uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w)) + cb * __uint_as_float(u[4 * j4 + 3]);
+                if (absorbed) {
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.wnu + i0) + j4);
+                  float e4 = ca * __uint_as_float(v[4 * j4 + 0]) * one_minus_ex2(ntaut * k4.x, ex2_approx(ntaut * k4.x)) * w4.x;
+                  e4 = fmaf(ca * __uint_as_float(v[4 * j4 + 1]) * one_minus_ex2(ntaut * k4.y, ex2_approx(ntaut * k4.y)), w4.y, e4);
+                  e4 = fmaf(ca * __uint_as_float(v[4 * j4 + 2]) * one_minus_ex2(ntaut * k4.z, ex2_approx(ntaut * k4.z)), w4.z, e4);
+                  e4 = fmaf(ca * __uint_as_float(v[4 * j4 + 3]) * one_minus_ex2(ntaut * k4.w, ex2_approx(ntaut * k4.w)), w4.w, e4);
+                  e_sub += e4;
+                }
               }
             } else {
               tmem_ld_wait();
@@ -264,9 +297,18 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
                 s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y);
                 s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z);
                 s[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w);
+                if (absorbed) {   // (the lone component's coefficient is applied with the final scale, like the fluxes')
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.wnu + i0) + j4);
+                  float e4 = __uint_as_float(v[4 * j4 + 0]) * one_minus_ex2(ntaut * k4.x, ex2_approx(ntaut * k4.x)) * w4.x;
+                  e4 = fmaf(__uint_as_float(v[4 * j4 + 1]) * one_minus_ex2(ntaut * k4.y, ex2_approx(ntaut * k4.y)), w4.y, e4);
+                  e4 = fmaf(__uint_as_float(v[4 * j4 + 2]) * one_minus_ex2(ntaut * k4.z, ex2_approx(ntaut * k4.z)), w4.z, e4);
+                  e4 = fmaf(__uint_as_float(v[4 * j4 + 3]) * one_minus_ex2(ntaut * k4.w, ex2_approx(ntaut * k4.w)), w4.w, e4);
+                  e_sub += e4;
+                }
               }
             }
           }
+          e_abs += e_sub;
           if (last_sub) {  // all TMEM reads of this accumulator are done: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -350,6 +392,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
 #pragma unroll
       for (int f = 0; f < kNF; ++f)
         if (f < A.n_filt) A.part[((size_t)grp * A.n_filt + f) * A.n_rows + row] = acc[f];
+      if (absorbed) A.e_part[(size_t)grp * A.n_rows + row] = e_abs;
     }
   }
 }
@@ -713,8 +756,21 @@ struct FinalizeArgs {
   const unsigned* g_trunc;
   float* out_base;
   double* out_scaled;
+  const float* e_part;       // dust emission (nullptr: none): absorbed-energy partials of the epilogue groups,
+  const float2* dust_duv;    // [dust_m_len][n_filt] filter numerators of the emission per unit absorbed energy, by shift m
+  const float* dust_g;       // [n_lam] the emission's spectrum per unit absorbed energy (spectra output)
+  const int* g_m;
+  int dust_m_len, n_lam;
+  float* out_spec;
   float filt_su[kMaxFilt], filt_sdv[kMaxFilt];
 };
+
+// absorbed energy of a row: the epilogue groups' partials in fixed order
+__device__ __forceinline__ float absorbed_energy(const FinalizeArgs& A, long long row) {
+  float e = 0.f;
+  for (int g = 0; g < A.n_groups; ++g) e += A.e_part[(size_t)g * A.n_rows + row];
+  return e;
+}
 
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs A, const int* __restrict__ n_units_dev,
                                                        int rows_per_unit) {
@@ -727,6 +783,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   const float sc = (A.n_comp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row];
   const unsigned trunc = A.g_trunc[row];
   const double mscale = A.g_mscale[row];
+  float e_abs = 0.f;
+  const float2* duv = nullptr;
+  if (A.e_part != nullptr) {
+    e_abs = absorbed_energy(A, row);
+    const int m = A.g_m[row];
+    if (m >= 0 && m < A.dust_m_len) duv = A.dust_duv + (size_t)m * A.n_filt;   // beyond: no filter reaches the axis any more
+  }
   // a galaxy's n_filt fluxes are contiguous in the output: build them four at a time and store 16 bytes at once
   // (the rows land in the caller's galaxy order, i.e. scattered -- scalar stores would touch each 32-byte sector 8x)
   const bool vec = (A.n_filt % 4) == 0 && ((reinterpret_cast<uintptr_t>(A.out_base) | reinterpret_cast<uintptr_t>(A.out_scaled)) & 15) == 0;
@@ -741,6 +804,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
         for (int g = 0; g < A.n_groups; ++g) {   // fixed order: plane g holds the chunks with c % n_groups == g
           const float2 a = A.part[((size_t)g * A.n_filt + f) * A.n_rows + row];
           nu += a.x; nv += a.y;
+        }
+        if (duv != nullptr) {
+          const float2 dd = __ldg(duv + f);
+          nu = fmaf(e_abs, dd.x, nu); nv = fmaf(e_abs, dd.y, nv);
         }
         float flux = fmaf(beta, nv, gamma * nu) / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * sc;
         if ((trunc >> f) & 1u) flux = __int_as_float(0x7fc00000);
@@ -762,6 +829,23 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
           if (A.out_scaled) A.out_scaled[(size_t)orig * A.n_filt + f0 + q] = (double)fl[q] * mscale;
         }
     }
+  }
+}
+
+// Spectra output with dust emission: out_spec[galaxy][i] += E_abs * g_i * scale (the emission vanishes where the IGM acts,
+// so it is added after the fact).  One block per 8 rows, threads along the wavelength axis.
+__global__ void __launch_bounds__(256) dust_spec_kernel(const __grid_constant__ FinalizeArgs A, const int* __restrict__ n_units_dev,
+                                                        int rows_per_unit) {
+  const long long rows = n_units_dev ? min(A.n_rows, (long long)__ldg(n_units_dev) * rows_per_unit) : A.n_rows;
+  for (int r = 0; r < 8; ++r) {
+    const long long row = (long long)blockIdx.x * 8 + r;
+    if (row >= rows) return;
+    const int orig = A.g_orig[row];
+    if (orig < 0) continue;
+    const float sc = (A.n_comp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row];
+    const float e = absorbed_energy(A, row) * sc;
+    float* o = A.out_spec + (size_t)orig * A.n_lam;
+    for (int i = threadIdx.x; i < A.n_lam; i += blockDim.x) o[i] = fmaf(e, __ldg(A.dust_g + i), o[i]);
   }
 }
 

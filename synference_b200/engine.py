@@ -96,6 +96,42 @@ def geometric_ratio(lam):
     return q
 
 
+DUST_W0 = 1.0e14      # Hz: keeps the float32 trapezoid weights and the emission's shape near 1
+
+
+def _dust_emission_tables(generator, lam, n_pad, uv, lo_l, hi_l, off_l, n_blue):
+    """Energy balance: ``total = emergent + E_abs g(nu)`` with ``E_abs`` the trapezoid over frequency of what the
+    screen removed.  The kernel forms ``E_abs`` per galaxy (``dust_wnu``); since the filter sums are linear, the emission's
+    share of every filter numerator is ``E_abs`` times a function of the integer redshift shift m only, tabulated here in
+    float64: ``dust_duv[m][f] = sum_i g_i (U_f, V_f)[i + m]``."""
+    n_lam = lam.size
+    nu = 2.99792458e18 / lam
+    w = np.empty(n_lam)
+    w[1:-1] = 0.5 * (nu[:-2] - nu[2:])
+    w[0], w[-1] = 0.5 * (nu[0] - nu[1]), 0.5 * (nu[-2] - nu[-1])
+    wnu = np.zeros(n_pad, dtype=np.float32)
+    wnu[:n_lam] = w / DUST_W0
+    g = np.asarray(generator.shape(lam), dtype=np.float64) * DUST_W0
+    if n_blue > 0:
+        if g[:n_blue].max() > 1e-30 * g.max():
+            raise NotImplementedError("the dust emission is not negligible at wavelengths the IGM absorbs; the batched path "
+                                      "adds it after the IGM step")
+        g[:n_blue] = 0.0
+    g32 = g.astype(np.float32).astype(np.float64)    # what the spectra path adds; the filter tables use the same values
+    m_len = int(max(hi_l)) + 3
+    n_filt = len(lo_l)
+    ends = list(off_l[1:]) + [uv.shape[0]]
+    pad = m_len + max(e - o for o, e in zip(off_l, ends))
+    gpad = np.concatenate([np.zeros(pad), g32, np.zeros(pad)])
+    duv = np.zeros((m_len, n_filt, 2))
+    for f, (lo, o, e) in enumerate(zip(lo_l, off_l, ends)):
+        win = np.lib.stride_tricks.sliding_window_view(gpad, e - o)
+        rows = win[pad + lo - 2 - np.arange(m_len)]            # row m: g[lo-2-m+k], k = 0..len-1   (n = i + m)
+        duv[:, f, :] = rows @ uv[o:e].astype(np.float64)
+    return dict(dust_wnu=wnu, dust_g=np.ascontiguousarray(g32, dtype=np.float32),
+                dust_duv=np.ascontiguousarray(duv, dtype=np.float32), dust_m_len=m_len)
+
+
 def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, filters: FilterCollection,
                  cosmo=Planck18, igm=True, variant="nu", z_table_max=100.0):
     """All float64 host-side derivations behind ``sb2_model_desc`` (kept as numpy arrays)."""
@@ -198,6 +234,15 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         # travels as coef_att (SynthEngine._fill)
         single_is_unatt=(n_comp == 1 and not has_att),
     )
+    if igm:
+        laf, dla = (igm if isinstance(igm, tuple) else (_igm.INOUE14_LAF, _igm.INOUE14_DLA))
+        tables["igm"] = _igm.device_tables(lam, laf, dla)
+    else:
+        tables["igm"] = None
+    tables.update(dust_wnu=None, dust_g=None, dust_duv=None, dust_m_len=0)
+    if getattr(emission_model, "has_dust_emission", lambda k: False)(emission_key) and kap is not None and not dust_free:
+        tables.update(_dust_emission_tables(emission_model.dust_emission, lam, n_chunk * lch, uv, lo_l, hi_l, off_l,
+                                            tables["igm"]["n_blue"] if tables["igm"] is not None else 0))
     lya = getattr(emission_model, "lya_line", lambda k: None)(emission_key)
     if lya is not None:
         # the line sits in the first grid of every recipe, i.e. in the kernel's component A, except when that grid is
@@ -207,11 +252,6 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         tables["lya_bin"] = int(lya_bin)
     else:
         tables["lya_line"], tables["lya_bin"] = None, 0
-    if igm:
-        laf, dla = (igm if isinstance(igm, tuple) else (_igm.INOUE14_LAF, _igm.INOUE14_DLA))
-        tables["igm"] = _igm.device_tables(lam, laf, dla)
-    else:
-        tables["igm"] = None
     tab = cosmo.table(z_max=z_table_max)
     tables["cosmo"] = tab
     return tables
@@ -254,6 +294,8 @@ class SynthEngine:
         d.dust_d0, d.dust_l2 = ptr(t["dust_d0"], C.c_float), ptr(t["dust_l2"], C.c_float)
         d.lya_line, d.lya_bin = ptr(t["lya_line"], C.c_double), int(t["lya_bin"])
         d.kappa_birth = ptr(t["kappa_birth"], C.c_float)
+        d.dust_wnu, d.dust_g = ptr(t["dust_wnu"], C.c_float), ptr(t["dust_g"], C.c_float)
+        d.dust_duv, d.dust_m_len = ptr(t["dust_duv"], C.c_float), int(t["dust_m_len"])
         d.filt_lo, d.filt_hi = ptr(t["filt_lo"], C.c_int32), ptr(t["filt_hi"], C.c_int32)
         d.filt_off, d.filt_uv = ptr(t["filt_off"], C.c_int32), ptr(t["filt_uv"], C.c_float)
         d.filt_uv_len = int(t["filt_uv"].shape[0])

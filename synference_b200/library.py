@@ -441,10 +441,18 @@ class GalaxyBasis:
         dust = em.dust_curve
         info = {
             "Model/grid_name": self.grid.grid_name, "Model/grid_dir": str(self.grid.grid_dir),
-            "Model/emission_model": type(em).__name__, "Model/fesc": float(em.fesc),
-            "Model/fesc_ly_alpha": float(em.fesc_ly_alpha),
+            "Model/emission_model": type(em).__name__,
+            # a string names a per-galaxy emitter parameter (the reference's convention), a number is global
+            "Model/fesc": em.fesc if isinstance(em.fesc, str) else float(em.fesc),
+            "Model/fesc_ly_alpha": em.fesc_ly_alpha if isinstance(em.fesc_ly_alpha, str) else float(em.fesc_ly_alpha),
             "Model/dust_law": None if dust is None else dust.name,
             "Model/dust_params": None if dust is None else dict(dust.params),
+            # dust emission generator, as library.py:2070-2074 records it (name, parameter keys / values / units)
+            "Model/dust_emission": None if em.dust_emission is None else type(em.dust_emission).__name__,
+            "Model/dust_emission_keys": None if em.dust_emission is None else ["temperature", "emissivity"],
+            "Model/dust_emission_values": None if em.dust_emission is None else [em.dust_emission.temperature,
+                                                                                 em.dust_emission.emissivity],
+            "Model/dust_emission_units": None if em.dust_emission is None else ["K", "dimensionless"],
             "Model/cosmology": repr(self.cosmo), "Model/instrument": self.instrument.label,
             "Model/filter_codes": list(self.instrument.filters.filter_codes),
             "Model/sfh_type": self.params and int(self.params.sfh_type),

@@ -616,6 +616,41 @@ class Instrument:
 
 
 # --------------------------------------------------------------------------
+# Dust emission generators (min_example.py:110, generate_library_basic.py:195)
+# --------------------------------------------------------------------------
+_H_OVER_K = 4.799243073366221e-11      # h / k_B  [K s]
+_C_ANGSTROM = 2.99792458e18            # c [A / s]
+
+
+class Greybody:
+    """Optically thin modified blackbody ``nu^emissivity B_nu(T)``, normalised to unit integral over ALL frequencies
+    (energy balance: the emission model scales it by the energy the dust absorbed).  ``shape(lam)`` is in 1/Hz."""
+
+    def __init__(self, temperature, emissivity=1.5, **kwargs):
+        self.temperature = float(strip_units(temperature))
+        self.emissivity = float(strip_units(emissivity))
+        if not self.temperature > 0:
+            raise ValueError("dust temperature must be positive")
+
+    def shape(self, lam):
+        from scipy.special import gamma, zeta
+        nu = _C_ANGSTROM / np.asarray(lam, dtype=np.float64)
+        x = _H_OVER_K * nu / self.temperature
+        p = 3.0 + self.emissivity
+        with np.errstate(over="ignore", under="ignore"):
+            f = x ** p / np.expm1(x)                       # -> 0 in the Wien tail (expm1 overflows to inf)
+        return f / (gamma(p + 1.0) * zeta(p + 1.0)) * (_H_OVER_K / self.temperature)     # d nu = (kT/h) dx
+
+    def same_as(self, other):
+        return type(other) is type(self) and other.temperature == self.temperature and other.emissivity == self.emissivity
+
+
+class Blackbody(Greybody):
+    def __init__(self, temperature, **kwargs):
+        super().__init__(temperature, emissivity=0.0)
+
+
+# --------------------------------------------------------------------------
 # Emission models (SURVEY A5)
 # --------------------------------------------------------------------------
 
@@ -659,8 +694,9 @@ class EmissionModel:
         # nearest 1216 A is scaled per galaxy; grids are lowered without it and lya_line() hands the kernel that value
         self.lya_per_galaxy = isinstance(fesc_ly_alpha, str)
         self.lya_name = fesc_ly_alpha if self.lya_per_galaxy else None
-        if dust_emission is not None:
-            raise NotImplementedError("dust emission / energy balance is not in the batched path yet")
+        if dust_emission is not None and not hasattr(dust_emission, "shape"):
+            raise NotImplementedError(f"dust emission generator {type(dust_emission).__name__}: only Greybody / Blackbody "
+                                      "(a fixed spectral shape scaled by energy balance) are in the batched path")
 
     # reference hooks (library.py:2506, 2512) - bookkeeping only
     def set_per_particle(self, flag):
@@ -683,6 +719,10 @@ class EmissionModel:
     _PER_GALAXY = {"incident": (None, "one"), "transmitted": (None, "1-f"), "nebular": (None, "1-f"),
                    "reprocessed": (None, "1-f"), "escaped": (None, "f"), "intrinsic": ("1-f", "f"),
                    "attenuated": ("1-f", None), "emergent": ("1-f", "f"), "total": ("1-f", "f")}
+
+    def has_dust_emission(self, key):
+        """'total' = 'emergent' + the generator's spectrum scaled to the energy the screen(s) removed (A5)."""
+        return key == "total" and self.dust_emission is not None and self.dust_curve is not None
 
     def dust_free(self, key):
         """True when the first grid of ``recipe(key)`` must NOT be attenuated (per-galaxy fesc, 'intrinsic':
@@ -772,19 +812,20 @@ class BimodalPacmanEmission(EmissionModel):
         for c in (dust_curve_ism, dust_curve_birth):
             if getattr(c, "per_galaxy", False):
                 raise NotImplementedError("per-galaxy dust-curve shape together with two screens is not in the batched path yet")
-        super().__init__(grid, fesc=0.0, fesc_ly_alpha=fesc_ly_alpha, dust_curve=dust_curve_ism, tau_v=tau_v_ism, **kwargs)
+        if (dust_emission_ism is None) != (dust_emission_birth is None) or (
+                dust_emission_ism is not None and not getattr(dust_emission_ism, "same_as", lambda o: False)(dust_emission_birth)):
+            raise NotImplementedError("two dust screens re-emitting with DIFFERENT generators need two absorbed-energy sums; "
+                                      "the batched path has one (every reference script passes the same generator twice)")
+        super().__init__(grid, fesc=0.0, fesc_ly_alpha=fesc_ly_alpha, dust_curve=dust_curve_ism, tau_v=tau_v_ism,
+                         dust_emission=dust_emission_ism, **kwargs)
         self.dust_curve_birth = dust_curve_birth
         self.tau_v_ism_name, self.tau_v_birth_name = tau_v_ism, tau_v_birth
         self.age_pivot = float(strip_units(age_pivot))
-        # dust emission is accepted and ignored up to 'emergent'; 'total' (which adds it) is refused in recipe()
-        self._has_dust_emission = dust_emission_ism is not None or dust_emission_birth is not None
 
     def two_screens(self, key):
         return key in ("attenuated", "emergent", "total")
 
     def recipe(self, key):
-        if key == "total" and self._has_dust_emission:
-            raise NotImplementedError("dust emission / energy balance is not in the batched path yet; use 'emergent'")
         att, un = super().recipe(key)
         if not self.two_screens(key):
             return att, un

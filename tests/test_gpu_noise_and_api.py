@@ -315,3 +315,28 @@ def test_bimodal_emission_model_through_the_api(tmp_path):
                         igm=(I.INOUE14_LAF, I.INOUE14_DLA),
                         two_screens=dict(age_pivot=7.0, dust_birth=dict(curve="Calzetti2000")))
     assert_flux_close(got, want)
+
+
+def test_total_spectrum_with_dust_emission_through_create_mock_library(tmp_path):
+    """emission_model_key="total" with a Greybody (min_example.py:110-120, the key every production script asks for) through
+    create_mock_library: library photometry against the oracle's energy-balance form, generator recorded under Model/."""
+    from oracle import adapter as A
+    from synference_b200.utils import read_container
+    n = 60
+    basis, d, grid, inst, _ = _small_basis(n, tmp_path)
+    em = S.PacmanEmission(grid=grid, fesc=0.1, fesc_ly_alpha=0.1, dust_curve=S.Calzetti2000(),
+                          dust_emission=S.Greybody(temperature=40.0, emissivity=1.5))
+    b = S.GalaxyBasis("total_basis", d["redshift"], grid, em, basis.sfhs, basis.metal_dists, galaxy_params={"tau_v": d["tau_v"]},
+                      instrument=inst, redshift_dependent_sfh=True, build_library=False)
+    masses = np.asarray(d["masses"], dtype=float)
+    b.create_mock_library(log_stellar_masses=list(masses), emission_model_key="total", out_name="total_lib",
+                          out_dir=str(tmp_path), n_proc=1, overwrite=True, batch_size=64)
+    lib = S.load_library_from_hdf5(os.path.join(str(tmp_path), "total_lib.hdf5"))
+    want = O.synthesize(A.galaxies_from_params(b.params), grid.log10ages, grid.metallicity, np.asarray(grid.lam), grid.spectra,
+                        [(f.lam, f.t) for f in inst.filters], key="emergent", fesc=0.1, fesc_ly_alpha=0.1,
+                        dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA),
+                        dust_emission=dict(kind="Greybody", temperature=40.0, emissivity=1.5))
+    assert_flux_close(lib["photometry"].T, O.scale_to_mass(want, masses))
+    _, attrs = read_container(os.path.join(str(tmp_path), "total_lib.hdf5"))
+    assert attrs["Model/dust_emission"] == "Greybody" and list(attrs["Model/dust_emission_values"]) == [40.0, 1.5]
+    assert attrs["Model/emission_model_key"] == "total"

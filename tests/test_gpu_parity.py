@@ -461,6 +461,65 @@ def test_two_screen_birth_cloud_and_ism_attenuation(key):
     eng.close(); plain.close()
 
 
+@pytest.mark.parametrize("model", ["pacman_fesc", "pacman_one_component", "blackbody_total_emission", "bimodal"])
+def test_dust_emission_with_energy_balance(model):
+    """Spectrum 'total' (the key of every production script): emergent light plus a Greybody / Blackbody scaled to the energy
+    the dust screen(s) removed (min_example.py:110-120, generate_library_basic.py:195, generate_library_full.py:217-231).
+    The kernel sums the absorbed energy over the WHOLE axis per galaxy; photometry and spectra against the oracle."""
+    from synference_b200.parametric import (BimodalPacmanEmission, Blackbody, Calzetti2000, Greybody, PacmanEmission,
+                                            TotalEmission)
+    n = 200
+    w = make_workload("cfg2", n)
+    okw = dict(fesc=0.0, fesc_ly_alpha=1.0, two_screens=None)
+    if model == "pacman_fesc":
+        em = PacmanEmission(grid=w.grid, fesc=0.1, fesc_ly_alpha=0.5, dust_curve=Calzetti2000(), dust_emission=Greybody(40.0, 1.5))
+        okw.update(fesc=0.1, fesc_ly_alpha=0.5, dust_emission=dict(kind="Greybody", temperature=40.0, emissivity=1.5))
+    elif model == "pacman_one_component":
+        em = PacmanEmission(grid=w.grid, fesc=0.0, fesc_ly_alpha=0.5, dust_curve=Calzetti2000(), dust_emission=Greybody(40.0, 1.5))
+        okw.update(fesc_ly_alpha=0.5, dust_emission=dict(kind="Greybody", temperature=40.0, emissivity=1.5))
+    elif model == "blackbody_total_emission":
+        em = TotalEmission(grid=w.grid, dust_curve=Calzetti2000(), dust_emission_model=Blackbody(temperature=35.0))
+        okw.update(dust_emission=dict(kind="Blackbody", temperature=35.0))
+    else:
+        gen = Greybody(40.0, 1.5)
+        em = BimodalPacmanEmission(grid=w.grid, dust_curve_ism=Calzetti2000(), dust_curve_birth=Calzetti2000(), age_pivot=7.0,
+                                   dust_emission_ism=gen, dust_emission_birth=Greybody(40.0, 1.5), fesc_ly_alpha=0.1)
+        okw.update(fesc_ly_alpha=0.1, dust_emission=dict(kind="Greybody", temperature=40.0, emissivity=1.5),
+                   two_screens=dict(age_pivot=7.0, dust_birth=dict(curve="Calzetti2000")))
+    eng = SynthEngine(w.grid, em, "total", w.filters, max_batch=4096)
+    assert eng.n_comp == (1 if model in ("pacman_one_component", "blackbody_total_emission") else 2)
+    p = w.params.slice(slice(0, n))
+    p.redshift = p.redshift.copy()
+    p.redshift[:40] = np.linspace(0.02, 1.5, 40)       # where the MIRI bands sit on the emission's Wien tail
+    gals_extra = {}
+    if model == "bimodal":
+        p.tau_v_birth = np.random.default_rng(4).uniform(0.0, 3.0, n)
+        gals_extra = dict(tau_v_birth=p.tau_v_birth)
+    got = eng.photometry(p, scaled=False)
+    spec = eng.spectra(p).astype(np.float64)
+    gals = A.galaxies_from_params(p)
+    for k, v in gals_extra.items():
+        for g, x in zip(gals, v):
+            g[k] = float(x)
+    lam = np.asarray(w.grid.lam)
+    filt = [(f.lam, f.t) for f in w.filters]
+    want, spec_want = O.synthesize(gals, w.grid.log10ages, w.grid.metallicity, lam, w.grid.spectra, filt, key="emergent",
+                                   dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA), return_spectra=True, **okw)
+    assert_flux_close(got, want)
+    ok = spec_want > 1e-25 * spec_want.max(axis=1, keepdims=True)
+    assert np.max(np.abs(spec[ok] - spec_want[ok]) / spec_want[ok]) < FLUX_RTOL
+    # the emission matters in this test: without it the reddest band of the nearby galaxies is visibly fainter
+    okw.pop("dust_emission")
+    bare = O.synthesize(gals[:40], w.grid.log10ages, w.grid.metallicity, lam, w.grid.spectra, filt, key="emergent",
+                        dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA), **okw)
+    assert np.max(want[:40, -1] / bare[:, -1]) > 1.05
+    # 'emergent' of the same model is untouched by the generator
+    eng2 = SynthEngine(w.grid, em, "emergent", w.filters, max_batch=4096)
+    assert eng2.tables["dust_wnu"] is None
+    np.testing.assert_allclose(eng2.photometry(p, scaled=False)[:40], bare, rtol=FLUX_RTOL)
+    eng.close(); eng2.close()
+
+
 def test_populations_larger_than_max_batch_stream_through_both_slots():
     """SynthEngine.photometry walks a population batch by batch through the two staging slots (submit / wait): the
     result is bit-identical to one big batch, for both output types."""

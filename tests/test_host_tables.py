@@ -173,6 +173,41 @@ def test_two_screen_layout():
         BimodalPacmanEmission(grid=w.grid, dust_curve_ism=Calzetti2000(), dust_curve_birth=Calzetti2000(), fesc=0.1)
 
 
+def test_dust_emission_tables():
+    """Greybody shape (closed-form normalisation vs the oracle's quadrature), trapezoid weights in frequency, and the per-shift
+    filter table: dust_duv[m][f] must equal the filter numerators of the emission's spectrum shifted by m bins."""
+    from synference_b200.engine import DUST_W0
+    from synference_b200.parametric import Calzetti2000, Greybody, PacmanEmission
+    w = make_workload("cfg2", 4)
+    em = PacmanEmission(grid=w.grid, fesc=0.1, dust_curve=Calzetti2000(), dust_emission=Greybody(40.0, 1.5))
+    t = build_tables(w.grid, em, "total", w.filters)
+    lam = np.asarray(w.grid.lam)
+    nl = len(lam)
+    shape = O.dust_emission_shape(lam, kind="Greybody", temperature=40.0, emissivity=1.5)
+    g = t["dust_g"].astype(np.float64) / DUST_W0
+    big = shape > 1e-20 * shape.max()
+    np.testing.assert_allclose(g[big], shape[big], rtol=1e-6)
+    flat = np.ones(nl)
+    nu = 2.99792458e18 / lam
+    assert float(t["dust_wnu"][:nl].astype(np.float64) @ flat) * DUST_W0 == pytest.approx(nu[0] - nu[-1], rel=1e-6)
+    assert np.all(t["dust_wnu"][nl:] == 0) and np.all(t["dust_g"][:t["igm"]["n_blue"]] == 0)
+    duv = t["dust_duv"].reshape(t["dust_m_len"], t["n_filt"], 2).astype(np.float64)
+    uv = t["filt_uv"].astype(np.float64)
+    for f in (0, 7, t["n_filt"] - 1):
+        lo, off = int(t["filt_lo"][f]), int(t["filt_off"][f])
+        end = int(t["filt_off"][f + 1]) if f + 1 < t["n_filt"] else uv.shape[0]
+        for m in (0, 1, 250, 1400, t["dust_m_len"] - 1):
+            num = np.zeros(2)
+            for k in range(end - off):
+                i = lo - 2 + k - m                   # table entry k is the sample n = lo - 2 + k = i + m
+                if 0 <= i < nl:
+                    num += t["dust_g"][i].astype(np.float64) * uv[off + k]
+            np.testing.assert_allclose(duv[m, f], num, rtol=1e-6, atol=1e-30)
+    assert build_tables(w.grid, em, "emergent", w.filters)["dust_wnu"] is None
+    with pytest.raises(NotImplementedError):
+        PacmanEmission(grid=w.grid, dust_curve=Calzetti2000(), dust_emission=object())
+
+
 def test_non_geometric_axis_is_rejected():
     with pytest.raises(ValueError, match="constant-R"):
         geometric_ratio(np.linspace(1000.0, 2000.0, 100))
