@@ -214,6 +214,34 @@ int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, 
                              uint64_t seed, uint64_t epoch, double norm_mag_limit, double* out_flux,
                              double* out_sigma, float* out_feat, void* stream);
 
+/* ---- Spectroscopic training path (cfg 5): library spectrum -> instrument-frame pixels ------------------------------
+ * Replaces the per-galaxy Python loop of SBI_Fitter.create_feature_array_from_raw_spectra (sbi_runner.py:1322-1334) over
+ * transform_spectrum (utils.py:185-254): redshift the axis, convolve with the per-pixel Gaussian of
+ * convolve_variable_width_gaussian (utils.py:129-182; sigma from the instrument's R(lambda) in quadrature with the model's,
+ * in units of the MEDIAN pixel of the redshifted axis, truncated at ceil(trunc*sigma), nearest-edge padding, sigma <= 0.01
+ * copies), then the flux-conserving rebin of `spectres` onto observed_wave (pixels not fully covered get `fill`).        */
+typedef struct sb2_resample_desc {
+  int32_t n_lam, n_px, n_res;
+  const double* theory_wave;   /* [n_lam] rest-frame wavelengths of the library spectra, increasing                */
+  const double* observed_wave; /* [n_px]  pixel centres of the instrument, same unit, increasing                   */
+  const double* res_wave;      /* [n_res] resolution curve abscissa (observed frame)                               */
+  const double* res_r;         /* [n_res] R = lambda / FWHM                                                        */
+  const double* theory_r;      /* [n_lam] resolution of the model spectra, or NULL: theory_r_scalar (inf = none)  */
+  double theory_r_scalar;
+  double trunc;                /* 4.0 in the reference                                                             */
+  double fill;                 /* 0.0 in the reference                                                             */
+} sb2_resample_desc;
+typedef struct sb2_resampler sb2_resampler;
+int sb2_resampler_create(const sb2_resample_desc* desc, int device, sb2_resampler** out);
+int sb2_resampler_destroy(sb2_resampler* r);
+/* spectra: device float32 [n][n_lam] (one row per galaxy, as sb2_synth_photometry's spec_out); redshift: device float64 [n];
+ * out: device float32 [n][n_px].  A non-finite or <= -1 redshift gives a NaN row.                                        */
+int sb2_resample_spectra(sb2_resampler* r, const float* spectra, const double* redshift, int64_t n, float* out, void* stream);
+/* Same with HOST buffers (synchronous; copies in, runs, copies out). */
+int sb2_resample_spectra_host(sb2_resampler* r, const float* spectra, const double* redshift, int64_t n, float* out);
+/* Device time [ms] of the most recent sb2_resample_spectra call on this resampler (blocks until it has finished). */
+int sb2_resample_last_ms(sb2_resampler* r, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -427,6 +427,77 @@ def synthesize(galaxies, log10ages, metallicities, lam, components, filters, *, 
     return (out, spectra) if return_spectra else out
 
 
+# --------------------------------------------------------------------------------------
+# Spectroscopic path: utils.py:129-182 variable-width Gaussian, utils.py:185-254 transform_spectrum.
+# The flux-conserving rebin is the third-party `spectres` package (Carnall 2017, arXiv:1705.05165; not installed
+# here, unpinned): bin edges at the midpoints of the wavelengths, end bins symmetric about their centres; a new bin is
+# the old bins' fluxes weighted by the overlapping widths; new bins not fully covered get `fill`.
+# --------------------------------------------------------------------------------------
+def spectres_bins(wavs):
+    wavs = np.asarray(wavs, dtype=float)
+    edges = np.empty(wavs.size + 1)
+    edges[0] = wavs[0] - (wavs[1] - wavs[0]) / 2
+    edges[-1] = wavs[-1] + (wavs[-1] - wavs[-2]) / 2
+    edges[1:-1] = (wavs[1:] + wavs[:-1]) / 2
+    return edges, np.diff(edges)
+
+
+def spectres_resample(new_wavs, spec_wavs, spec_fluxes, fill=0.0):
+    old_edges, old_widths = spectres_bins(spec_wavs)
+    new_edges, _ = spectres_bins(new_wavs)
+    flux = np.asarray(spec_fluxes, dtype=float)
+    out = np.full(len(new_wavs), float(fill))
+    start = stop = 0
+    for j in range(len(new_wavs)):
+        if new_edges[j] < old_edges[0] or new_edges[j + 1] > old_edges[-1]:
+            continue
+        while old_edges[start + 1] <= new_edges[j]:
+            start += 1
+        while old_edges[stop + 1] < new_edges[j + 1]:
+            stop += 1
+        if stop == start:
+            out[j] = flux[start]
+            continue
+        w = old_widths[start:stop + 1].copy()
+        w[0] *= (old_edges[start + 1] - new_edges[j]) / (old_edges[start + 1] - old_edges[start])
+        w[-1] *= (new_edges[j + 1] - old_edges[stop]) / (old_edges[stop + 1] - old_edges[stop])
+        out[j] = np.sum(w * flux[start:stop + 1]) / np.sum(w)
+    return out
+
+
+def convolve_variable_width_gaussian(flux, sigma_pixels, trunc=4.0):
+    """utils.py:129-182: per output pixel its own normalised Gaussian (sigma in pixels, truncated at ceil(trunc sigma)),
+    nearest-edge padding, pixels with sigma <= 0.01 copied."""
+    flux = np.asarray(flux, dtype=float)
+    n = flux.size
+    out = np.empty(n)
+    for i in range(n):
+        sg = float(sigma_pixels[i])
+        if sg <= 0.01:
+            out[i] = flux[i]
+            continue
+        hw = int(np.ceil(sg * trunc))
+        x = np.arange(-hw, hw + 1)
+        k = np.exp(-0.5 * (x / sg) ** 2)
+        k /= k.sum()
+        out[i] = np.dot(flux[np.clip(i + x, 0, n - 1)], k)
+    return out
+
+
+def transform_spectrum(theory_wave, theory_flux, z, observed_wave, resolution_curve_wave, resolution_curve_r,
+                       theory_r=np.inf, trunc_constant=4.0):
+    """utils.py:185-254: redshift the axis, smooth to the instrument's R(lambda) (in quadrature with the model's own
+    resolution; sigma in pixels uses the MEDIAN pixel width of the redshifted axis), rebin to the observed pixels."""
+    wz = np.asarray(theory_wave, dtype=float) * (1 + z)
+    c = 2 * np.sqrt(2 * np.log(2))
+    s_inst = wz / np.interp(wz, resolution_curve_wave, resolution_curve_r) / c
+    r_th = np.full_like(wz, theory_r) if np.ndim(theory_r) == 0 else np.asarray(theory_r, dtype=float)
+    s_th = wz / r_th / c
+    s_pix = np.sqrt(np.maximum(s_inst**2 - s_th**2, 0.0)) / np.median(np.diff(wz))
+    conv = convolve_variable_width_gaussian(theory_flux, s_pix, trunc=trunc_constant)
+    return np.asarray(observed_wave), spectres_resample(observed_wave, wz, conv, fill=0.0)
+
+
 def scale_to_mass(flux_base, log_mass, log_base_mass=9.0):
     """library.py:4588-4609  photometry cast to float32, then multiplied by the float64 mass ratio."""
     scale = 10.0 ** np.asarray(log_mass, dtype=float) / 10.0**log_base_mass

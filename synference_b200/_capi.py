@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = (
     "sb2_last_error", "sb2_device_count", "sb2_model_create", "sb2_model_destroy", "sb2_build_weights",
     "sb2_synth_photometry", "sb2_synth_photometry_host", "sb2_depth_noise_features", "sb2_last_stage_ms", "sb2_wait_debug",
     "sb2_synth_photometry_host_submit", "sb2_synth_photometry_host_wait",
+    "sb2_resampler_create", "sb2_resampler_destroy", "sb2_resample_spectra", "sb2_resample_spectra_host", "sb2_resample_last_ms",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -60,6 +61,14 @@ class Params(C.Structure):
     ]
 
 
+class ResampleDesc(C.Structure):
+    _fields_ = [
+        ("n_lam", C.c_int32), ("n_px", C.c_int32), ("n_res", C.c_int32),
+        ("theory_wave", _dp), ("observed_wave", _dp), ("res_wave", _dp), ("res_r", _dp), ("theory_r", _dp),
+        ("theory_r_scalar", C.c_double), ("trunc", C.c_double), ("fill", C.c_double),
+    ]
+
+
 _lib = None
 
 
@@ -93,6 +102,11 @@ def load():
     lib.sb2_depth_noise_features.argtypes = [
         C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_uint64,
         C.c_uint64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sb2_resampler_create.argtypes = [C.POINTER(ResampleDesc), C.c_int, C.POINTER(C.c_void_p)]
+    lib.sb2_resampler_destroy.argtypes = [C.c_void_p]
+    lib.sb2_resample_spectra.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.sb2_resample_spectra_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.sb2_resample_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 

@@ -15,6 +15,7 @@
 #include "../../include/synference_b200.h"
 #include "noise_kernel.cuh"
 #include "prep_kernel.cuh"
+#include "resample_kernel.cuh"
 #include "synth_kernel.cuh"
 
 namespace {
@@ -909,6 +910,178 @@ int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, 
     sb2::depth_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
   }
   CU_TRY(cudaGetLastError());
+  return SB2_OK;
+}
+
+// ---- spectroscopic path -------------------------------------------------------------------------------------------
+struct sb2_resampler {
+  int device = 0, n_sm = 148;
+  sb2::ResampleArgs a{};
+  double *old_edges = nullptr, *new_edges = nullptr;
+  float *lam = nullptr, *lam_k = nullptr, *qth2 = nullptr, *res_wave = nullptr, *res_r = nullptr, *res_slope = nullptr;
+  int *edge_lut = nullptr, *res_lut = nullptr;
+  size_t smem = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool ev_valid = false;
+  float* stage_in = nullptr; double* stage_z = nullptr; float* stage_out = nullptr;   // host-buffer form
+  long long stage_n = 0;
+};
+
+static void spectres_edges(const double* w, int n, std::vector<double>& e) {   // bin edges as `spectres` makes them
+  e.resize((size_t)n + 1);
+  e[0] = w[0] - (w[1] - w[0]) / 2;
+  e[n] = w[n - 1] + (w[n - 1] - w[n - 2]) / 2;
+  for (int i = 1; i < n; ++i) e[i] = (w[i] + w[i - 1]) / 2;
+}
+
+int sb2_resampler_create(const sb2_resample_desc* d, int device, sb2_resampler** out) {
+  if (!d || !out) return fail(SB2_ERR_INVALID, "null argument");
+  if (d->n_lam < 3 || d->n_px < 2 || d->n_res < 1 || !d->theory_wave || !d->observed_wave || !d->res_wave || !d->res_r)
+    return fail(SB2_ERR_INVALID, "resampler: need >= 3 model wavelengths, >= 2 pixels and a resolution curve");
+  for (int i = 1; i < d->n_lam; ++i)
+    if (!(d->theory_wave[i] > d->theory_wave[i - 1])) return fail(SB2_ERR_INVALID, "theory_wave must increase");
+  for (int i = 1; i < d->n_px; ++i)
+    if (!(d->observed_wave[i] > d->observed_wave[i - 1])) return fail(SB2_ERR_INVALID, "observed_wave must increase");
+  for (int i = 1; i < d->n_res; ++i)
+    if (!(d->res_wave[i] > d->res_wave[i - 1])) return fail(SB2_ERR_INVALID, "resolution curve abscissa must increase");
+  for (int i = 0; i < d->n_res; ++i)
+    if (!(d->res_r[i] > 0)) return fail(SB2_ERR_INVALID, "resolution R must be positive");
+  if (!(d->trunc > 0)) return fail(SB2_ERR_INVALID, "trunc must be positive");
+  CU_TRY(cudaSetDevice(device));
+  sb2_resampler* r = new sb2_resampler();
+  r->device = device;
+  cudaDeviceGetAttribute(&r->n_sm, cudaDevAttrMultiProcessorCount, device);
+  std::vector<double> oe, ne, diff((size_t)d->n_lam - 1);
+  spectres_edges(d->theory_wave, d->n_lam, oe);
+  spectres_edges(d->observed_wave, d->n_px, ne);
+  for (int i = 0; i + 1 < d->n_lam; ++i) diff[i] = d->theory_wave[i + 1] - d->theory_wave[i];
+  std::sort(diff.begin(), diff.end());
+  const size_t nd = diff.size();
+  const double med = (nd & 1) ? diff[nd / 2] : 0.5 * (diff[nd / 2 - 1] + diff[nd / 2]);   // np.median
+  std::vector<float> lam(d->n_lam), lam_k(d->n_lam), qth2(d->n_lam), rw(d->n_res), rr(d->n_res), rs(std::max(d->n_res - 1, 1), 0.f);
+  const double fwhm = 2.0 * std::sqrt(2.0 * std::log(2.0));
+  for (int i = 0; i < d->n_lam; ++i) {
+    lam[i] = (float)d->theory_wave[i];
+    // the reference divides with where=pixel_scale != 0 -> sigma 0
+    lam_k[i] = med > 0 ? (float)(d->theory_wave[i] / (med * fwhm)) : 0.f;
+    const double rt = d->theory_r ? d->theory_r[i] : d->theory_r_scalar;
+    qth2[i] = (float)(1.0 / (rt * rt));        // inf -> 0
+  }
+  for (int i = 0; i < d->n_res; ++i) { rw[i] = (float)d->res_wave[i]; rr[i] = (float)d->res_r[i]; }
+  for (int i = 0; i + 1 < d->n_res; ++i) rs[i] = (float)((d->res_r[i + 1] - d->res_r[i]) / (d->res_wave[i + 1] - d->res_wave[i]));
+  int rc = SB2_OK;
+#define RUP(dst, src, n) if (rc == SB2_OK) rc = upload(&r->dst, src, (size_t)(n));
+  RUP(old_edges, oe.data(), oe.size());
+  RUP(new_edges, ne.data(), ne.size());
+  RUP(lam, lam.data(), lam.size());
+  RUP(lam_k, lam_k.data(), lam_k.size());
+  RUP(qth2, qth2.data(), qth2.size());
+  RUP(res_wave, rw.data(), rw.size());
+  RUP(res_r, rr.data(), rr.size());
+  RUP(res_slope, rs.data(), rs.size());
+  // search tables over uniform steps of log2(wavelength): entry b = last node at or below the left end of bucket b
+  auto make_lut = [](const double* x, int n, int buckets, std::vector<int>& lut, float& u0, float& inv_du) {
+    const double a = std::log2(x[0]), b = std::log2(x[n - 1]);
+    const double du = (b - a) / buckets;
+    u0 = (float)a; inv_du = (float)(1.0 / du);
+    lut.resize(buckets);
+    int k = 0;
+    for (int i = 0; i < buckets; ++i) {
+      // (a shade to the left of the bucket's nominal end, so that float rounding of u0 / inv_du cannot overshoot)
+      const double left = std::exp2(a + (i - 0.5) * du);
+      while (k + 1 < n && x[k + 1] <= left) ++k;
+      lut[i] = k;
+    }
+  };
+  std::vector<int> elut, rlut;
+  sb2::ResampleArgs& a = r->a;
+  if (oe[0] > 0 && !std::getenv("SB2_RESAMPLE_BSEARCH")) {
+    make_lut(oe.data(), d->n_lam + 1, 4 * d->n_lam, elut, a.lut_u0, a.lut_inv_du);
+    RUP(edge_lut, elut.data(), elut.size());
+    a.lut_n = (int)elut.size();
+    if (d->n_res >= 2 && d->res_wave[0] > 0) {
+      make_lut(d->res_wave, d->n_res, 16 * d->n_res, rlut, a.res_u0, a.res_inv_du);
+      RUP(res_lut, rlut.data(), rlut.size());
+      a.res_lut_n = (int)rlut.size();
+    }
+  }
+#undef RUP
+  if (rc == SB2_OK && (cudaEventCreate(&r->ev[0]) != cudaSuccess || cudaEventCreate(&r->ev[1]) != cudaSuccess))
+    rc = fail(SB2_ERR_CUDA, "cudaEventCreate");
+  a.edge_lut = r->edge_lut; a.res_lut = r->res_lut;
+  a.n_lam = d->n_lam; a.n_px = d->n_px; a.n_res = d->n_res;
+  a.old_edges = r->old_edges; a.new_edges = r->new_edges; a.lam = r->lam; a.lam_k = r->lam_k; a.qth2 = r->qth2;
+  a.res_wave = r->res_wave; a.res_r = r->res_r; a.res_slope = r->res_slope;
+  a.trunc = (float)d->trunc; a.fill = (float)d->fill;
+  // staging: the contributing bins (at most the whole axis) plus 2 * h_cap taps, plus the smoothed bins
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  a.h_cap = 512;
+  r->smem = ((size_t)2 * d->n_lam + 2 * (size_t)a.h_cap) * sizeof(float);
+  if (rc == SB2_OK && r->smem > (size_t)max_smem - 1024) rc = fail(SB2_ERR_INVALID, "resampler: model axis too long for one CTA's shared memory");
+  if (rc == SB2_OK && cudaFuncSetAttribute(sb2::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r->smem) != cudaSuccess)
+    rc = fail(SB2_ERR_CUDA, "cudaFuncSetAttribute(resample_kernel)");
+  if (rc != SB2_OK) { sb2_resampler_destroy(r); return rc; }
+  *out = r;
+  return SB2_OK;
+}
+
+int sb2_resampler_destroy(sb2_resampler* r) {
+  if (!r) return SB2_OK;
+  cudaSetDevice(r->device);
+  void* ptrs[] = {r->old_edges, r->new_edges, r->lam, r->lam_k, r->qth2, r->res_wave, r->res_r, r->res_slope, r->edge_lut, r->res_lut, r->stage_in, r->stage_z, r->stage_out};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& e : r->ev) if (e) cudaEventDestroy(e);
+  delete r;
+  return SB2_OK;
+}
+
+int sb2_resample_spectra(sb2_resampler* r, const float* spectra, const double* redshift, int64_t n, float* out, void* stream) {
+  if (!r || !spectra || !redshift || !out) return fail(SB2_ERR_INVALID, "null argument");
+  if (n < 0) return fail(SB2_ERR_INVALID, "negative n");
+  if (n == 0) return SB2_OK;
+  CU_TRY(cudaSetDevice(r->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  sb2::ResampleArgs a = r->a;
+  a.spectra = spectra; a.redshift = redshift; a.out = out; a.n = n;
+  // persistent grid: whole waves of the CTAs that fit on the SMs
+  int per_sm = 1;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb2::resample_kernel, sb2::kResampleThreads, r->smem));
+  const long long grid = std::min<long long>(n, (long long)r->n_sm * std::max(per_sm, 1));
+  cudaEventRecord(r->ev[0], st);
+  sb2::resample_kernel<<<(unsigned)grid, sb2::kResampleThreads, r->smem, st>>>(a);
+  CU_TRY(cudaGetLastError());
+  cudaEventRecord(r->ev[1], st);
+  r->ev_valid = true;
+  return SB2_OK;
+}
+
+int sb2_resample_last_ms(sb2_resampler* r, float* ms) {
+  if (!r || !ms) return fail(SB2_ERR_INVALID, "null argument");
+  if (!r->ev_valid) return fail(SB2_ERR_INVALID, "no sb2_resample_spectra call to time");
+  CU_TRY(cudaEventSynchronize(r->ev[1]));
+  CU_TRY(cudaEventElapsedTime(ms, r->ev[0], r->ev[1]));
+  return SB2_OK;
+}
+
+int sb2_resample_spectra_host(sb2_resampler* r, const float* spectra, const double* redshift, int64_t n, float* out) {
+  if (!r || !spectra || !redshift || !out) return fail(SB2_ERR_INVALID, "null argument");
+  if (n < 0) return fail(SB2_ERR_INVALID, "negative n");
+  if (n == 0) return SB2_OK;
+  CU_TRY(cudaSetDevice(r->device));
+  if (n > r->stage_n) {
+    for (void* p : {(void*)r->stage_in, (void*)r->stage_z, (void*)r->stage_out}) if (p) cudaFree(p);
+    r->stage_in = nullptr; r->stage_z = nullptr; r->stage_out = nullptr; r->stage_n = 0;
+    CU_TRY(cudaMalloc(&r->stage_in, (size_t)n * r->a.n_lam * sizeof(float)));
+    CU_TRY(cudaMalloc(&r->stage_z, (size_t)n * sizeof(double)));
+    CU_TRY(cudaMalloc(&r->stage_out, (size_t)n * r->a.n_px * sizeof(float)));
+    r->stage_n = n;
+  }
+  CU_TRY(cudaMemcpy(r->stage_in, spectra, (size_t)n * r->a.n_lam * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(r->stage_z, redshift, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  int rc = sb2_resample_spectra(r, r->stage_in, r->stage_z, n, r->stage_out, nullptr);
+  if (rc != SB2_OK) return rc;
+  CU_TRY(cudaMemcpy(out, r->stage_out, (size_t)n * r->a.n_px * sizeof(float), cudaMemcpyDeviceToHost));
   return SB2_OK;
 }
 

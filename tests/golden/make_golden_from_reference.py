@@ -133,6 +133,29 @@ def main():
     d = draw(pr, N=100, rng=42, unlog_keys=["masses"])
     for k, v in d.items():
         g[f"lhc_{k}"] = np.asarray(v)
+    # ---- spectroscopic path (utils.py:129-254): the convolution is the reference's own loop (numba decorator dropped);
+    #      transform_spectrum is the reference's own function with `spectres` (third party, not installed) served by the
+    #      oracle's restatement of its published algorithm -- that half stays unpinned.
+    from oracle import oracle as ORC
+    conv = lift(os.path.join(REF, "utils.py"), "convolve_variable_width_gaussian")
+    sp_ns = types.SimpleNamespace(spectres=lambda new_wavs, spec_wavs, spec_fluxes, fill=0.0, verbose=False:
+                                  ORC.spectres_resample(new_wavs, spec_wavs, spec_fluxes, fill=fill))
+    transform = lift(os.path.join(REF, "utils.py"), "transform_spectrum",
+                     extra={"convolve_variable_width_gaussian": conv, "spectres": sp_ns, "Union": None, "Tuple": None})
+    rs = np.random.default_rng(17)
+    tw = 0.05 * (1 + 0.5 / 300) ** np.arange(3000)                       # um, constant-R axis (utils.py:284-287)
+    tf = np.abs(rs.normal(1.0, 0.3, tw.size)) * (tw / 1.0) ** 0.5
+    tf[rs.integers(0, tw.size, 25)] *= 8.0                                # narrow lines
+    sig = np.concatenate([np.zeros(5), rs.uniform(0.0, 9.0, tw.size - 5)])
+    g["sp_wave"], g["sp_flux"], g["sp_sigma_pix"] = tw, tf, sig
+    g["sp_conv"] = conv(tf, sig, 4.0)
+    ow = np.linspace(0.6, 5.3, 700)
+    rw = np.linspace(0.5, 5.5, 60)
+    rr = 30.0 + 270.0 * ((rw - 0.5) / 5.0) ** 1.5                         # PRISM-like R(lambda) 30 -> 300
+    g["sp_obs_wave"], g["sp_res_wave"], g["sp_res_r"] = ow, rw, rr
+    g["sp_z"] = np.array([0.0, 0.7, 3.2, 9.5, 14.0])
+    g["sp_out"] = np.stack([transform(tw, tf, float(z), ow, rw, rr)[1] for z in g["sp_z"]])
+    g["sp_out_r1000"] = transform(tw, tf, 2.0, ow, rw, rr, theory_r=1000.0)[1]
     np.savez(OUT, **g)
     print("wrote", OUT, {k: np.shape(v) for k, v in g.items()})
 

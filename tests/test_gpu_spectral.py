@@ -1,0 +1,158 @@
+"""GPU parity tests for the spectroscopic path: the resample kernel, called through the C ABI, against
+(1) golden vectors produced by the reference's own transform_spectrum / convolve_variable_width_gaussian
+(tests/golden/make_golden_from_reference.py) and (2) the float64 oracle on seeded inputs.
+
+Tolerance (floating point, stated here as the contract asks): the kernel works in float32 (library spectra are stored in
+float32; the reference's own smoothed array is float32 too for such input), so |got - want| <= 2e-5 |want| + 2e-6 max|row|.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from synference_b200.spectral import SpectrumResampler, create_feature_array_from_raw_spectra, transform_spectrum
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_noise_golden.npz"))
+RTOL, ATOL_REL = 2e-5, 2e-6
+
+
+def close(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape
+    tol = RTOL * np.abs(want) + ATOL_REL * np.abs(want).max(axis=-1, keepdims=True)
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), f"{bad.sum()} of {bad.size} pixels off; worst {np.max(np.abs(got - want) / (np.abs(want) + 1e-300)):.3e}"
+
+
+def test_golden_vectors_from_the_reference_function():
+    plan = SpectrumResampler(G["sp_wave"], G["sp_obs_wave"], G["sp_res_wave"], G["sp_res_r"])
+    zs = G["sp_z"]
+    got = plan.transform(np.repeat(G["sp_flux"][None, :], len(zs), 0), zs)
+    close(got, G["sp_out"])
+    assert ((got == 0) == (G["sp_out"] == 0)).all()                    # the same pixels are left at `fill`
+    plan.close()
+    plan = SpectrumResampler(G["sp_wave"], G["sp_obs_wave"], G["sp_res_wave"], G["sp_res_r"], theory_r=1000.0)
+    close(plan.transform(G["sp_flux"][None, :], np.array([2.0])), G["sp_out_r1000"][None, :])
+    plan.close()
+    # the reference-signature entry point, one spectrum per call
+    w, f = transform_spectrum(G["sp_wave"], G["sp_flux"], 0.7, G["sp_obs_wave"], G["sp_res_wave"], G["sp_res_r"])
+    assert w is G["sp_obs_wave"] or np.array_equal(w, G["sp_obs_wave"])
+    close(f[None, :], G["sp_out"][1][None, :])
+
+
+def _axes(n_lam=3790, n_px=1000):
+    tw = 0.04 * (1 + 0.5 / 300) ** np.arange(n_lam)                    # um; cfg 2's constant-R axis to ~22 um
+    ow = np.linspace(0.6, 5.3, n_px)
+    rw = np.linspace(0.55, 5.4, 80)
+    rr = 30.0 + 270.0 * ((rw - 0.55) / 4.85) ** 1.3                    # PRISM-like 30 -> 300
+    return tw, ow, rw, rr
+
+
+def test_random_batch_matches_oracle_including_edges():
+    tw, ow, rw, rr = _axes()
+    rng = np.random.default_rng(5)
+    n = 24
+    spec = (np.abs(rng.normal(1.0, 0.4, (n, tw.size))) * (tw / 0.5) ** rng.uniform(-1, 2, (n, 1))).astype(np.float32)
+    spec[:, rng.integers(0, tw.size, 40)] *= 6.0
+    spec[3, :900] = 0.0                                                   # a Lyman-break style dropout
+    z = rng.uniform(0.0, 12.0, n)
+    z[:6] = (0.0, 14.5, 25.0, 0.01, 7.0, 200.0)                           # partially covered, barely covered, not covered
+    plan = SpectrumResampler(tw, ow, rw, rr)
+    got = plan.transform(spec, z)
+    want = np.stack([O.transform_spectrum(tw, spec[i].astype(np.float64), z[i], ow, rw, rr)[1] for i in range(n)])
+    close(got, want)
+    assert (got[5] == 0).all() and (got[2] == 0).any() and (got[0] > 0).all()
+    assert plan.last_ms() > 0
+    # unusable redshifts give NaN rows and leave the neighbours alone
+    zb = z.copy()
+    zb[[1, 8]] = (np.nan, -1.0)
+    gb = plan.transform(spec, zb)
+    assert np.isnan(gb[[1, 8]]).all()
+    keep = np.setdiff1d(np.arange(n), [1, 8])
+    assert np.array_equal(gb[keep], got[keep])
+    # single spectrum, and batch-composition independence
+    assert np.array_equal(plan.transform(spec[7:8], z[7:8])[0], got[7])
+    plan.close()
+
+
+def test_model_resolution_in_quadrature_and_sharp_instrument():
+    """theory_r per wavelength; an instrument sharper than the model (sigma^2 < 0 -> 0) copies bins unsmoothed."""
+    tw, ow, rw, rr = _axes(n_lam=2500, n_px=400)
+    rng = np.random.default_rng(9)
+    spec = np.abs(rng.normal(1.0, 0.5, (6, tw.size))).astype(np.float32)
+    z = np.array([0.1, 1.0, 2.5, 4.0, 6.0, 9.0])
+    tr = np.linspace(100.0, 400.0, tw.size)
+    plan = SpectrumResampler(tw, ow, rw, rr, theory_r=tr)
+    want = np.stack([O.transform_spectrum(tw, spec[i].astype(np.float64), z[i], ow, rw, rr, theory_r=tr)[1] for i in range(6)])
+    close(plan.transform(spec, z), want)
+    plan.close()
+    sharp = SpectrumResampler(tw, ow, rw, np.full_like(rr, 1e5))
+    want = np.stack([O.transform_spectrum(tw, spec[i].astype(np.float64), z[i], ow, rw, np.full_like(rr, 1e5))[1] for i in range(6)])
+    close(sharp.transform(spec, z), want)
+    sharp.close()
+    with pytest.raises(ValueError):
+        SpectrumResampler(tw[::-1], ow, rw, rr)
+    with pytest.raises(ValueError):
+        SpectrumResampler(tw, ow, rw, rr).transform(spec[:, :-1], z)
+
+
+def test_very_wide_kernels_take_the_unstaged_path():
+    """R = 0.5 makes the kernel half-width exceed the shared-memory staging cap: taps are then read from global memory."""
+    tw, ow, rw, rr = _axes(n_lam=3000, n_px=300)
+    rng = np.random.default_rng(2)
+    spec = np.abs(rng.normal(1.0, 0.5, (3, tw.size))).astype(np.float32)
+    z = np.array([0.5, 2.0, 5.0])
+    lowr = np.full_like(rr, 0.5)
+    plan = SpectrumResampler(tw, ow, rw, lowr)
+    want = np.stack([O.transform_spectrum(tw, spec[i].astype(np.float64), z[i], ow, rw, lowr)[1] for i in range(3)])
+    close(plan.transform(spec, z), want)
+    plan.close()
+
+
+def test_full_size_properties_and_device_tensors():
+    """At library scale: a flat spectrum stays flat on every covered pixel (flux conservation of smoothing + rebin), the
+    transform is linear, and CUDA tensors in give the same numbers as host arrays."""
+    import torch
+    tw, ow, rw, rr = _axes()
+    n = 20000
+    rng = np.random.default_rng(1)
+    z = rng.uniform(0.0, 13.0, n)
+    plan = SpectrumResampler(tw, ow, rw, rr)
+    flat = torch.full((n, tw.size), 2.5, dtype=torch.float32, device="cuda")
+    out = plan.transform(flat, torch.as_tensor(z, device="cuda"))
+    assert out.is_cuda and out.shape == (n, ow.size)
+    o = out.cpu().numpy()
+    assert np.all((np.abs(o - 2.5) < 1e-5) | (o == 0.0)) and (o != 0).mean() > 0.95
+    a = torch.rand((512, tw.size), device="cuda") + 0.1
+    b = torch.rand((512, tw.size), device="cuda") + 0.1
+    zz = torch.as_tensor(z[:512], device="cuda")
+    lin = plan.transform(2 * a + 3 * b, zz) - (2 * plan.transform(a, zz) + 3 * plan.transform(b, zz))
+    assert float(lin.abs().max()) < 2e-5
+    host = plan.transform(a.cpu().numpy(), z[:512])
+    assert np.array_equal(host, plan.transform(a, zz).cpu().numpy())
+    plan.close()
+
+
+def test_feature_array_from_raw_spectra():
+    tw, ow, rw, rr = _axes(n_lam=2000, n_px=300)
+    rng = np.random.default_rng(4)
+    n = 50
+    lib = np.abs(rng.normal(50.0, 10.0, (tw.size, n))).astype(np.float32)           # (N_lam, N_gal), nJy
+    params = np.column_stack([rng.uniform(0.1, 8.0, n), rng.uniform(8, 11, n)])
+    feat, names, wavs = create_feature_array_from_raw_spectra(
+        lib, tw, params, ["redshift", "log_mass"], extra_features=["redshift"], crop_wavelength_range=(1.0, 4.0),
+        normed_flux_units="AB", resample_wavelengths=ow, inst_resolution_wavelengths=rw, inst_resolution_r=rr)
+    keep = (ow >= 1.0) & (ow <= 4.0)
+    assert names == ["spectra", "redshift"] and feat.shape == (n, keep.sum() + 1) and np.array_equal(wavs, ow[keep])
+    want = np.stack([O.transform_spectrum(tw, lib[:, i].astype(np.float64), params[i, 0], ow[keep], rw, rr)[1] for i in range(n)])
+    with np.errstate(divide="ignore"):
+        want_ab = -2.5 * np.log10(want * 1e-9) + 8.90
+    ok = np.isfinite(want_ab)
+    assert np.max(np.abs(feat[:, :-1][ok] - want_ab[ok])) < 1e-4 and np.array_equal(feat[:, -1], params[:, 0])
+    with pytest.raises(ValueError):
+        create_feature_array_from_raw_spectra(lib, tw, params, ["redshift", "log_mass"], extra_features=["nope"],
+                                              resample_wavelengths=ow, inst_resolution_wavelengths=rw, inst_resolution_r=rr)

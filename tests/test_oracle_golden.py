@@ -52,6 +52,23 @@ def test_asinh_and_constant_r_match_reference_code():
     np.testing.assert_array_equal(O.constant_r_grid(1000.0, 1100.0, 300), G["const_r_300"])
 
 
+def test_spectroscopic_path_matches_reference_code():
+    """utils.py:129-254 run offline: the variable-width Gaussian is the reference's own loop; transform_spectrum is the
+    reference's own function around the oracle's restatement of `spectres` (third party, unpinned)."""
+    conv = O.convolve_variable_width_gaussian(G["sp_flux"], G["sp_sigma_pix"], 4.0)
+    np.testing.assert_allclose(conv, G["sp_conv"], rtol=1e-13)
+    for z, want in zip(G["sp_z"], G["sp_out"]):
+        _, got = O.transform_spectrum(G["sp_wave"], G["sp_flux"], float(z), G["sp_obs_wave"], G["sp_res_wave"], G["sp_res_r"])
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+    _, got = O.transform_spectrum(G["sp_wave"], G["sp_flux"], 2.0, G["sp_obs_wave"], G["sp_res_wave"], G["sp_res_r"], theory_r=1000.0)
+    np.testing.assert_allclose(got, G["sp_out_r1000"], rtol=1e-12)
+    assert (G["sp_out"][-1] == 0).sum() > 0 and (G["sp_out"][0] > 0).all()     # z = 14: the bluest pixels are not covered -> fill
+    # the rebin conserves flux: a constant spectrum stays constant, integral over covered pixels is preserved
+    w = G["sp_wave"]
+    flat = O.spectres_resample(G["sp_obs_wave"], w, np.full(w.size, 3.0))
+    np.testing.assert_allclose(flat, 3.0, rtol=1e-13)
+
+
 def test_product_host_code_matches_reference_code():
     """The API-level host functions of the product against the same vectors."""
     import synference_b200 as S
