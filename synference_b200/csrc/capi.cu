@@ -1017,7 +1017,19 @@ int sb2_resampler_create(const sb2_resample_desc* d, int device, sb2_resampler**
   int max_smem = 0;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   a.h_cap = 512;
-  r->smem = ((size_t)2 * d->n_lam + 2 * (size_t)a.h_cap) * sizeof(float);
+  // the bins under the observed window: its rest-frame image [first edge / (1+z), last edge / (1+z)] has a fixed RATIO, so
+  // the largest count over all redshifts is the largest count over all windows of that ratio along the axis
+  int nb_max = d->n_lam;
+  if (oe[0] > 0 && ne[0] > 0) {
+    const double ratio = ne[d->n_px] / ne[0] * (1.0 + 1e-9);
+    nb_max = 1;
+    for (int k = 0, k2 = 0; k < d->n_lam; ++k) {
+      while (k2 < d->n_lam && oe[k2] < oe[k] * ratio) ++k2;     // bins k .. k2-1 start inside a window that starts in bin k
+      nb_max = std::max(nb_max, k2 - k + 1);
+    }
+    nb_max = std::min(nb_max + 1, d->n_lam);
+  }
+  r->smem = ((size_t)2 * nb_max + 2 * (size_t)a.h_cap) * sizeof(float);
   if (rc == SB2_OK && r->smem > (size_t)max_smem - 1024) rc = fail(SB2_ERR_INVALID, "resampler: model axis too long for one CTA's shared memory");
   if (rc == SB2_OK && cudaFuncSetAttribute(sb2::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r->smem) != cudaSuccess)
     rc = fail(SB2_ERR_CUDA, "cudaFuncSetAttribute(resample_kernel)");
