@@ -24,6 +24,8 @@ from .noise_models import (AsinhEmpiricalUncertaintyModel, DepthUncertaintyModel
 from .engine import GalaxyParams, SynthEngine, depth_noise_features  # noqa: F401
 from .library import CombinedBasis, GalaxyBasis, GalaxySimulator, create_galaxy  # noqa: F401
 from .features import ResampledFeatures, create_feature_array_from_raw_photometry  # noqa: F401
+from .supplementary import (calculate_burstiness, calculate_mass_weighted_age, calculate_sfh_quantile,  # noqa: F401
+                            calculate_sfr, calculate_surviving_mass)
 from .spectral import SpectrumResampler, create_feature_array_from_raw_spectra, transform_spectrum  # noqa: F401
 
 __version__ = "0.1.0"

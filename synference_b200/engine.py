@@ -486,6 +486,13 @@ class SynthEngine:
         return out
 
 
+    def sfzh(self, params: GalaxyParams):
+        """SFZH ``(N, n_age, n_z)`` float64, normalised to 1 per galaxy (host array; the by-products of
+        ``synference_b200.supplementary`` are evaluated from it)."""
+        t = self.tables
+        return self.weights(params).reshape(len(params), t["n_z"], t["n_age"]).transpose(0, 2, 1)
+
+
 @dataclass
 class DeviceParams:
     host: GalaxyParams

@@ -25,6 +25,7 @@ from typing import Dict, List, Optional, Union
 import numpy as np
 
 from . import distributed as _dist
+from . import supplementary as _supp
 from .cosmology import Planck18
 from .engine import GalaxyParams, SynthEngine
 from .igm import Inoue14
@@ -291,10 +292,7 @@ class GalaxyBasis:
         Each batch is one pass of the CUDA path at the base mass; per-batch files are the resume unit:
         an existing ``<out_name>_<i>.hdf5`` is skipped unless ``overwrite``.
         """
-        if extra_analysis_functions:
-            raise NotImplementedError(
-                "supplementary analysis callbacks operate on Synthesizer objects and are outside the hot "
-                f"path (SURVEY 2 row 12): {list(extra_analysis_functions)}")
+        _supp.check_supported(extra_analysis_functions)     # history-based ones only; others raise NotImplementedError
         if em_lines_to_save:
             raise NotImplementedError("emission-line outputs are outside the hot path")
         if self.params is None:
@@ -328,6 +326,7 @@ class GalaxyBasis:
                 logger.warning(f"Skipping batch {batch_i + 1} as {final} already exists.")
                 continue
             start = datetime.now()
+            supp_units = {}
             p = self.params.slice(sl)
             # the pipeline always runs at the base mass (library.py:3217): no mass scaling here
             p.log_mass = None
@@ -351,6 +350,13 @@ class GalaxyBasis:
                     p.fesc_lya = np.asarray(strip_units(self.all_parameters[lya_name]), dtype=float)[sl]
                 flux = eng.photometry(p, scaled=False)
                 results["photometry"][key].append(flux)
+                if extra_analysis_functions and key == keys[0]:
+                    # by-products of the weights (library.py:2593-2601 stores callback results as supp_<name>)
+                    supp = _supp.evaluate(extra_analysis_functions, eng.sfzh(p) * 10.0 ** 9, self.grid.log10ages,
+                                          p.redshift, self.cosmo)
+                    for name, (vals, units) in supp.items():
+                        datasets[f"Galaxies/supp_{name}"] = vals
+                        supp_units[name] = units
                 label = self.instrument.label
                 for j, code in enumerate(eng.filter_codes):
                     datasets[f"Galaxies/Stars/Photometry/Fluxes/{key}/{label}/{code}"] = flux[:, j].astype(np.float64)
@@ -374,7 +380,8 @@ class GalaxyBasis:
                          "pipeline_time": str(elapsed), "WavelengthUnits": "Angstrom",
                          "FilterCodes": list(self.instrument.filters.filter_codes),
                          "InstrumentLabel": self.instrument.label, "batch": batch_i + 1, "n_batches": n_batches,
-                         "rank": rank, "world_size": size, "galaxy_start": sl.start, "galaxy_stop": sl.stop}
+                         "rank": rank, "world_size": size, "galaxy_start": sl.start, "galaxy_stop": sl.stop,
+                         "supp_names": list(supp_units), "supp_units": [supp_units[k] for k in supp_units]}
                 write_container(final, datasets, attrs, compress=False)
                 logger.info(f"Written pipeline to disk at {final}.")
         return {k: {kk: (np.concatenate(vv) if vv else None) for kk, vv in v.items()} for k, v in results.items()}
@@ -548,13 +555,19 @@ class CombinedBasis:
             key = self.base_emission_model_keys[i]
             label = parts[0][3].get("InstrumentLabel", base.instrument.label)
             codes = list(parts[0][3].get("FilterCodes", base.instrument.filters.filter_codes))
-            props = {}
+            props, supp_props = {}, {}
+            s_units = dict(zip(parts[0][3].get("supp_names", []), parts[0][3].get("supp_units", [])))
             for name in parts[0][2]:
                 if name.startswith("Galaxies/") and name.count("/") == 1:
-                    props[name.split("/", 1)[1]] = np.concatenate([p[2][name] for p in parts])
+                    short = name.split("/", 1)[1]
+                    col = np.concatenate([p[2][name] for p in parts])
+                    if short.startswith("supp_"):      # library.py:3446-3448
+                        supp_props[short[5:]] = (col, s_units.get(short[5:], "dimensionless"))
+                    else:
+                        props[short] = col
             phot = {c: np.concatenate([p[2][f"Galaxies/Stars/Photometry/Fluxes/{key}/{label}/{c}"] for p in parts])
                     for c in codes}
-            entry = {"properties": props, "observed_photometry": phot, "supp_properties": {},
+            entry = {"properties": props, "observed_photometry": phot, "supp_properties": supp_props,
                      "wavelengths": parts[0][2]["Wavelengths"], "filter_codes": codes, "stem": stem}
             skey = f"Galaxies/Stars/Spectra/SpectralFluxDensities/{key}"
             if load_spectra:
@@ -630,10 +643,23 @@ class CombinedBasis:
                 param_units.append(UNIT_DICT.get(short, str(src.units) if has_units(src) else "dimensionless"))
         combined_outputs = np.ascontiguousarray(total.T)          # (n_filters | n_lam, n_gal)
         combined_params = np.stack(rows, 0)                        # (n_params, n_gal)
-        supp = np.zeros((0, combined_params.shape[1]))
+        # supplementary parameters: rescaled from the base mass like the photometry (library.py:4631-4656)
+        supp_names, supp_units_l, supp_rows = [], [], []
+        first = outputs[self.bases[0].model_name]
+        if first["supp_properties"]:
+            if multi:
+                raise NotImplementedError("supplementary parameters of multi-base libraries are not combined yet")
+            scale = 10.0 ** log_mass / first["properties"]["mass"]
+            for name, (vals, units) in first["supp_properties"].items():
+                how = _supp.scales_with_mass(units)
+                vals = np.asarray(vals, dtype=float)
+                supp_rows.append(vals * scale if how == "linear" else vals + np.log10(scale) if how == "log" else vals)
+                supp_names.append(name)
+                supp_units_l.append(units)
+        supp = np.stack(supp_rows, 0) if supp_rows else np.zeros((0, combined_params.shape[1]))
         out = {"parameters": combined_params, "parameter_names": param_columns,
-               "supplementary_parameters": supp, "supplementary_parameter_names": [],
-               "supplementary_parameter_units": [], "parameter_units": param_units}
+               "supplementary_parameters": supp, "supplementary_parameter_names": supp_names,
+               "supplementary_parameter_units": supp_units_l, "parameter_units": param_units}
         if spectral_mode:
             out["spectra"] = combined_outputs
             self.library_spectra = combined_outputs
@@ -647,8 +673,8 @@ class CombinedBasis:
         self.library_parameter_names = param_columns
         self.library_parameter_units = param_units
         self.library_supplementary_parameters = supp
-        self.library_supplementary_parameter_names = []
-        self.library_supplementary_parameter_units = []
+        self.library_supplementary_parameter_names = supp_names
+        self.library_supplementary_parameter_units = supp_units_l
         logger.info(f"Combined outputs shape: {combined_outputs.shape}; parameters {combined_params.shape}")
         if save:
             self.save_library(out, overload_out_name=overload_out_name, overwrite=overwrite)

@@ -156,6 +156,32 @@ def main():
     g["sp_z"] = np.array([0.0, 0.7, 3.2, 9.5, 14.0])
     g["sp_out"] = np.stack([transform(tw, tf, float(z), ow, rw, rr)[1] for z in g["sp_z"]])
     g["sp_out_r1000"] = transform(tw, tf, 2.0, ow, rw, rr, theory_r=1000.0)[1]
+    # ---- calculate_sfh_quantile (library.py:468-509): the reference's own function on duck-typed galaxy objects
+    from synference_b200.cosmology import Planck18 as P18
+
+    class YearArray:                      # unyt keeps the unit on a scalar element; the shim's ndarray view does not
+        def __init__(self, v):
+            self.v = np.asarray(v, dtype=float)
+
+        def __getitem__(self, k):
+            r = self.v[k]
+            return YearArray(r) if np.ndim(r) else shim.Quantity(r, "yr")
+
+    class FakeGalaxy:
+        def __init__(self, sf_hist, ages_yr, z):
+            self.stars = types.SimpleNamespace(sf_hist=sf_hist, ages=YearArray(ages_yr), sfh=True)
+            self.redshift = z
+
+    quant = lift(os.path.join(REF, "library.py"), "calculate_sfh_quantile", extra={"Galaxy": FakeGalaxy, "Planck18": P18})
+    rq = np.random.default_rng(23)
+    ages = 10.0 ** np.arange(6.0, 11.05, 0.1)
+    sfh = np.abs(rq.normal(1.0, 1.0, (12, ages.size))) * (rq.uniform(0, 1, (12, ages.size)) > 0.3)
+    sfh[:, -1] = 0.0
+    zq = rq.uniform(0.1, 8.0, 12)
+    g["q_ages"], g["q_sfh"], g["q_z"] = ages, sfh, zq
+    for q in (0.25, 0.5, 0.9):
+        g[f"q_{int(q * 100)}"] = np.array([float(np.asarray(quant(FakeGalaxy(sfh[i], ages, zq[i]), q))) for i in range(12)])
+    g["q_50_norm"] = np.array([float(np.asarray(quant(FakeGalaxy(sfh[i], ages, zq[i]), 0.5, True, P18))) for i in range(12)])
     np.savez(OUT, **g)
     print("wrote", OUT, {k: np.shape(v) for k, v in g.items()})
 

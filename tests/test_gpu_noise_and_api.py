@@ -340,3 +340,39 @@ def test_total_spectrum_with_dust_emission_through_create_mock_library(tmp_path)
     _, attrs = read_container(os.path.join(str(tmp_path), "total_lib.hdf5"))
     assert attrs["Model/dust_emission"] == "Greybody" and list(attrs["Model/dust_emission_values"]) == [40.0, 1.5]
     assert attrs["Model/emission_model_key"] == "total"
+
+
+def test_supplementary_parameters_through_create_mock_library(tmp_path):
+    """batch_library_generation.py:520-547 style extras (mass-weighted age, SFR over 10/100 Myr, SFH quantile, burstiness)
+    come out of create_mock_library as Grid/SupplementaryParameters, rescaled from the base mass like the photometry."""
+    from oracle import adapter as A
+    n = 90
+    basis, d, grid, inst, em = _small_basis(n, tmp_path)
+    masses = np.asarray(d["masses"], dtype=float)
+    combined = basis.create_mock_library(
+        log_stellar_masses=list(masses), emission_model_key="emergent", out_name="supp_lib", out_dir=str(tmp_path),
+        overwrite=True, batch_size=40, mass_weighted_age=S.calculate_mass_weighted_age, sfr_10=(S.calculate_sfr, 10 * S.Myr),
+        sfr_100=(S.calculate_sfr, 100 * S.Myr), sfh_quant_50=(S.calculate_sfh_quantile, 0.50, True),
+        burstiness=S.calculate_burstiness)
+    lib = S.load_library_from_hdf5(os.path.join(str(tmp_path), "supp_lib.hdf5"))
+    names = list(lib["supplementary_parameter_names"])
+    assert names == ["mass_weighted_age", "sfr_10", "sfr_100", "sfh_quant_50", "burstiness"]
+    assert list(lib["supplementary_parameter_units"]) == ["Myr", "Msun/yr", "Msun/yr", "dimensionless", "dimensionless"]
+    supp = np.asarray(lib["supplementary_parameters"])
+    assert supp.shape == (5, n) and combined.library_supplementary_parameter_names == names
+    # against the float64 oracle's SFZH
+    ages = 10.0 ** np.asarray(grid.log10ages)
+    gals = A.galaxies_from_params(basis.params)
+    sf = np.stack([O.weights_for(g, grid.log10ages, grid.metallicity).sum(axis=1) for g in gals])
+    sf = sf / sf.sum(1, keepdims=True)
+    np.testing.assert_allclose(supp[0], sf @ ages / 1e6, rtol=1e-9)
+    edges = np.concatenate([[0.0], 0.5 * (ages[1:] + ages[:-1]), [ages[-1]]])
+    frac = np.clip((1e7 - edges[:-1]) / np.diff(edges), 0, 1)
+    want_sfr10 = (sf @ frac) * 10.0 ** masses / 1e7                # scaled to each galaxy's mass
+    np.testing.assert_allclose(supp[1], want_sfr10, rtol=1e-8, atol=1e-30)
+    ok = supp[2] > 0
+    np.testing.assert_allclose(supp[4][ok], (supp[1] / supp[2])[ok], rtol=1e-9)
+    assert np.all((supp[3] > 0) & (supp[3] < 1.0))
+    with pytest.raises(NotImplementedError):
+        basis.create_mock_library(log_stellar_masses=list(masses), emission_model_key="emergent", out_name="supp_bad",
+                                  out_dir=str(tmp_path), overwrite=True, beta=lambda galaxy: 0.0)

@@ -242,3 +242,38 @@ def test_per_galaxy_fesc_recipe_and_coefficients():
     rebuilt = a0.copy()
     rebuilt[..., i] += vals
     np.testing.assert_allclose(rebuilt, a1, rtol=1e-14, atol=0)
+
+
+def test_supplementary_by_products_of_the_sfzh():
+    """synference_b200.supplementary: history-based callbacks of library.py:223-241, 427-442, 468-526 evaluated per batch.
+    calculate_sfh_quantile is pinned on the reference's own function (golden vectors); the others on their definitions."""
+    import os
+    from synference_b200 import supplementary as SP
+    from synference_b200.cosmology import Planck18
+    from synference_b200.units import Myr
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_noise_golden.npz"))
+    ages, sfh, z = G["q_ages"], G["q_sfh"], G["q_z"]
+    n_z = 3
+    zfrac = np.array([0.2, 0.5, 0.3])
+    sfzh = sfh[:, :, None] * zfrac[None, None, :]
+    ctx = SP._Context(sfzh, np.log10(ages), z, Planck18)
+    for q in (25, 50, 90):
+        np.testing.assert_allclose(SP.calculate_sfh_quantile(ctx, q / 100), G[f"q_{q}"], rtol=1e-12)
+    np.testing.assert_allclose(SP.calculate_sfh_quantile(ctx, 0.5, True, Planck18), G["q_50_norm"], rtol=1e-9)
+    np.testing.assert_allclose(SP.calculate_mass_weighted_age(ctx), (sfh @ ages) / sfh.sum(1) / 1e6, rtol=1e-13)
+    # SFR over a timescale: brute-force integral of the piecewise-uniform history
+    edges = np.concatenate([[0.0], 0.5 * (ages[1:] + ages[:-1]), [ages[-1]]])
+    dens = sfh / np.diff(edges)
+    t = np.linspace(0, 3e7, 300001)
+    mid = 0.5 * (t[1:] + t[:-1])
+    mass = (dens[:, np.searchsorted(edges, mid, side="right") - 1] * np.diff(t)).sum(1)
+    np.testing.assert_allclose(SP.calculate_sfr(ctx, 30 * Myr), mass / 3e7, rtol=1e-4)     # (the brute-force sum has 100 yr steps)
+    np.testing.assert_allclose(SP.calculate_burstiness(ctx), SP.calculate_sfr(ctx, 1e7) / SP.calculate_sfr(ctx, 1e8), rtol=1e-13)
+    grid = type("G", (), {"stellar_fraction": np.linspace(1.0, 0.5, ages.size)[:, None] * np.ones((1, n_z))})()
+    np.testing.assert_allclose(SP.calculate_surviving_mass(ctx, grid), np.log10(sfh @ np.linspace(1.0, 0.5, ages.size)), rtol=1e-13)
+    out = SP.evaluate({"mwa": SP.calculate_mass_weighted_age, "sfr_10": (SP.calculate_sfr, 10 * Myr),
+                       "q50n": (SP.calculate_sfh_quantile, 0.5, True)}, sfzh, np.log10(ages), z, Planck18)
+    assert [out[k][1] for k in ("mwa", "sfr_10", "q50n")] == ["Myr", "Msun/yr", "dimensionless"]
+    assert [SP.scales_with_mass(u) for u in ("Myr", "Msun/yr", "log10_Msun")] == ["none", "linear", "log"]
+    with pytest.raises(NotImplementedError):
+        SP.check_supported({"beta": lambda galaxy: 0.0})
