@@ -109,7 +109,8 @@ def run_reference(args, rank, world):
         return
     from synference_b200.configs import make_workload
     threads = os.cpu_count() or 1
-    n_step = args.ref_sample
+    # a bounded sample per step: about two minutes of CPU work for the whole run at ~10 k galaxies/s on 16 threads
+    n_step = args.ref_sample if args.ref_sample > 0 else int(np.clip(1_200_000 // max(1, args.steps + 1), 10_000, 150_000))
     w = make_workload(args.workload, n_step)
     for _ in range(max(1, min(args.warmup, 1))):
         time_cpu(w, min(n_step, 2000), threads)
@@ -140,12 +141,12 @@ def workload_name(key):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--galaxies", type=int, default=1_000_000, help="galaxies per GPU per step")
-    ap.add_argument("--ref-sample", type=int, default=150000, help="galaxies per CPU step")
+    ap.add_argument("--ref-sample", type=int, default=0, help="galaxies per CPU step (0: sized so that K steps take ~2 min)")
     ap.add_argument("--cpu-sample", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per contraction launch, if known")
@@ -234,7 +235,7 @@ def main():
     for _ in range(2):
         eng.photometry(pinned, scaled=False, out=host_out)
     barrier()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 20))     # the same K as the device-resident loop (bounded: host time)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         eng.photometry(pinned, scaled=False, out=host_out)
