@@ -242,6 +242,36 @@ int sb2_resample_spectra_host(sb2_resampler* r, const float* spectra, const doub
 /* Device time [ms] of the most recent sb2_resample_spectra call on this resampler (blocks until it has finished). */
 int sb2_resample_last_ms(sb2_resampler* r, float* ms);
 
+/* ---- Empirical uncertainty models on the device ---------------------------------------------------------------------
+ * Replaces SBI_Fitter._apply_empirical_noise_models (sbi_runner.py:813-903: per filter, row copy ->
+ * GeneralEmpiricalUncertaintyModel.apply_noise, noise_models.py:818-880) for all filters and rows in one launch.
+ * One sb2_empirical_model per filter: the binned catalogue statistics the interpolators are built from
+ * (noise_models.py:347-381), units, and the upper-limit rules with their replacement values resolved on the host
+ * (noise_models.py:882-957).  Units: *_is_ab = 1 for AB magnitudes, else *_to_jy is the size of the linear unit in Jy.   */
+#define SB2_EMP_MAX_BINS 64
+typedef struct sb2_empirical_model {
+  int32_t n_bins, extrapolate;
+  int32_t internal_is_ab, in_is_ab, out_is_ab;
+  int32_t observed_error;     /* error_type == "observed": sigma drawn again at the noisy flux                       */
+  int32_t upper_limits;       /* SNR-based upper limits on                                                         */
+  int32_t ul_active;          /* ... and an upper-limit value exists (upper_limit_value is not None)               */
+  double internal_to_jy, in_to_jy, out_to_jy;
+  double sigma_clip;          /* < 0: plain normal scatter, else truncated at +-sigma_clip sigma                   */
+  double snr_threshold;       /* treat_as_upper_limits_below                                                       */
+  double ul_flux;             /* replacement flux (interpolation unit): the limit, or a numeric behaviour          */
+  double ul_scatter_std;      /* "scatter_limit": std of the +-3 sigma truncated normal added to ul_flux; < 0: none */
+  double ul_err;              /* replacement error (interpolation unit)                                            */
+  double min_err, max_err;    /* final clip of the error (output unit)                                             */
+  double centers[SB2_EMP_MAX_BINS], median[SB2_EMP_MAX_BINS], stdev[SB2_EMP_MAX_BINS];
+} sb2_empirical_model;
+/* flux: device float64 [n_filt][n] (the reference's (N_f, N_rows) layout); models: HOST array [n_filt];
+ * draws: device float64 [4][n_filt][n] injected draws (sigma uniform, scatter normal -- uniform when sigma-clipped --,
+ * re-draw uniform, limit-scatter uniform) or NULL => Philox4x32-10 keyed by (seed, epoch), counter (row, filter);
+ * out_flux / out_sigma: device float64 [n_filt][n] (out_sigma may be NULL).                                          */
+int sb2_empirical_noise(const double* flux, int64_t n, int32_t n_filt, const sb2_empirical_model* models,
+                        const double* draws, uint64_t seed, uint64_t epoch, double* out_flux, double* out_sigma,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -529,6 +529,79 @@ def depth_model_sigma_jy(depth_ab, sigma_level=5.0):
     return ab_to_jy(depth_ab) / sigma_level  # noise_models.py:104-105
 
 
+def empirical_apply_noise(flux, model, draws, true_flux_units=None, out_units=None):
+    """noise_models.py:818-880 (GeneralEmpiricalUncertaintyModel.apply_noise) with the random numbers injected per element.
+
+    ``model``: dict(centers, median, std, extrapolate, flux_unit, interpolation_flux_unit, sigma_clip, error_type,
+    upper_limits, snr_threshold, upper_limit_value, ul_flux_behaviour, ul_err_value, min_err, max_err); units are "AB" or
+    the size of a linear unit in Jy.  ``draws`` (4, n): uniform for the sigma draw, normal for the scatter (uniform when
+    sigma-clipped), uniform for the "observed" re-draw, uniform for the scatter about the upper limit.  The reference draws
+    the last three only for the elements that need them (compacted arrays); a caller reproducing its stream scatters them.
+    Returns (noisy flux, sigma) in ``out_units``."""
+    from scipy import stats
+    c, med, sd = (np.asarray(model[k], dtype=float) for k in ("centers", "median", "std"))
+
+    def interp(y, v):
+        v = np.asarray(v, dtype=float)
+        out = np.interp(v, c, y)                                  # end-value fill
+        if model.get("extrapolate", False):
+            lo, hi = v < c[0], v > c[-1]
+            out = np.where(lo, y[0] + (v - c[0]) * (y[1] - y[0]) / (c[1] - c[0]), out)
+            out = np.where(hi, y[-2] + (v - c[-2]) * (y[-1] - y[-2]) / (c[-1] - c[-2]), out)
+        return out
+
+    def to_jy(f, e, unit):
+        if unit == "AB":
+            fj = ab_to_jy(f)
+            return fj, ab_err_to_jy(e, fj)
+        return f * unit, e * unit
+
+    def convert(f, e, src, dst):
+        if src == dst:
+            return f, e
+        if src == "AB":
+            fj, ej = to_jy(f, e, "AB")
+            return fj / dst, ej / dst
+        if dst == "AB":
+            fj, ej = f * src, e * src
+            return jy_to_ab(fj), jy_err_to_ab(ej, fj)
+        return f * (src / dst), e * (src / dst)
+
+    def sample(f, u):
+        mu, ss = interp(med, f), np.maximum(0, interp(sd, f))
+        a = (0 - mu) / np.where(ss > 1e-9, ss, 1)
+        return mu + ss * stats.truncnorm.ppf(u, a, np.inf)
+
+    def below(f, e):
+        fj, ej = to_jy(f, e, iu)
+        with np.errstate(all="ignore"):
+            snr = fj / ej
+        return ~np.isfinite(snr) | (snr < model["snr_threshold"])
+
+    iu = model["interpolation_flux_unit"]
+    flux = np.asarray(flux, dtype=float)
+    src = model["flux_unit"] if true_flux_units is None else true_flux_units
+    dst = model["flux_unit"] if out_units is None else out_units
+    f_int, _ = convert(flux, np.zeros_like(flux), src, iu)
+    sig = sample(f_int, draws[0])
+    init = below(f_int, sig) if model["upper_limits"] else np.zeros(flux.shape, dtype=bool)
+    zz = stats.truncnorm.ppf(draws[1], -model["sigma_clip"], model["sigma_clip"]) if model.get("sigma_clip") is not None else draws[1]
+    noisy = np.where(init, f_int, f_int + (0.0 + sig * zz))
+    final = sample(noisy, draws[2]) if model["error_type"] == "observed" else sig
+    if model["upper_limits"] and model.get("upper_limit_value") is not None:
+        mask = init | below(noisy, final)
+        beh, ul = model["ul_flux_behaviour"], model["upper_limit_value"]
+        if beh == "scatter_limit":
+            repl = ul + float(np.maximum(0, interp(sd, ul))) * stats.truncnorm.ppf(draws[3], -3, 3)
+        else:
+            repl = np.full(flux.shape, ul if beh == "upper_limit" else float(beh))
+        noisy = np.where(mask, repl, noisy)
+        final = np.where(mask, model["ul_err_value"], final)
+    with np.errstate(all="ignore"):
+        of, os_ = convert(noisy, final, iu, dst)
+    return of, np.clip(os_, model["min_err"], model["max_err"])
+
+
 def depth_model_apply_noise(flux_jy, depth_ab, z, sigma_level=5.0, out_units=None,
                             min_err=0.0, max_err=np.inf):
     """DepthUncertaintyModel.apply_noise with the normal draws ``z`` injected

@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = (
     "sb2_synth_photometry", "sb2_synth_photometry_host", "sb2_depth_noise_features", "sb2_last_stage_ms", "sb2_wait_debug",
     "sb2_synth_photometry_host_submit", "sb2_synth_photometry_host_wait",
     "sb2_resampler_create", "sb2_resampler_destroy", "sb2_resample_spectra", "sb2_resample_spectra_host", "sb2_resample_last_ms",
+    "sb2_empirical_noise",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -69,6 +70,21 @@ class ResampleDesc(C.Structure):
     ]
 
 
+EMP_MAX_BINS = 64
+
+
+class EmpiricalModel(C.Structure):
+    _fields_ = [
+        ("n_bins", C.c_int32), ("extrapolate", C.c_int32),
+        ("internal_is_ab", C.c_int32), ("in_is_ab", C.c_int32), ("out_is_ab", C.c_int32),
+        ("observed_error", C.c_int32), ("upper_limits", C.c_int32), ("ul_active", C.c_int32),
+        ("internal_to_jy", C.c_double), ("in_to_jy", C.c_double), ("out_to_jy", C.c_double),
+        ("sigma_clip", C.c_double), ("snr_threshold", C.c_double), ("ul_flux", C.c_double),
+        ("ul_scatter_std", C.c_double), ("ul_err", C.c_double), ("min_err", C.c_double), ("max_err", C.c_double),
+        ("centers", C.c_double * EMP_MAX_BINS), ("median", C.c_double * EMP_MAX_BINS), ("stdev", C.c_double * EMP_MAX_BINS),
+    ]
+
+
 _lib = None
 
 
@@ -107,6 +123,8 @@ def load():
     lib.sb2_resample_spectra.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.sb2_resample_spectra_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.sb2_resample_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.sb2_empirical_noise.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(EmpiricalModel), C.c_void_p, C.c_uint64,
+                                        C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

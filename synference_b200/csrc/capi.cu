@@ -14,6 +14,7 @@
 
 #include "../../include/synference_b200.h"
 #include "noise_kernel.cuh"
+#include "empirical_kernel.cuh"
 #include "prep_kernel.cuh"
 #include "resample_kernel.cuh"
 #include "synth_kernel.cuh"
@@ -1094,6 +1095,54 @@ int sb2_resample_spectra_host(sb2_resampler* r, const float* spectra, const doub
   int rc = sb2_resample_spectra(r, r->stage_in, r->stage_z, n, r->stage_out, nullptr);
   if (rc != SB2_OK) return rc;
   CU_TRY(cudaMemcpy(out, r->stage_out, (size_t)n * r->a.n_px * sizeof(float), cudaMemcpyDeviceToHost));
+  return SB2_OK;
+}
+
+// ---- empirical uncertainty models ---------------------------------------------------------------------------------
+static_assert(SB2_EMP_MAX_BINS == sb2::kEmpMaxBins, "header and kernel disagree on the table size");
+
+int sb2_empirical_noise(const double* flux, int64_t n, int32_t n_filt, const sb2_empirical_model* models,
+                        const double* draws, uint64_t seed, uint64_t epoch, double* out_flux, double* out_sigma,
+                        void* stream) {
+  if (!flux || !models || !out_flux || n < 0 || n_filt < 1) return fail(SB2_ERR_INVALID, "bad argument");
+  if (n == 0) return SB2_OK;
+  std::vector<sb2::EmpiricalModelDev> h((size_t)n_filt);
+  for (int f = 0; f < n_filt; ++f) {
+    const sb2_empirical_model& m = models[f];
+    if (m.n_bins < 2 || m.n_bins > SB2_EMP_MAX_BINS) return fail(SB2_ERR_INVALID, "empirical model: 2 <= n_bins <= SB2_EMP_MAX_BINS");
+    for (int i = 1; i < m.n_bins; ++i)
+      if (!(m.centers[i] > m.centers[i - 1])) return fail(SB2_ERR_INVALID, "empirical model: bin centres must increase");
+    if ((!m.internal_is_ab && !(m.internal_to_jy > 0)) || (!m.in_is_ab && !(m.in_to_jy > 0)) || (!m.out_is_ab && !(m.out_to_jy > 0)))
+      return fail(SB2_ERR_INVALID, "empirical model: linear units need a positive size in Jy");
+    sb2::EmpiricalModelDev& d = h[f];
+    d.n_bins = m.n_bins; d.extrapolate = m.extrapolate; d.internal_is_ab = m.internal_is_ab; d.in_is_ab = m.in_is_ab;
+    d.out_is_ab = m.out_is_ab; d.observed_error = m.observed_error; d.upper_limits = m.upper_limits; d.ul_active = m.ul_active;
+    d.internal_to_jy = m.internal_to_jy; d.in_to_jy = m.in_to_jy; d.out_to_jy = m.out_to_jy; d.sigma_clip = m.sigma_clip;
+    d.snr_threshold = m.snr_threshold; d.ul_flux = m.ul_flux; d.ul_scatter_std = m.ul_scatter_std; d.ul_err = m.ul_err;
+    d.min_err = m.min_err; d.max_err = m.max_err;
+    std::memcpy(d.centers, m.centers, sizeof(d.centers));
+    std::memcpy(d.median, m.median, sizeof(d.median));
+    std::memcpy(d.stdev, m.stdev, sizeof(d.stdev));
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  sb2::EmpiricalModelDev* dm = nullptr;
+  CU_TRY(cudaMallocAsync(reinterpret_cast<void**>(&dm), h.size() * sizeof(sb2::EmpiricalModelDev), st));
+  cudaError_t e = cudaMemcpyAsync(dm, h.data(), h.size() * sizeof(sb2::EmpiricalModelDev), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);    // h is pageable and goes out of scope
+  if (e != cudaSuccess) { cudaFreeAsync(dm, st); return fail(SB2_ERR_CUDA, cudaGetErrorString(e)); }
+  sb2::EmpiricalArgs a{};
+  a.flux = flux; a.n = n; a.n_filt = n_filt; a.models = dm; a.draws = draws; a.seed = seed; a.epoch = epoch;
+  a.out_flux = out_flux; a.out_sigma = out_sigma;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  long long bx = (n + 255) / 256;
+  const long long cap = std::max<long long>(1, (long long)n_sm * 8 / n_filt);
+  if (bx > cap) bx = cap;
+  sb2::empirical_noise_kernel<<<dim3((unsigned)bx, (unsigned)n_filt), 256, 0, st>>>(a);
+  e = cudaGetLastError();
+  cudaFreeAsync(dm, st);
+  if (e != cudaSuccess) return fail(SB2_ERR_CUDA, cudaGetErrorString(e));
   return SB2_OK;
 }
 

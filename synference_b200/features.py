@@ -132,6 +132,64 @@ def create_feature_array_from_raw_photometry(
     return out.cpu().numpy(), feature_names, (None if params is None else params.cpu().numpy())
 
 
+def apply_empirical_noise_models(photometry_array, phot_names, empirical_noise_models, N_scatters: int = 5,
+                                 min_flux_pc_error: float = 0.0, flux_units: str = "AB", return_errors: bool = False,
+                                 normed_flux_units: str = "AB", draws=None, seed: int = 0, epoch: int = 0, device=0):
+    """``SBI_Fitter._apply_empirical_noise_models`` (``sbi_runner.py:813-903``) in one CUDA launch for all filters.
+
+    ``photometry_array`` is ``(N_f, N_gal)`` in ``flux_units``; each column is repeated ``N_scatters`` times
+    (``np.repeat(..., axis=1)``) and every filter row goes through its model's ``apply_noise(flux, true_flux_units=flux_units,
+    out_units=normed_flux_units)``.  numpy in -> numpy out; CUDA tensors in -> CUDA tensors out.  ``draws`` (4, N_f, N_rows)
+    injects the random numbers (see ``include/synference_b200.h``); otherwise Philox keyed by ``(seed, epoch)``.
+    ``min_flux_pc_error`` is accepted and unused, as in the reference."""
+    import ctypes as C
+
+    import torch
+
+    from . import _capi
+    from .noise_models import GeneralEmpiricalUncertaintyModel
+    if not isinstance(empirical_noise_models, dict):
+        raise ValueError("empirical_noise_models must be a dictionary")
+    for name in phot_names:
+        if name not in empirical_noise_models:
+            raise ValueError(f"No empirical noise model found for filter {name}. Please provide a valid model.")
+    for name in empirical_noise_models:
+        if name not in phot_names:
+            raise ValueError(f"Filter {name} in empirical_noise_models is not in phot_names: {phot_names}.")
+    lib = _capi.load()
+    if lib.sb2_device_count() < 1:
+        raise RuntimeError("synference_b200: no CUDA device visible; the noise path has no CPU fallback")
+    models = (_capi.EmpiricalModel * len(phot_names))()
+    for i, name in enumerate(phot_names):
+        mod = empirical_noise_models[name]
+        if not isinstance(mod, GeneralEmpiricalUncertaintyModel):
+            raise NotImplementedError(f"{type(mod).__name__}: only GeneralEmpiricalUncertaintyModel runs on the device so far")
+        models[i] = mod.device_model(true_flux_units=flux_units, out_units=normed_flux_units)
+    dev = torch.device("cuda", int(device))
+    was_numpy = not isinstance(photometry_array, torch.Tensor)
+    phot = torch.as_tensor(np.asarray(photometry_array, dtype=np.float64) if was_numpy else photometry_array, device=dev)
+    phot = phot.to(torch.float64)
+    if phot.ndim != 2 or phot.shape[0] != len(phot_names):
+        raise ValueError("photometry_array must be (N_filters, N_galaxies)")
+    rep = torch.repeat_interleave(phot, int(N_scatters), dim=1).contiguous()
+    n = rep.shape[1]
+    d_ptr = None
+    if draws is not None:
+        dr = torch.as_tensor(np.asarray(draws, dtype=np.float64) if not isinstance(draws, torch.Tensor) else draws,
+                             device=dev).to(torch.float64).contiguous()
+        if tuple(dr.shape) != (4, len(phot_names), n):
+            raise ValueError(f"draws must have shape (4, {len(phot_names)}, {n})")
+        d_ptr = C.c_void_p(dr.data_ptr())
+    out_f, out_s = torch.empty_like(rep), torch.empty_like(rep)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _capi.check(lib.sb2_empirical_noise(C.c_void_p(rep.data_ptr()), n, len(phot_names), models, d_ptr, int(seed), int(epoch),
+                                        C.c_void_p(out_f.data_ptr()), C.c_void_p(out_s.data_ptr()), C.c_void_p(st)),
+                "sb2_empirical_noise")
+    if was_numpy:
+        out_f, out_s = out_f.cpu().numpy(), out_s.cpu().numpy()
+    return (out_f, out_s) if return_errors else out_f
+
+
 class ResampledFeatures:
     """Library photometry resident in HBM; a fresh noise realisation of every row per epoch.
 

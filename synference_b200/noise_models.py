@@ -507,6 +507,42 @@ class GeneralEmpiricalUncertaintyModel(EmpiricalUncertaintyModel):
         out_s = np.clip(out_s, self.min_flux_error, self.max_flux_error)
         return (out_f, out_s) if self.return_noise else out_f
 
+    def device_model(self, true_flux_units=None, out_units=None):
+        """This model as the C ABI's ``sb2_empirical_model`` (``include/synference_b200.h``): the interpolation tables,
+        the three units, and the upper-limit rules with their replacement values resolved here (they are constants:
+        ``noise_models.py:882-957``)."""
+        from . import _capi
+        m = _capi.EmpiricalModel()
+        nb = len(self.bin_centers)
+        if nb > _capi.EMP_MAX_BINS:
+            raise ValueError(f"empirical model has {nb} bins; the device table holds {_capi.EMP_MAX_BINS}")
+        m.n_bins, m.extrapolate = nb, int(bool(self.extrapolate))
+        for i in range(nb):
+            m.centers[i], m.median[i], m.stdev[i] = self.bin_centers[i], self.median_error_in_bin[i], self.std_error_in_bin[i]
+
+        def unit(u):
+            return (1, 1.0) if str(u) == "AB" else (0, float(Unit(str(u)).factor))
+        m.internal_is_ab, m.internal_to_jy = unit(self.interpolation_flux_unit)
+        m.in_is_ab, m.in_to_jy = unit(self.flux_unit if true_flux_units is None else true_flux_units)
+        m.out_is_ab, m.out_to_jy = unit(self.flux_unit if out_units is None else out_units)
+        m.sigma_clip = -1.0 if self.sigma_clip is None else float(self.sigma_clip)
+        m.observed_error = int(self.error_type == "observed")
+        m.upper_limits = int(bool(self.upper_limits))
+        m.ul_active = int(bool(self.upper_limits) and self.upper_limit_value is not None)
+        m.snr_threshold = float(self.treat_as_upper_limits_below) if self.treat_as_upper_limits_below is not None else 0.0
+        m.ul_flux, m.ul_scatter_std, m.ul_err = 0.0, -1.0, 0.0
+        if m.ul_active:
+            if self.upper_limit_flux_behaviour == "scatter_limit":
+                m.ul_flux = float(self.upper_limit_value)
+                m.ul_scatter_std = float(self._sigma_sigma_interpolator(self.upper_limit_value))
+            elif self.upper_limit_flux_behaviour == "upper_limit":
+                m.ul_flux = float(self.upper_limit_value)
+            else:
+                m.ul_flux = float(self.upper_limit_flux_behaviour)
+            m.ul_err = float(self._apply_error_behaviour(np.zeros(1), np.ones(1, dtype=bool))[0])
+        m.min_err, m.max_err = float(self.min_flux_error), float(self.max_flux_error)
+        return m
+
     def apply_scalings(self, flux, error, flux_units=None, out_units=None):
         """Deterministic part only: unit conversion, upper-limit replacement, clip."""
         f, e = self._convert_units(flux, error, flux_units)

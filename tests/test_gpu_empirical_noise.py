@@ -1,0 +1,131 @@
+"""GPU parity tests for the empirical uncertainty models on the device: sb2_empirical_noise through
+`apply_empirical_noise_models`, against (1) golden outputs of the reference's own GeneralEmpiricalUncertaintyModel.apply_noise
+(numpy stream seeded, the consumed draws replayed per element) and (2) the float64 oracle for unit / rule combinations.
+
+Tolerance: float64 on both sides; the inverse normal CDF and 10**x come from different math libraries -> rtol 1e-9."""
+
+import os
+
+import numpy as np
+import pytest
+
+import synference_b200 as S
+from oracle import oracle as O
+from tests.test_oracle_golden import EMP_CASES, empirical_case
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_noise_golden.npz"))
+RTOL = 1e-9
+
+
+def host_model(case, **over):
+    """The product's model object with the golden case's binned statistics (already_binned=True path)."""
+    m = empirical_case(case)
+    kw = dict(flux_unit="AB", sigma_clip=m["sigma_clip"], error_type=m["error_type"], upper_limits=m["upper_limits"],
+              treat_as_upper_limits_below=m["snr_threshold"] if m["upper_limits"] else None,
+              upper_limit_flux_behaviour=m["ul_flux_behaviour"], min_flux_error=m["min_err"], max_flux_error=m["max_err"],
+              upper_limit_flux_err_behaviour={"limits": "flux", "limits_const": "sig_1"}.get(case, "flux"), return_noise=True)
+    kw.update(over)
+    mod = S.GeneralEmpiricalUncertaintyModel(m["centers"], None, already_binned=True, bin_median_errors=m["median"],
+                                             bin_std_errors=m["std"], **kw)
+    mod.upper_limit_value = m["upper_limit_value"]
+    return mod
+
+
+@pytest.mark.parametrize("case", list(EMP_CASES))
+def test_golden_outputs_of_the_reference_class(case):
+    mod = host_model(case)
+    f, s = S.apply_empirical_noise_models(G["en_true_ab"][None, :], ["F"], {"F": mod}, N_scatters=1, flux_units="AB",
+                                          normed_flux_units="AB", return_errors=True, draws=G[f"en_{case}_draws"][:, None, :])
+    np.testing.assert_allclose(f[0], G[f"en_{case}_out_flux"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(s[0], G[f"en_{case}_out_sigma"], rtol=RTOL, atol=1e-12)
+
+
+def test_units_rules_and_several_filters_against_the_oracle():
+    """Interpolation in nJy / uJy / AB, inputs in nJy, outputs in AB / uJy / nJy, extrapolation, every upper-limit rule."""
+    rng = np.random.default_rng(3)
+    n = 5000
+    flux_njy = np.abs(rng.lognormal(3.0, 1.5, n)) + 0.01
+    centers = np.geomspace(0.5, 5000.0, 24)
+    med = 2.0 + 0.02 * centers + rng.uniform(0, 0.2, 24)
+    sd = 0.3 + 0.004 * centers
+    cfgs = [
+        dict(iu="nJy", out="AB", extrapolate=False, kw=dict()),
+        dict(iu="uJy", out="uJy", extrapolate=True, kw=dict(sigma_clip=2.5, error_type="observed")),
+        dict(iu="nJy", out="nJy", extrapolate=False, kw=dict(upper_limits=True, treat_as_upper_limits_below=3.0,
+             upper_limit_flux_behaviour=7.5, upper_limit_flux_err_behaviour="max", max_flux_error=40.0)),
+        dict(iu="nJy", out="AB", extrapolate=True, kw=dict(upper_limits=True, treat_as_upper_limits_below=2.0,
+             upper_limit_flux_behaviour="scatter_limit", upper_limit_flux_err_behaviour="upper_limit", error_type="observed")),
+    ]
+    names, models, omodels = [], {}, []
+    size = {"nJy": 1e-9, "uJy": 1e-6, "AB": "AB"}
+    for i, c in enumerate(cfgs):
+        scale = 1e-3 if c["iu"] == "uJy" else 1.0
+        mod = S.GeneralEmpiricalUncertaintyModel(centers * scale, None, flux_unit=c["iu"], already_binned=True,
+                                                 bin_median_errors=med * scale, bin_std_errors=sd * scale,
+                                                 extrapolate=c["extrapolate"], return_noise=True, **c["kw"])
+        if c["kw"].get("upper_limits"):
+            mod.upper_limit_value = 12.0 * scale                       # as _setup_upper_limit_interpolator would leave it
+        names.append(f"F{i}")
+        models[f"F{i}"] = mod
+        kw = c["kw"]
+        om = dict(centers=centers * scale, median=med * scale, std=sd * scale, extrapolate=c["extrapolate"],
+                  flux_unit=size[c["iu"]], interpolation_flux_unit=size[c["iu"]], sigma_clip=kw.get("sigma_clip"),
+                  error_type=kw.get("error_type", "empirical"), upper_limits=kw.get("upper_limits", False),
+                  snr_threshold=kw.get("treat_as_upper_limits_below", 0.0),
+                  upper_limit_value=mod.upper_limit_value, ul_flux_behaviour=kw.get("upper_limit_flux_behaviour", "scatter_limit"),
+                  ul_err_value=0.0, min_err=0.0, max_err=kw.get("max_flux_error", np.inf))
+        if om["upper_limits"]:
+            om["ul_err_value"] = float(mod._apply_error_behaviour(np.zeros(1), np.ones(1, dtype=bool))[0])
+        omodels.append((om, size[c["out"]]))
+    phot = np.repeat(flux_njy[None, :], len(cfgs), 0)
+    draws = np.stack([rng.uniform(1e-6, 1 - 1e-6, (len(cfgs), n)), rng.standard_normal((len(cfgs), n)),
+                      rng.uniform(1e-6, 1 - 1e-6, (len(cfgs), n)), rng.uniform(1e-6, 1 - 1e-6, (len(cfgs), n))])
+    draws[1, 1] = rng.uniform(1e-6, 1 - 1e-6, n)                        # the sigma-clipped filter takes a uniform
+    for out_unit in ("AB", "uJy"):
+        f, s = S.apply_empirical_noise_models(phot, names, models, N_scatters=1, flux_units="nJy", normed_flux_units=out_unit,
+                                              return_errors=True, draws=draws)
+        for i, (om, _) in enumerate(omodels):
+            wf, ws = O.empirical_apply_noise(flux_njy, om, draws[:, i], true_flux_units=1e-9, out_units=size[out_unit])
+            ok = np.isfinite(wf)
+            assert ok.mean() > 0.9 and np.array_equal(np.isfinite(f[i]), ok)
+            np.testing.assert_allclose(f[i][ok], wf[ok], rtol=RTOL, atol=1e-12)
+            oks = np.isfinite(ws)
+            np.testing.assert_allclose(s[i][oks], ws[oks], rtol=RTOL, atol=1e-12)
+    # the upper-limit rules did fire
+    f, s = S.apply_empirical_noise_models(phot, names, models, N_scatters=1, flux_units="nJy", normed_flux_units="nJy",
+                                          return_errors=True, draws=draws)
+    assert (f[2] == 7.5).sum() > 10 and (s[2][f[2] == 7.5] == 40.0).all()
+
+
+def test_philox_mode_statistics_layout_and_errors():
+    import torch
+    rng = np.random.default_rng(8)
+    centers = np.linspace(20.0, 31.0, 16)
+    mod = S.GeneralEmpiricalUncertaintyModel(centers, None, flux_unit="AB", already_binned=True,
+                                             bin_median_errors=0.02 + np.exp((centers - 28) / 1.5), bin_std_errors=np.full(16, 0.01),
+                                             return_noise=True)
+    n_gal, n_sc = 40000, 3
+    phot = rng.uniform(22, 27, (2, n_gal))
+    f, s = S.apply_empirical_noise_models(phot, ["a", "b"], {"a": mod, "b": mod}, N_scatters=n_sc, flux_units="AB",
+                                          normed_flux_units="AB", return_errors=True, seed=5, epoch=0)
+    assert f.shape == (2, n_gal * n_sc)
+    rep = np.repeat(phot, n_sc, axis=1)                                  # np.repeat layout: scatters of a galaxy are adjacent
+    zs = (f - rep) / s
+    assert abs(zs.mean()) < 0.01 and abs(zs.std() - 1) < 0.02            # sigma is drawn per element, mean sigma ~ mu(f)
+    mu = np.interp(rep, centers, mod.median_error_in_bin)
+    assert np.all(s > 0) and abs(np.mean(s / mu) - 1) < 0.05 and abs(np.std(s - mu) - 0.01) < 1e-3
+    assert abs(np.corrcoef(zs[0], zs[1])[0, 1]) < 0.01 and abs(np.corrcoef(zs[0, :-1], zs[0, 1:])[0, 1]) < 0.01
+    f2 = S.apply_empirical_noise_models(phot, ["a", "b"], {"a": mod, "b": mod}, N_scatters=n_sc, flux_units="AB", seed=5, epoch=0)
+    f3 = S.apply_empirical_noise_models(phot, ["a", "b"], {"a": mod, "b": mod}, N_scatters=n_sc, flux_units="AB", seed=5, epoch=1)
+    assert np.array_equal(f, f2) and not np.array_equal(f, f3)
+    t = S.apply_empirical_noise_models(torch.as_tensor(phot, device="cuda"), ["a", "b"], {"a": mod, "b": mod}, N_scatters=n_sc,
+                                       flux_units="AB", seed=5, epoch=0)
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), f)
+    with pytest.raises(ValueError):
+        S.apply_empirical_noise_models(phot, ["a", "b"], {"a": mod}, N_scatters=1)
+    with pytest.raises(ValueError):
+        S.apply_empirical_noise_models(phot, ["a"], {"a": mod, "b": mod}, N_scatters=1)
+    with pytest.raises(ValueError):
+        S.apply_empirical_noise_models(phot, ["a", "b"], [mod, mod])

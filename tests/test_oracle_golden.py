@@ -69,6 +69,36 @@ def test_spectroscopic_path_matches_reference_code():
     np.testing.assert_allclose(flat, 3.0, rtol=1e-13)
 
 
+EMP_CASES = {"plain": dict(), "clip": dict(sigma_clip=2.0),
+             "limits": dict(upper_limits=True, snr_threshold=3.0, ul_flux_behaviour="scatter_limit", error_type="observed",
+                            max_err=5.0),
+             "limits_const": dict(upper_limits=True, snr_threshold=2.0, ul_flux_behaviour="upper_limit", min_err=0.02)}
+
+
+def empirical_case(name):
+    """The oracle's model dict for one of the golden cases (tests/golden/make_golden_from_reference.py)."""
+    m = dict(centers=G[f"en_{name}_centers"], median=G[f"en_{name}_median"], std=G[f"en_{name}_std"], extrapolate=False,
+             flux_unit="AB", interpolation_flux_unit="AB", sigma_clip=None, error_type="empirical", upper_limits=False,
+             snr_threshold=0.0, upper_limit_value=None, ul_flux_behaviour="scatter_limit", ul_err_value=0.0, min_err=0.0,
+             max_err=np.inf)
+    m.update(EMP_CASES[name])
+    if m["upper_limits"]:
+        m["upper_limit_value"] = float(G[f"en_{name}_ul_value"])
+        m["ul_err_value"] = float(G[f"en_{name}_ul_err"])
+    return m
+
+
+@pytest.mark.parametrize("name", list(EMP_CASES))
+def test_empirical_noise_oracle_matches_reference_class(name):
+    """GeneralEmpiricalUncertaintyModel.apply_noise run by the reference's own code with numpy's global stream seeded; the
+    oracle gets the same random numbers per element and must reproduce fluxes and errors."""
+    f, s = O.empirical_apply_noise(G["en_true_ab"], empirical_case(name), G[f"en_{name}_draws"])
+    np.testing.assert_allclose(f, G[f"en_{name}_out_flux"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(s, G[f"en_{name}_out_sigma"], rtol=1e-12, atol=1e-12)
+    if name.startswith("limits"):
+        assert (f == float(G[f"en_{name}_ul_value"])).sum() > 5 or name == "limits"      # some sources became upper limits
+
+
 def test_product_host_code_matches_reference_code():
     """The API-level host functions of the product against the same vectors."""
     import synference_b200 as S
