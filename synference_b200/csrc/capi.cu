@@ -1139,7 +1139,8 @@ int sb2_empirical_noise(const double* flux, int64_t n, int32_t n_filt, const sb2
   long long bx = (n + 255) / 256;
   const long long cap = std::max<long long>(1, (long long)n_sm * 8 / n_filt);
   if (bx > cap) bx = cap;
-  sb2::empirical_noise_kernel<<<dim3((unsigned)bx, (unsigned)n_filt), 256, 0, st>>>(a);
+  if (draws) sb2::empirical_noise_kernel<false><<<dim3((unsigned)bx, (unsigned)n_filt), 256, 0, st>>>(a);
+  else sb2::empirical_noise_kernel<true><<<dim3((unsigned)bx, (unsigned)n_filt), 256, 0, st>>>(a);
   e = cudaGetLastError();
   cudaFreeAsync(dm, st);
   if (e != cudaSuccess) return fail(SB2_ERR_CUDA, cudaGetErrorString(e));

@@ -13,8 +13,9 @@
 // Truncated normals are drawn by inversion, x = Phi^-1(Phi(a) + u (Phi(b) - Phi(a))) evaluated on the tail that keeps
 // precision, so that a test can inject the uniforms and compare with scipy's ppf.  Draws: injected ([4][n_filt][n]: sigma
 // uniform, scatter normal (or uniform when sigma-clipped), re-draw uniform, limit-scatter uniform) or Philox4x32-10 keyed by
-// (seed, epoch) with counter (row, filter).  float64 throughout; one thread per (filter, row); HBM-bound: 8 B read + 16 B
-// written per element (+ 32 B of injected draws in the parity mode).
+// (seed, epoch) with counter (row, filter).  The injected (parity) mode is float64 throughout; the Philox (production) mode
+// evaluates the normal CDF / inverse CDF and Box-Muller in float32.  One thread per (filter, row); 8 B read + 16 B written per
+// element (+ 32 B of injected draws in the parity mode).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -51,20 +52,6 @@ __device__ __forceinline__ double jy_to_ab(double f) { return -2.5 * log10(f) + 
 __device__ __forceinline__ double ab_err_to_jy(double e, double fjy) { return (fjy * e * 2.302585092994046) / 2.5; }
 __device__ __forceinline__ double jy_err_to_ab(double e, double fjy) { return fabs((2.5 / 2.302585092994046) * (e / fjy)); }
 
-// scipy interp1d(kind="linear", bounds_error=False, fill_value=(y0, y_last) | "extrapolate")
-__device__ __forceinline__ double interp_table(const double* x, const double* y, int n, int extrapolate, double v) {
-  if (!(v == v)) return v;
-  if (v < x[0]) { if (!extrapolate) return y[0]; return y[0] + (v - x[0]) * ((y[1] - y[0]) / (x[1] - x[0])); }
-  if (v > x[n - 1]) { if (!extrapolate) return y[n - 1]; return y[n - 2] + (v - x[n - 2]) * ((y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2])); }
-  int lo = 0, hi = n - 1;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (x[mid] <= v) lo = mid; else hi = mid;
-  }
-  const double slope = (y[hi] - y[lo]) / (x[hi] - x[lo]);
-  return slope * (v - x[lo]) + y[lo];
-}
-
 // inverse CDF of the standard normal truncated to [a, b] at probability u
 __device__ __forceinline__ double truncnorm_ppf(double u, double a, double b) {
   if (a > 0.0) {   // work on the mirrored (left) tail, where the CDF values are small and precise
@@ -85,13 +72,59 @@ __device__ __forceinline__ bool below_snr(const EmpiricalModelDev& M, double f, 
   const double snr = fj / ej;
   return !isfinite(snr) || snr < M.snr_threshold;
 }
-__device__ __forceinline__ double sample_sigma(const EmpiricalModelDev& M, double f, double u) {
-  const double mu = interp_table(M.centers, M.median, M.n_bins, M.extrapolate, f);
-  const double ss = fmax(0.0, interp_table(M.centers, M.stdev, M.n_bins, M.extrapolate, f));
-  const double a = (0.0 - mu) / (ss > 1e-9 ? ss : 1.0);
-  return mu + ss * truncnorm_ppf(u, a, INFINITY);
+// mu_sigma(v) and sigma_sigma(v): scipy interp1d(kind="linear", bounds_error=False, fill_value=(y0, y_last) | "extrapolate");
+// the two tables share the abscissa, hence the bin search
+__device__ __forceinline__ void interp_both(const EmpiricalModelDev& M, double v, double& mu, double& ss) {
+  const double* x = M.centers;
+  const int n = M.n_bins;
+  if (!(v == v)) { mu = ss = v; return; }
+  int lo, hi;
+  if (v < x[0]) {
+    if (!M.extrapolate) { mu = M.median[0]; ss = M.stdev[0]; return; }
+    const double d = v - x[0], w = x[1] - x[0];
+    mu = M.median[0] + d * ((M.median[1] - M.median[0]) / w);
+    ss = M.stdev[0] + d * ((M.stdev[1] - M.stdev[0]) / w);
+    return;
+  }
+  if (v > x[n - 1]) {
+    if (!M.extrapolate) { mu = M.median[n - 1]; ss = M.stdev[n - 1]; return; }
+    const double d = v - x[n - 2], w = x[n - 1] - x[n - 2];
+    mu = M.median[n - 2] + d * ((M.median[n - 1] - M.median[n - 2]) / w);
+    ss = M.stdev[n - 2] + d * ((M.stdev[n - 1] - M.stdev[n - 2]) / w);
+    return;
+  }
+  lo = 0; hi = n - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (x[mid] <= v) lo = mid; else hi = mid;
+  }
+  const double d = v - x[lo], w = x[hi] - x[lo];
+  mu = ((M.median[hi] - M.median[lo]) / w) * d + M.median[lo];
+  ss = ((M.stdev[hi] - M.stdev[lo]) / w) * d + M.stdev[lo];
 }
 
+// float32 special functions for the production (Philox) mode: the draw's relative accuracy (1e-6) is far below its spread
+__device__ __forceinline__ double truncnorm_ppf_fast(double u, double a, double b) {
+  const float af = (float)a, bf = (float)b, uf = (float)u;
+  if (af > 0.f) {
+    const float pa = normcdff(-af), pb = isinf(bf) ? 0.f : normcdff(-bf);
+    return (double)(-normcdfinvf(fmaf(1.f - uf, pa - pb, pb)));
+  }
+  const float pa = normcdff(af), pb = isinf(bf) ? 1.f : normcdff(bf);
+  return (double)normcdfinvf(fminf(fmaf(uf, pb - pa, pa), 0.99999994f));
+}
+
+template <bool kFast>
+__device__ __forceinline__ double sample_sigma(const EmpiricalModelDev& M, double f, double u) {
+  double mu, ss;
+  interp_both(M, f, mu, ss);
+  ss = fmax(0.0, ss);
+  const double a = (0.0 - mu) / (ss > 1e-9 ? ss : 1.0);
+  return mu + ss * (kFast ? truncnorm_ppf_fast(u, a, INFINITY) : truncnorm_ppf(u, a, INFINITY));
+}
+
+// kFast: Philox draws + float32 special functions (production); otherwise injected draws, float64 throughout (parity)
+template <bool kFast>
 __global__ void __launch_bounds__(256) empirical_noise_kernel(EmpiricalArgs A) {
   __shared__ EmpiricalModelDev M;
   const int f = blockIdx.y;
@@ -105,19 +138,25 @@ __global__ void __launch_bounds__(256) empirical_noise_kernel(EmpiricalArgs A) {
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.n; r += (long long)gridDim.x * blockDim.x) {
     const long long idx = (long long)f * A.n + r;
     double u_sig, z_noise, u_obs, u_lim;
-    if (A.draws) {
+    if (!kFast) {
       u_sig = A.draws[idx]; z_noise = A.draws[stride + idx]; u_obs = A.draws[2 * stride + idx]; u_lim = A.draws[3 * stride + idx];
     } else {
-      uint32_t a4[4], b4[4];
+      uint32_t a4[4], b4[4] = {0u, 0u, 0u, 0u};
       philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)f, (uint32_t)A.epoch, (uint32_t)A.seed,
                     (uint32_t)(A.seed >> 32) ^ (uint32_t)(A.epoch >> 32), a4);
-      philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)f | 0x80000000u, (uint32_t)A.epoch, (uint32_t)A.seed,
-                    (uint32_t)(A.seed >> 32) ^ (uint32_t)(A.epoch >> 32), b4);
-      // 53-bit uniforms in (0, 1) from pairs of words
-      auto uni = [](uint32_t hi, uint32_t lo) { return (((double)(hi >> 6) * 134217728.0 + (double)(lo >> 5)) + 0.5) * (1.0 / 9007199254740992.0); };
-      u_sig = uni(a4[0], a4[1]); u_obs = uni(a4[2], a4[3]); u_lim = uni(b4[0], b4[1]);
-      const double u_n = uni(b4[2], b4[3]);
-      z_noise = M.sigma_clip >= 0.0 ? u_n : normcdfinv(u_n);
+      if (M.sigma_clip < 0.0)
+        philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)f | 0x80000000u, (uint32_t)A.epoch, (uint32_t)A.seed,
+                      (uint32_t)(A.seed >> 32) ^ (uint32_t)(A.epoch >> 32), b4);
+      // 24-bit uniforms in (0, 1); the scatter normal by Box-Muller in float32 (as depth_noise_kernel)
+      auto uni = [](uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); };
+      u_sig = uni(a4[0]); u_obs = uni(a4[1]); u_lim = uni(a4[2]);
+      if (M.sigma_clip >= 0.0) {
+        z_noise = uni(a4[3]);
+      } else {
+        float sn, cs;
+        sincospif(2.0f * uni(b4[1]), &sn, &cs);
+        z_noise = (double)(sqrtf(-2.0f * logf(uni(b4[0]))) * cs);
+      }
     }
     // 1. to the interpolation unit
     const double fin = A.flux[idx];
@@ -126,19 +165,19 @@ __global__ void __launch_bounds__(256) empirical_noise_kernel(EmpiricalArgs A) {
     else if (M.in_is_ab) fi = ab_to_jy(fin) / M.internal_to_jy;
     else fi = jy_to_ab(fin * M.in_to_jy);
     // 2. sampled uncertainty at the true flux
-    const double sig0 = sample_sigma(M, fi, u_sig);
+    const double sig0 = sample_sigma<kFast>(M, fi, u_sig);
     // 3. scatter, unless the source is already below the SNR threshold
     const bool init_lim = M.upper_limits && below_snr(M, fi, sig0);
     double noisy = fi;
     if (!init_lim) {
-      const double zz = M.sigma_clip >= 0.0 ? truncnorm_ppf(z_noise, -M.sigma_clip, M.sigma_clip) : z_noise;
+      const double zz = M.sigma_clip >= 0.0 ? (kFast ? truncnorm_ppf_fast(z_noise, -M.sigma_clip, M.sigma_clip) : truncnorm_ppf(z_noise, -M.sigma_clip, M.sigma_clip)) : z_noise;
       noisy = fi + (0.0 + sig0 * zz);
     }
     // 4. "observed" errors: drawn again at the noisy flux
-    double sig = M.observed_error ? sample_sigma(M, noisy, u_obs) : sig0;
+    double sig = M.observed_error ? sample_sigma<kFast>(M, noisy, u_obs) : sig0;
     // 5. upper limits
     if (M.upper_limits && M.ul_active && (init_lim || below_snr(M, noisy, sig))) {
-      noisy = M.ul_scatter_std >= 0.0 ? M.ul_flux + (0.0 + M.ul_scatter_std * truncnorm_ppf(u_lim, -3.0, 3.0)) : M.ul_flux;
+      noisy = M.ul_scatter_std >= 0.0 ? M.ul_flux + (0.0 + M.ul_scatter_std * (kFast ? truncnorm_ppf_fast(u_lim, -3.0, 3.0) : truncnorm_ppf(u_lim, -3.0, 3.0))) : M.ul_flux;
       sig = M.ul_err;
     }
     // 6. to the output unit, error clip
