@@ -25,7 +25,7 @@ from .engine import GalaxyParams, SynthEngine, depth_noise_features  # noqa: F40
 from .library import CombinedBasis, GalaxyBasis, GalaxySimulator, create_galaxy  # noqa: F401
 from .features import (ResampledFeatures, apply_empirical_noise_models,  # noqa: F401
                        create_feature_array_from_raw_photometry)
-from .supplementary import (calculate_burstiness, calculate_mass_weighted_age, calculate_sfh_quantile,  # noqa: F401
+from .supplementary import (calculate_burstiness, calculate_mass_weighted_age, calculate_muv, calculate_MUV, calculate_sfh_quantile,  # noqa: F401
                             calculate_sfr, calculate_surviving_mass)
 from .spectral import SpectrumResampler, create_feature_array_from_raw_spectra, transform_spectrum  # noqa: F401
 

@@ -267,6 +267,7 @@ class SynthEngine:
         if self.lib.sb2_device_count() < 1:
             raise RuntimeError("synference_b200: no CUDA device visible; the hot path has no CPU fallback")
         self.tables = t = build_tables(grid, emission_model, emission_key, filters, cosmo, igm, variant)
+        self.tables_lam = np.asarray(grid.lam, dtype=np.float64)
         self.filter_codes = list(filters.filter_codes)
         self.n_filt, self.n_lam, self.n_comp = t["n_filt"], t["n_lam"], t["n_comp"]
         self.k = t["n_age"] * t["n_z"]
@@ -485,6 +486,36 @@ class SynthEngine:
             out[a:b] = w.cpu().numpy()
         return out
 
+
+    def rest_band_flux(self, params: GalaxyParams, lam_lo: float, lam_hi: float):
+        """Observed-frame f_nu [nJy] at base mass averaged over a REST-frame top-hat ``[lam_lo, lam_hi]`` (Angstrom), ``(N,)``
+        float64: the photometry convention of A9 (trapezoid of ``f T / nu`` over the in-band samples divided by that of
+        ``T / nu``) applied to the synthesised spectrum, reduced on the device -- only N numbers come back.  This is what the
+        reference's ``calculate_muv`` measures with its 1500 +- 50 A top-hat (``library.py:100-104, 172-196``)."""
+        import torch
+        lam = np.asarray(self.tables_lam, dtype=np.float64)
+        inb = np.nonzero((lam >= lam_lo) & (lam <= lam_hi))[0]
+        if inb.size < 2:
+            raise ValueError(f"fewer than two wavelength samples in [{lam_lo}, {lam_hi}] A")
+        nu = 2.99792458e18 / lam[inb]
+        w = np.zeros(inb.size)
+        d = np.abs(np.diff(nu))
+        w[:-1] += 0.5 * d
+        w[1:] += 0.5 * d
+        w = w / nu                                   # trapezoid weights of  integral( . T / nu d nu )
+        dev = torch.device("cuda", self.device)
+        wt = torch.as_tensor(w / w.sum(), dtype=torch.float64, device=dev)
+        n = len(params)
+        out = np.empty(n, dtype=np.float64)
+        i0, i1 = int(inb[0]), int(inb[-1]) + 1
+        for a in range(0, n, self.max_batch):
+            b = min(n, a + self.max_batch)
+            dpar = self.to_device(params.slice(slice(a, b)))
+            spec = torch.empty((b - a, self.n_lam), dtype=torch.float32, device=dev)
+            flux = torch.empty((b - a, self.n_filt), dtype=torch.float32, device=dev)
+            self.photometry_device(dpar, flux_base=flux, spectra=spec)
+            out[a:b] = (spec[:, i0:i1].to(torch.float64) @ wt).cpu().numpy()
+        return out
 
     def sfzh(self, params: GalaxyParams):
         """SFZH ``(N, n_age, n_z)`` float64, normalised to 1 per galaxy (host array; the by-products of

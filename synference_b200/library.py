@@ -353,7 +353,8 @@ class GalaxyBasis:
                 if extra_analysis_functions and key == keys[0]:
                     # by-products of the weights (library.py:2593-2601 stores callback results as supp_<name>)
                     supp = _supp.evaluate(extra_analysis_functions, eng.sfzh(p) * 10.0 ** 9, self.grid.log10ages,
-                                          p.redshift, self.cosmo)
+                                          p.redshift, self.cosmo,
+                                          band_flux=lambda lo, hi, eng=eng, p=p: eng.rest_band_flux(p, lo, hi))
                     for name, (vals, units) in supp.items():
                         datasets[f"Galaxies/supp_{name}"] = vals
                         supp_units[name] = units

@@ -14,26 +14,32 @@ name (``library.py``)                 definition                                
 ``calculate_burstiness`` :427         SFR(10 Myr) / SFR(100 Myr)                                 dimensionless
 ``calculate_sfh_quantile`` :468       age by which a fraction of the mass has formed (as coded)  Myr | dimensionless
 ``calculate_surviving_mass`` :512     log10 sum(w * grid.stellar_fraction)                       log10_Msun (scales)
+``calculate_muv`` :172                f_nu through the rest-frame 1500 +- 50 A top-hat            nJy (scales)
+``calculate_MUV`` :199                L_nu through the same top-hat                              erg/s/Hz (scales)
 ====================================  =========================================================  ==================
+
+The two UV ones read the synthesised spectrum of the emission key being processed (the reference returns one value per saved
+spectrum; the library keeps the requested key's): the band average is reduced on the device, ``SynthEngine.rest_band_flux``.
 
 ``sf_hist`` is the mass per age bin of A2 (bin edges at the mid-points of the grid ages, first edge 0); within a bin the mass
 is taken as uniform in age when a timescale cuts through it (pin: the third-party ``Stars.calculate_average_sfr`` is not
-available to check against).  Callbacks that need spectra or lines (mUV, D4000, beta, equivalent widths) are not provided and
-raise ``NotImplementedError`` when requested.
+available to check against).  Callbacks built on third-party ``Sed`` measurements or lines (D4000, beta, equivalent widths)
+are not provided and raise ``NotImplementedError`` when requested.
 """
 
 import numpy as np
 
 from .units import strip_units
 
-__all__ = ["calculate_mass_weighted_age", "calculate_sfr", "calculate_burstiness", "calculate_sfh_quantile",
+__all__ = ["calculate_muv", "calculate_MUV", "calculate_mass_weighted_age", "calculate_sfr", "calculate_burstiness", "calculate_sfh_quantile",
            "calculate_surviving_mass", "evaluate"]
 
 
 class _Context:
     """What a batch offers: ``sf_hist`` (N, n_age) and ``sfzh`` (N, n_age, n_z) in Msun at the base mass, ages [yr]."""
 
-    def __init__(self, sfzh, log10ages, redshift, cosmo):
+    def __init__(self, sfzh, log10ages, redshift, cosmo, band_flux=None):
+        self.band_flux = band_flux        # callable (lam_lo, lam_hi) -> (N,) observed-frame f_nu [nJy] in a rest-frame top-hat
         self.sfzh = sfzh
         self.sf_hist = sfzh.sum(axis=2)
         self.ages = 10.0 ** np.asarray(log10ages, dtype=np.float64)
@@ -57,6 +63,24 @@ def _batched(units):
         fn._sb2_units = units
         return fn
     return deco
+
+
+MUV_BAND = (1450.0, 1550.0)      # tophats = {"MUV": {"lam_eff": 1500 A, "lam_fwhm": 100 A}}  (library.py:100-104)
+
+
+@_batched("nJy")
+def calculate_muv(ctx, cosmo=None):
+    if ctx.band_flux is None:
+        raise ValueError("calculate_muv needs the synthesised spectrum (run it through create_mock_library)")
+    return ctx.band_flux(*MUV_BAND)
+
+
+@_batched("erg/s/Hz")
+def calculate_MUV(ctx, cosmo=None):
+    """Rest-frame L_nu: the observed flux density with the distance factor of A7 taken out again."""
+    c = cosmo or ctx.cosmo
+    dl_cm = np.asarray(strip_units(c.luminosity_distance(ctx.redshift), "cm"), dtype=float)
+    return calculate_muv(ctx) * 1e-32 * 4.0 * np.pi * dl_cm**2 / (1.0 + ctx.redshift)
 
 
 @_batched("Myr")
@@ -110,10 +134,10 @@ calculate_surviving_mass._sb2_units = "log10_Msun"
 def scales_with_mass(units: str) -> str:
     """How create_full_library rescales a supplementary column from the base mass to the galaxy's mass
     (``utils.py:929-988`` check_scaling / check_log_scaling on the unit string): 'linear', 'log' or 'none'."""
-    if "Msun" in units and "log" not in units:
-        return "linear"
-    if "log10" in units and "Msun" in units:
+    if "log" in units:
         return "log"
+    if any(k in units for k in ("Msun", "Jy", "erg")):        # mass, mass / time, flux densities, luminosities
+        return "linear"
     return "none"
 
 
@@ -134,9 +158,9 @@ def check_supported(extra_analysis_functions):
                 "reference) and has no spectrum / line callbacks yet")
 
 
-def evaluate(extra_analysis_functions, sfzh, log10ages, redshift, cosmo):
+def evaluate(extra_analysis_functions, sfzh, log10ages, redshift, cosmo, band_flux=None):
     """``{name: (values (N,), unit string)}`` for one batch (unit strings as unyt would print them)."""
-    ctx = _Context(sfzh, log10ages, redshift, cosmo)
+    ctx = _Context(sfzh, log10ages, redshift, cosmo, band_flux)
     out = {}
     for name, spec in extra_analysis_functions.items():
         fn, args = split(spec)

@@ -353,13 +353,14 @@ def test_supplementary_parameters_through_create_mock_library(tmp_path):
         log_stellar_masses=list(masses), emission_model_key="emergent", out_name="supp_lib", out_dir=str(tmp_path),
         overwrite=True, batch_size=40, mass_weighted_age=S.calculate_mass_weighted_age, sfr_10=(S.calculate_sfr, 10 * S.Myr),
         sfr_100=(S.calculate_sfr, 100 * S.Myr), sfh_quant_50=(S.calculate_sfh_quantile, 0.50, True),
-        burstiness=S.calculate_burstiness)
+        burstiness=S.calculate_burstiness, mUV=(S.calculate_muv, S.Planck18), MUV=S.calculate_MUV)
     lib = S.load_library_from_hdf5(os.path.join(str(tmp_path), "supp_lib.hdf5"))
     names = list(lib["supplementary_parameter_names"])
-    assert names == ["mass_weighted_age", "sfr_10", "sfr_100", "sfh_quant_50", "burstiness"]
-    assert list(lib["supplementary_parameter_units"]) == ["Myr", "Msun/yr", "Msun/yr", "dimensionless", "dimensionless"]
+    assert names == ["mass_weighted_age", "sfr_10", "sfr_100", "sfh_quant_50", "burstiness", "mUV", "MUV"]
+    assert list(lib["supplementary_parameter_units"]) == ["Myr", "Msun/yr", "Msun/yr", "dimensionless", "dimensionless", "nJy",
+                                                          "erg/s/Hz"]
     supp = np.asarray(lib["supplementary_parameters"])
-    assert supp.shape == (5, n) and combined.library_supplementary_parameter_names == names
+    assert supp.shape == (7, n) and combined.library_supplementary_parameter_names == names
     # against the float64 oracle's SFZH
     ages = 10.0 ** np.asarray(grid.log10ages)
     gals = A.galaxies_from_params(basis.params)
@@ -373,6 +374,17 @@ def test_supplementary_parameters_through_create_mock_library(tmp_path):
     ok = supp[2] > 0
     np.testing.assert_allclose(supp[4][ok], (supp[1] / supp[2])[ok], rtol=1e-9)
     assert np.all((supp[3] > 0) & (supp[3] < 1.0))
+    # mUV: the rest-frame 1500 +- 50 A top-hat through the oracle's spectrum, scaled to the galaxy's mass (library.py:172-196)
+    lam = np.asarray(grid.lam)
+    _, spec = O.synthesize(gals, grid.log10ages, grid.metallicity, lam, grid.spectra, [(f.lam, f.t) for f in inst.filters],
+                           key="emergent", fesc=0.1, fesc_ly_alpha=0.1, dust=dict(curve="Calzetti2000"),
+                           igm=(I.INOUE14_LAF, I.INOUE14_DLA), return_spectra=True)
+    tophat = ((lam >= 1450.0) & (lam <= 1550.0)).astype(float)
+    want_muv = np.array([O.apply_filter(spec[i], lam, lam, tophat, "nu") for i in range(n)]) * 10.0 ** masses / 1e9
+    np.testing.assert_allclose(supp[5], want_muv, rtol=1e-5)
+    z = np.asarray(d["redshift"], dtype=float)
+    dl = np.array([O.luminosity_distance_cm(zz) for zz in z])
+    np.testing.assert_allclose(supp[6], want_muv * 1e-32 * 4 * np.pi * dl**2 / (1 + z), rtol=2e-5)
     with pytest.raises(NotImplementedError):
         basis.create_mock_library(log_stellar_masses=list(masses), emission_model_key="emergent", out_name="supp_bad",
                                   out_dir=str(tmp_path), overwrite=True, beta=lambda galaxy: 0.0)
