@@ -156,3 +156,37 @@ def test_feature_array_from_raw_spectra():
     with pytest.raises(ValueError):
         create_feature_array_from_raw_spectra(lib, tw, params, ["redshift", "log_mass"], extra_features=["nope"],
                                               resample_wavelengths=ow, inst_resolution_wavelengths=rw, inst_resolution_r=rr)
+
+
+def test_cfg5_chain_engine_spectra_to_prism_pixels_on_device():
+    """BASELINE cfg 5: cfg 2 physics with spectra + photometry out.  The contraction kernel's full-wavelength output stays on
+    the device, the resample kernel turns it into ~1000 PRISM-like pixels; both against the float64 oracle chain."""
+    import torch
+    from oracle import adapter as A
+    from synference_b200 import igm as I
+    from synference_b200.configs import make_workload
+    from synference_b200.engine import SynthEngine
+    n = 48
+    w = make_workload("cfg2", n)
+    eng = SynthEngine(w.grid, w.emission_model, w.emission_key, w.filters, max_batch=4096)
+    dpar = eng.to_device(w.params)
+    spec = torch.empty((n, eng.n_lam), dtype=torch.float32, device="cuda")
+    flux = torch.empty((n, eng.n_filt), dtype=torch.float32, device="cuda")
+    eng.photometry_device(dpar, flux_base=flux, spectra=spec)
+    lam_um = np.asarray(w.grid.lam) * 1e-4
+    ow = np.linspace(0.6, 5.3, 1000)
+    rw = np.linspace(0.55, 5.4, 80)
+    rr = 30.0 + 270.0 * ((rw - 0.55) / 4.85) ** 1.3
+    plan = SpectrumResampler(lam_um, ow, rw, rr)
+    z = np.asarray(w.params.redshift, dtype=np.float64)
+    px = plan.transform(spec, torch.as_tensor(z, device="cuda")).cpu().numpy()
+    em = w.emission_model
+    want_flux, want_spec = O.synthesize(A.galaxies_from_params(w.params), w.grid.log10ages, w.grid.metallicity,
+                                        np.asarray(w.grid.lam), w.grid.spectra, [(f.lam, f.t) for f in w.filters],
+                                        key=w.emission_key, fesc=float(em.fesc), fesc_ly_alpha=float(em.fesc_ly_alpha),
+                                        dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA), return_spectra=True)
+    want_px = np.stack([O.transform_spectrum(lam_um, want_spec[i], z[i], ow, rw, rr)[1] for i in range(n)])
+    close(px, want_px)
+    from tests.helpers import assert_flux_close
+    assert_flux_close(flux.cpu().numpy(), want_flux)
+    plan.close(); eng.close()
