@@ -262,6 +262,11 @@ typedef struct sb2_empirical_model {
   double ul_scatter_std;      /* "scatter_limit": std of the +-3 sigma truncated normal added to ul_flux; < 0: none */
   double ul_err;              /* replacement error (interpolation unit)                                            */
   double min_err, max_err;    /* final clip of the error (output unit)                                             */
+  /* AsinhEmpiricalUncertaintyModel (noise_models.py:443-635): outputs are asinh magnitudes with softening asinh_b [Jy]
+   * (utils.py:647-704).  asinh_mode 0: general model above; 1: tables in asinh magnitudes; 2: tables in the linear unit
+   * internal_to_jy.  observed_error = (error_type != "empirical"); the upper-limit fields and out_* are unused.         */
+  int32_t asinh_mode, reserved_;
+  double asinh_b;
   double centers[SB2_EMP_MAX_BINS], median[SB2_EMP_MAX_BINS], stdev[SB2_EMP_MAX_BINS];
 } sb2_empirical_model;
 /* flux: device float64 [n_filt][n] (the reference's (N_f, N_rows) layout); models: HOST array [n_filt];

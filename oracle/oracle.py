@@ -602,6 +602,50 @@ def empirical_apply_noise(flux, model, draws, true_flux_units=None, out_units=No
     return of, np.clip(os_, model["min_err"], model["max_err"])
 
 
+def asinh_mag(f_jy, b_jy):
+    """utils.py:647-675"""
+    return -2.5 * np.log10(np.e) * (np.arcsinh(np.asarray(f_jy, dtype=float) / (2 * b_jy)) + np.log(b_jy / 3631.0))
+
+
+def asinh_mag_err(f_jy, e_jy, b_jy):
+    """utils.py:678-704"""
+    return 2.5 * np.log10(np.e) * np.asarray(e_jy, dtype=float) / np.sqrt(np.asarray(f_jy, dtype=float) ** 2 + (2 * b_jy) ** 2)
+
+
+def empirical_asinh_apply_noise(flux_jy, model, draws):
+    """noise_models.py:507-557 (AsinhEmpiricalUncertaintyModel.apply_noise) with injected draws (3, n): sigma uniform,
+    scatter normal, second sigma uniform.  ``model``: dict(centers, median, std, extrapolate, b [Jy], interpolation unit
+    ("asinh" or the size of a linear unit in Jy), error_type, min_err, max_err).  Returns (asinh magnitudes, errors)."""
+    from scipy import stats
+    c, med, sd = (np.asarray(model[k], dtype=float) for k in ("centers", "median", "std"))
+
+    def interp(y, v):
+        out = np.interp(v, c, y)
+        if model.get("extrapolate", False):
+            out = np.where(v < c[0], y[0] + (v - c[0]) * (y[1] - y[0]) / (c[1] - c[0]), out)
+            out = np.where(v > c[-1], y[-2] + (v - c[-2]) * (y[-1] - y[-2]) / (c[-1] - c[-2]), out)
+        return out
+
+    def sample(v, u):
+        mu, ss = interp(med, v), np.maximum(0, interp(sd, v))
+        return mu + ss * stats.truncnorm.ppf(u, (0 - mu) / np.where(ss > 1e-9, ss, 1), np.inf)
+
+    f = np.asarray(flux_jy, dtype=float)
+    b, iu = model["b"], model["interpolation_flux_unit"]
+    if iu == "asinh":
+        m_true = asinh_mag(f, b)
+        e0 = sample(m_true, draws[0])
+        m_noisy = m_true + (0.0 + e0 * draws[1])
+        err = e0 if model["error_type"] == "empirical" else sample(m_noisy, draws[2])
+    else:
+        e0 = sample(f / iu, draws[0]) * iu
+        noisy = f + (0.0 + e0 * draws[1])
+        m_noisy = asinh_mag(noisy, b)
+        e1 = sample(noisy / iu, draws[2]) * iu if model["error_type"] == "empirical" else e0
+        err = asinh_mag_err(noisy, e1, b)
+    return m_noisy, np.clip(err, model["min_err"], model["max_err"])
+
+
 def depth_model_apply_noise(flux_jy, depth_ab, z, sigma_level=5.0, out_units=None,
                             min_err=0.0, max_err=np.inf):
     """DepthUncertaintyModel.apply_noise with the normal draws ``z`` injected

@@ -81,6 +81,7 @@ class EmpiricalModel(C.Structure):
         ("internal_to_jy", C.c_double), ("in_to_jy", C.c_double), ("out_to_jy", C.c_double),
         ("sigma_clip", C.c_double), ("snr_threshold", C.c_double), ("ul_flux", C.c_double),
         ("ul_scatter_std", C.c_double), ("ul_err", C.c_double), ("min_err", C.c_double), ("max_err", C.c_double),
+        ("asinh_mode", C.c_int32), ("reserved_", C.c_int32), ("asinh_b", C.c_double),
         ("centers", C.c_double * EMP_MAX_BINS), ("median", C.c_double * EMP_MAX_BINS), ("stdev", C.c_double * EMP_MAX_BINS),
     ]
 

@@ -1112,7 +1112,7 @@ int sb2_empirical_noise(const double* flux, int64_t n, int32_t n_filt, const sb2
     if (m.n_bins < 2 || m.n_bins > SB2_EMP_MAX_BINS) return fail(SB2_ERR_INVALID, "empirical model: 2 <= n_bins <= SB2_EMP_MAX_BINS");
     for (int i = 1; i < m.n_bins; ++i)
       if (!(m.centers[i] > m.centers[i - 1])) return fail(SB2_ERR_INVALID, "empirical model: bin centres must increase");
-    if ((!m.internal_is_ab && !(m.internal_to_jy > 0)) || (!m.in_is_ab && !(m.in_to_jy > 0)) || (!m.out_is_ab && !(m.out_to_jy > 0)))
+    if ((!m.internal_is_ab && m.asinh_mode != 1 && !(m.internal_to_jy > 0)) || (!m.in_is_ab && !(m.in_to_jy > 0)) || (!m.out_is_ab && !(m.out_to_jy > 0)))
       return fail(SB2_ERR_INVALID, "empirical model: linear units need a positive size in Jy");
     sb2::EmpiricalModelDev& d = h[f];
     d.n_bins = m.n_bins; d.extrapolate = m.extrapolate; d.internal_is_ab = m.internal_is_ab; d.in_is_ab = m.in_is_ab;
@@ -1120,6 +1120,10 @@ int sb2_empirical_noise(const double* flux, int64_t n, int32_t n_filt, const sb2
     d.internal_to_jy = m.internal_to_jy; d.in_to_jy = m.in_to_jy; d.out_to_jy = m.out_to_jy; d.sigma_clip = m.sigma_clip;
     d.snr_threshold = m.snr_threshold; d.ul_flux = m.ul_flux; d.ul_scatter_std = m.ul_scatter_std; d.ul_err = m.ul_err;
     d.min_err = m.min_err; d.max_err = m.max_err;
+    d.asinh_mode = m.asinh_mode; d.pad_ = 0; d.asinh_b = m.asinh_b;
+    if (m.asinh_mode < 0 || m.asinh_mode > 2 || (m.asinh_mode && !(m.asinh_b > 0)))
+      return fail(SB2_ERR_INVALID, "empirical model: asinh_mode in {0, 1, 2}, asinh_b > 0");
+    if (m.asinh_mode == 2 && !(m.internal_to_jy > 0)) return fail(SB2_ERR_INVALID, "empirical model: asinh_mode 2 needs a linear interpolation unit");
     std::memcpy(d.centers, m.centers, sizeof(d.centers));
     std::memcpy(d.median, m.median, sizeof(d.median));
     std::memcpy(d.stdev, m.stdev, sizeof(d.stdev));

@@ -33,6 +33,8 @@ struct EmpiricalModelDev {
   double sigma_clip;                               // < 0: plain normal
   double snr_threshold, ul_flux, ul_scatter_std, ul_err;   // ul_scatter_std < 0: ul_flux is the replacement value itself
   double min_err, max_err;
+  int asinh_mode, pad_;                            // 0: general model; 1: asinh magnitudes, tables in asinh mags;
+  double asinh_b;                                  // 2: asinh magnitudes out, tables in a linear flux unit.  b in Jy
   double centers[kEmpMaxBins], median[kEmpMaxBins], stdev[kEmpMaxBins];
 };
 
@@ -60,6 +62,14 @@ __device__ __forceinline__ double truncnorm_ppf(double u, double a, double b) {
   }
   const double pa = normcdf(a), pb = isinf(b) ? 1.0 : normcdf(b);
   return normcdfinv(pa + u * (pb - pa));
+}
+
+// utils.py:647-704: asinh magnitudes with softening b [Jy]
+__device__ __forceinline__ double jy_to_asinh(double f, double b) {
+  return -1.0857362047581296 * (asinh(f / (2.0 * b)) + log(b / 3631.0));
+}
+__device__ __forceinline__ double jy_err_to_asinh(double f, double e, double b) {
+  return 1.0857362047581296 * e / sqrt(f * f + (2.0 * b) * (2.0 * b));
 }
 
 __device__ __forceinline__ void to_jy(const EmpiricalModelDev& M, double f, double e, double& fj, double& ej) {
@@ -158,8 +168,28 @@ __global__ void __launch_bounds__(256) empirical_noise_kernel(EmpiricalArgs A) {
         z_noise = (double)(sqrtf(-2.0f * logf(uni(b4[0]))) * cs);
       }
     }
-    // 1. to the interpolation unit
     const double fin = A.flux[idx];
+    if (M.asinh_mode) {   // AsinhEmpiricalUncertaintyModel.apply_noise (noise_models.py:507-557); the scatter is always normal
+      const double fjy = M.in_is_ab ? ab_to_jy(fin) : fin * M.in_to_jy;
+      double m_noisy, err;
+      if (M.asinh_mode == 1) {
+        const double m_true = jy_to_asinh(fjy, M.asinh_b);
+        const double e0 = sample_sigma<kFast>(M, m_true, u_sig);
+        m_noisy = m_true + (0.0 + e0 * z_noise);
+        err = M.observed_error ? sample_sigma<kFast>(M, m_noisy, u_obs) : e0;
+      } else {
+        const double e0 = sample_sigma<kFast>(M, fjy / M.internal_to_jy, u_sig) * M.internal_to_jy;
+        const double njy = fjy + (0.0 + e0 * z_noise);
+        m_noisy = jy_to_asinh(njy, M.asinh_b);
+        // (in this branch the reference re-draws for error_type "empirical" and keeps the first draw otherwise)
+        const double e1 = M.observed_error ? e0 : sample_sigma<kFast>(M, njy / M.internal_to_jy, u_obs) * M.internal_to_jy;
+        err = jy_err_to_asinh(njy, e1, M.asinh_b);
+      }
+      A.out_flux[idx] = m_noisy;
+      if (A.out_sigma) A.out_sigma[idx] = fmin(fmax(err, M.min_err), M.max_err);
+      continue;
+    }
+    // 1. to the interpolation unit
     double fi;
     if (M.in_is_ab == M.internal_is_ab) fi = M.in_is_ab ? fin : fin * (M.in_to_jy / M.internal_to_jy);
     else if (M.in_is_ab) fi = ab_to_jy(fin) / M.internal_to_jy;

@@ -147,7 +147,7 @@ def apply_empirical_noise_models(photometry_array, phot_names, empirical_noise_m
     import torch
 
     from . import _capi
-    from .noise_models import GeneralEmpiricalUncertaintyModel
+    from .noise_models import AsinhEmpiricalUncertaintyModel, GeneralEmpiricalUncertaintyModel
     if not isinstance(empirical_noise_models, dict):
         raise ValueError("empirical_noise_models must be a dictionary")
     for name in phot_names:
@@ -162,8 +162,8 @@ def apply_empirical_noise_models(photometry_array, phot_names, empirical_noise_m
     models = (_capi.EmpiricalModel * len(phot_names))()
     for i, name in enumerate(phot_names):
         mod = empirical_noise_models[name]
-        if not isinstance(mod, GeneralEmpiricalUncertaintyModel):
-            raise NotImplementedError(f"{type(mod).__name__}: only GeneralEmpiricalUncertaintyModel runs on the device so far")
+        if not isinstance(mod, (GeneralEmpiricalUncertaintyModel, AsinhEmpiricalUncertaintyModel)):
+            raise NotImplementedError(f"{type(mod).__name__} has no device form (General / Asinh empirical models do)")
         models[i] = mod.device_model(true_flux_units=flux_units, out_units=normed_flux_units)
     dev = torch.device("cuda", int(device))
     was_numpy = not isinstance(photometry_array, torch.Tensor)

@@ -328,6 +328,29 @@ class AsinhEmpiricalUncertaintyModel(EmpiricalUncertaintyModel):
         final = np.clip(final, self.min_flux_error, self.max_flux_error)
         return (m_noisy, final) if self.return_noise else m_noisy
 
+    def device_model(self, true_flux_units=None, out_units=None):
+        """This model as the C ABI's ``sb2_empirical_model`` (asinh modes; ``out_units`` has no effect: asinh magnitudes)."""
+        from . import _capi
+        m = _capi.EmpiricalModel()
+        nb = len(self.bin_centers)
+        if nb > _capi.EMP_MAX_BINS:
+            raise ValueError(f"empirical model has {nb} bins; the device table holds {_capi.EMP_MAX_BINS}")
+        m.n_bins, m.extrapolate = nb, int(bool(self.extrapolate))
+        for i in range(nb):
+            m.centers[i], m.median[i], m.stdev[i] = self.bin_centers[i], self.median_error_in_bin[i], self.std_error_in_bin[i]
+        u = "Jy" if true_flux_units is None else true_flux_units
+        m.in_is_ab, m.in_to_jy = (1, 1.0) if str(u) == "AB" else (0, float(Unit(str(u)).factor))
+        m.out_is_ab, m.out_to_jy, m.internal_is_ab = 0, 1.0, 0
+        if self.interpolation_flux_unit == "asinh":
+            m.asinh_mode, m.internal_to_jy = 1, 1.0
+        else:
+            m.asinh_mode, m.internal_to_jy = 2, float(Unit(str(self.interpolation_flux_unit)).factor)
+        m.asinh_b = float(self.b.value)
+        m.observed_error = int(self.error_type != "empirical")
+        m.sigma_clip, m.upper_limits, m.ul_active, m.ul_scatter_std = -1.0, 0, 0, -1.0
+        m.min_err, m.max_err = float(self.min_flux_error), float(self.max_flux_error)
+        return m
+
     def apply_scalings(self, flux, error, **kwargs):
         if kwargs:
             print(f"WARNING {kwargs} arguments will have no effect with this model. Input must be in Jy.")

@@ -129,3 +129,30 @@ def test_philox_mode_statistics_layout_and_errors():
         S.apply_empirical_noise_models(phot, ["a"], {"a": mod, "b": mod}, N_scatters=1)
     with pytest.raises(ValueError):
         S.apply_empirical_noise_models(phot, ["a", "b"], [mod, mod])
+
+
+@pytest.mark.parametrize("case", ["asinh", "asinh_observed", "asinh_flux_interp"])
+def test_asinh_model_golden_outputs_of_the_reference_class(case):
+    """AsinhEmpiricalUncertaintyModel on the device (noise_models.py:507-557; asinh magnitudes, utils.py:647-704)."""
+    from synference_b200.units import Quantity
+    from tests.test_oracle_golden import ASINH_CASES
+    kw = ASINH_CASES[case]
+    mod = S.AsinhEmpiricalUncertaintyModel(error_type=kw["error_type"], max_flux_error=kw["max_err"], return_noise=True,
+                                           interpolation_flux_unit="asinh" if kw["interpolation_flux_unit"] == "asinh" else "nJy")
+    mod.bin_centers, mod.median_error_in_bin, mod.std_error_in_bin = (G[f"ea_{case}_centers"], G[f"ea_{case}_median"],
+                                                                      G[f"ea_{case}_std"])
+    mod.b = Quantity(float(G[f"ea_{case}_b"]), "Jy")
+    mod._create_interpolators()
+    n = G["ea_true_jy"].size
+    draws = np.full((4, 1, n), 0.5)
+    draws[:3, 0] = G[f"ea_{case}_draws"]
+    m, e = S.apply_empirical_noise_models(G["ea_true_jy"][None, :], ["F"], {"F": mod}, N_scatters=1, flux_units="Jy",
+                                          return_errors=True, draws=draws)
+    np.testing.assert_allclose(m[0], G[f"ea_{case}_out_mag"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(e[0], G[f"ea_{case}_out_err"], rtol=RTOL, atol=1e-12)
+    # inputs in nJy give the same magnitudes; the Philox mode runs and keeps the noise level
+    m2 = S.apply_empirical_noise_models(G["ea_true_jy"][None, :] * 1e9, ["F"], {"F": mod}, N_scatters=1, flux_units="nJy", draws=draws)
+    np.testing.assert_allclose(m2[0], m[0], rtol=1e-9)
+    mp, ep = S.apply_empirical_noise_models(np.repeat(G["ea_true_jy"][None, :], 1, 0), ["F"], {"F": mod}, N_scatters=200,
+                                            flux_units="Jy", return_errors=True, seed=3)
+    assert np.isfinite(mp).all() and abs(np.median(ep) / np.median(e[0]) - 1) < 0.05

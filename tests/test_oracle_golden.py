@@ -99,6 +99,26 @@ def test_empirical_noise_oracle_matches_reference_class(name):
         assert (f == float(G[f"en_{name}_ul_value"])).sum() > 5 or name == "limits"      # some sources became upper limits
 
 
+ASINH_CASES = {"asinh": dict(error_type="empirical", interpolation_flux_unit="asinh", max_err=np.inf),
+               "asinh_observed": dict(error_type="observed", interpolation_flux_unit="asinh", max_err=0.8),
+               "asinh_flux_interp": dict(error_type="empirical", interpolation_flux_unit=1e-9, max_err=np.inf)}
+
+
+def asinh_case(name):
+    m = dict(centers=G[f"ea_{name}_centers"], median=G[f"ea_{name}_median"], std=G[f"ea_{name}_std"], extrapolate=False,
+             b=float(G[f"ea_{name}_b"]), min_err=0.0)
+    m.update(ASINH_CASES[name])
+    return m
+
+
+@pytest.mark.parametrize("name", [k for k in ASINH_CASES if f"ea_{k}_out_mag" in G.files])
+def test_asinh_noise_oracle_matches_reference_class(name):
+    """AsinhEmpiricalUncertaintyModel.apply_noise by the reference's own code (global numpy stream seeded, draws replayed)."""
+    m, e = O.empirical_asinh_apply_noise(G["ea_true_jy"], asinh_case(name), G[f"ea_{name}_draws"])
+    np.testing.assert_allclose(m, G[f"ea_{name}_out_mag"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(e, G[f"ea_{name}_out_err"], rtol=1e-12, atol=1e-12)
+
+
 def test_product_host_code_matches_reference_code():
     """The API-level host functions of the product against the same vectors."""
     import synference_b200 as S
