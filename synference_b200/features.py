@@ -43,13 +43,15 @@ def create_feature_array_from_raw_photometry(
         min_flux_pc_error: float = 0.0, norm_mag_limit: float = 50.0, remove_nan_inf: bool = True,
         photometry_to_remove: Optional[list] = None, drop_dropouts: bool = False,
         drop_dropout_fraction: float = 1.0, parameter_array=None, normals=None, seed: int = 0,
-        epoch: int = 0, device: int = 0, return_torch: bool = False):
+        epoch: int = 0, device: int = 0, return_torch: bool = False, empirical_noise_models=None):
     """``(N_filters, N_gal)`` library photometry -> ``(feature_array (N_rows, N_feat) float32,
     feature_names, parameter_array (N_rows, N_par) | None)``.
 
     ``scatter_fluxes`` is the number of noisy replicas per galaxy (0/False: no scatter, one row per
     galaxy).  With ``normals`` (``(N_filters, N_rows)`` float64) the scatter is bit-exact with numpy's
     ``flux + np.random.normal(0, sigma)`` for the same draws; otherwise Philox4x32-10(seed, epoch).
+    ``empirical_noise_models`` (``{filter name: model}``, instead of ``depths``) scatters with the per-filter empirical models
+    on the device (``sbi_runner.py:1678-1692``): the models hand back magnitudes and their errors directly.
     """
     import torch
     if normed_flux_units != "AB":
@@ -70,7 +72,10 @@ def create_feature_array_from_raw_photometry(
     grid = grid * _TO_NJY[str(raw_observation_units)]
     n_filt, n_gal = grid.shape
     n_sc = int(scatter_fluxes) if scatter_fluxes else 1
-    if scatter_fluxes:
+    empirical = bool(scatter_fluxes) and depths is None and empirical_noise_models is not None
+    if empirical:
+        sigma = None
+    elif scatter_fluxes:
         assert depths is not None, "If scattering fluxes, depths or empirical noise models must be provided."
         if isinstance(depths, dict):  # keyed by filter name (sbi_runner.py:1639-1645)
             vals = [depths[n] for n in names]
@@ -86,11 +91,20 @@ def create_feature_array_from_raw_photometry(
     else:
         sigma = np.zeros(n_filt)
         normals = torch.zeros((n_filt, n_gal), dtype=torch.float64, device=dev)
-    flux_gf = grid.t().contiguous()                                   # (n_gal, n_filt), kernel layout
-    _, _, feat = depth_noise_features(flux_gf, sigma, n_scatter=n_sc, normals=normals, seed=seed, epoch=epoch,
-                                      norm_mag_limit=norm_mag_limit, min_flux_pc_error=min_flux_pc_error,
-                                      want_flux=False, want_features=True, device=device)
-    mags, errs = feat[:, :n_filt], feat[:, n_filt:]
+    if empirical:
+        sub = {k: empirical_noise_models[k] for k in names} if all(k in empirical_noise_models for k in names) \
+            else empirical_noise_models
+        m, e = apply_empirical_noise_models(grid, names, sub, N_scatters=n_sc, flux_units="nJy", return_errors=True,
+                                            normed_flux_units="AB", seed=seed, epoch=epoch, device=device)
+        mags = torch.clamp(m.t(), max=norm_mag_limit).to(torch.float32)     # sbi_runner.py:1927-1932
+        mags = torch.where(torch.isnan(m.t()), torch.full_like(mags, float("nan")), mags)
+        errs = e.t().to(torch.float32)
+    else:
+        flux_gf = grid.t().contiguous()                                   # (n_gal, n_filt), kernel layout
+        _, _, feat = depth_noise_features(flux_gf, sigma, n_scatter=n_sc, normals=normals, seed=seed, epoch=epoch,
+                                          norm_mag_limit=norm_mag_limit, min_flux_pc_error=min_flux_pc_error,
+                                          want_flux=False, want_features=True, device=device)
+        mags, errs = feat[:, :n_filt], feat[:, n_filt:]
     feature_names = list(names)
     if normalize_method is not None:
         if normalize_method not in names:

@@ -156,3 +156,24 @@ def test_asinh_model_golden_outputs_of_the_reference_class(case):
     mp, ep = S.apply_empirical_noise_models(np.repeat(G["ea_true_jy"][None, :], 1, 0), ["F"], {"F": mod}, N_scatters=200,
                                             flux_units="Jy", return_errors=True, seed=3)
     assert np.isfinite(mp).all() and abs(np.median(ep) / np.median(e[0]) - 1) < 0.05
+
+
+def test_feature_builder_with_empirical_models():
+    """create_feature_array_from_raw_photometry(..., empirical_noise_models=...) (sbi_runner.py:1678-1692): rows are the
+    models' noisy AB magnitudes (clipped at norm_mag_limit) followed by their errors."""
+    rng = np.random.default_rng(6)
+    centers = np.linspace(20.0, 31.0, 16)
+    mod = S.GeneralEmpiricalUncertaintyModel(centers, None, flux_unit="AB", already_binned=True,
+                                             bin_median_errors=0.02 + np.exp((centers - 28) / 1.5), bin_std_errors=np.full(16, 0.01),
+                                             return_noise=True)
+    names = ["a", "b", "c"]
+    grid = np.abs(rng.lognormal(4.0, 1.0, (3, 2000))) + 1.0                    # nJy
+    feat, fnames, par = S.create_feature_array_from_raw_photometry(
+        grid, names, scatter_fluxes=2, empirical_noise_models={k: mod for k in names}, include_errors_in_feature_array=True,
+        parameter_array=rng.uniform(0, 1, (2000, 2)), seed=11)
+    assert feat.shape == (4000, 6) and feat.dtype == np.float32 and fnames == names + [f"unc_{k}" for k in names]
+    m0 = -2.5 * np.log10(np.repeat(grid, 2, axis=1).T * 1e-9) + 8.90
+    zs = (feat[:, :3] - m0) / feat[:, 3:]
+    assert abs(zs.mean()) < 0.05 and abs(zs.std() - 1) < 0.05 and par.shape == (4000, 2)
+    mu = np.interp(m0, centers, mod.median_error_in_bin)
+    assert abs(np.mean(feat[:, 3:] / mu) - 1) < 0.05
