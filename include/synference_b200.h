@@ -214,6 +214,14 @@ int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, 
                              uint64_t seed, uint64_t epoch, double norm_mag_limit, double* out_flux,
                              double* out_sigma, float* out_feat, void* stream);
 
+/* Same with several depth sets (2-D `depths` of SBI_Fitter._apply_depths, sbi_runner.py:626-647): sigma_sets is device
+ * float64 [n_sets][n_filt]; set_index device int32 [n_filt][n_scatter] says which set the rows [j*n_gal, (j+1)*n_gal) of
+ * filter f use (the reference draws it with np.random.randint and expands it with np.repeat(..., n, axis=1)).           */
+int sb2_depth_noise_features_sets(const double* flux, int64_t n_gal, int32_t n_filt, int32_t n_scatter,
+                                  const double* sigma_sets, int32_t n_sets, const int32_t* set_index,
+                                  double min_flux_pc_error, const double* normals, uint64_t seed, uint64_t epoch,
+                                  double norm_mag_limit, double* out_flux, double* out_sigma, float* out_feat, void* stream);
+
 /* ---- Spectroscopic training path (cfg 5): library spectrum -> instrument-frame pixels ------------------------------
  * Replaces the per-galaxy Python loop of SBI_Fitter.create_feature_array_from_raw_spectra (sbi_runner.py:1322-1334) over
  * transform_spectrum (utils.py:185-254): redshift the axis, convolve with the per-pixel Gaussian of

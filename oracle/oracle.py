@@ -662,11 +662,18 @@ def depth_model_apply_noise(flux_jy, depth_ab, z, sigma_level=5.0, out_units=Non
 # --------------------------------------------------------------------------------------
 # sbi_runner.py:580-691 _apply_depths ; :1698-1716 AB features ; :1927-1932 clip
 # --------------------------------------------------------------------------------------
-def apply_depths(phot, depths_std, z, n_scatters, min_flux_pc_error=0.0):
-    """phot (m, n) -> (m, n_scatters*n) noisy copy and the sigma used; ``z`` are injected normals."""
+def apply_depths(phot, depths_std, z, n_scatters, min_flux_pc_error=0.0, depth_indices=None):
+    """phot (m, n) -> (m, n_scatters*n) noisy copy and the sigma used; ``z`` are injected normals.
+    2-D ``depths_std`` (k, m) with ``depth_indices`` (m, n_scatters): sbi_runner.py:626-647 -- the picked set is expanded with
+    ``np.repeat(..., n, axis=1)``, i.e. columns [j n, (j+1) n) of the repeated array use the set drawn for (row, j)."""
     m, n = phot.shape
     rep = np.repeat(phot, n_scatters, axis=1)
-    std = np.repeat(np.asarray(depths_std, dtype=float)[:, None], n_scatters * n, axis=1)
+    depths_std = np.asarray(depths_std, dtype=float)
+    if depths_std.ndim == 2:
+        sel = depths_std[np.asarray(depth_indices), np.arange(m)[:, None]]       # (m, n_scatters)
+        std = np.repeat(sel, n, axis=1)
+    else:
+        std = np.repeat(depths_std[:, None], n_scatters * n, axis=1)
     if min_flux_pc_error > 0.0:
         std = np.maximum(std, rep * min_flux_pc_error / 100.0)
     return rep + (0 + std * z), std

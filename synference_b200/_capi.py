@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     "sb2_synth_photometry", "sb2_synth_photometry_host", "sb2_depth_noise_features", "sb2_last_stage_ms", "sb2_wait_debug",
     "sb2_synth_photometry_host_submit", "sb2_synth_photometry_host_wait",
     "sb2_resampler_create", "sb2_resampler_destroy", "sb2_resample_spectra", "sb2_resample_spectra_host", "sb2_resample_last_ms",
-    "sb2_empirical_noise",
+    "sb2_empirical_noise", "sb2_depth_noise_features_sets",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -118,6 +118,9 @@ def load():
     lib.sb2_last_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.sb2_depth_noise_features.argtypes = [
         C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_uint64,
+        C.c_uint64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sb2_depth_noise_features_sets.argtypes = [
+        C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_uint64,
         C.c_uint64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sb2_resampler_create.argtypes = [C.POINTER(ResampleDesc), C.c_int, C.POINTER(C.c_void_p)]
     lib.sb2_resampler_destroy.argtypes = [C.c_void_p]

@@ -914,6 +914,27 @@ int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, 
   return SB2_OK;
 }
 
+int sb2_depth_noise_features_sets(const double* flux, int64_t n_gal, int32_t n_filt, int32_t n_scatter,
+                                  const double* sigma_sets, int32_t n_sets, const int32_t* set_index,
+                                  double min_flux_pc_error, const double* normals, uint64_t seed, uint64_t epoch,
+                                  double norm_mag_limit, double* out_flux, double* out_sigma, float* out_feat, void* stream) {
+  if (!flux || !sigma_sets || !set_index || n_gal < 1 || n_filt < 1 || n_scatter < 1 || n_sets < 1)
+    return fail(SB2_ERR_INVALID, "bad argument");
+  if (!out_flux && !out_feat) return fail(SB2_ERR_INVALID, "no output requested");
+  sb2::NoiseArgs a{};
+  a.flux = flux; a.n_gal = n_gal; a.n_filt = n_filt; a.n_scatter = n_scatter; a.sigma = sigma_sets; a.set_index = set_index;
+  a.min_pc = min_flux_pc_error; a.normals = normals; a.seed = seed; a.epoch = epoch; a.mag_limit = norm_mag_limit;
+  a.out_flux = out_flux; a.out_sigma = out_sigma; a.out_feat = out_feat;
+  const long long rows = (long long)n_gal * n_scatter;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = std::min<long long>((rows + 255) / 256, (long long)n_sm * 16);
+  sb2::depth_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  CU_TRY(cudaGetLastError());
+  return SB2_OK;
+}
+
 // ---- spectroscopic path -------------------------------------------------------------------------------------------
 struct sb2_resampler {
   int device = 0, n_sm = 148;

@@ -31,7 +31,8 @@ struct NoiseArgs {
   const double* flux;     // [n_gal][n_filt]
   long long n_gal;
   int n_filt, n_scatter;
-  const double* sigma;    // [n_filt]
+  const double* sigma;    // [n_filt], or [n_sets][n_filt] with set_index
+  const int* set_index;   // [n_filt][n_scatter] which depth set each (filter, block of n_gal rows) uses, or nullptr
   double min_pc;
   const double* normals;  // [n_filt][n_rows] or nullptr
   unsigned long long seed, epoch;
@@ -65,7 +66,9 @@ __global__ void __launch_bounds__(256) depth_noise_kernel(NoiseArgs A) {
         const int f = f0 + d;
         if (f >= A.n_filt) break;
         const double rep = A.flux[g * A.n_filt + f];
-        double sd = A.sigma[f];
+        // 2-D depths (sbi_runner.py:626-647): rows [j n_gal, (j+1) n_gal) of the repeated array share the depth set drawn
+        // for (filter, j) -- the reference expands its (m, N_scatters) pick with np.repeat(..., n, axis=1)
+        double sd = A.set_index ? A.sigma[(long long)A.set_index[f * A.n_scatter + (int)(r / A.n_gal)] * A.n_filt + f] : A.sigma[f];
         if (A.min_pc > 0.0) sd = fmax(sd, __ddiv_rn(__dmul_rn(rep, A.min_pc), 100.0));
         const double z = A.normals ? A.normals[(long long)f * n_rows + r] : (double)zf[d];
         const double noisy = __dadd_rn(rep, __dadd_rn(0.0, __dmul_rn(sd, z)));

@@ -531,10 +531,11 @@ class DeviceParams:
 
 
 def depth_noise_features(flux, sigma, n_scatter=1, normals=None, seed=0, epoch=0, norm_mag_limit=50.0,
-                         min_flux_pc_error=0.0, want_flux=True, want_features=True, device=0):
+                         min_flux_pc_error=0.0, want_flux=True, want_features=True, device=0, set_index=None):
     """Depth scatter + AB feature rows on the GPU (``sb2_depth_noise_features``).
 
-    flux ``(n_gal, n_filt)`` nJy (numpy or CUDA torch tensor), sigma ``(n_filt,)`` nJy.
+    flux ``(n_gal, n_filt)`` nJy (numpy or CUDA torch tensor), sigma ``(n_filt,)`` nJy -- or ``(n_sets, n_filt)`` together
+    with ``set_index (n_filt, n_scatter)`` int: which depth set each block of ``n_gal`` rows uses (``sbi_runner.py:626-647``).
     Returns ``(noisy_flux (n_filt, n_rows) f64 | None, sigma (n_filt, n_rows) f64 | None,
     features (n_rows, 2 n_filt) f32 | None)`` as torch CUDA tensors.
     """
@@ -554,6 +555,17 @@ def depth_noise_features(flux, sigma, n_scatter=1, normals=None, seed=0, epoch=0
     feat = torch.empty((n_rows, 2 * n_filt), dtype=torch.float32, device=dev) if want_features else None
     dp = lambda x: None if x is None else x.data_ptr()  # noqa: E731
     st = torch.cuda.current_stream(device).cuda_stream
+    if set_index is not None:
+        if sg.ndim != 2 or sg.shape[1] != n_filt:
+            raise ValueError("with set_index, sigma must be (n_sets, n_filt)")
+        si = torch.as_tensor(np.asarray(set_index, dtype=np.int32)).to(dev).contiguous()
+        if tuple(si.shape) != (n_filt, int(n_scatter)) or int(si.min()) < 0 or int(si.max()) >= sg.shape[0]:
+            raise ValueError("set_index must be (n_filt, n_scatter) with entries in [0, n_sets)")
+        rc = lib.sb2_depth_noise_features_sets(fl.data_ptr(), n_gal, n_filt, int(n_scatter), sg.data_ptr(), int(sg.shape[0]),
+                                               si.data_ptr(), float(min_flux_pc_error), dp(nz), int(seed), int(epoch),
+                                               float(norm_mag_limit), dp(of), dp(osig), dp(feat), st)
+        _capi.check(rc, "sb2_depth_noise_features_sets")
+        return of, osig, feat
     rc = lib.sb2_depth_noise_features(fl.data_ptr(), n_gal, n_filt, int(n_scatter), sg.data_ptr(),
                                       float(min_flux_pc_error), dp(nz), int(seed), int(epoch),
                                       float(norm_mag_limit), dp(of), dp(osig), dp(feat), st)

@@ -43,7 +43,8 @@ def create_feature_array_from_raw_photometry(
         min_flux_pc_error: float = 0.0, norm_mag_limit: float = 50.0, remove_nan_inf: bool = True,
         photometry_to_remove: Optional[list] = None, drop_dropouts: bool = False,
         drop_dropout_fraction: float = 1.0, parameter_array=None, normals=None, seed: int = 0,
-        epoch: int = 0, device: int = 0, return_torch: bool = False, empirical_noise_models=None):
+        epoch: int = 0, device: int = 0, return_torch: bool = False, empirical_noise_models=None,
+        depth_indices=None):
     """``(N_filters, N_gal)`` library photometry -> ``(feature_array (N_rows, N_feat) float32,
     feature_names, parameter_array (N_rows, N_par) | None)``.
 
@@ -52,6 +53,9 @@ def create_feature_array_from_raw_photometry(
     ``flux + np.random.normal(0, sigma)`` for the same draws; otherwise Philox4x32-10(seed, epoch).
     ``empirical_noise_models`` (``{filter name: model}``, instead of ``depths``) scatters with the per-filter empirical models
     on the device (``sbi_runner.py:1678-1692``): the models hand back magnitudes and their errors directly.
+    2-D ``depths`` ``(k, N_filters)`` are k alternative depth sets: every (filter, scatter) picks one at random
+    (``sbi_runner.py:626-647``; ``depth_indices (N_filters, scatter_fluxes)`` injects the pick, otherwise it is drawn from
+    ``numpy.random.default_rng((seed, epoch))``).
     """
     import torch
     if normed_flux_units != "AB":
@@ -72,6 +76,7 @@ def create_feature_array_from_raw_photometry(
     grid = grid * _TO_NJY[str(raw_observation_units)]
     n_filt, n_gal = grid.shape
     n_sc = int(scatter_fluxes) if scatter_fluxes else 1
+    set_index = None
     empirical = bool(scatter_fluxes) and depths is None and empirical_noise_models is not None
     if empirical:
         sigma = None
@@ -83,9 +88,18 @@ def create_feature_array_from_raw_photometry(
                 sigma = np.array([float(strip_units(v, "nJy")) for v in vals]) / depth_sigma
             else:
                 sigma = depths_to_sigma_njy(np.array(vals, dtype=float), depth_sigma)
+        elif np.ndim(strip_units(depths)) == 2:
+            d2 = np.asarray(strip_units(depths, "nJy") if has_units(depths)
+                            else 10 ** ((np.asarray(depths, dtype=np.float64) - 23.9) / -2.5) * 1e3, dtype=np.float64)
+            if d2.shape[1] != n_filt:
+                raise ValueError(f"Mismatch in dimensions: photometry_array has {n_filt} rows but depths has "
+                                 f"{d2.shape[1]} columns")
+            sigma = d2 / depth_sigma
+            set_index = (np.asarray(depth_indices) if depth_indices is not None
+                         else np.random.default_rng((int(seed), int(epoch))).integers(0, d2.shape[0], size=(n_filt, n_sc)))
         else:
             sigma = depths_to_sigma_njy(depths, depth_sigma, n_filt)
-        if sigma.shape[0] != n_filt:
+        if sigma.shape[-1] != n_filt:
             raise ValueError(f"Mismatch in dimensions: photometry_array has {n_filt} rows but depths has "
                              f"{sigma.shape[0]} elements")
     else:
@@ -103,7 +117,7 @@ def create_feature_array_from_raw_photometry(
         flux_gf = grid.t().contiguous()                                   # (n_gal, n_filt), kernel layout
         _, _, feat = depth_noise_features(flux_gf, sigma, n_scatter=n_sc, normals=normals, seed=seed, epoch=epoch,
                                           norm_mag_limit=norm_mag_limit, min_flux_pc_error=min_flux_pc_error,
-                                          want_flux=False, want_features=True, device=device)
+                                          want_flux=False, want_features=True, device=device, set_index=set_index)
         mags, errs = feat[:, :n_filt], feat[:, n_filt:]
     feature_names = list(names)
     if normalize_method is not None:

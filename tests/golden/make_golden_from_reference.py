@@ -126,6 +126,14 @@ def main():
     np.random.seed(99)
     out2, err2 = apply_depths(None, depths, phot, N_scatters=3, depth_sigma=5, return_errors=True, min_flux_pc_error=10.0)
     g["ad_out_pc"], g["ad_err_pc"] = np.asarray(out2), np.asarray(err2)
+    # 2-D depths: a random depth set per (filter, scatter) (sbi_runner.py:626-647); randint first, then the normals
+    depths2 = shim.Quantity(np.array([[5.0, 10.0, 20.0, 40.0], [8.0, 6.0, 30.0, 25.0], [3.0, 12.0, 15.0, 60.0]]), "nJy")
+    np.random.seed(123)
+    g["ad2_idx"] = np.random.randint(0, 3, size=(4, 3))
+    g["ad2_z"] = np.random.normal(size=(4, 18))
+    np.random.seed(123)
+    out3, err3 = apply_depths(None, depths2, phot, N_scatters=3, depth_sigma=5, return_errors=True)
+    g["ad2_depths"], g["ad2_out"], g["ad2_err"] = np.asarray(depths2), np.asarray(out3), np.asarray(err3)
 
     draw = lift(os.path.join(REF, "library.py"), "draw_from_hypercube")
     pr = {"redshift": (0.01, 10), "masses": (5, 11), "tau_v": (0, 2), "peak_age": (0, 0.99), "tau": (0.1, 1.5),

@@ -388,3 +388,32 @@ def test_supplementary_parameters_through_create_mock_library(tmp_path):
     with pytest.raises(NotImplementedError):
         basis.create_mock_library(log_stellar_masses=list(masses), emission_model_key="emergent", out_name="supp_bad",
                                   out_dir=str(tmp_path), overwrite=True, beta=lambda galaxy: 0.0)
+
+
+def test_depth_sets_2d_depths_bit_exact_and_in_the_feature_builder():
+    """2-D depths (sbi_runner.py:626-647): golden output of the reference's _apply_depths reproduced bit for bit with the
+    injected pick and normals; the feature builder accepts (k, N_filters) depths."""
+    from synference_b200.engine import depth_noise_features
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_noise_golden.npz"))
+    phot = G["ad_phot"]                                   # (4 filters, 6 galaxies), nJy
+    noisy, sig, _ = depth_noise_features(phot.T.copy(), G["ad2_depths"] / 5.0, n_scatter=3, normals=G["ad2_z"],
+                                         set_index=G["ad2_idx"], want_features=False)
+    assert np.array_equal(noisy.cpu().numpy(), G["ad2_out"]) and np.array_equal(sig.cpu().numpy(), G["ad2_err"])
+    rng = np.random.default_rng(2)
+    grid = np.abs(rng.normal(60, 10, (4, 3000))) + 5
+    depths = np.array([[29.0, 29.0, 29.0, 29.0], [27.0, 27.5, 28.0, 28.5]])            # AB, two sets
+    idx = np.array([[0, 1], [1, 1], [0, 0], [1, 0]])
+    z = rng.standard_normal((4, 6000))
+    feat, names, _ = create_feature_array_from_raw_photometry(grid, list("abcd"), scatter_fluxes=2, depths=depths,
+                                                              depth_indices=idx, normals=z, include_errors_in_feature_array=True)
+    sig_sets = depths_to_sigma_njy(depths)                # (2, 4)
+    want_noisy, want_std = O.apply_depths(grid, sig_sets, z, 2, depth_indices=idx)
+    mag, merr = O.ab_features(want_noisy, want_std)
+    want = np.concatenate([mag, merr], 0).T
+    keep = np.isfinite(want).all(1)
+    np.testing.assert_allclose(feat, want[keep], atol=1e-4)
+    f2, _, _ = create_feature_array_from_raw_photometry(grid, list("abcd"), scatter_fluxes=2, depths=depths, seed=4, epoch=1)
+    f3, _, _ = create_feature_array_from_raw_photometry(grid, list("abcd"), scatter_fluxes=2, depths=depths, seed=4, epoch=1)
+    assert np.array_equal(f2, f3) and f2.shape == (6000, 4)
+    with pytest.raises(ValueError):
+        create_feature_array_from_raw_photometry(grid, list("abcd"), scatter_fluxes=2, depths=depths[:, :3])

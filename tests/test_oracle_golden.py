@@ -46,6 +46,13 @@ def test_apply_depths_matches_reference_code_bit_exact():
     np.testing.assert_array_equal(err, G["ad_err_pc"])
 
 
+def test_apply_depths_with_depth_sets_matches_reference_code():
+    """2-D depths (sbi_runner.py:626-647): randint pick per (filter, scatter), expanded with np.repeat(..., n, axis=1)."""
+    noisy, std = O.apply_depths(G["ad_phot"], G["ad2_depths"] / 5.0, G["ad2_z"], 3, depth_indices=G["ad2_idx"])
+    np.testing.assert_array_equal(std, G["ad2_err"])
+    np.testing.assert_array_equal(noisy, G["ad2_out"])
+
+
 def test_asinh_and_constant_r_match_reference_code():
     np.testing.assert_allclose(O.f_jy_to_asinh(G["asinh_f"], float(G["asinh_b"])), G["asinh_mag"], rtol=1e-14)
     np.testing.assert_allclose(O.f_jy_err_to_asinh(G["asinh_f"], G["asinh_e"], float(G["asinh_b"])), G["asinh_err"], rtol=1e-14)
