@@ -44,7 +44,7 @@ def create_feature_array_from_raw_photometry(
         photometry_to_remove: Optional[list] = None, drop_dropouts: bool = False,
         drop_dropout_fraction: float = 1.0, parameter_array=None, normals=None, seed: int = 0,
         epoch: int = 0, device: int = 0, return_torch: bool = False, empirical_noise_models=None,
-        depth_indices=None):
+        depth_indices=None, asinh_softening_parameters=None):
     """``(N_filters, N_gal)`` library photometry -> ``(feature_array (N_rows, N_feat) float32,
     feature_names, parameter_array (N_rows, N_par) | None)``.
 
@@ -56,12 +56,21 @@ def create_feature_array_from_raw_photometry(
     2-D ``depths`` ``(k, N_filters)`` are k alternative depth sets: every (filter, scatter) picks one at random
     (``sbi_runner.py:626-647``; ``depth_indices (N_filters, scatter_fluxes)`` injects the pick, otherwise it is drawn from
     ``numpy.random.default_rng((seed, epoch))``).
+    ``normed_flux_units="asinh"`` (``sbi_runner.py:1598-1625, 1660-1676, 1718-1730``): asinh magnitudes with the softening
+    ``asinh_softening_parameters`` -- one flux per filter (a Quantity array, or a list / dict of quantities), or ``"SNR_x"``:
+    x times the 1-sigma depth of each filter.  No magnitude limit is applied in this branch, as in the reference.
     """
     import torch
-    if normed_flux_units != "AB":
-        raise NotImplementedError("the device feature builder implements normed_flux_units='AB' "
-                                  "(asinh / linear features: SURVEY 8f-3)")
+    if normed_flux_units not in ("AB", "asinh"):
+        raise NotImplementedError("the device feature builder implements normed_flux_units 'AB' and 'asinh'")
+    asinh = normed_flux_units == "asinh"
+    if asinh:
+        assert asinh_softening_parameters is not None, "asinh_softening_parameters must be provided for asinh normalization."
+        if empirical_noise_models is not None and depths is None:
+            raise NotImplementedError("asinh features with empirical noise models: use AsinhEmpiricalUncertaintyModel through "
+                                      "apply_empirical_noise_models (it returns asinh magnitudes itself)")
     names = list(raw_observation_names)
+    all_names = list(names)
     dev = torch.device("cuda", device)
     grid = phot_grid if isinstance(phot_grid, torch.Tensor) else torch.as_tensor(np.asarray(phot_grid, dtype=np.float64))
     grid = grid.to(dev, dtype=torch.float64)
@@ -113,6 +122,37 @@ def create_feature_array_from_raw_photometry(
         mags = torch.clamp(m.t(), max=norm_mag_limit).to(torch.float32)     # sbi_runner.py:1927-1932
         mags = torch.where(torch.isnan(m.t()), torch.full_like(mags, float("nan")), mags)
         errs = e.t().to(torch.float32)
+    elif asinh:
+        # softening per filter [Jy]
+        sp = asinh_softening_parameters
+        if isinstance(sp, str):
+            assert sp.startswith("SNR_"), "If a string, asinh_softening_parameters must start with 'SNR_'."
+            assert scatter_fluxes and sigma is not None and set_index is None, \
+                "If setting asinh_softening_parameters from noise models, depths must be provided."
+            b_jy = float(sp.split("_")[-1]) * np.asarray(sigma, dtype=np.float64) * 1e-9
+        elif isinstance(sp, dict):
+            b_jy = np.array([float(strip_units(sp[n], "Jy")) for n in names])
+        elif has_units(sp):
+            b_jy = np.atleast_1d(np.asarray(strip_units(sp, "Jy"), dtype=np.float64))
+            if b_jy.size == len(all_names) and len(names) != len(all_names):
+                b_jy = b_jy[[all_names.index(n) for n in names]]
+        else:
+            b_jy = np.array([float(strip_units(v, "Jy")) for v in sp])
+            assert len(b_jy) == len(all_names), "asinh_softening_parameter must be a list of the same length as raw_observation_names"
+            b_jy = b_jy[[all_names.index(n) for n in names]]
+        if b_jy.size == 1:
+            b_jy = np.full(n_filt, float(b_jy[0]))
+        if b_jy.size != n_filt or not np.all(b_jy > 0):
+            raise ValueError("asinh softening: one positive flux per filter")
+        flux_gf = grid.t().contiguous()
+        noisy, sig, _ = depth_noise_features(flux_gf, sigma, n_scatter=n_sc, normals=normals, seed=seed, epoch=epoch,
+                                             norm_mag_limit=norm_mag_limit, min_flux_pc_error=min_flux_pc_error,
+                                             want_flux=True, want_features=False, device=device, set_index=set_index)
+        b = torch.as_tensor(b_jy, dtype=torch.float64, device=dev)[:, None]
+        f_jy, e_jy = noisy * 1e-9, sig * 1e-9                              # (n_filt, n_rows)
+        pog = 2.5 * np.log10(np.e)
+        mags = (-pog * (torch.asinh(f_jy / (2 * b)) + torch.log(b / 3631.0))).t()       # utils.py:647-675
+        errs = (pog * e_jy / torch.sqrt(f_jy * f_jy + (2 * b) ** 2)).t()                # utils.py:678-704
     else:
         flux_gf = grid.t().contiguous()                                   # (n_gal, n_filt), kernel layout
         _, _, feat = depth_noise_features(flux_gf, sigma, n_scatter=n_sc, normals=normals, seed=seed, epoch=epoch,
@@ -127,7 +167,9 @@ def create_feature_array_from_raw_photometry(
         j = names.index(normalize_method)
         norm = mags[:, j:j + 1]
         others = [i for i in range(n_filt) if i != j]
-        mags = torch.clamp(mags[:, others] - norm, max=norm_mag_limit)
+        mags = mags[:, others] - norm
+        if not asinh:
+            mags = torch.clamp(mags, max=norm_mag_limit)
         errs = errs[:, others]
         feature_names = [names[i] for i in others]
         cols = [mags] + ([errs] if include_errors_in_feature_array and scatter_fluxes else []) + [norm]

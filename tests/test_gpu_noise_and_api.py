@@ -417,3 +417,31 @@ def test_depth_sets_2d_depths_bit_exact_and_in_the_feature_builder():
     assert np.array_equal(f2, f3) and f2.shape == (6000, 4)
     with pytest.raises(ValueError):
         create_feature_array_from_raw_photometry(grid, list("abcd"), scatter_fluxes=2, depths=depths[:, :3])
+
+
+def test_asinh_feature_rows():
+    """normed_flux_units="asinh" (sbi_runner.py:1718-1730): asinh magnitudes and their errors with a per-filter softening,
+    given explicitly or as "SNR_x" (x times the 1-sigma depth, :1660-1676); normalisation by a band subtracts."""
+    rng = np.random.default_rng(13)
+    names = ["a", "b", "c"]
+    grid = rng.normal(20.0, 30.0, (3, 4000))                       # nJy, with negative fluxes: the point of asinh magnitudes
+    z = rng.standard_normal((3, 8000))
+    depths = np.array([29.0, 28.5, 28.0])
+    sigma = depths_to_sigma_njy(depths)
+    feat, fnames, _ = create_feature_array_from_raw_photometry(
+        grid, names, normed_flux_units="asinh", asinh_softening_parameters="SNR_1", scatter_fluxes=2, depths=depths, normals=z,
+        include_errors_in_feature_array=True)
+    noisy, std = O.apply_depths(grid, sigma, z, 2)
+    b = (1.0 * sigma * 1e-9)[:, None]
+    want = np.concatenate([O.asinh_mag(noisy * 1e-9, b), O.asinh_mag_err(noisy * 1e-9, std * 1e-9, b)], 0).T
+    assert feat.shape == want.shape and fnames == names + [f"unc_{n}" for n in names]
+    np.testing.assert_allclose(feat, want, rtol=2e-6, atol=2e-6)
+    assert np.isfinite(feat).all()                                  # negative fluxes are fine in asinh magnitudes
+    soft = S.unyt_array([5.0, 8.0, 10.0], "nJy")
+    f2, n2, _ = create_feature_array_from_raw_photometry(grid, names, normed_flux_units="asinh", asinh_softening_parameters=soft,
+                                                         normalize_method="b")
+    m = O.asinh_mag(grid * 1e-9, (np.array([5.0, 8.0, 10.0]) * 1e-9)[:, None]).T
+    np.testing.assert_allclose(f2, np.stack([m[:, 0] - m[:, 1], m[:, 2] - m[:, 1], m[:, 1]], 1), rtol=2e-6, atol=2e-6)
+    assert n2 == ["a", "c", "norm_b"]
+    with pytest.raises(AssertionError):
+        create_feature_array_from_raw_photometry(grid, names, normed_flux_units="asinh")
