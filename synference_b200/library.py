@@ -583,8 +583,103 @@ class CombinedBasis:
         if not self.draw_parameter_combinations:
             return self.create_full_library(override_instrument, overwrite=overwrite, save=save,
                                             overload_out_name=overload_out_name)
-        raise NotImplementedError("meshgrid mode (draw_parameter_combinations=True, library.py:3644-3974) is not "
-                                  "part of the batched path; draw the combinations up front instead")
+        return self._create_combination_library(override_instrument, save=save, overload_out_name=overload_out_name,
+                                                overwrite=overwrite)
+
+    def _create_combination_library(self, override_instrument=None, save=True, overload_out_name="", overwrite=False):
+        """``draw_parameter_combinations=True`` (``library.py:3644-3974``): for every redshift x total mass x combination
+        weight, every combination of the bases' galaxies AT that redshift (``np.meshgrid(..., indexing="ij")`` order), base
+        photometry (cast to float32 first) scaled to ``weight * total mass`` and summed over the bases; supplementary
+        parameters that scale with mass are scaled and summed the same way.  Vectorised over the combinations."""
+        out_name = overload_out_name or self.out_name
+        path = os.path.join(self.out_dir, out_name)
+        if not path.endswith(".hdf5"):
+            path += ".hdf5"
+        if os.path.exists(path) and not overwrite:
+            logger.warning(f"File {path} already exists. Skipping.")
+            return self.load_library_from_file(path)
+        outputs = self.load_bases()
+        base_filters = outputs[self.bases[0].model_name]["filter_codes"]
+        for b in self.bases[1:]:
+            if outputs[b.model_name]["filter_codes"] != base_filters:
+                raise ValueError("All bases must share the same filters")
+        if override_instrument is not None:
+            for code in override_instrument.filters.filter_codes:
+                if code not in base_filters:
+                    raise ValueError(f"Filter {code} not found in base filters. Cannot override instrument.")
+            filter_codes = list(override_instrument.filters.filter_codes)
+        else:
+            filter_codes = list(base_filters)
+        multi = len(self.bases) > 1
+        names_per_base = {b.model_name: [(f"{b.model_name}/{n}" if multi else n, n) for n in b.varying_param_names
+                                         if n != "redshift"] for b in self.bases}
+        param_columns = ["redshift", "log_mass"] + (["weight_fraction"] if multi else [])
+        param_units = ["dimensionless", "log10(Mstar/Msun)"] + (["dimensionless"] if multi else [])
+        for b in self.bases:
+            for col, short in names_per_base[b.model_name]:
+                param_columns.append(col)
+                src = b.all_parameters.get(short)
+                param_units.append(UNIT_DICT.get(short.lower(), str(src.units) if has_units(src) else "dimensionless"))
+        supp_keys = list(outputs[self.bases[0].model_name]["supp_properties"].keys())
+        for b in self.bases:
+            if list(outputs[b.model_name]["supp_properties"].keys()) != supp_keys:
+                raise AssertionError("Not all bases have the same supplementary parameters.")
+        supp_units = [outputs[self.bases[0].model_name]["supp_properties"][k][1] for k in supp_keys]
+        weights = np.asarray(self.combination_weights, dtype=float).reshape(-1, len(self.bases))
+        redshifts = np.atleast_1d(np.asarray(strip_units(self.redshifts), dtype=float))     # looped as given, like the reference
+        all_out, all_par, all_supp = [], [], []
+        for z in redshifts:
+            per_base = []
+            for b in self.bases:
+                o = outputs[b.model_name]
+                mask = np.asarray(o["properties"]["redshift"], dtype=float) == z
+                phot = np.stack([np.asarray(o["observed_photometry"][c])[mask] for c in filter_codes], 0).astype(np.float32)
+                per_base.append((mask, phot, np.asarray(o["properties"]["mass"], dtype=float)[mask]))
+            counts = [pb[1].shape[1] for pb in per_base]
+            if min(counts) == 0:
+                continue
+            combos = np.array(np.meshgrid(*[np.arange(c) for c in counts], indexing="ij")).T.reshape(-1, len(counts))
+            for log_total_mass in np.atleast_1d(self.log_stellar_masses):
+                total_mass = 10.0 ** float(log_total_mass)
+                for comb in weights:
+                    dim = combos.shape[0]
+                    out = np.zeros((len(filter_codes), dim))
+                    rows = [np.full(dim, z), np.full(dim, float(log_total_mass))] + ([np.full(dim, comb[0])] if multi else [])
+                    supp = np.zeros((len(supp_keys), dim))
+                    for j, b in enumerate(self.bases):
+                        mask, phot, mass = per_base[j]
+                        scale = comb[j] * total_mass / mass                          # per galaxy of this base
+                        out += (phot * scale)[:, combos[:, j]]
+                        o = outputs[b.model_name]
+                        for col, short in names_per_base[b.model_name]:
+                            rows.append(np.asarray(o["properties"][short], dtype=float)[mask][combos[:, j]])
+                        for k, key in enumerate(supp_keys):
+                            vals, units = o["supp_properties"][key]
+                            vals = np.asarray(vals, dtype=float)[mask]
+                            # (the reference scales every unit-carrying column here, library.py:3866-3881)
+                            if units != "dimensionless":
+                                vals = vals * scale
+                            supp[k] += vals[combos[:, j]]
+                    all_out.append(out)
+                    all_par.append(np.stack(rows, 0))
+                    all_supp.append(supp)
+        if not all_out:
+            raise ValueError("no galaxies found at the requested redshifts")
+        combined_outputs, combined_params = np.hstack(all_out), np.hstack(all_par)
+        combined_supp = np.hstack(all_supp)
+        out = {"photometry": combined_outputs, "parameters": combined_params, "parameter_names": param_columns,
+               "filter_codes": filter_codes, "supplementary_parameters": combined_supp,
+               "supplementary_parameter_names": supp_keys, "supplementary_parameter_units": supp_units,
+               "parameter_units": param_units}
+        self.library_photometry, self.library_parameters = combined_outputs, combined_params
+        self.library_parameter_names, self.library_filter_codes = param_columns, filter_codes
+        self.library_parameter_units = param_units
+        self.library_supplementary_parameters = combined_supp
+        self.library_supplementary_parameter_names = supp_keys
+        self.library_supplementary_parameter_units = supp_units
+        if save:
+            self.save_library(out, overload_out_name=overload_out_name, overwrite=overwrite)
+        return out
 
     def create_spectral_grid(self, override_instrument=None, save=True, overload_out_name="", overwrite=False):
         return self.create_full_library(override_instrument, save=save, overload_out_name=overload_out_name,

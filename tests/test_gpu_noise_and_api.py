@@ -445,3 +445,45 @@ def test_asinh_feature_rows():
     assert n2 == ["a", "c", "norm_b"]
     with pytest.raises(AssertionError):
         create_feature_array_from_raw_photometry(grid, names, normed_flux_units="asinh")
+
+
+def test_combination_library_meshgrid_mode(tmp_path):
+    """draw_parameter_combinations=True (library.py:3644-3974; the reference's combined_library_basis_params fixture,
+    tests/test_library.py:46-74): two grid-built bases with different emission models, every combination of their galaxies
+    at each redshift x total mass x weight pair; against a brute-force restatement of the reference's loops."""
+    from tests.test_host_api import _basis
+    b1, b2 = _basis(build_library=True), _basis(build_library=True)
+    b2.emission_model = S.TotalEmission(grid=b2.grid, fesc=0.2, fesc_ly_alpha=0.2, dust_curve=S.Calzetti2000(),
+                                        dust_emission_model=None)
+    b1.model_name, b2.model_name = "comb_basis1", "comb_basis2"
+    weights = np.array([np.array([i, 1 - i]) for i in np.arange(0, 1.1, 0.25)])
+    cb = S.CombinedBasis(bases=[b1, b2], log_stellar_masses=[9.0, 10.5], redshifts=b1.redshifts,
+                         base_emission_model_keys=["emergent", "emergent"], combination_weights=weights,
+                         out_name="comb_lib", out_dir=str(tmp_path), log_base_masses=9, draw_parameter_combinations=True)
+    cb.process_bases(overwrite=True)
+    out = cb.create_library(overwrite=True)
+    n_z, n_per_z, n_m, n_w = 3, 3, 2, len(weights)
+    assert out["photometry"].shape == (8, n_z * n_m * n_w * n_per_z * n_per_z)
+    assert out["parameter_names"] == ["redshift", "log_mass", "weight_fraction", "comb_basis1/tau_v", "comb_basis2/tau_v"]
+    assert os.path.exists(os.path.join(str(tmp_path), "comb_lib.hdf5"))
+    with pytest.raises(AssertionError):
+        cb.create_full_library()
+    # brute force, in the reference's loop order
+    o = cb.load_bases()
+    codes = out["filter_codes"]
+    cols, pars = [], []
+    for z in b1.redshifts:
+        for lm in (9.0, 10.5):
+            for comb in weights:
+                sel = [np.asarray(o[b.model_name]["properties"]["redshift"]) == z for b in (b1, b2)]
+                ph = [np.array([o[b.model_name]["observed_photometry"][c][m] for c in codes], dtype=np.float32)
+                      * (comb[j] * 10 ** lm / o[b.model_name]["properties"]["mass"][m]) for j, (b, m) in enumerate(zip((b1, b2), sel))]
+                tv = [np.asarray(o[b.model_name]["properties"]["tau_v"])[m] for b, m in zip((b1, b2), sel)]
+                combos = np.array(np.meshgrid(np.arange(3), np.arange(3), indexing="ij")).T.reshape(-1, 2)
+                for i0, i1 in combos:
+                    cols.append(ph[0][:, i0] + ph[1][:, i1])
+                    pars.append([z, lm, comb[0], tv[0][i0], tv[1][i1]])
+    np.testing.assert_allclose(out["photometry"], np.array(cols).T, rtol=1e-12)
+    np.testing.assert_allclose(out["parameters"], np.array(pars).T, rtol=1e-12)
+    lib = S.load_library_from_hdf5(os.path.join(str(tmp_path), "comb_lib.hdf5"))
+    assert lib["photometry"].shape == out["photometry"].shape
