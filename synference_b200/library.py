@@ -974,7 +974,8 @@ class GalaxySimulator:
         bc = lambda v: np.broadcast_to(np.asarray(strip_units(v), dtype=float).reshape(-1), (n,))  # noqa: E731
         from .parametric import SFH_MAX_PARAMS, ZD_DELTA_LINEAR, ZD_DELTA_LOG10, ZD_NORMAL_LOG10
         cls = self.sfh_model
-        rows = np.zeros((n, SFH_MAX_PARAMS))
+        # (only the columns this SFH family uses: a 100 k x 24 float64 block was most of the host time per call)
+        rows = np.zeros((n, min(SFH_MAX_PARAMS, max(4, 2 + len(cls.param_names)))))
         to_yr = lambda v: bc(v) * (v.units.factor if has_units(v) else 1.0)  # noqa: E731
         rows[:, 1] = to_yr(params["max_age"])
         if "min_age" in params:
@@ -1060,44 +1061,51 @@ class GalaxySimulator:
             outputs["filters"] = self.instrument.filters
             return outputs
         fluxes = outputs[self.output_type[0]]
-        rows = []
-        for g in range(fluxes.shape[0]):
-            f, errors = self._scatter(fluxes[g], flux_units=self.out_flux_unit)
-            if self.normalize_method is not None:
-                f = self._normalize(f, method=self.normalize_method, norm_unit=self.out_flux_unit)
-            if self.include_phot_errors:
-                f = np.concatenate((f, errors))
-            rows.append(f)
-        out = np.stack(rows) if batched else rows[0]
+        # scatter / normalise / append errors for all rows at once: the functions below work along the last axis (the
+        # reference handles one galaxy per call; a per-row Python loop here cost 100x the GPU time for 100 k rows)
+        f, errors = self._scatter(fluxes, flux_units=self.out_flux_unit)
+        if self.normalize_method is not None:
+            f = self._normalize(f, method=self.normalize_method, norm_unit=self.out_flux_unit)
+        if self.include_phot_errors:
+            if errors is None:
+                raise ValueError("include_phot_errors needs depths or noise_models (and ignore_scatter=False)")
+            f = np.concatenate((f, np.broadcast_to(errors, fluxes.shape)), axis=-1)
+        out = f if batched else f[0]
         if self.return_type == "tensor":
             import torch
             out = torch.tensor(np.atleast_2d(out), device=self.device)
         return out
 
     def _normalize(self, fluxes, method=None, norm_unit="AB", add_norm_pos=-1):
+        """``library.py:5866-5904`` along the last axis (one galaxy ``(n_filt,)`` or a batch ``(n, n_filt)``)."""
         if method is None:
             return fluxes
+        fluxes = np.asarray(fluxes)
         func = np.subtract if norm_unit == "AB" else np.divide
         if isinstance(method, str):
             codes = self.instrument.filters.filter_codes
             if method not in codes:
                 raise ValueError(f"Filter {method} not found in filter codes. Cannot normalize photometry.")
-            norm = fluxes[codes.index(method)]
+            norm = fluxes[..., codes.index(method)]
         elif has_units(method):
             norm = -2.5 * np.log10(float(strip_units(method, "Jy"))) + 8.9 if norm_unit == "AB" else \
                 float(strip_units(method, norm_unit))
+            norm = np.full(fluxes.shape[:-1], norm)
         elif callable(method):
-            norm = method(fluxes)
+            norm = method(fluxes) if fluxes.ndim == 1 else np.array([method(row) for row in fluxes])
         else:
-            norm = method
-        fluxes = func(fluxes, norm)
+            norm = np.full(fluxes.shape[:-1], method, dtype=float)
+        norm = np.asarray(norm, dtype=float)
+        fluxes = func(fluxes, norm[..., None])
         if add_norm_pos is not None:
-            fluxes = np.append(fluxes, norm) if add_norm_pos == -1 else np.insert(fluxes, add_norm_pos, norm)
+            pos = fluxes.shape[-1] if add_norm_pos == -1 else add_norm_pos
+            fluxes = np.insert(fluxes, pos, norm, axis=-1)
         return fluxes
 
     def _scatter(self, fluxes: np.ndarray, flux_units: str = "nJy"):
-        """Depth or noise-model scatter of one galaxy's photometry (``library.py:5906-5997``), including
-        its quirks: depth errors are returned in uJy, and the AB-mode error carries a minus sign."""
+        """Depth or noise-model scatter (``library.py:5906-5997``) along the last axis -- one galaxy ``(n_filt,)`` or a
+        batch ``(n, n_filt)``; the depth branch consumes numpy's stream in the same order as a row-by-row loop would.
+        Including the reference's quirks: depth errors are returned in uJy, and the AB-mode error carries a minus sign."""
         if self.ignore_scatter:
             return fluxes, None
         to_ujy = {"nJy": 1e-3, "uJy": 1.0, "mJy": 1e3, "Jy": 1e6}
@@ -1126,9 +1134,9 @@ class GalaxySimulator:
             for i, code in enumerate(self.instrument.filters.filter_codes):
                 model = self.noise_models.get(code)
                 model.return_noise = True
-                sf, sig = model.apply_noise(flux=np.atleast_1d(fluxes[i]), true_flux_units=flux_units,
-                                            out_units=self.out_flux_unit)
-                scattered[i], errors[i] = np.asarray(sf).reshape(-1)[0], np.asarray(sig).reshape(-1)[0]
+                col = np.atleast_1d(fluxes[..., i])                    # one value, or this filter's column of a batch
+                sf, sig = model.apply_noise(flux=col, true_flux_units=flux_units, out_units=self.out_flux_unit)
+                scattered[..., i], errors[..., i] = np.asarray(sf).reshape(col.shape), np.asarray(sig).reshape(col.shape)
             return scattered, errors
         return fluxes, None
 

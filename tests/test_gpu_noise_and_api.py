@@ -487,3 +487,24 @@ def test_combination_library_meshgrid_mode(tmp_path):
     np.testing.assert_allclose(out["parameters"], np.array(pars).T, rtol=1e-12)
     lib = S.load_library_from_hdf5(os.path.join(str(tmp_path), "comb_lib.hdf5"))
     assert lib["photometry"].shape == out["photometry"].shape
+
+
+def test_simulator_batch_equals_row_by_row_calls(tmp_path):
+    """A batch through GalaxySimulator scatters, normalises and appends errors along the last axis; with depths it consumes
+    numpy's global stream in the order a per-galaxy loop (the reference's calling pattern, sbi_runner.py:7659-7664) does."""
+    basis, d, grid, inst, em = _small_basis(8, tmp_path)
+    sim = S.GalaxySimulator(sfh_model=S.SFH.LogNormal, zdist_model=S.ZDist.DeltaConstant, grid=grid, instrument=inst,
+                            emission_model=em, emission_model_key="emergent", out_flux_unit="AB", ignore_scatter=False,
+                            include_phot_errors=True, depths=np.full(7, 29.0), normalize_method="JWST/NIRCam.F444W",
+                            param_units={"peak_age": S.Myr, "max_age": S.Myr},
+                            param_order=["redshift", "log_mass", "tau", "peak_age", "max_age", "log10metallicity", "tau_v"])
+    rng = np.random.default_rng(4)
+    n = 6
+    p = np.column_stack([rng.uniform(0.5, 8, n), rng.uniform(9, 11, n), rng.uniform(0.2, 1.5, n), rng.uniform(10, 200, n),
+                         rng.uniform(250, 400, n), rng.uniform(-3, -1.4, n), rng.uniform(0, 2, n)])
+    np.random.seed(5)
+    batch = sim(p)
+    np.random.seed(5)
+    rows = np.stack([sim(p[i]) for i in range(n)])
+    assert batch.shape == (n, 7 + 1 + 7)
+    np.testing.assert_array_equal(batch, rows)
