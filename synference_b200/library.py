@@ -430,21 +430,30 @@ class GalaxyBasis:
                                em_lines_to_save=em_lines_to_save, **extra_analysis_functions)
         if compile_grid:
             logger.info("Compiling the library after processing bases.")
+            # the Model/ block (library.py:2017-2132) travels with the library's single write
+            combined._extra_attrs = self._model_info({"emission_model_key": emission_model_key,
+                                                      "timestamp": datetime.now().isoformat(), "cat_type": cat_type},
+                                                     parameter_transforms_to_save)
             if cat_type == "photometry":
                 combined.create_library(overwrite=overwrite)
             else:
                 combined.create_spectral_grid(overwrite=overwrite)
-            out_path = os.path.join(combined.out_dir, combined.out_name)
-            if not out_path.endswith(".hdf5"):
-                out_path += ".hdf5"
-            self._store_model(out_path, other_info={"emission_model_key": emission_model_key,
-                                                    "timestamp": datetime.now().isoformat(), "cat_type": cat_type},
-                              parameter_transforms_to_save=parameter_transforms_to_save)
             logger.info("Processed the bases and saved the output.")
             return combined
 
     def _store_model(self, model_path, other_info=None, parameter_transforms_to_save=None):
-        """Record what is needed to rebuild the simulator next to the library (``library.py:2017-2132``)."""
+        """Record what is needed to rebuild the simulator next to the library (``library.py:2017-2132``).  (Rewrites an
+        existing library file; ``create_mock_library`` hands the same block to ``save_library`` instead, so that the
+        library is written once.)"""
+        info = self._model_info(other_info, parameter_transforms_to_save)
+        if os.path.exists(model_path):
+            data, attrs = read_container(model_path)
+            attrs.update(info)
+            write_container(model_path, data, attrs, compress=_library_compression())
+        else:
+            write_container(model_path, {}, info, compress=False)
+
+    def _model_info(self, other_info=None, parameter_transforms_to_save=None):
         em = self.emission_model
         dust = em.dust_curve
         info = {
@@ -472,13 +481,19 @@ class GalaxyBasis:
         info.update({f"Model/{k}": v for k, v in (other_info or {}).items()})
         if parameter_transforms_to_save:
             info["Model/parameter_transforms"] = sorted(str(k) for k in parameter_transforms_to_save)
-        if os.path.exists(model_path):
-            data, attrs = read_container(model_path)
-            attrs.update(info)
-            write_container(model_path, data, attrs)
+        return info
 
     def plot_galaxy(self, *a, **k):
         raise NotImplementedError("plotting helpers are outside the hot path (SURVEY 2 row 13)")
+
+
+def _library_compression():
+    """Deflate level for library files: ``SYNFERENCE_B200_COMPRESS`` = 0 (default: none -- float photometry deflates by a
+    quarter at 25 MB/s on one core, which would be most of a library build; SURVEY: "optional compression off"), 1 ... 9."""
+    try:
+        return int(os.environ.get("SYNFERENCE_B200_COMPRESS", "0"))
+    except ValueError:
+        return 0
 
 
 class _LazyGalaxyList:
@@ -829,7 +844,8 @@ class CombinedBasis:
                  "CreationDT": datetime.now().strftime("%Y%m%d_%H%M%S"), "rank": rank, "world_size": size}
         for param in library_params_to_save:
             attrs[param] = [str(getattr(b, param)) for b in self.bases]
-        write_container(path, datasets, attrs)
+        attrs.update(getattr(self, "_extra_attrs", None) or {})
+        write_container(path, datasets, attrs, compress=_library_compression())
         self.library_path = path
 
     def load_library_from_file(self, file_path: str):

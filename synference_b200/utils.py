@@ -125,19 +125,29 @@ def _have_h5py():
 
 
 def write_container(path, datasets: dict, attrs: dict, compress=True):
-    """Write ``{dataset path: array}`` and ``{attr: value}``; returns the path actually written."""
+    """Write ``{dataset path: array}`` and ``{attr: value}``; returns the path actually written.
+    ``compress``: False / 0 none, True deflate at zlib's default level, 1 ... 9 that deflate level."""
+    level = 6 if compress is True else int(compress or 0)
     if _have_h5py() and not os.environ.get("SYNFERENCE_B200_FORCE_NPZ"):
         import h5py
         with h5py.File(path, "w") as f:
             for k, v in datasets.items():
-                f.create_dataset(k, data=v, compression="gzip" if compress and np.ndim(v) else None)
+                kw = dict(compression="gzip", compression_opts=level) if level and np.ndim(v) else {}
+                f.create_dataset(k, data=v, **kw)
             for k, v in attrs.items():
                 f.attrs[k] = v
         return path
     payload = {k.replace("/", "::"): np.asarray(v) for k, v in datasets.items()}
     payload["__attrs__"] = np.frombuffer(json.dumps(_jsonable(attrs)).encode(), dtype=np.uint8)
-    with open(path, "wb") as fh:  # keep the reference's file name, whatever its suffix
-        (np.savez_compressed if compress else np.savez)(fh, **payload)
+    if level in (0, 6):
+        with open(path, "wb") as fh:  # keep the reference's file name, whatever its suffix
+            (np.savez_compressed if level else np.savez)(fh, **payload)
+        return path
+    import zipfile
+    with zipfile.ZipFile(path, "w", compression=zipfile.ZIP_DEFLATED, compresslevel=level, allowZip64=True) as zf:
+        for k, v in payload.items():
+            with zf.open(k + ".npy", "w", force_zip64=True) as f:
+                np.lib.format.write_array(f, np.asanyarray(v), allow_pickle=False)
     return path
 
 
