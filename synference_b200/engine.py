@@ -553,21 +553,22 @@ def depth_noise_features(flux, sigma, n_scatter=1, normals=None, seed=0, epoch=0
     of = torch.empty((n_filt, n_rows), dtype=torch.float64, device=dev) if want_flux else None
     osig = torch.empty((n_filt, n_rows), dtype=torch.float64, device=dev) if want_flux else None
     feat = torch.empty((n_rows, 2 * n_filt), dtype=torch.float32, device=dev) if want_features else None
-    dp = lambda x: None if x is None else x.data_ptr()  # noqa: E731
-    st = torch.cuda.current_stream(device).cuda_stream
-    if set_index is not None:
-        if sg.ndim != 2 or sg.shape[1] != n_filt:
-            raise ValueError("with set_index, sigma must be (n_sets, n_filt)")
-        si = torch.as_tensor(np.asarray(set_index, dtype=np.int32)).to(dev).contiguous()
-        if tuple(si.shape) != (n_filt, int(n_scatter)) or int(si.min()) < 0 or int(si.max()) >= sg.shape[0]:
-            raise ValueError("set_index must be (n_filt, n_scatter) with entries in [0, n_sets)")
-        rc = lib.sb2_depth_noise_features_sets(fl.data_ptr(), n_gal, n_filt, int(n_scatter), sg.data_ptr(), int(sg.shape[0]),
-                                               si.data_ptr(), float(min_flux_pc_error), dp(nz), int(seed), int(epoch),
-                                               float(norm_mag_limit), dp(of), dp(osig), dp(feat), st)
-        _capi.check(rc, "sb2_depth_noise_features_sets")
+    with torch.cuda.device(dev):      # the entry points launch on the current device
+        dp = lambda x: None if x is None else x.data_ptr()  # noqa: E731
+        st = torch.cuda.current_stream(device).cuda_stream
+        if set_index is not None:
+            if sg.ndim != 2 or sg.shape[1] != n_filt:
+                raise ValueError("with set_index, sigma must be (n_sets, n_filt)")
+            si = torch.as_tensor(np.asarray(set_index, dtype=np.int32)).to(dev).contiguous()
+            if tuple(si.shape) != (n_filt, int(n_scatter)) or int(si.min()) < 0 or int(si.max()) >= sg.shape[0]:
+                raise ValueError("set_index must be (n_filt, n_scatter) with entries in [0, n_sets)")
+            rc = lib.sb2_depth_noise_features_sets(fl.data_ptr(), n_gal, n_filt, int(n_scatter), sg.data_ptr(), int(sg.shape[0]),
+                                                   si.data_ptr(), float(min_flux_pc_error), dp(nz), int(seed), int(epoch),
+                                                   float(norm_mag_limit), dp(of), dp(osig), dp(feat), st)
+            _capi.check(rc, "sb2_depth_noise_features_sets")
+            return of, osig, feat
+        rc = lib.sb2_depth_noise_features(fl.data_ptr(), n_gal, n_filt, int(n_scatter), sg.data_ptr(),
+                                          float(min_flux_pc_error), dp(nz), int(seed), int(epoch),
+                                          float(norm_mag_limit), dp(of), dp(osig), dp(feat), st)
+        _capi.check(rc, "sb2_depth_noise_features")
         return of, osig, feat
-    rc = lib.sb2_depth_noise_features(fl.data_ptr(), n_gal, n_filt, int(n_scatter), sg.data_ptr(),
-                                      float(min_flux_pc_error), dp(nz), int(seed), int(epoch),
-                                      float(norm_mag_limit), dp(of), dp(osig), dp(feat), st)
-    _capi.check(rc, "sb2_depth_noise_features")
-    return of, osig, feat

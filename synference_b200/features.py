@@ -251,10 +251,11 @@ def apply_empirical_noise_models(photometry_array, phot_names, empirical_noise_m
             raise ValueError(f"draws must have shape (4, {len(phot_names)}, {n})")
         d_ptr = C.c_void_p(dr.data_ptr())
     out_f, out_s = torch.empty_like(rep), torch.empty_like(rep)
-    st = torch.cuda.current_stream(dev).cuda_stream
-    _capi.check(lib.sb2_empirical_noise(C.c_void_p(rep.data_ptr()), n, len(phot_names), models, d_ptr, int(seed), int(epoch),
-                                        C.c_void_p(out_f.data_ptr()), C.c_void_p(out_s.data_ptr()), C.c_void_p(st)),
-                "sb2_empirical_noise")
+    with torch.cuda.device(dev):      # the entry point launches on the current device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _capi.check(lib.sb2_empirical_noise(C.c_void_p(rep.data_ptr()), n, len(phot_names), models, d_ptr, int(seed), int(epoch),
+                                            C.c_void_p(out_f.data_ptr()), C.c_void_p(out_s.data_ptr()), C.c_void_p(st)),
+                    "sb2_empirical_noise")
     if was_numpy:
         out_f, out_s = out_f.cpu().numpy(), out_s.cpu().numpy()
     return (out_f, out_s) if return_errors else out_f
