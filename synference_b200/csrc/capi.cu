@@ -1051,6 +1051,7 @@ int sb2_resampler_create(const sb2_resample_desc* d, int device, sb2_resampler**
     }
     nb_max = std::min(nb_max + 1, d->n_lam);
   }
+  a.nb_max = nb_max;
   r->smem = ((size_t)2 * nb_max + 2 * (size_t)a.h_cap) * sizeof(float);
   if (rc == SB2_OK && r->smem > (size_t)max_smem - 1024) rc = fail(SB2_ERR_INVALID, "resampler: model axis too long for one CTA's shared memory");
   if (rc == SB2_OK && cudaFuncSetAttribute(sb2::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r->smem) != cudaSuccess)

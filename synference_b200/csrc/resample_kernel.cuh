@@ -34,6 +34,7 @@ struct ResampleArgs {
   float trunc;
   float fill;
   int h_cap;                 // widest kernel half-width the shared-memory staging buffer was sized for
+  int nb_max;                // most bins the launch reserved shared memory for (any redshift's window fits: see capi)
   // Search accelerators (nullptr: plain binary search).  A table over uniform steps of log2(wavelength) holds, per bucket, the
   // last edge / curve node at or below the bucket's left end: a lower bound from which the exact answer is a few steps away.
   const int* edge_lut;       // [lut_n]
@@ -122,8 +123,11 @@ __global__ void __launch_bounds__(kResampleThreads) resample_kernel(const __grid
       k_hi = min(last_edge_lt(A, s, inv_sf, __ldg(A.new_edges + A.n_px)), A.n_lam - 1);
       // (window entirely off either end of the axis: every pixel gets `fill` in step 5; the range below is then harmless)
     }
-    if (bad || k_hi < k_lo) {   // nothing of the spectrum under the observed window (or an unusable redshift)
-      for (int j = tid; j < A.n_px; j += kResampleThreads) out[j] = bad ? __int_as_float(0x7fc00000) : A.fill;
+    // (a window wider than the launch sized shared memory for cannot happen by construction; if it ever did, the row is
+    //  marked NaN rather than written past the buffers)
+    const bool too_wide = !bad && (k_hi - k_lo + 1) > A.nb_max;
+    if (bad || too_wide || k_hi < k_lo) {   // nothing of the spectrum under the observed window (or an unusable redshift)
+      for (int j = tid; j < A.n_px; j += kResampleThreads) out[j] = (bad || too_wide) ? __int_as_float(0x7fc00000) : A.fill;
       continue;
     }
     const int n_bins = k_hi - k_lo + 1;
