@@ -555,7 +555,9 @@ class Filter:
         assert self.lam.shape == self.t.shape
 
     def pivwv(self):
-        return np.sqrt(np.trapezoid(self.t * self.lam, self.lam) / np.trapezoid(self.t / self.lam, self.lam))
+        if getattr(self, "_pivwv", None) is None:       # curves are immutable once built; callers ask per simulate() call
+            self._pivwv = np.sqrt(np.trapezoid(self.t * self.lam, self.lam) / np.trapezoid(self.t / self.lam, self.lam))
+        return self._pivwv
 
 
 class FilterCollection:
