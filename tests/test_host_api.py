@@ -299,3 +299,23 @@ def test_bench_reference_arm_contract():
     r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                          "--warmup", "0", "--ref-sample", "200"], capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_new_device_paths_fail_loudly_without_a_gpu():
+    """No CPU fallback anywhere: on a box without a CUDA device the spectral and empirical-noise entry points raise."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a GPU-less box")
+    lam = 0.05 * (1 + 0.5 / 300) ** np.arange(500)
+    with pytest.raises(RuntimeError):
+        S.SpectrumResampler(lam, np.linspace(0.6, 1.0, 50), np.array([0.5, 1.1]), np.array([30.0, 100.0]))
+    with pytest.raises(RuntimeError):
+        S.transform_spectrum(lam, np.ones(500), 1.0, np.linspace(0.6, 1.0, 50), np.array([0.5, 1.1]), np.array([30.0, 100.0]))
+    c = np.linspace(20.0, 30.0, 8)
+    mod = S.GeneralEmpiricalUncertaintyModel(c, None, flux_unit="AB", already_binned=True, bin_median_errors=np.full(8, 0.1),
+                                             bin_std_errors=np.full(8, 0.01))
+    with pytest.raises(RuntimeError):
+        S.apply_empirical_noise_models(np.full((1, 4), 25.0), ["a"], {"a": mod}, N_scatters=1)
+    # the model still lowers to the C struct on the host
+    m = mod.device_model("nJy", "AB")
+    assert m.n_bins == 8 and m.internal_is_ab == 1 and m.in_is_ab == 0 and m.in_to_jy == 1e-9 and m.out_is_ab == 1
