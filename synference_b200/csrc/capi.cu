@@ -18,6 +18,7 @@
 #include "prep_kernel.cuh"
 #include "resample_kernel.cuh"
 #include "synth_kernel.cuh"
+#include "synth3_kernel.cuh"
 
 namespace {
 
@@ -157,9 +158,29 @@ __global__ void group_scatter_kernel(const unsigned* __restrict__ keys_sorted, c
 
 }  // namespace
 
+// Experiment / fallback switches (environment), read ONCE when a model is created -- never on the per-call path.
+struct Switches {
+  bool n256 = false, cta_pair = false, libm = false, weights_v1 = false, one_pass = false, trace = false, no_synth3 = false;
+  int dbg = 0, s3_n = 96;
+  long long host_slices = 0;   // 0: automatic
+  static bool on(const char* k) { const char* e = std::getenv(k); return e && e[0] && e[0] != '0'; }
+  void read() {
+    n256 = on("SB2_N256"); cta_pair = on("SB2_CTA_PAIR"); libm = on("SB2_LIBM"); weights_v1 = on("SB2_WEIGHTS_V1");
+    one_pass = on("SB2_ONE_PASS"); trace = on("SB2_TRACE"); no_synth3 = on("SB2_NO_SYNTH3");
+    if (const char* e = std::getenv("SB2_DBG")) dbg = std::atoi(e);
+    if (const char* e = std::getenv("SB2_S3_N")) s3_n = std::atoi(e) == 128 ? 128 : 96;
+    if (const char* e = std::getenv("SB2_HOST_SLICES")) host_slices = std::atoll(e);
+  }
+};
+
 struct sb2_model {
   int device = 0;
   int n_sm = 0;
+  Switches sw;
+  // synth3 (weights as the TMEM operand): raw SFH bin masses, tile-blocked, and the two metallicity factors
+  double *sf = nullptr, *s0 = nullptr, *s1 = nullptr;
+  CUtensorMap tm_g96_hi, tm_g96_lo, tm_g128_hi, tm_g128_lo;
+  bool s3_ok = false;
   sb2_model_desc d{};  // dims and scalars (pointers inside are NOT valid after create)
   long long cap = 0, cap_pad = 0;
   // model tables
@@ -245,7 +266,7 @@ int sb2_model_destroy(sb2_model* m) {
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage, m->fm_log, m->fm_exp, m->fm_tail,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
                   m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params[0],
-                  m->stage_params[1], m->stage_flux[0], m->stage_flux[1], m->stage_flux64[0], m->stage_flux64[1]};
+                  m->stage_params[1], m->stage_flux[0], m->stage_flux[1], m->stage_flux64[0], m->stage_flux64[1], m->sf, m->s0, m->s1};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : m->ev)
@@ -287,6 +308,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   m->device = device;
   m->n_sm = prop.multiProcessorCount;
   m->d = *d;
+  m->sw.read();
   int rc = SB2_OK;
 #define UP(dst, src, n) if ((rc = upload(&m->dst, src, (size_t)(n))) != SB2_OK) { sb2_model_destroy(m); return rc; }
   // ages and bin edges (A2): e_0 = 0, e_{i+1} = (t_i + t_{i+1})/2
@@ -402,6 +424,9 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(g_beta, np * 4); AL(g_gamma, np * 4); AL(g_taut, np * 4); AL(g_scale, np * 4); AL(g_ca, np * 4); AL(g_cb, np * 4);
   AL(keys, np * 4); AL(keys_sorted, np * 4); AL(perm_pad, np * 4); AL(tile_k0, (np / 128) * 4); AL(grp, (3 * kMaxGroups + 1) * 4);
   AL(g_mscale, np * 8); AL(g_trunc, np * 4); AL(zpow, np * 13 * 8);
+  // synth3: bracket-grouped batches whose two metallicities' columns fit the TMEM weights region
+  m->s3_ok = m->wd_stride > 0 && m->wd_stride <= sb2::kS3WCols && d->n_age <= 64 && d->n_age_pad % 8 == 0 && !m->sw.no_synth3;
+  if (m->s3_ok) { AL(sf, (np / 128) * (size_t)d->n_age * 128 * 8); AL(s0, np * 8); AL(s1, np * 8); }
   m->cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)m->cap);
   AL(cub_tmp, m->cub_bytes + 16);
@@ -419,6 +444,10 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
       (rc = make_tmap(&m->tm_g2_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN2 / 2)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g160_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 160)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g160_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 160)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g96_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 96)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g96_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 96)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g128_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 128)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g128_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 128)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK) {
     sb2_model_destroy(m);
@@ -466,7 +495,18 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
 namespace {
 
 // One spectral component: chunks of 160 columns and three TMEM accumulators (unless SB2_N256 asks for the two-accumulator form)
-bool use_n160(const sb2_model* m) { return m->d.n_comp == 1 && !std::getenv("SB2_N256"); }
+bool use_n160(const sb2_model* m) { return m->d.n_comp == 1 && !m->sw.n256; }
+
+bool delta_mode(const sb2_model* m, const sb2_params* p) {
+  return m->wd_stride > 0 && (p->zd_type == SB2_ZD_DELTA_LINEAR || p->zd_type == SB2_ZD_DELTA_LOG10);
+}
+
+// Bracket-grouped batches without per-galaxy emission extras take synth3_kernel (weights as the TMEM operand).
+bool use_s3(const sb2_model* m, const sb2_params* p) {
+  return m->s3_ok && delta_mode(m, p) && !m->dust_d0 && !m->lya_line && !m->kappa_birth && !m->dust_wnu && !m->sw.cta_pair;
+}
+int s3_cols(const sb2_model* m) { return m->d.n_comp == 1 ? m->sw.s3_n : 128; }   // accumulator columns per chunk
+
 
 template <int C, int NF, bool SPEC, bool PG>
 int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
@@ -528,6 +568,49 @@ int launch_synth2(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t 
 #undef SB2_PICK
 }
 
+template <int C, int NF, bool SPEC, int N>
+int launch_synth3_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
+  auto k = sb2::synth3_kernel<C, NF, SPEC, N>;
+  sb2::SynthArgs a2 = a;
+  sb2::Synth3Args x{};
+  x.sf = m->sf; x.s0 = m->s0; x.s1 = m->s1; x.n_age = m->d.n_age; x.na_pad = m->d.n_age_pad; x.w_stride = m->wd_stride;
+  x.kb_split = a.n_kb / 2;
+  bool spec = false;
+  const int kap_len = m->d.n_chunk * (sb2::kBN / C);
+  if (SPEC && sb2::synth3_smem_bytes(N, 3, x.n_age, m->uv_len, kap_len, true) <= m->smem_optin) { spec = true; a2.spec_smem = 1; }
+  int ns = sb2::kS3MaxStages;
+  while (ns > 1 && sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec) > m->smem_optin) --ns;
+  const size_t bytes = sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec);
+  if (ns < 2 || bytes > m->smem_optin) return fail(SB2_ERR_INVALID, "synth3_kernel: filter tables leave no room for the operand ring");
+  x.n_stages = ns;
+  CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  const CUtensorMap& th = C == 2 ? m->tm_g2_hi : (N == 96 ? m->tm_g96_hi : m->tm_g128_hi);
+  const CUtensorMap& tl = C == 2 ? m->tm_g2_lo : (N == 96 ? m->tm_g96_lo : m->tm_g128_lo);
+  k<<<grid, sb2::kS3Threads, bytes, st>>>(th, tl, a2, x);
+  STAGE_CHECK("synth3_kernel", st);
+  return SB2_OK;
+}
+
+int launch_synth3(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
+  const int nf = m->d.n_filt, c = m->d.n_comp;
+  const bool spec = a.out_spec != nullptr;
+#define SB2_PICK3(C, NF, N) (spec ? launch_synth3_t<C, NF, true, N>(m, a, grid, st) : launch_synth3_t<C, NF, false, N>(m, a, grid, st))
+  if (c == 1) {
+    if (s3_cols(m) == 128) {
+      if (nf <= 8) return SB2_PICK3(1, 8, 128);
+      if (nf <= 24) return SB2_PICK3(1, 24, 128);
+      return SB2_PICK3(1, 32, 128);
+    }
+    if (nf <= 8) return SB2_PICK3(1, 8, 96);
+    if (nf <= 24) return SB2_PICK3(1, 24, 96);
+    return SB2_PICK3(1, 32, 96);
+  }
+  if (nf <= 8) return SB2_PICK3(2, 8, 128);
+  if (nf <= 24) return SB2_PICK3(2, 24, 128);
+  return SB2_PICK3(2, 32, 128);
+#undef SB2_PICK3
+}
+
 int launch_synth(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
   const int nf = m->d.n_filt, c = m->d.n_comp;
   const bool spec = a.out_spec != nullptr;
@@ -544,10 +627,6 @@ int launch_synth(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cu
   if (nf <= 24) return SB2_PICK(2, 24);
   return SB2_PICK(2, 32);
 #undef SB2_PICK
-}
-
-bool delta_mode(const sb2_model* m, const sb2_params* p) {
-  return m->wd_stride > 0 && (p->zd_type == SB2_ZD_DELTA_LINEAR || p->zd_type == SB2_ZD_DELTA_LOG10);
 }
 
 sb2::PrepModel prep_model(const sb2_model* m) {
@@ -599,7 +678,7 @@ int check_params(const sb2_model* m, const sb2_params* p) {
 int rows_per_unit(const sb2_model* m, bool delta) {
   // The CTA-pair kernel (synth2_kernel) is parity-tested but not yet faster than the single-CTA kernel on B200
   // (both sit on the same synchronisation/epilogue floor); it is opt-in: SB2_CTA_PAIR=1.
-  return (delta && m->smem2_bytes > 0 && !m->dust_d0 && !m->lya_line && !m->kappa_birth && !m->dust_wnu && std::getenv("SB2_CTA_PAIR")) ? 256 : 128;
+  return (delta && m->smem2_bytes > 0 && !m->dust_d0 && !m->lya_line && !m->kappa_birth && !m->dust_wnu && m->sw.cta_pair) ? 256 : 128;
 }
 // Rows the grouped layout of a batch of n galaxies can occupy (every group is padded to whole units).
 long long padded_rows(const sb2_model* m, long long n, bool delta) {
@@ -652,21 +731,29 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
     int lo_min = m->h_lo[0], hi_max = m->h_hi[0];
     for (int f = 1; f < d.n_filt; ++f) { lo_min = std::min(lo_min, m->h_lo[f]); hi_max = std::max(hi_max, m->h_hi[f]); }
     const int wpb = 8, n_units = (int)(n_pad / rpu);
+    const int cols = rpu == 256 ? sb2::kBN2 : ((delta && use_s3(m, p)) ? s3_cols(m) : (use_n160(m) ? 160 : sb2::kBN));
     sb2::tile_range_kernel<<<(n_units + wpb - 1) / wpb, wpb * 32, 0, st>>>(m->g_m, m->g_orig, n_units, rpu, lo_min, hi_max, d.n_lam,
-                                                                         (rpu == 256 ? sb2::kBN2 : (use_n160(m) ? 160 : sb2::kBN)) / d.n_comp, all_lam ? 1 : 0, m->tile_range);
+                                                                         cols / d.n_comp, all_lam ? 1 : 0, m->tile_range);
     STAGE_CHECK("tile_range_kernel", st);
   }
   const size_t sh = sb2::weights_smem_doubles(M.n_age, M.n_z) * sizeof(double);
   const unsigned blocks = (unsigned)((n_pad + sb2::kWGal - 1) / sb2::kWGal);
   sb2::FastMath F{};
-  const bool fast = m->fm_tail && !std::getenv("SB2_LIBM");
+  const bool fast = m->fm_tail && !m->sw.libm;
   if (fast) {
     F.log_tab = reinterpret_cast<const double2*>(m->fm_log); F.exp_tab = m->fm_exp;
     F.tail_tab = reinterpret_cast<const double2*>(m->fm_tail);
     F.tail_w = m->d.fm_tail_w; F.tail_inv_w = 1.0 / m->d.fm_tail_w; F.tail_n = m->d.fm_tail_n;
   }
   const bool dpl = p->sfh_type == SB2_SFH_DOUBLE_POWERLAW;
-  if (M.n_age <= 64 && M.n_z <= 64 && !std::getenv("SB2_WEIGHTS_V1")) {   // half-warp per galaxy
+  if (use_s3(m, p) && (delta || w_f64)) {   // one galaxy per thread: raw bin masses, tile-blocked (expanded on chip by synth3_kernel)
+    sb2::SfOut S{m->sf, m->s0, m->s1};
+    const unsigned blocks3 = (unsigned)((n_pad + sb2::kW3Threads - 1) / sb2::kW3Threads);
+    if (dpl) sb2::weights3_kernel<false, 2><<<blocks3, sb2::kW3Threads, 0, st>>>(M, F, P, S, w_f64, perm, n_pad);
+    else if (p->sfh_type == SB2_SFH_CONTINUITY) sb2::weights3_kernel<false, 1><<<blocks3, sb2::kW3Threads, 0, st>>>(M, F, P, S, w_f64, perm, n_pad);
+    else if (fast) sb2::weights3_kernel<true, 0><<<blocks3, sb2::kW3Threads, 0, st>>>(M, F, P, S, w_f64, perm, n_pad);
+    else sb2::weights3_kernel<false, 0><<<blocks3, sb2::kW3Threads, 0, st>>>(M, F, P, S, w_f64, perm, n_pad);
+  } else if (M.n_age <= 64 && M.n_z <= 64 && !m->sw.weights_v1) {   // half-warp per galaxy
     const unsigned blocks2 = (unsigned)((n_pad + sb2::kW2Gal - 1) / sb2::kW2Gal);
     const bool lya = p->fesc_lya != nullptr && !w_f64;
     if (dpl && lya) sb2::weights2_kernel<false, true, true><<<blocks2, sb2::kW2Gal * 16, 0, st>>>(M, F, P, O, perm, n_pad);
@@ -722,9 +809,8 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.n_tiles_dev = m->grp + 3 * kMaxGroups;
   a.tile_k0 = m->tile_k0;
   a.k8_total = (delta ? m->wd_stride : d.k_pad) / 8;
-  a.dbg = std::getenv("SB2_DBG") ? std::atoi(std::getenv("SB2_DBG")) : 0;
-  if (a.dbg & 256) a.n_kb = 1;   // experiment: one k-block per chunk
-  a.two_pass = (!delta && !std::getenv("SB2_ONE_PASS")) ? 1 : 0;
+  a.dbg = m->sw.dbg;
+  a.two_pass = (!delta && !m->sw.one_pass) ? 1 : 0;
   a.n_chunk = d.n_chunk; a.n_kb = (a.k8_total + 3) / 4; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
   a.n_blue = d.n_blue; a.n_blue_pad = m->n_blue_pad; a.uv_len = m->uv_len;
   a.tile_range = m->tile_range;
@@ -744,6 +830,8 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   if (rpu == 256) {
     const int grid = 2 * std::min(a.n_tiles, m->n_sm / 2);
     rc = launch_synth2(m, a, grid, st);
+  } else if (use_s3(m, p)) {
+    rc = launch_synth3(m, a, a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm, st);
   } else {
     const int grid = a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm;
     rc = launch_synth(m, a, grid, delta, st);
@@ -822,14 +910,13 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
   }
   int n_slice = 1;
   {
-    const char* e = std::getenv("SB2_HOST_SLICES");
     // measured on B200: each extra slice costs ~0.3 ms of per-launch overhead, 2 slices per 1M galaxies is best for a
     // lone batch; when the other slot is in flight the neighbouring batch already provides the overlap
-    const long long want = e ? std::atoll(e) : (m->slot_busy[slot ^ 1] ? 1 : (long long)(n / 400000));
+    const long long want = m->sw.host_slices > 0 ? m->sw.host_slices : (m->slot_busy[slot ^ 1] ? 1 : (long long)(n / 400000));
     n_slice = (int)std::min<long long>(8, std::max<long long>(1, want));
   }
   const size_t per = ((n + n_slice - 1) / n_slice + 255) / 256 * 256;
-  const bool trace = std::getenv("SB2_TRACE") != nullptr;   // per-slice timeline on stderr (diagnostics)
+  const bool trace = m->sw.trace;   // per-slice timeline on stderr (diagnostics)
   cudaEvent_t tr[1 + 8 * 4] = {};
   if (trace) {
     for (auto& e : tr) cudaEventCreate(&e);
@@ -902,7 +989,7 @@ int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, 
   const long long cap = (long long)n_sm * 16;
   if (blocks > cap) blocks = cap;
   if (!normals && !out_flux && !out_sigma && out_feat && (reinterpret_cast<uintptr_t>(flux) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(out_feat) & 7) == 0 && !std::getenv("SB2_NOISE_V1")) {
+      (reinterpret_cast<uintptr_t>(out_feat) & 7) == 0) {
     const long long pairs = rows * ((n_filt + 1) / 2);
     long long b2 = (pairs + 255) / 256;
     if (b2 > (long long)n_sm * 32) b2 = (long long)n_sm * 32;
@@ -1017,7 +1104,7 @@ int sb2_resampler_create(const sb2_resample_desc* d, int device, sb2_resampler**
   };
   std::vector<int> elut, rlut;
   sb2::ResampleArgs& a = r->a;
-  if (oe[0] > 0 && !std::getenv("SB2_RESAMPLE_BSEARCH")) {
+  if (oe[0] > 0) {
     make_lut(oe.data(), d->n_lam + 1, 4 * d->n_lam, elut, a.lut_u0, a.lut_inv_du);
     RUP(edge_lut, elut.data(), elut.size());
     a.lut_n = (int)elut.size();

@@ -657,6 +657,185 @@ weights2_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __r
   }
 }
 
+// ---- SFH bin masses, ONE GALAXY PER THREAD (bracket-grouped batches; feeds synth3_kernel) ---------------------------
+// The half-warp builder above spends most of its ~675 warp instructions per galaxy on per-galaxy set-up replicated in 16
+// lanes, shuffles and the strided hi/lo row write.  Here a thread walks its galaxy's age-bin edges in order (each edge
+// evaluated once, differenced with the previous one in registers) and writes the RAW float64 bin masses tile-blocked,
+// sf[(tile*n_age + a)*128 + t], so a warp's stores are contiguous; the two metallicity factors of a DeltaConstant galaxy
+// travel as s0 = (1-f)/sum(sf), s1 = f/sum(sf).  The contraction kernel expands w[k] = sf[a]*s into the TF32 hi/lo pair
+// on chip (408 B per galaxy through HBM instead of 896 B, and the same arithmetic as weights2_kernel: sf[a] * s).
+struct SfOut {
+  double* sf;   // [n_tiles][n_age][128] raw bin masses (rows of padding galaxies are 0)
+  double* s0;   // [n_pad]
+  double* s1;   // [n_pad]
+};
+
+// families whose edge value needs at most two parameters (everything except DoublePowerLaw and Continuity)
+template <bool kFast>
+__device__ __forceinline__ EdgeVal sfh_edge_s(const FastMath& F, int type, double p0, double p1, double gc0, double mn, double mx,
+                                              double e_raw) {
+  const double r = 0.70710678118654752440;
+  const double t = fmin(fmax(e_raw, mn), mx);
+  EdgeVal v{0.0, 0.0};
+  switch (type) {
+    case SB2_SFH_CONSTANT:
+      v.a = t;
+      break;
+    case SB2_SFH_GAUSSIAN: {
+      const double u = (t - p0) / p1;
+      v.a = kFast ? fm_tail(F, fabs(u)) : 0.5 * erfc(fabs(u) * r);
+      v.b = u;
+      break;
+    }
+    case SB2_SFH_EXPONENTIAL:
+    case SB2_SFH_DECLINING_EXP: {
+      const double tau = (type == SB2_SFH_EXPONENTIAL) ? p0 : -p0;
+      const double shift = tau > 0.0 ? (mx - mn) / tau : 0.0;
+      const double arg = (mx - t) / tau - shift;
+      v.a = -tau * ((kFast && arg <= 0.0) ? fm_exp(F, arg) : exp(arg));
+      break;
+    }
+    case SB2_SFH_DELAYED_EXP: {
+      const double tau = p0, T = mx - t;
+      const double arg = -T / tau;
+      v.a = tau * (T + tau) * ((kFast && arg <= 0.0) ? fm_exp(F, arg) : exp(arg));
+      break;
+    }
+    case SB2_SFH_LOGNORMAL: {
+      const double x = fmax(mx - t, 1e-300);
+      const double u = ((kFast ? fm_log(F, x) : log(x)) - gc0) / p0;
+      v.a = kFast ? fm_tail(F, fabs(u)) : 0.5 * erfc(fabs(u) * r);
+      v.b = u;
+      break;
+    }
+    default:
+      v.a = nan("");
+  }
+  return v;
+}
+
+__device__ __forceinline__ double sfh_mass_s(int type, double p0, double p1, EdgeVal lo, EdgeVal hi) {
+  const double s2pi = 2.50662827463100050242;
+  switch (type) {
+    case SB2_SFH_GAUSSIAN: return p1 * s2pi * phi_between(lo, hi);
+    case SB2_SFH_LOGNORMAL: return -p0 * s2pi * phi_between(lo, hi);
+    default: return hi.a - lo.a;
+  }
+}
+
+// kMode 0: two-parameter families (scalars in registers); 1: Continuity; 2: DoublePowerLaw (parameter row read from global)
+// `put(a, mass)` receives the n_age bin masses in order; returns their sum.  s_edges: the grid's bin edges (shared memory).
+template <bool kFast, int kMode, class Put>
+__device__ __forceinline__ double sfh_masses_thread(const PrepModel& M, const FastMath& F, const PrepParams& P, long long g,
+                                                    const double* __restrict__ s_edges, Put put) {
+  const double* row = P.sfh_rows + g * P.sfh_stride;
+  double mn = row[0], mx = row[1];
+  double mxz = 1.0;
+  if (P.max_age_from_z) {   // library.py:1206 / :1287-1289
+    const double s = log1p(P.redshift[g]);
+    mxz = (hermite_lut(M.age, M.dage, M.cosmo_ds, M.cosmo_n, s) - P.age_zmax_gyr) * 1.0e9;
+    mx = mxz;
+  }
+  auto par = [&](int i) -> double {   // parameter i of the family, `_norm` ones scaled by max_age
+    const double v = (2 + i < P.sfh_stride) ? row[2 + i] : 0.0;
+    return (P.max_age_from_z && ((P.norm_mask >> i) & 1u)) ? v * mxz : v;
+  };
+  const int n_age = M.n_age;
+  double part = 0.0;
+  if constexpr (kMode == 0) {
+    const int type = P.sfh_type;
+    const double p0 = par(0), p1 = par(1);
+    double gc0 = 0.0;
+    if (type == SB2_SFH_LOGNORMAL) {
+      const double x = mx - p1;
+      gc0 = ((kFast && x > 2.3e-308 && x < 1.7e308) ? fm_log(F, x) : log(x)) + p0 * p0;
+    }
+    EdgeVal prev = sfh_edge_s<kFast>(F, type, p0, p1, gc0, mn, mx, s_edges[0]);
+#pragma unroll 2
+    for (int a = 0; a + 1 < n_age; ++a) {
+      const EdgeVal cur = sfh_edge_s<kFast>(F, type, p0, p1, gc0, mn, mx, s_edges[a + 1]);
+      const double mass = sfh_mass_s(type, p0, p1, prev, cur);
+      put(a, mass);
+      part += mass;
+      prev = cur;
+    }
+  } else if constexpr (kMode == 1) {
+    // piecewise-constant SFR over nb bins [edges_j, edges_j+1], SFR_j = prod_{i<=j} 10^(-ratio_i); F(e) = sum_j SFR_j * overlap
+    const int nb = (int)par(0);
+    double sfr[kGConst];
+    {
+      double cur = 1.0;
+      sfr[0] = 1.0;
+      for (int j = 1; j < nb && j < kGConst; ++j) { cur *= pow(10.0, -par(1 + nb + 1 + j - 1)); sfr[j] = cur; }
+    }
+    auto Fe = [&](double e) {
+      double acc = 0.0;
+      for (int j = 0; j < nb && j < kGConst; ++j) {
+        const double ov = fmin(e, par(1 + j + 1)) - par(1 + j);
+        if (ov > 0.0) acc += sfr[j] * ov;
+      }
+      return acc;
+    };
+    double prev = Fe(s_edges[0]);
+    for (int a = 0; a + 1 < n_age; ++a) {
+      const double cur = Fe(s_edges[a + 1]);
+      const double mass = cur - prev;
+      put(a, mass);
+      part += mass;
+      prev = cur;
+    }
+  } else {
+    double p[3] = {par(0), par(1), par(2)};
+    double prev = fmin(fmax(s_edges[0], mn), mx);
+    for (int a = 0; a + 1 < n_age; ++a) {
+      const double cur = fmin(fmax(s_edges[a + 1], mn), mx);
+      const double mass = dpl_bin_mass(p, prev, cur);
+      put(a, mass);
+      part += mass;
+      prev = cur;
+    }
+  }
+  put(n_age - 1, 0.0);   // the last age bin receives no mass (A2)
+  return part;
+}
+
+constexpr int kW3Threads = 128;   // one tile of the contraction kernel per block
+
+template <bool kFast, int kMode>
+__global__ void __launch_bounds__(kW3Threads)
+weights3_kernel(PrepModel M, FastMath F, PrepParams P, SfOut O, double* __restrict__ w_f64, const int* __restrict__ perm,
+                long long n_pad) {
+  __shared__ double s_edges[64];
+  if (threadIdx.x < M.n_age) s_edges[threadIdx.x] = M.edges[threadIdx.x];
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * kW3Threads + threadIdx.x;
+  if (t >= n_pad) return;
+  const long long g = perm ? (long long)perm[t] : (t < P.n ? t : -1);
+  double* sf = O.sf + (size_t)blockIdx.x * M.n_age * kW3Threads + threadIdx.x;
+  if (g < 0) {
+    for (int a = 0; a < M.n_age; ++a) sf[(size_t)a * kW3Threads] = 0.0;
+    O.s0[t] = 0.0; O.s1[t] = 0.0;
+    return;
+  }
+  const double part = sfh_masses_thread<kFast, kMode>(M, F, P, g, s_edges, [&](int a, double m) { sf[(size_t)a * kW3Threads] = m; });
+  const bool logz = (P.zd_type == SB2_ZD_DELTA_LOG10);
+  double zf = 0.0;
+  int zj = 0;
+  if (M.n_z >= 2) zj = delta_bracket(logz ? M.log10zmet : M.zmet, M.n_z, P.zd_value[g], &zf);
+  const double inv_sf = 1.0 / part;
+  const double s0 = (1.0 - zf) * inv_sf, s1 = zf * inv_sf;
+  O.s0[t] = s0; O.s1[t] = s1;
+  if (w_f64) {   // parity hook: the full row in the caller's order, k = iz*n_age + ia
+    double* w = w_f64 + g * M.K;
+    for (int k = 0; k < M.K; ++k) w[k] = 0.0;
+    for (int a = 0; a < M.n_age; ++a) {
+      const double m = sf[(size_t)a * kW3Threads];
+      w[zj * M.n_age + a] = m * s0;
+      if (M.n_z >= 2) w[(zj + 1) * M.n_age + a] = m * s1;
+    }
+  }
+}
+
 // First / last wavelength chunk (and bin) that any filter of a unit's galaxies can reach; one warp per unit
 // (a tile of 128 rows, or a pair of tiles).
 // Chunks outside the range are skipped by the contraction kernel, IGM bins below it are not evaluated.

@@ -38,14 +38,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The suspend-time hint lets the hardware park a waiting warp for up to ~kWaitHintNs instead of returning early: waiting
+// warps (writers, producer, idle epilogue groups) otherwise re-issue the try_wait loop hundreds of millions of times per
+// launch and take issue slots from the MMA warp on their scheduler (ncu, round 2: 45 % of all executed instructions).
+// A completed phase wakes the warp at once, so the hint adds no latency.
+constexpr uint32_t kWaitHintNs = 20000u;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs)
       : "memory");
   return ok != 0;
 }
@@ -75,7 +80,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0u) {
+    if ((++spins & 0x3Fu) == 0u) {
       const uint64_t now = global_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 2000000000ull) mbar_timeout(id, parity);
@@ -317,6 +322,41 @@ __device__ __forceinline__ void tma_load_2d_2sm_e(uint32_t elected, uint32_t sme
         "r"(elected)
       : "memory");
 }
+// ---------------------------------------------------------------- TS-mode MMA (A operand in TMEM), TMEM stores, bulk copies
+// D[tmem] (+)= A[tmem] * B[smem]: A is M=128 lanes x K=8 consecutive 32-bit columns at tmem_a (element (m, k) in lane m,
+// column tmem_a + k), B a K-major SWIZZLE_128B shared-memory tile.  Warp-uniform issue, one elected lane (see umma_tf32_e).
+__device__ __forceinline__ void umma_tf32_ts_e(uint32_t elected, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+// registers -> TMEM: thread t of the warp writes columns [c, c+N) of lane (base + t)  (mirror of tmem_ld_32x32b_x32)
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 1-D bulk copy global -> shared (bytes and both addresses multiples of 16), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load_e(uint32_t elected, uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar_addr) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar_addr), "r"(elected)
+      : "memory");
+}
+// Register budget hand-over between warpgroups (all four warps of an aligned warpgroup execute the same one)
+template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
 // Tell the compiler a value is the same in every lane of the (converged) warp.
 __device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 

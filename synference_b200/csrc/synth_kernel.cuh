@@ -157,17 +157,26 @@ __device__ __forceinline__ int chunk_rot(int n_c, unsigned who) { return 0; }
 // "Accumulator ready" barriers are PER GROUP (tfull_bar[kTfPerGroup g + k % kTfPerGroup] for the group's k-th chunk): an mbarrier
 // wait only carries one parity bit, so a waiter must see every phase of a barrier in order -- which a group does
 // for its own pair, but would not for per-buffer barriers that other groups also consume.
-template <int kComp, int kNF, bool kSpec, int kCta, int kN, int kGroups, bool kPgDust>
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+
+// kKapS: the attenuation curve is read from shared memory (kap_saddr) instead of global memory -- with ~225 KB of the SM's
+// 228 KB configured as shared memory there is no L1 left, so every __ldg of the curve was an L2 round trip per sub-chunk.
+template <int kComp, int kNF, bool kSpec, int kCta, int kN, int kGroups, bool kPgDust, int kWarp0 = kEpiWarp0, int kBufT = 512 / kN,
+          bool kKapS = false>
 __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* s_uv, float* s_spec, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tempty_addr, uint32_t tmem_base, int unit0, int unit_stride,
-                                              int n_units, uint32_t cta_rank) {
+                                              int n_units, uint32_t cta_rank, uint32_t kap_saddr = 0u) {
   constexpr int kLch = kN / kComp;      // wavelengths per chunk
   constexpr int kSub = kLch / 32;       // 32-wavelength sub-chunks per chunk
-  constexpr uint32_t kBuf = 512 / kN;   // TMEM accumulators (2 x 256 or 4 x 128 columns)
+  constexpr uint32_t kBuf = kBufT;      // TMEM accumulators (2 x 256, 3 x 160 or 4 x 128 columns; synth3: what W leaves free)
   static_assert((int)kBuf <= kTfPerGroup && kGroups <= (int)kBuf && kGroups <= kMaxGroups, "a group must own a whole accumulator while it drains it");
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
   const int c_all_last = (A.n_chunk * kBN / kComp + kLch - 1) / kLch - 1;   // last chunk of kLch wavelengths on the padded axis
-  const uint32_t grp = (uint32_t)(warp - kEpiWarp0) >> 2;
+  const uint32_t grp = (uint32_t)(warp - kWarp0) >> 2;
   if (grp >= (uint32_t)kGroups) return;
   {
     const int et = (warp & 3) * 32 + lane;                     // galaxy within tile == TMEM lane (a warp may only touch
@@ -248,7 +257,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               }
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                float4 k4 = __ldg(kp + j4);
+                float4 k4 = kKapS ? lds_f4(kap_saddr + (uint32_t)(i0 + 4 * j4) * 4u) : __ldg(kp + j4);
                 if (pg_dust && dust_pg) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
                                              __ldg(reinterpret_cast<const float4*>(A.dust_l2 + i0) + j4), slope, ampl);
                 if (two_screens) {   // young: birth cloud + ISM, old: ISM only (both components are attenuated)
@@ -290,7 +299,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               } else
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {  // ca goes into the final scale
-                float4 k4 = __ldg(kp + j4);
+                float4 k4 = kKapS ? lds_f4(kap_saddr + (uint32_t)(i0 + 4 * j4) * 4u) : __ldg(kp + j4);
                 if (pg_dust && dust_pg) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
                                              __ldg(reinterpret_cast<const float4*>(A.dust_l2 + i0) + j4), slope, ampl);
                 s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x);
@@ -328,7 +337,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               if (s_spec != nullptr) {
                 // a thread holds 32 wavelengths of ONE galaxy; transposed through a 32 x 33 tile so that each store
                 // instruction writes 128 contiguous bytes of one output row (per-thread stores reached 2 % of HBM)
-                float* tile = s_spec + (warp - kEpiWarp0) * (32 * 33);
+                float* tile = s_spec + (warp - kWarp0) * (32 * 33);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = s[j] * sc;
                 __syncwarp();
@@ -429,7 +438,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   uint64_t* tempty_bar = tfull_bar + kTfPerGroup * kMaxGroups;    // [kBuf]           epilogue -> MMA, per TMEM accumulator
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;   // uniform: see synth3_kernel
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo); prefetch_tmap(&tm_g_hi); prefetch_tmap(&tm_g_lo);

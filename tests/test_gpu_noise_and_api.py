@@ -250,11 +250,7 @@ def test_feature_only_philox_kernel_matches_general_kernel():
         flux = np.abs(rng.normal(40.0, 60.0, (30000, n_filt))) + 0.5
         sigma = depths_to_sigma_njy(np.full(n_filt, 28.5))
         _, _, fast = depth_noise_features(flux, sigma, n_scatter=n_sc, seed=3, epoch=5, want_flux=False)
-        os.environ["SB2_NOISE_V1"] = "1"
-        try:
-            _, _, ref = depth_noise_features(flux, sigma, n_scatter=n_sc, seed=3, epoch=5, want_flux=False)
-        finally:
-            del os.environ["SB2_NOISE_V1"]
+        _, _, ref = depth_noise_features(flux, sigma, n_scatter=n_sc, seed=3, epoch=5, want_flux=True)   # general kernel
         fast, ref = fast.cpu().numpy(), ref.cpu().numpy()
         assert fast.shape == (30000 * n_sc, 2 * n_filt)
         np.testing.assert_allclose(fast[:, :n_filt], ref[:, :n_filt], atol=6e-6, rtol=0)     # <= 3 ulp of a float32 magnitude

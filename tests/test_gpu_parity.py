@@ -39,11 +39,18 @@ def oracle_flux(w, params=None, spectra=False, c=False):
 def engines():
     cache = {}
 
-    def get(name, n, **kw):
-        key = (name, tuple(sorted(kw.items())))
+    def get(name, n, env=None, **kw):
+        """``env``: SB2_* switches; the library reads them once, when a model is created."""
+        import os
+        key = (name, tuple(sorted(kw.items())), tuple(sorted((env or {}).items())))
         w = make_workload(name, n)
         if key not in cache:
-            cache[key] = SynthEngine(w.grid, w.emission_model, w.emission_key, w.filters, max_batch=1 << 15, **kw)
+            os.environ.update(env or {})
+            try:
+                cache[key] = SynthEngine(w.grid, w.emission_model, w.emission_key, w.filters, max_batch=1 << 15, **kw)
+            finally:
+                for k in (env or {}):
+                    del os.environ[k]
         return w, cache[key]
 
     yield get
@@ -59,12 +66,10 @@ def test_weights_match_oracle(engines, name):
     # weights sum to 1; the table-driven normal tail / log / exp of the kernel are good to ~1e-12 relative
     np.testing.assert_allclose(W, Wo, rtol=0, atol=2e-12)
     np.testing.assert_allclose(W.sum(1), 1.0, rtol=0, atol=1e-12)
-    import os
-    os.environ["SB2_LIBM"] = "1"          # same kernel with the CUDA math library's erfc / log / exp
-    try:
-        np.testing.assert_allclose(eng.weights(w.params), Wo, rtol=0, atol=1e-13)
-    finally:
-        del os.environ["SB2_LIBM"]
+    _, libm = engines(name, 300, env={"SB2_LIBM": "1"})   # same kernel with the CUDA math library's erfc / log / exp
+    np.testing.assert_allclose(libm.weights(w.params), Wo, rtol=0, atol=1e-13)
+    _, half = engines(name, 300, env={"SB2_NO_SYNTH3": "1"})   # the half-warp builder behind synth_kernel
+    np.testing.assert_allclose(half.weights(w.params), Wo, rtol=0, atol=2e-12)
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
@@ -269,31 +274,23 @@ def test_results_do_not_depend_on_batch_composition(engines):
     """Chunks are handed to epilogue groups by chunk index, partial sums are added in a fixed order, and the
     host entry's slices are independent batches: a galaxy's fluxes are bit-identical alone, in a batch, and
     under any slicing of the batch."""
-    import os
     w, eng = engines("cfg2", 3000)
     full = eng.photometry(w.params, scaled=False)
     for sl in (slice(7, 8), slice(1000, 1300), slice(2990, 3000)):
         assert np.array_equal(eng.photometry(w.params.slice(sl), scaled=False), full[sl])
-    os.environ["SB2_HOST_SLICES"] = "3"
-    try:
-        assert np.array_equal(eng.photometry(w.params, scaled=False), full)
-    finally:
-        del os.environ["SB2_HOST_SLICES"]
+    _, sliced = engines("cfg2", 3000, env={"SB2_HOST_SLICES": "3"})
+    assert np.array_equal(sliced.photometry(w.params, scaled=False), full)
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2"])
 def test_cta_pair_kernel_matches_oracle_and_single_cta(engines, name):
     """synth2_kernel (cta_group::2, weights resident in shared memory) is opt-in; it must agree with the oracle
-    and, since both kernels multiply the same operands in the same order, bit for bit with the default kernel."""
-    import os
-    w, eng = engines(name, 2500)
+    and, since both kernels multiply the same operands in the same order, bit for bit with synth_kernel."""
+    w, eng = engines(name, 2500, env={"SB2_NO_SYNTH3": "1"})
     single = eng.photometry(w.params, scaled=False)
-    os.environ["SB2_CTA_PAIR"] = "1"
-    try:
-        pair = eng.photometry(w.params, scaled=False)
-        spec = eng.spectra(w.params.slice(slice(0, 300)))
-    finally:
-        del os.environ["SB2_CTA_PAIR"]
+    _, peng = engines(name, 2500, env={"SB2_CTA_PAIR": "1"})
+    pair = peng.photometry(w.params, scaled=False)
+    spec = peng.spectra(w.params.slice(slice(0, 300)))
     want, spec_want = oracle_flux(w, params=w.params.slice(slice(0, 300)), spectra=True)
     assert_flux_close(pair[:300], want)
     big = spec_want > 1e-25 * spec_want.max(axis=1, keepdims=True)
