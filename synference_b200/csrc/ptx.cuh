@@ -336,6 +336,22 @@ __device__ __forceinline__ void umma_tf32_ts_e(uint32_t elected, uint32_t tmem_d
       : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
       : "memory");
 }
+// Same, with the B descriptor given as its LOW word only (start address >> 4 | LBO field); the high word of a K-major
+// SWIZZLE_128B descriptor is a constant (SBO = 1024 B, version 1, layout 2), so the issue loop does 32-bit arithmetic.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t kDescLoBase = 1u << 16;
+__device__ __forceinline__ void umma_tf32_ts_lo_e(uint32_t elected, uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_b_lo,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "r"(elected), "r"(kDescHiSw128)
+      : "memory");
+}
 // registers -> TMEM: thread t of the warp writes columns [c, c+N) of lane (base + t)  (mirror of tmem_ld_32x32b_x32)
 __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"

@@ -77,14 +77,14 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
   // (the shuffle tells ptxas the role branches below are warp-uniform: inside a branch it cannot prove uniform it keeps
   //  every loop variable and descriptor in vector registers and pays an R2UR per MMA operand)
   const int warp = warp_uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
-  constexpr int kWTma = 14, kWMma = 15, kWLoad = 13, kWAlloc = 12;
+  constexpr int kWMma = 15, kWMma2 = 14, kWTma = 13, kWLoad = 12, kWAlloc = 12;
 
   if (warp == kWTma && lane == 0) { prefetch_tmap(&tm_g_hi); prefetch_tmap(&tm_g_lo); }
   if (warp == kWMma && lane == 0) {
-    for (int s = 0; s < kS3MaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kS3MaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }   // empty: both issuers
     for (int b = 0; b < kTfPerGroup * 2; ++b) mbar_init(&tfull_bar[b], 1);
     for (int b = 0; b < 4; ++b) mbar_init(&tempty_bar[b], 4);
-    for (int r = 0; r < 2; ++r) { mbar_init(&wready_bar[r], 4); mbar_init(&wfree_bar[r], 1); }
+    for (int r = 0; r < 2; ++r) { mbar_init(&wready_bar[r], 4); mbar_init(&wfree_bar[r], 2); }   // wfree: both issuers
     mbar_init(sfull_bar, 1);
     mbar_init(sempty_bar, 4);
     fence_barrier_init();
@@ -119,6 +119,11 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1, 0x3100u + (uint32_t)stage);
             const uint32_t st = s_addr + (uint32_t)stage * kStageBytes, fb = full0 + (uint32_t)stage * 8u;
+            if (SB2_DBG_BITS(A) & 1024) {   // experiment: no operand traffic
+              mbar_expect_tx_e(elected, &full_bar[stage], 0);
+              if (++stage == n_stages) { stage = 0; phase ^= 1; }
+              continue;
+            }
             mbar_expect_tx_e(elected, &full_bar[stage], kStageBytes);
             if constexpr (kComp == 1) {
               tma_load_2d_e(elected, st, &tm_g_hi, fb, k0 + kb * kBK, c * kN, kEvictLast);
@@ -136,61 +141,75 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
           }
         }
       }
-    } else if (warp == kWMma) {
-      // ===================================================================== MMA issuer (A from TMEM)
+    } else if (warp == kWMma || warp == kWMma2) {
+      // ===================================================================== MMA issuers (A from TMEM), one per epilogue group
+      // Issuing one M128 x N96 x K8 MMA costs this warp ~10 instructions of descriptor arithmetic, i.e. more than the 48 cycles
+      // the tensor pipe needs for it: a single issuer warp was busy 80 % of the time for 64 % tensor-pipe activity (ncu).
+      // Two issuers split the chunks by parity -- issuer g feeds epilogue group g -- each with its own commit stream.
       constexpr uint32_t idesc = make_idesc_tf32(kBM, kN);
+      const uint32_t me = warp == kWMma2 ? 1u : 0u;
       const uint32_t elected = elect_one() ? 1u : 0u;
-      const uint32_t s_addr = smem_u32(smem);
-      const uint64_t desc0 = make_kmajor_sw128_desc(0);
+      const uint32_t s_lo0 = ((smem_u32(smem) & 0x3FFFFu) >> 4) | kDescLoBase;
       const uint32_t tmem_u = (uint32_t)warp_uniform((int)tmem_base);
       const uint32_t a_hi0 = tmem_u + kS3WBase, a_lo0 = a_hi0 + kS3WCols;
       const int n_tiles_u = warp_uniform(n_tiles), k8_total = A.k8_total;
       const int kb_free0 = max(kb_split, 1) - 1;
-      int stage = 0; uint32_t phase = 0, it = 0, ti = 0;
-      uint32_t gk0 = 0, gk1 = 0;
+      int stage = 0; uint32_t phase = 0, it = 0, ti = 0, gk = 0;
       for (int tile = blockIdx.x; tile < n_tiles_u; tile += gridDim.x, ++ti) {
         const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
         const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
-        if (c_last < c_first) {   // nothing to multiply (padding-only tile): keep the weights hand-shake in step
+        const int my_first = c_first + (int)(((uint32_t)c_first ^ me) & 1u), my_last = c_last - (int)(((uint32_t)c_last ^ me) & 1u);
+        if (my_last < my_first) {
+          // no chunk of this tile is mine: keep the weights hand-shake in step.  The wait comes first -- this tile's weights
+          // are only written once BOTH issuers released the previous tile's, so neither can arrive twice in one phase.
           mbar_wait(&wready_bar[0], ti & 1u, 0x3200u);
           mbar_wait(&wready_bar[1], ti & 1u, 0x3201u);
           umma_commit_e(elected, &wfree_bar[0]);
           umma_commit_e(elected, &wfree_bar[1]);
-          continue;
         }
         for (int c = c_first; c <= c_last; ++c, ++it) {
+          // Both issuers walk EVERY chunk and observe every phase of the barriers they share (an mbarrier wait carries one
+          // parity bit: a waiter that skipped a phase would alias).  The other issuer's stages are released as soon as they
+          // have been seen -- the ring slot is refilled once both have arrived (count 2).
           const uint32_t buf = it % kBuf;
           mbar_wait(&tempty_bar[buf], ((it / kBuf) & 1u) ^ 1u, 0x3300u + (it << 12));
+          if (((uint32_t)c & 1u) != me) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+              mbar_wait(&full_bar[stage], phase, 0x3580u + (uint32_t)stage);
+              if (elected) mbar_arrive(&empty_bar[stage]);
+              if (++stage == n_stages) { stage = 0; phase ^= 1; }
+            }
+            continue;
+          }
           tc_fence_after();
           const uint32_t d_tmem = tmem_u + buf * kN;
           for (int kb = 0; kb < n_kb; ++kb) {
-            if (c == c_first) {   // this tile's weights: region A before the first k-block, region B before k-block kb_split
+            if (c == my_first) {   // this tile's weights: region A before the first k-block, region B before k-block kb_split
               if (kb == 0) { mbar_wait(&wready_bar[0], ti & 1u, 0x3400u); if (kb_split == 0) mbar_wait(&wready_bar[1], ti & 1u, 0x3401u); tc_fence_after(); }
               else if (kb == kb_split) { mbar_wait(&wready_bar[1], ti & 1u, 0x3402u); tc_fence_after(); }
             }
             mbar_wait(&full_bar[stage], phase, 0x3500u + (uint32_t)stage);
             tc_fence_after();
-            const uint64_t db = desc0 + (uint64_t)(((s_addr + stage * kStageBytes) & 0x3FFFF) >> 4);
+            const uint32_t b_lo32 = s_lo0 + (uint32_t)stage * (uint32_t)(kStageBytes >> 4);
+            const uint32_t a_hi = a_hi0 + (uint32_t)(kb * kBK), a_lo = a_lo0 + (uint32_t)(kb * kBK);
             const int k4n = min(kBK / 8, k8_total - kb * (kBK / 8));
 #pragma unroll
             for (int k4 = 0; k4 < kBK / 8; ++k4) {
               if (k4 < k4n) {
-                const uint32_t a_hi = a_hi0 + (uint32_t)(kb * kBK + k4 * 8), a_lo = a_lo0 + (uint32_t)(kb * kBK + k4 * 8);
-                const uint64_t b_hi = db + (uint64_t)(k4 * 2), b_lo = db + (uint64_t)((kHalf >> 4) + k4 * 2);
-                umma_tf32_ts_e(elected, d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
-                umma_tf32_ts_e(elected, d_tmem, a_hi, b_lo, idesc, 1u);
-                umma_tf32_ts_e(elected, d_tmem, a_hi, b_hi, idesc, 1u);
+                umma_tf32_ts_lo_e(elected, d_tmem, a_lo + k4 * 8, b_lo32 + k4 * 2, idesc, (kb | k4) != 0);  // small terms first
+                umma_tf32_ts_lo_e(elected, d_tmem, a_hi + k4 * 8, b_lo32 + (kHalf >> 4) + k4 * 2, idesc, 1u);
+                umma_tf32_ts_lo_e(elected, d_tmem, a_hi + k4 * 8, b_lo32 + k4 * 2, idesc, 1u);
               }
             }
             umma_commit_e(elected, &empty_bar[stage]);
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
-            if (c == c_last) {    // last chunk of the tile: hand the weights regions back as their MMAs retire
+            if (c == my_last) {    // my last chunk of the tile: hand the weights regions back as their MMAs retire
               if (kb == kb_free0) umma_commit_e(elected, &wfree_bar[0]);
               if (kb == n_kb - 1) umma_commit_e(elected, &wfree_bar[1]);
             }
           }
-          if ((c & 1) == 0) { umma_commit_e(elected, &tfull_bar[gk0 % kTfPerGroup]); ++gk0; }
-          else              { umma_commit_e(elected, &tfull_bar[kTfPerGroup + gk1 % kTfPerGroup]); ++gk1; }
+          umma_commit_e(elected, &tfull_bar[kTfPerGroup * me + gk % kTfPerGroup]);   // wake epilogue group `me`
+          ++gk;
         }
       }
     } else if (warp == kWLoad) {
@@ -218,7 +237,7 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
       for (int r = 0; r < 2; ++r) {
         mbar_wait(&wfree_bar[r], (ti & 1u) ^ 1u, 0x3800u + (uint32_t)r);
         tc_fence_after();
-        const int c_lo = r ? split_col : 0, c_hi = r ? X.w_stride : split_col;
+        const int c_lo = r ? split_col : 0, c_hi = ((SB2_DBG_BITS(A) & 512) && ti > 0) ? 0 : (r ? X.w_stride : split_col);   // experiment 512: hand-shake only
         for (int c = c_lo; c < c_hi; c += 8) {    // na_pad is a multiple of 8: a group of 8 columns has one metallicity
           const bool up = c >= X.na_pad;
           const int a0 = c - (up ? X.na_pad : 0);
