@@ -675,14 +675,18 @@ int check_params(const sb2_model* m, const sb2_params* p) {
 
 // A unit of work of the contraction kernel: one 128-galaxy tile, or a PAIR of tiles for the CTA-pair kernel
 // (bracket-grouped batches).
-int rows_per_unit(const sb2_model* m, bool delta) {
+int rows_per_unit_old(const sb2_model* m, bool delta) {
   // The CTA-pair kernel (synth2_kernel) is parity-tested but not yet faster than the single-CTA kernel on B200
   // (both sit on the same synchronisation/epilogue floor); it is opt-in: SB2_CTA_PAIR=1.
   return (delta && m->smem2_bytes > 0 && !m->dust_d0 && !m->lya_line && !m->kappa_birth && !m->dust_wnu && m->sw.cta_pair) ? 256 : 128;
 }
+int rows_per_unit(const sb2_model* m, const sb2_params* p, bool delta) {
+  if (delta && use_s3(m, p)) return 128;
+  return rows_per_unit_old(m, delta);
+}
 // Rows the grouped layout of a batch of n galaxies can occupy (every group is padded to whole units).
-long long padded_rows(const sb2_model* m, long long n, bool delta) {
-  const long long rpu = rows_per_unit(m, delta);
+long long padded_rows(const sb2_model* m, const sb2_params* p, long long n, bool delta) {
+  const long long rpu = rows_per_unit(m, p, delta);
   return (n + rpu - 1) / rpu * rpu + (delta ? rpu * (m->d.n_z - 1) : 0);
 }
 
@@ -690,8 +694,8 @@ long long padded_rows(const sb2_model* m, long long n, bool delta) {
 int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool all_lam, cudaStream_t st) {
   const long long n = p->n;
   const bool delta = sorted && delta_mode(m, p);
-  const long long n_pad = padded_rows(m, n, delta);
-  const int rpu = rows_per_unit(m, delta);
+  const long long n_pad = padded_rows(m, p, n, delta);
+  const int rpu = rows_per_unit(m, p, delta);
   const int* perm = nullptr;
   cudaEventRecord(m->ev[0], st);
   if (sorted) {
@@ -731,7 +735,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
     int lo_min = m->h_lo[0], hi_max = m->h_hi[0];
     for (int f = 1; f < d.n_filt; ++f) { lo_min = std::min(lo_min, m->h_lo[f]); hi_max = std::max(hi_max, m->h_hi[f]); }
     const int wpb = 8, n_units = (int)(n_pad / rpu);
-    const int cols = rpu == 256 ? sb2::kBN2 : ((delta && use_s3(m, p)) ? s3_cols(m) : (use_n160(m) ? 160 : sb2::kBN));
+    const int cols = (delta && use_s3(m, p)) ? s3_cols(m) : (rpu == 256 ? sb2::kBN2 : (use_n160(m) ? 160 : sb2::kBN));
     sb2::tile_range_kernel<<<(n_units + wpb - 1) / wpb, wpb * 32, 0, st>>>(m->g_m, m->g_orig, n_units, rpu, lo_min, hi_max, d.n_lam,
                                                                          cols / d.n_comp, all_lam ? 1 : 0, m->tile_range);
     STAGE_CHECK("tile_range_kernel", st);
@@ -772,7 +776,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   STAGE_CHECK("weights_kernel", st);
   if (M.igm_on && !w_f64) {
     dim3 grid((unsigned)(n_pad / 128), (unsigned)((m->n_blue_pad + sb2::kIgmStrip - 1) / sb2::kIgmStrip));
-    sb2::igm_kernel<<<grid, 128, 0, st>>>(M, m->zpow, m->igm, m->tile_range, rpu == 256 ? 1 : 0, m->n_blue_pad, n_pad);
+    sb2::igm_kernel<<<grid, 128, 0, st>>>(M, m->zpow, m->g_orig, m->igm, m->tile_range, rpu == 256 ? 1 : 0, m->n_blue_pad, n_pad);
     STAGE_CHECK("igm_kernel", st);
   }
   cudaEventRecord(m->ev[2], st);
@@ -804,8 +808,8 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   sb2::SynthArgs a{};
   const bool delta = delta_mode(m, p);
   a.n_gal = (int)p->n;
-  const int rpu = rows_per_unit(m, delta);
-  a.n_tiles = (int)(padded_rows(m, p->n, delta) / rpu);  // units
+  const int rpu = rows_per_unit(m, p, delta);
+  a.n_tiles = (int)(padded_rows(m, p, p->n, delta) / rpu);  // units
   a.n_tiles_dev = m->grp + 3 * kMaxGroups;
   a.tile_k0 = m->tile_k0;
   a.k8_total = (delta ? m->wd_stride : d.k_pad) / 8;

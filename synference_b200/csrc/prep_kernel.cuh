@@ -868,22 +868,86 @@ __global__ void tile_range_kernel(const int* __restrict__ g_m, const int* __rest
 }
 
 // Inoue+14 transmission exp(-tau(z, lam_i (1+z))) for the bins blueward of Ly-alpha.
-// Block = one 128-galaxy tile x one strip of 64 wavelength bins; thread = galaxy, so the per-bin tables are
-// warp-uniform loads, the (redshift-sorted) galaxies of a warp take the same branches, and the store of
-// 128 consecutive floats per bin is coalesced in the tile-blocked layout the contraction epilogue reads.
-// No pow(): every term is coef * (lam_i/911.8)^p * (1+z)^p with host-tabulated bin powers and the
-// per-galaxy z powers from prep_kernel; "lines in regime k" are prefixes of the wavelength-sorted
-// line list, tracked by pointers that only move down as the bin index grows.
+// Block = one 128-galaxy tile x one strip of 64 wavelength bins; thread = galaxy; the store of 128 consecutive floats per
+// bin is coalesced in the tile-blocked layout the contraction epilogue reads.
+//
+// With x = lam_i / 911.8 every term of tau is coef * x^p * (1+z)^p' and WHICH terms apply (lines in each regime, the
+// Lyman-continuum branches) depends on z only through a handful of comparisons.  The galaxies of a tile are redshift
+// neighbours, so for almost every (tile, bin) all 128 take the same branches and
+//       tau_g = c0 + sum_k c_k * (1+z_g)^{p_k},   p = (1.2, 2.1, 3.7, 5.5, -0.3, 2, 3)
+// with coefficients that depend on the bin only.  Phase 1 (one thread per bin of the strip) evaluates the branch logic
+// at the tile's lowest and highest redshift; if they agree it stores the 8 coefficients, else it flags the bin.  Phase 2
+// (one thread per galaxy) is then a 7-term float64 dot product per bin -- ~25 instructions instead of ~100 -- and only
+// flagged bins (a tile straddling a regime boundary at that wavelength) take the exact per-galaxy evaluation.
+// No pow(): bin powers are host-tabulated, the (1+z) powers come from scalars_kernel; "lines in regime k" are prefixes of
+// the wavelength-sorted line list, so per-regime sums are differences of prefix sums.
 constexpr int kIgmStrip = 64;
 
-__global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __restrict__ zpow, float* __restrict__ igm,
-                                                  const int4* __restrict__ tile_range, int range_shift, int nb_pad,
-                                                  long long n_pad) {
+struct IgmRegime { int a, b, c, dla, laf, xc; };   // line-regime prefixes, Lyman-continuum branch classes
+
+__device__ __forceinline__ IgmRegime igm_regime(const double* __restrict__ s_thr, double xl, double z, int J) {
+  int n1 = 0, n2 = 0, nd = 0;   // lines (sorted by decreasing wavelength) still below the regime thresholds
+#pragma unroll
+  for (int step = 32; step; step >>= 1) {
+    if (s_thr[0 * 64 + n1 + step - 1] > xl) n1 += step;
+    if (s_thr[1 * 64 + n2 + step - 1] > xl) n2 += step;
+    if (s_thr[2 * 64 + nd + step - 1] > xl) nd += step;
+  }
+  IgmRegime r;
+  r.a = min(J, n1); r.b = min(J, n2); r.c = min(J, nd);
+  r.dla = z < 2.0 ? 0 : (xl >= 3.0 ? 1 : 2);
+  r.laf = z < 1.2 ? 0 : (z < 4.7 ? (xl >= 2.2 ? 1 : 2) : (xl > 5.7 ? 3 : ((xl >= 2.2 && xl < 5.7) ? 4 : (xl < 2.2 ? 5 : 6))));
+  r.xc = 0;
+  return r;
+}
+
+// coefficients of (1, Z0..Z6) for one bin in regime R; q = per-bin powers x^1.2, x^2.1, x^3.7, x^5.5, x^-0.3, x
+__device__ __forceinline__ void igm_coefficients(const double* __restrict__ s_pre, const IgmRegime& R, int J, bool lc_on,
+                                                 double x12, double x21, double x37, double x55, double xm3, double x1, double* c) {
+  const double x2 = x1 * x1, x3 = x2 * x1;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c[k] = 0.0;
+  c[1] = x12 * s_pre[0 * 64 + R.a];
+  c[3] = x37 * (s_pre[1 * 64 + R.b] - s_pre[1 * 64 + R.a]);
+  c[4] = x55 * (s_pre[2 * 64 + J] - s_pre[2 * 64 + R.b]);
+  c[6] = x2 * s_pre[3 * 64 + R.c];
+  c[7] = x3 * (s_pre[4 * 64 + J] - s_pre[4 * 64 + R.c]);
+  if (!lc_on) return;
+  // Lyman continuum, DLA component
+  if (R.dla == 0) c[6] += 0.2113 - 0.07661 * xm3 - 0.1347 * x2;
+  else if (R.dla == 1) c[7] += 0.04696 - 0.01779 * xm3 - 0.02916 * x3;
+  else { c[0] += 0.6340; c[7] += 0.04696 - 0.01779 * xm3; c[6] -= 0.1347 * x2; c[5] -= 0.2905 * xm3; }
+  // Lyman continuum, LAF component
+  switch (R.laf) {
+    case 0: c[1] += 0.3248 * (x12 - x21); break;
+    case 1: c[3] += 2.545e-2 * (x21 - x37); break;
+    case 2: c[3] += 2.545e-2 * x21; c[1] += 0.3248 * x12; c[2] -= 0.2496 * x21; break;
+    case 3: c[4] += 5.221e-4 * (x21 - x55); break;
+    case 4: c[4] += 5.221e-4 * x21; c[2] += 0.2182 * x21; c[3] -= 2.545e-2 * x37; break;
+    case 5: c[4] += 5.221e-4 * x21; c[1] += 0.3248 * x12; c[2] -= 3.140e-2 * x21; break;
+    default: break;
+  }
+}
+
+__device__ __forceinline__ float igm_exp(double tau) {
+  // exp(-tau) = 2^n * 2^f with the split done in float64 and only 2^f (|f| <= 1/2) in float32
+  const double y = -tau * 1.44269504088896340736;
+  const double yn = rint(fmin(fmax(y, -200.0), 100.0));
+  const int ex = (int)yn + 127;
+  return ex > 0 ? __int_as_float(ex << 23) * exp2f((float)(y - yn)) : 0.f;
+}
+
+__global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __restrict__ zpow, const int* __restrict__ g_orig,
+                                                  float* __restrict__ igm, const int4* __restrict__ tile_range, int range_shift,
+                                                  int nb_pad, long long n_pad) {
   const int first_bin = tile_range ? tile_range[blockIdx.x >> range_shift].z : 0;  // bins below it are never integrated (warp-uniform)
   if ((int)(blockIdx.y + 1) * kIgmStrip <= first_bin) return;
   __shared__ double s_thr[3 * 64];
   __shared__ double s_pre[5 * 64];
   __shared__ __align__(16) double s_bin[kIgmStrip * 8];   // per bin: x^1.2, x^2.1, x^3.7, x^5.5, x^-0.3, x, nline, lc_on
+  __shared__ __align__(16) double s_c[kIgmStrip * 8];     // per bin: coefficients of (1, Z0..Z6)
+  __shared__ int s_uni[kIgmStrip];
+  __shared__ double s_zr[8];
   const int np1 = M.n_lines + 1;
   const int nb = M.n_blue;
   const int strip0 = (int)blockIdx.y * kIgmStrip;
@@ -900,68 +964,70 @@ __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __r
     }
     s_bin[i] = v;
   }
-  __syncthreads();
   const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
-  double Z[12];
-#pragma unroll
-  for (int p = 0; p < 12; ++p) Z[p] = zpow[(size_t)p * n_pad + t];
   const double z = zpow[(size_t)12 * n_pad + t];
-  const double zp = 1.0 + z;
+  {  // the tile's redshift range over its real galaxies
+    const bool valid = g_orig[t] >= 0;
+    double zlo = valid ? z : 1e300, zhi = valid ? z : -1e300;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      zlo = fmin(zlo, __shfl_xor_sync(0xffffffffu, zlo, o));
+      zhi = fmax(zhi, __shfl_xor_sync(0xffffffffu, zhi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_zr[threadIdx.x >> 5] = zlo; s_zr[4 + (threadIdx.x >> 5)] = zhi; }
+  }
+  __syncthreads();
+  const double zlo = fmin(fmin(s_zr[0], s_zr[1]), fmin(s_zr[2], s_zr[3])), zhi = fmax(fmax(s_zr[4], s_zr[5]), fmax(s_zr[6], s_zr[7]));
   const int i0 = max(strip0, first_bin);
   const int i1 = min(nb, strip0 + kIgmStrip);
+  // ---- phase 1: one thread per bin of the strip
+  if (threadIdx.x < kIgmStrip) {
+    const int i = strip0 + threadIdx.x;
+    int uni = 0;
+    if (i >= i0 && i < i1 && zlo <= zhi) {
+      const double* q = s_bin + threadIdx.x * 8;
+      const int J = (int)q[6];
+      const IgmRegime r0 = igm_regime(s_thr, q[5] * (1.0 + zlo), zlo, J), r1 = igm_regime(s_thr, q[5] * (1.0 + zhi), zhi, J);
+      const bool lc = q[7] != 0.0;
+      uni = (r0.a == r1.a && r0.b == r1.b && r0.c == r1.c && (!lc || (r0.dla == r1.dla && r0.laf == r1.laf))) ? 1 : 0;
+      if (uni) igm_coefficients(s_pre, r0, J, lc, q[0], q[1], q[2], q[3], q[4], q[5], s_c + threadIdx.x * 8);
+    }
+    s_uni[threadIdx.x] = uni;
+  }
+  __syncthreads();
+  // ---- phase 2: one thread per galaxy
+  double Z[7];
+#pragma unroll
+  for (int p = 0; p < 7; ++p) Z[p] = zpow[(size_t)p * n_pad + t];
   float* out = igm + ((size_t)blockIdx.x * nb_pad) * 128 + threadIdx.x;
   for (int i = max(i0, nb); i < min(nb_pad, strip0 + kIgmStrip); ++i) out[(size_t)i * 128] = 1.f;  // padding rows
   if (i0 >= nb) return;
-  // lines (sorted by decreasing wavelength) still below the regime thresholds at the strip's first bin
-  int n1 = 0, n2 = 0, nd = 0;
-  {
-    const double xl = s_bin[(i0 - strip0) * 8 + 5] * zp;
-#pragma unroll
-    for (int step = 32; step; step >>= 1) {
-      if (s_thr[0 * 64 + n1 + step - 1] > xl) n1 += step;
-      if (s_thr[1 * 64 + n2 + step - 1] > xl) n2 += step;
-      if (s_thr[2 * 64 + nd + step - 1] > xl) nd += step;
-    }
-  }
-  // regime flags that depend on the galaxy only
-  const bool dla_lo = z < 2.0, laf_a = z < 1.2, laf_b = z < 4.7;
-  const double2* bp = reinterpret_cast<const double2*>(s_bin + (i0 - strip0) * 8);
   float* op = out + (size_t)i0 * 128;
-  for (int i = i0; i < i1; ++i, bp += 4, op += 128) {
-    const double2 q01 = bp[0], q23 = bp[1], q45 = bp[2], q67 = bp[3];
-    const double xl = q45.y * zp;  // lam_obs / 911.8
-    while (n1 > 0 && !(s_thr[0 * 64 + n1 - 1] > xl)) --n1;
-    while (n2 > 0 && !(s_thr[1 * 64 + n2 - 1] > xl)) --n2;
-    while (nd > 0 && !(s_thr[2 * 64 + nd - 1] > xl)) --nd;
-    const double b12 = q01.x * Z[0], b37 = q23.x * Z[2], b55 = q23.y * Z[3];
-    const double b2 = xl * xl, b3 = b2 * xl;
-    const int J = (int)q67.x;
-    const int a = min(J, n1), b = min(J, n2), c = min(J, nd);
-    double tau = b12 * s_pre[0 * 64 + a] + b37 * (s_pre[1 * 64 + b] - s_pre[1 * 64 + a]) +
-                 b55 * (s_pre[2 * 64 + J] - s_pre[2 * 64 + b]) + b2 * s_pre[3 * 64 + c] +
-                 b3 * (s_pre[4 * 64 + J] - s_pre[4 * 64 + c]);
-    if (q67.y != 0.0) {
-      const double b21 = q01.y * Z[1], bm3 = q45.x * Z[4];
-      // Lyman continuum, DLA component
-      if (dla_lo) tau += 0.2113 * Z[5] - 0.07661 * Z[10] * bm3 - 0.1347 * b2;
-      else if (xl >= 3.0) tau += 0.04696 * Z[6] - 0.01779 * Z[11] * bm3 - 0.02916 * b3;
-      else tau += 0.6340 + 0.04696 * Z[6] - 0.01779 * Z[11] * bm3 - 0.1347 * b2 - 0.2905 * bm3;
-      // Lyman continuum, LAF component
-      if (laf_a) tau += 0.3248 * (b12 - Z[7] * b21);
-      else if (laf_b) {
-        if (xl >= 2.2) tau += 2.545e-2 * (Z[8] * b21 - b37);
-        else tau += 2.545e-2 * Z[8] * b21 + 0.3248 * b12 - 0.2496 * b21;
-      } else {
-        if (xl > 5.7) tau += 5.221e-4 * (Z[9] * b21 - b55);
-        else if (xl >= 2.2 && xl < 5.7) tau += 5.221e-4 * Z[9] * b21 + 0.2182 * b21 - 2.545e-2 * b37;
-        else if (xl < 2.2) tau += 5.221e-4 * Z[9] * b21 + 0.3248 * b12 - 3.140e-2 * b21;
-      }
+  for (int i = i0; i < i1; ++i, op += 128) {
+    const int b = i - strip0;
+    double tau;
+    if (s_uni[b]) {
+      const double2* c = reinterpret_cast<const double2*>(s_c + b * 8);
+      const double2 c01 = c[0], c23 = c[1], c45 = c[2], c67 = c[3];
+      tau = c01.x;
+      tau = fma(c01.y, Z[0], tau);
+      tau = fma(c23.x, Z[1], tau);
+      tau = fma(c23.y, Z[2], tau);
+      tau = fma(c45.x, Z[3], tau);
+      tau = fma(c45.y, Z[4], tau);
+      tau = fma(c67.x, Z[5], tau);
+      tau = fma(c67.y, Z[6], tau);
+    } else {   // the tile straddles a regime boundary at this wavelength: this galaxy's own branches
+      const double* q = s_bin + b * 8;
+      const int J = (int)q[6];
+      const IgmRegime r = igm_regime(s_thr, q[5] * (1.0 + z), z, J);
+      double c[8];
+      igm_coefficients(s_pre, r, J, q[7] != 0.0, q[0], q[1], q[2], q[3], q[4], q[5], c);
+      tau = c[0];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) tau = fma(c[k + 1], Z[k], tau);
     }
-    // exp(-tau) = 2^n * 2^f with the split done in float64 and only 2^f (|f| <= 1/2) in float32
-    const double y = -tau * 1.44269504088896340736;
-    const double yn = rint(fmin(fmax(y, -200.0), 100.0));
-    const int ex = (int)yn + 127;
-    *op = ex > 0 ? __int_as_float(ex << 23) * exp2f((float)(y - yn)) : 0.f;
+    *op = igm_exp(tau);
   }
 }
 
