@@ -930,11 +930,14 @@ __device__ __forceinline__ void igm_coefficients(const double* __restrict__ s_pr
 }
 
 __device__ __forceinline__ float igm_exp(double tau) {
-  // exp(-tau) = 2^n * 2^f with the split done in float64 and only 2^f (|f| <= 1/2) in float32
+  // exp(-tau) = 2^n * 2^f: the split n = round(y), f = y - n is done in float64 (adding 1.5 * 2^52 leaves round(y) in the
+  // low word), only 2^f with |f| <= 1/2 in float32 (ex2.approx: 2 ulp), so the result keeps float32 accuracy for any tau
   const double y = -tau * 1.44269504088896340736;
-  const double yn = rint(fmin(fmax(y, -200.0), 100.0));
-  const int ex = (int)yn + 127;
-  return ex > 0 ? __int_as_float(ex << 23) * exp2f((float)(y - yn)) : 0.f;
+  const double t = y + 6755399441055744.0;
+  const int n = __double2loint(t);
+  const float f = (float)(y - (t - 6755399441055744.0));
+  const int ex = min(n, 127) + 127;
+  return (y > -150.0 && ex > 0) ? __int_as_float(ex << 23) * ex2_approx(f) : 0.f;
 }
 
 __global__ void __launch_bounds__(128) igm_kernel(PrepModel M, const double* __restrict__ zpow, const int* __restrict__ g_orig,
