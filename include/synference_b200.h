@@ -125,6 +125,10 @@ typedef struct sb2_model_desc {
   const double* fm_tail_tab;
   int32_t fm_tail_n;
   double fm_tail_w;
+  /* 1: rest-frame luminosities through the filters instead of observed fluxes (GalaxySimulator output_type "photo_lnu",
+   * src/synference/library.py:5756-5761): no redshift shift, no distance factor -- results are L_nu in erg/s/Hz at
+   * base_mass; create the model without IGM tables.  redshift is then only used for max_age_from_z.            */
+  int32_t rest_frame;
 } sb2_model_desc;
 
 /* Per-galaxy parameters, struct of arrays (float64).  Replaces the per-galaxy object lists

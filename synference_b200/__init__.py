@@ -16,7 +16,7 @@ from .sampling import (continuity_sfh_array, draw_from_hypercube, generate_metal
                        generate_sfh_basis, load_hypercube_from_npy)
 from .utils import (asinh_err_to_f_jy, asinh_to_f_jy, asinh_to_snr, calculate_min_max_wav_grid,  # noqa: F401
                     check_log_scaling, check_scaling, f_jy_err_to_asinh, f_jy_to_asinh, generate_constant_R,
-                    load_library_from_hdf5)
+                    load_library_from_hdf5, combine_rank_files)
 from .noise_models import (AsinhEmpiricalUncertaintyModel, DepthUncertaintyModel,  # noqa: F401
                            EmpiricalUncertaintyModel, GeneralEmpiricalUncertaintyModel,
                            SpectralUncertaintyModel, UncertaintyModel, load_unc_model_from_hdf5,

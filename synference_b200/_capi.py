@@ -46,6 +46,7 @@ class ModelDesc(C.Structure):
         ("lya_line", _dp), ("lya_bin", C.c_int32), ("kappa_birth", _fp),
         ("dust_wnu", _fp), ("dust_g", _fp), ("dust_duv", _fp), ("dust_m_len", C.c_int32),
         ("fm_log_tab", _dp), ("fm_exp_tab", _dp), ("fm_tail_tab", _dp), ("fm_tail_n", C.c_int32), ("fm_tail_w", C.c_double),
+        ("rest_frame", C.c_int32),
     ]
 
 

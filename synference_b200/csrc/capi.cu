@@ -295,6 +295,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   const int lch = sb2::kBN / d->n_comp;
   if (d->n_chunk != (d->n_lam + lch - 1) / lch) return fail(SB2_ERR_INVALID, "bad n_chunk");
   if (d->max_batch < 1) return fail(SB2_ERR_INVALID, "max_batch must be positive");
+  if (d->rest_frame && d->igm_bin_pow) return fail(SB2_ERR_INVALID, "rest_frame models take no IGM tables");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(SB2_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
@@ -635,6 +636,7 @@ sb2::PrepModel prep_model(const sb2_model* m) {
   M.n_age = d.n_age; M.n_z = d.n_z; M.na_pad = d.n_age_pad; M.K = d.n_age * d.n_z; M.k_pad = d.k_pad; M.n_lam = d.n_lam;
   M.n_filt = d.n_filt; M.n_blue = d.n_blue; M.n_lines = d.n_lines; M.variant = d.interp_variant;
   M.igm_on = d.n_blue > 0;
+  M.rest_frame = d.rest_frame ? 1 : 0;
   M.ages = m->ages; M.edges = m->edges; M.zmet = m->zmet; M.log10zmet = m->log10zmet;
   M.lam0 = d.lam0; M.q = d.q; M.ln_q = std::log(d.q); M.grid_scale = d.grid_scale; M.base_mass = d.base_mass;
   M.filt_lo = m->filt_lo; M.filt_hi = m->filt_hi;

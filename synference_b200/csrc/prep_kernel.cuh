@@ -16,7 +16,7 @@
 namespace sb2 {
 
 struct PrepModel {
-  int n_age, na_pad, n_z, K, k_pad, n_lam, n_filt, n_blue, n_lines, variant, igm_on;
+  int n_age, na_pad, n_z, K, k_pad, n_lam, n_filt, n_blue, n_lines, variant, igm_on, rest_frame;
   int delta;     // 1: DeltaConstant batch grouped by metallicity bracket -> weights row holds only the
                  //    two bracketing grid metallicities: [sf*(1-f) (na_pad) | sf*f (na_pad)], stride w_stride
   int w_stride;  // floats per weights row (k_pad, or 2*na_pad in delta mode)
@@ -309,7 +309,7 @@ scalars_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ per
   // a redshift that is not a finite number >= 0 cannot be placed on the wavelength axis: the galaxy gets NaN fluxes
   // (every filter flagged) and a harmless shift, instead of indexing the filter tables with garbage
   const bool z_ok = (z >= 0.0) && (z <= 1.0e6);
-  if (!z_ok) z = 0.0;
+  if (!z_ok || M.rest_frame) z = 0.0;     // rest_frame: luminosities through the filters at their own wavelengths
   const double zp = 1.0 + z;
   const double s = log1p(z);
   const double tq = s / M.ln_q;
@@ -323,7 +323,8 @@ scalars_kernel(PrepModel M, PrepParams P, PrepOut O, const int* __restrict__ per
   }
   const double dc = hermite_lut(M.dc, M.ddc, M.cosmo_ds, M.cosmo_n, s);
   const double dl_cm = zp * dc * 3.0856775814913673e24;
-  const double scale = M.grid_scale * M.base_mass * zp / (4.0 * 3.14159265358979323846 * dl_cm * dl_cm) * 1.0e32;
+  const double scale = M.rest_frame ? M.grid_scale * M.base_mass
+                                    : M.grid_scale * M.base_mass * zp / (4.0 * 3.14159265358979323846 * dl_cm * dl_cm) * 1.0e32;
   O.g_m[t] = m;
   O.g_beta[t] = (float)beta;
   O.g_gamma[t] = (float)((M.variant == 0) ? (1.0 / r - 1.0 / M.q) / (1.0 - 1.0 / M.q) : (M.q - r) / (M.q - 1.0));

@@ -81,7 +81,9 @@ def gather_rows(local, total: int):
 
 
 def merge_rank_shards(paths, out_path):
-    """Host-side merge of per-rank library shards into one library (``utils.py:2214-2328`` analogue)."""
+    """Host-side merge of per-rank LIBRARY shards (``Grid/Photometry`` ... with galaxies along the LAST axis, as
+    ``CombinedBasis.save_library`` writes them) into one library; everything that is not per-galaxy (the ``Model`` group)
+    is taken from the first shard."""
     from .utils import read_container, write_container
     datasets, attrs = None, None
     for p in paths:
@@ -90,8 +92,9 @@ def merge_rank_shards(paths, out_path):
             datasets, attrs = {k: [v] for k, v in d.items()}, dict(a)
         else:
             for k, v in d.items():
-                datasets[k].append(v)
-    merged = {k: np.concatenate(v, axis=-1) for k, v in datasets.items()}
+                if k.startswith("Grid/"):
+                    datasets[k].append(v)
+    merged = {k: (np.concatenate(v, axis=-1) if k.startswith("Grid/") else v[0]) for k, v in datasets.items()}
     attrs["world_size"], attrs["rank"] = 1, 0
     write_container(out_path, merged, attrs)
     return out_path

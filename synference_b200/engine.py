@@ -262,10 +262,12 @@ class SynthEngine:
 
     def __init__(self, grid: Grid, emission_model: EmissionModel, emission_key: str,
                  filters: FilterCollection, cosmo=Planck18, igm=True, variant="nu", base_mass=1.0e9,
-                 max_batch=1 << 20, device=0, fast_math=True):
+                 max_batch=1 << 20, device=0, fast_math=True, rest_frame=False):
         self.lib = _capi.load()
         if self.lib.sb2_device_count() < 1:
             raise RuntimeError("synference_b200: no CUDA device visible; the hot path has no CPU fallback")
+        if rest_frame and igm:
+            raise ValueError("rest_frame=True (luminosities through the filters) takes igm=False")
         self.tables = t = build_tables(grid, emission_model, emission_key, filters, cosmo, igm, variant)
         self.tables_lam = np.asarray(grid.lam, dtype=np.float64)
         self.filter_codes = list(filters.filter_codes)
@@ -312,6 +314,7 @@ class SynthEngine:
         d.cosmo_dc, d.cosmo_ddc = ptr(cz.dc, C.c_double), ptr(cz.ddc, C.c_double)
         d.cosmo_age, d.cosmo_dage = ptr(cz.age, C.c_double), ptr(cz.dage, C.c_double)
         d.base_mass, d.max_batch = self.base_mass, self.max_batch
+        d.rest_frame = 1 if rest_frame else 0
         if fast_math:
             fm = _fm.build_tables()
             d.fm_log_tab, d.fm_exp_tab = ptr(fm["log_tab"], C.c_double), ptr(fm["exp_tab"], C.c_double)

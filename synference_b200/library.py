@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import copy
 import os
+from concurrent.futures import ThreadPoolExecutor
 from datetime import datetime
 from typing import Dict, List, Optional, Union
 
@@ -270,15 +271,18 @@ class GalaxyBasis:
         return self._create_matched_galaxies(log_base_masses, galaxies_mask, n_proc)
 
     # ---------------------------------------------------------------------------------------
+    _MAX_ENGINES = 3     # device models kept alive per basis (one per emission key in use; least recently used is closed)
+
     def _engine(self, emission_key, igm=Inoue14, max_batch=40_000) -> SynthEngine:
         tag = f"{emission_key}|{bool(igm)}|{max_batch}"
-        if tag not in self._engines:
-            for e in self._engines.values():
-                e.close()
-            self._engines.clear()
-            self._engines[tag] = SynthEngine(self.grid, self.emission_model, emission_key,
-                                             self.instrument.filters, cosmo=self.cosmo, igm=bool(igm),
-                                             max_batch=max_batch, device=_dist.local_device())
+        if tag in self._engines:
+            self._engines[tag] = self._engines.pop(tag)          # most recently used last
+            return self._engines[tag]
+        while len(self._engines) >= self._MAX_ENGINES:
+            self._engines.pop(next(iter(self._engines))).close()
+        self._engines[tag] = SynthEngine(self.grid, self.emission_model, emission_key,
+                                         self.instrument.filters, cosmo=self.cosmo, igm=bool(igm),
+                                         max_batch=max_batch, device=_dist.local_device())
         return self._engines[tag]
 
     def process_galaxies(self, galaxies=None, out_name: str = "auto", out_dir: str = "internal", n_proc: int = 4,
@@ -317,6 +321,12 @@ class GalaxyBasis:
         spectra_keys = set(spectra_to_save or [])
         results = {"photometry": {k: [] for k in keys}, "spectra": {k: [] for k in keys if k in spectra_keys}}
         rank, size = _rank_size(multi_node)
+        # pipeline files are written by a background thread (the npz / HDF5 write releases the GIL in its I/O), so the
+        # next batch's kernels run while the previous batch's file goes to disk; what was written is also kept in
+        # memory for CombinedBasis.load_bases, which otherwise re-reads every file it has just produced
+        writer = ThreadPoolExecutor(max_workers=1) if save else None
+        pending = []
+        self._pipeline_cache = {"out_dir": os.path.abspath(out_dir), "parts": [], "complete": True}
         for batch_i in range(n_batches):
             sl = slice(batch_i * batch_size, min(n_gal, (batch_i + 1) * batch_size))
             final = fullpath if n_batches == 1 else fullpath.replace(".hdf5", f"_{batch_i + 1}.hdf5")
@@ -324,6 +334,17 @@ class GalaxyBasis:
                 final = final.replace(".hdf5", f"_rank{rank}.hdf5")
             if save and os.path.exists(final) and not overwrite:
                 logger.warning(f"Skipping batch {batch_i + 1} as {final} already exists.")
+                # keep the returned arrays aligned with the parameters: read the rows this file holds back
+                self._pipeline_cache["complete"] = False
+                old, _ = read_container(final)
+                label = self.instrument.label
+                for key in keys:
+                    cols = [old.get(f"Galaxies/Stars/Photometry/Fluxes/{key}/{label}/{c}") for c in self.instrument.filters.filter_codes]
+                    if all(c is not None for c in cols):
+                        results["photometry"][key].append(np.stack(cols, 1).astype(np.float32))
+                    skey = f"Galaxies/Stars/Spectra/SpectralFluxDensities/{key}"
+                    if key in results["spectra"] and skey in old:
+                        results["spectra"][key].append(old[skey])
                 continue
             start = datetime.now()
             supp_units = {}
@@ -383,8 +404,13 @@ class GalaxyBasis:
                          "InstrumentLabel": self.instrument.label, "batch": batch_i + 1, "n_batches": n_batches,
                          "rank": rank, "world_size": size, "galaxy_start": sl.start, "galaxy_stop": sl.stop,
                          "supp_names": list(supp_units), "supp_units": [supp_units[k] for k in supp_units]}
-                write_container(final, datasets, attrs, compress=False)
-                logger.info(f"Written pipeline to disk at {final}.")
+                self._pipeline_cache["parts"].append((os.path.basename(final), datasets, attrs))
+                pending.append(writer.submit(write_container, final, datasets, attrs, False))
+                logger.info(f"Writing pipeline to disk at {final}.")
+        for fut in pending:
+            fut.result()          # re-raises a failed write
+        if writer is not None:
+            writer.shutdown()
         return {k: {kk: (np.concatenate(vv) if vv else None) for kk, vv in v.items()} for k, v in results.items()}
 
     def process_base(self, out_name, log_stellar_masses=9, emission_model_key="total", out_dir=library_folder,
@@ -431,9 +457,9 @@ class GalaxyBasis:
         if compile_grid:
             logger.info("Compiling the library after processing bases.")
             # the Model/ block (library.py:2017-2132) travels with the library's single write
-            combined._extra_attrs = self._model_info({"emission_model_key": emission_model_key,
-                                                      "timestamp": datetime.now().isoformat(), "cat_type": cat_type},
-                                                     parameter_transforms_to_save)
+            combined._extra_datasets, combined._extra_attrs = self._model_block(
+                {"emission_model_key": emission_model_key, "timestamp": datetime.now().isoformat(), "cat_type": cat_type},
+                parameter_transforms_to_save)
             if cat_type == "photometry":
                 combined.create_library(overwrite=overwrite)
             else:
@@ -445,43 +471,109 @@ class GalaxyBasis:
         """Record what is needed to rebuild the simulator next to the library (``library.py:2017-2132``).  (Rewrites an
         existing library file; ``create_mock_library`` hands the same block to ``save_library`` instead, so that the
         library is written once.)"""
-        info = self._model_info(other_info, parameter_transforms_to_save)
+        m_data, m_attrs = self._model_block(other_info, parameter_transforms_to_save)
         if os.path.exists(model_path):
             data, attrs = read_container(model_path)
-            attrs.update(info)
+            data = {k: v for k, v in data.items() if not k.startswith("Model/")}
+            attrs = {k: v for k, v in attrs.items() if not k.startswith("Model")}
+            data.update(m_data)
+            attrs.update(m_attrs)
             write_container(model_path, data, attrs, compress=_library_compression())
         else:
-            write_container(model_path, {}, info, compress=False)
+            write_container(model_path, m_data, m_attrs, compress=False)
+        return True
 
-    def _model_info(self, other_info=None, parameter_transforms_to_save=None):
+    def _model_block(self, other_info=None, parameter_transforms_to_save=None):
+        """The ``Model`` group of a library file in the reference's layout (``library.py:2017-2132``) as
+        ``(datasets, attributes)`` for :func:`write_container` (``"Model/EmissionModel@name"`` is the attribute ``name`` of
+        the group ``Model/EmissionModel``): grid name / directory, emission model class + fixed parameters + dust law +
+        dust emission, cosmology, the instrument's filters on their wavelength axis, SFH / metallicity-distribution class
+        names, emitter parameters, varying / fixed parameter bookkeeping, the source of saved parameter transforms."""
+        from inspect import getsource
         em = self.emission_model
         dust = em.dust_curve
-        info = {
-            "Model/grid_name": self.grid.grid_name, "Model/grid_dir": str(self.grid.grid_dir),
-            "Model/emission_model": type(em).__name__,
-            # a string names a per-galaxy emitter parameter (the reference's convention), a number is global
-            "Model/fesc": em.fesc if isinstance(em.fesc, str) else float(em.fesc),
-            "Model/fesc_ly_alpha": em.fesc_ly_alpha if isinstance(em.fesc_ly_alpha, str) else float(em.fesc_ly_alpha),
-            "Model/dust_law": None if dust is None else dust.name,
-            "Model/dust_params": None if dust is None else dict(dust.params),
-            # dust emission generator, as library.py:2070-2074 records it (name, parameter keys / values / units)
-            "Model/dust_emission": None if em.dust_emission is None else type(em.dust_emission).__name__,
-            "Model/dust_emission_keys": None if em.dust_emission is None else ["temperature", "emissivity"],
-            "Model/dust_emission_values": None if em.dust_emission is None else [em.dust_emission.temperature,
-                                                                                 em.dust_emission.emissivity],
-            "Model/dust_emission_units": None if em.dust_emission is None else ["K", "dimensionless"],
-            "Model/cosmology": repr(self.cosmo), "Model/instrument": self.instrument.label,
-            "Model/filter_codes": list(self.instrument.filters.filter_codes),
-            "Model/sfh_type": self.params and int(self.params.sfh_type),
-            "Model/zd_type": self.params and int(self.params.zd_type),
-            "Model/varying_param_names": list(self.varying_param_names),
-            "Model/fixed_param_names": list(self.fixed_param_names),
-            "Model/fixed_param_values": list(self.fixed_param_values),
-        }
-        info.update({f"Model/{k}": v for k, v in (other_info or {}).items()})
-        if parameter_transforms_to_save:
-            info["Model/parameter_transforms"] = sorted(str(k) for k in parameter_transforms_to_save)
-        return info
+        A, D = {}, {}
+        A["Model@grid_name"] = self.grid.grid_name
+        A["Model@grid_dir"] = str(self.grid.grid_dir)
+        A["Model/EmissionModel@name"] = type(em).__name__
+        keys, vals = ["fesc", "fesc_ly_alpha"], [em.fesc, em.fesc_ly_alpha]
+        if getattr(em, "tau_v_birth_name", None) is not None:       # two screens: the names the emitter parameters travel under
+            keys += ["tau_v_ism", "tau_v_birth", "age_pivot"]
+            vals += [em.tau_v_ism_name, em.tau_v_birth_name, em.age_pivot]
+        else:
+            keys.append("tau_v")
+            vals.append(em.tau_v)
+        A["Model/EmissionModel@parameter_keys"] = keys
+        A["Model/EmissionModel@parameter_values"] = [str(v) for v in vals]     # a name (per-galaxy parameter) or a number
+        A["Model/EmissionModel@parameter_units"] = [""] * len(keys)
+        if dust is not None:
+            A["Model/EmissionModel@dust_law"] = dust.name
+            dp = dict(dust.params)
+            for nm, attr in (("slope", "slope_name"), ("ampl", "ampl_name")):
+                if getattr(dust, attr, None) is not None:
+                    dp[nm] = getattr(dust, attr)
+            A["Model/EmissionModel@dust_attenuation_keys"] = list(dp)
+            A["Model/EmissionModel@dust_attenuation_values"] = [str(v) for v in dp.values()]
+            A["Model/EmissionModel@dust_attenuation_units"] = ["um" if k in ("cent_lam", "gamma") else "" for k in dp]
+            birth = getattr(em, "dust_curve_birth", None)
+            if birth is not None:
+                A["Model/EmissionModel@dust_law_birth"] = birth.name
+                A["Model/EmissionModel@dust_attenuation_birth_keys"] = list(birth.params)
+                A["Model/EmissionModel@dust_attenuation_birth_values"] = [str(v) for v in birth.params.values()]
+        if em.dust_emission is not None:
+            A["Model/EmissionModel@dust_emission"] = type(em.dust_emission).__name__
+            A["Model/EmissionModel@dust_emission_keys"] = ["temperature", "emissivity"]
+            A["Model/EmissionModel@dust_emission_values"] = [em.dust_emission.temperature, em.dust_emission.emissivity]
+            A["Model/EmissionModel@dust_emission_units"] = ["K", ""]
+        A["Model@cosmology"] = repr(self.cosmo)
+        A["Model@instrument"] = self.instrument.label if self.instrument else "None"
+        if self.instrument:
+            A["Model@filters"] = list(self.instrument.filters.filter_codes)
+            A["Model/Instrument@label"] = self.instrument.label
+            fc = self.instrument.filters
+            lam0 = fc.lam if fc.lam is not None else fc.filters[0].lam
+            D["Model/Instrument/Filters/Header/Wavelengths"] = np.asarray(strip_units(lam0), dtype=np.float64)
+            A["Model/Instrument/Filters/Header@filter_codes"] = list(fc.filter_codes)
+            for f in fc.filters:
+                D[f"Model/Instrument/Filters/{f.filter_code}/Transmission"] = np.asarray(f.t, dtype=np.float64)
+                if fc.lam is None:
+                    D[f"Model/Instrument/Filters/{f.filter_code}/Wavelengths"] = np.asarray(f.lam, dtype=np.float64)
+
+        def cls_name(objs):
+            if isinstance(objs, SFHArray):
+                c = objs.sfh_type
+            elif isinstance(objs, ZDistArray):
+                c = type(objs[0])
+            else:
+                c = type(list(objs)[0])
+            return c.__name__.lstrip("_")
+        A["Model@sfh_class"] = cls_name(self.sfhs)
+        A["Model@metallicity_distribution_class"] = cls_name(self.metal_dists)
+        A["Model@model_name"] = self.model_name
+        for key, value in (other_info or {}).items():
+            if isinstance(value, (list, np.ndarray)) or (has_units(value) and np.ndim(value) > 0):
+                D[f"Model/{key}"] = np.asarray(strip_units(value))
+                if has_units(value):
+                    A[f"Model/{key}@units"] = str(value.units)
+            else:
+                A[f"Model@{key}"] = value
+        A["Model@stellar_params"] = list(self.galaxy_params.keys())
+        for key, value in (parameter_transforms_to_save or {}).items():
+            if isinstance(value, tuple) or callable(value):
+                if callable(value):
+                    value = (key, value)
+                name = key if isinstance(key, str) else "+".join(key)
+                D[f"Model/Transforms/{name}"] = np.frombuffer(getsource(value[1]).encode("utf-8"), dtype=np.uint8)
+                A[f"Model/Transforms/{name}@new_parameter_name"] = value[0] if isinstance(value[0], str) else list(value[0])
+        A["Model@varying_param_names"] = list(self.varying_param_names)
+        A["Model@fixed_param_names"] = list(self.fixed_param_names)
+        A["Model@fixed_param_values"] = list(self.fixed_param_values)
+        A["Model@fixed_param_units"] = list(self.fixed_param_units)
+        return D, A
+
+    def _model_info(self, other_info=None, parameter_transforms_to_save=None):
+        """Attribute half of :meth:`_model_block` (kept for callers that only need the bookkeeping)."""
+        return self._model_block(other_info, parameter_transforms_to_save)[1]
 
     def plot_galaxy(self, *a, **k):
         raise NotImplementedError("plotting helpers are outside the hot path (SURVEY 2 row 13)")
@@ -555,18 +647,32 @@ class CombinedBasis:
 
     def load_bases(self, load_spectra=False) -> dict:
         """Read the pipeline files back and concatenate batches / rank shards (``library.py:3385-3642``)."""
+        import re
         out = {}
+        rank, size = _rank_size(self._multi_node)
         for i, base in enumerate(self.bases):
             stem = os.path.join(self.out_dir, base.model_name)
-            files = [f for f in sorted(os.listdir(self.out_dir))
-                     if f.startswith(base.model_name) and f.endswith(".hdf5")
-                     and (f == base.model_name + ".hdf5" or f[len(base.model_name)] == "_")]
-            if not files:
-                raise FileNotFoundError(f"No pipeline output for base {base.model_name} in {self.out_dir}")
+            # <model>.hdf5 | <model>_<batch>.hdf5 | ..._rank<r>.hdf5 -- nothing else that merely starts with the name.
+            # With multi_node every rank compiles ITS OWN shard: only this rank's files are loaded (the ranks share out_dir).
+            pat = re.compile(r"^" + re.escape(base.model_name) + r"(_\d+)?(_rank(\d+))?\.hdf5$")
+            cache = getattr(base, "_pipeline_cache", None)
             parts = []
-            for f in files:
-                data, attrs = read_container(os.path.join(self.out_dir, f))
-                parts.append((int(attrs.get("galaxy_start", 0)), int(attrs.get("rank", 0)), data, attrs))
+            if cache and cache["complete"] and cache["parts"] and cache["out_dir"] == os.path.abspath(self.out_dir):
+                for fname, data, attrs in cache["parts"]:      # just written by process_galaxies: no need to read them back
+                    parts.append((int(attrs.get("galaxy_start", 0)), int(attrs.get("rank", 0)), data, attrs))
+            else:
+                files = []
+                for f in sorted(os.listdir(self.out_dir)):
+                    mt = pat.match(f)
+                    if mt and (size == 1 or mt.group(3) is None or int(mt.group(3)) == rank):
+                        files.append(f)
+                if not files:
+                    raise FileNotFoundError(f"No pipeline output for base {base.model_name} in {self.out_dir}")
+                for f in files:
+                    data, attrs = read_container(os.path.join(self.out_dir, f))
+                    if size > 1 and int(attrs.get("world_size", 1)) > 1 and int(attrs.get("rank", 0)) != rank:
+                        continue
+                    parts.append((int(attrs.get("galaxy_start", 0)), int(attrs.get("rank", 0)), data, attrs))
             parts.sort(key=lambda t: (t[1], t[0]))
             key = self.base_emission_model_keys[i]
             label = parts[0][3].get("InstrumentLabel", base.instrument.label)
@@ -845,6 +951,7 @@ class CombinedBasis:
         for param in library_params_to_save:
             attrs[param] = [str(getattr(b, param)) for b in self.bases]
         attrs.update(getattr(self, "_extra_attrs", None) or {})
+        datasets.update(getattr(self, "_extra_datasets", None) or {})
         write_container(path, datasets, attrs, compress=_library_compression())
         self.library_path = path
 
@@ -922,6 +1029,157 @@ class GalaxySimulator:
         name = zdist_model.__name__
         return ["log10metallicity"] if name == "_DeltaConstant" else ["mean", "sigma"]
 
+    @classmethod
+    def from_library(cls, library_path: str, override_synthesizer_grid_dir: Union[None, str, bool] = True,
+                     override_emission_model: Optional[EmissionModel] = None, **kwargs):
+        """Rebuild the simulator that produced a library from the ``Model`` group stored in it
+        (``library.py:5219-5551``): grid by name / directory (``override_synthesizer_grid_dir`` or ``SYNTHESIZER_GRID_DIR``
+        when the recorded directory does not exist here; a ready ``grid=`` may be passed instead), instrument from the
+        stored filter curves, SFH / metallicity-distribution classes, emission model with its dust law and dust emission,
+        parameter order and units from the library's ``ParameterNames`` / ``ParameterUnits``, fixed parameters and saved
+        parameter transforms.  Extra keyword arguments go to the constructor, as in the reference."""
+        import inspect
+        import json
+        from . import parametric as P
+        from .parametric import SFH, ZDist, Filter, FilterCollection
+        from .units import Unit
+        if not os.path.exists(library_path):
+            raise FileNotFoundError(f"Library path {library_path} does not exist. Cannot create GalaxySimulator.")
+        data, attrs = read_container(library_path)
+        if not any(k.startswith("Model@") or k.startswith("Model/") for k in list(attrs) + list(data)):
+            raise ValueError(f"Library file {library_path} does not contain 'Model' group. Cannot create GalaxySimulator.")
+        g = lambda k, d=None: attrs.get(f"Model@{k}", d)                                        # noqa: E731
+        e = lambda k, d=None: attrs.get(f"Model/EmissionModel@{k}", d)                          # noqa: E731
+        lam = np.asarray(data["Model/Instrument/Filters/Header/Wavelengths"], dtype=float)
+        # Step 1: grid
+        grid = kwargs.pop("grid", None)
+        if grid is None:
+            grid_name, grid_dir = g("grid_name"), g("grid_dir")
+            if override_synthesizer_grid_dir is not None and not os.path.exists(str(grid_dir)):
+                if isinstance(override_synthesizer_grid_dir, str) and os.path.exists(override_synthesizer_grid_dir):
+                    grid_dir = override_synthesizer_grid_dir
+                else:
+                    grid_dir = os.getenv("SYNTHESIZER_GRID_DIR", None) or "."
+            if isinstance(grid_dir, str) and grid_dir.endswith((".hdf5", ".h5", ".npz")):
+                logger.info("Overriding internal library name from provided file path.")
+                grid_name = os.path.basename(grid_dir).replace(".hdf5", "").replace(".h5", "").replace(".npz", "")
+                grid_dir = os.path.dirname(grid_dir)
+            grid = Grid(grid_name, grid_dir)
+        if np.asarray(grid.lam).shape != lam.shape or np.max(np.abs(np.asarray(grid.lam) / lam - 1.0)) > 1e-12:
+            grid = Grid(grid.grid_name, grid.grid_dir, new_lam=lam, log10ages=grid.log10ages, metallicity=grid.metallicity,
+                        lam=grid.lam, spectra=grid.spectra)
+        # Step 2: instrument
+        codes = list(attrs.get("Model/Instrument/Filters/Header@filter_codes", g("filters", [])))
+        filters = []
+        for code in codes:
+            t = np.asarray(data[f"Model/Instrument/Filters/{code}/Transmission"], dtype=float)
+            fl = data.get(f"Model/Instrument/Filters/{code}/Wavelengths")
+            filters.append(Filter(code, lam if fl is None else np.asarray(fl, dtype=float), t))
+        fc = FilterCollection(filters=filters)
+        if all(f.lam.shape == lam.shape for f in filters):
+            fc.lam = Quantity(lam, "Angstrom")
+        instrument = Instrument(attrs.get("Model/Instrument@label", g("instrument", "instrument")), filters=fc)
+        # Step 3: cosmology (the reference falls back to Planck18 when the stored one cannot be rebuilt)
+        cosmo = Planck18
+        if "Planck18" not in str(g("cosmology", "Planck18")):
+            logger.warning("Failed to load cosmology from the library file. Using Planck18 instead.")
+        # Step 4: SFH / metallicity-distribution classes
+        sfh_name, zd_name = g("sfh_class"), g("metallicity_distribution_class")
+        sfh_model = getattr(SFH, str(sfh_name), None)
+        if sfh_model is None:
+            raise ValueError(f"SFH model {sfh_name} not found in SFH module. Cannot create GalaxySimulator.")
+        zdist_model = getattr(ZDist, str(zd_name), None)
+        if zdist_model is None:
+            raise ValueError(f"ZDist model {zd_name} not found in ZDist module. Cannot create GalaxySimulator.")
+        emission_model_key = kwargs.pop("emission_model_key", g("emission_model_key", "total"))
+
+        def value(v, unit=""):
+            if unit not in ("", None):
+                return Quantity(float(v), str(unit))
+            if isinstance(v, str):
+                try:
+                    return float(v)
+                except ValueError:
+                    return v                     # the name of a per-galaxy emitter parameter
+            return v
+
+        def build(prefix_keys, prefix_vals, prefix_units=None):
+            ks, vs = list(e(prefix_keys, [])), list(e(prefix_vals, []))
+            us = list(e(prefix_units, [""] * len(ks))) if prefix_units else [""] * len(ks)
+            return {k: value(v, u) for k, v, u in zip(ks, vs, us)}
+
+        if override_emission_model is not None:
+            emission_model = override_emission_model
+        else:
+            em_name = e("name")
+            em_cls = getattr(P, str(em_name), None)
+            if em_cls is None or not (inspect.isclass(em_cls) and issubclass(em_cls, EmissionModel)):
+                raise ValueError(f"Emission model {em_name} not found in synference_b200.parametric. Cannot create GalaxySimulator.")
+            params = build("parameter_keys", "parameter_values", "parameter_units")
+            dust_model = None
+            if e("dust_law") is not None:
+                dcls = getattr(P, str(e("dust_law")), None)
+                if dcls is None:
+                    raise ValueError(f"Dust model {e('dust_law')} not found. Cannot create GalaxySimulator.")
+                dust_model = dcls(**build("dust_attenuation_keys", "dust_attenuation_values", "dust_attenuation_units"))
+            dust_emission = None
+            if e("dust_emission") is not None:
+                gcls = getattr(P, str(e("dust_emission")), None)
+                if gcls is None:
+                    raise ValueError(f"Dust emission model {e('dust_emission')} not found. Cannot create from_library.")
+                gp = build("dust_emission_keys", "dust_emission_values", "dust_emission_units")
+                gp.pop("cmb_factor", None)
+                gp.pop("temperature_z", None)
+                if gcls.__name__ == "Blackbody":
+                    gp.pop("emissivity", None)
+                dust_emission = gcls(**{k: float(strip_units(v)) for k, v in gp.items()})
+            if e("dust_law_birth") is not None:       # two screens
+                bcls = getattr(P, str(e("dust_law_birth")))
+                birth = bcls(**build("dust_attenuation_birth_keys", "dust_attenuation_birth_values"))
+                emission_model = em_cls(grid, dust_curve_ism=dust_model, dust_curve_birth=birth,
+                                        dust_emission_ism=dust_emission, dust_emission_birth=dust_emission, **params)
+            else:
+                sig = inspect.signature(em_cls.__init__).parameters
+                if dust_model is not None:
+                    params["dust_curve"] = dust_model
+                if dust_emission is not None:
+                    params["dust_emission_model" if "dust_emission_model" in sig else "dust_emission"] = dust_emission
+                emission_model = em_cls(grid=grid, **params)
+        # Steps 5-9: emitter parameters, order / units, fixed parameters, transforms
+        emitter_params = {"stellar": list(g("stellar_params", [])), "galaxy": {}}
+        param_order = list(attrs.get("ParameterNames", []))
+        units = list(attrs.get("ParameterUnits", []))
+        param_units = {}
+        for pname, u in zip(param_order, units):
+            if not any(tag in u for tag in ("dimensionless", "log", "mag")):
+                try:
+                    param_units[pname] = Unit(u)
+                except Exception:
+                    pass
+        fixed_params = {}
+        for name, val, unit in zip(g("fixed_param_names", []), g("fixed_param_values", []), g("fixed_param_units", [])):
+            fixed_params[name] = Quantity(val, unit) if unit not in ("", None) else val
+        param_transforms = {}
+        for key in [k for k in data if k.startswith("Model/Transforms/")]:
+            name = key[len("Model/Transforms/"):]
+            code = inspect.cleandoc("\n" + bytes(np.asarray(data[key], dtype=np.uint8)).decode("utf-8") + "\n")
+            scope = {}
+            try:
+                exec(code, {"np": np}, scope)
+                func = scope[code.split("def ")[-1].split("(")[0]]
+            except Exception as err:
+                logger.error(f"Error evaluating transform function for {name}: {err}")
+                continue
+            new_key = attrs.get(f"{key}@new_parameter_name")
+            tkey = tuple(name.split("+")) if "+" in name else name
+            param_transforms[tkey] = (new_key if isinstance(new_key, str) else tuple(new_key), func) if new_key is not None else func
+        dict_create = dict(sfh_model=sfh_model, zdist_model=zdist_model, grid=grid, emission_model=emission_model,
+                           emission_model_key=emission_model_key, instrument=instrument, cosmo=cosmo,
+                           emitter_params=emitter_params, param_order=param_order, param_units=param_units,
+                           param_transforms=param_transforms, fixed_params=fixed_params)
+        dict_create.update(kwargs)
+        return cls(**dict_create)
+
     def update_photo_filters(self, photometry_to_remove=None, photometry_to_add=None):
         """Restrict / extend the filter set (``library.py:5180-5216``); rebuilds the device tables lazily."""
         from .parametric import FilterCollection
@@ -933,11 +1191,18 @@ class GalaxySimulator:
         fc = FilterCollection(filters=filters)
         fc.lam = self.instrument.filters.lam
         self.instrument = Instrument(self.instrument.label, filters=fc)
-        if self._engine is not None:
-            self._engine.close()
-            self._engine = None
+        for name in ("_engine", "_engine_rest"):
+            if getattr(self, name, None) is not None:
+                getattr(self, name).close()
+                setattr(self, name, None)
 
-    def _get_engine(self):
+    def _get_engine(self, rest_frame=False):
+        if rest_frame:
+            if getattr(self, "_engine_rest", None) is None:
+                self._engine_rest = SynthEngine(self.grid, self.emission_model, self.emission_model_key,
+                                                self.instrument.filters, cosmo=self.cosmo, igm=False, rest_frame=True,
+                                                max_batch=self._max_batch, device=_dist.local_device())
+            return self._engine_rest
         if self._engine is None:
             self._engine = SynthEngine(self.grid, self.emission_model, self.emission_model_key,
                                        self.instrument.filters, cosmo=self.cosmo, igm=True,
@@ -1055,8 +1320,21 @@ class GalaxySimulator:
             spec = eng.spectra(p).astype(np.float64) * (10.0 ** p.log_mass / eng.base_mass)[:, None]
             outputs["fnu"] = spec
             outputs["fnu_wav"] = np.asarray(self.grid.lam)[None, :] * (1.0 + p.redshift)[:, None]
+        if "sfh" in self.output_type:
+            # mass formed per age bin / bin width (library.py:5736-5750): Msun / yr on the grid's ages
+            ages = 10.0 ** np.asarray(self.grid.log10ages, dtype=float)
+            sfh = eng.sfzh(p).sum(-1) * (10.0 ** p.log_mass)[:, None] / np.diff(ages, prepend=0.0)[None, :]
+            time_myr = ages / 1.0e6
+            outputs["sfh"] = Quantity(sfh if batched else sfh[0], "Msun/yr")
+            outputs["sfh_time"] = Quantity(time_myr, "Myr")
+            outputs["redshift"] = p.redshift if batched else float(p.redshift[0])
+            t_abs = np.asarray(self.cosmo.age(p.redshift).to("Myr").value, dtype=float)[:, None] - time_myr[None, :]
+            outputs["sfh_time_abs"] = Quantity(t_abs if batched else t_abs[0], "Myr")
+        if "photo_lnu" in self.output_type:
+            # rest-frame luminosities through the filters (library.py:5756-5761): no redshift, no IGM, no distance
+            outputs["photo_lnu"] = self._get_engine(rest_frame=True).photometry(p, scaled=True)    # erg / s / Hz
         for t in self.output_type:
-            if t not in ("photo_fnu", "fnu"):
+            if t not in ("photo_fnu", "fnu", "sfh", "photo_lnu"):
                 raise NotImplementedError(f"output_type '{t}' is not available in the batched path")
         conv = {"nJy": 1.0, "uJy": 1e-3, "mJy": 1e-6, "Jy": 1e-9}
         for k in ("photo_fnu", "fnu"):
@@ -1076,6 +1354,8 @@ class GalaxySimulator:
         if len(self.output_type) > 1:
             outputs["filters"] = self.instrument.filters
             return outputs
+        if self.output_type[0] == "sfh":
+            return outputs["sfh"]
         fluxes = outputs[self.output_type[0]]
         # scatter / normalise / append errors for all rows at once: the functions below work along the last axis (the
         # reference handles one galaxy per call; a per-row Python loop here cost 100x the GPU time for 100 k rows)

@@ -21,7 +21,8 @@ __all__ = [
 # name -> (dimension, factor to the base unit of that dimension)
 _REGISTRY = {
     "yr": ("time", 1.0), "Myr": ("time", 1.0e6), "Gyr": ("time", 1.0e9),
-    "Msun": ("mass", 1.0),
+    "Msun": ("mass", 1.0), "Msun/yr": ("mass_rate", 1.0), "K": ("temperature", 1.0),
+    "erg/s/Hz": ("luminosity_density", 1.0),
     "Jy": ("flux", 1.0), "mJy": ("flux", 1.0e-3), "uJy": ("flux", 1.0e-6), "nJy": ("flux", 1.0e-9),
     "Angstrom": ("length", 1.0), "nm": ("length", 10.0), "um": ("length", 1.0e4),
     "cm": ("length", 1.0e8), "Mpc": ("length", 3.0856775814913673e32),

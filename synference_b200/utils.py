@@ -124,8 +124,30 @@ def _have_h5py():
         return False
 
 
+def _h5_attr(h5py, v):
+    """A value h5py can store as an attribute (it has no encoding for ``None``, dicts or mixed lists), or ``None`` to skip."""
+    if v is None:
+        return None
+    if isinstance(v, dict):
+        return json.dumps(_jsonable(v))
+    if isinstance(v, (list, tuple, np.ndarray)):
+        items = list(v.tolist() if isinstance(v, np.ndarray) else v)
+        if not items:
+            return np.zeros(0, dtype=np.float64)
+        if all(isinstance(x, (bool, int, float, np.integer, np.floating, np.bool_)) for x in items):
+            return np.asarray(items)
+        return np.array(["" if x is None else (json.dumps(_jsonable(x)) if isinstance(x, (dict, list, tuple)) else str(x))
+                         for x in items], dtype=h5py.string_dtype())
+    if isinstance(v, (np.floating, np.integer, np.bool_)):
+        return v.item()
+    return v
+
+
 def write_container(path, datasets: dict, attrs: dict, compress=True):
     """Write ``{dataset path: array}`` and ``{attr: value}``; returns the path actually written.
+
+    An attribute key ``"Group/Sub@name"`` belongs to that group (or dataset), a plain key to the file root -- the ``Model``
+    block of a library is a group with attributes and sub-groups (``library.py:2017-2132``).
     ``compress``: False / 0 none, True deflate at zlib's default level, 1 ... 9 that deflate level."""
     level = 6 if compress is True else int(compress or 0)
     if _have_h5py() and not os.environ.get("SYNFERENCE_B200_FORCE_NPZ"):
@@ -135,7 +157,15 @@ def write_container(path, datasets: dict, attrs: dict, compress=True):
                 kw = dict(compression="gzip", compression_opts=level) if level and np.ndim(v) else {}
                 f.create_dataset(k, data=v, **kw)
             for k, v in attrs.items():
-                f.attrs[k] = v
+                v = _h5_attr(h5py, v)
+                if v is None:
+                    continue
+                if "@" in k:
+                    where, name = k.rsplit("@", 1)
+                    obj = f[where] if where in f else f.require_group(where)
+                    obj.attrs[name] = v
+                else:
+                    f.attrs[k] = v
         return path
     payload = {k.replace("/", "::"): np.asarray(v) for k, v in datasets.items()}
     payload["__attrs__"] = np.frombuffer(json.dumps(_jsonable(attrs)).encode(), dtype=np.uint8)
@@ -160,11 +190,27 @@ def _jsonable(x):
         return x.tolist()
     if isinstance(x, (np.floating, np.integer, np.bool_)):
         return x.item()
+    if isinstance(x, bytes):
+        return x.decode("utf-8", "replace")
     return x
 
 
+def _plain(v):
+    """h5py attribute value -> plain Python (bytes -> str, string arrays -> list of str)."""
+    if isinstance(v, bytes):
+        return v.decode("utf-8", "replace")
+    if isinstance(v, np.ndarray):
+        if v.dtype.kind in ("O", "S", "U"):
+            return [_plain(x) for x in v.tolist()]
+        return v.tolist()
+    if isinstance(v, (np.floating, np.integer, np.bool_)):
+        return v.item()
+    return v
+
+
 def read_container(path):
-    """Inverse of :func:`write_container` -> ``(datasets, attrs)``."""
+    """Inverse of :func:`write_container` -> ``(datasets, attrs)``; group / dataset attributes come back under
+    ``"Group/Sub@name"`` keys."""
     with open(path, "rb") as fh:
         magic = fh.read(4)
     if magic[:2] == b"PK":
@@ -174,8 +220,13 @@ def read_container(path):
     import h5py
     out, attrs = {}, {}
     with h5py.File(path, "r") as f:
-        f.visititems(lambda n, o: out.__setitem__(n, o[()]) if isinstance(o, h5py.Dataset) else None)
-        attrs = {k: f.attrs[k] for k in f.attrs}
+        def visit(name, obj):
+            if isinstance(obj, h5py.Dataset):
+                out[name] = obj[()]
+            for k in obj.attrs:
+                attrs[f"{name}@{k}"] = _plain(obj.attrs[k])
+        f.visititems(visit)
+        attrs.update({k: _plain(f.attrs[k]) for k in f.attrs})
     return out, attrs
 
 
@@ -198,3 +249,35 @@ def load_library_from_hdf5(hdf5_path, photometry_key="Grid/Photometry", paramete
         out["supplementary_parameter_names"] = list(attrs.get("SupplementaryParameterNames", []))
         out["supplementary_parameter_units"] = list(attrs.get("SupplementaryParameterUnits", []))
     return out
+
+
+def combine_rank_files(size, filepath, num_galaxies, starts, ends):
+    """Combine per-rank PIPELINE files into one (``utils.py:2214-2328``, same signature): ``filepath`` is any of the rank
+    files ``<stem>_<rank>.hdf5``; per-galaxy datasets (first axis = galaxies) land in ``[starts[r]:ends[r]]`` of datasets
+    sized ``num_galaxies``, the ``Instruments`` / ``EmissionModel`` / ``Model`` groups and the wavelength axis are copied
+    once from rank 0, attributes come from the first file that has them; the rank files are removed.  Returns the path."""
+    ext = filepath.split(".")[-1]
+    path_no_ext = ".".join(filepath.split(".")[:-1])
+    new_path = "_".join(path_no_ext.split("_")[:-1]) + f".{ext}"
+    temp_path = "_".join(path_no_ext.split("_")[:-1]) + "_<rank>." + ext
+    static = ("Instruments/", "EmissionModel/", "Model/", "Wavelengths")
+    out, attrs = {}, {}
+    for rank in range(size):
+        data, a = read_container(temp_path.replace("<rank>", str(rank)))
+        for k, v in a.items():
+            attrs.setdefault(k, v)
+        for k, v in data.items():
+            v = np.asarray(v)
+            if k.startswith(static) or v.ndim == 0:
+                out.setdefault(k, v)
+                continue
+            if k not in out:
+                out[k] = np.zeros((num_galaxies,) + v.shape[1:], dtype=v.dtype)
+            out[k][starts[rank]:ends[rank], ...] = v
+    attrs["rank"], attrs["world_size"] = 0, 1
+    attrs["galaxy_start"], attrs["galaxy_stop"] = 0, int(num_galaxies)
+    write_container(new_path, out, attrs, compress=False)
+    for rank in range(size):
+        os.remove(temp_path.replace("<rank>", str(rank)))
+    return new_path
+
