@@ -156,12 +156,20 @@ typedef struct sb2_params {
   const double* dust_ampl;  /* [n] per-galaxy UV-bump amplitude                       (requires dust_d0/dust_l2)  */
   const double* fesc_lya;   /* [n] per-galaxy Lyman-alpha escape fraction             (requires lya_line)         */
   const double* tau_v_birth;/* [n] birth-cloud optical depth of the young population (requires kappa_birth; tau_v = ISM) */
+  /* HOST entry points only: 1 = every array above holds float32 values (the pointers are then const float* cast to
+   * const double*), as draw_from_hypercube returns its draws (src/synference/library.py:1098).  They cross PCIe as
+   * float32 -- half the bytes -- and are widened to float64 on the device; with max_age_from_z the SFH rows need no
+   * host-side float64 arithmetic at all.  Must be 0 for the device entry points.                                   */
+  int32_t host_f32;
 } sb2_params;
 
 typedef struct sb2_model sb2_model;
 
 const char* sb2_last_error(void);
 int sb2_device_count(void);
+/* Number of kernels of THIS library launched by the calling process so far (the sort's CUB kernels are not counted).
+ * Measurement hook for bench.py's `gpu_launches`; no reference counterpart.                                       */
+long long sb2_kernel_launches(void);
 
 /* Build / destroy the device-resident model.  `device` is the CUDA ordinal. */
 int sb2_model_create(const sb2_model_desc* desc, int device, sb2_model** out);

@@ -12,15 +12,15 @@ from .parametric import (SFH, Blackbody, Calzetti2000, Greybody, EmergentEmissio
                          Grid, IncidentEmission, Instrument, IntrinsicEmission, PacmanEmission, BimodalPacmanEmission, PowerLaw,
                          SFHArray, TotalEmission, ZDist, ZDistArray)
 from .igm import Inoue14  # noqa: F401
-from .sampling import (continuity_sfh_array, draw_from_hypercube, generate_metallicity_distribution,  # noqa: F401
-                       generate_sfh_basis, load_hypercube_from_npy)
+from .sampling import (continuity_sfh_array, draw_from_hypercube, generate_emission_models,  # noqa: F401
+                       generate_metallicity_distribution, generate_sfh_basis, generate_sfh_grid, load_hypercube_from_npy)
 from .utils import (asinh_err_to_f_jy, asinh_to_f_jy, asinh_to_snr, calculate_min_max_wav_grid,  # noqa: F401
                     check_log_scaling, check_scaling, f_jy_err_to_asinh, f_jy_to_asinh, generate_constant_R,
                     load_library_from_hdf5, combine_rank_files)
 from .noise_models import (AsinhEmpiricalUncertaintyModel, DepthUncertaintyModel,  # noqa: F401
                            EmpiricalUncertaintyModel, GeneralEmpiricalUncertaintyModel,
-                           SpectralUncertaintyModel, UncertaintyModel, load_unc_model_from_hdf5,
-                           save_unc_model_to_hdf5)
+                           SpectralUncertaintyModel, UncertaintyModel, create_uncertainty_models_from_EPOCHS_cat,
+                           load_unc_model_from_hdf5, save_unc_model_to_hdf5)
 from .engine import GalaxyParams, SynthEngine, depth_noise_features  # noqa: F401
 from .library import CombinedBasis, GalaxyBasis, GalaxySimulator, create_galaxy  # noqa: F401
 from .features import (ResampledFeatures, apply_empirical_noise_models,  # noqa: F401

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     "sb2_synth_photometry", "sb2_synth_photometry_host", "sb2_depth_noise_features", "sb2_last_stage_ms", "sb2_wait_debug",
     "sb2_synth_photometry_host_submit", "sb2_synth_photometry_host_wait",
     "sb2_resampler_create", "sb2_resampler_destroy", "sb2_resample_spectra", "sb2_resample_spectra_host", "sb2_resample_last_ms",
-    "sb2_empirical_noise", "sb2_depth_noise_features_sets",
+    "sb2_empirical_noise", "sb2_depth_noise_features_sets", "sb2_kernel_launches",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -60,6 +60,7 @@ class Params(C.Structure):
         ("coef_att", C.c_void_p), ("coef_unatt", C.c_void_p),
         ("dust_slope", C.c_void_p), ("dust_ampl", C.c_void_p), ("fesc_lya", C.c_void_p),
         ("tau_v_birth", C.c_void_p),
+        ("host_f32", C.c_int32),
     ]
 
 
@@ -106,6 +107,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.sb2_last_error.restype = C.c_char_p
     lib.sb2_device_count.restype = C.c_int
+    lib.sb2_kernel_launches.restype = C.c_longlong
     lib.sb2_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_void_p)]
     lib.sb2_model_destroy.argtypes = [C.c_void_p]
     lib.sb2_wait_debug.argtypes = [C.c_void_p]

@@ -1,6 +1,7 @@
 // C ABI of the B200-native mock-library hot path (see include/synference_b200.h).
 // Owns the device-resident model, the per-batch workspace, the TMA descriptors and the launches.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,8 +46,10 @@ bool debug_sync() {
   }
   return v == 1;
 }
+std::atomic<long long> g_launches{0};   // kernels of this library launched by this process (sb2_kernel_launches)
 #define STAGE_CHECK(name, st)                                                                  \
   do {                                                                                         \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
     cudaError_t e_ = cudaGetLastError();                                                       \
     if (e_ == cudaSuccess && debug_sync()) e_ = cudaStreamSynchronize(st);                     \
     if (e_ != cudaSuccess) return fail(SB2_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(e_)); \
@@ -146,6 +149,11 @@ __global__ void group_layout_kernel(const int* __restrict__ counts, int n_groups
   }
 }
 
+// float32 parameters staged by the host entry (sb2_params.host_f32) -> the float64 arrays the kernels read
+__global__ void widen_kernel(const float* __restrict__ src, double* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+}
+
 __global__ void group_scatter_kernel(const unsigned* __restrict__ keys_sorted, const int* __restrict__ perm_sorted,
                                      const int* __restrict__ cum, const int* __restrict__ pad_start, int* perm_pad,
                                      long long n) {
@@ -220,6 +228,7 @@ struct sb2_model {
   // host-entry staging (device side)
   // two staging slots, so the copies of one batch overlap the kernels of the next (sb2_synth_photometry_host_submit)
   double* stage_params[2] = {nullptr, nullptr};  // redshift | log_mass | tau_v | zd_value | zd_sigma | ca | cb | sfh rows
+  float* stage_params32[2] = {nullptr, nullptr}; // the same arrays as float32 (host_f32 transport), widened on the device
   float* stage_flux[2] = {nullptr, nullptr};
   double* stage_flux64[2] = {nullptr, nullptr};
   cudaEvent_t ev_slot[2] = {nullptr, nullptr};   // slot's results are on the host
@@ -253,6 +262,8 @@ const char* sb2_wait_debug(sb2_model* m) {
   return out.c_str();
 }
 
+long long sb2_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
 int sb2_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -266,7 +277,8 @@ int sb2_model_destroy(sb2_model* m) {
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage, m->fm_log, m->fm_exp, m->fm_tail,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
                   m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params[0],
-                  m->stage_params[1], m->stage_flux[0], m->stage_flux[1], m->stage_flux64[0], m->stage_flux64[1], m->sf, m->s0, m->s1};
+                  m->stage_params[1], m->stage_flux[0], m->stage_flux[1], m->stage_flux64[0], m->stage_flux64[1], m->sf, m->s0, m->s1,
+                  m->stage_params32[0], m->stage_params32[1]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : m->ev)
@@ -433,6 +445,7 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(cub_tmp, m->cub_bytes + 16);
   for (int sl = 0; sl < 2; ++sl) {
     AL(stage_params[sl], (size_t)m->cap * (11 + SB2_SFH_ROW) * 8);
+    AL(stage_params32[sl], (size_t)m->cap * (11 + SB2_SFH_ROW) * 4);
     AL(stage_flux[sl], (size_t)m->cap * d->n_filt * 4);
     AL(stage_flux64[sl], (size_t)m->cap * d->n_filt * 8);
   }
@@ -675,6 +688,12 @@ int check_params(const sb2_model* m, const sb2_params* p) {
   return SB2_OK;
 }
 
+int check_device_params(const sb2_model* m, const sb2_params* p) {
+  int rc = check_params(m, p);
+  if (rc == SB2_OK && p->host_f32) return fail(SB2_ERR_INVALID, "host_f32 is a host-entry transport option; device arrays are float64");
+  return rc;
+}
+
 // A unit of work of the contraction kernel: one 128-galaxy tile, or a PAIR of tiles for the CTA-pair kernel
 // (bracket-grouped batches).
 int rows_per_unit_old(const sb2_model* m, bool delta) {
@@ -790,7 +809,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
 extern "C" {
 
 int sb2_build_weights(sb2_model* m, const sb2_params* p, double* w_out, void* stream) {
-  int rc = check_params(m, p);
+  int rc = check_device_params(m, p);
   if (rc != SB2_OK) return rc;
   if (!w_out) return fail(SB2_ERR_INVALID, "w_out is null");
   CU_TRY(cudaSetDevice(m->device));
@@ -799,7 +818,7 @@ int sb2_build_weights(sb2_model* m, const sb2_params* p, double* w_out, void* st
 
 int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, double* flux_scaled,
                          float* spec_out, void* stream) {
-  int rc = check_params(m, p);
+  int rc = check_device_params(m, p);
   if (rc != SB2_OK) return rc;
   if (!flux_base && !flux_scaled && !spec_out) return fail(SB2_ERR_INVALID, "no output requested");
   CU_TRY(cudaSetDevice(m->device));
@@ -936,13 +955,29 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
     for (int i = 0; i < kNA; ++i) {
       if (!src[i]) continue;
       const size_t w = (i == kNA - 1) ? (size_t)p->sfh_stride : 1;
-      CU_TRY(cudaMemcpyAsync(dev[i] + a * w, src[i] + a * w, (b - a) * w * sizeof(double), cudaMemcpyHostToDevice, m->st_h2d));
+      if (p->host_f32) {   // half the PCIe bytes; widened on the compute stream below
+        float* d32 = m->stage_params32[slot] + (dev[i] - m->stage_params[slot]);
+        CU_TRY(cudaMemcpyAsync(d32 + a * w, reinterpret_cast<const float*>(src[i]) + a * w, (b - a) * w * sizeof(float), cudaMemcpyHostToDevice, m->st_h2d));
+      } else {
+        CU_TRY(cudaMemcpyAsync(dev[i] + a * w, src[i] + a * w, (b - a) * w * sizeof(double), cudaMemcpyHostToDevice, m->st_h2d));
+      }
     }
     CU_TRY(cudaEventRecord(m->ev_in[sl], m->st_h2d));
     if (trace) cudaEventRecord(tr[1 + sl * 4 + 0], m->st_h2d);
     CU_TRY(cudaStreamWaitEvent(m->st_comp, m->ev_in[sl], 0));
     if (trace) cudaEventRecord(tr[1 + sl * 4 + 1], m->st_comp);
+    if (p->host_f32) {
+      for (int i = 0; i < kNA; ++i) {
+        if (!src[i]) continue;
+        const size_t w = (i == kNA - 1) ? (size_t)p->sfh_stride : 1;
+        const long long cnt = (long long)((b - a) * w);
+        const float* d32 = m->stage_params32[slot] + (dev[i] - m->stage_params[slot]) + a * w;
+        widen_kernel<<<(unsigned)std::min<long long>((cnt + 255) / 256, 2048), 256, 0, m->st_comp>>>(d32, dev[i] + a * w, cnt);
+      }
+      STAGE_CHECK("widen_kernel", m->st_comp);
+    }
     sb2_params dp = *p;
+    dp.host_f32 = 0;
     dp.n = (int64_t)(b - a);
     dp.redshift = dev[0] + a; dp.log_mass = dev[1] ? dev[1] + a : nullptr; dp.tau_v = dev[2] ? dev[2] + a : nullptr;
     dp.zd_value = dev[3] + a; dp.zd_sigma = dev[4] ? dev[4] + a : nullptr;

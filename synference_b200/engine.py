@@ -375,22 +375,24 @@ class SynthEngine:
         return get_ptr(sl), get_ptr(am)
 
     @staticmethod
-    def _host_ptr_factory(keep):
+    def _host_ptr_factory(keep, dtype=np.float64):
         def get(a):
             if a is None:
                 return None
-            a = np.ascontiguousarray(a, dtype=np.float64)
+            a = np.ascontiguousarray(a, dtype=dtype)
             keep.append(a)
             return a.ctypes.data
         return get
 
     # ---- host-buffer entry (what a drop-in caller uses) --------------------------------------
-    def photometry(self, params: GalaxyParams, scaled=True, out=None):
+    def photometry(self, params: GalaxyParams, scaled=True, out=None, transport="f64"):
         """Fluxes [nJy] as a host array ``(N, n_filt)``: float64 scaled by stellar mass
         (``float32(base) * 10**log_mass / base_mass``, ``library.py:4588-4609``) or float32 at base mass.
 
         Populations larger than ``max_batch`` run batch by batch through the two staging slots of the C ABI, so
-        the copies of one batch overlap the kernels of the next."""
+        the copies of one batch overlap the kernels of the next.  ``transport="f32"`` sends the parameters over PCIe as
+        float32 (what ``draw_from_hypercube`` produces, ``library.py:1098``) and widens them on the device: half the
+        host-to-device bytes, exact for float32 draws (use ``max_age_from_z`` so the SFH rows hold the raw draws)."""
         n = len(params)
         res = out if out is not None else np.empty((n, self.n_filt), dtype=np.float64 if scaled else np.float32)
         pending = []
@@ -398,18 +400,21 @@ class SynthEngine:
             b = min(n, a + self.max_batch)
             if len(pending) == 2:
                 self.wait(pending.pop(0))
-            pending.append(self.submit(params.slice(slice(a, b)), res[a:b], scaled=scaled, slot=i & 1))
+            pending.append(self.submit(params.slice(slice(a, b)), res[a:b], scaled=scaled, slot=i & 1, transport=transport))
         for t in pending:
             self.wait(t)
         return res
 
-    def submit(self, params: GalaxyParams, out, scaled=True, slot=0):
+    def submit(self, params: GalaxyParams, out, scaled=True, slot=0, transport="f64"):
         """Enqueue one batch (``len(params) <= max_batch``) and return a ticket for :meth:`wait`; ``out`` is the
         host array the results land in (pinned memory gives real copy/compute overlap)."""
         assert out.flags.c_contiguous and out.shape == (len(params), self.n_filt)
         assert out.dtype == (np.float64 if scaled else np.float32)
         keep = [out]
-        s = self._fill(params, self._host_ptr_factory(keep))
+        if transport not in ("f64", "f32"):
+            raise ValueError("transport must be 'f64' or 'f32'")
+        s = self._fill(params, self._host_ptr_factory(keep, np.float32 if transport == "f32" else np.float64))
+        s.host_f32 = 1 if transport == "f32" else 0
         rc = self.lib.sb2_synth_photometry_host_submit(self._h, C.byref(s), None if scaled else out.ctypes.data,
                                                        out.ctypes.data if scaled else None, int(slot))
         _capi.check(rc, "sb2_synth_photometry_host_submit")

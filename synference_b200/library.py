@@ -180,7 +180,7 @@ class GalaxyBasis:
             if key in self.params_to_ignore:
                 continue
             v = np.asarray(strip_units(value), dtype=float)
-            if np.unique(v).size == 1:
+            if v.size and v.min() == v.max():        # one distinct value (np.unique sorts: 10x the time for 1M rows)
                 self.fixed_param_names.append(key)
                 self.fixed_param_values.append(float(v.flat[0]))
                 self.fixed_param_units.append(str(value.units) if has_units(value) else "")
@@ -405,13 +405,24 @@ class GalaxyBasis:
                          "rank": rank, "world_size": size, "galaxy_start": sl.start, "galaxy_stop": sl.stop,
                          "supp_names": list(supp_units), "supp_units": [supp_units[k] for k in supp_units]}
                 self._pipeline_cache["parts"].append((os.path.basename(final), datasets, attrs))
+                self._pipeline_cache.setdefault("phot", {}).setdefault(keys[0], []).append(results["photometry"][keys[0]][-1])
                 pending.append(writer.submit(write_container, final, datasets, attrs, False))
                 logger.info(f"Writing pipeline to disk at {final}.")
+        # the files keep being written while the caller goes on (create_mock_library compiles the library from the in-memory
+        # copy meanwhile); wait_for_writes() joins them and re-raises a failed write
+        self._pending_writes = (writer, pending)
+        if not getattr(self, "_defer_write_join", False):
+            self.wait_for_writes()
+        return {k: {kk: (np.concatenate(vv) if vv else None) for kk, vv in v.items()} for k, v in results.items()}
+
+    def wait_for_writes(self):
+        """Block until the pipeline files of the last process_galaxies call are on disk."""
+        writer, pending = getattr(self, "_pending_writes", (None, []))
+        self._pending_writes = (None, [])
         for fut in pending:
-            fut.result()          # re-raises a failed write
+            fut.result()
         if writer is not None:
             writer.shutdown()
-        return {k: {kk: (np.concatenate(vv) if vv else None) for kk, vv in v.items()} for k, v in results.items()}
 
     def process_base(self, out_name, log_stellar_masses=9, emission_model_key="total", out_dir=library_folder,
                      n_proc=6, overwrite=False, verbose=False, batch_size=40_000, multi_node=False, **kw):
@@ -451,9 +462,15 @@ class GalaxyBasis:
             raise ValueError(f"Unknown catalog type: {cat_type}. Use 'photometry' or 'spectra'.")
         if cat_type == "spectra" and not spectra_to_save:
             spectra_to_save = [emission_model_key]
-        combined.process_bases(n_proc=n_proc, overwrite=overwrite, verbose=verbose, batch_size=batch_size,
-                               multi_node=multi_node, galaxies_mask=galaxy_mask, spectra_to_save=spectra_to_save,
-                               em_lines_to_save=em_lines_to_save, **extra_analysis_functions)
+        self._defer_write_join = bool(compile_grid)      # the library is compiled from memory while the files are written
+        try:
+            combined.process_bases(n_proc=n_proc, overwrite=overwrite, verbose=verbose, batch_size=batch_size,
+                                   multi_node=multi_node, galaxies_mask=galaxy_mask, spectra_to_save=spectra_to_save,
+                                   em_lines_to_save=em_lines_to_save, **extra_analysis_functions)
+        finally:
+            self._defer_write_join = False
+        if not compile_grid:
+            self.wait_for_writes()
         if compile_grid:
             logger.info("Compiling the library after processing bases.")
             # the Model/ block (library.py:2017-2132) travels with the library's single write
@@ -464,6 +481,7 @@ class GalaxyBasis:
                 combined.create_library(overwrite=overwrite)
             else:
                 combined.create_spectral_grid(overwrite=overwrite)
+            self.wait_for_writes()
             logger.info("Processed the bases and saved the output.")
             return combined
 
@@ -645,6 +663,10 @@ class CombinedBasis:
         if multi_node:
             _dist.barrier()
 
+    def _join_writes(self):
+        for base in self.bases:
+            base.wait_for_writes()
+
     def load_bases(self, load_spectra=False) -> dict:
         """Read the pipeline files back and concatenate batches / rank shards (``library.py:3385-3642``)."""
         import re
@@ -657,10 +679,12 @@ class CombinedBasis:
             pat = re.compile(r"^" + re.escape(base.model_name) + r"(_\d+)?(_rank(\d+))?\.hdf5$")
             cache = getattr(base, "_pipeline_cache", None)
             parts = []
-            if cache and cache["complete"] and cache["parts"] and cache["out_dir"] == os.path.abspath(self.out_dir):
+            from_cache = bool(cache and cache["complete"] and cache["parts"] and cache["out_dir"] == os.path.abspath(self.out_dir))
+            if from_cache:
                 for fname, data, attrs in cache["parts"]:      # just written by process_galaxies: no need to read them back
                     parts.append((int(attrs.get("galaxy_start", 0)), int(attrs.get("rank", 0)), data, attrs))
             else:
+                base.wait_for_writes()
                 files = []
                 for f in sorted(os.listdir(self.out_dir)):
                     mt = pat.match(f)
@@ -691,6 +715,9 @@ class CombinedBasis:
                     for c in codes}
             entry = {"properties": props, "observed_photometry": phot, "supp_properties": supp_props,
                      "wavelengths": parts[0][2]["Wavelengths"], "filter_codes": codes, "stem": stem}
+            if cache and cache["complete"] and cache.get("phot", {}).get(key) and from_cache:
+                # the (N, n_filt) float32 matrix the kernels produced, in batch order (= sorted by galaxy_start)
+                entry["photometry_matrix"] = np.concatenate(cache["phot"][key]) if len(cache["phot"][key]) > 1 else cache["phot"][key][0]
             skey = f"Galaxies/Stars/Spectra/SpectralFluxDensities/{key}"
             if load_spectra:
                 if skey not in parts[0][2]:
@@ -846,8 +873,13 @@ class CombinedBasis:
             if spectral_mode:
                 contrib = o["observed_spectra"].astype(np.float32) * scale[:, None]
             else:
-                phot = np.stack([o["observed_photometry"][c] for c in filter_codes], 1).astype(np.float32)
-                contrib = phot * scale[:, None]
+                if "photometry_matrix" in o and filter_codes == list(o["filter_codes"]):
+                    phot = o["photometry_matrix"]                     # float32 (N, n_filt) straight from the kernels
+                else:
+                    phot = np.stack([o["observed_photometry"][c] for c in filter_codes], 1).astype(np.float32)
+                # float32(base) x float64 mass ratio (library.py:4588-4609), formed directly in the library's
+                # (n_filters, n_galaxies) layout
+                contrib = phot.T.astype(np.float64) * scale[None, :]
             total = contrib if total is None else total + contrib
             for name in base.varying_param_names:
                 if name == "redshift":
@@ -858,20 +890,23 @@ class CombinedBasis:
                 short = name.lower()
                 src = base.all_parameters.get(name)
                 param_units.append(UNIT_DICT.get(short, str(src.units) if has_units(src) else "dimensionless"))
-        combined_outputs = np.ascontiguousarray(total.T)          # (n_filters | n_lam, n_gal)
+        combined_outputs = np.ascontiguousarray(total.T if spectral_mode else total)          # (n_filters | n_lam, n_gal)
         combined_params = np.stack(rows, 0)                        # (n_params, n_gal)
         # supplementary parameters: rescaled from the base mass like the photometry (library.py:4631-4656)
         supp_names, supp_units_l, supp_rows = [], [], []
-        first = outputs[self.bases[0].model_name]
-        if first["supp_properties"]:
-            if multi:
-                raise NotImplementedError("supplementary parameters of multi-base libraries are not combined yet")
-            scale = 10.0 ** log_mass / first["properties"]["mass"]
-            for name, (vals, units) in first["supp_properties"].items():
+        for i, base in enumerate(self.bases):
+            o = outputs[base.model_name]
+            if not o["supp_properties"]:
+                continue
+            # every base's by-products are rescaled by ITS share of the total mass (weight x mass / base mass), and in a
+            # multi-base library they are named <model_name>/<name>, like the parameters
+            scale = (weights[:, i] if multi else 1.0) * 10.0 ** log_mass / o["properties"]["mass"]
+            for name, (vals, units) in o["supp_properties"].items():
                 how = _supp.scales_with_mass(units)
                 vals = np.asarray(vals, dtype=float)
-                supp_rows.append(vals * scale if how == "linear" else vals + np.log10(scale) if how == "log" else vals)
-                supp_names.append(name)
+                with np.errstate(divide="ignore"):
+                    supp_rows.append(vals * scale if how == "linear" else vals + np.log10(scale) if how == "log" else vals)
+                supp_names.append(f"{base.model_name}/{name}" if multi else name)
                 supp_units_l.append(units)
         supp = np.stack(supp_rows, 0) if supp_rows else np.zeros((0, combined_params.shape[1]))
         out = {"parameters": combined_params, "parameter_names": param_columns,

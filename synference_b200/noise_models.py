@@ -680,3 +680,66 @@ def load_unc_model_from_hdf5(filepath: str, group_name: str) -> UncertaintyModel
     if name not in _MODEL_REGISTRY:
         raise TypeError(f"Unknown model class '{name}' in HDF5 file.")
     return _MODEL_REGISTRY[name]._from_hdf5_group(g)
+
+
+def create_uncertainty_models_from_EPOCHS_cat(file, bands, new_band_names=None, plot=False, old=False, hdu=0, save=False,
+                                              save_path=None, model_class="general", **kwargs):
+    """One uncertainty model per band from an EPOCHS-style catalogue (``noise_models.py:1159-1330``).
+
+    ``file``: a table with the columns ``MAG_APER_<band>_aper_corr``, ``FLUX_APER_<band>_aper_corr_Jy`` and
+    ``loc_depth_<band>`` -- an astropy ``Table``, a pandas ``DataFrame``, a numpy structured array or a dict of arrays; a path
+    is read with ``astropy.table.Table.read`` (needs astropy).  ``model_class``: ``"general"`` (AB magnitudes, SNR < 1 treated
+    as upper limits), ``"depth"`` (median local depth) or ``"asinh"``.  Flux errors are ``ab_to_jy(loc_depth) / 5``."""
+    if plot:
+        raise NotImplementedError("plotting helpers are outside the hot path; build the models with plot=False")
+    if isinstance(bands, str):
+        bands = [bands]
+    if isinstance(file, (str, bytes)) or hasattr(file, "__fspath__"):
+        try:
+            from astropy.table import Table
+        except ImportError as err:
+            raise ImportError("reading a catalogue file needs astropy; pass the table's columns as a dict / DataFrame / "
+                              "structured array instead") from err
+        file = Table.read(file, hdu=hdu)
+    names = list(getattr(file, "colnames", None) or getattr(getattr(file, "dtype", None), "names", None) or
+                 getattr(file, "columns", None) or file.keys())
+    col = lambda k: np.asarray(getattr(file[k], "filled", lambda v: file[k])(np.nan), dtype=float)   # noqa: E731
+    if new_band_names is not None:
+        assert len(new_band_names) == len(bands), \
+            f"new_band_names length {len(new_band_names)} does not match bands length {len(bands)}. Cannot create uncertainty models."
+    else:
+        new_band_names = bands
+    models = {}
+    for band, new_name in zip(bands, new_band_names):
+        if f"loc_depth_{band}" not in names:
+            raise ValueError(f"Column loc_depth_{band} not found in the table.")
+        mag = col(f"MAG_APER_{band}_aper_corr")
+        flux = col(f"FLUX_APER_{band}_aper_corr_Jy")
+        loc_depth = col(f"loc_depth_{band}")
+        flux_err = UncertaintyModel.ab_to_jy(loc_depth) / 5
+        if old:
+            mag, flux = mag[:, 0], flux[:, 0]
+            flux_err = flux          # (sic) the reference's old-format branch, noise_models.py:1236
+        with np.errstate(all="ignore"):
+            mag_err = (2.5 * flux_err) / (flux * np.log(10))
+        mask = (mag != -99) & np.isfinite(mag) & (mag_err >= 0)
+        base = {"return_noise": True, "error_type": "observed", "num_bins": 20}
+        if model_class == "general":
+            kw = dict(log_bins=False, upper_limits=True, treat_as_upper_limits_below=1, upper_limit_flux_behaviour=40,
+                      upper_limit_flux_err_behaviour="sig_1")
+            kw.update(base)
+            kw.update(kwargs)
+            model = GeneralEmpiricalUncertaintyModel(mag[mask], mag_err[mask], **kw)
+        elif model_class == "depth":
+            base.update(kwargs)
+            model = DepthUncertaintyModel(float(np.nanmedian(loc_depth)), depth_sigma_level=5.0, **base)
+        elif model_class == "asinh":
+            base.update(kwargs)
+            base["interpolation_flux_unit"] = "asinh"
+            base["log_bins"] = True
+            model = AsinhEmpiricalUncertaintyModel(flux, flux_err, **base)
+        else:
+            raise ValueError(f"Unknown model_class: {model_class}. Supported: 'general', 'depth', 'asinh'.")
+        models[new_name] = model
+    return models
+

@@ -198,3 +198,83 @@ def generate_metallicity_distribution(zmet_dist=ZDist.DeltaConstant, zmet=None, 
     if zmet_dist is ZDist.Normal:
         return ZDistArray.normal(kwargs["mean"], kwargs["sigma"], log10=kwargs.get("log10", True))
     raise ValueError(f"Unsupported metallicity distribution {zmet_dist}")
+
+
+def generate_sfh_grid(sfh_type, sfh_priors, redshift, max_redshift: float = 15, cosmo=Planck18):
+    """Every combination of drawn redshifts and SFH-parameter samples (``library.py:742-873``).
+
+    ``sfh_priors[name]`` = ``{"prior": scipy.stats distribution, "min", "max", "size", ["units"], ["name"],
+    ["depends_on": "max_redshift"]}``; a parameter that depends on redshift is drawn per redshift with its upper bound capped
+    at the age available there (``size // n_redshifts`` samples each).  Returns ``(SFHArray, param_combinations)`` with
+    ``param_combinations[:, 0]`` the redshift -- the reference returns a list of SFH objects; the array materialises the
+    same objects on indexing.  ``max_age = age(z) - age(max_redshift)`` as in ``generate_sfh_basis``."""
+    if isinstance(redshift, dict):
+        redshifts = redshift["prior"].rvs(size=int(redshift["size"]), loc=redshift["min"], scale=redshift["max"] - redshift["min"])
+    else:
+        redshifts = np.array([redshift], dtype=float)
+    redshifts = np.asarray(redshifts, dtype=np.float64)
+    max_ages = np.asarray((cosmo.age(redshifts) - cosmo.age(max_redshift)).to("Myr").value, dtype=np.float64)
+    param_arrays, param_names, units = [redshifts], ["redshift"], {}
+    for key, pd in sfh_priors.items():
+        size, lo, hi = int(pd["size"]), pd["min"], pd["max"]
+        unit = pd.get("units")
+        if pd.get("depends_on") == "max_redshift":
+            vals = []
+            for mx in max_ages:
+                top = min(hi, mx)
+                vals.append(pd["prior"].rvs(size=size // len(redshifts), loc=lo, scale=top - lo))
+            values = np.concatenate(vals)
+        else:
+            values = pd["prior"].rvs(size=size, loc=lo, scale=hi - lo)
+        param_arrays.append(np.asarray(values, dtype=np.float64))
+        param_names.append(pd.get("name", key))
+        units[pd.get("name", key)] = unit
+    mesh = np.meshgrid(*param_arrays, indexing="ij")
+    combos = np.stack([m.reshape(-1) for m in mesh], axis=1)
+    z = combos[:, 0]
+    mx_myr = np.asarray((cosmo.age(z) - cosmo.age(max_redshift)).to("Myr").value, dtype=np.float64)
+    rows = np.zeros((len(z), SFH_MAX_PARAMS))
+    rows[:, 1] = mx_myr * 1.0e6
+    cols = {name: combos[:, j + 1] for j, name in enumerate(param_names[1:])}
+    for name in cols:
+        if name not in sfh_type.param_names and name != "min_age":
+            raise TypeError(f"{sfh_type.__name__}() got an unexpected parameter '{name}'")
+
+    def in_yr(name):
+        u = units.get(name)
+        return cols[name] * (Unit(str(u)).factor if u is not None else 1.0)
+
+    if "min_age" in cols:
+        rows[:, 0] = in_yr("min_age")
+    for j, name in enumerate(sfh_type.param_names):
+        if name not in cols:
+            raise TypeError(f"{sfh_type.__name__}() missing required parameter '{name}'")
+        rows[:, 2 + j] = in_yr(name) if name in sfh_type.time_params else cols[name]
+    return SFHArray(sfh_type, rows, z), combos
+
+
+def generate_emission_models(emission_model, varying_params: dict, grid, fixed_params: dict = None):
+    """One emission model per combination of drawn parameter values (``library.py:931-1018``): returns
+    ``(models, {name: values per model})``.  ``varying_params[name]`` = ``{"prior", "min", "max", "size", ["units"]}``."""
+    arrays = []
+    for key, pd in varying_params.items():
+        args = {k: v for k, v in pd.items() if k not in ("units", "name", "prior", "min", "max")}
+        if "min" in pd:
+            args["loc"] = pd["min"]
+        if "max" in pd:
+            args["scale"] = pd["max"] - pd["min"]
+        arrays.append(np.asarray(pd["prior"].rvs(**args), dtype=np.float64))
+    mesh = np.meshgrid(*arrays, indexing="ij") if arrays else []
+    combos = np.stack([m.reshape(-1) for m in mesh], axis=1) if arrays else np.zeros((1, 0))
+    fixed_params = fixed_params or {}
+    models, out_params = [], {k: [] for k in varying_params}
+    for row in combos:
+        kw = {}
+        for j, key in enumerate(varying_params):
+            unit = varying_params[key].get("units")
+            kw[key] = row[j] * unit if unit is not None else float(row[j])
+            out_params[key].append(kw[key])
+        kw.update(fixed_params)
+        models.append(emission_model(grid=grid, **kw))
+    return models, out_params
+

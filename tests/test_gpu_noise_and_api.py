@@ -568,3 +568,24 @@ def test_simulator_sfh_and_rest_frame_photometry_outputs(tmp_path):
         lnu = (np.tensordot(w, ga, axes=([0, 1], [0, 1])) * np.exp(-g["tau_v"] * kap) + np.tensordot(w, gu, axes=([0, 1], [0, 1]))) * 10.0 ** vec[i, 1]
         want = np.array([O.apply_filter(lnu, lam, f.lam, f.t) for f in inst.filters])
         np.testing.assert_allclose(got[i], want, rtol=1e-5)
+
+
+def test_multi_base_supplementary_parameters(tmp_path):
+    """library.py:4631-4656 with two bases: each base's by-products are rescaled by its share of the galaxy's mass
+    (weight x 10^logM / base mass) and named <model_name>/<name>."""
+    n = 30
+    b1, d, grid, inst, em = _small_basis(n, tmp_path)
+    b2, _, _, _, _ = _small_basis(n, tmp_path)
+    b2.model_name = "burst_basis"
+    w = np.stack([np.linspace(0.3, 0.9, n), 1 - np.linspace(0.3, 0.9, n)], 1)
+    cb = S.CombinedBasis([b1, b2], np.full(n, 10.0), np.asarray(d["redshift"], dtype=float), ["emergent", "emergent"], w,
+                         out_name="combo_supp", out_dir=str(tmp_path))
+    cb.process_bases(overwrite=True, sfr_10=(S.calculate_sfr, 10 * S.Myr), mass_weighted_age=S.calculate_mass_weighted_age)
+    out = cb.create_library(overwrite=True)
+    names = out["supplementary_parameter_names"]
+    assert names == ["test_lhc_basis/sfr_10", "test_lhc_basis/mass_weighted_age", "burst_basis/sfr_10", "burst_basis/mass_weighted_age"]
+    supp = out["supplementary_parameters"]
+    np.testing.assert_allclose(supp[0] / w[:, 0], supp[2] / w[:, 1], rtol=1e-12)      # same galaxies, linear in the mass share
+    np.testing.assert_allclose(supp[1], supp[3], rtol=1e-12)                          # an age does not scale
+    lib = S.load_library_from_hdf5(cb.library_path)
+    assert list(lib["supplementary_parameter_names"]) == names

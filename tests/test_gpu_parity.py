@@ -200,6 +200,35 @@ def test_device_max_age_from_redshift_matches_host_path(engines):
     np.testing.assert_allclose(dev, host, rtol=2e-6)
 
 
+def test_float32_parameter_transport_is_exact_for_float32_draws(engines):
+    """parameters cross PCIe as float32 (sb2_params.host_f32) and are widened on the device.  The draws of
+    draw_from_hypercube ARE float32 (library.py:1098): sending the raw draws with max_age_from_z gives bit-identical fluxes
+    to the float64 transport of the same values; the device entry refuses the flag."""
+    from synference_b200.cosmology import Planck18
+    w, eng = engines("cfg2", 3000)
+    s = w.samples
+    n = len(w.params)
+    rows = np.zeros((n, 4), dtype=np.float32)
+    rows[:, 2], rows[:, 3] = s["tau"], s["peak_age_norm"]
+    q = GalaxyParams(np.asarray(s["redshift"], dtype=np.float32), w.params.sfh_type, rows, w.params.zd_type,
+                     np.asarray(s["log_zmet"], dtype=np.float32), None, np.asarray(s["log_stellar_mass"], dtype=np.float32),
+                     np.asarray(s["tau_v"], dtype=np.float32), max_age_from_z=True, norm_mask=0b10,
+                     age_zmax_gyr=float(Planck18.age(20.0).value))
+    assert q.redshift.dtype == np.float32 and q.sfh_rows.dtype == np.float32
+    f64 = eng.photometry(q, scaled=True, transport="f64")
+    f32 = eng.photometry(q, scaled=True, transport="f32")
+    assert np.array_equal(f32, f64)
+    assert_flux_close(eng.photometry(q, scaled=False, transport="f32"), oracle_flux(w, params=w.params.slice(slice(0, n)), c=True), rtol=1e-5)
+    import ctypes as C
+    dpar = eng.to_device(q)
+    st = eng._fill(dpar.host, lambda a: None)
+    eng._set_device_ptrs(st, dpar.tensors)
+    st.host_f32 = 1
+    import torch
+    out = torch.empty((n, eng.n_filt), dtype=torch.float32, device="cuda")
+    assert eng.lib.sb2_synth_photometry(eng._h, C.byref(st), out.data_ptr(), None, None, None) != 0
+
+
 def test_full_size_properties(engines):
     """Size-independent properties at BASELINE size (1M galaxies): permutation invariance, idempotence,
     mass linearity, dust monotonicity, finite outputs."""

@@ -319,3 +319,57 @@ def test_new_device_paths_fail_loudly_without_a_gpu():
     # the model still lowers to the C struct on the host
     m = mod.device_model("nJy", "AB")
     assert m.n_bins == 8 and m.internal_is_ab == 1 and m.in_is_ab == 0 and m.in_to_jy == 1e-9 and m.out_is_ab == 1
+
+
+def test_generate_sfh_grid_and_emission_models():
+    """library.py:742-873 / :931-1018: meshgrid of drawn redshifts x SFH parameters (redshift-dependent upper bounds) and one
+    emission model per drawn parameter combination."""
+    from scipy.stats import uniform
+    import synference_b200 as S
+    from synference_b200.synthetic import synthetic_grid
+    np.random.seed(3)
+    pri = {"tau": {"prior": uniform, "min": 0.1, "max": 1.5, "size": 4},
+           "peak_age": {"prior": uniform, "min": 0.0, "max": 13000.0, "size": 6, "units": S.Myr, "depends_on": "max_redshift"}}
+    sfhs, combos = S.generate_sfh_grid(S.SFH.LogNormal, pri, {"prior": uniform, "min": 0.5, "max": 8.0, "size": 3}, max_redshift=15)
+    assert combos.shape == (3 * 4 * 6, 3) and len(sfhs) == 72
+    z = combos[:, 0]
+    want_max = (S.Planck18.age(z) - S.Planck18.age(15)).to("Myr").value
+    np.testing.assert_allclose(sfhs.rows[:, 1], want_max * 1e6, rtol=1e-12)
+    np.testing.assert_allclose(sfhs.rows[:, 2], combos[:, 1])                  # tau
+    np.testing.assert_allclose(sfhs.rows[:, 3], combos[:, 2] * 1e6)            # peak_age Myr -> yr
+    assert np.all(combos[:, 2].reshape(3, 4, 6).max(axis=(0, 1)) <= want_max.max())   # capped by the available age
+    one = sfhs[5]
+    assert type(one).__name__ == "_LogNormal" and abs(one.redshift - z[5]) < 1e-12
+    lam = S.generate_constant_R(R=100, start=900 * S.Angstrom, end=5e4 * S.Angstrom)
+    grid = synthetic_grid(lam)
+    models, out = S.generate_emission_models(S.PacmanEmission, {"fesc": {"prior": uniform, "min": 0.0, "max": 0.5, "size": 3}},
+                                             grid, fixed_params={"dust_curve": S.Calzetti2000()})
+    assert len(models) == 3 and len(out["fesc"]) == 3 and all(0 <= m.fesc <= 0.5 for m in models)
+    assert all(m.dust_curve.name == "Calzetti2000" for m in models)
+
+
+def test_uncertainty_models_from_an_epochs_style_table():
+    """noise_models.py:1159-1330 on a synthetic catalogue passed as a dict of columns (no astropy needed)."""
+    import synference_b200 as S
+    rng = np.random.default_rng(0)
+    n = 4000
+    depth = rng.normal(29.0, 0.2, n)
+    mag = rng.uniform(23, 30, n)
+    flux = 10 ** (-0.4 * (mag - 8.9))
+    tab = {"MAG_APER_F444W_aper_corr": mag, "FLUX_APER_F444W_aper_corr_Jy": flux, "loc_depth_F444W": depth}
+    tab["MAG_APER_F444W_aper_corr"][:5] = -99
+    ms = S.create_uncertainty_models_from_EPOCHS_cat(tab, "F444W", new_band_names=["JWST/NIRCam.F444W"])
+    m = ms["JWST/NIRCam.F444W"]
+    assert isinstance(m, S.GeneralEmpiricalUncertaintyModel) and m.return_noise
+    np.random.seed(1)
+    noisy, sig = m.apply_noise(np.full(100, 26.0), true_flux_units="AB", out_units="AB")
+    want_sigma = 2.5 / np.log(10) * (10 ** (-0.4 * (29.0 - 8.9)) / 5) / 10 ** (-0.4 * (26.0 - 8.9))
+    assert abs(np.median(sig) / want_sigma - 1) < 0.3
+    d = S.create_uncertainty_models_from_EPOCHS_cat(tab, ["F444W"], model_class="depth")["F444W"]
+    assert isinstance(d, S.DepthUncertaintyModel) and abs(d.depth_ab - np.median(depth)) < 1e-12
+    a = S.create_uncertainty_models_from_EPOCHS_cat(tab, ["F444W"], model_class="asinh")["F444W"]
+    assert isinstance(a, S.AsinhEmpiricalUncertaintyModel)
+    with pytest.raises(ValueError):
+        S.create_uncertainty_models_from_EPOCHS_cat(tab, "F200W")
+    with pytest.raises(ValueError):
+        S.create_uncertainty_models_from_EPOCHS_cat(tab, "F444W", model_class="nope")
