@@ -44,9 +44,11 @@ def _p(a):
 
 
 def synthesize(p, log10ages, metallicities, lam, g_att, g_un, filters, *, kappa=None, igm=None,
-               variant="nu", base_mass=1e9, nthreads=0, return_spectra=False):
+               variant="nu", base_mass=1e9, nthreads=0, return_spectra=False, two_screens=None, dust_shape=None):
     """Same contract as ``oracle.synthesize`` but threaded C.  ``p`` is GalaxyParams-like;
-    g_att / g_un are (n_age, n_z, n_lam) float64 or None; filters = [(lam_table, t_table), ...]."""
+    g_att / g_un are (n_age, n_z, n_lam) float64 or None; filters = [(lam_table, t_table), ...].
+    two_screens: dict(age_pivot=log10 yr, kappa_birth=(n_lam,), tau_v_birth=(n,)) -- SURVEY A5 birth cloud + ISM;
+    dust_shape: (n_lam,) unit-integral emission spectrum for the energy balance ('total')."""
     lib = load()
     f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
     z, tv = f64(p.redshift), f64(p.tau_v)
@@ -65,12 +67,18 @@ def synthesize(p, log10ages, metallicities, lam, g_att, g_un, filters, *, kappa=
     dla = f64(igm[1]) if igm is not None else None
     out = np.empty((n, len(filters)))
     spec = np.empty((n, lm.size)) if return_spectra else None
-    rc = lib.oracle_synthesize(
+    kb = tvb = young = None
+    if two_screens is not None:
+        kb, tvb = f64(two_screens["kappa_birth"]), f64(two_screens["tau_v_birth"])
+        young = np.ascontiguousarray(np.asarray(log10ages) < two_screens["age_pivot"], dtype=np.int32)
+    ds = f64(dust_shape)
+    rc = lib.oracle_synthesize_ex(
         C.c_int64(n), _p(z), _p(tv), C.c_int(int(p.sfh_type)), C.c_int(rows.shape[1]), _p(rows),
         C.c_int(int(p.zd_type)), _p(zv), _p(zs), C.c_int(la.size), C.c_int(zm.size), C.c_int(lm.size),
         _p(la), _p(zm), _p(lm), _p(ga), _p(gu), _p(kap), C.c_int(1 if igm is not None else 0), _p(laf), _p(dla),
         C.c_int(0 if laf is None else laf.shape[0]), C.c_int(len(filters)), _p(off), _p(fl), _p(ft),
-        C.c_int(0 if variant == "nu" else 1), C.c_double(base_mass), C.c_int(int(nthreads)), _p(out), _p(spec))
+        C.c_int(0 if variant == "nu" else 1), C.c_double(base_mass), C.c_int(int(nthreads)), _p(out), _p(spec),
+        _p(kb), _p(tvb), _p(young), _p(ds))
     if rc != 0:
         raise ValueError(f"filter lies entirely outside the spectrum for galaxy {rc - 1}")
     return (out, spec) if return_spectra else out

@@ -160,13 +160,17 @@ static double interp0(double x, const double* xp, const double* fp, int n) {
  * variant 0: integrate in nu (filter table interpolated in nu); 1: in lambda.
  * Returns 0, or (1 + galaxy index) of the first galaxy for which a filter has no in-band sample.
  */
-int oracle_synthesize(int64_t n_gal, const double* redshift, const double* tau_v, int sfh_type, int sfh_stride,
+/* Extended form: optional second dust screen -- stars of the age bins flagged in `young` sit behind
+ * exp(-tau_v_birth kappa_birth - tau_v kappa), the others behind exp(-tau_v kappa) -- and optional dust emission with
+ * energy balance: + E_abs * dust_shape(nu), E_abs = trapezoid over nu of the light the screen(s) removed. */
+int oracle_synthesize_ex(int64_t n_gal, const double* redshift, const double* tau_v, int sfh_type, int sfh_stride,
                       const double* sfh_rows, int zd_type, const double* zd_value, const double* zd_sigma,
                       int n_age, int n_z, int n_lam, const double* log10ages, const double* zmet,
                       const double* lam, const double* g_att, const double* g_un, const double* kappa,
                       int igm_on, const double* laf, const double* dla, int n_lines, int n_filt,
                       const int64_t* filt_off, const double* filt_lam, const double* filt_t, int variant,
-                      double base_mass, int nthreads, double* out_flux, double* out_spec) {
+                      double base_mass, int nthreads, double* out_flux, double* out_spec,
+                      const double* kappa_birth, const double* tau_v_birth, const int* young, const double* dust_shape) {
   cosmo_init();
   int bad = 0;
   double* ages = (double*)malloc(sizeof(double) * n_age);
@@ -194,6 +198,7 @@ int oracle_synthesize(int64_t n_gal, const double* redshift, const double* tau_v
     double* zd = (double*)malloc(sizeof(double) * n_z);
     double* fnu = (double*)malloc(sizeof(double) * n_lam);
     double* att = (double*)malloc(sizeof(double) * n_lam);
+    double* atty = (double*)malloc(sizeof(double) * n_lam);   /* young stars' share of the attenuated grid (two screens) */
     double* x = (double*)malloc(sizeof(double) * n_lam);
     double* tb = (double*)malloc(sizeof(double) * n_lam);
     double row[24];
@@ -230,7 +235,7 @@ int oracle_synthesize(int64_t n_gal, const double* redshift, const double* tau_v
         }
       }
       /* A4: grid-weighted sum over (age, Z) cells */
-      for (int i = 0; i < n_lam; ++i) { fnu[i] = 0.0; att[i] = 0.0; }
+      for (int i = 0; i < n_lam; ++i) { fnu[i] = 0.0; att[i] = 0.0; atty[i] = 0.0; }
       for (int a = 0; a < n_age; ++a) {
         if (sf[a] == 0.0) continue;
         for (int iz = 0; iz < n_z; ++iz) {
@@ -238,15 +243,31 @@ int oracle_synthesize(int64_t n_gal, const double* redshift, const double* tau_v
           if (w == 0.0) continue;
           size_t base = ((size_t)a * n_z + iz) * n_lam;
           if (g_un) for (int i = 0; i < n_lam; ++i) fnu[i] += w * g_un[base + i];
-          if (g_att) for (int i = 0; i < n_lam; ++i) att[i] += w * g_att[base + i];
+          if (g_att) {
+            double* dst = (kappa_birth && young && young[a]) ? atty : att;
+            for (int i = 0; i < n_lam; ++i) dst[i] += w * g_att[base + i];
+          }
         }
       }
       double dl = oracle_luminosity_distance_cm(z);
       double scale = base_mass * (1.0 + z) / (4.0 * M_PI * dl * dl) * 1e23 * 1e9;
       double tv = tau_v ? tau_v[g] : 0.0;
+      double tvb = tau_v_birth ? tau_v_birth[g] : 0.0;
+      if (g_att && kappa) {   /* screens, then energy balance on the rest-frame axis */
+        double e_abs = 0.0, prev_d = 0.0;
+        for (int i = 0; i < n_lam; ++i) {
+          double before = att[i] + atty[i];
+          double after = att[i] * exp(-tv * kappa[i]);
+          if (kappa_birth) after += atty[i] * exp(-tvb * kappa_birth[i] - tv * kappa[i]);
+          double d = before - after;
+          if (i > 0) e_abs += 0.5 * (d + prev_d) * (C_ANG / lam[i - 1] - C_ANG / lam[i]);
+          prev_d = d;
+          att[i] = after;
+        }
+        if (dust_shape) for (int i = 0; i < n_lam; ++i) att[i] += e_abs * dust_shape[i];
+      }
       for (int i = 0; i < n_lam; ++i) {
         double a_ = att[i];
-        if (g_att && kappa) a_ *= exp(-tv * kappa[i]);
         double lobs = lam[i] * (1.0 + z);
         double v = (fnu[i] + a_) * scale;
         if (igm_on) v *= exp(-igm_tau(z, lobs, laf, dla, n_lines));
@@ -278,10 +299,22 @@ int oracle_synthesize(int64_t n_gal, const double* redshift, const double* tau_v
         } else out_flux[g * n_filt + f] = num / den;
       }
     }
-    free(sf); free(zd); free(fnu); free(att); free(x); free(tb);
+    free(sf); free(zd); free(fnu); free(att); free(atty); free(x); free(tb);
   }
   free(ages); free(edges); free(fx); free(ft);
   return bad;
+}
+
+int oracle_synthesize(int64_t n_gal, const double* redshift, const double* tau_v, int sfh_type, int sfh_stride,
+                      const double* sfh_rows, int zd_type, const double* zd_value, const double* zd_sigma,
+                      int n_age, int n_z, int n_lam, const double* log10ages, const double* zmet,
+                      const double* lam, const double* g_att, const double* g_un, const double* kappa,
+                      int igm_on, const double* laf, const double* dla, int n_lines, int n_filt,
+                      const int64_t* filt_off, const double* filt_lam, const double* filt_t, int variant,
+                      double base_mass, int nthreads, double* out_flux, double* out_spec) {
+  return oracle_synthesize_ex(n_gal, redshift, tau_v, sfh_type, sfh_stride, sfh_rows, zd_type, zd_value, zd_sigma, n_age, n_z,
+                              n_lam, log10ages, zmet, lam, g_att, g_un, kappa, igm_on, laf, dla, n_lines, n_filt, filt_off,
+                              filt_lam, filt_t, variant, base_mass, nthreads, out_flux, out_spec, NULL, NULL, NULL, NULL);
 }
 
 int oracle_num_threads(void) {

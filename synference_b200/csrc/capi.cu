@@ -181,6 +181,8 @@ struct Switches {
   }
 };
 
+const sb2_model* g_wait_owner[64] = {};   // per device: the model whose host-mapped buffer the watchdog symbol points to
+
 struct sb2_model {
   int device = 0;
   int n_sm = 0;
@@ -292,7 +294,14 @@ int sb2_model_destroy(sb2_model* m) {
   if (m->st_h2d) cudaStreamDestroy(m->st_h2d);
   if (m->st_comp) cudaStreamDestroy(m->st_comp);
   if (m->st_d2h) cudaStreamDestroy(m->st_d2h);
-  if (m->wait_dbg) cudaFreeHost(m->wait_dbg);
+  if (m->wait_dbg) {
+    if (m->device >= 0 && m->device < 64 && g_wait_owner[m->device] == m) {   // do not leave the symbol dangling
+      unsigned int* none = nullptr;
+      cudaMemcpyToSymbol(sb2::g_wait_dbg, &none, sizeof(none));
+      g_wait_owner[m->device] = nullptr;
+    }
+    cudaFreeHost(m->wait_dbg);
+  }
   delete m;
   return SB2_OK;
 }
@@ -480,8 +489,9 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   if (cudaHostAlloc(reinterpret_cast<void**>(&m->wait_dbg), 260 * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess) {
     std::memset(m->wait_dbg, 0, 260 * sizeof(unsigned int));
     unsigned int* dptr = nullptr;
-    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), m->wait_dbg, 0) == cudaSuccess)
-      cudaMemcpyToSymbol(sb2::g_wait_dbg, &dptr, sizeof(dptr));
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), m->wait_dbg, 0) == cudaSuccess &&
+        cudaMemcpyToSymbol(sb2::g_wait_dbg, &dptr, sizeof(dptr)) == cudaSuccess && device >= 0 && device < 64)
+      g_wait_owner[device] = m;     // (one record buffer per device: the most recently created model's)
   }
   bool ok = cudaStreamCreateWithFlags(&m->st_h2d, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&m->st_comp, cudaStreamNonBlocking) == cudaSuccess &&
@@ -988,7 +998,12 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
     dp.sfh_rows = dev[11] + a * p->sfh_stride;
     rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux[slot] + a * nf : nullptr,
                               flux_scaled ? m->stage_flux64[slot] + a * nf : nullptr, nullptr, m->st_comp);
-    if (rc != SB2_OK) return rc;
+    if (rc != SB2_OK) {   // earlier slices are still in flight on the three streams: drain them before reporting
+      const std::string msg = g_err;
+      cudaStreamSynchronize(m->st_h2d); cudaStreamSynchronize(m->st_comp); cudaStreamSynchronize(m->st_d2h);
+      g_err = msg;
+      return rc;
+    }
     CU_TRY(cudaEventRecord(m->ev_done[sl], m->st_comp));
     if (trace) cudaEventRecord(tr[1 + sl * 4 + 2], m->st_comp);
     CU_TRY(cudaStreamWaitEvent(m->st_d2h, m->ev_done[sl], 0));

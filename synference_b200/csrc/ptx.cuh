@@ -74,7 +74,12 @@ __device__ __forceinline__ uint64_t global_ns() {
   return t;
 }
 // try_wait suspends the warp in hardware for a while (it does not burn the issue slots the epilogue warps of the
-// same scheduler need); the watchdog is wall-clock based: no legitimate wait of these kernels lasts 2 s.
+// same scheduler need).  The watchdog turns a protocol bug into a trap instead of a hung GPU; it is wall-clock based
+// (%globaltimer keeps running while a context is time-sliced or stopped in a debugger), so the bound is generous -- no
+// legitimate wait of these kernels lasts a millisecond -- and -DSB2_NO_WATCHDOG removes it altogether.
+#ifndef SB2_WATCHDOG_NS
+#define SB2_WATCHDOG_NS 30000000000ull
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t id = 0) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
@@ -82,8 +87,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3Fu) == 0u) {
       const uint64_t now = global_ns();
+#ifndef SB2_NO_WATCHDOG
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) mbar_timeout(id, parity);
+      else if (now - t0 > SB2_WATCHDOG_NS) mbar_timeout(id, parity);
+#endif
     }
   }
 }

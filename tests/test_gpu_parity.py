@@ -200,6 +200,52 @@ def test_device_max_age_from_redshift_matches_host_path(engines):
     np.testing.assert_allclose(dev, host, rtol=2e-6)
 
 
+def test_cfg3_dense_path_matches_c_oracle_at_20000(engines):
+    """the dense-K path (Continuity SFH x Normal metallicity distribution, K = 663, z 0-15) -- the
+    configuration with the thinnest margin -- at 20 000 galaxies against the C oracle."""
+    w, eng = engines("cfg3", 20000)
+    want = oracle_flux(w, c=True)
+    got = eng.photometry(w.params, scaled=False)
+    err = assert_flux_close(got, want)
+    print(f"cfg3 dense path, 20000 galaxies: max rel err {err:.3e}")
+
+
+@pytest.mark.parametrize("model", ["total_one_screen", "total_two_screens", "emergent_two_screens"])
+def test_emission_variants_match_c_oracle_at_20000(model):
+    """the production emission keys at 20 000 galaxies against the C oracle: 'total' with dust emission
+    (energy balance over the whole axis), and the birth-cloud + ISM screens with and without emission."""
+    from synference_b200.parametric import BimodalPacmanEmission, Calzetti2000, Greybody, PacmanEmission
+    n = 20000
+    w = make_workload("cfg2", n)
+    lam = np.asarray(w.grid.lam)
+    filt = [(f.lam, f.t) for f in w.filters]
+    p = w.params.slice(slice(0, n))
+    de = dict(kind="Greybody", temperature=40.0, emissivity=1.5)
+    key = "emergent" if model == "emergent_two_screens" else "total"
+    kw = {}
+    if model == "total_one_screen":
+        em = PacmanEmission(grid=w.grid, fesc=0.1, fesc_ly_alpha=0.5, dust_curve=Calzetti2000(), dust_emission=Greybody(40.0, 1.5))
+        ga, gu = O.emission_parts(w.grid.spectra, lam, key, 0.1, 0.5)
+        kw["dust_shape"] = O.dust_emission_shape(lam, **de)
+    else:
+        gen = Greybody(40.0, 1.5) if model == "total_two_screens" else None
+        em = BimodalPacmanEmission(grid=w.grid, dust_curve_ism=Calzetti2000(), dust_curve_birth=Calzetti2000(slope=-0.7), age_pivot=7.0,
+                                   dust_emission_ism=gen, dust_emission_birth=None if gen is None else Greybody(40.0, 1.5),
+                                   fesc_ly_alpha=0.4)
+        p.tau_v_birth = np.random.default_rng(4).uniform(0.0, 3.0, n)
+        ga, gu = O.emission_parts(w.grid.spectra, lam, key, 0.0, 0.4)
+        kw["two_screens"] = dict(age_pivot=7.0, kappa_birth=O.dust_kappa(lam, slope=-0.7), tau_v_birth=p.tau_v_birth)
+        if gen is not None:
+            kw["dust_shape"] = O.dust_emission_shape(lam, **de)
+    eng = SynthEngine(w.grid, em, key, w.filters, max_batch=1 << 15)
+    got = eng.photometry(p, scaled=False)
+    want = CO.synthesize(p, w.grid.log10ages, w.grid.metallicity, lam, ga, gu, filt, kappa=O.dust_kappa(lam),
+                         igm=(I.INOUE14_LAF, I.INOUE14_DLA), **kw)
+    err = assert_flux_close(got, want)
+    print(f"{model}, 20000 galaxies: max rel err {err:.3e}")
+    eng.close()
+
+
 def test_float32_parameter_transport_is_exact_for_float32_draws(engines):
     """parameters cross PCIe as float32 (sb2_params.host_f32) and are widened on the device.  The draws of
     draw_from_hypercube ARE float32 (library.py:1098): sending the raw draws with max_age_from_z gives bit-identical fluxes

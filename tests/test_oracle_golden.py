@@ -252,3 +252,36 @@ def test_filter_variants_differ_at_the_expected_level():
     assert 0 < abs(a / b - 1) < 5e-5
     with pytest.raises(ValueError):
         O.apply_filter(fnu, lam * 100.0, fl, ft, "nu")
+
+
+def test_c_oracle_extensions_match_numpy_oracle():
+    """The C restatement's two-screen attenuation and dust-emission energy balance (used to check 20 000-galaxy batches on
+    the GPU) against the numpy oracle, galaxy by galaxy."""
+    from oracle import adapter as A, c_oracle as CO, oracle as O
+    from synference_b200 import igm as I
+    from synference_b200.configs import make_workload
+    w = make_workload("cfg2", 24)
+    lam = np.asarray(w.grid.lam)
+    filt = [(f.lam, f.t) for f in w.filters]
+    p = w.params
+    tau_b = np.random.default_rng(0).uniform(0, 3, len(p))
+    gals = A.galaxies_from_params(p)
+    for g, tb in zip(gals, tau_b):
+        g["tau_v_birth"] = float(tb)
+    ts = dict(age_pivot=7.0, dust_birth=dict(curve="Calzetti2000", slope=-0.7))
+    de = dict(kind="Greybody", temperature=40.0, emissivity=1.5)
+    want = O.synthesize(gals, w.grid.log10ages, w.grid.metallicity, lam, w.grid.spectra, filt, key="total", fesc_ly_alpha=0.4,
+                        dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA), two_screens=ts, dust_emission=de)
+    ga, gu = O.emission_parts(w.grid.spectra, lam, "total", 0.0, 0.4)
+    got = CO.synthesize(p, w.grid.log10ages, w.grid.metallicity, lam, ga, gu, filt, kappa=O.dust_kappa(lam),
+                        igm=(I.INOUE14_LAF, I.INOUE14_DLA),
+                        two_screens=dict(age_pivot=7.0, kappa_birth=O.dust_kappa(lam, slope=-0.7), tau_v_birth=tau_b),
+                        dust_shape=O.dust_emission_shape(lam, **de))
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    # single screen + emission
+    want1 = O.synthesize(gals, w.grid.log10ages, w.grid.metallicity, lam, w.grid.spectra, filt, key="total", fesc=0.1, fesc_ly_alpha=0.5,
+                         dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA), dust_emission=de)
+    ga, gu = O.emission_parts(w.grid.spectra, lam, "total", 0.1, 0.5)
+    got1 = CO.synthesize(p, w.grid.log10ages, w.grid.metallicity, lam, ga, gu, filt, kappa=O.dust_kappa(lam),
+                         igm=(I.INOUE14_LAF, I.INOUE14_DLA), dust_shape=O.dust_emission_shape(lam, **de))
+    np.testing.assert_allclose(got1, want1, rtol=1e-10)
