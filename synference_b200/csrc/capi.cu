@@ -169,14 +169,13 @@ __global__ void group_scatter_kernel(const unsigned* __restrict__ keys_sorted, c
 // Experiment / fallback switches (environment), read ONCE when a model is created -- never on the per-call path.
 struct Switches {
   bool n256 = false, cta_pair = false, libm = false, weights_v1 = false, one_pass = false, trace = false, no_synth3 = false;
-  int dbg = 0, s3_n = 96;
+  int dbg = 0;
   long long host_slices = 0;   // 0: automatic
   static bool on(const char* k) { const char* e = std::getenv(k); return e && e[0] && e[0] != '0'; }
   void read() {
     n256 = on("SB2_N256"); cta_pair = on("SB2_CTA_PAIR"); libm = on("SB2_LIBM"); weights_v1 = on("SB2_WEIGHTS_V1");
     one_pass = on("SB2_ONE_PASS"); trace = on("SB2_TRACE"); no_synth3 = on("SB2_NO_SYNTH3");
     if (const char* e = std::getenv("SB2_DBG")) dbg = std::atoi(e);
-    if (const char* e = std::getenv("SB2_S3_N")) s3_n = std::atoi(e) == 128 ? 128 : 96;
     if (const char* e = std::getenv("SB2_HOST_SLICES")) host_slices = std::atoll(e);
   }
 };
@@ -189,7 +188,7 @@ struct sb2_model {
   Switches sw;
   // synth3 (weights as the TMEM operand): raw SFH bin masses, tile-blocked, and the two metallicity factors
   double *sf = nullptr, *s0 = nullptr, *s1 = nullptr;
-  CUtensorMap tm_g96_hi, tm_g96_lo, tm_g128_hi, tm_g128_lo;
+  CUtensorMap tm_g96_hi, tm_g96_lo;
   bool s3_ok = false;
   sb2_model_desc d{};  // dims and scalars (pointers inside are NOT valid after create)
   long long cap = 0, cap_pad = 0;
@@ -469,8 +468,6 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
       (rc = make_tmap(&m->tm_g160_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 160)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g96_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 96)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g96_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 96)) != SB2_OK ||
-      (rc = make_tmap(&m->tm_g128_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 128)) != SB2_OK ||
-      (rc = make_tmap(&m->tm_g128_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 128)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK) {
     sb2_model_destroy(m);
@@ -525,11 +522,24 @@ bool delta_mode(const sb2_model* m, const sb2_params* p) {
   return m->wd_stride > 0 && (p->zd_type == SB2_ZD_DELTA_LINEAR || p->zd_type == SB2_ZD_DELTA_LOG10);
 }
 
-// Bracket-grouped batches without per-galaxy emission extras take synth3_kernel (weights as the TMEM operand).
-bool use_s3(const sb2_model* m, const sb2_params* p) {
-  return m->s3_ok && delta_mode(m, p) && !m->dust_d0 && !m->lya_line && !m->kappa_birth && !m->dust_wnu && !m->sw.cta_pair;
+// Per-galaxy emission extras of a model as a synth3_kernel feature set (sb2::kFeat*).
+int model_features(const sb2_model* m) {
+  return (m->dust_d0 ? sb2::kFeatDustShape : 0) | (m->lya_line ? sb2::kFeatLya : 0) | (m->kappa_birth ? sb2::kFeatTwoScreens : 0) |
+         (m->dust_wnu ? sb2::kFeatAbsorbed : 0);
 }
-int s3_cols(const sb2_model* m) { return m->d.n_comp == 1 ? m->sw.s3_n : 128; }   // accumulator columns per chunk
+// feature sets synth3_kernel is instantiated for (what the reference's scripts combine): none | Lya | dust shape (+ Lya) |
+// two screens | absorbed energy | two screens + absorbed | dust shape + Lya + absorbed (the production script's `total`)
+bool s3_has_features(int f) {
+  using namespace sb2;
+  return f == 0 || f == kFeatLya || f == kFeatDustShape || f == (kFeatDustShape | kFeatLya) || f == kFeatTwoScreens ||
+         f == kFeatAbsorbed || f == (kFeatTwoScreens | kFeatAbsorbed) || f == (kFeatDustShape | kFeatLya | kFeatAbsorbed) ||
+         f == (kFeatLya | kFeatAbsorbed);
+}
+// Bracket-grouped batches take synth3_kernel (weights as the TMEM operand).
+bool use_s3(const sb2_model* m, const sb2_params* p) {
+  return m->s3_ok && delta_mode(m, p) && s3_has_features(model_features(m)) && !m->sw.cta_pair;
+}
+int s3_cols(const sb2_model* m) { return m->d.n_comp == 1 ? 96 : 128; }   // accumulator columns per chunk (3 x 96 | 2 x 128 beside the weights)
 
 
 template <int C, int NF, bool SPEC, bool PG>
@@ -592,39 +602,60 @@ int launch_synth2(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t 
 #undef SB2_PICK
 }
 
-template <int C, int NF, bool SPEC, int N>
+template <int C, int NF, bool SPEC, int N, int FEAT = 0>
 int launch_synth3_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
-  auto k = sb2::synth3_kernel<C, NF, SPEC, N>;
+  auto k = sb2::synth3_kernel<C, NF, SPEC, N, FEAT>;
   sb2::SynthArgs a2 = a;
   sb2::Synth3Args x{};
   x.sf = m->sf; x.s0 = m->s0; x.s1 = m->s1; x.n_age = m->d.n_age; x.na_pad = m->d.n_age_pad; x.w_stride = m->wd_stride;
   x.kb_split = a.n_kb / 2;
   bool spec = false;
   const int kap_len = m->d.n_chunk * (sb2::kBN / C);
-  if (SPEC && sb2::synth3_smem_bytes(N, 3, x.n_age, m->uv_len, kap_len, true) <= m->smem_optin) { spec = true; a2.spec_smem = 1; }
+  if (SPEC && sb2::synth3_smem_bytes(N, 3, x.n_age, m->uv_len, kap_len, true, FEAT) <= m->smem_optin) { spec = true; a2.spec_smem = 1; }
   int ns = sb2::kS3MaxStages;
-  while (ns > 1 && sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec) > m->smem_optin) --ns;
-  const size_t bytes = sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec);
+  while (ns > 1 && sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec, FEAT) > m->smem_optin) --ns;
+  const size_t bytes = sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec, FEAT);
   if (ns < 2 || bytes > m->smem_optin) return fail(SB2_ERR_INVALID, "synth3_kernel: filter tables leave no room for the operand ring");
   x.n_stages = ns;
   CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  const CUtensorMap& th = C == 2 ? m->tm_g2_hi : (N == 96 ? m->tm_g96_hi : m->tm_g128_hi);
-  const CUtensorMap& tl = C == 2 ? m->tm_g2_lo : (N == 96 ? m->tm_g96_lo : m->tm_g128_lo);
+  const CUtensorMap& th = C == 2 ? m->tm_g2_hi : m->tm_g96_hi;      // boxes of 64 rows (one component of a chunk) | 96 rows
+  const CUtensorMap& tl = C == 2 ? m->tm_g2_lo : m->tm_g96_lo;
   k<<<grid, sb2::kS3Threads, bytes, st>>>(th, tl, a2, x);
   STAGE_CHECK("synth3_kernel", st);
   return SB2_OK;
 }
 
+// feature-set instantiations: one accumulator width (32 filters) to bound the number of kernels
+template <int FEAT>
+int launch_synth3_feat(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
+  const bool spec = a.out_spec != nullptr;
+  if (m->d.n_comp == 1) {
+    if constexpr ((FEAT & sb2::kFeatTwoScreens) != 0) return fail(SB2_ERR_INVALID, "two dust screens need two components");
+    else return spec ? launch_synth3_t<1, 32, true, 96, FEAT>(m, a, grid, st) : launch_synth3_t<1, 32, false, 96, FEAT>(m, a, grid, st);
+  }
+  return spec ? launch_synth3_t<2, 32, true, 128, FEAT>(m, a, grid, st) : launch_synth3_t<2, 32, false, 128, FEAT>(m, a, grid, st);
+}
+
 int launch_synth3(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_t st) {
   const int nf = m->d.n_filt, c = m->d.n_comp;
   const bool spec = a.out_spec != nullptr;
+  {
+    using namespace sb2;
+    switch (model_features(m)) {
+      case 0: break;
+      case kFeatLya: return launch_synth3_feat<kFeatLya>(m, a, grid, st);
+      case kFeatDustShape: return launch_synth3_feat<kFeatDustShape>(m, a, grid, st);
+      case kFeatDustShape | kFeatLya: return launch_synth3_feat<kFeatDustShape | kFeatLya>(m, a, grid, st);
+      case kFeatTwoScreens: return launch_synth3_feat<kFeatTwoScreens>(m, a, grid, st);
+      case kFeatAbsorbed: return launch_synth3_feat<kFeatAbsorbed>(m, a, grid, st);
+      case kFeatTwoScreens | kFeatAbsorbed: return launch_synth3_feat<kFeatTwoScreens | kFeatAbsorbed>(m, a, grid, st);
+      case kFeatLya | kFeatAbsorbed: return launch_synth3_feat<kFeatLya | kFeatAbsorbed>(m, a, grid, st);
+      case kFeatDustShape | kFeatLya | kFeatAbsorbed: return launch_synth3_feat<kFeatDustShape | kFeatLya | kFeatAbsorbed>(m, a, grid, st);
+      default: return fail(SB2_ERR_INVALID, "no synth3_kernel instantiation for this feature set");
+    }
+  }
 #define SB2_PICK3(C, NF, N) (spec ? launch_synth3_t<C, NF, true, N>(m, a, grid, st) : launch_synth3_t<C, NF, false, N>(m, a, grid, st))
   if (c == 1) {
-    if (s3_cols(m) == 128) {
-      if (nf <= 8) return SB2_PICK3(1, 8, 128);
-      if (nf <= 24) return SB2_PICK3(1, 24, 128);
-      return SB2_PICK3(1, 32, 128);
-    }
     if (nf <= 8) return SB2_PICK3(1, 8, 96);
     if (nf <= 24) return SB2_PICK3(1, 24, 96);
     return SB2_PICK3(1, 32, 96);
@@ -782,12 +813,16 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   }
   const bool dpl = p->sfh_type == SB2_SFH_DOUBLE_POWERLAW;
   if (use_s3(m, p) && (delta || w_f64)) {   // one galaxy per thread: raw bin masses, tile-blocked (expanded on chip by synth3_kernel)
-    sb2::SfOut S{m->sf, m->s0, m->s1};
+    sb2::SfOut S{m->sf, m->s0, m->s1, m->g_lya};
     const unsigned blocks3 = (unsigned)((n_pad + sb2::kW3Threads - 1) / sb2::kW3Threads);
-    if (dpl) sb2::weights3_kernel<false, 2><<<blocks3, sb2::kW3Threads, 0, st>>>(M, F, P, S, w_f64, perm, n_pad);
-    else if (p->sfh_type == SB2_SFH_CONTINUITY) sb2::weights3_kernel<false, 1><<<blocks3, sb2::kW3Threads, 0, st>>>(M, F, P, S, w_f64, perm, n_pad);
-    else if (fast) sb2::weights3_kernel<true, 0><<<blocks3, sb2::kW3Threads, 0, st>>>(M, F, P, S, w_f64, perm, n_pad);
-    else sb2::weights3_kernel<false, 0><<<blocks3, sb2::kW3Threads, 0, st>>>(M, F, P, S, w_f64, perm, n_pad);
+    const bool lya = p->fesc_lya != nullptr && !w_f64;
+#define SB2_W3(FAST, MODE) (lya ? sb2::weights3_kernel<FAST, MODE, true><<<blocks3, sb2::kW3Threads, 0, st>>>(M, F, P, S, w_f64, perm, n_pad) \
+                                : sb2::weights3_kernel<FAST, MODE, false><<<blocks3, sb2::kW3Threads, 0, st>>>(M, F, P, S, w_f64, perm, n_pad))
+    if (dpl) SB2_W3(false, 2);
+    else if (p->sfh_type == SB2_SFH_CONTINUITY) SB2_W3(false, 1);
+    else if (fast) SB2_W3(true, 0);
+    else SB2_W3(false, 0);
+#undef SB2_W3
   } else if (M.n_age <= 64 && M.n_z <= 64 && !m->sw.weights_v1) {   // half-warp per galaxy
     const unsigned blocks2 = (unsigned)((n_pad + sb2::kW2Gal - 1) / sb2::kW2Gal);
     const bool lya = p->fesc_lya != nullptr && !w_f64;

@@ -669,6 +669,7 @@ struct SfOut {
   double* sf;   // [n_tiles][n_age][128] raw bin masses (rows of padding galaxies are 0)
   double* s0;   // [n_pad]
   double* s1;   // [n_pad]
+  float* g_lya; // [n_pad] fesc_lya_g * sum_k w_k lya_line[k] (kLya instantiations; nullptr otherwise)
 };
 
 // families whose edge value needs at most two parameters (everything except DoublePowerLaw and Continuity)
@@ -802,7 +803,7 @@ __device__ __forceinline__ double sfh_masses_thread(const PrepModel& M, const Fa
 
 constexpr int kW3Threads = 128;   // one tile of the contraction kernel per block
 
-template <bool kFast, int kMode>
+template <bool kFast, int kMode, bool kLya = false>
 __global__ void __launch_bounds__(kW3Threads)
 weights3_kernel(PrepModel M, FastMath F, PrepParams P, SfOut O, double* __restrict__ w_f64, const int* __restrict__ perm,
                 long long n_pad) {
@@ -816,14 +817,22 @@ weights3_kernel(PrepModel M, FastMath F, PrepParams P, SfOut O, double* __restri
   if (g < 0) {
     for (int a = 0; a < M.n_age; ++a) sf[(size_t)a * kW3Threads] = 0.0;
     O.s0[t] = 0.0; O.s1[t] = 0.0;
+    if constexpr (kLya) O.g_lya[t] = 0.f;
     return;
   }
-  const double part = sfh_masses_thread<kFast, kMode>(M, F, P, g, s_edges, [&](int a, double m) { sf[(size_t)a * kW3Threads] = m; });
   const bool logz = (P.zd_type == SB2_ZD_DELTA_LOG10);
   double zf = 0.0;
   int zj = 0;
   if (M.n_z >= 2) zj = delta_bracket(logz ? M.log10zmet : M.zmet, M.n_z, P.zd_value[g], &zf);
+  // per-galaxy Lyman-alpha line: the weighted sum of the line-continuum value of that one bin over the (age, Z) cells
+  double lya_acc = 0.0;
+  const double part = sfh_masses_thread<kFast, kMode>(M, F, P, g, s_edges, [&](int a, double m) {
+    sf[(size_t)a * kW3Threads] = m;
+    if constexpr (kLya)
+      lya_acc += m * ((1.0 - zf) * __ldg(M.lya_line + zj * M.n_age + a) + (M.n_z >= 2 ? zf * __ldg(M.lya_line + (zj + 1) * M.n_age + a) : 0.0));
+  });
   const double inv_sf = 1.0 / part;
+  if constexpr (kLya) O.g_lya[t] = (float)(P.fesc_lya[g] * lya_acc * inv_sf);
   const double s0 = (1.0 - zf) * inv_sf, s1 = zf * inv_sf;
   O.s0[t] = s0; O.s1[t] = s1;
   if (w_f64) {   // parity hook: the full row in the caller's order, k = iz*n_age + ia

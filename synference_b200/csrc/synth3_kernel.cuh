@@ -42,12 +42,16 @@ struct Synth3Cfg {
   static constexpr int kStageBytes = 2 * kN * kBK * 4;        // hi | lo tile of one grid k-block
 };
 
-__host__ __device__ inline size_t synth3_smem_bytes(int kn, int n_stages, int n_age, int uv_len, int kap_len, bool spec) {
+// per-wavelength tables the epilogue reads from shared memory: the attenuation curve plus what the feature set adds
+__host__ __device__ inline int synth3_n_tables(int feat) {
+  return 1 + ((feat & kFeatDustShape) ? 2 : 0) + ((feat & kFeatTwoScreens) ? 1 : 0) + ((feat & kFeatAbsorbed) ? 1 : 0);
+}
+__host__ __device__ inline size_t synth3_smem_bytes(int kn, int n_stages, int n_age, int uv_len, int kap_len, bool spec, int feat = 0) {
   return 1024 + (size_t)n_stages * (2 * kn * kBK * 4) + (size_t)n_age * 1024 + (((size_t)uv_len * 8 + 15) & ~size_t(15)) +
-         (size_t)kap_len * 4 + kS3BarBytes + (spec ? kSpecSmemBytes : 0);
+         (size_t)kap_len * 4 * synth3_n_tables(feat) + kS3BarBytes + (spec ? kSpecSmemBytes : 0);
 }
 
-template <int kComp, int kNF, bool kSpec, int kN>
+template <int kComp, int kNF, bool kSpec, int kN, int kFeat = 0>
 __global__ void __launch_bounds__(kS3Threads, 1)
 synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo,
               const __grid_constant__ SynthArgs A, const __grid_constant__ Synth3Args X) {
@@ -63,7 +67,13 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
   float2* s_uv = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(s_sf) + (size_t)X.n_age * 1024);
   float* s_kap = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_uv) + ((A.uv_len * 8 + 15) & ~15));   // attenuation curve (or zeros)
   const int kap_len = A.n_chunk * (kBN / kComp);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kap + kap_len);
+  // feature-set tables follow the attenuation curve: dust_d0 | dust_l2 | kappa_birth | wnu (only those the set uses)
+  float* s_tab = s_kap + kap_len;
+  float* s_d0 = nullptr; float* s_l2 = nullptr; float* s_kapb = nullptr; float* s_wnu = nullptr;
+  if constexpr ((kFeat & kFeatDustShape) != 0) { s_d0 = s_tab; s_l2 = s_tab + kap_len; s_tab += 2 * kap_len; }
+  if constexpr ((kFeat & kFeatTwoScreens) != 0) { s_kapb = s_tab; s_tab += kap_len; }
+  if constexpr ((kFeat & kFeatAbsorbed) != 0) { s_wnu = s_tab; s_tab += kap_len; }
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab);
   uint64_t* full_bar = bars;                                   // [kS3MaxStages] TMA -> MMA
   uint64_t* empty_bar = full_bar + kS3MaxStages;               // [kS3MaxStages] MMA -> TMA
   uint64_t* tfull_bar = empty_bar + kS3MaxStages;              // [kTfPerGroup * 2] MMA -> epilogue group
@@ -94,7 +104,12 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < A.uv_len; i += kS3Threads) s_uv[i] = A.filt_uv[i];
-  for (int i = threadIdx.x; i < kap_len; i += kS3Threads) s_kap[i] = A.kappa[i];
+  for (int i = threadIdx.x; i < kap_len; i += kS3Threads) {
+    s_kap[i] = A.kappa[i];
+    if constexpr ((kFeat & kFeatDustShape) != 0) { s_d0[i] = A.dust_d0[i]; s_l2[i] = A.dust_l2[i]; }
+    if constexpr ((kFeat & kFeatTwoScreens) != 0) s_kapb[i] = A.kappa_birth[i];
+    if constexpr ((kFeat & kFeatAbsorbed) != 0) s_wnu[i] = A.wnu[i];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -264,8 +279,11 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
   } else {
     reg_inc<176>();
     float* s_spec = (kSpec && A.spec_smem) ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kS3BarBytes) : nullptr;
-    epilogue_loop<kComp, kNF, kSpec, 1, kN, 2, false, kS3EpiWarp0, (int)kBuf, true>(A, s_uv, s_spec, tfull_bar, tempty_bar, 0u, tmem_base,
-                                                                                   (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u, smem_u32(s_kap));
+    const EpiTables tabs{smem_u32(s_kap), s_d0 ? smem_u32(s_d0) : 0u, s_l2 ? smem_u32(s_l2) : 0u, s_kapb ? smem_u32(s_kapb) : 0u,
+                         s_wnu ? smem_u32(s_wnu) : 0u};
+    epilogue_loop<kComp, kNF, kSpec, 1, kN, 2, false, kS3EpiWarp0, (int)kBuf, kFeat, true>(A, s_uv, s_spec, tfull_bar, tempty_bar, 0u,
+                                                                                          tmem_base, (int)blockIdx.x, (int)gridDim.x,
+                                                                                          n_tiles, 0u, tabs);
   }
 
   tc_fence_before();

@@ -163,13 +163,30 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   return r;
 }
 
-// kKapS: the attenuation curve is read from shared memory (kap_saddr) instead of global memory -- with ~225 KB of the SM's
-// 228 KB configured as shared memory there is no L1 left, so every __ldg of the curve was an L2 round trip per sub-chunk.
+// Per-galaxy emission extras of the epilogue, as a compile-time feature set (synth3_kernel: one instantiation per set that
+// the models actually use) -- or kFeatRuntime: the pointers in SynthArgs decide at run time (synth_kernel's kPgDust blob).
+constexpr int kFeatDustShape = 1;   // per-galaxy dust-curve slope / bump amplitude (dust_d0, dust_l2, g_slope, g_ampl)
+constexpr int kFeatLya = 2;         // per-galaxy Lyman-alpha line term (g_lya at lya_bin)
+constexpr int kFeatTwoScreens = 4;  // birth cloud + ISM (kappa_birth, g_taub); two components, both attenuated
+constexpr int kFeatAbsorbed = 8;    // energy balance: absorbed-energy sum for the dust emission (wnu, e_part)
+constexpr int kFeatRuntime = -1;
+
+// Shared-memory copies of the per-wavelength tables (byte addresses; 0: read the global array instead).  With ~225 KB of
+// the SM's 228 KB configured as shared memory there is no L1 left, so every __ldg of a table was an L2 round trip per
+// sub-chunk with two epilogue warps per scheduler to hide it.
+struct EpiTables { uint32_t kappa, d0, l2, kappa_birth, wnu; };
+
+template <bool kTabS>
+__device__ __forceinline__ float4 epi_tab4(const float* g, uint32_t saddr, int i0, int j4) {
+  if constexpr (kTabS) return lds_f4(saddr + (uint32_t)(i0 + 4 * j4) * 4u);
+  else return __ldg(reinterpret_cast<const float4*>(g + i0) + j4);
+}
+
 template <int kComp, int kNF, bool kSpec, int kCta, int kN, int kGroups, bool kPgDust, int kWarp0 = kEpiWarp0, int kBufT = 512 / kN,
-          bool kKapS = false>
+          int kFeat = kFeatRuntime, bool kTabS = false>
 __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* s_uv, float* s_spec, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tempty_addr, uint32_t tmem_base, int unit0, int unit_stride,
-                                              int n_units, uint32_t cta_rank, uint32_t kap_saddr = 0u) {
+                                              int n_units, uint32_t cta_rank, EpiTables T = EpiTables{0u, 0u, 0u, 0u, 0u}) {
   constexpr int kLch = kN / kComp;      // wavelengths per chunk
   constexpr int kSub = kLch / 32;       // 32-wavelength sub-chunks per chunk
   constexpr uint32_t kBuf = kBufT;      // TMEM accumulators (2 x 256, 3 x 160 or 4 x 128 columns; synth3: what W leaves free)
@@ -192,14 +209,16 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
       const int orig = A.g_orig[row];
       int m = A.g_m[row];
       const float ntaut = -A.g_taut[row];
-      constexpr bool pg_dust = kPgDust;   // compile-time: a run-time test here cost 10 % of the kernel (register pressure)
+      constexpr bool kStatic = kFeat != kFeatRuntime;   // feature set fixed at compile time (folds every test below)
+      constexpr bool pg_dust = kStatic ? (kFeat != 0) : kPgDust;   // compile-time: a run-time test here cost 10 % of the kernel (register pressure)
       // (kPgDust instantiations carry all per-galaxy emission extras: dust-curve shape and/or the Lyman-alpha line)
-      const bool dust_pg = pg_dust && A.dust_d0 != nullptr;
+      const bool dust_pg = kStatic ? bool(kFeat & kFeatDustShape) : (pg_dust && A.dust_d0 != nullptr);
       const float slope = dust_pg ? A.g_slope[row] : 0.f, ampl = dust_pg ? A.g_ampl[row] : 0.f;
-      const float lya = (pg_dust && A.g_lya != nullptr) ? A.g_lya[row] : 0.f;
-      const bool two_screens = pg_dust && kComp == 2 && A.kappa_birth != nullptr;
+      const bool lya_on = kStatic ? bool(kFeat & kFeatLya) : (pg_dust && A.g_lya != nullptr);
+      const float lya = lya_on ? A.g_lya[row] : 0.f;
+      const bool two_screens = kStatic ? bool(kFeat & kFeatTwoScreens) && kComp == 2 : (pg_dust && kComp == 2 && A.kappa_birth != nullptr);
       const float ntaub = two_screens ? -A.g_taub[row] : 0.f;
-      const bool absorbed = pg_dust && A.wnu != nullptr;   // energy balance: what the dust removes, summed over the axis
+      const bool absorbed = kStatic ? bool(kFeat & kFeatAbsorbed) : (pg_dust && A.wnu != nullptr);   // energy balance: what the dust removes, summed over the axis
       float e_abs = 0.f;
       // redshift-shift range of this warp's real galaxies (padding rows follow the others)
       int mmin = orig >= 0 ? m : INT_MAX, mmax = orig >= 0 ? m : INT_MIN;
@@ -249,25 +268,23 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
             } else {
               tmem_ld_32x32b_x32(t_acc + sub * 32, v);
             }
-            const float4* kp = reinterpret_cast<const float4*>(A.kappa + i0);
             if constexpr (kComp == 2) {
               const float ca = A.g_ca[row], cb = A.g_cb[row];
               uint32_t u[32];
               tmem_ld_32x32b_x32(t_acc + kLch + sub * 32, u);
               tmem_ld_wait();
-              if (pg_dust && A.g_lya != nullptr && A.lya_bin >= i0 && A.lya_bin < i0 + 32) {
+              if (lya_on && A.lya_bin >= i0 && A.lya_bin < i0 + 32) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (i0 + j == A.lya_bin) v[j] = __float_as_uint(__uint_as_float(v[j]) + lya);
               }
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                float4 k4 = kKapS ? lds_f4(kap_saddr + (uint32_t)(i0 + 4 * j4) * 4u) : __ldg(kp + j4);
-                if (pg_dust && dust_pg) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
-                                             __ldg(reinterpret_cast<const float4*>(A.dust_l2 + i0) + j4), slope, ampl);
+                float4 k4 = epi_tab4<kTabS>(A.kappa, T.kappa, i0, j4);
+                if (pg_dust && dust_pg) k4 = dust_shape(k4, epi_tab4<kTabS>(A.dust_d0, T.d0, i0, j4), epi_tab4<kTabS>(A.dust_l2, T.l2, i0, j4), slope, ampl);
                 if (two_screens) {   // young: birth cloud + ISM, old: ISM only (both components are attenuated)
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(A.kappa_birth + i0) + j4);
-                  const float4 w4 = absorbed ? __ldg(reinterpret_cast<const float4*>(A.wnu + i0) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  const float4 b4 = epi_tab4<kTabS>(A.kappa_birth, T.kappa_birth, i0, j4);
+                  const float4 w4 = absorbed ? epi_tab4<kTabS>(A.wnu, T.wnu, i0, j4) : make_float4(0.f, 0.f, 0.f, 0.f);
                   float e4 = 0.f;
 #define SB2_TS(q, K, B, W) { const float yo = ntaut * (K), yy = fmaf(ntaub, (B), yo), To = ex2_approx(yo), Ty = ex2_approx(yy); \
                              const float vy = ca * __uint_as_float(v[4 * j4 + q]), vo = cb * __uint_as_float(u[4 * j4 + q]); \
@@ -283,7 +300,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
                 s[4 * j4 + 2] = ca * (__uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z)) + cb * __uint_as_float(u[4 * j4 + 2]);
                 s[4 * j4 + 3] = ca * (__uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w)) + cb * __uint_as_float(u[4 * j4 + 3]);
                 if (absorbed) {
-                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.wnu + i0) + j4);
+                  const float4 w4 = epi_tab4<kTabS>(A.wnu, T.wnu, i0, j4);
                   float e4 = ca * __uint_as_float(v[4 * j4 + 0]) * one_minus_ex2(ntaut * k4.x, ex2_approx(ntaut * k4.x)) * w4.x;
                   e4 = fmaf(ca * __uint_as_float(v[4 * j4 + 1]) * one_minus_ex2(ntaut * k4.y, ex2_approx(ntaut * k4.y)), w4.y, e4);
                   e4 = fmaf(ca * __uint_as_float(v[4 * j4 + 2]) * one_minus_ex2(ntaut * k4.z, ex2_approx(ntaut * k4.z)), w4.z, e4);
@@ -293,7 +310,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               }
             } else {
               tmem_ld_wait();
-              if (pg_dust && A.g_lya != nullptr && A.lya_bin >= i0 && A.lya_bin < i0 + 32) {
+              if (lya_on && A.lya_bin >= i0 && A.lya_bin < i0 + 32) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (i0 + j == A.lya_bin) v[j] = __float_as_uint(__uint_as_float(v[j]) + lya);
@@ -304,15 +321,14 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               } else
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {  // ca goes into the final scale
-                float4 k4 = kKapS ? lds_f4(kap_saddr + (uint32_t)(i0 + 4 * j4) * 4u) : __ldg(kp + j4);
-                if (pg_dust && dust_pg) k4 = dust_shape(k4, __ldg(reinterpret_cast<const float4*>(A.dust_d0 + i0) + j4),
-                                             __ldg(reinterpret_cast<const float4*>(A.dust_l2 + i0) + j4), slope, ampl);
+                float4 k4 = epi_tab4<kTabS>(A.kappa, T.kappa, i0, j4);
+                if (pg_dust && dust_pg) k4 = dust_shape(k4, epi_tab4<kTabS>(A.dust_d0, T.d0, i0, j4), epi_tab4<kTabS>(A.dust_l2, T.l2, i0, j4), slope, ampl);
                 s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * ex2_approx(ntaut * k4.x);
                 s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y);
                 s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z);
                 s[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w);
                 if (absorbed) {   // (the lone component's coefficient is applied with the final scale, like the fluxes')
-                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.wnu + i0) + j4);
+                  const float4 w4 = epi_tab4<kTabS>(A.wnu, T.wnu, i0, j4);
                   float e4 = __uint_as_float(v[4 * j4 + 0]) * one_minus_ex2(ntaut * k4.x, ex2_approx(ntaut * k4.x)) * w4.x;
                   e4 = fmaf(__uint_as_float(v[4 * j4 + 1]) * one_minus_ex2(ntaut * k4.y, ex2_approx(ntaut * k4.y)), w4.y, e4);
                   e4 = fmaf(__uint_as_float(v[4 * j4 + 2]) * one_minus_ex2(ntaut * k4.z, ex2_approx(ntaut * k4.z)), w4.z, e4);
