@@ -199,7 +199,10 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* params, float* flux_bas
  * wall-clock `pipeline_time` attribute, library.py:2617-2622.)                                   */
 int sb2_last_stage_ms(sb2_model* m, float* out3);
 
-/* Same, with HOST buffers: copies parameters in, runs, copies results out (synchronous). */
+/* Same, with HOST buffers: copies parameters in, runs, copies results out (synchronous).  With spec_out (host float32
+ * [n][n_lam]: Pipeline.get_observed_spectra kept for the library, src/synference/library.py:4887-4919 / :4610-4617) the batch
+ * is walked in slices through two device buffers, so that the 4*n_lam bytes per galaxy leaving the device overlap the kernels
+ * of the next slice (pinned spec_out for real overlap).                                                              */
 int sb2_synth_photometry_host(sb2_model* m, const sb2_params* params, float* flux_base, double* flux_scaled,
                               float* spec_out);
 

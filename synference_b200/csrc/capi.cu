@@ -230,6 +230,9 @@ struct sb2_model {
   // two staging slots, so the copies of one batch overlap the kernels of the next (sb2_synth_photometry_host_submit)
   double* stage_params[2] = {nullptr, nullptr};  // redshift | log_mass | tau_v | zd_value | zd_sigma | ca | cb | sfh rows
   float* stage_params32[2] = {nullptr, nullptr}; // the same arrays as float32 (host_f32 transport), widened on the device
+  float* stage_spec[2] = {nullptr, nullptr};     // full-wavelength output of one slice (host entry with spec_out), allocated on first use
+  long long stage_spec_rows = 0;
+  cudaEvent_t ev_spec[2] = {nullptr, nullptr};   // slice's spectra are on the host
   float* stage_flux[2] = {nullptr, nullptr};
   double* stage_flux64[2] = {nullptr, nullptr};
   cudaEvent_t ev_slot[2] = {nullptr, nullptr};   // slot's results are on the host
@@ -279,13 +282,15 @@ int sb2_model_destroy(sb2_model* m) {
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
                   m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params[0],
                   m->stage_params[1], m->stage_flux[0], m->stage_flux[1], m->stage_flux64[0], m->stage_flux64[1], m->sf, m->s0, m->s1,
-                  m->stage_params32[0], m->stage_params32[1]};
+                  m->stage_params32[0], m->stage_params32[1], m->stage_spec[0], m->stage_spec[1]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : m->ev)
     if (e) cudaEventDestroy(e);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     if (m->ev_slot[i]) cudaEventDestroy(m->ev_slot[i]);
+    if (m->ev_spec[i]) cudaEventDestroy(m->ev_spec[i]);
+  }
   for (int i = 0; i < 8; ++i) {
     if (m->ev_in[i]) cudaEventDestroy(m->ev_in[i]);
     if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
@@ -945,9 +950,84 @@ int sb2_synth_photometry_host_wait(sb2_model* m, int slot) {
   return SB2_OK;
 }
 
+// Host entry with full-wavelength output (cfg 5's write path, library.py:4887-4919): 4 n_lam bytes per galaxy leave the
+// device, so the batch is walked in slices of kSpecSlice galaxies through TWO device buffers -- the device-to-host copy of
+// one slice's spectra (pinned destination for real overlap) runs beside the kernels of the next.
+namespace {
+constexpr long long kSpecSlice = 32768;
+
+int host_with_spectra(sb2_model* m, const sb2_params* p, float* flux_base, double* flux_scaled, float* spec_out) {
+  int rc = check_params(m, p);
+  if (rc != SB2_OK) return rc;
+  if (p->host_f32) return fail(SB2_ERR_INVALID, "host_f32 transport is not available together with spec_out");
+  CU_TRY(cudaSetDevice(m->device));
+  for (int s = 0; s < 2; ++s) {
+    rc = sb2_synth_photometry_host_wait(m, s);     // the staging areas below are shared with the photometry-only entry
+    if (rc != SB2_OK) return rc;
+  }
+  const long long n = p->n, rows = std::min<long long>(kSpecSlice, m->cap);
+  const int nf = m->d.n_filt, nl = m->d.n_lam;
+  if (m->stage_spec_rows < rows) {
+    for (int s = 0; s < 2; ++s) {
+      if (m->stage_spec[s]) cudaFree(m->stage_spec[s]);
+      m->stage_spec[s] = nullptr;
+      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&m->stage_spec[s]), (size_t)rows * nl * sizeof(float)));
+      if (!m->ev_spec[s]) CU_TRY(cudaEventCreateWithFlags(&m->ev_spec[s], cudaEventDisableTiming));
+    }
+    m->stage_spec_rows = rows;
+  }
+  constexpr int kNA = 12;
+  const double* src[kNA] = {p->redshift, p->log_mass, p->tau_v, p->zd_value, p->zd_sigma, p->coef_att, p->coef_unatt,
+                            p->dust_slope, p->dust_ampl, p->fesc_lya, p->tau_v_birth, p->sfh_rows};
+  bool used[2] = {false, false};
+  int k = 0;
+  for (long long a = 0; a < n; a += rows, ++k) {
+    const long long b = std::min(n, a + rows), cnt = b - a;
+    const int s = k & 1;
+    if (used[s]) CU_TRY(cudaEventSynchronize(m->ev_spec[s]));   // slot's previous spectra have left the device
+    double* base = m->stage_params[s];
+    sb2_params dp = *p;
+    dp.n = cnt;
+    double* dev[kNA];
+    for (int i = 0; i < kNA; ++i) {
+      const size_t w = (i == kNA - 1) ? (size_t)p->sfh_stride : 1;
+      dev[i] = src[i] ? base : nullptr;
+      if (src[i]) {
+        CU_TRY(cudaMemcpyAsync(base, src[i] + a * w, (size_t)cnt * w * sizeof(double), cudaMemcpyHostToDevice, m->st_h2d));
+        base += (size_t)cnt * w;
+      }
+    }
+    CU_TRY(cudaEventRecord(m->ev_in[s], m->st_h2d));
+    CU_TRY(cudaStreamWaitEvent(m->st_comp, m->ev_in[s], 0));
+    dp.redshift = dev[0]; dp.log_mass = dev[1]; dp.tau_v = dev[2]; dp.zd_value = dev[3]; dp.zd_sigma = dev[4];
+    dp.coef_att = dev[5]; dp.coef_unatt = dev[6]; dp.dust_slope = dev[7]; dp.dust_ampl = dev[8]; dp.fesc_lya = dev[9];
+    dp.tau_v_birth = dev[10]; dp.sfh_rows = dev[11];
+    rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux[s] : nullptr, flux_scaled ? m->stage_flux64[s] : nullptr,
+                              m->stage_spec[s], m->st_comp);
+    if (rc != SB2_OK) {
+      const std::string msg = g_err;
+      cudaStreamSynchronize(m->st_h2d); cudaStreamSynchronize(m->st_comp); cudaStreamSynchronize(m->st_d2h);
+      g_err = msg;
+      return rc;
+    }
+    CU_TRY(cudaEventRecord(m->ev_done[s], m->st_comp));
+    CU_TRY(cudaStreamWaitEvent(m->st_d2h, m->ev_done[s], 0));
+    CU_TRY(cudaMemcpyAsync(spec_out + (size_t)a * nl, m->stage_spec[s], (size_t)cnt * nl * sizeof(float), cudaMemcpyDeviceToHost, m->st_d2h));
+    if (flux_base) CU_TRY(cudaMemcpyAsync(flux_base + (size_t)a * nf, m->stage_flux[s], (size_t)cnt * nf * 4, cudaMemcpyDeviceToHost, m->st_d2h));
+    if (flux_scaled) CU_TRY(cudaMemcpyAsync(flux_scaled + (size_t)a * nf, m->stage_flux64[s], (size_t)cnt * nf * 8, cudaMemcpyDeviceToHost, m->st_d2h));
+    CU_TRY(cudaEventRecord(m->ev_spec[s], m->st_d2h));
+    used[s] = true;
+    // the next slice must not overwrite this slot's parameter staging before its kernels have read it: slot s is reused two
+    // slices later, after ev_spec[s] (recorded behind ev_done[s]) has been waited for above
+  }
+  CU_TRY(cudaStreamSynchronize(m->st_d2h));
+  return SB2_OK;
+}
+}  // namespace
+
 int sb2_synth_photometry_host(sb2_model* m, const sb2_params* p, float* flux_base, double* flux_scaled,
                               float* spec_out) {
-  if (spec_out) return fail(SB2_ERR_INVALID, "spec_out is only supported through the device entry point");
+  if (spec_out) return host_with_spectra(m, p, flux_base, flux_scaled, spec_out);
   int rc = sb2_synth_photometry_host_submit(m, p, flux_base, flux_scaled, 0);
   if (rc != SB2_OK) return rc;
   return sb2_synth_photometry_host_wait(m, 0);

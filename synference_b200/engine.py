@@ -462,20 +462,25 @@ class SynthEngine:
         rc = self.lib.sb2_synth_photometry(self._h, C.byref(s), dp(flux_base), dp(flux_scaled), dp(spectra), st)
         _capi.check(rc, "sb2_synth_photometry")
 
-    def spectra(self, params: GalaxyParams):
-        """Observed-frame f_nu [nJy] at base mass on the rest-frame axis, ``(N, n_lam)`` float32 (host)."""
-        import torch
+    def spectra(self, params: GalaxyParams, out=None, photometry_out=None):
+        """Observed-frame f_nu [nJy] at base mass on the rest-frame axis, ``(N, n_lam)`` float32 (host), through the host entry
+        of the C ABI (``sb2_synth_photometry_host`` with ``spec_out``): the batch is walked in slices whose device-to-host
+        copies overlap the kernels of the next slice.  ``out`` may be a pinned array (real overlap; e.g. a
+        ``torch.empty(...).pin_memory().numpy()`` view) -- this is cfg 5's write path (``library.py:4887-4919``);
+        ``photometry_out`` ``(N, n_filt)`` float32 receives the base-mass photometry of the same pass."""
         n = len(params)
-        out = np.empty((n, self.n_lam), dtype=np.float32)
-        dev = torch.device("cuda", self.device)
+        res = out if out is not None else np.empty((n, self.n_lam), dtype=np.float32)
+        assert res.flags.c_contiguous and res.shape == (n, self.n_lam) and res.dtype == np.float32
+        if photometry_out is not None:
+            assert photometry_out.flags.c_contiguous and photometry_out.shape == (n, self.n_filt) and photometry_out.dtype == np.float32
         for a in range(0, n, self.max_batch):
             b = min(n, a + self.max_batch)
-            dpar = self.to_device(params.slice(slice(a, b)))
-            spec = torch.empty((b - a, self.n_lam), dtype=torch.float32, device=dev)
-            flux = torch.empty((b - a, self.n_filt), dtype=torch.float32, device=dev)
-            self.photometry_device(dpar, flux_base=flux, spectra=spec)
-            out[a:b] = spec.cpu().numpy()
-        return out
+            keep = []
+            s = self._fill(params.slice(slice(a, b)), self._host_ptr_factory(keep))
+            fp = None if photometry_out is None else photometry_out[a:b].ctypes.data
+            rc = self.lib.sb2_synth_photometry_host(self._h, C.byref(s), fp, None, res[a:b].ctypes.data)
+            _capi.check(rc, "sb2_synth_photometry_host")
+        return res
 
     def weights(self, params: GalaxyParams):
         """SFZH weights ``(N, n_age*n_z)`` float64, k = iz*n_age + ia (parity hook)."""

@@ -18,7 +18,7 @@ import numpy as np
 from . import _capi
 from .units import has_units, strip_units
 
-__all__ = ["SpectrumResampler", "transform_spectrum", "create_feature_array_from_raw_spectra"]
+__all__ = ["SpectrumResampler", "transform_spectrum", "create_feature_array_from_raw_spectra", "write_spectral_library"]
 
 
 def _um(x):
@@ -101,6 +101,20 @@ class SpectrumResampler:
         _capi.check(self.lib.sb2_resample_spectra_host(self._h, sp.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p),
                                                        sp.shape[0], out.ctypes.data_as(C.c_void_p)),
                     "sb2_resample_spectra_host")
+        return out
+
+    def transform_into(self, spectra, redshift, out):
+        """Device form without allocations: CUDA tensors ``spectra`` (n, n_lam) float32 and ``redshift`` (n,) float64 in,
+        pixels written to the caller's CUDA tensor ``out`` (n, n_px) float32 on the current stream."""
+        import torch
+        assert spectra.is_cuda and out.is_cuda and redshift.is_cuda
+        assert spectra.dtype == torch.float32 and out.dtype == torch.float32 and redshift.dtype == torch.float64
+        assert spectra.is_contiguous() and out.is_contiguous() and redshift.is_contiguous()
+        n = spectra.shape[0]
+        assert spectra.shape == (n, self.n_lam) and out.shape == (n, self.n_px) and redshift.shape == (n,)
+        st = torch.cuda.current_stream(spectra.device).cuda_stream
+        _capi.check(self.lib.sb2_resample_spectra(self._h, C.c_void_p(spectra.data_ptr()), C.c_void_p(redshift.data_ptr()), n,
+                                                  C.c_void_p(out.data_ptr()), C.c_void_p(st)), "sb2_resample_spectra")
         return out
 
     def last_ms(self) -> float:
@@ -190,3 +204,102 @@ def create_feature_array_from_raw_spectra(spectra, wavelengths, parameter_array,
         cols.append(params[:, names.index(name)][:, None])
     feature_array = np.concatenate([feat] + cols, axis=1) if cols else feat
     return feature_array, ["spectra"] + extra_features, wavs
+
+
+def write_spectral_library(engine, resampler, params, out_dir=None, name="spectral_library", batch_size=65536, device=None,
+                           keep_in_memory=False):
+    """cfg 5's write path (``library.py:4887-4919``, ``:4610-4617``): spectra + photometry of a population, batch by batch.
+
+    Each batch runs the whole chain on the device -- contraction kernel with its full-wavelength output kept in HBM, then the
+    instrument-resolution resampling (``resampler``) -- and only the ``n_px`` pixels and ``n_filt`` fluxes per galaxy leave it:
+    they are copied into one of TWO pinned host buffers on a side stream while the next batch is being synthesised, and a
+    writer thread stores each filled buffer as a pair of uncompressed shards ``<name>_<i>_start<row>.spectra.npy`` (n, n_px)
+    float32 and ``....photometry.npy`` (n, n_filt) float32.  Returns ``dict(shards=[paths], seconds=..., galaxies_per_s=..., bytes=...,
+    spectra=..., photometry=...)`` (the arrays only with ``keep_in_memory``; ``out_dir=None`` skips the files)."""
+    import os
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    import torch
+    dev = torch.device("cuda", engine.device if device is None else device)
+    n = len(params)
+    bs = int(min(batch_size, engine.max_batch))
+    n_px, n_filt = resampler.n_px, engine.n_filt
+    # pinned and device buffers are kept on the engine between calls (pinning 2 x bs x n_px x 4 B costs more than a batch)
+    key = (str(dev), bs, n_px, n_filt, engine.n_lam)
+    ws = getattr(engine, "_spectral_ws", None)
+    if ws is None or ws["key"] != key:
+        ws = engine._spectral_ws = dict(
+            key=key,
+            pin_px=[torch.empty((bs, n_px), dtype=torch.float32).pin_memory() for _ in range(2)],
+            pin_ph=[torch.empty((bs, n_filt), dtype=torch.float32).pin_memory() for _ in range(2)],
+            spec=torch.empty((bs, engine.n_lam), dtype=torch.float32, device=dev),
+            flux=[torch.empty((bs, n_filt), dtype=torch.float32, device=dev) for _ in range(2)],
+            pix=[torch.empty((bs, n_px), dtype=torch.float32, device=dev) for _ in range(2)],
+            side=torch.cuda.Stream(device=dev))
+    pin_px, pin_ph, spec, flux, pix, side = ws["pin_px"], ws["pin_ph"], ws["spec"], ws["flux"], ws["pix"], ws["side"]
+    done = [torch.cuda.Event(), torch.cuda.Event()]          # slot's device buffers are free again (copy-out finished)
+    writer = ThreadPoolExecutor(max_workers=1) if out_dir is not None else None
+    if out_dir is not None:
+        os.makedirs(out_dir, exist_ok=True)
+    all_px = np.empty((n, n_px), dtype=np.float32) if keep_in_memory else None
+    all_ph = np.empty((n, n_filt), dtype=np.float32) if keep_in_memory else None
+    shards, pending, busy = [], [None, None], [False, False]
+
+    def store(slot, start, cnt, index):
+        px, ph = pin_px[slot][:cnt].numpy(), pin_ph[slot][:cnt].numpy()
+        if all_px is not None:
+            all_px[start:start + cnt], all_ph[start:start + cnt] = px, ph
+        if out_dir is not None:
+            # plain .npy files: an .npz member costs a CRC-32 pass (~1 GB/s on one core) on top of the write
+            path = os.path.join(out_dir, f"{name}_{index:05d}_start{start}.spectra.npy")
+            np.save(path, px)
+            np.save(path.replace(".spectra.npy", ".photometry.npy"), ph)
+            return path
+        return None
+
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    with torch.cuda.device(dev):
+        for i, a in enumerate(range(0, n, bs)):
+            b = min(n, a + bs)
+            cnt, slot = b - a, i & 1
+            if pending[slot] is not None:           # the pinned buffers of this slot must have been written out
+                shards.append(pending[slot].result())
+                pending[slot] = None
+            if busy[slot]:
+                torch.cuda.current_stream(dev).wait_event(done[slot])
+            dpar = engine.to_device(params.slice(slice(a, b)))
+            engine.photometry_device(dpar, flux_base=flux[slot][:cnt], spectra=spec[:cnt])
+            resampler.transform_into(spec[:cnt], dpar.tensors["redshift"], pix[slot][:cnt])
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                pin_px[slot][:cnt].copy_(pix[slot][:cnt], non_blocking=True)
+                pin_ph[slot][:cnt].copy_(flux[slot][:cnt], non_blocking=True)
+                done[slot].record()
+            busy[slot] = True
+            ev = done[slot]
+
+            def job(slot=slot, a=a, cnt=cnt, i=i, ev=ev):
+                ev.synchronize()
+                return store(slot, a, cnt, i)
+            pending[slot] = (writer.submit(job) if writer is not None else _Immediate(job))
+        for slot in (0, 1):
+            if pending[slot] is not None:
+                shards.append(pending[slot].result())
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    if writer is not None:
+        writer.shutdown()
+    shards = sorted(p for p in shards if p)
+    return dict(shards=shards, seconds=dt, galaxies_per_s=n / dt, bytes=int(n) * 4 * (n_px + n_filt), spectra=all_px, photometry=all_ph)
+
+
+class _Immediate:
+    def __init__(self, fn):
+        self._v = fn()
+
+    def result(self):
+        return self._v
+

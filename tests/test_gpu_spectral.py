@@ -190,3 +190,48 @@ def test_cfg5_chain_engine_spectra_to_prism_pixels_on_device():
     from tests.helpers import assert_flux_close
     assert_flux_close(flux.cpu().numpy(), want_flux)
     plan.close(); eng.close()
+
+
+def test_spectral_library_writer_and_host_spectra_entry(tmp_path):
+    """cfg 5's write path (library.py:4887-4919): write_spectral_library streams batches through the device chain into pinned
+    double buffers and uncompressed shards; the shards hold exactly what the one-shot device chain produces.  The host entry of
+    the C ABI with spec_out (slices through two device buffers) returns the same spectra as the device entry."""
+    import torch
+    from synference_b200.configs import make_workload
+    from synference_b200.engine import SynthEngine
+    from synference_b200.spectral import write_spectral_library
+    n = 700
+    w = make_workload("cfg2", n)
+    eng = SynthEngine(w.grid, w.emission_model, w.emission_key, w.filters, max_batch=4096)
+    lam_um = np.asarray(w.grid.lam) * 1e-4
+    ow = np.linspace(0.6, 5.3, 1000)
+    rw = np.linspace(0.55, 5.4, 80)
+    rr = 30.0 + 270.0 * ((rw - 0.55) / 4.85) ** 1.3
+    plan = SpectrumResampler(lam_um, ow, rw, rr)
+    dpar = eng.to_device(w.params)
+    spec = torch.empty((n, eng.n_lam), dtype=torch.float32, device="cuda")
+    flux = torch.empty((n, eng.n_filt), dtype=torch.float32, device="cuda")
+    eng.photometry_device(dpar, flux_base=flux, spectra=spec)
+    px = plan.transform(spec, dpar.tensors["redshift"]).cpu().numpy()
+    res = write_spectral_library(eng, plan, w.params, out_dir=str(tmp_path), name="lib", batch_size=256, keep_in_memory=True)
+    assert len(res["shards"]) == 3 and res["bytes"] == n * 4 * (1000 + eng.n_filt)
+    got_px, got_ph = np.empty_like(px), np.empty((n, eng.n_filt), dtype=np.float32)
+    for path in res["shards"]:
+        a = int(path.split("_start")[1].split(".")[0])
+        sp_, ph_ = np.load(path), np.load(path.replace(".spectra.npy", ".photometry.npy"))
+        got_px[a:a + sp_.shape[0]] = sp_
+        got_ph[a:a + ph_.shape[0]] = ph_
+    # a galaxy's result does not depend on what else is in its batch (chunks are handed out by index, sums in fixed order)
+    assert np.array_equal(got_px, px) and np.array_equal(got_ph, flux.cpu().numpy())
+    assert np.array_equal(res["spectra"], px)
+    # host entry with spec_out: pinned destination, photometry of the same pass
+    host_spec = torch.empty((n, eng.n_lam), dtype=torch.float32).pin_memory().numpy()
+    host_phot = np.empty((n, eng.n_filt), dtype=np.float32)
+    eng.spectra(w.params, out=host_spec, photometry_out=host_phot)
+    assert np.array_equal(host_spec, spec.cpu().numpy()) and np.array_equal(host_phot, flux.cpu().numpy())
+    big = make_workload("cfg2", 40000)                  # more than one 32768-galaxy slice of the host entry
+    sp = eng.spectra(big.params.slice(slice(0, 4096)))
+    eng2 = SynthEngine(big.grid, big.emission_model, big.emission_key, big.filters, max_batch=40000)
+    sp2 = eng2.spectra(big.params)
+    assert sp2.shape == (40000, eng.n_lam) and np.isfinite(sp2).all() and np.array_equal(sp2[:4096], sp)
+    plan.close(); eng.close(); eng2.close()
