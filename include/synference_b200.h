@@ -300,6 +300,22 @@ int sb2_empirical_noise(const double* flux, int64_t n, int32_t n_filt, const sb2
                         const double* draws, uint64_t seed, uint64_t epoch, double* out_flux, double* out_sigma,
                         void* stream);
 
+/* ---- filter integration on a GENERAL wavelength axis (fallback) ------------------------------------------------------------
+ * The fused epilogue needs grid and filters on one constant-R axis.  For models on the SPS grid's native axis (the
+ * reference's README and tests: README.md:100-102, tests/conftest.py:70,85) the spectra of a batch are written to device
+ * memory (sb2_synth_photometry with spec_out) and integrated here with the general semantics of
+ * Sed.get_photo_fnu -> Filter.apply_filter: every filter's OWN table (offsets[f] .. offsets[f+1] of
+ * filt_lam / filt_t, ascending wavelengths) interpolated linearly in the integration variable (variant 0: nu, 1: lambda)
+ * onto the observed abscissa, samples with T > 0 only, trapezoid of f T / x over trapezoid of T / x.                    */
+typedef struct sb2_filterset sb2_filterset;
+int sb2_filterset_create(int32_t n_filt, const int64_t* offsets, const double* filt_lam, const double* filt_t,
+                         const double* grid_lam, int32_t n_lam, int32_t variant, int device, sb2_filterset** out);
+int sb2_filterset_destroy(sb2_filterset* s);
+/* spectra: device float32 [n][n_lam] (spec_out); redshift / log_mass: device float64 [n] (log_mass may be NULL);
+ * flux_base device float32 [n][n_filt] and/or flux_scaled device float64 = float32(base) * 10^log_mass / base_mass.  */
+int sb2_filter_integrate(sb2_filterset* s, const float* spectra, const double* redshift, const double* log_mass, double base_mass,
+                         int64_t n, float* flux_base, double* flux_scaled, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

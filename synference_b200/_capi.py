@@ -21,6 +21,7 @@ EXPORTED_SYMBOLS = (
     "sb2_synth_photometry_host_submit", "sb2_synth_photometry_host_wait",
     "sb2_resampler_create", "sb2_resampler_destroy", "sb2_resample_spectra", "sb2_resample_spectra_host", "sb2_resample_last_ms",
     "sb2_empirical_noise", "sb2_depth_noise_features_sets", "sb2_kernel_launches",
+    "sb2_filterset_create", "sb2_filterset_destroy", "sb2_filter_integrate",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -108,6 +109,11 @@ def load():
     lib.sb2_last_error.restype = C.c_char_p
     lib.sb2_device_count.restype = C.c_int
     lib.sb2_kernel_launches.restype = C.c_longlong
+    lib.sb2_filterset_create.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int,
+                                         C.POINTER(C.c_void_p)]
+    lib.sb2_filterset_destroy.argtypes = [C.c_void_p]
+    lib.sb2_filter_integrate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]
     lib.sb2_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_void_p)]
     lib.sb2_model_destroy.argtypes = [C.c_void_p]
     lib.sb2_wait_debug.argtypes = [C.c_void_p]

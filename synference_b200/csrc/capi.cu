@@ -16,6 +16,7 @@
 #include "../../include/synference_b200.h"
 #include "noise_kernel.cuh"
 #include "empirical_kernel.cuh"
+#include "general_filter_kernel.cuh"
 #include "prep_kernel.cuh"
 #include "resample_kernel.cuh"
 #include "synth_kernel.cuh"
@@ -452,6 +453,11 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   AL(g_mscale, np * 8); AL(g_trunc, np * 4); AL(zpow, np * 13 * 8);
   // synth3: bracket-grouped batches whose two metallicities' columns fit the TMEM weights region
   m->s3_ok = m->wd_stride > 0 && m->wd_stride <= sb2::kS3WCols && d->n_age <= 64 && d->n_age_pad % 8 == 0 && !m->sw.no_synth3;
+  if (m->s3_ok) {   // ... and whose per-wavelength tables leave room for the operand ring in shared memory (long native axes do not)
+    const int c = d->n_comp, kap_len = d->n_chunk * (sb2::kBN / c), uvl = (int)(d->filt_uv_len + 2 * sb2::kUvPad * d->n_filt);
+    const int feat = (d->dust_d0 ? sb2::kFeatDustShape : 0) | (d->kappa_birth ? sb2::kFeatTwoScreens : 0) | (d->dust_wnu ? sb2::kFeatAbsorbed : 0);
+    if (sb2::synth3_smem_bytes(c == 1 ? 96 : 128, 3, d->n_age, uvl, kap_len, true, feat) > (size_t)prop.sharedMemPerBlockOptin) m->s3_ok = false;
+  }
   if (m->s3_ok) { AL(sf, (np / 128) * (size_t)d->n_age * 128 * 8); AL(s0, np * 8); AL(s1, np * 8); }
   m->cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, m->cub_bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)m->cap);
@@ -1428,6 +1434,62 @@ int sb2_empirical_noise(const double* flux, int64_t n, int32_t n_filt, const sb2
   e = cudaGetLastError();
   cudaFreeAsync(dm, st);
   if (e != cudaSuccess) return fail(SB2_ERR_CUDA, cudaGetErrorString(e));
+  return SB2_OK;
+}
+
+// ---- filter integration on a general wavelength axis ----------------------------------------------------------------
+struct sb2_filterset {
+  int device = 0, n_sm = 148, n_filt = 0, n_lam = 0, variant = 0;
+  double* lam = nullptr; long long* off = nullptr; double* f_lam = nullptr; double* f_t = nullptr;
+};
+
+int sb2_filterset_create(int32_t n_filt, const int64_t* offsets, const double* filt_lam, const double* filt_t,
+                         const double* grid_lam, int32_t n_lam, int32_t variant, int device, sb2_filterset** out) {
+  if (!offsets || !filt_lam || !filt_t || !grid_lam || !out || n_filt < 1 || n_lam < 2) return fail(SB2_ERR_INVALID, "bad argument");
+  for (int f = 0; f < n_filt; ++f) {
+    if (offsets[f + 1] - offsets[f] < 2) return fail(SB2_ERR_INVALID, "a filter table needs at least two samples");
+    for (int64_t i = offsets[f] + 1; i < offsets[f + 1]; ++i)
+      if (!(filt_lam[i] >= filt_lam[i - 1])) return fail(SB2_ERR_INVALID, "filter wavelengths must not decrease");
+  }
+  for (int i = 1; i < n_lam; ++i)
+    if (!(grid_lam[i] > grid_lam[i - 1])) return fail(SB2_ERR_INVALID, "the wavelength axis must increase");
+  CU_TRY(cudaSetDevice(device));
+  sb2_filterset* s = new sb2_filterset();
+  s->device = device; s->n_filt = n_filt; s->n_lam = n_lam; s->variant = variant;
+  cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, device);
+  std::vector<long long> off(offsets, offsets + n_filt + 1);
+  int rc = upload(&s->lam, grid_lam, (size_t)n_lam);
+  if (rc == SB2_OK) rc = upload(&s->off, off.data(), off.size());
+  if (rc == SB2_OK) rc = upload(&s->f_lam, filt_lam, (size_t)offsets[n_filt]);
+  if (rc == SB2_OK) rc = upload(&s->f_t, filt_t, (size_t)offsets[n_filt]);
+  if (rc != SB2_OK) { sb2_filterset_destroy(s); return rc; }
+  *out = s;
+  return SB2_OK;
+}
+
+int sb2_filterset_destroy(sb2_filterset* s) {
+  if (!s) return SB2_OK;
+  cudaSetDevice(s->device);
+  for (void* p : {(void*)s->lam, (void*)s->off, (void*)s->f_lam, (void*)s->f_t}) if (p) cudaFree(p);
+  delete s;
+  return SB2_OK;
+}
+
+int sb2_filter_integrate(sb2_filterset* s, const float* spectra, const double* redshift, const double* log_mass, double base_mass,
+                         int64_t n, float* flux_base, double* flux_scaled, void* stream) {
+  if (!s || !spectra || !redshift || n < 0) return fail(SB2_ERR_INVALID, "bad argument");
+  if (!flux_base && !flux_scaled) return fail(SB2_ERR_INVALID, "no output requested");
+  if (n == 0) return SB2_OK;
+  CU_TRY(cudaSetDevice(s->device));
+  sb2::GeneralFilterArgs a{};
+  a.spectra = spectra; a.redshift = redshift; a.log_mass = log_mass; a.base_mass = base_mass; a.n = n;
+  a.n_lam = s->n_lam; a.n_filt = s->n_filt; a.variant = s->variant; a.lam = s->lam; a.off = s->off; a.f_lam = s->f_lam; a.f_t = s->f_t;
+  a.flux_base = flux_base; a.flux_scaled = flux_scaled;
+  const long long warps = (long long)n * s->n_filt;
+  const long long blocks = std::min<long long>((warps + 7) / 8, (long long)s->n_sm * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  sb2::general_filter_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  STAGE_CHECK("general_filter_kernel", st);
   return SB2_OK;
 }
 

@@ -137,7 +137,19 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
     """All float64 host-side derivations behind ``sb2_model_desc`` (kept as numpy arrays)."""
     lam = np.asarray(grid.lam, dtype=np.float64)
     n_lam = lam.size
-    q = geometric_ratio(lam)
+    try:
+        q = geometric_ratio(lam)
+        general = None
+    except ValueError:
+        # not a constant-R axis (the reference's README / tests keep the grid's native one): the contraction kernel then
+        # only writes spectra (a dummy full-axis "filter" drives it) and the filters are integrated from those spectra by
+        # general_filter_kernel with the reference's general semantics -- slower, same results
+        if np.any(np.diff(lam) <= 0):
+            raise ValueError("the wavelength axis must increase")
+        q = 1.0e30
+        off = np.concatenate([[0], np.cumsum([len(f.lam) for f in filters])]).astype(np.int64)
+        general = dict(off=off, lam=np.concatenate([np.asarray(f.lam, dtype=np.float64) for f in filters]),
+                       t=np.concatenate([np.asarray(f.t, dtype=np.float64) for f in filters]), n_filt=len(filters))
     att, un = emission_model.recipe(emission_key)
     has_att, has_un = bool(np.any(att != 0)), bool(np.any(un != 0))
     dust = emission_model.dust_curve
@@ -196,7 +208,10 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         raise ValueError("variant must be 'nu' or 'lam'")
     c_left, c_right = ((q - 1) / 2, (1 - 1 / q) / 2) if variant == "nu" else ((1 - 1 / q) / 2, (q - 1) / 2)
     lo_l, hi_l, off_l, su_l, sdv_l, uv = [], [], [], [], [], []
-    for f in filters:
+    if general is not None:
+        lo_l, hi_l, off_l, su_l, sdv_l = [1], [2], [0], [1.0], [1.0]      # a two-bin placeholder: spec_out multiplies every chunk
+        uv = [np.zeros((2 - 1 + 4, 2))]
+    for f in (filters if general is None else []):
         if f.lam.shape != lam.shape or np.max(np.abs(f.lam / lam - 1)) > 1e-12:
             raise ValueError(f"filter {f.filter_code} is not tabulated on the grid's wavelength axis; "
                              "use FilterCollection.resample_filters(new_lam=grid.lam)")
@@ -233,6 +248,7 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         # a lone component is the kernel's component A whichever grid it came from: its per-galaxy coefficient
         # travels as coef_att (SynthEngine._fill)
         single_is_unatt=(n_comp == 1 and not has_att),
+        general=general,
     )
     if igm:
         laf, dla = (igm if isinstance(igm, tuple) else (_igm.INOUE14_LAF, _igm.INOUE14_DLA))
@@ -240,6 +256,9 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
     else:
         tables["igm"] = None
     tables.update(dust_wnu=None, dust_g=None, dust_duv=None, dust_m_len=0)
+    if general is not None and getattr(emission_model, "has_dust_emission", lambda k: False)(emission_key) and kap is not None:
+        raise NotImplementedError("dust emission (spectrum 'total') on a non-constant-R wavelength axis: resample grid and "
+                                  "filters with generate_constant_R first")
     if getattr(emission_model, "has_dust_emission", lambda k: False)(emission_key) and kap is not None and not dust_free:
         tables.update(_dust_emission_tables(emission_model.dust_emission, lam, n_chunk * lch, uv, lo_l, hi_l, off_l,
                                             tables["igm"]["n_blue"] if tables["igm"] is not None else 0))
@@ -271,7 +290,9 @@ class SynthEngine:
         self.tables = t = build_tables(grid, emission_model, emission_key, filters, cosmo, igm, variant)
         self.tables_lam = np.asarray(grid.lam, dtype=np.float64)
         self.filter_codes = list(filters.filter_codes)
-        self.n_filt, self.n_lam, self.n_comp = t["n_filt"], t["n_lam"], t["n_comp"]
+        self.general = t["general"] is not None
+        self.n_filt, self.n_lam, self.n_comp = (t["general"]["n_filt"] if self.general else t["n_filt"]), t["n_lam"], t["n_comp"]
+        self.variant = variant
         self.k = t["n_age"] * t["n_z"]
         self.k_pad = t["k_pad"]
         self.max_batch = int(max_batch)
@@ -322,9 +343,20 @@ class SynthEngine:
         handle = C.c_void_p()
         _capi.check(self.lib.sb2_model_create(C.byref(d), self.device, C.byref(handle)), "sb2_model_create")
         self._h = handle
+        self._fs = None
+        if self.general:
+            g = t["general"]
+            fs = C.c_void_p()
+            _capi.check(self.lib.sb2_filterset_create(int(g["n_filt"]), g["off"].ctypes.data, g["lam"].ctypes.data, g["t"].ctypes.data,
+                                                      self.tables_lam.ctypes.data, int(self.n_lam), 0 if variant == "nu" else 1,
+                                                      self.device, C.byref(fs)), "sb2_filterset_create")
+            self._fs = fs
         del keep
 
     def close(self):
+        if getattr(self, "_fs", None):
+            self.lib.sb2_filterset_destroy(self._fs)
+            self._fs = None
         if getattr(self, "_h", None):
             self.lib.sb2_model_destroy(self._h)
             self._h = None
@@ -395,6 +427,8 @@ class SynthEngine:
         host-to-device bytes, exact for float32 draws (use ``max_age_from_z`` so the SFH rows hold the raw draws)."""
         n = len(params)
         res = out if out is not None else np.empty((n, self.n_filt), dtype=np.float64 if scaled else np.float32)
+        if self.general:
+            return self._photometry_general(params, scaled, res)
         pending = []
         for i, a in enumerate(range(0, n, self.max_batch)):
             b = min(n, a + self.max_batch)
@@ -410,6 +444,9 @@ class SynthEngine:
         host array the results land in (pinned memory gives real copy/compute overlap)."""
         assert out.flags.c_contiguous and out.shape == (len(params), self.n_filt)
         assert out.dtype == (np.float64 if scaled else np.float32)
+        if self.general:      # the fallback path has no staging slots: run it now
+            self._photometry_general(params, scaled, out)
+            return (-1, [out])
         keep = [out]
         if transport not in ("f64", "f32"):
             raise ValueError("transport must be 'f64' or 'f32'")
@@ -421,6 +458,8 @@ class SynthEngine:
         return (int(slot), keep)
 
     def wait(self, ticket):
+        if ticket[0] < 0:
+            return
         _capi.check(self.lib.sb2_synth_photometry_host_wait(self._h, ticket[0]), "sb2_synth_photometry_host_wait")
 
     # ---- device entry (torch tensors stay on the GPU) ------------------------------------------
@@ -455,12 +494,52 @@ class SynthEngine:
         import torch
         p = dparams.host
         t = dparams.tensors
+        if self.general:
+            return self._device_general(dparams, flux_base, flux_scaled, spectra)
         s = self._fill(p, lambda a: None)
         self._set_device_ptrs(s, t)
         st = torch.cuda.current_stream(self.device).cuda_stream
         dp = lambda x: None if x is None else x.data_ptr()  # noqa: E731
         rc = self.lib.sb2_synth_photometry(self._h, C.byref(s), dp(flux_base), dp(flux_scaled), dp(spectra), st)
         _capi.check(rc, "sb2_synth_photometry")
+
+    # ---- general (non-constant-R) wavelength axis: spectra to HBM, then general_filter_kernel -----------------------
+    def _general_rows(self):
+        return int(max(256, min(32768, self.max_batch, (1 << 30) // (4 * self.n_lam))))
+
+    def _device_general(self, dparams, flux_base=None, flux_scaled=None, spectra=None):
+        import torch
+        p, t = dparams.host, dparams.tensors
+        n = len(p)
+        dev = t["redshift"].device
+        rows = n if spectra is not None else self._general_rows()
+        buf = spectra if spectra is not None else torch.empty((min(rows, n), self.n_lam), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        dp = lambda x: None if x is None else x.data_ptr()  # noqa: E731
+        for a in range(0, n, rows):
+            b = min(n, a + rows)
+            sub = DeviceParams(p.slice(slice(a, b)), {k: (None if v is None else v[a:b]) for k, v in t.items()})
+            s = self._fill(sub.host, lambda x: None)
+            self._set_device_ptrs(s, sub.tensors)
+            sp = buf[a:b] if spectra is not None else buf[:b - a]
+            _capi.check(self.lib.sb2_synth_photometry(self._h, C.byref(s), None, None, sp.data_ptr(), st), "sb2_synth_photometry")
+            if flux_base is not None or flux_scaled is not None:
+                _capi.check(self.lib.sb2_filter_integrate(
+                    self._fs, sp.data_ptr(), sub.tensors["redshift"].data_ptr(), dp(sub.tensors.get("log_mass")), self.base_mass,
+                    b - a, dp(None if flux_base is None else flux_base[a:b]), dp(None if flux_scaled is None else flux_scaled[a:b]), st),
+                    "sb2_filter_integrate")
+
+    def _photometry_general(self, params, scaled, res):
+        import torch
+        n = len(params)
+        dev = torch.device("cuda", self.device)
+        for a in range(0, n, self.max_batch):
+            b = min(n, a + self.max_batch)
+            dpar = self.to_device(params.slice(slice(a, b)))
+            out = torch.empty((b - a, self.n_filt), dtype=torch.float64 if scaled else torch.float32, device=dev)
+            self._device_general(dpar, flux_base=None if scaled else out, flux_scaled=out if scaled else None)
+            res[a:b] = out.cpu().numpy()
+        return res
 
     def spectra(self, params: GalaxyParams, out=None, photometry_out=None):
         """Observed-frame f_nu [nJy] at base mass on the rest-frame axis, ``(N, n_lam)`` float32 (host), through the host entry
@@ -471,6 +550,9 @@ class SynthEngine:
         n = len(params)
         res = out if out is not None else np.empty((n, self.n_lam), dtype=np.float32)
         assert res.flags.c_contiguous and res.shape == (n, self.n_lam) and res.dtype == np.float32
+        if self.general and photometry_out is not None:
+            photometry_out[...] = self.photometry(params, scaled=False)
+            photometry_out = None
         if photometry_out is not None:
             assert photometry_out.flags.c_contiguous and photometry_out.shape == (n, self.n_filt) and photometry_out.dtype == np.float32
         for a in range(0, n, self.max_batch):
