@@ -169,13 +169,13 @@ __global__ void group_scatter_kernel(const unsigned* __restrict__ keys_sorted, c
 
 // Experiment / fallback switches (environment), read ONCE when a model is created -- never on the per-call path.
 struct Switches {
-  bool n256 = false, cta_pair = false, libm = false, weights_v1 = false, one_pass = false, trace = false, no_synth3 = false;
+  bool n256 = false, cta_pair = false, libm = false, weights_v1 = false, one_pass = false, trace = false, no_synth3 = false, no_split = false;
   int dbg = 0;
   long long host_slices = 0;   // 0: automatic
   static bool on(const char* k) { const char* e = std::getenv(k); return e && e[0] && e[0] != '0'; }
   void read() {
     n256 = on("SB2_N256"); cta_pair = on("SB2_CTA_PAIR"); libm = on("SB2_LIBM"); weights_v1 = on("SB2_WEIGHTS_V1");
-    one_pass = on("SB2_ONE_PASS"); trace = on("SB2_TRACE"); no_synth3 = on("SB2_NO_SYNTH3");
+    one_pass = on("SB2_ONE_PASS"); trace = on("SB2_TRACE"); no_synth3 = on("SB2_NO_SYNTH3"); no_split = on("SB2_NO_SPLIT");
     if (const char* e = std::getenv("SB2_DBG")) dbg = std::atoi(e);
     if (const char* e = std::getenv("SB2_HOST_SLICES")) host_slices = std::atoll(e);
   }
@@ -552,9 +552,29 @@ bool use_s3(const sb2_model* m, const sb2_params* p) {
 }
 int s3_cols(const sb2_model* m) { return m->d.n_comp == 1 ? 96 : 128; }   // accumulator columns per chunk (3 x 96 | 2 x 128 beside the weights)
 
+// Dense K (weights over every (age, Z) bin): the hi*hi terms of a chunk go to kDenseSplit accumulators of 128 columns by K
+// range, which divides the truncation error of the tensor core's FP32 accumulation by as much (synth_kernel, kSplit).
+constexpr int kDenseSplit = 4;
+bool use_split(const sb2_model* m, bool delta) {
+  return !delta && !m->sw.no_split && (m->d.k_pad / 8 + 3) / 4 >= kDenseSplit;   // every accumulator gets a k-block
+}
+
 
 template <int C, int NF, bool SPEC, bool PG>
 int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, cudaStream_t st) {
+  if (use_split(m, delta)) {
+    auto k = sb2::synth_kernel<C, NF, SPEC, 128, PG, kDenseSplit>;
+    sb2::SynthArgs a2 = a;
+    size_t bytes = 1024 + (size_t)sb2::kStages * sb2::SynthCfg<128>::kStageBytesN + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + sb2::kBarBytes;
+    if (SPEC && bytes + sb2::kSpecSmemBytes <= m->smem_optin) {
+      bytes += sb2::kSpecSmemBytes;
+      a2.spec_smem = 1;
+    }
+    CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    k<<<grid, sb2::kSynthThreads, bytes, st>>>(m->tm_w_hi, m->tm_w_lo, m->tm_g2_hi, m->tm_g2_lo, a2);
+    STAGE_CHECK("synth_kernel (split accumulators)", st);
+    return SB2_OK;
+  }
   if constexpr (C == 1) {
     if (use_n160(m)) {
       auto k = sb2::synth_kernel<C, NF, SPEC, 160, PG>;
@@ -808,7 +828,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
     int lo_min = m->h_lo[0], hi_max = m->h_hi[0];
     for (int f = 1; f < d.n_filt; ++f) { lo_min = std::min(lo_min, m->h_lo[f]); hi_max = std::max(hi_max, m->h_hi[f]); }
     const int wpb = 8, n_units = (int)(n_pad / rpu);
-    const int cols = (delta && use_s3(m, p)) ? s3_cols(m) : (rpu == 256 ? sb2::kBN2 : (use_n160(m) ? 160 : sb2::kBN));
+    const int cols = (delta && use_s3(m, p)) ? s3_cols(m) : (rpu == 256 || use_split(m, delta)) ? sb2::kBN2 : (use_n160(m) ? 160 : sb2::kBN);
     sb2::tile_range_kernel<<<(n_units + wpb - 1) / wpb, wpb * 32, 0, st>>>(m->g_m, m->g_orig, n_units, rpu, lo_min, hi_max, d.n_lam,
                                                                          cols / d.n_comp, all_lam ? 1 : 0, m->tile_range);
     STAGE_CHECK("tile_range_kernel", st);

@@ -29,6 +29,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 struct NoiseArgs {
   const double* flux;     // [n_gal][n_filt]
+  const float* flux32;    // the same as float32 (feature-only kernel; widened on the device, as numpy would), or nullptr
   long long n_gal;
   int n_filt, n_scatter;
   const double* sigma;    // [n_filt], or [n_sets][n_filt] with set_index
@@ -42,27 +43,41 @@ struct NoiseArgs {
   float* out_feat;        // [n_rows][2*n_filt] or nullptr
 };
 
+// Philox draws of one (row, filter QUAD): counter (row, quad, epoch), key (seed, epoch); the block's four words make two
+// Box-Muller pairs = the normals of filters 4q .. 4q+3.  kFast: hardware log2 / sin / cos (feature-only kernel; the
+// normals then differ from the library functions' by ~1e-6 relative, far inside the 1e-4 mag tolerance of the rows).
+template <bool kFast>
+__device__ __forceinline__ void philox_normals4(long long r, int quad, unsigned long long seed, unsigned long long epoch, float (&z)[4]) {
+  uint32_t rnd[4];
+  philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)quad, (uint32_t)epoch, (uint32_t)seed,
+                (uint32_t)(seed >> 32) ^ (uint32_t)(epoch >> 32), rnd);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)(rnd[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(rnd[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float rad, sn, cs;
+    if constexpr (kFast) {
+      rad = sqrtf(-1.3862943611198906f * __log2f(u1));       // -2 ln u = -2 ln2 log2 u
+      __sincosf(6.283185307179586f * u2, &sn, &cs);
+    } else {
+      rad = sqrtf(-2.0f * logf(u1));
+      sincospif(2.0f * u2, &sn, &cs);
+    }
+    z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
+  }
+}
+
 __global__ void __launch_bounds__(256) depth_noise_kernel(NoiseArgs A) {
   const long long n_rows = A.n_gal * A.n_scatter;
   const double ln10 = 2.302585092994046;
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
        r += (long long)gridDim.x * blockDim.x) {
     const long long g = r / A.n_scatter;
-    for (int f0 = 0; f0 < A.n_filt; f0 += 2) {
-      float zf[2] = {0.f, 0.f};
-      if (A.normals == nullptr) {  // one Philox block -> two Box-Muller normals (filters f0, f0+1)
-        uint32_t rnd[4];
-        philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)(f0 >> 1), (uint32_t)A.epoch,
-                      (uint32_t)A.seed, (uint32_t)(A.seed >> 32) ^ (uint32_t)(A.epoch >> 32), rnd);
-        const float u1 = ((float)(rnd[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float u2 = ((float)(rnd[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float rad = sqrtf(-2.0f * logf(u1));
-        float sn, cs;
-        sincospif(2.0f * u2, &sn, &cs);
-        zf[0] = rad * cs; zf[1] = rad * sn;
-      }
+    for (int f0 = 0; f0 < A.n_filt; f0 += 4) {
+      float zf[4] = {0.f, 0.f, 0.f, 0.f};
+      if (A.normals == nullptr) philox_normals4<false>(r, f0 >> 2, A.seed, A.epoch, zf);
 #pragma unroll
-      for (int d = 0; d < 2; ++d) {
+      for (int d = 0; d < 4; ++d) {
         const int f = f0 + d;
         if (f >= A.n_filt) break;
         const double rep = A.flux[g * A.n_filt + f];
@@ -88,59 +103,65 @@ __global__ void __launch_bounds__(256) depth_noise_kernel(NoiseArgs A) {
   }
 }
 
-// Feature rows only, Philox draws (the per-epoch resampling of a training set): one thread per (row, filter PAIR),
-// so the float64 fluxes are read as coalesced 16-byte pairs, one Philox block yields the pair's two normals, and the
-// (mag, mag_err) rows are written as coalesced float2.  Same counters, hence the same draws, as depth_noise_kernel; the
-// noisy flux is formed in float64 exactly as there, only log10 and the error ratio run in float32 (|d mag| < 6e-6,
-// tolerance 1e-4 mag).  HBM-bound: 16 B read + 16 B written per pair.
+// Feature rows only, Philox draws (the per-epoch resampling of a training set): one thread per (row, filter QUAD).  The
+// fluxes of the quad are read as one or two 16-byte loads (float32 | float64 input), one Philox block yields its four
+// normals, and (mag, mag_err) are written as float4.  Same counters as depth_noise_kernel; the noisy flux is formed in
+// float64 exactly as there, log2 / sin / cos / the error ratio run on the special-function unit (|d mag| < 6e-6,
+// tolerance 1e-4 mag).  HBM-bound: 16 | 32 B read + 32 B written per quad.  The (row, quad) of a thread come from a
+// per-block decomposition (a block walks whole rows), so the loop has no 64-bit division.
+template <typename T>
 __global__ void __launch_bounds__(256) depth_noise_feat_kernel(NoiseArgs A) {
   const long long n_rows = A.n_gal * A.n_scatter;
-  const int npair = (A.n_filt + 1) >> 1;
-  const long long total = n_rows * npair;
-  const bool even = (A.n_filt & 1) == 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / npair;
-    const int pr = (int)(i - r * npair), f0 = 2 * pr;
-    const long long g = r / A.n_scatter;
-    uint32_t rnd[4];
-    philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)pr, (uint32_t)A.epoch, (uint32_t)A.seed,
-                  (uint32_t)(A.seed >> 32) ^ (uint32_t)(A.epoch >> 32), rnd);
-    const float u1 = ((float)(rnd[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float u2 = ((float)(rnd[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float rad = sqrtf(-2.0f * logf(u1));
-    float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
-    const float zf[2] = {rad * cs, rad * sn};
-    double rep[2];
-    if (even) {
-      const double2 v = *reinterpret_cast<const double2*>(A.flux + g * A.n_filt + f0);
-      rep[0] = v.x; rep[1] = v.y;
-    } else {
-      rep[0] = A.flux[g * A.n_filt + f0];
-      rep[1] = (f0 + 1 < A.n_filt) ? A.flux[g * A.n_filt + f0 + 1] : 1.0;
-    }
-    float mag[2], merr[2];
+  const int nf = A.n_filt, nquad = (nf + 3) >> 2;
+  const int rows_pb = 256 / nquad;                       // whole rows per block and pass (nquad <= 8 for 32 filters)
+  const int rl = (int)threadIdx.x / nquad, q = (int)threadIdx.x - rl * nquad, f0 = 4 * q;
+  if (rl >= rows_pb) return;
+  const bool vec = (nf & 3) == 0;
+  const T* flux = sizeof(T) == 8 ? reinterpret_cast<const T*>(A.flux) : reinterpret_cast<const T*>(A.flux32);
+  const float lim = (float)A.mag_limit;
+  double sdq[4];
 #pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const int f = min(f0 + d, A.n_filt - 1);
-      double sd = A.sigma[f];
+  for (int d = 0; d < 4; ++d) sdq[d] = A.sigma[min(f0 + d, nf - 1)];
+  const bool small = n_rows < 0x7fffffffLL;
+  for (long long r = (long long)blockIdx.x * rows_pb + rl; r < n_rows; r += (long long)gridDim.x * rows_pb) {
+    const long long g = A.n_scatter == 1 ? r : (small ? (long long)((unsigned)r / (unsigned)A.n_scatter) : r / A.n_scatter);
+    float zf[4];
+    philox_normals4<true>(r, q, A.seed, A.epoch, zf);
+    double rep[4];
+    const T* src = flux + g * nf + f0;
+    if (vec) {
+      if constexpr (sizeof(T) == 8) {
+        const double2 a = *reinterpret_cast<const double2*>(src), b = *reinterpret_cast<const double2*>(src + 2);
+        rep[0] = a.x; rep[1] = a.y; rep[2] = b.x; rep[3] = b.y;
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(src);
+        rep[0] = a.x; rep[1] = a.y; rep[2] = a.z; rep[3] = a.w;
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < 4; ++d) rep[d] = (f0 + d < nf) ? (double)src[d] : 1.0;
+    }
+    float mag[4], merr[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      double sd = sdq[d];
       if (A.min_pc > 0.0) sd = fmax(sd, __ddiv_rn(__dmul_rn(rep[d], A.min_pc), 100.0));
       const double noisy = __dadd_rn(rep[d], __dadd_rn(0.0, __dmul_rn(sd, (double)zf[d])));
       const float f_ujy = (float)(noisy * 1e-3), e_ujy = (float)(sd * 1e-3);
-      float m = -2.5f * log10f(f_ujy) + 23.9f;
-      const float lim = (float)A.mag_limit;
-      if (f_ujy < 0.f) m = lim;
+      float m = fmaf(-0.7525749891599529f, __log2f(f_ujy), 23.9f);     // -2.5 log10 f = -2.5 log10(2) log2 f
+      if (!(f_ujy >= 0.f)) m = lim;
       if (m > lim) m = lim;
       mag[d] = m;
-      merr[d] = 2.5f * e_ujy / (2.302585092994046f * f_ujy);
+      merr[d] = __fdividef(1.0857362047581296f * e_ujy, f_ujy);        // 2.5 / ln 10
     }
-    float* row = A.out_feat + r * (2LL * A.n_filt);
-    if (even) {
-      *reinterpret_cast<float2*>(row + f0) = make_float2(mag[0], mag[1]);
-      *reinterpret_cast<float2*>(row + A.n_filt + f0) = make_float2(merr[0], merr[1]);
+    float* row = A.out_feat + r * (2LL * nf);
+    if (vec) {
+      *reinterpret_cast<float4*>(row + f0) = make_float4(mag[0], mag[1], mag[2], mag[3]);
+      *reinterpret_cast<float4*>(row + nf + f0) = make_float4(merr[0], merr[1], merr[2], merr[3]);
     } else {
-      row[f0] = mag[0]; row[A.n_filt + f0] = merr[0];
-      if (f0 + 1 < A.n_filt) { row[f0 + 1] = mag[1]; row[A.n_filt + f0 + 1] = merr[1]; }
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
+        if (f0 + d < nf) { row[f0 + d] = mag[d]; row[nf + f0 + d] = merr[d]; }
     }
   }
 }

@@ -183,14 +183,19 @@ __device__ __forceinline__ float4 epi_tab4(const float* g, uint32_t saddr, int i
 }
 
 template <int kComp, int kNF, bool kSpec, int kCta, int kN, int kGroups, bool kPgDust, int kWarp0 = kEpiWarp0, int kBufT = 512 / kN,
-          int kFeat = kFeatRuntime, bool kTabS = false>
+          int kFeat = kFeatRuntime, bool kTabS = false, int kSplit = 1>
 __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* s_uv, float* s_spec, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tempty_addr, uint32_t tmem_base, int unit0, int unit_stride,
                                               int n_units, uint32_t cta_rank, EpiTables T = EpiTables{0u, 0u, 0u, 0u, 0u}) {
   constexpr int kLch = kN / kComp;      // wavelengths per chunk
   constexpr int kSub = kLch / 32;       // 32-wavelength sub-chunks per chunk
   constexpr uint32_t kBuf = kBufT;      // TMEM accumulators (2 x 256, 3 x 160 or 4 x 128 columns; synth3: what W leaves free)
-  static_assert((int)kBuf <= kTfPerGroup && kGroups <= (int)kBuf && kGroups <= kMaxGroups, "a group must own a whole accumulator while it drains it");
+  // kSplit > 1 (dense K): a chunk's sum is spread over kSplit accumulators of kN columns (K ranges; see synth_kernel), which
+  // the epilogue adds in FP32 (round to nearest) as it reads them.  All of TMEM is then ONE set, so the groups share every
+  // chunk instead of alternating: group g takes the 32-wavelength sub-chunks with sub % kGroups == g.
+  constexpr bool kShare = kSplit > 1;
+  static_assert((int)kBuf <= kTfPerGroup && (kShare || kGroups <= (int)kBuf) && kGroups <= kMaxGroups, "a group must own a whole accumulator while it drains it");
+  static_assert(kBuf * kN * kSplit <= 512, "TMEM columns");
   const int warp = warp_uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
   const int c_all_last = (A.n_chunk * kBN / kComp + kLch - 1) / kLch - 1;   // last chunk of kLch wavelengths on the padded axis
   const uint32_t grp = (uint32_t)(warp - kWarp0) >> 2;
@@ -241,7 +246,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
       const int n_c = cr.y - cr.x + 1, rot = chunk_rot(n_c, blockIdx.x / kCta);
       for (int j = 0; j < n_c; ++j, ++it) {
         const int c = chunk_at(cr.x, n_c, rot, j);
-        if ((uint32_t)c % (uint32_t)kGroups != grp) continue;
+        if (!kShare && (uint32_t)c % (uint32_t)kGroups != grp) continue;
         const uint32_t buf = it % kBuf;
         mbar_wait(&tfull_bar[kTfPerGroup * grp + (gk % kTfPerGroup)], (gk / kTfPerGroup) & 1u, 0x600u + (it << 12));
         ++gk;
@@ -251,11 +256,19 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
           if (lane == 0) { if constexpr (kCta == 2) mbar_arrive_cluster(tempty_addr + buf * 8u); else mbar_arrive(tempty_bar + buf); }
           continue;
         }
-        const uint32_t t_acc = tmem_base + lane_base + buf * kN;
+        const uint32_t t_acc = tmem_base + lane_base + buf * (kN * kSplit);
+        const int sub_step = kShare ? kGroups : 1;
+        // sub-chunks of this chunk that hold wavelengths (>= 1), and this group's first one
+        const int n_sub = kShare ? max(1, min(kSub, (A.n_lam - c * kLch + 31) >> 5)) : kSub;
+        if (kShare && (int)grp >= n_sub) {   // nothing of this chunk for the group: hand the set back at once
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + buf);
+          continue;
+        }
 #pragma unroll 1
-        for (int sub = 0; sub < kSub; ++sub) {
+        for (int sub = kShare ? (int)grp : 0; sub < kSub; sub += sub_step) {
           const int i0 = c * kLch + sub * 32;
-          const bool last_sub = (sub == kSub - 1) || (i0 + 32 >= A.n_lam);
+          const bool last_sub = kShare ? (sub + sub_step >= n_sub) : ((sub == kSub - 1) || (i0 + 32 >= A.n_lam));
           float s[32];
           float e_sub = 0.f;   // absorbed energy of this sub-chunk (blocked summation: 4 -> 32 -> axis)
           {
@@ -267,11 +280,31 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               for (int j = 0; j < 32; ++j) v[j] = 0x3f800000u;
             } else {
               tmem_ld_32x32b_x32(t_acc + sub * 32, v);
+              if constexpr (kSplit > 1) {   // + the other K ranges' partial sums
+#pragma unroll 1
+                for (int p = 1; p < kSplit; ++p) {
+                  uint32_t w[32];
+                  tmem_ld_32x32b_x32(t_acc + p * kN + sub * 32, w);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+                }
+              }
             }
             if constexpr (kComp == 2) {
               const float ca = A.g_ca[row], cb = A.g_cb[row];
               uint32_t u[32];
               tmem_ld_32x32b_x32(t_acc + kLch + sub * 32, u);
+              if constexpr (kSplit > 1) {
+#pragma unroll 1
+                for (int p = 1; p < kSplit; ++p) {
+                  uint32_t w[32];
+                  tmem_ld_32x32b_x32(t_acc + p * kN + kLch + sub * 32, w);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) + __uint_as_float(w[j]));
+                }
+              }
               tmem_ld_wait();
               if (lya_on && A.lya_bin >= i0 && A.lya_bin < i0 + 32) {
 #pragma unroll
@@ -437,15 +470,19 @@ struct SynthCfg {
   static constexpr int kBufN = 512 / kN;
 };
 
-template <int kComp, int kNF, bool kSpec, int kN, bool kPgDust>
+// kSplit > 1 (dense K, kN = 128): the W_hi*G_hi terms of a chunk are spread over kSplit accumulators by K range (the small
+// cross terms go to the first), so each running sum -- and with it the truncation of every tensor-core accumulation -- is
+// kSplit times smaller; the epilogue adds the partial sums.  G is then fetched as 64-row boxes (the pair kernel's maps).
+template <int kComp, int kNF, bool kSpec, int kN, bool kPgDust, int kSplit = 1>
 __global__ void __launch_bounds__(kSynthThreads, 1)
 synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
              const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo,
              const __grid_constant__ SynthArgs A) {
-  static_assert(kN == kBN || kComp == 1, "the grid's two-component row layout is built for 256-column chunks");
+  static_assert(kN == kBN || kComp == 1 || kSplit > 1, "the grid's two-component row layout is built for 256-column chunks");
+  static_assert(kSplit == 1 || kN == 128, "split accumulators: 64-row boxes of G, two per operand");
   constexpr int kBBytes = SynthCfg<kN>::kBBytesN;
   constexpr int kStageBytes = SynthCfg<kN>::kStageBytesN;
-  constexpr uint32_t kBuf = SynthCfg<kN>::kBufN;
+  constexpr uint32_t kBuf = SynthCfg<kN>::kBufN / kSplit;
   constexpr int kLch = kN / kComp;  // wavelengths per chunk
   constexpr int kSub = kLch / 32;    // 32-wavelength sub-chunks per chunk
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -467,7 +504,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < kTfPerGroup * kMaxGroups; ++b) mbar_init(&tfull_bar[b], 1);
-    for (int b = 0; b < (int)kBuf; ++b) mbar_init(&tempty_bar[b], 4);  // 4 warps per epilogue group
+    for (int b = 0; b < (int)kBuf; ++b) mbar_init(&tempty_bar[b], kSplit > 1 ? 8 : 4);  // 4 warps per epilogue group (split: both groups drain every chunk)
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -508,10 +545,21 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
               } else {
               mbar_expect_tx_e(elected, &full_bar[stage], lo_tiles ? kStageBytes : kABytes + kBBytes);
               tma_load_2d_e(elected, st, &tm_w_hi, fb, kb * kBK, tile * kBM, kEvictNormal);
-              tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, c * kN, kEvictLast);
-              if (lo_tiles) {
-                tma_load_2d_e(elected, st + kABytes, &tm_w_lo, fb, kb * kBK, tile * kBM, kEvictNormal);
-                tma_load_2d_e(elected, st + 2 * kABytes + kBBytes, &tm_g_lo, fb, k0 + kb * kBK, c * kN, kEvictLast);
+              if (lo_tiles) tma_load_2d_e(elected, st + kABytes, &tm_w_lo, fb, kb * kBK, tile * kBM, kEvictNormal);
+              if constexpr (kSplit > 1) {
+                // rows of the chunk: one component = kLch consecutive wavelengths; with two components the grid's rows come
+                // in blocks of 256 [component 0: 128 wavelengths | component 1: the same 128] (as in synth3_kernel)
+                const int r0 = kComp == 1 ? c * kN : (c * kLch / (kBN / 2)) * kBN + (c * kLch) % (kBN / 2);
+                const int r1 = kComp == 1 ? r0 + 64 : r0 + kBN / 2;
+                tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, r0, kEvictLast);
+                tma_load_2d_e(elected, st + 2 * kABytes + kBBytes / 2, &tm_g_hi, fb, k0 + kb * kBK, r1, kEvictLast);
+                if (lo_tiles) {
+                  tma_load_2d_e(elected, st + 2 * kABytes + kBBytes, &tm_g_lo, fb, k0 + kb * kBK, r0, kEvictLast);
+                  tma_load_2d_e(elected, st + 2 * kABytes + kBBytes + kBBytes / 2, &tm_g_lo, fb, k0 + kb * kBK, r1, kEvictLast);
+                }
+              } else {
+                tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, c * kN, kEvictLast);
+                if (lo_tiles) tma_load_2d_e(elected, st + 2 * kABytes + kBBytes, &tm_g_lo, fb, k0 + kb * kBK, c * kN, kEvictLast);
               }
               }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -543,9 +591,14 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
           const uint32_t buf = it % kBuf;
           mbar_wait(&tempty_bar[buf], ((it / kBuf) & 1u) ^ 1u);  // epilogue has drained this accumulator
           tc_fence_after();
-          const uint32_t d_tmem = tmem_u + buf * kN;
+          const uint32_t d_tmem = tmem_u + buf * (kN * kSplit);
           for (int pass = 0; pass <= two_pass; ++pass) {
             for (int kb = 0; kb < n_kb; ++kb) {
+              // split accumulators: k-block kb's hi*hi terms go to accumulator kb * kSplit / n_kb; the first MMA into
+              // accumulators 1.. overwrites (accumulator 0 already holds cross terms by then)
+              const int part = kSplit > 1 ? (kb * kSplit) / n_kb : 0;
+              const bool part_first = kSplit > 1 && part > 0 && ((kb - 1) * kSplit) / n_kb != part;
+              const uint32_t d_hh = d_tmem + (uint32_t)part * kN;
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
               const uint64_t da = desc0 + (uint64_t)(((s_addr + stage * kStageBytes) & 0x3FFFF) >> 4);
@@ -561,7 +614,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
                     umma_tf32_e(elected, d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
                     umma_tf32_e(elected, d_tmem, a_hi, b_lo, idesc, 1u);
                   }
-                  if (pass == two_pass) umma_tf32_e(elected, d_tmem, a_hi, b_hi, idesc, 1u);
+                  if (pass == two_pass) umma_tf32_e(elected, d_hh, a_hi, b_hi, idesc, (part_first && k4 == 0) ? 0u : 1u);
                   }
                 }
               }
@@ -569,6 +622,10 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
+          if (kSplit > 1) {   // both groups drain every chunk
+            umma_commit_e(elected, &tfull_bar[gk0 % kTfPerGroup]); ++gk0;
+            umma_commit_e(elected, &tfull_bar[kTfPerGroup + gk1 % kTfPerGroup]); ++gk1;
+          } else
           if ((c & 1) == 0) { umma_commit_e(elected, &tfull_bar[gk0 % kTfPerGroup]); ++gk0; }                 // accumulator complete:
           else              { umma_commit_e(elected, &tfull_bar[kTfPerGroup + gk1 % kTfPerGroup]); ++gk1; }   // wake the group that owns chunk c
         }
@@ -576,7 +633,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
     }
   } else if (warp >= kEpiWarp0) {
     float* s_spec = (kSpec && A.spec_smem) ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes) : nullptr;
-    epilogue_loop<kComp, kNF, kSpec, 1, kN, 2, kPgDust>(A, s_uv, s_spec, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
+    epilogue_loop<kComp, kNF, kSpec, 1, kN, 2, kPgDust, kEpiWarp0, (int)kBuf, kFeatRuntime, false, kSplit>(A, s_uv, s_spec, tfull_bar, tempty_bar, 0u, tmem_base, (int)blockIdx.x, (int)gridDim.x, n_tiles, 0u);
   }
 
   tc_fence_before();
