@@ -220,7 +220,7 @@ int sb2_synth_photometry_host_wait(sb2_model* m, int slot);
  * create_feature_array_from_raw_photometry (sbi_runner.py:1698-1716, 1927-1932).
  *   flux      float64 [n_gal][n_filt] (nJy)        sigma float64 [n_filt] (nJy, depth/sigma level)
  *   normals   float64 [n_filt][n_gal*n_scatter] injected N(0,1) draws, or NULL => Philox4x32-10
- *             keyed by (seed, epoch) with counter (row, filter)
+ *             keyed by (seed, epoch) with counter (row, filter quad): one block = the normals of four filters
  *   out_flux  float64 [n_filt][n_rows] noisy flux (may be NULL)   -- bit-exact vs numpy for injected draws
  *   out_feat  float32 [n_rows][2*n_filt] = (mag..., mag_err...)   (may be NULL)
  * n_rows = n_gal*n_scatter, row r = g*n_scatter + s (np.repeat order).                      */
@@ -228,6 +228,14 @@ int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, 
                              const double* sigma, double min_flux_pc_error, const double* normals,
                              uint64_t seed, uint64_t epoch, double norm_mag_limit, double* out_flux,
                              double* out_sigma, float* out_feat, void* stream);
+
+/* Feature rows only, Philox draws, float32 fluxes (a library's Grid/Photometry as stored; widened on the device, which is
+ * what numpy does with float32 flux + float64 noise): the per-epoch resampling of a training set, sbi_runner.py:580-691 +
+ * :1698-1716.  flux float32 [n_gal][n_filt], out_feat float32 [n_rows][2*n_filt]; both 16-byte aligned.  Same draws and
+ * rows as sb2_depth_noise_features(flux as float64, normals = NULL, out_flux = out_sigma = NULL).                        */
+int sb2_depth_noise_features_f32(const float* flux, int64_t n_gal, int32_t n_filt, int32_t n_scatter, const double* sigma,
+                                 double min_flux_pc_error, uint64_t seed, uint64_t epoch, double norm_mag_limit,
+                                 float* out_feat, void* stream);
 
 /* Same with several depth sets (2-D `depths` of SBI_Fitter._apply_depths, sbi_runner.py:626-647): sigma_sets is device
  * float64 [n_sets][n_filt]; set_index device int32 [n_filt][n_scatter] says which set the rows [j*n_gal, (j+1)*n_gal) of

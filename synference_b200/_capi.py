@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     "sb2_synth_photometry", "sb2_synth_photometry_host", "sb2_depth_noise_features", "sb2_last_stage_ms", "sb2_wait_debug",
     "sb2_synth_photometry_host_submit", "sb2_synth_photometry_host_wait",
     "sb2_resampler_create", "sb2_resampler_destroy", "sb2_resample_spectra", "sb2_resample_spectra_host", "sb2_resample_last_ms",
-    "sb2_empirical_noise", "sb2_depth_noise_features_sets", "sb2_kernel_launches",
+    "sb2_empirical_noise", "sb2_depth_noise_features_sets", "sb2_depth_noise_features_f32", "sb2_kernel_launches",
     "sb2_filterset_create", "sb2_filterset_destroy", "sb2_filter_integrate",
 )
 
@@ -128,6 +128,9 @@ def load():
     lib.sb2_depth_noise_features.argtypes = [
         C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_uint64,
         C.c_uint64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sb2_depth_noise_features_f32.argtypes = [
+        C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.c_void_p,
+        C.c_void_p]
     lib.sb2_depth_noise_features_sets.argtypes = [
         C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_uint64,
         C.c_uint64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

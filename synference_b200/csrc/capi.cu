@@ -554,7 +554,7 @@ int s3_cols(const sb2_model* m) { return m->d.n_comp == 1 ? 96 : 128; }   // acc
 
 // Dense K (weights over every (age, Z) bin): the hi*hi terms of a chunk go to kDenseSplit accumulators of 128 columns by K
 // range, which divides the truncation error of the tensor core's FP32 accumulation by as much (synth_kernel, kSplit).
-constexpr int kDenseSplit = 4;
+constexpr int kDenseSplit = 3;
 bool use_split(const sb2_model* m, bool delta) {
   return !delta && !m->sw.no_split && (m->d.k_pad / 8 + 3) / 4 >= kDenseSplit;   // every accumulator gets a k-block
 }
@@ -1168,6 +1168,27 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
   return SB2_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// Feature rows only with Philox draws: depth_noise_feat_kernel (one thread per row and filter quad).
+template <typename T>
+int launch_noise_feat(const sb2::NoiseArgs& a, cudaStream_t st) {
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const long long rows = a.n_gal * a.n_scatter;
+  const int rows_pb = 256 / ((a.n_filt + 3) / 4);
+  long long blocks = (rows + rows_pb - 1) / rows_pb;
+  if (blocks > (long long)n_sm * 32) blocks = (long long)n_sm * 32;
+  sb2::depth_noise_feat_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a);
+  STAGE_CHECK("depth_noise_feat_kernel", st);
+  return SB2_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, int32_t n_scatter,
                              const double* sigma, double min_flux_pc_error, const double* normals, uint64_t seed,
                              uint64_t epoch, double norm_mag_limit, double* out_flux, double* out_sigma,
@@ -1179,23 +1200,30 @@ int sb2_depth_noise_features(const double* flux, int64_t n_gal, int32_t n_filt, 
   a.min_pc = min_flux_pc_error; a.normals = normals; a.seed = seed; a.epoch = epoch; a.mag_limit = norm_mag_limit;
   a.out_flux = out_flux; a.out_sigma = out_sigma; a.out_feat = out_feat;
   const long long rows = (long long)n_gal * n_scatter;
+  if (!normals && !out_flux && !out_sigma && out_feat && n_filt <= 1024 && (reinterpret_cast<uintptr_t>(flux) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out_feat) & 15) == 0)
+    return launch_noise_feat<double>(a, (cudaStream_t)stream);
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   long long blocks = (rows + 255) / 256;
   const long long cap = (long long)n_sm * 16;
   if (blocks > cap) blocks = cap;
-  if (!normals && !out_flux && !out_sigma && out_feat && (reinterpret_cast<uintptr_t>(flux) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(out_feat) & 7) == 0) {
-    const long long pairs = rows * ((n_filt + 1) / 2);
-    long long b2 = (pairs + 255) / 256;
-    if (b2 > (long long)n_sm * 32) b2 = (long long)n_sm * 32;
-    sb2::depth_noise_feat_kernel<<<(unsigned)b2, 256, 0, (cudaStream_t)stream>>>(a);
-  } else {
-    sb2::depth_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
-  }
-  CU_TRY(cudaGetLastError());
+  sb2::depth_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  STAGE_CHECK("depth_noise_kernel", (cudaStream_t)stream);
   return SB2_OK;
+}
+
+int sb2_depth_noise_features_f32(const float* flux, int64_t n_gal, int32_t n_filt, int32_t n_scatter, const double* sigma,
+                                 double min_flux_pc_error, uint64_t seed, uint64_t epoch, double norm_mag_limit,
+                                 float* out_feat, void* stream) {
+  if (!flux || !sigma || !out_feat || n_gal < 1 || n_filt < 1 || n_filt > 1024 || n_scatter < 1) return fail(SB2_ERR_INVALID, "bad argument");
+  if ((reinterpret_cast<uintptr_t>(flux) & 15) != 0 || (reinterpret_cast<uintptr_t>(out_feat) & 15) != 0)
+    return fail(SB2_ERR_INVALID, "flux and out_feat must be 16-byte aligned");
+  sb2::NoiseArgs a{};
+  a.flux32 = flux; a.n_gal = n_gal; a.n_filt = n_filt; a.n_scatter = n_scatter; a.sigma = sigma;
+  a.min_pc = min_flux_pc_error; a.seed = seed; a.epoch = epoch; a.mag_limit = norm_mag_limit; a.out_feat = out_feat;
+  return launch_noise_feat<float>(a, (cudaStream_t)stream);
 }
 
 int sb2_depth_noise_features_sets(const double* flux, int64_t n_gal, int32_t n_filt, int32_t n_scatter,

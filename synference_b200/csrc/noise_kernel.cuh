@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) depth_noise_feat_kernel(NoiseArgs A) {
       const double noisy = __dadd_rn(rep[d], __dadd_rn(0.0, __dmul_rn(sd, (double)zf[d])));
       const float f_ujy = (float)(noisy * 1e-3), e_ujy = (float)(sd * 1e-3);
       float m = fmaf(-0.7525749891599529f, __log2f(f_ujy), 23.9f);     // -2.5 log10 f = -2.5 log10(2) log2 f
-      if (!(f_ujy >= 0.f)) m = lim;
+      if (f_ujy < 0.f) m = lim;
       if (m > lim) m = lim;
       mag[d] = m;
       merr[d] = __fdividef(1.0857362047581296f * e_ujy, f_ujy);        // 2.5 / ln 10

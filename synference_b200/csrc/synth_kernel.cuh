@@ -191,11 +191,12 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
   constexpr int kSub = kLch / 32;       // 32-wavelength sub-chunks per chunk
   constexpr uint32_t kBuf = kBufT;      // TMEM accumulators (2 x 256, 3 x 160 or 4 x 128 columns; synth3: what W leaves free)
   // kSplit > 1 (dense K): a chunk's sum is spread over kSplit accumulators of kN columns (K ranges; see synth_kernel), which
-  // the epilogue adds in FP32 (round to nearest) as it reads them.  All of TMEM is then ONE set, so the groups share every
-  // chunk instead of alternating: group g takes the 32-wavelength sub-chunks with sub % kGroups == g.
+  // the epilogue adds in FP32 (round to nearest) as it reads them.  The chunk with sequence number `it` owns accumulators
+  // (3 it + p) mod 4, p < kSplit = 3 -- the fourth is where the MMA warp already sums the NEXT chunk's cross terms -- and
+  // the groups share every chunk instead of alternating: group g takes the 32-wavelength sub-chunks with sub % kGroups == g.
   constexpr bool kShare = kSplit > 1;
+  static_assert(!kShare || (kSplit == 3 && kN == 128), "rotating accumulators: three of four 128-column accumulators per chunk");
   static_assert((int)kBuf <= kTfPerGroup && (kShare || kGroups <= (int)kBuf) && kGroups <= kMaxGroups, "a group must own a whole accumulator while it drains it");
-  static_assert(kBuf * kN * kSplit <= 512, "TMEM columns");
   const int warp = warp_uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
   const int c_all_last = (A.n_chunk * kBN / kComp + kLch - 1) / kLch - 1;   // last chunk of kLch wavelengths on the padded axis
   const uint32_t grp = (uint32_t)(warp - kWarp0) >> 2;
@@ -256,13 +257,15 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
           if (lane == 0) { if constexpr (kCta == 2) mbar_arrive_cluster(tempty_addr + buf * 8u); else mbar_arrive(tempty_bar + buf); }
           continue;
         }
-        const uint32_t t_acc = tmem_base + lane_base + buf * (kN * kSplit);
+        const uint32_t t_lane = tmem_base + lane_base;
+        const uint32_t t_acc = t_lane + (kShare ? ((3u * it) & 3u) : buf) * kN;
         const int sub_step = kShare ? kGroups : 1;
         // sub-chunks of this chunk that hold wavelengths (>= 1), and this group's first one
         const int n_sub = kShare ? max(1, min(kSub, (A.n_lam - c * kLch + 31) >> 5)) : kSub;
-        if (kShare && (int)grp >= n_sub) {   // nothing of this chunk for the group: hand the set back at once
+        if (kShare && (int)grp >= n_sub) {   // nothing of this chunk for the group: hand its accumulators back at once
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + buf);
+          if (lane == 0)
+            for (int p = 0; p < kSplit; ++p) mbar_arrive(tempty_bar + ((3u * it + p) & 3u));
           continue;
         }
 #pragma unroll 1
@@ -284,7 +287,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
 #pragma unroll 1
                 for (int p = 1; p < kSplit; ++p) {
                   uint32_t w[32];
-                  tmem_ld_32x32b_x32(t_acc + p * kN + sub * 32, w);
+                  tmem_ld_32x32b_x32(t_lane + ((3u * it + p) & 3u) * kN + sub * 32, w);
                   tmem_ld_wait();
 #pragma unroll
                   for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
@@ -299,7 +302,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
 #pragma unroll 1
                 for (int p = 1; p < kSplit; ++p) {
                   uint32_t w[32];
-                  tmem_ld_32x32b_x32(t_acc + p * kN + kLch + sub * 32, w);
+                  tmem_ld_32x32b_x32(t_lane + ((3u * it + p) & 3u) * kN + kLch + sub * 32, w);
                   tmem_ld_wait();
 #pragma unroll
                   for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) + __uint_as_float(w[j]));
@@ -377,6 +380,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
             __syncwarp();
             if (lane == 0) {
               if constexpr (kCta == 2) mbar_arrive_cluster(tempty_addr + buf * 8u);   // the leader CTA's barrier
+              else if constexpr (kShare) { for (int p = 0; p < kSplit; ++p) mbar_arrive(tempty_bar + ((3u * it + p) & 3u)); }
               else mbar_arrive(tempty_bar + buf);
             }
           }
@@ -470,9 +474,12 @@ struct SynthCfg {
   static constexpr int kBufN = 512 / kN;
 };
 
-// kSplit > 1 (dense K, kN = 128): the W_hi*G_hi terms of a chunk are spread over kSplit accumulators by K range (the small
+// kSplit = 3 (dense K, kN = 128): the W_hi*G_hi terms of a chunk are spread over three accumulators by K range (the small
 // cross terms go to the first), so each running sum -- and with it the truncation of every tensor-core accumulation -- is
-// kSplit times smaller; the epilogue adds the partial sums.  G is then fetched as 64-row boxes (the pair kernel's maps).
+// three times smaller; the epilogue adds the partial sums.  TMEM holds four such accumulators and chunk `it` takes numbers
+// (3 it + p) mod 4: the one left over is the FIRST accumulator of chunk it + 1, whose cross-term pass (two thirds of a
+// chunk's MMAs) therefore runs while the epilogue drains chunk it -- the tensor pipe never waits for the epilogue.
+// G is fetched as 64-row boxes (the pair kernel's maps).
 template <int kComp, int kNF, bool kSpec, int kN, bool kPgDust, int kSplit = 1>
 __global__ void __launch_bounds__(kSynthThreads, 1)
 synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -482,7 +489,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   static_assert(kSplit == 1 || kN == 128, "split accumulators: 64-row boxes of G, two per operand");
   constexpr int kBBytes = SynthCfg<kN>::kBBytesN;
   constexpr int kStageBytes = SynthCfg<kN>::kStageBytesN;
-  constexpr uint32_t kBuf = SynthCfg<kN>::kBufN / kSplit;
+  constexpr uint32_t kBuf = SynthCfg<kN>::kBufN;
   constexpr int kLch = kN / kComp;  // wavelengths per chunk
   constexpr int kSub = kLch / 32;    // 32-wavelength sub-chunks per chunk
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -504,7 +511,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < kTfPerGroup * kMaxGroups; ++b) mbar_init(&tfull_bar[b], 1);
-    for (int b = 0; b < (int)kBuf; ++b) mbar_init(&tempty_bar[b], kSplit > 1 ? 8 : 4);  // 4 warps per epilogue group (split: both groups drain every chunk)
+    for (int b = 0; b < (kSplit > 1 ? 4 : (int)kBuf); ++b) mbar_init(&tempty_bar[b], kSplit > 1 ? 8 : 4);  // 4 warps per epilogue group (split: both groups drain every chunk)
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -582,23 +589,34 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
       const int n_tiles_u = warp_uniform(n_tiles), n_kb = A.n_kb, k8_total = A.k8_total, two_pass = A.two_pass;
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
       uint32_t gk0 = 0, gk1 = 0;   // chunks handed to epilogue group 0 / 1 so far
+      uint32_t acc_par = 0;        // split accumulators: bit x = parity of the uses of accumulator x so far
       for (int tile = blockIdx.x; tile < n_tiles_u; tile += gridDim.x) {
         const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
         const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
         const int n_c = c_last - c_first + 1, rot = chunk_rot(n_c, blockIdx.x);
         for (int j = 0; j < n_c; ++j, ++it) {
           const int c = chunk_at(c_first, n_c, rot, j);
-          const uint32_t buf = it % kBuf;
-          mbar_wait(&tempty_bar[buf], ((it / kBuf) & 1u) ^ 1u);  // epilogue has drained this accumulator
+          const uint32_t buf = kSplit > 1 ? ((3u * it) & 3u) : it % kBuf;
+          if constexpr (kSplit > 1) {
+            mbar_wait(&tempty_bar[buf], ((acc_par >> buf) & 1u) ^ 1u);
+            acc_par ^= 1u << buf;
+          } else {
+            mbar_wait(&tempty_bar[buf], ((it / kBuf) & 1u) ^ 1u);  // epilogue has drained this accumulator
+          }
           tc_fence_after();
-          const uint32_t d_tmem = tmem_u + buf * (kN * kSplit);
+          const uint32_t d_tmem = tmem_u + buf * kN;
           for (int pass = 0; pass <= two_pass; ++pass) {
             for (int kb = 0; kb < n_kb; ++kb) {
               // split accumulators: k-block kb's hi*hi terms go to accumulator kb * kSplit / n_kb; the first MMA into
               // accumulators 1.. overwrites (accumulator 0 already holds cross terms by then)
               const int part = kSplit > 1 ? (kb * kSplit) / n_kb : 0;
-              const bool part_first = kSplit > 1 && part > 0 && ((kb - 1) * kSplit) / n_kb != part;
-              const uint32_t d_hh = d_tmem + (uint32_t)part * kN;
+              const bool part_first = kSplit > 1 && part > 0 && ((kb - 1) * kSplit) / n_kb != part && pass == two_pass;
+              const uint32_t acc_hh = (buf + (uint32_t)part) & 3u;
+              const uint32_t d_hh = kSplit > 1 ? tmem_u + acc_hh * kN : d_tmem;
+              if (part_first) {   // (the previous chunk's epilogue has long finished with it: see the header comment)
+                mbar_wait(&tempty_bar[acc_hh], ((acc_par >> acc_hh) & 1u) ^ 1u);
+                acc_par ^= 1u << acc_hh;
+              }
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
               const uint64_t da = desc0 + (uint64_t)(((s_addr + stage * kStageBytes) & 0x3FFFF) >> 4);

@@ -637,6 +637,20 @@ def depth_noise_features(flux, sigma, n_scatter=1, normals=None, seed=0, epoch=0
     import torch
     lib = _capi.load()
     dev = torch.device("cuda", device)
+    # float32 fluxes (a library's photometry as stored) stay float32 across PCIe and in HBM when only Philox feature rows are
+    # wanted: sb2_depth_noise_features_f32 widens them on the device, as numpy does for float32 flux + float64 noise
+    is32 = (isinstance(flux, torch.Tensor) and flux.dtype == torch.float32) or (isinstance(flux, np.ndarray) and flux.dtype == np.float32)
+    if is32 and normals is None and set_index is None and want_features and not want_flux:
+        fl = torch.as_tensor(flux).to(dev).contiguous()
+        n_gal, n_filt = fl.shape
+        sg = torch.as_tensor(np.asarray(sigma, dtype=np.float64)).to(dev).contiguous()
+        feat = torch.empty((n_gal * int(n_scatter), 2 * n_filt), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.sb2_depth_noise_features_f32(fl.data_ptr(), n_gal, n_filt, int(n_scatter), sg.data_ptr(), float(min_flux_pc_error),
+                                                  int(seed), int(epoch), float(norm_mag_limit), feat.data_ptr(),
+                                                  torch.cuda.current_stream(device).cuda_stream)
+        _capi.check(rc, "sb2_depth_noise_features_f32")
+        return None, None, feat
     fl = torch.as_tensor(flux, dtype=torch.float64).to(dev).contiguous()
     n_gal, n_filt = fl.shape
     sg = torch.as_tensor(np.asarray(sigma, dtype=np.float64)).to(dev).contiguous()
