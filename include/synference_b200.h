@@ -161,6 +161,12 @@ typedef struct sb2_params {
    * float32 -- half the bytes -- and are widened to float64 on the device; with max_age_from_z the SFH rows need no
    * host-side float64 arithmetic at all.  Must be 0 for the device entry points.                                   */
   int32_t host_f32;
+  /* Layout of `flux_scaled`: 0 = [n][n_filt] (one row per galaxy).  > 0 = TRANSPOSED, [n_filt][scaled_ld] with galaxy g of
+   * this call in column g (scaled_ld >= n): the (n_filters, n_galaxies) layout of a library's Grid/Photometry
+   * (src/synference/library.py:4739-4742, :4074-4100), so that a batch lands in its column range of the library matrix
+   * without a host-side transpose -- pass `matrix + first_column` and scaled_ld = the matrix's row length.
+   * Not available together with spec_out on the host entry.                                                        */
+  int64_t scaled_ld;
 } sb2_params;
 
 typedef struct sb2_model sb2_model;
@@ -187,7 +193,7 @@ int sb2_build_weights(sb2_model* m, const sb2_params* params, double* w_out, voi
  * Replaces GalaxyBasis.process_galaxies -> Pipeline.run (library.py:2447-2694) and the mass
  * scaling loop of CombinedBasis.create_full_library (library.py:4567-4609).
  *   flux_base   device float32 [n][n_filt]  nJy at base_mass            (may be NULL)
- *   flux_scaled device float64 [n][n_filt]  float32(base)*10^logM/base  (may be NULL)
+ *   flux_scaled device float64 [n][n_filt]  float32(base)*10^logM/base  (may be NULL; transposed if params->scaled_ld > 0)
  *   spec_out    device float32 [n][n_lam]   observed-frame f_nu [nJy] at base_mass on the
  *               rest-frame axis (Pipeline.get_observed_spectra, library.py:2604) (may be NULL) */
 int sb2_synth_photometry(sb2_model* m, const sb2_params* params, float* flux_base, double* flux_scaled,

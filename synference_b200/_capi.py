@@ -62,6 +62,7 @@ class Params(C.Structure):
         ("dust_slope", C.c_void_p), ("dust_ampl", C.c_void_p), ("fesc_lya", C.c_void_p),
         ("tau_v_birth", C.c_void_p),
         ("host_f32", C.c_int32),
+        ("scaled_ld", C.c_int64),
     ]
 
 

@@ -757,6 +757,7 @@ int check_params(const sb2_model* m, const sb2_params* p) {
   if (p->fesc_lya && !m->lya_line) return fail(SB2_ERR_INVALID, "per-galaxy fesc_lya needs a model created with lya_line");
   if (m->lya_line && !p->fesc_lya) return fail(SB2_ERR_INVALID, "this model reads fesc_lya per galaxy: params.fesc_lya is required");
   if (p->fesc_lya && (m->d.n_age > 64 || m->d.n_z > 64)) return fail(SB2_ERR_INVALID, "per-galaxy fesc_lya supports n_age, n_z <= 64");
+  if (p->scaled_ld != 0 && p->scaled_ld < p->n) return fail(SB2_ERR_INVALID, "scaled_ld must be 0 or >= n");
   return SB2_OK;
 }
 
@@ -942,6 +943,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
     fa.part = m->part; fa.n_rows = a.n_rows; fa.n_filt = d.n_filt; fa.n_comp = d.n_comp; fa.n_groups = (rpu == 256 && sb2::kT2Buf >= 3 && sb2::kMaxGroups >= 3) ? 3 : 2;
     fa.g_beta = m->g_beta; fa.g_gamma = m->g_gamma; fa.g_scale = m->g_scale; fa.g_ca = m->g_ca; fa.g_orig = m->g_orig;
     fa.g_mscale = m->g_mscale; fa.g_trunc = m->g_trunc; fa.out_base = flux_base; fa.out_scaled = flux_scaled;
+    fa.scaled_ld = flux_scaled ? p->scaled_ld : 0;
     for (int f = 0; f < d.n_filt; ++f) { fa.filt_su[f] = m->h_su[f]; fa.filt_sdv[f] = m->h_sdv[f]; }
     fa.e_part = m->dust_wnu ? m->e_part : nullptr; fa.dust_duv = reinterpret_cast<const float2*>(m->dust_duv); fa.dust_g = m->dust_g;
     fa.g_m = m->g_m; fa.dust_m_len = d.dust_m_len; fa.n_lam = d.n_lam; fa.out_spec = spec_out;
@@ -986,6 +988,7 @@ int host_with_spectra(sb2_model* m, const sb2_params* p, float* flux_base, doubl
   int rc = check_params(m, p);
   if (rc != SB2_OK) return rc;
   if (p->host_f32) return fail(SB2_ERR_INVALID, "host_f32 transport is not available together with spec_out");
+  if (p->scaled_ld) return fail(SB2_ERR_INVALID, "a transposed flux_scaled (scaled_ld) is not available together with spec_out");
   CU_TRY(cudaSetDevice(m->device));
   for (int s = 0; s < 2; ++s) {
     rc = sb2_synth_photometry_host_wait(m, s);     // the staging areas below are shared with the photometry-only entry
@@ -1137,8 +1140,11 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
     dp.fesc_lya = dev[9] ? dev[9] + a : nullptr;
     dp.tau_v_birth = dev[10] ? dev[10] + a : nullptr;
     dp.sfh_rows = dev[11] + a * p->sfh_stride;
+    // transposed scaled output: the staging area is [n_filt][n], this slice fills its columns [a, b)
+    const bool transp = flux_scaled && p->scaled_ld > 0;
+    dp.scaled_ld = transp ? (int64_t)n : 0;
     rc = sb2_synth_photometry(m, &dp, flux_base ? m->stage_flux[slot] + a * nf : nullptr,
-                              flux_scaled ? m->stage_flux64[slot] + a * nf : nullptr, nullptr, m->st_comp);
+                              flux_scaled ? m->stage_flux64[slot] + (transp ? a : a * nf) : nullptr, nullptr, m->st_comp);
     if (rc != SB2_OK) {   // earlier slices are still in flight on the three streams: drain them before reporting
       const std::string msg = g_err;
       cudaStreamSynchronize(m->st_h2d); cudaStreamSynchronize(m->st_comp); cudaStreamSynchronize(m->st_d2h);
@@ -1150,7 +1156,10 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
     CU_TRY(cudaStreamWaitEvent(m->st_d2h, m->ev_done[sl], 0));
     if (flux_base)
       CU_TRY(cudaMemcpyAsync(flux_base + a * nf, m->stage_flux[slot] + a * nf, (b - a) * nf * 4, cudaMemcpyDeviceToHost, m->st_d2h));
-    if (flux_scaled)
+    if (transp)
+      CU_TRY(cudaMemcpy2DAsync(flux_scaled + a, (size_t)p->scaled_ld * 8, m->stage_flux64[slot] + a, n * 8, (b - a) * 8, (size_t)nf,
+                               cudaMemcpyDeviceToHost, m->st_d2h));
+    else if (flux_scaled)
       CU_TRY(cudaMemcpyAsync(flux_scaled + a * nf, m->stage_flux64[slot] + a * nf, (b - a) * nf * 8, cudaMemcpyDeviceToHost, m->st_d2h));
     if (trace) cudaEventRecord(tr[1 + sl * 4 + 3], m->st_d2h);
   }

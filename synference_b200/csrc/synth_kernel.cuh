@@ -861,6 +861,7 @@ struct FinalizeArgs {
   const unsigned* g_trunc;
   float* out_base;
   double* out_scaled;
+  long long scaled_ld;       // 0: out_scaled is [galaxy][filter]; > 0: [filter][scaled_ld] (a library's Grid/Photometry layout)
   const float* e_part;       // dust emission (nullptr: none): absorbed-energy partials of the epilogue groups,
   const float2* dust_duv;    // [dust_m_len][n_filt] filter numerators of the emission per unit absorbed energy, by shift m
   const float* dust_g;       // [n_lam] the emission's spectrum per unit absorbed energy (spectra output)
@@ -897,7 +898,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   }
   // a galaxy's n_filt fluxes are contiguous in the output: build them four at a time and store 16 bytes at once
   // (the rows land in the caller's galaxy order, i.e. scattered -- scalar stores would touch each 32-byte sector 8x)
-  const bool vec = (A.n_filt % 4) == 0 && ((reinterpret_cast<uintptr_t>(A.out_base) | reinterpret_cast<uintptr_t>(A.out_scaled)) & 15) == 0;
+  const bool tr = A.scaled_ld > 0;   // transposed scaled output: scalar stores into n_filt rows (neighbouring rows of a tile are
+                                     // redshift neighbours, not galaxy neighbours, so the columns are scattered either way)
+  const bool vec = (A.n_filt % 4) == 0 && ((reinterpret_cast<uintptr_t>(A.out_base) | (tr ? 0 : reinterpret_cast<uintptr_t>(A.out_scaled))) & 15) == 0;
   for (int f0 = 0; f0 < A.n_filt; f0 += 4) {
     float fl[4];
 #pragma unroll
@@ -921,7 +924,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
     }
     if (vec) {
       if (A.out_base) *reinterpret_cast<float4*>(A.out_base + (size_t)orig * A.n_filt + f0) = make_float4(fl[0], fl[1], fl[2], fl[3]);
-      if (A.out_scaled) {
+      if (A.out_scaled && tr) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) A.out_scaled[(size_t)(f0 + q) * A.scaled_ld + orig] = (double)fl[q] * mscale;
+      } else if (A.out_scaled) {
         double2* o = reinterpret_cast<double2*>(A.out_scaled + (size_t)orig * A.n_filt + f0);
         o[0] = make_double2((double)fl[0] * mscale, (double)fl[1] * mscale);
         o[1] = make_double2((double)fl[2] * mscale, (double)fl[3] * mscale);
@@ -931,7 +937,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
       for (int q = 0; q < 4; ++q)
         if (f0 + q < A.n_filt) {
           if (A.out_base) A.out_base[(size_t)orig * A.n_filt + f0 + q] = fl[q];
-          if (A.out_scaled) A.out_scaled[(size_t)orig * A.n_filt + f0 + q] = (double)fl[q] * mscale;
+          if (A.out_scaled) A.out_scaled[tr ? (size_t)(f0 + q) * A.scaled_ld + orig : (size_t)orig * A.n_filt + f0 + q] = (double)fl[q] * mscale;
         }
     }
   }

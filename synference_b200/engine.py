@@ -71,7 +71,9 @@ class GalaxyParams:
             np.asarray(strip_units(a), dtype=np.float64), (n,)).copy()
         if rows.shape[0] == 1 and n > 1:
             rows = np.repeat(rows, n, axis=0)
-        used = max(2, int(np.max(np.nonzero(np.abs(rows).sum(0))[0], initial=1)) + 1)
+        used = getattr(sfhs, "n_used", None)       # an SFHArray knows its column count: no scan of the (N, 24) table
+        if used is None:
+            used = max(2, int(np.max(np.nonzero(np.abs(rows).sum(0))[0], initial=1)) + 1)
         return cls(redshift=bc(redshifts), sfh_type=sfh_type, sfh_rows=np.ascontiguousarray(rows[:, :used]),
                    zd_type=zd_type, zd_value=bc(zv), zd_sigma=bc(zs) if zd_type >= ZD_NORMAL_LINEAR else None,
                    log_mass=bc(log_mass), tau_v=bc(tau_v), **kw)
@@ -417,16 +419,28 @@ class SynthEngine:
         return get
 
     # ---- host-buffer entry (what a drop-in caller uses) --------------------------------------
-    def photometry(self, params: GalaxyParams, scaled=True, out=None, transport="f64"):
+    def photometry(self, params: GalaxyParams, scaled=True, out=None, transport="f64", library_out=None):
         """Fluxes [nJy] as a host array ``(N, n_filt)``: float64 scaled by stellar mass
         (``float32(base) * 10**log_mass / base_mass``, ``library.py:4588-4609``) or float32 at base mass.
 
         Populations larger than ``max_batch`` run batch by batch through the two staging slots of the C ABI, so
         the copies of one batch overlap the kernels of the next.  ``transport="f32"`` sends the parameters over PCIe as
         float32 (what ``draw_from_hypercube`` produces, ``library.py:1098``) and widens them on the device: half the
-        host-to-device bytes, exact for float32 draws (use ``max_age_from_z`` so the SFH rows hold the raw draws)."""
+        host-to-device bytes, exact for float32 draws (use ``max_age_from_z`` so the SFH rows hold the raw draws).
+
+        ``library_out=(matrix, first_column)`` (with ``scaled=False``): the same pass ALSO writes the mass-scaled float64
+        fluxes into columns ``[first_column, first_column + N)`` of ``matrix``, a C-contiguous float64 ``(n_filt, N_total)``
+        array -- the layout of a library's ``Grid/Photometry`` (``library.py:4739-4742``) -- transposed on the device
+        (``sb2_params.scaled_ld``), so a library build needs no host-side cast, multiply or transpose."""
         n = len(params)
         res = out if out is not None else np.empty((n, self.n_filt), dtype=np.float64 if scaled else np.float32)
+        if library_out is not None:
+            mat, col0 = library_out
+            if scaled or self.general or params.log_mass is None:
+                raise ValueError("library_out needs scaled=False, a constant-R wavelength axis and params.log_mass")
+            if not (isinstance(mat, np.ndarray) and mat.dtype == np.float64 and mat.flags.c_contiguous and mat.ndim == 2
+                    and mat.shape[0] == self.n_filt and 0 <= col0 and col0 + n <= mat.shape[1]):
+                raise ValueError("library_out: matrix must be C-contiguous float64 (n_filt, N_total) with room for the batch")
         if self.general:
             return self._photometry_general(params, scaled, res)
         pending = []
@@ -434,12 +448,14 @@ class SynthEngine:
             b = min(n, a + self.max_batch)
             if len(pending) == 2:
                 self.wait(pending.pop(0))
-            pending.append(self.submit(params.slice(slice(a, b)), res[a:b], scaled=scaled, slot=i & 1, transport=transport))
+            lo = None if library_out is None else (library_out[0], library_out[1] + a)
+            pending.append(self.submit(params.slice(slice(a, b)), res[a:b], scaled=scaled, slot=i & 1, transport=transport,
+                                       library_out=lo))
         for t in pending:
             self.wait(t)
         return res
 
-    def submit(self, params: GalaxyParams, out, scaled=True, slot=0, transport="f64"):
+    def submit(self, params: GalaxyParams, out, scaled=True, slot=0, transport="f64", library_out=None):
         """Enqueue one batch (``len(params) <= max_batch``) and return a ticket for :meth:`wait`; ``out`` is the
         host array the results land in (pinned memory gives real copy/compute overlap)."""
         assert out.flags.c_contiguous and out.shape == (len(params), self.n_filt)
@@ -452,8 +468,14 @@ class SynthEngine:
             raise ValueError("transport must be 'f64' or 'f32'")
         s = self._fill(params, self._host_ptr_factory(keep, np.float32 if transport == "f32" else np.float64))
         s.host_f32 = 1 if transport == "f32" else 0
+        scaled_ptr = out.ctypes.data if scaled else None
+        if library_out is not None:      # float32 base rows into `out` and the transposed float64 scaled block in one pass
+            mat, col0 = library_out
+            keep.append(mat)
+            scaled_ptr = mat.ctypes.data + 8 * int(col0)
+            s.scaled_ld = int(mat.shape[1])
         rc = self.lib.sb2_synth_photometry_host_submit(self._h, C.byref(s), None if scaled else out.ctypes.data,
-                                                       out.ctypes.data if scaled else None, int(slot))
+                                                       scaled_ptr, int(slot))
         _capi.check(rc, "sb2_synth_photometry_host_submit")
         return (int(slot), keep)
 

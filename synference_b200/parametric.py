@@ -228,6 +228,9 @@ class SFHArray:
         self.sfh_type = sfh_type
         self.rows = np.ascontiguousarray(rows, dtype=np.float64)  # (N, SFH_MAX_PARAMS)
         self.redshifts = None if redshifts is None else np.asarray(redshifts, dtype=float)
+        # leading columns that can be non-zero (min_age, max_age, the type's parameters); None: unknown, scan the rows
+        names = getattr(sfh_type, "param_names", ())
+        self.n_used = 2 + len(names) if names else None
 
     @property
     def type_id(self):

@@ -655,3 +655,32 @@ def test_general_wavelength_axis_matches_oracle(tmp_path):
                       fesc_ly_alpha=0.3, dust=dict(curve="Calzetti2000"), igm=(I.INOUE14_LAF, I.INOUE14_DLA))
     assert_flux_close(one[None, :], O.scale_to_mass(w1, [9.5]))
     eng.close()
+
+
+def test_library_out_writes_the_scaled_block_transposed_in_the_same_pass():
+    """``photometry(scaled=False, library_out=(matrix, col0))`` returns the float32 base-mass rows AND fills columns
+    ``[col0, col0 + N)`` of a (n_filt, N_total) float64 matrix -- the layout of a library's Grid/Photometry
+    (library.py:4739-4742) -- with ``float32(base) * 10**log_mass / base_mass`` (library.py:4588-4609): bit-identical
+    to the separate scaled call, for one batch and for a population streamed through both staging slots."""
+    n = 40_000
+    w = make_workload("cfg2", n)
+    for max_batch in (n, 16_384):
+        eng = SynthEngine(w.grid, w.emission_model, w.emission_key, w.filters, max_batch=max_batch)
+        base = eng.photometry(w.params, scaled=False)
+        scaled = eng.photometry(w.params, scaled=True)
+        mat = np.full((eng.n_filt, n + 7), -1.0)
+        for transport in ("f64", "f32"):
+            mat[:] = -1.0
+            got = eng.photometry(w.params, scaled=False, library_out=(mat, 5), transport=transport)
+            if transport == "f64":
+                assert np.array_equal(got, base)
+                assert np.array_equal(mat[:, 5:5 + n], scaled.T)
+            else:
+                ref32 = eng.photometry(w.params, scaled=True, transport="f32")
+                assert np.array_equal(mat[:, 5:5 + n], ref32.T)
+            assert np.all(mat[:, :5] == -1.0) and np.all(mat[:, 5 + n:] == -1.0)
+        with pytest.raises(ValueError):
+            eng.photometry(w.params, scaled=True, library_out=(mat, 5))
+        with pytest.raises(ValueError):
+            eng.photometry(w.params, scaled=False, library_out=(mat, 8))
+        eng.close()
