@@ -53,7 +53,7 @@ typedef struct sb2_model_desc {
                       * iz*n_age_pad + ia, so every metallicity's columns start 16-byte (32-byte) aligned,
                       * which the TMA box origin of a bracket-grouped tile needs                        */
   int32_t k_pad;   /* n_age_pad*n_z rounded up to a multiple of 32                          */
-  int32_t n_chunk; /* wavelength chunks of 256/n_comp bins                                  */
+  int32_t n_chunk; /* wavelength chunks of 256/n_comp bins (pseudo-bins included, see x_bins) */
   const double* log10ages;     /* [n_age]                                                   */
   const double* metallicities; /* [n_z]                                                     */
   /* Transposed, TF32 hi/lo-split grid in internal units, K-major:
@@ -129,6 +129,14 @@ typedef struct sb2_model_desc {
    * src/synference/library.py:5756-5761): no redshift shift, no distance factor -- results are L_nu in erg/s/Hz at
    * base_mass; create the model without IGM tables.  redshift is then only used for max_age_from_z.            */
   int32_t rest_frame;
+  /* Optional PSEUDO-BINS for the absorbed-energy sum of the dust emission (needs dust_wnu; 0: the sum runs over the axis).
+   * sum_i wnu_i L_i (1 - exp(-tau kappa_i)) depends on a wavelength only through kappa_i, so the axis can be projected onto
+   * x_bins nodes in kappa: rows [x_bin0, x_bin0 + x_bins) of the padded axis (x_bin0 >= n_lam, both multiples of 192) hold
+   * gt = sum_i wnu_i l_j(kappa_i) grid_i (l_j: Lagrange weights of node j), kappa = the node and dust_wnu = 1, and n_chunk
+   * covers them.  The bracket-grouped kernel then multiplies these x_bins extra rows per tile instead of the whole axis and
+   * keeps its wavelength-chunk skipping; other kernels ignore them.  Accurate to < 1e-6 of E_abs while
+   * tau_V * (node spacing) < 0.42 -- beyond that the caller sets sb2_params.energy_full_axis.                          */
+  int32_t x_bin0, x_bins;
 } sb2_model_desc;
 
 /* Per-galaxy parameters, struct of arrays (float64).  Replaces the per-galaxy object lists
@@ -167,6 +175,9 @@ typedef struct sb2_params {
    * without a host-side transpose -- pass `matrix + first_column` and scaled_ld = the matrix's row length.
    * Not available together with spec_out on the host entry.                                                        */
   int64_t scaled_ld;
+  /* 1: form the dust emission's absorbed energy over the whole wavelength axis even if the model holds pseudo-bins
+   * (sb2_model_desc.x_bins): for optical depths beyond the pseudo-bins' accuracy range.                              */
+  int32_t energy_full_axis;
 } sb2_params;
 
 typedef struct sb2_model sb2_model;

@@ -47,7 +47,7 @@ class ModelDesc(C.Structure):
         ("lya_line", _dp), ("lya_bin", C.c_int32), ("kappa_birth", _fp),
         ("dust_wnu", _fp), ("dust_g", _fp), ("dust_duv", _fp), ("dust_m_len", C.c_int32),
         ("fm_log_tab", _dp), ("fm_exp_tab", _dp), ("fm_tail_tab", _dp), ("fm_tail_n", C.c_int32), ("fm_tail_w", C.c_double),
-        ("rest_frame", C.c_int32),
+        ("rest_frame", C.c_int32), ("x_bin0", C.c_int32), ("x_bins", C.c_int32),
     ]
 
 
@@ -63,6 +63,7 @@ class Params(C.Structure):
         ("tau_v_birth", C.c_void_p),
         ("host_f32", C.c_int32),
         ("scaled_ld", C.c_int64),
+        ("energy_full_axis", C.c_int32),
     ]
 
 

@@ -319,7 +319,9 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   if (d->n_age_pad < d->n_age || d->n_age_pad % 4 != 0) return fail(SB2_ERR_INVALID, "n_age_pad must be a multiple of 4 >= n_age");
   if (d->k_pad % 32 != 0 || d->k_pad < d->n_age_pad * d->n_z) return fail(SB2_ERR_INVALID, "bad k_pad");
   const int lch = sb2::kBN / d->n_comp;
-  if (d->n_chunk != (d->n_lam + lch - 1) / lch) return fail(SB2_ERR_INVALID, "bad n_chunk");
+  if (d->x_bins < 0 || (d->x_bins > 0 && (!d->dust_wnu || d->x_bins % 192 != 0 || d->x_bin0 % 192 != 0 || d->x_bin0 < d->n_lam)))
+    return fail(SB2_ERR_INVALID, "pseudo-bins need dust_wnu; x_bin0 >= n_lam and x_bins must be multiples of 192");
+  if (d->n_chunk != ((d->x_bins > 0 ? d->x_bin0 + d->x_bins : d->n_lam) + lch - 1) / lch) return fail(SB2_ERR_INVALID, "bad n_chunk");
   if (d->max_batch < 1) return fail(SB2_ERR_INVALID, "max_batch must be positive");
   if (d->rest_frame && d->igm_bin_pow) return fail(SB2_ERR_INVALID, "rest_frame models take no IGM tables");
   int ndev = 0;
@@ -456,7 +458,9 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   if (m->s3_ok) {   // ... and whose per-wavelength tables leave room for the operand ring in shared memory (long native axes do not)
     const int c = d->n_comp, kap_len = d->n_chunk * (sb2::kBN / c), uvl = (int)(d->filt_uv_len + 2 * sb2::kUvPad * d->n_filt);
     const int feat = (d->dust_d0 ? sb2::kFeatDustShape : 0) | (d->kappa_birth ? sb2::kFeatTwoScreens : 0) | (d->dust_wnu ? sb2::kFeatAbsorbed : 0);
-    if (sb2::synth3_smem_bytes(c == 1 ? 96 : 128, 3, d->n_age, uvl, kap_len, true, feat) > (size_t)prop.sharedMemPerBlockOptin) m->s3_ok = false;
+    // (the least launch_synth3_t can run with: two ring stages and no transpose tiles for spectra.  Asking for more here --
+    //  three stages AND the spectra tiles -- sent every two-component model to the round-1 kernel: 4.6 -> 5.6 ms per 1M.)
+    if (sb2::synth3_smem_bytes(c == 1 ? 96 : 128, 2, d->n_age, uvl, kap_len, false, feat) > (size_t)prop.sharedMemPerBlockOptin) m->s3_ok = false;
   }
   if (m->s3_ok) { AL(sf, (np / 128) * (size_t)d->n_age * 128 * 8); AL(s0, np * 8); AL(s1, np * 8); }
   m->cub_bytes = 0;
@@ -642,10 +646,11 @@ int launch_synth3_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_
   x.kb_split = a.n_kb / 2;
   bool spec = false;
   const int kap_len = m->d.n_chunk * (sb2::kBN / C);
-  if (SPEC && sb2::synth3_smem_bytes(N, 3, x.n_age, m->uv_len, kap_len, true, FEAT) <= m->smem_optin) { spec = true; a2.spec_smem = 1; }
+  const int feat_tab = a.x_count > 0 ? (FEAT & ~sb2::kFeatAbsorbed) : FEAT;    // pseudo-bins: the energy weights are 1, no table
+  if (SPEC && sb2::synth3_smem_bytes(N, 3, x.n_age, m->uv_len, kap_len, true, feat_tab) <= m->smem_optin) { spec = true; a2.spec_smem = 1; }
   int ns = sb2::kS3MaxStages;
-  while (ns > 1 && sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec, FEAT) > m->smem_optin) --ns;
-  const size_t bytes = sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec, FEAT);
+  while (ns > 1 && sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec, feat_tab) > m->smem_optin) --ns;
+  const size_t bytes = sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec, feat_tab);
   if (ns < 2 || bytes > m->smem_optin) return fail(SB2_ERR_INVALID, "synth3_kernel: filter tables leave no room for the operand ring");
   x.n_stages = ns;
   CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -901,7 +906,9 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   CU_TRY(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
   // (spectra and the absorbed-energy sum of the dust emission need every wavelength chunk, not just the filters')
-  if ((rc = run_prep(m, p, nullptr, true, spec_out != nullptr || m->dust_wnu != nullptr, st)) != SB2_OK) return rc;
+  // ... unless the model holds pseudo-bins for that sum and the batch takes the kernel that reads them (synth3_kernel)
+  const bool x_mode = m->d.x_bins > 0 && !p->energy_full_axis && use_s3(m, p);
+  if ((rc = run_prep(m, p, nullptr, true, spec_out != nullptr || (m->dust_wnu != nullptr && !x_mode), st)) != SB2_OK) return rc;
   const sb2_model_desc& d = m->d;
   sb2::SynthArgs a{};
   const bool delta = delta_mode(m, p);
@@ -913,7 +920,14 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.k8_total = (delta ? m->wd_stride : d.k_pad) / 8;
   a.dbg = m->sw.dbg;
   a.two_pass = (!delta && !m->sw.one_pass) ? 1 : 0;
-  a.n_chunk = d.n_chunk; a.n_kb = (a.k8_total + 3) / 4; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
+  {
+    const int lch = sb2::kBN / d.n_comp, lch3 = s3_cols(m) / d.n_comp;
+    a.n_chunk = (d.n_lam + lch - 1) / lch;          // the real axis; the tables (kap_len) also cover the pseudo-bins
+    a.kap_len = d.n_chunk * lch;
+    a.x_first = x_mode ? d.x_bin0 / lch3 : 0;
+    a.x_count = x_mode ? d.x_bins / lch3 : 0;
+  }
+  a.n_kb = (a.k8_total + 3) / 4; a.n_lam = d.n_lam; a.n_filt = d.n_filt;
   a.n_blue = d.n_blue; a.n_blue_pad = m->n_blue_pad; a.uv_len = m->uv_len;
   a.tile_range = m->tile_range;
   a.dust_d0 = m->dust_d0; a.dust_l2 = m->dust_l2; a.g_slope = m->g_slope; a.g_ampl = m->g_ampl;
@@ -1483,11 +1497,12 @@ int sb2_empirical_noise(const double* flux, int64_t n, int32_t n_filt, const sb2
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  long long bx = (n + 255) / 256;
+  // parity mode: one thread per element; production mode: one thread per pair of rows
+  long long bx = ((draws ? n : (n + 1) / 2) + 255) / 256;
   const long long cap = std::max<long long>(1, (long long)n_sm * 8 / n_filt);
   if (bx > cap) bx = cap;
-  if (draws) sb2::empirical_noise_kernel<false><<<dim3((unsigned)bx, (unsigned)n_filt), 256, 0, st>>>(a);
-  else sb2::empirical_noise_kernel<true><<<dim3((unsigned)bx, (unsigned)n_filt), 256, 0, st>>>(a);
+  if (draws) sb2::empirical_noise_kernel<<<dim3((unsigned)bx, (unsigned)n_filt), 256, 0, st>>>(a);
+  else sb2::empirical_noise_fast_kernel<<<dim3((unsigned)bx, (unsigned)n_filt), 256, 0, st>>>(a);
   e = cudaGetLastError();
   cudaFreeAsync(dm, st);
   if (e != cudaSuccess) return fail(SB2_ERR_CUDA, cudaGetErrorString(e));

@@ -66,13 +66,14 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
   double* s_sf = reinterpret_cast<double*>(smem + (size_t)n_stages * kStageBytes);           // [n_age][128]
   float2* s_uv = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(s_sf) + (size_t)X.n_age * 1024);
   float* s_kap = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_uv) + ((A.uv_len * 8 + 15) & ~15));   // attenuation curve (or zeros)
-  const int kap_len = A.n_chunk * (kBN / kComp);
+  const int kap_len = A.kap_len;
   // feature-set tables follow the attenuation curve: dust_d0 | dust_l2 | kappa_birth | wnu (only those the set uses)
   float* s_tab = s_kap + kap_len;
   float* s_d0 = nullptr; float* s_l2 = nullptr; float* s_kapb = nullptr; float* s_wnu = nullptr;
   if constexpr ((kFeat & kFeatDustShape) != 0) { s_d0 = s_tab; s_l2 = s_tab + kap_len; s_tab += 2 * kap_len; }
   if constexpr ((kFeat & kFeatTwoScreens) != 0) { s_kapb = s_tab; s_tab += kap_len; }
-  if constexpr ((kFeat & kFeatAbsorbed) != 0) { s_wnu = s_tab; s_tab += kap_len; }
+  // (with pseudo-bins the energy weights are 1 on the chunks that use them: no table, see launch_synth3_t)
+  if constexpr ((kFeat & kFeatAbsorbed) != 0) { if (A.x_count == 0) { s_wnu = s_tab; s_tab += kap_len; } }
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab);
   uint64_t* full_bar = bars;                                   // [kS3MaxStages] TMA -> MMA
   uint64_t* empty_bar = full_bar + kS3MaxStages;               // [kS3MaxStages] MMA -> TMA
@@ -108,7 +109,7 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
     s_kap[i] = A.kappa[i];
     if constexpr ((kFeat & kFeatDustShape) != 0) { s_d0[i] = A.dust_d0[i]; s_l2[i] = A.dust_l2[i]; }
     if constexpr ((kFeat & kFeatTwoScreens) != 0) s_kapb[i] = A.kappa_birth[i];
-    if constexpr ((kFeat & kFeatAbsorbed) != 0) s_wnu[i] = A.wnu[i];
+    if constexpr ((kFeat & kFeatAbsorbed) != 0) { if (s_wnu) s_wnu[i] = A.wnu[i]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -130,7 +131,9 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
         const int k0 = warp_uniform(A.tile_k0 ? __ldg(A.tile_k0 + tile) : 0);
         const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
         const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
-        for (int c = c_first; c <= c_last; ++c) {
+        const int n_real = max(c_last - c_first + 1, 0), n_c = n_real + A.x_count;   // + the absorbed-energy chunks (SynthArgs)
+        for (int j = 0; j < n_c; ++j) {
+          const int c = j < n_real ? c_first + j : A.x_first + (j - n_real);
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1, 0x3100u + (uint32_t)stage);
             const uint32_t st = s_addr + (uint32_t)stage * kStageBytes, fb = full0 + (uint32_t)stage * 8u;
@@ -173,7 +176,12 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
       for (int tile = blockIdx.x; tile < n_tiles_u; tile += gridDim.x, ++ti) {
         const int4 cr = A.tile_range ? __ldg(A.tile_range + tile) : make_int4(0, c_all_last, 0, 0);
         const int c_first = warp_uniform(cr.x), c_last = warp_uniform(cr.y);
-        const int my_first = c_first + (int)(((uint32_t)c_first ^ me) & 1u), my_last = c_last - (int)(((uint32_t)c_last ^ me) & 1u);
+        const int n_real = max(c_last - c_first + 1, 0), n_c = n_real + A.x_count;
+        auto chunk = [&](int j) { return j < n_real ? c_first + j : A.x_first + (j - n_real); };
+        // first / last position of the tile's chunk list that is mine (chunks go to the issuers by the parity of c)
+        int my_first = 0, my_last = n_c - 1;
+        while (my_first < n_c && (((uint32_t)chunk(my_first) ^ me) & 1u)) ++my_first;
+        while (my_last >= 0 && (((uint32_t)chunk(my_last) ^ me) & 1u)) --my_last;
         if (my_last < my_first) {
           // no chunk of this tile is mine: keep the weights hand-shake in step.  The wait comes first -- this tile's weights
           // are only written once BOTH issuers released the previous tile's, so neither can arrive twice in one phase.
@@ -182,7 +190,8 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
           umma_commit_e(elected, &wfree_bar[0]);
           umma_commit_e(elected, &wfree_bar[1]);
         }
-        for (int c = c_first; c <= c_last; ++c, ++it) {
+        for (int j = 0; j < n_c; ++j, ++it) {
+          const int c = chunk(j);
           // Both issuers walk EVERY chunk and observe every phase of the barriers they share (an mbarrier wait carries one
           // parity bit: a waiter that skipped a phase would alias).  The other issuer's stages are released as soon as they
           // have been seen -- the ring slot is refilled once both have arrived (count 2).
@@ -199,7 +208,7 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
           tc_fence_after();
           const uint32_t d_tmem = tmem_u + buf * kN;
           for (int kb = 0; kb < n_kb; ++kb) {
-            if (c == my_first) {   // this tile's weights: region A before the first k-block, region B before k-block kb_split
+            if (j == my_first) {   // this tile's weights: region A before the first k-block, region B before k-block kb_split
               if (kb == 0) { mbar_wait(&wready_bar[0], ti & 1u, 0x3400u); if (kb_split == 0) mbar_wait(&wready_bar[1], ti & 1u, 0x3401u); tc_fence_after(); }
               else if (kb == kb_split) { mbar_wait(&wready_bar[1], ti & 1u, 0x3402u); tc_fence_after(); }
             }
@@ -218,7 +227,7 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
             }
             umma_commit_e(elected, &empty_bar[stage]);
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
-            if (c == my_last) {    // my last chunk of the tile: hand the weights regions back as their MMAs retire
+            if (j == my_last) {    // my last chunk of the tile: hand the weights regions back as their MMAs retire
               if (kb == kb_free0) umma_commit_e(elected, &wfree_bar[0]);
               if (kb == n_kb - 1) umma_commit_e(elected, &wfree_bar[1]);
             }

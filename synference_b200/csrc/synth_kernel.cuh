@@ -83,6 +83,14 @@ struct SynthArgs {
   float* e_part;             // [kMaxGroups][n_rows] each epilogue group's share of sum_i (unattenuated - attenuated)_i wnu_i
   const float* g_lya;        // per-galaxy Lyman-alpha line term, added to the first component at bin lya_bin; nullptr: none
   int lya_bin;
+  // Absorbed energy from PSEUDO-BINS (synth3_kernel only; x_count = 0: none).  The absorbed-energy sum over the whole axis,
+  // sum_i wnu_i v_i (1 - exp(-tau kappa_i)), depends on a wavelength only through kappa_i, so the host projects the grid
+  // onto x_bins nodes in kappa (degree-7 Lagrange weights; engine.py) and appends them to the axis as extra rows of the
+  // grid with kappa = the node and wnu = 1.  Every tile then multiplies x_count extra chunks [x_first, x_first + x_count)
+  // (units of the launched kernel's chunk) after the chunks its filters need, the energy sum runs on those chunks only,
+  // and the real chunks keep their skipping and the plain epilogue.
+  int x_first, x_count;
+  int kap_len;               // length of the kappa / wnu / ... tables (real axis padded + pseudo-bins)
   const float2* filt_uv;     // padded tables, uv_len entries
   const float* igm;          // [n_tiles][n_blue_pad][128]
   const int* g_m;
@@ -244,9 +252,11 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
       // lo_f - 32 - mmax <= i0 <= hi_f - mmin  (warp-uniform bounds)
       const int w_lo = (lane < A.n_filt ? A.filt_lo[lane < kMaxFilt ? lane : 0] : INT_MAX / 2) - 32 - mmax;
       const int w_hi = (lane < A.n_filt ? A.filt_hi[lane < kMaxFilt ? lane : 0] : -1) - mmin;
-      const int n_c = cr.y - cr.x + 1, rot = chunk_rot(n_c, blockIdx.x / kCta);
+      const int n_real = max(cr.y - cr.x + 1, 0), n_c = n_real + A.x_count;
       for (int j = 0; j < n_c; ++j, ++it) {
-        const int c = chunk_at(cr.x, n_c, rot, j);
+        const bool pseudo = j >= n_real;                       // an absorbed-energy chunk (warp-uniform)
+        const int c = pseudo ? A.x_first + (j - n_real) : cr.x + j;
+        const bool absorb_here = absorbed && (A.x_count == 0 || pseudo);
         if (!kShare && (uint32_t)c % (uint32_t)kGroups != grp) continue;
         const uint32_t buf = it % kBuf;
         mbar_wait(&tfull_bar[kTfPerGroup * grp + (gk % kTfPerGroup)], (gk / kTfPerGroup) & 1u, 0x600u + (it << 12));
@@ -271,7 +281,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
 #pragma unroll 1
         for (int sub = kShare ? (int)grp : 0; sub < kSub; sub += sub_step) {
           const int i0 = c * kLch + sub * 32;
-          const bool last_sub = kShare ? (sub + sub_step >= n_sub) : ((sub == kSub - 1) || (i0 + 32 >= A.n_lam));
+          const bool last_sub = kShare ? (sub + sub_step >= n_sub) : ((sub == kSub - 1) || (!pseudo && i0 + 32 >= A.n_lam));
           float s[32];
           float e_sub = 0.f;   // absorbed energy of this sub-chunk (blocked summation: 4 -> 32 -> axis)
           {
@@ -320,12 +330,12 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
                 if (pg_dust && dust_pg) k4 = dust_shape(k4, epi_tab4<kTabS>(A.dust_d0, T.d0, i0, j4), epi_tab4<kTabS>(A.dust_l2, T.l2, i0, j4), slope, ampl);
                 if (two_screens) {   // young: birth cloud + ISM, old: ISM only (both components are attenuated)
                   const float4 b4 = epi_tab4<kTabS>(A.kappa_birth, T.kappa_birth, i0, j4);
-                  const float4 w4 = absorbed ? epi_tab4<kTabS>(A.wnu, T.wnu, i0, j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  const float4 w4 = !absorb_here ? make_float4(0.f, 0.f, 0.f, 0.f) : pseudo ? make_float4(1.f, 1.f, 1.f, 1.f) : epi_tab4<kTabS>(A.wnu, T.wnu, i0, j4);
                   float e4 = 0.f;
 #define SB2_TS(q, K, B, W) { const float yo = ntaut * (K), yy = fmaf(ntaub, (B), yo), To = ex2_approx(yo), Ty = ex2_approx(yy); \
                              const float vy = ca * __uint_as_float(v[4 * j4 + q]), vo = cb * __uint_as_float(u[4 * j4 + q]); \
                              s[4 * j4 + q] = vy * Ty + vo * To; \
-                             if (absorbed) e4 = fmaf(fmaf(vy, one_minus_ex2(yy, Ty), vo * one_minus_ex2(yo, To)), (W), e4); }
+                             if (absorb_here) e4 = fmaf(fmaf(vy, one_minus_ex2(yy, Ty), vo * one_minus_ex2(yo, To)), (W), e4); }
                   SB2_TS(0, k4.x, b4.x, w4.x) SB2_TS(1, k4.y, b4.y, w4.y) SB2_TS(2, k4.z, b4.z, w4.z) SB2_TS(3, k4.w, b4.w, w4.w)
 #undef SB2_TS
                   e_sub += e4;
@@ -335,8 +345,8 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
                 s[4 * j4 + 1] = ca * (__uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y)) + cb * __uint_as_float(u[4 * j4 + 1]);
                 s[4 * j4 + 2] = ca * (__uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z)) + cb * __uint_as_float(u[4 * j4 + 2]);
                 s[4 * j4 + 3] = ca * (__uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w)) + cb * __uint_as_float(u[4 * j4 + 3]);
-                if (absorbed) {
-                  const float4 w4 = epi_tab4<kTabS>(A.wnu, T.wnu, i0, j4);
+                if (absorb_here) {
+                  const float4 w4 = pseudo ? make_float4(1.f, 1.f, 1.f, 1.f) : epi_tab4<kTabS>(A.wnu, T.wnu, i0, j4);
                   float e4 = ca * __uint_as_float(v[4 * j4 + 0]) * one_minus_ex2(ntaut * k4.x, ex2_approx(ntaut * k4.x)) * w4.x;
                   e4 = fmaf(ca * __uint_as_float(v[4 * j4 + 1]) * one_minus_ex2(ntaut * k4.y, ex2_approx(ntaut * k4.y)), w4.y, e4);
                   e4 = fmaf(ca * __uint_as_float(v[4 * j4 + 2]) * one_minus_ex2(ntaut * k4.z, ex2_approx(ntaut * k4.z)), w4.z, e4);
@@ -363,8 +373,8 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
                 s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * ex2_approx(ntaut * k4.y);
                 s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * ex2_approx(ntaut * k4.z);
                 s[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * ex2_approx(ntaut * k4.w);
-                if (absorbed) {   // (the lone component's coefficient is applied with the final scale, like the fluxes')
-                  const float4 w4 = epi_tab4<kTabS>(A.wnu, T.wnu, i0, j4);
+                if (absorb_here) {   // (the lone component's coefficient is applied with the final scale, like the fluxes')
+                  const float4 w4 = pseudo ? make_float4(1.f, 1.f, 1.f, 1.f) : epi_tab4<kTabS>(A.wnu, T.wnu, i0, j4);
                   float e4 = __uint_as_float(v[4 * j4 + 0]) * one_minus_ex2(ntaut * k4.x, ex2_approx(ntaut * k4.x)) * w4.x;
                   e4 = fmaf(__uint_as_float(v[4 * j4 + 1]) * one_minus_ex2(ntaut * k4.y, ex2_approx(ntaut * k4.y)), w4.y, e4);
                   e4 = fmaf(__uint_as_float(v[4 * j4 + 2]) * one_minus_ex2(ntaut * k4.z, ex2_approx(ntaut * k4.z)), w4.z, e4);
@@ -373,6 +383,12 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
                 }
               }
             }
+          }
+          if (lya_on && absorb_here && pseudo && j == n_real && sub == 0) {
+            // the per-galaxy Lyman-alpha term is not part of the grid, hence not of the pseudo-bins: its absorbed share
+            const float yl = fmaf(two_screens ? ntaub : 0.f, two_screens ? __ldg(A.kappa_birth + A.lya_bin) : 0.f,
+                                  ntaut * __ldg(A.kappa + A.lya_bin));
+            e_sub += (kComp == 2 ? A.g_ca[row] : 1.f) * lya * one_minus_ex2(yl, ex2_approx(yl)) * __ldg(A.wnu + A.lya_bin);
           }
           e_abs += e_sub;
           if (last_sub) {  // all TMEM reads of this accumulator are done: hand it back to the MMA warp
@@ -390,7 +406,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
             for (int j = 0; j < 32; ++j) s[j] *= __ldg(ig + j * 128);
           }
           if constexpr (kSpec) {
-            if (A.out_spec != nullptr) {
+            if (A.out_spec != nullptr && !pseudo) {
               const float sc = orig < 0 ? 0.f : ((kComp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row]);
               if (s_spec != nullptr) {
                 // a thread holds 32 wavelengths of ONE galaxy; transposed through a 32 x 33 tile so that each store
@@ -415,7 +431,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
           }
           // filter numerators: (numU_f, numV_f) += s_i * (U_f[n], V_f[n]),  n = i + m ; loop over the filters whose
           // window overlaps this sub-chunk (warp-uniform), compact code: one body, accumulator picked by a switch
-          unsigned fm = __ballot_sync(FULL, i0 >= w_lo && i0 <= w_hi);
+          unsigned fm = __ballot_sync(FULL, !pseudo && i0 >= w_lo && i0 <= w_hi);
           if (SB2_DBG_BITS(A) & 1) fm = 0u;
 #pragma unroll 1
           while (fm != 0u) {

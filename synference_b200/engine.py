@@ -11,6 +11,7 @@ no torch at all.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -134,6 +135,39 @@ def _dust_emission_tables(generator, lam, n_pad, uv, lo_l, hi_l, off_l, n_blue):
                 dust_duv=np.ascontiguousarray(duv, dtype=np.float32), dust_m_len=m_len)
 
 
+X_BINS = 192          # pseudo-bins of the absorbed-energy sum: nodes in kappa (a multiple of 192 = lcm of the kernels' chunks)
+X_DEGREE = 7          # Lagrange degree of the projection onto the nodes
+X_H_TAU_MAX = 0.42    # node spacing x optical depth up to which the projection is good to < 1e-6 of E_abs (measured)
+
+
+def _energy_pseudo_bins(kappa, wnu, comps, absorbing, n_bins=X_BINS, degree=X_DEGREE):
+    """Project the absorbed-energy sum onto nodes in kappa.
+
+    ``E_abs = sum_i wnu_i L_i (1 - exp(-tau kappa_i))`` (``L`` the light before the screen) sees a wavelength only
+    through ``kappa_i``.  With Lagrange weights ``l_j`` of degree ``degree`` on ``n_bins`` uniform nodes over the curve's range,
+    ``exp(-tau kappa_i) ~= sum_j l_j(kappa_i) exp(-tau node_j)`` and therefore
+    ``E_abs ~= sum_j [sum_i wnu_i l_j(kappa_i) L_i] (1 - exp(-tau node_j))`` (the weights sum to 1, so tau = 0 stays exact):
+    the bracket is linear in the grid, i.e. ``n_bins`` extra rows of it.  Returns ``(nodes, rows)`` with ``rows[c]`` of shape
+    ``(n_bins, n_z, n_age)`` for every component of ``comps`` ((age, Z, lam) arrays; zero rows where ``absorbing[c]`` is False)."""
+    lo, hi = float(kappa.min()), float(kappa.max())
+    span = max(hi - lo, 1e-6)
+    # (nodes as the float32 values the kernel's kappa table holds, so that the weights belong to exactly those nodes)
+    nodes = np.linspace(lo - 1e-6 * span, hi + 1e-6 * span, n_bins).astype(np.float32).astype(np.float64)
+    h = (nodes[-1] - nodes[0]) / (n_bins - 1)
+    first = np.clip(np.floor((kappa - nodes[0]) / h).astype(np.int64) - (degree - 1) // 2, 0, n_bins - degree - 1)
+    proj = np.zeros((kappa.size, n_bins))
+    rows_i = np.arange(kappa.size)
+    for a in range(degree + 1):
+        wgt = np.ones_like(kappa)
+        for b in range(degree + 1):
+            if a != b:
+                wgt = wgt * (kappa - nodes[first + b]) / (nodes[first + a] - nodes[first + b])
+        proj[rows_i, first + a] = wgt
+    proj *= wnu[:, None]
+    rows = [np.einsum("azl,lj->jza", np.asarray(c, dtype=np.float64), proj) if on else None for c, on in zip(comps, absorbing)]
+    return nodes, h, rows
+
+
 def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, filters: FilterCollection,
                  cosmo=Planck18, igm=True, variant="nu", z_table_max=100.0):
     """All float64 host-side derivations behind ``sb2_model_desc`` (kept as numpy arrays)."""
@@ -181,11 +215,35 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
     grid_scale = float(max(c.max() for c in comps))
     if not np.isfinite(grid_scale) or grid_scale <= 0:
         raise ValueError("grid spectra must be finite and not all zero")
+    # dust emission: the absorbed-energy sum through pseudo-bins (see _energy_pseudo_bins) when the exponent is tau x ONE
+    # global curve -- a global dust curve, and for two screens a birth-cloud curve proportional to the ISM one
+    x_bin0 = x_bins = 0
+    x_nodes = x_rows = None
+    x_h = x_ratio = 0.0
+    wants_energy = (general is None and kappa is not None and not dust_free
+                    and getattr(emission_model, "has_dust_emission", lambda k: False)(emission_key))
+    if wants_energy and not getattr(dust, "per_galaxy", False) and not os.environ.get("SB2_NO_PSEUDO_BINS"):
+        kb = emission_model.dust_curve_birth.get_tau(lam) if two_screens else None
+        big = np.abs(kappa) > 1e-6 * np.abs(kappa).max()
+        x_ratio = float(np.median(kb[big] / kappa[big])) if two_screens else 0.0
+        if not two_screens or np.allclose(kb, x_ratio * kappa, rtol=1e-9, atol=1e-12 * np.abs(kappa).max()):
+            nu = 2.99792458e18 / lam
+            w_nu = np.empty(n_lam)
+            w_nu[1:-1] = 0.5 * (nu[:-2] - nu[2:])
+            w_nu[0], w_nu[-1] = 0.5 * (nu[0] - nu[1]), 0.5 * (nu[-2] - nu[-1])
+            # which components the screen acts on: both of the two-screen model, else the attenuated one (the first)
+            x_nodes, x_h, x_rows = _energy_pseudo_bins(np.asarray(kappa, dtype=np.float64), w_nu / DUST_W0, comps,
+                                                       [True, True] if two_screens else [True] + [False] * (n_comp - 1))
+            x_bins = X_BINS
+            x_bin0 = (n_lam + 191) // 192 * 192
+            n_chunk = (x_bin0 + x_bins + lch - 1) // lch
     gt = np.zeros((n_chunk, n_comp, lch, k_pad), dtype=np.float64)
     for ci, comp in enumerate(comps):
         # (age, Z, lam) -> (lam, Z, age) -> rows lam, columns k = iz*na_pad + ia
         pad = np.zeros((n_chunk * lch, nz, na_pad))
         pad[:n_lam, :, :na] = np.transpose(comp, (2, 1, 0)) / grid_scale
+        if x_bins and x_rows[ci] is not None:
+            pad[x_bin0:x_bin0 + x_bins, :, :na] = x_rows[ci] / grid_scale
         gt[:, ci, :, :nz * na_pad] = pad.reshape(n_chunk, lch, nz * na_pad)
     gt = gt.reshape(n_chunk * CHUNK_COLS, k_pad)
     gt_hi, gt_lo = tf32_split(gt)
@@ -193,9 +251,13 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
     if kappa is not None:
         kap = np.zeros(n_chunk * lch, dtype=np.float32)
         kap[:n_lam] = kappa
+        if x_bins:
+            kap[x_bin0:x_bin0 + x_bins] = x_nodes
         if two_screens:
             kap_birth = np.zeros_like(kap)
             kap_birth[:n_lam] = emission_model.dust_curve_birth.get_tau(lam)
+            if x_bins:
+                kap_birth[x_bin0:x_bin0 + x_bins] = x_ratio * x_nodes
         if getattr(dust, "per_galaxy", False) and not dust_free:
             # per-galaxy slope / bump amplitude: kappa holds the curve at slope = 0, ampl = 0 (get_tau already used 0 for
             # the string-named ones; a numeric one is broadcast to every galaxy by SynthEngine._fill)
@@ -251,6 +313,9 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
         # travels as coef_att (SynthEngine._fill)
         single_is_unatt=(n_comp == 1 and not has_att),
         general=general,
+        x_bin0=x_bin0, x_bins=x_bins,
+        # largest tau_V (+ ratio x tau_V_birth) the pseudo-bins are accurate for; beyond it a batch sums over the whole axis
+        x_tau_max=(X_H_TAU_MAX / x_h if x_bins else 0.0), x_birth_ratio=x_ratio,
     )
     if igm:
         laf, dla = (igm if isinstance(igm, tuple) else (_igm.INOUE14_LAF, _igm.INOUE14_DLA))
@@ -264,6 +329,8 @@ def build_tables(grid: Grid, emission_model: EmissionModel, emission_key: str, f
     if getattr(emission_model, "has_dust_emission", lambda k: False)(emission_key) and kap is not None and not dust_free:
         tables.update(_dust_emission_tables(emission_model.dust_emission, lam, n_chunk * lch, uv, lo_l, hi_l, off_l,
                                             tables["igm"]["n_blue"] if tables["igm"] is not None else 0))
+        if x_bins:
+            tables["dust_wnu"][x_bin0:x_bin0 + x_bins] = 1.0
     lya = getattr(emission_model, "lya_line", lambda k: None)(emission_key)
     if lya is not None:
         # the line sits in the first grid of every recipe, i.e. in the kernel's component A, except when that grid is
@@ -338,6 +405,7 @@ class SynthEngine:
         d.cosmo_age, d.cosmo_dage = ptr(cz.age, C.c_double), ptr(cz.dage, C.c_double)
         d.base_mass, d.max_batch = self.base_mass, self.max_batch
         d.rest_frame = 1 if rest_frame else 0
+        d.x_bin0, d.x_bins = int(t["x_bin0"]), int(t["x_bins"])
         if fast_math:
             fm = _fm.build_tables()
             d.fm_log_tab, d.fm_exp_tab = ptr(fm["log_tab"], C.c_double), ptr(fm["exp_tab"], C.c_double)
@@ -393,6 +461,17 @@ class SynthEngine:
         if p.tau_v_birth is None and self.tables["kappa_birth"] is not None:
             raise ValueError("the emission model has two dust screens: GalaxyParams.tau_v_birth is required")
         s.tau_v_birth = get_ptr(p.tau_v_birth)
+        if self.tables.get("x_bins"):
+            # pseudo-bins of the absorbed-energy sum: good to < 1e-6 up to x_tau_max; a batch beyond it sums over the axis
+            def top(a):
+                if a is None:
+                    return 0.0
+                return float(a.max()) if hasattr(a, "max") else float(np.max(a))
+            key = (id(p.tau_v), id(p.tau_v_birth))
+            if getattr(p, "_tau_top", (None, 0.0))[0] != key:      # (a DeviceParams batch is filled on every step)
+                p._tau_top = (key, top(p.tau_v) + self.tables["x_birth_ratio"] * top(p.tau_v_birth))
+            tau_eff = p._tau_top[1]
+            s.energy_full_axis = 1 if (not np.isfinite(tau_eff) or tau_eff > self.tables["x_tau_max"]) else 0
         return s
 
     def _dust_arrays(self, p: GalaxyParams, get_ptr):

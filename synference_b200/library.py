@@ -180,7 +180,7 @@ class GalaxyBasis:
             if key in self.params_to_ignore:
                 continue
             v = np.asarray(strip_units(value), dtype=float)
-            if v.size and v.min() == v.max():        # one distinct value (np.unique sorts: 10x the time for 1M rows)
+            if v.size and bool((v == v.flat[0]).all()):   # one distinct value (np.unique sorts: 10x the time for 1M rows)
                 self.fixed_param_names.append(key)
                 self.fixed_param_values.append(float(v.flat[0]))
                 self.fixed_param_units.append(str(value.units) if has_units(value) else "")
@@ -324,9 +324,14 @@ class GalaxyBasis:
         # pipeline files are written by a background thread (the npz / HDF5 write releases the GIL in its I/O), so the
         # next batch's kernels run while the previous batch's file goes to disk; what was written is also kept in
         # memory for CombinedBasis.load_bases, which otherwise re-reads every file it has just produced
-        writer = ThreadPoolExecutor(max_workers=1) if save else None
+        writer = ThreadPoolExecutor(max_workers=self._WRITER_THREADS) if save else None
         pending = []
         self._pipeline_cache = {"out_dir": os.path.abspath(out_dir), "parts": [], "complete": True}
+        full_props = {name: np.asarray(strip_units(arr), dtype=float) for name, arr in self.all_parameters.items()}
+        # create_mock_library's single-base build: the kernels also write the mass-scaled float64 block of every batch into
+        # its columns of the library's (n_filters, n_galaxies) matrix (sb2_params.scaled_ld), so that create_full_library has
+        # no cast / multiply / transpose left to do on the host
+        sink = getattr(self, "_library_sink", None) if len(keys) == 1 else None
         for batch_i in range(n_batches):
             sl = slice(batch_i * batch_size, min(n_gal, (batch_i + 1) * batch_size))
             final = fullpath if n_batches == 1 else fullpath.replace(".hdf5", f"_{batch_i + 1}.hdf5")
@@ -352,6 +357,7 @@ class GalaxyBasis:
             # the pipeline always runs at the base mass (library.py:3217): no mass scaling here
             p.log_mass = None
             datasets = {}
+            phot_blocks = []
             for key in keys:
                 eng = self._engine(key, igm=igm, max_batch=max(batch_size, 1))
                 if getattr(self.emission_model, "fesc_per_galaxy", False):
@@ -369,7 +375,14 @@ class GalaxyBasis:
                 p.fesc_lya = None
                 if lya_name is not None and self.emission_model.lya_line(key) is not None:
                     p.fesc_lya = np.asarray(strip_units(self.all_parameters[lya_name]), dtype=float)[sl]
-                flux = eng.photometry(p, scaled=False)
+                if sink is not None and not eng.general:
+                    p.log_mass = sink["log_mass"][sl]
+                    flux = eng.photometry(p, scaled=False, library_out=(sink["matrix"], sl.start))
+                    p.log_mass = None
+                    sink["filled"] += sl.stop - sl.start
+                else:
+                    sink = None
+                    flux = eng.photometry(p, scaled=False)
                 results["photometry"][key].append(flux)
                 if extra_analysis_functions and key == keys[0]:
                     # by-products of the weights (library.py:2593-2601 stores callback results as supp_<name>)
@@ -380,8 +393,8 @@ class GalaxyBasis:
                         datasets[f"Galaxies/supp_{name}"] = vals
                         supp_units[name] = units
                 label = self.instrument.label
-                for j, code in enumerate(eng.filter_codes):
-                    datasets[f"Galaxies/Stars/Photometry/Fluxes/{key}/{label}/{code}"] = flux[:, j].astype(np.float64)
+                # the per-filter float64 columns of the pipeline file are cut from this matrix by the writer thread
+                phot_blocks.append((f"Galaxies/Stars/Photometry/Fluxes/{key}/{label}/", list(eng.filter_codes), flux))
                 if key in spectra_keys:
                     spec = eng.spectra(p)
                     results["spectra"][key].append(spec)
@@ -389,8 +402,8 @@ class GalaxyBasis:
             elapsed = datetime.now() - start
             logger.info(f"Pipeline (CUDA) took {elapsed} for {sl.stop - sl.start} galaxies.")
             if save:
-                for name, arr in self.all_parameters.items():
-                    datasets[f"Galaxies/{name}"] = np.asarray(strip_units(arr), dtype=float)[sl]
+                for name, arr in full_props.items():
+                    datasets[f"Galaxies/{name}"] = arr[sl]
                 datasets["Galaxies/mass"] = np.full(sl.stop - sl.start, 10.0 ** 9)
                 datasets["Wavelengths"] = np.asarray(self.grid.lam)
                 attrs = {"varying_param_names": list(self.varying_param_names),
@@ -404,16 +417,23 @@ class GalaxyBasis:
                          "InstrumentLabel": self.instrument.label, "batch": batch_i + 1, "n_batches": n_batches,
                          "rank": rank, "world_size": size, "galaxy_start": sl.start, "galaxy_stop": sl.stop,
                          "supp_names": list(supp_units), "supp_units": [supp_units[k] for k in supp_units]}
-                self._pipeline_cache["parts"].append((os.path.basename(final), datasets, attrs))
+                self._pipeline_cache["parts"].append((os.path.basename(final), datasets, attrs, phot_blocks))
                 self._pipeline_cache.setdefault("phot", {}).setdefault(keys[0], []).append(results["photometry"][keys[0]][-1])
-                pending.append(writer.submit(write_container, final, datasets, attrs, False))
+                pending.append(writer.submit(_write_pipeline_part, final, datasets, attrs, phot_blocks))
                 logger.info(f"Writing pipeline to disk at {final}.")
         # the files keep being written while the caller goes on (create_mock_library compiles the library from the in-memory
         # copy meanwhile); wait_for_writes() joins them and re-raises a failed write
+        if sink is not None and save and self._pipeline_cache["complete"] and sink["filled"] == sink["matrix"].shape[1]:
+            self._pipeline_cache["scaled_matrix"] = {keys[0]: (sink["matrix"], sink["log_mass"])}
+        self._pipeline_cache["full_props"] = full_props
         self._pending_writes = (writer, pending)
         if not getattr(self, "_defer_write_join", False):
             self.wait_for_writes()
+        else:
+            return None      # create_mock_library's internal call: nobody reads the concatenated copies
         return {k: {kk: (np.concatenate(vv) if vv else None) for kk, vv in v.items()} for k, v in results.items()}
+
+    _WRITER_THREADS = 4   # file writes release the GIL (crc32 and write of whole arrays): batches go to disk side by side
 
     def wait_for_writes(self):
         """Block until the pipeline files of the last process_galaxies call are on disk."""
@@ -463,12 +483,20 @@ class GalaxyBasis:
         if cat_type == "spectra" and not spectra_to_save:
             spectra_to_save = [emission_model_key]
         self._defer_write_join = bool(compile_grid)      # the library is compiled from memory while the files are written
+        self._library_sink = None
+        lm = np.asarray(log_stellar_masses, dtype=float)
+        if compile_grid and cat_type == "photometry" and lm.ndim == 1 and lm.size == len(combined.redshifts) and not self.build_library:
+            if galaxy_mask is not None:
+                lm = lm[galaxy_mask]
+            self._library_sink = {"matrix": np.empty((len(self.instrument.filters.filter_codes), lm.size)),
+                                  "log_mass": np.ascontiguousarray(lm), "filled": 0}
         try:
             combined.process_bases(n_proc=n_proc, overwrite=overwrite, verbose=verbose, batch_size=batch_size,
                                    multi_node=multi_node, galaxies_mask=galaxy_mask, spectra_to_save=spectra_to_save,
                                    em_lines_to_save=em_lines_to_save, **extra_analysis_functions)
         finally:
             self._defer_write_join = False
+            self._library_sink = None
         if not compile_grid:
             self.wait_for_writes()
         if compile_grid:
@@ -477,10 +505,20 @@ class GalaxyBasis:
             combined._extra_datasets, combined._extra_attrs = self._model_block(
                 {"emission_model_key": emission_model_key, "timestamp": datetime.now().isoformat(), "cat_type": cat_type},
                 parameter_transforms_to_save)
-            if cat_type == "photometry":
-                combined.create_library(overwrite=overwrite)
-            else:
-                combined.create_spectral_grid(overwrite=overwrite)
+            combined._save_executor = ThreadPoolExecutor(max_workers=1)   # the library file is written beside the pipeline files
+            try:
+                if cat_type == "photometry":
+                    combined.create_library(overwrite=overwrite)
+                else:
+                    combined.create_spectral_grid(overwrite=overwrite)
+            finally:
+                ex, combined._save_executor = combined._save_executor, None
+                pending_save, combined._pending_save = getattr(combined, "_pending_save", None), None
+                try:
+                    if pending_save is not None:
+                        pending_save.result()
+                finally:
+                    ex.shutdown()
             self.wait_for_writes()
             logger.info("Processed the bases and saved the output.")
             return combined
@@ -597,6 +635,24 @@ class GalaxyBasis:
         raise NotImplementedError("plotting helpers are outside the hot path (SURVEY 2 row 13)")
 
 
+def _photometry_columns(phot_blocks):
+    """``{dataset path: (n,) float64}`` of a batch's per-filter columns (the reference's pipeline layout,
+    ``library.py:3437-3565``) from the kernels' float32 ``(n, n_filt)`` matrices: one transposing cast per block."""
+    out = {}
+    for prefix, codes, flux in phot_blocks:
+        cols = np.ascontiguousarray(flux.T, dtype=np.float64)
+        for j, code in enumerate(codes):
+            out[prefix + code] = cols[j]
+    return out
+
+
+def _write_pipeline_part(path, datasets, attrs, phot_blocks):
+    """Writer-thread body of process_galaxies: cut the photometry columns, then write the container."""
+    data = _photometry_columns(phot_blocks)
+    data.update(datasets)
+    return write_container(path, data, attrs, False)
+
+
 def _library_compression():
     """Deflate level for library files: ``SYNFERENCE_B200_COMPRESS`` = 0 (default: none -- float photometry deflates by a
     quarter at 25 MB/s on one core, which would be most of a library build; SURVEY: "optional compression off"), 1 ... 9."""
@@ -604,6 +660,38 @@ def _library_compression():
         return int(os.environ.get("SYNFERENCE_B200_COMPRESS", "0"))
     except ValueError:
         return 0
+
+
+class _LazyColumns(dict):
+    """``{filter code: column}`` whose columns are built on first access."""
+
+    def __init__(self, codes, make):
+        super().__init__()
+        self._codes, self._make = list(codes), make
+
+    def __missing__(self, code):
+        if code not in self._codes:
+            raise KeyError(code)
+        self[code] = self._make(code)
+        return self[code]
+
+    def __contains__(self, code):
+        return code in self._codes
+
+    def __iter__(self):
+        return iter(self._codes)
+
+    def __len__(self):
+        return len(self._codes)
+
+    def keys(self):
+        return list(self._codes)
+
+    def items(self):
+        return [(c, self[c]) for c in self._codes]
+
+    def values(self):
+        return [self[c] for c in self._codes]
 
 
 class _LazyGalaxyList:
@@ -681,8 +769,8 @@ class CombinedBasis:
             parts = []
             from_cache = bool(cache and cache["complete"] and cache["parts"] and cache["out_dir"] == os.path.abspath(self.out_dir))
             if from_cache:
-                for fname, data, attrs in cache["parts"]:      # just written by process_galaxies: no need to read them back
-                    parts.append((int(attrs.get("galaxy_start", 0)), int(attrs.get("rank", 0)), data, attrs))
+                for fname, data, attrs, blocks in cache["parts"]:      # just written by process_galaxies: no need to read them back
+                    parts.append((int(attrs.get("galaxy_start", 0)), int(attrs.get("rank", 0)), data, attrs, blocks))
             else:
                 base.wait_for_writes()
                 files = []
@@ -703,21 +791,32 @@ class CombinedBasis:
             codes = list(parts[0][3].get("FilterCodes", base.instrument.filters.filter_codes))
             props, supp_props = {}, {}
             s_units = dict(zip(parts[0][3].get("supp_names", []), parts[0][3].get("supp_units", [])))
+            # every batch of this process is in the cache, in order: a parameter column is the basis' own full array
+            whole = cache.get("full_props", {}) if from_cache else {}
             for name in parts[0][2]:
                 if name.startswith("Galaxies/") and name.count("/") == 1:
                     short = name.split("/", 1)[1]
-                    col = np.concatenate([p[2][name] for p in parts])
+                    col = whole[short] if short in whole else np.concatenate([p[2][name] for p in parts])
                     if short.startswith("supp_"):      # library.py:3446-3448
                         supp_props[short[5:]] = (col, s_units.get(short[5:], "dimensionless"))
                     else:
                         props[short] = col
-            phot = {c: np.concatenate([p[2][f"Galaxies/Stars/Photometry/Fluxes/{key}/{label}/{c}"] for p in parts])
-                    for c in codes}
+            pkey = f"Galaxies/Stars/Photometry/Fluxes/{key}/{label}/"
+            if from_cache:       # columns are cut from the kernels' matrices only if somebody asks for them
+                phot = _LazyColumns(codes, lambda c, parts=parts, pkey=pkey: np.concatenate(
+                    [_photometry_columns(p[4])[pkey + c] for p in parts]))
+            else:
+                phot = {c: np.concatenate([p[2][pkey + c] for p in parts]) for c in codes}
             entry = {"properties": props, "observed_photometry": phot, "supp_properties": supp_props,
                      "wavelengths": parts[0][2]["Wavelengths"], "filter_codes": codes, "stem": stem}
             if cache and cache["complete"] and cache.get("phot", {}).get(key) and from_cache:
                 # the (N, n_filt) float32 matrix the kernels produced, in batch order (= sorted by galaxy_start)
-                entry["photometry_matrix"] = np.concatenate(cache["phot"][key]) if len(cache["phot"][key]) > 1 else cache["phot"][key][0]
+                if key in cache.get("scaled_matrix", {}):
+                    # (n_filt, N) float64 already scaled to the stellar masses it was built for, and those masses
+                    entry["scaled_matrix"], entry["scaled_log_mass"] = cache["scaled_matrix"][key]
+                    entry["photometry_blocks"] = cache["phot"][key]
+                else:
+                    entry["photometry_matrix"] = np.concatenate(cache["phot"][key]) if len(cache["phot"][key]) > 1 else cache["phot"][key][0]
             skey = f"Galaxies/Stars/Spectra/SpectralFluxDensities/{key}"
             if load_spectra:
                 if skey not in parts[0][2]:
@@ -872,7 +971,13 @@ class CombinedBasis:
             scale = (weights[:, i] if multi else 1.0) * 10.0 ** log_mass / mass
             if spectral_mode:
                 contrib = o["observed_spectra"].astype(np.float32) * scale[:, None]
+            elif (not multi and "scaled_matrix" in o and filter_codes == list(o["filter_codes"]) and np.all(mass == 1e9)
+                  and o["scaled_matrix"].shape[1] == len(log_mass) and np.array_equal(o["scaled_log_mass"], log_mass)):
+                # the kernels wrote float32(base) x 10^log_mass / base_mass into this matrix batch by batch (library_out)
+                contrib = o["scaled_matrix"]
             else:
+                if "photometry_blocks" in o and "photometry_matrix" not in o:
+                    o["photometry_matrix"] = np.concatenate(o["photometry_blocks"])
                 if "photometry_matrix" in o and filter_codes == list(o["filter_codes"]):
                     phot = o["photometry_matrix"]                     # float32 (N, n_filt) straight from the kernels
                 else:
@@ -943,6 +1048,8 @@ class CombinedBasis:
         if len(library_dict["parameter_names"]) != par.shape[0]:
             raise ValueError("parameter_names does not match the parameter array")
         for name, arr in ((check_type, phot), ("parameters", par)):
+            if np.isfinite(arr).all():       # one pass over the (large) array in the usual case
+                continue
             if np.isnan(arr).any():
                 raise ValueError(f"{name} array contains NaN values.")
             if np.isinf(arr).any():
@@ -987,7 +1094,11 @@ class CombinedBasis:
             attrs[param] = [str(getattr(b, param)) for b in self.bases]
         attrs.update(getattr(self, "_extra_attrs", None) or {})
         datasets.update(getattr(self, "_extra_datasets", None) or {})
-        write_container(path, datasets, attrs, compress=_library_compression())
+        ex = getattr(self, "_save_executor", None)
+        if ex is not None:       # create_mock_library joins this write before it returns
+            self._pending_save = ex.submit(write_container, path, datasets, attrs, _library_compression())
+        else:
+            write_container(path, datasets, attrs, compress=_library_compression())
         self.library_path = path
 
     def load_library_from_file(self, file_path: str):

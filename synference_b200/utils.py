@@ -113,8 +113,8 @@ def check_log_scaling(arr) -> bool:
 
 # ---- library container --------------------------------------------------------
 # The reference writes HDF5 (library.py:4074-4153).  h5py is not installable here, so
-# the same logical layout (dataset paths + attrs) is kept in an .npz next to a JSON
-# attribute block; when h5py is importable a real HDF5 file is written instead.
+# the same logical layout (dataset paths + attrs) is kept in a flat container (raw arrays behind a JSON
+# header when uncompressed, a deflated .npz otherwise); when h5py is importable a real HDF5 file is written instead.
 
 def _have_h5py():
     try:
@@ -167,18 +167,67 @@ def write_container(path, datasets: dict, attrs: dict, compress=True):
                 else:
                     f.attrs[k] = v
         return path
+    if level == 0:
+        return _write_raw_container(path, datasets, attrs)
+    import zipfile
     payload = {k.replace("/", "::"): np.asarray(v) for k, v in datasets.items()}
     payload["__attrs__"] = np.frombuffer(json.dumps(_jsonable(attrs)).encode(), dtype=np.uint8)
-    if level in (0, 6):
+    if level == 6:
         with open(path, "wb") as fh:  # keep the reference's file name, whatever its suffix
-            (np.savez_compressed if level else np.savez)(fh, **payload)
+            np.savez_compressed(fh, **payload)
         return path
-    import zipfile
     with zipfile.ZipFile(path, "w", compression=zipfile.ZIP_DEFLATED, compresslevel=level, allowZip64=True) as zf:
         for k, v in payload.items():
             with zf.open(k + ".npy", "w", force_zip64=True) as f:
                 np.lib.format.write_array(f, np.asanyarray(v), allow_pickle=False)
     return path
+
+
+# Uncompressed container without h5py: magic, header length, JSON header ({dataset: dtype, shape, offset}, attrs), then the
+# arrays' bytes at 64-byte aligned offsets.  One write per array straight from its memory: no CRC pass and no staging copy
+# (an .npz member costs both), so a library build's files go out at page-cache speed from the writer threads.
+_RAW_MAGIC = b"SB2CONT1"
+
+
+def _write_raw_container(path, datasets: dict, attrs: dict):
+    arrays, table, off = [], [], 0
+    for k, v in datasets.items():
+        a = np.asanyarray(v)
+        if a.dtype.hasobject:
+            raise TypeError(f"dataset {k}: object arrays cannot be stored")
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        off = (off + 63) // 64 * 64
+        table.append([k, a.dtype.str, list(a.shape), off, int(a.nbytes)])
+        arrays.append((off, a))
+        off += a.nbytes
+    header = json.dumps({"datasets": table, "attrs": _jsonable(attrs)}).encode()
+    start = (16 + len(header) + 63) // 64 * 64
+    with open(path, "wb", buffering=0) as fh:
+        fh.write(_RAW_MAGIC + len(header).to_bytes(8, "little") + header + b"\0" * (start - 16 - len(header)))
+        pos = 0
+        for o, a in arrays:
+            if o > pos:
+                fh.write(b"\0" * (o - pos))
+            if a.nbytes:
+                fh.write(a.reshape(-1).view(np.uint8))
+            pos = o + a.nbytes
+    return path
+
+
+def _read_raw_container(path):
+    with open(path, "rb") as fh:
+        head = fh.read(16)
+        n = int.from_bytes(head[8:16], "little")
+        meta = json.loads(fh.read(n).decode())
+        start = (16 + n + 63) // 64 * 64
+        out = {}
+        for k, dt, shape, off, nbytes in meta["datasets"]:
+            dt = np.dtype(dt)
+            fh.seek(start + off)
+            a = np.fromfile(fh, dtype=dt, count=nbytes // dt.itemsize if dt.itemsize else 0)
+            out[k] = a.reshape(shape)
+    return out, meta["attrs"]
 
 
 def _jsonable(x):
@@ -212,7 +261,9 @@ def read_container(path):
     """Inverse of :func:`write_container` -> ``(datasets, attrs)``; group / dataset attributes come back under
     ``"Group/Sub@name"`` keys."""
     with open(path, "rb") as fh:
-        magic = fh.read(4)
+        magic = fh.read(8)
+    if magic == _RAW_MAGIC:
+        return _read_raw_container(path)
     if magic[:2] == b"PK":
         d = np.load(path, allow_pickle=False)
         attrs = json.loads(bytes(d["__attrs__"]).decode()) if "__attrs__" in d.files else {}

@@ -54,9 +54,15 @@ class _StubEngine:
     def __init__(self, codes):
         self.filter_codes = list(codes)
 
-    def photometry(self, p, scaled=False):
+    general = False
+
+    def photometry(self, p, scaled=False, library_out=None):
         z = np.asarray(p.redshift, dtype=np.float64)
-        return np.stack([(j + 1) * (1.0 + z) for j in range(len(self.filter_codes))], 1).astype(np.float32)
+        base = np.stack([(j + 1) * (1.0 + z) for j in range(len(self.filter_codes))], 1).astype(np.float32)
+        if library_out is not None:      # SynthEngine.photometry's contract: the mass-scaled block, transposed, in the same pass
+            mat, col0 = library_out
+            mat[:, col0:col0 + len(z)] = base.T.astype(np.float64) * (10.0 ** np.asarray(p.log_mass) / 1e9)
+        return base
 
 
 def _library_worker(rank, world, port, n, tmp):

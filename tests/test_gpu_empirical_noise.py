@@ -177,3 +177,82 @@ def test_feature_builder_with_empirical_models():
     assert abs(zs.mean()) < 0.05 and abs(zs.std() - 1) < 0.05 and par.shape == (4000, 2)
     mu = np.interp(m0, centers, mod.median_error_in_bin)
     assert abs(np.mean(feat[:, 3:] / mu) - 1) < 0.05
+
+
+def _same_law(want, got, what):
+    """Two samples of one distribution: equal share of non-finite values, and empirical CDFs that agree to 0.008 (5 standard
+    errors at 100 000 draws) at the first sample's 2 / 16 / 50 / 84 / 98 % points -- evaluated a relative 1e-4 to either side
+    of each point, which steps over float32 rounding of a point mass (a constant a rule puts in place of many sources)."""
+    fin_w, fin_g = np.isfinite(want), np.isfinite(got)
+    assert abs(fin_w.mean() - fin_g.mean()) < 0.01, what          # log of a negative noisy flux: NaN on both sides
+    w, g = want[fin_w], got[fin_g]
+    for t in np.quantile(w, [0.02, 0.16, 0.5, 0.84, 0.98]):
+        for eps in (-1e-4, 1e-4):
+            tt = t + eps * abs(t)
+            assert abs(np.mean(w <= tt) - np.mean(g <= tt)) < 0.008, (what, t, eps, np.mean(w <= tt), np.mean(g <= tt))
+
+
+def test_production_kernel_draws_from_the_same_law_as_the_parity_kernel():
+    """`empirical_noise_fast_kernel` (Philox, float32 arithmetic) against `empirical_noise_kernel` (float64, injected numpy
+    draws) for unit changes, sigma clipping, re-drawn errors, both upper-limit rules and the asinh models: at a handful of
+    fixed true fluxes the two outputs are samples of one distribution, so their quantiles and the share of replaced sources
+    agree within sampling error (`_same_law`)."""
+    rng = np.random.default_rng(17)
+    centers = np.geomspace(0.5, 5000.0, 24)
+    med = 2.0 + 0.02 * centers
+    sd = 0.3 + 0.004 * centers
+    m_per = 100_000
+    levels = np.array([4.0, 30.0, 400.0, 3000.0, 9000.0])                   # nJy, the last one beyond the table
+    flux = np.repeat(levels, m_per)[None, :]
+    cfgs = [
+        dict(iu="nJy", out="AB", extrapolate=False, kw=dict()),
+        dict(iu="uJy", out="uJy", extrapolate=True, kw=dict(sigma_clip=2.5, error_type="observed")),
+        dict(iu="nJy", out="nJy", extrapolate=False, kw=dict(upper_limits=True, treat_as_upper_limits_below=3.0,
+             upper_limit_flux_behaviour=7.5, upper_limit_flux_err_behaviour="max", max_flux_error=40.0)),
+        dict(iu="nJy", out="AB", extrapolate=True, kw=dict(upper_limits=True, treat_as_upper_limits_below=2.0,
+             upper_limit_flux_behaviour="scatter_limit", upper_limit_flux_err_behaviour="upper_limit", error_type="observed")),
+    ]
+    for c in cfgs:
+        scale = {"nJy": 1.0, "uJy": 1e-3}[c["iu"]]
+        mod = S.GeneralEmpiricalUncertaintyModel(centers * scale, None, flux_unit=c["iu"], already_binned=True,
+                                                 bin_median_errors=med * scale, bin_std_errors=sd * scale, return_noise=True,
+                                                 extrapolate=c["extrapolate"], **c["kw"])
+        if c["kw"].get("upper_limits"):
+            mod.upper_limit_value = 6.0 * scale
+        n = flux.shape[1]
+        draws = np.stack([rng.uniform(0, 1, (1, n)), rng.uniform(0, 1, (1, n)) if "sigma_clip" in c["kw"] else rng.standard_normal((1, n)),
+                          rng.uniform(0, 1, (1, n)), rng.uniform(0, 1, (1, n))])
+        want_f, want_s = S.apply_empirical_noise_models(flux, ["F"], {"F": mod}, N_scatters=1, flux_units="nJy",
+                                                        normed_flux_units=c["out"], return_errors=True, draws=draws)
+        got_f, got_s = S.apply_empirical_noise_models(flux, ["F"], {"F": mod}, N_scatters=1, flux_units="nJy",
+                                                      normed_flux_units=c["out"], return_errors=True, seed=9, epoch=2)
+        if c["out"] == "AB":       # compare on a linear scale: a magnitude's far tail (noisy flux -> 0) has no stable quantiles
+            want_s, got_s = want_s * 10 ** (-0.4 * want_f), got_s * 10 ** (-0.4 * got_f)
+            want_f, got_f = 10 ** (-0.4 * want_f), 10 ** (-0.4 * got_f)
+        for k in range(len(levels)):
+            sl = slice(k * m_per, (k + 1) * m_per)
+            _same_law(want_f[0, sl], got_f[0, sl], (c, k, "flux"))
+            _same_law(want_s[0, sl], got_s[0, sl], (c, k, "sigma"))
+    # asinh magnitudes: tables in asinh mags and in a linear unit
+    from synference_b200.units import Quantity
+    for iu in ("asinh", "nJy"):
+        mod = S.AsinhEmpiricalUncertaintyModel(error_type="empirical", return_noise=True, interpolation_flux_unit=iu)
+        b = 5.0
+        mod.b = Quantity(b * 1e-9, "Jy")
+        if iu == "asinh":
+            cm = np.linspace(22.0, 32.0, 20)
+            mod.bin_centers, mod.median_error_in_bin, mod.std_error_in_bin = cm, 0.02 + 0.3 * np.exp((cm - 29) / 1.2), np.full(20, 0.01)
+        else:
+            mod.bin_centers, mod.median_error_in_bin, mod.std_error_in_bin = centers, med, sd
+        mod._create_interpolators()
+        n = flux.shape[1]
+        draws = np.stack([rng.uniform(0, 1, (1, n)), rng.standard_normal((1, n)), rng.uniform(0, 1, (1, n)), np.full((1, n), 0.5)])
+        want_f, want_s = S.apply_empirical_noise_models(flux, ["F"], {"F": mod}, N_scatters=1, flux_units="nJy", return_errors=True, draws=draws)
+        got_f, got_s = S.apply_empirical_noise_models(flux, ["F"], {"F": mod}, N_scatters=1, flux_units="nJy", return_errors=True, seed=4)
+        for k in range(len(levels)):
+            sl = slice(k * m_per, (k + 1) * m_per)
+            _same_law(want_f[0, sl], got_f[0, sl], (iu, k, "mag"))
+            _same_law(want_s[0, sl], got_s[0, sl], (iu, k, "err"))
+    # an odd row count takes the scalar tail path and every element is still written
+    f_odd = S.apply_empirical_noise_models(flux[:, :10001], ["F"], {"F": mod}, N_scatters=1, flux_units="nJy", seed=4)
+    assert f_odd.shape == (1, 10001) and np.isfinite(f_odd).all()

@@ -146,6 +146,18 @@ def test_create_mock_library_end_to_end(tmp_path):
     want = O.scale_to_mass(want, np.asarray(d["masses"], dtype=float))
     assert_flux_close(lib["photometry"].T, want)
     np.testing.assert_allclose(lib["parameters"][0], np.asarray(d["redshift"], dtype=float))
+    # the single-base build takes the library matrix straight from the kernels (library_out): it must equal the reference's
+    # host arithmetic on the pipeline files' base-mass columns, float32(base) * 10**log_mass / base_mass (library.py:4588-4609)
+    assert "scaled_matrix" in basis._pipeline_cache
+    from synference_b200.utils import read_container
+    cols = []
+    for i in (1, 2):
+        data, attrs = read_container(os.path.join(out_dir, f"test_lhc_basis_{i}.hdf5"))
+        assert data["Galaxies/mass"][0] == 1e9 and attrs["n_batches"] == 2
+        cols.append(np.stack([data[f"Galaxies/Stars/Photometry/Fluxes/emergent/JWST/{c}"] for c in inst.filters.filter_codes], 0))
+    base = np.concatenate(cols, 1)
+    assert base.dtype == np.float64 and np.array_equal(base, base.astype(np.float32))
+    np.testing.assert_allclose(lib["photometry"], base * (10.0 ** np.asarray(d["masses"], dtype=float) / 1e9)[None, :], rtol=1e-15)
     # resume semantics: without overwrite existing batch files and library are kept (library.py:2546-2553)
     t0 = os.path.getmtime(lib_file)
     basis.create_mock_library(log_stellar_masses=list(np.asarray(d["masses"], dtype=float)), emission_model_key="emergent",

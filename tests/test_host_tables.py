@@ -190,7 +190,10 @@ def test_dust_emission_tables():
     flat = np.ones(nl)
     nu = 2.99792458e18 / lam
     assert float(t["dust_wnu"][:nl].astype(np.float64) @ flat) * DUST_W0 == pytest.approx(nu[0] - nu[-1], rel=1e-6)
-    assert np.all(t["dust_wnu"][nl:] == 0) and np.all(t["dust_g"][:t["igm"]["n_blue"]] == 0)
+    x0, xn = t["x_bin0"], t["x_bins"]
+    assert xn == 192 and x0 % 192 == 0 and x0 >= nl and t["n_chunk"] * (256 // t["n_comp"]) >= x0 + xn
+    assert np.all(t["dust_wnu"][nl:x0] == 0) and np.all(t["dust_wnu"][x0:x0 + xn] == 1) and np.all(t["dust_wnu"][x0 + xn:] == 0)
+    assert np.all(t["dust_g"][:t["igm"]["n_blue"]] == 0)
     duv = t["dust_duv"].reshape(t["dust_m_len"], t["n_filt"], 2).astype(np.float64)
     uv = t["filt_uv"].astype(np.float64)
     for f in (0, 7, t["n_filt"] - 1):
@@ -206,6 +209,50 @@ def test_dust_emission_tables():
     assert build_tables(w.grid, em, "emergent", w.filters)["dust_wnu"] is None
     with pytest.raises(NotImplementedError):
         PacmanEmission(grid=w.grid, dust_curve=Calzetti2000(), dust_emission=object())
+
+
+@pytest.mark.parametrize("model", ["one_component", "two_components", "two_screens"])
+def test_absorbed_energy_pseudo_bins_reproduce_the_sum_over_the_axis(model):
+    """The pseudo-bin rows appended to the grid (engine._energy_pseudo_bins): for random (age, Z) weights and optical depths up
+    to the stated range, sum_j [W . rows_j] (1 - exp(-tau node_j)) equals the absorbed energy summed over the whole axis,
+    sum_i wnu_i [W . grid_i] (1 - exp(-tau kappa_i)), to < 1e-6 -- evaluated from the very tables the kernel reads (float32
+    kappa / nodes, TF32 hi + lo grid rows)."""
+    from synference_b200.parametric import BimodalPacmanEmission, Calzetti2000, Greybody, PacmanEmission
+    w = make_workload("cfg2", 4)
+    if model == "two_screens":
+        em = BimodalPacmanEmission(grid=w.grid, dust_curve_ism=Calzetti2000(), dust_curve_birth=Calzetti2000(), age_pivot=7.0,
+                                   dust_emission_ism=Greybody(40.0, 1.5), dust_emission_birth=Greybody(40.0, 1.5))
+    else:
+        em = PacmanEmission(grid=w.grid, fesc=0.1 if model == "two_components" else 0.0, dust_curve=Calzetti2000(),
+                            dust_emission=Greybody(40.0, 1.5))
+    t = build_tables(w.grid, em, "total", w.filters)
+    nl, nc, x0, xn = t["n_lam"], t["n_comp"], t["x_bin0"], t["x_bins"]
+    assert xn == 192 and t["x_tau_max"] > 9.0
+    lch = 256 // nc
+    g = (t["gt_hi"].astype(np.float64) + t["gt_lo"].astype(np.float64)).reshape(t["n_chunk"], nc, lch, t["k_pad"])
+    kap, wnu = t["kappa"].astype(np.float64), t["dust_wnu"].astype(np.float64)
+    rng = np.random.default_rng(2)
+    absorbing = [0, 1] if model == "two_screens" else [0]
+    for ci in range(nc):
+        rows = g[:, ci].reshape(t["n_chunk"] * lch, t["k_pad"])
+        if ci not in absorbing:
+            assert np.all(rows[x0:x0 + xn] == 0)
+            continue
+        for trial in range(6):
+            wgt = np.zeros(t["k_pad"])
+            pick = rng.choice(t["n_age_pad"] * t["n_z"], 5 if trial else 1, replace=False)     # a few bins, as a real SFH gives
+            wgt[pick] = rng.uniform(0.1, 1.0, pick.size)
+            light = rows @ wgt
+            for tau in (0.003, 0.3, 1.0, 3.0, 9.0):
+                exact = np.sum(wnu[:nl] * light[:nl] * -np.expm1(-tau * kap[:nl]))
+                pseudo = np.sum(light[x0:x0 + xn] * -np.expm1(-tau * kap[x0:x0 + xn]))
+                scale = np.sum(np.abs(wnu[:nl] * light[:nl] * np.expm1(-tau * kap[:nl])))
+                assert abs(pseudo - exact) <= 1e-6 * scale, (model, ci, trial, tau, pseudo, exact)
+    if model == "two_screens":
+        np.testing.assert_allclose(t["kappa_birth"][x0:x0 + xn], t["x_birth_ratio"] * t["kappa"][x0:x0 + xn], rtol=1e-6)
+    # a per-galaxy dust curve has no single kappa axis: no pseudo-bins
+    em_pg = PacmanEmission(grid=w.grid, dust_curve=Calzetti2000(slope="slope", ampl="ampl"), dust_emission=Greybody(40.0, 1.5))
+    assert build_tables(w.grid, em_pg, "total", w.filters)["x_bins"] == 0
 
 
 def test_non_geometric_axis_is_rejected():
