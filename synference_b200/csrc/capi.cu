@@ -100,7 +100,11 @@ int make_tmap(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, 
 // bracket (so a DeltaConstant batch multiplies only the 2*n_age grid columns it can touch) in redshift
 // order (so the filter windows of a warp's galaxies coincide).  Dense batches use bracket 0 for everyone.
 constexpr int kMaxGroups = 64;
-constexpr int kKeyShift = 26;  // key = bracket << 26 | float_bits(z) >> 6
+// Sort key = bracket << 12 | ln(1 + z) in 4096 steps up to z = 100 (three steps per wavelength bin of an R = 300 axis: what a
+// tile needs is neighbours in the integer redshift SHIFT, not in z to 17 mantissa bits).  With <= 16 brackets the key has 16
+// bits and the radix sort takes two 8-bit passes instead of four.
+constexpr int kKeyShift = 12;
+constexpr float kKeyScale = 4095.f / 4.7f;
 
 __global__ void group_keys_kernel(const double* __restrict__ z, const double* __restrict__ zv,
                                   const double* __restrict__ zx, int n_z, int delta, unsigned* keys, int* idx,
@@ -116,7 +120,7 @@ __global__ void group_keys_kernel(const double* __restrict__ z, const double* __
       j = sb2::delta_bracket(zx, n_z, zv[i], &f);
     }
     const float zf = (z[i] >= 0.0 && z[i] <= 1.0e6) ? (float)z[i] : 0.f;   // unusable redshifts sort first (scalars_kernel flags them)
-    keys[i] = ((unsigned)j << kKeyShift) | (__float_as_uint(zf) >> (32 - kKeyShift));
+    keys[i] = ((unsigned)j << kKeyShift) | min(4095u, (unsigned)(log1pf(zf) * kKeyScale));
     idx[i] = (int)i;
     atomicAdd(&h[j], 1);
   }
@@ -170,12 +174,14 @@ __global__ void group_scatter_kernel(const unsigned* __restrict__ keys_sorted, c
 // Experiment / fallback switches (environment), read ONCE when a model is created -- never on the per-call path.
 struct Switches {
   bool n256 = false, cta_pair = false, libm = false, weights_v1 = false, one_pass = false, trace = false, no_synth3 = false, no_split = false;
+  bool no_fuse = false;
   int dbg = 0;
   long long host_slices = 0;   // 0: automatic
   static bool on(const char* k) { const char* e = std::getenv(k); return e && e[0] && e[0] != '0'; }
   void read() {
     n256 = on("SB2_N256"); cta_pair = on("SB2_CTA_PAIR"); libm = on("SB2_LIBM"); weights_v1 = on("SB2_WEIGHTS_V1");
     one_pass = on("SB2_ONE_PASS"); trace = on("SB2_TRACE"); no_synth3 = on("SB2_NO_SYNTH3"); no_split = on("SB2_NO_SPLIT");
+    no_fuse = on("SB2_NO_FUSE");
     if (const char* e = std::getenv("SB2_DBG")) dbg = std::atoi(e);
     if (const char* e = std::getenv("SB2_HOST_SLICES")) host_slices = std::atoll(e);
   }
@@ -191,6 +197,7 @@ struct sb2_model {
   double *sf = nullptr, *s0 = nullptr, *s1 = nullptr;
   CUtensorMap tm_g96_hi, tm_g96_lo;
   bool s3_ok = false;
+  bool last_fused = false;   // the last synth3 launch wrote the fluxes itself (no finalize_kernel needed)
   sb2_model_desc d{};  // dims and scalars (pointers inside are NOT valid after create)
   long long cap = 0, cap_pad = 0;
   // model tables
@@ -647,10 +654,14 @@ int launch_synth3_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_
   bool spec = false;
   const int kap_len = m->d.n_chunk * (sb2::kBN / C);
   const int feat_tab = a.x_count > 0 ? (FEAT & ~sb2::kFeatAbsorbed) : FEAT;    // pseudo-bins: the energy weights are 1, no table
-  if (SPEC && sb2::synth3_smem_bytes(N, 3, x.n_age, m->uv_len, kap_len, true, feat_tab) <= m->smem_optin) { spec = true; a2.spec_smem = 1; }
+  // fused output (SynthArgs.fuse_out): n_filt KB for the groups' exchange, if three ring stages still fit beside it
+  int n_x = a.fuse_out ? m->d.n_filt : 0;
+  if (n_x && sb2::synth3_smem_bytes(N, 3, x.n_age, m->uv_len, kap_len, false, feat_tab, n_x) > m->smem_optin) { n_x = 0; a2.fuse_out = 0; }
+  m->last_fused = a2.fuse_out != 0;
+  if (SPEC && sb2::synth3_smem_bytes(N, 3, x.n_age, m->uv_len, kap_len, true, feat_tab, n_x) <= m->smem_optin) { spec = true; a2.spec_smem = 1; }
   int ns = sb2::kS3MaxStages;
-  while (ns > 1 && sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec, feat_tab) > m->smem_optin) --ns;
-  const size_t bytes = sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec, feat_tab);
+  while (ns > 1 && sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec, feat_tab, n_x) > m->smem_optin) --ns;
+  const size_t bytes = sb2::synth3_smem_bytes(N, ns, x.n_age, m->uv_len, kap_len, spec, feat_tab, n_x);
   if (ns < 2 || bytes > m->smem_optin) return fail(SB2_ERR_INVALID, "synth3_kernel: filter tables leave no room for the operand ring");
   x.n_stages = ns;
   CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -807,7 +818,9 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
                                                                    m->d.n_z, delta ? 1 : 0, m->keys, m->idx, m->grp, n);
     STAGE_CHECK("group_keys_kernel", st);
     size_t bytes = m->cub_bytes;
-    CU_TRY(cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)n, 0, 32, st));
+    int key_bits = kKeyShift + 1;
+    while ((1 << (key_bits - kKeyShift)) < n_groups) ++key_bits;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->keys, m->keys_sorted, m->idx, m->perm, (int)n, 0, key_bits, st));
     STAGE_CHECK("radix sort", st);
     group_layout_kernel<<<1, 256, 0, st>>>(m->grp, n_groups, m->d.n_age_pad, rpu, m->grp + kMaxGroups, m->grp + 2 * kMaxGroups,
                                            m->tile_k0, m->grp + 3 * kMaxGroups, (int)(n_pad / rpu));
@@ -943,6 +956,10 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   }
   a.part = m->part;
   a.n_rows = (long long)a.n_tiles * rpu;
+  // fused output: synth3_kernel's epilogue writes the fluxes (the dust emission's share is finalize_kernel's business)
+  m->last_fused = false;
+  a.fuse_out = (rpu != 256 && use_s3(m, p) && !m->dust_wnu && !m->sw.no_fuse) ? 1 : 0;
+  a.scaled_ld = flux_scaled ? p->scaled_ld : 0;
   if (rpu == 256) {
     const int grid = 2 * std::min(a.n_tiles, m->n_sm / 2);
     rc = launch_synth2(m, a, grid, st);
@@ -965,7 +982,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
       sb2::dust_spec_kernel<<<(unsigned)((a.n_rows + 7) / 8), 256, 0, st>>>(fa, a.n_tiles_dev, rpu);
       STAGE_CHECK("dust_spec_kernel", st);
     }
-    if (flux_base || flux_scaled) {
+    if ((flux_base || flux_scaled) && !m->last_fused) {
       sb2::finalize_kernel<<<(unsigned)((a.n_rows + 255) / 256), 256, 0, st>>>(fa, a.n_tiles_dev, rpu);
       STAGE_CHECK("finalize_kernel", st);
     }
@@ -1494,6 +1511,10 @@ int sb2_empirical_noise(const double* flux, int64_t n, int32_t n_filt, const sb2
   sb2::EmpiricalArgs a{};
   a.flux = flux; a.n = n; a.n_filt = n_filt; a.models = dm; a.draws = draws; a.seed = seed; a.epoch = epoch;
   a.out_flux = out_flux; a.out_sigma = out_sigma;
+  for (int r = 0; r < 10; ++r) {   // key (seed_lo, seed_hi ^ epoch_hi), bumped per round by Philox's Weyl constants
+    a.rk0[r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+    a.rk1[r] = ((uint32_t)(seed >> 32) ^ (uint32_t)(epoch >> 32)) + (uint32_t)r * 0xBB67AE85u;
+  }
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);

@@ -49,7 +49,22 @@ struct EmpiricalArgs {
   unsigned long long seed, epoch;
   double* out_flux;        // [n_filt][n]
   double* out_sigma;       // [n_filt][n]
+  // Philox round keys of (seed, epoch), filled by the host: as kernel parameters they are constant-bank operands of the
+  // rounds' XORs (bumping the key in registers cost 20 integer adds per Philox block)
+  uint32_t rk0[10], rk1[10];
 };
+
+// Philox4x32-10 with the round keys given (same function of (counter, key) as philox4x32_10)
+__device__ __forceinline__ void philox4x32_10_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk0)[10],
+                                                    const uint32_t (&rk1)[10], uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ rk0[r]; c1 = lo1; c2 = hi0 ^ c3 ^ rk1[r]; c3 = lo0;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
 
 __device__ __forceinline__ double ab_to_jy(double m) { return pow(10.0, -0.4 * (m - 8.90)); }
 __device__ __forceinline__ double jy_to_ab(double f) { return -2.5 * log10(f) + 8.90; }
@@ -204,11 +219,16 @@ __global__ void __launch_bounds__(256) empirical_noise_kernel(EmpiricalArgs A) {
 // float32 helpers.  Accuracy is set against the quantities' own spread (errors are a few per cent of a flux, drawn at random):
 // the normal quantile is good to 1e-6 absolute, the CDF to 3e-7 absolute, magnitudes to a float32 ulp (2e-6 mag).
 struct EmpFastTab {
-  float x[kEmpMaxBins], med[kEmpMaxBins], dmed[kEmpMaxBins], sd[kEmpMaxBins], dsd[kEmpMaxBins];   // x padded with +inf
+  float x[kEmpMaxBins];        // centres, padded with +inf (the search reads x alone)
+  float4 seg[kEmpMaxBins];     // per segment: x, median, its slope, stdev -- one 16-byte read
+  float dsd[kEmpMaxBins];      // slope of the stdev
   float x0, xlast;
+  float lo_clamp, hi_clamp;    // x0, xlast when values beyond the table take the end values; -inf, +inf when it extrapolates
   float clip_p0, clip_dp;      // Phi(-clip), Phi(clip) - Phi(-clip): the sigma-clipped scatter by inversion
   float lim_p0, lim_dp;        // the same for the +-3 sigma scatter about an upper limit
   float log_b;                 // asinh modes: log(b / 3631 Jy)
+  float inv_dx;                // > 0: the centres are equally spaced, 1 / spacing
+  float c_out_f;
   float min_err, max_err;
   double c_in, c_out;          // linear unit changes: input -> interpolation unit, interpolation unit -> output (1 for AB)
   int n_bins, extrapolate, simple;
@@ -248,15 +268,20 @@ __device__ __forceinline__ float jy_to_ab_f(float f) { return fmaf(-0.7525749891
 
 // mu_sigma(v), sigma_sigma(v) from the slope tables, then sigma ~ TruncNorm(mu, ss; >= 0) at probability u
 __device__ __forceinline__ float emp_sigma_fast(const EmpFastTab& T, int n_bins, int extrapolate, float v, float u) {
-  const float vc = extrapolate ? v : fminf(fmaxf(v, T.x0), T.xlast);
+  const float vc = fminf(fmaxf(v, T.lo_clamp), T.hi_clamp);
   int lo = 0;
+  if (T.inv_dx > 0.f) {   // equally spaced centres (linear bins, none dropped): the segment by arithmetic.  A value within
+                          // rounding of a centre may land in the neighbouring segment, where the interpolant is the same.
+    lo = (int)((vc - T.x0) * T.inv_dx);       // (NaN and out-of-range values convert to a clamped integer)
+  } else {
 #pragma unroll
-  for (int s = kEmpMaxBins / 2; s; s >>= 1) lo = (T.x[lo + s] <= vc) ? lo + s : lo;
-  lo = min(lo, n_bins - 2);
-  const float d = vc - T.x[lo];
-  const float mu = fmaf(T.dmed[lo], d, T.med[lo]);
-  const float ss = fmaxf(0.f, fmaf(T.dsd[lo], d, T.sd[lo]));
-  if (!(v == v)) return v;
+    for (int s = kEmpMaxBins / 2; s; s >>= 1) lo = (T.x[lo + s] <= vc) ? lo + s : lo;
+  }
+  lo = max(min(lo, n_bins - 2), 0);
+  const float4 sg = T.seg[lo];
+  const float d = vc - sg.x;
+  const float mu = fmaf(sg.z, d, sg.y);
+  const float ss = fmaxf(0.f, fmaf(T.dsd[lo], d, sg.w));
   const float a = __fdividef(-mu, ss > 1e-9f ? ss : 1.f);
   float x;
   if (a > 0.f) {   // negative mean error (an extrapolated table): the mirrored tail, library functions (rare)
@@ -265,7 +290,7 @@ __device__ __forceinline__ float emp_sigma_fast(const EmpFastTab& T, int n_bins,
     const float pa = ncdf_neg_fast(a);
     x = ndtri_fast(fminf(fmaf(u, 1.f - pa, pa), 0.99999994f));
   }
-  return fmaf(ss, x, mu);
+  return (v == v) ? fmaf(ss, x, mu) : v;      // NaN in, NaN out
 }
 __device__ __forceinline__ bool emp_below_snr_fast(const EmpiricalModelDev& M, float f, float e) {
   // AB: flux / (flux e ln10 / 2.5) does not depend on the flux; linear units: the unit cancels
@@ -279,7 +304,7 @@ __device__ __forceinline__ void emp_element_simple(const EmpFastTab& T, double f
   const double fi_d = fin * T.c_in;
   const float sig0 = emp_sigma_fast(T, T.n_bins, T.extrapolate, (float)fi_d, u_sig);
   of = (fi_d + (double)(sig0 * zz)) * T.c_out;
-  os = (double)fminf(fmaxf(sig0 * (float)T.c_out, T.min_err), T.max_err);
+  os = (double)fminf(fmaxf(sig0 * T.c_out_f, T.min_err), T.max_err);
 }
 
 // one element: uniforms u_sig, u_obs, u_lim in (0, 1); zz the scatter's standard normal, or a uniform when the model clips
@@ -361,13 +386,13 @@ __global__ void __launch_bounds__(256, 4) empirical_noise_fast_kernel(EmpiricalA
     const bool in = i < n, seg = i < n - 1;
     const double w = seg ? M.centers[i + 1] - M.centers[i] : 1.0;
     T.x[i] = in ? (float)M.centers[i] : INFINITY;
-    T.med[i] = in ? (float)M.median[i] : 0.f;
-    T.sd[i] = in ? (float)M.stdev[i] : 0.f;
-    T.dmed[i] = seg ? (float)((M.median[i + 1] - M.median[i]) / w) : 0.f;
+    T.seg[i] = make_float4(in ? (float)M.centers[i] : 0.f, in ? (float)M.median[i] : 0.f,
+                           seg ? (float)((M.median[i + 1] - M.median[i]) / w) : 0.f, in ? (float)M.stdev[i] : 0.f);
     T.dsd[i] = seg ? (float)((M.stdev[i + 1] - M.stdev[i]) / w) : 0.f;
   }
   if (threadIdx.x == 0) {
     T.x0 = (float)M.centers[0]; T.xlast = (float)M.centers[M.n_bins - 1];
+    T.lo_clamp = M.extrapolate ? -INFINITY : T.x0; T.hi_clamp = M.extrapolate ? INFINITY : T.xlast;
     const double c = M.sigma_clip >= 0.0 ? M.sigma_clip : 0.0;
     T.clip_p0 = (float)normcdf(-c); T.clip_dp = (float)(normcdf(c) - normcdf(-c));
     T.lim_p0 = (float)normcdf(-3.0); T.lim_dp = (float)(normcdf(3.0) - normcdf(-3.0));
@@ -378,6 +403,11 @@ __global__ void __launch_bounds__(256, 4) empirical_noise_fast_kernel(EmpiricalA
     T.c_in = (same && !M.internal_is_ab) ? M.in_to_jy / M.internal_to_jy : 1.0;
     T.c_out = (same && !M.internal_is_ab) ? M.internal_to_jy / M.out_to_jy : 1.0;
     T.simple = same && !M.asinh_mode && !M.upper_limits && !M.observed_error && M.sigma_clip < 0.0;
+    T.c_out_f = (float)T.c_out;
+    const double dx = (M.centers[M.n_bins - 1] - M.centers[0]) / (M.n_bins - 1);
+    bool even = dx > 0.0;
+    for (int i = 1; i < M.n_bins && even; ++i) even = fabs(M.centers[i] - (M.centers[0] + i * dx)) <= 1e-6 * dx;
+    T.inv_dx = even ? (float)(1.0 / dx) : 0.f;
   }
   __syncthreads();
   // the second Philox block (re-draw and upper-limit uniforms) only for the models that consume it
@@ -386,12 +416,12 @@ __global__ void __launch_bounds__(256, 4) empirical_noise_fast_kernel(EmpiricalA
   const bool simple = T.simple != 0;
   const bool vec = (A.n & 1) == 0 && ((reinterpret_cast<uintptr_t>(A.flux) | reinterpret_cast<uintptr_t>(A.out_flux) |
                                        reinterpret_cast<uintptr_t>(A.out_sigma)) & 15) == 0;
-  const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32) ^ (uint32_t)(A.epoch >> 32);
   const long long n_pairs = (A.n + 1) >> 1;
   const double* in = A.flux + (long long)f * A.n;
   double* o_f = A.out_flux + (long long)f * A.n;
   double* o_s = A.out_sigma ? A.out_sigma + (long long)f * A.n : nullptr;
-  auto uni = [](uint32_t w) { return fminf(((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f), 0.99999994f); };
+  // 23-bit uniforms (k + 1/2) / 2^23: exact in float32, inside (0, 1), so no clamp
+  auto uni = [](uint32_t w) { return fmaf((float)(w >> 9), 1.0f / 8388608.0f, 0.5f / 8388608.0f); };
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n_pairs; q += (long long)gridDim.x * blockDim.x) {
     const long long r = 2 * q;
     const bool two = r + 1 < A.n;
@@ -399,13 +429,14 @@ __global__ void __launch_bounds__(256, 4) empirical_noise_fast_kernel(EmpiricalA
     if (vec) { const double2 v = *reinterpret_cast<const double2*>(in + r); fin[0] = v.x; fin[1] = v.y; }
     else { fin[0] = in[r]; fin[1] = two ? in[r + 1] : in[r]; }
     uint32_t a4[4];
-    philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)f | 0x40000000u, (uint32_t)A.epoch, k0, k1, a4);
+    philox4x32_10_keyed((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)f | 0x40000000u, (uint32_t)A.epoch, A.rk0, A.rk1, a4);
     float zz[2];
     if (clipped) { zz[0] = uni(a4[2]); zz[1] = uni(a4[3]); }
     else {   // one Box-Muller pair: both normals are used
       float sn, cs;
       __sincosf(6.2831853f * (uni(a4[3]) - 0.5f), &sn, &cs);
-      const float rad = sqrtf(fmaxf(-2.f * __logf(uni(a4[2])), 0.f));
+      float rad;
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(fmaxf(-2.f * __logf(uni(a4[2])), 0.f)));
       zz[0] = rad * cs; zz[1] = rad * sn;
     }
     double of[2], os[2];
@@ -414,7 +445,7 @@ __global__ void __launch_bounds__(256, 4) empirical_noise_fast_kernel(EmpiricalA
       emp_element_simple(T, fin[1], uni(a4[1]), zz[1], of[1], os[1]);
     } else {
       uint32_t b4[4] = {0x80000000u, 0x80000000u, 0x80000000u, 0x80000000u};
-      if (need2) philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)f | 0xC0000000u, (uint32_t)A.epoch, k0, k1, b4);
+      if (need2) philox4x32_10_keyed((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)f | 0xC0000000u, (uint32_t)A.epoch, A.rk0, A.rk1, b4);
       emp_element_fast(M, T, fin[0], uni(a4[0]), zz[0], uni(b4[0]), uni(b4[2]), of[0], os[0]);
       emp_element_fast(M, T, fin[1], uni(a4[1]), zz[1], uni(b4[1]), uni(b4[3]), of[1], os[1]);
     }

@@ -403,4 +403,8 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+// named barriers (ids 1..15; 0 is __syncthreads): `count` threads take part, arriving or waiting
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 }  // namespace sb2

@@ -46,9 +46,11 @@ struct Synth3Cfg {
 __host__ __device__ inline int synth3_n_tables(int feat) {
   return 1 + ((feat & kFeatDustShape) ? 2 : 0) + ((feat & kFeatTwoScreens) ? 1 : 0) + ((feat & kFeatAbsorbed) ? 1 : 0);
 }
-__host__ __device__ inline size_t synth3_smem_bytes(int kn, int n_stages, int n_age, int uv_len, int kap_len, bool spec, int feat = 0) {
+// n_x: filters whose numerators the epilogue groups exchange for the fused output (0: finalize_kernel does it), 1 KB each
+__host__ __device__ inline size_t synth3_smem_bytes(int kn, int n_stages, int n_age, int uv_len, int kap_len, bool spec, int feat = 0,
+                                                    int n_x = 0) {
   return 1024 + (size_t)n_stages * (2 * kn * kBK * 4) + (size_t)n_age * 1024 + (((size_t)uv_len * 8 + 15) & ~size_t(15)) +
-         (size_t)kap_len * 4 * synth3_n_tables(feat) + kS3BarBytes + (spec ? kSpecSmemBytes : 0);
+         (size_t)kap_len * 4 * synth3_n_tables(feat) + kS3BarBytes + (spec ? kSpecSmemBytes : 0) + (size_t)n_x * kBM * 8;
 }
 
 template <int kComp, int kNF, bool kSpec, int kN, int kFeat = 0>
@@ -290,9 +292,11 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
     float* s_spec = (kSpec && A.spec_smem) ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kS3BarBytes) : nullptr;
     const EpiTables tabs{smem_u32(s_kap), s_d0 ? smem_u32(s_d0) : 0u, s_l2 ? smem_u32(s_l2) : 0u, s_kapb ? smem_u32(s_kapb) : 0u,
                          s_wnu ? smem_u32(s_wnu) : 0u};
+    float2* s_x = A.fuse_out ? reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + kS3BarBytes + (A.spec_smem ? kSpecSmemBytes : 0))
+                             : nullptr;
     epilogue_loop<kComp, kNF, kSpec, 1, kN, 2, false, kS3EpiWarp0, (int)kBuf, kFeat, true>(A, s_uv, s_spec, tfull_bar, tempty_bar, 0u,
                                                                                           tmem_base, (int)blockIdx.x, (int)gridDim.x,
-                                                                                          n_tiles, 0u, tabs);
+                                                                                          n_tiles, 0u, tabs, s_x);
   }
 
   tc_fence_before();

@@ -91,6 +91,10 @@ struct SynthArgs {
   // and the real chunks keep their skipping and the plain epilogue.
   int x_first, x_count;
   int kap_len;               // length of the kappa / wnu / ... tables (real axis padded + pseudo-bins)
+  // synth3_kernel, fused output: the two epilogue groups exchange their filter numerators through shared memory at the end
+  // of a tile and group 0 writes the fluxes itself (what finalize_kernel does from the `part` planes in HBM otherwise)
+  int fuse_out;
+  long long scaled_ld;       // layout of out_scaled for the fused output (FinalizeArgs.scaled_ld)
   const float2* filt_uv;     // padded tables, uv_len entries
   const float* igm;          // [n_tiles][n_blue_pad][128]
   const int* g_m;
@@ -194,7 +198,8 @@ template <int kComp, int kNF, bool kSpec, int kCta, int kN, int kGroups, bool kP
           int kFeat = kFeatRuntime, bool kTabS = false, int kSplit = 1>
 __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* s_uv, float* s_spec, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tempty_addr, uint32_t tmem_base, int unit0, int unit_stride,
-                                              int n_units, uint32_t cta_rank, EpiTables T = EpiTables{0u, 0u, 0u, 0u, 0u}) {
+                                              int n_units, uint32_t cta_rank, EpiTables T = EpiTables{0u, 0u, 0u, 0u, 0u},
+                                              float2* s_x = nullptr) {
   constexpr int kLch = kN / kComp;      // wavelengths per chunk
   constexpr int kSub = kLch / 32;       // 32-wavelength sub-chunks per chunk
   constexpr uint32_t kBuf = kBufT;      // TMEM accumulators (2 x 256, 3 x 160 or 4 x 128 columns; synth3: what W leaves free)
@@ -216,6 +221,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
     const uint32_t uv_base = smem_u32(s_uv);
     const unsigned FULL = 0xffffffffu;
     uint32_t it = 0, gk = 0;   // chunks seen by the CTA / chunks taken by this group
+    bool x_seen = false;       // fused output: group 1 has handed a tile's numerators over before
     for (int unit = unit0; unit < n_units; unit += unit_stride) {
       const int tile = unit * kCta + (int)cta_rank;
       const int4 cr = A.tile_range ? __ldg(A.tile_range + unit) : make_int4(0, c_all_last, 0, 0);
@@ -469,6 +475,72 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
             }
           }
           if (last_sub) break;
+        }
+      }
+      if constexpr (kTabS && kGroups == 2 && !kShare && kCta == 1) {
+        if (s_x != nullptr) {
+          // ---- fused output: group 1 parks its numerators in shared memory (named barrier 1: "full", 2: "read"), group 0
+          //      adds its own in the order finalize_kernel uses (group 0 + group 1) and writes the fluxes
+          if (grp == 1) {
+            if (x_seen) named_bar_sync(2, 256);
+            x_seen = true;
+#pragma unroll
+            for (int f = 0; f < kNF; ++f)
+              if (f < A.n_filt) s_x[f * kBM + et] = acc[f];
+            __threadfence_block();
+            named_bar_arrive(1, 256);
+          } else {
+            named_bar_sync(1, 256);
+            if (orig >= 0) {
+              const float beta = A.g_beta[row], gamma = A.g_gamma[row];
+              const float scf = (kComp == 1) ? A.g_scale[row] * A.g_ca[row] : A.g_scale[row];
+              const unsigned trunc = A.g_trunc[row];
+              const double mscale = A.out_scaled ? A.g_mscale[row] : 0.0;
+              const bool tr = A.scaled_ld > 0;
+              const bool vec = (A.n_filt % 4) == 0 &&
+                               ((reinterpret_cast<uintptr_t>(A.out_base) | (tr ? 0 : reinterpret_cast<uintptr_t>(A.out_scaled))) & 15) == 0;
+#pragma unroll
+              for (int f0 = 0; f0 < kNF; f0 += 4) {
+                if (f0 < A.n_filt) {
+                  float fl[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    constexpr int kLast = kNF - 1;
+                    const int f = f0 + q;
+                    fl[q] = 0.f;
+                    if (f < A.n_filt) {
+                      const float2 o = s_x[f * kBM + et];
+                      const float nu = acc[f <= kLast ? f : kLast].x + o.x, nv = acc[f <= kLast ? f : kLast].y + o.y;
+                      float flux = fmaf(beta, nv, gamma * nu) / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * scf;
+                      if ((trunc >> f) & 1u) flux = __int_as_float(0x7fc00000);
+                      fl[q] = flux;
+                    }
+                  }
+                  if (vec) {
+                    if (A.out_base) *reinterpret_cast<float4*>(A.out_base + (size_t)orig * A.n_filt + f0) = make_float4(fl[0], fl[1], fl[2], fl[3]);
+                    if (A.out_scaled && tr) {
+#pragma unroll
+                      for (int q = 0; q < 4; ++q) A.out_scaled[(size_t)(f0 + q) * A.scaled_ld + orig] = (double)fl[q] * mscale;
+                    } else if (A.out_scaled) {
+                      double2* o2 = reinterpret_cast<double2*>(A.out_scaled + (size_t)orig * A.n_filt + f0);
+                      o2[0] = make_double2((double)fl[0] * mscale, (double)fl[1] * mscale);
+                      o2[1] = make_double2((double)fl[2] * mscale, (double)fl[3] * mscale);
+                    }
+                  } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                      if (f0 + q < A.n_filt) {
+                        if (A.out_base) A.out_base[(size_t)orig * A.n_filt + f0 + q] = fl[q];
+                        if (A.out_scaled)
+                          A.out_scaled[tr ? (size_t)(f0 + q) * A.scaled_ld + orig : (size_t)orig * A.n_filt + f0 + q] = (double)fl[q] * mscale;
+                      }
+                  }
+                }
+              }
+            }
+            if (unit + unit_stride < n_units) named_bar_arrive(2, 256);
+          }
+          continue;
         }
       }
       // ---- this group's partial numerators (finalize_kernel adds the two groups and scales)

@@ -138,3 +138,29 @@ def test_combine_rank_files_slices_galaxies_along_the_first_axis(tmp_path):
     d, a = U.read_container(path)
     np.testing.assert_array_equal(d["Galaxies/Stars/Photometry/Fluxes/total/JWST/b"], np.arange(7.0) + 100.0)
     assert d["Wavelengths"].shape == (5,) and a["world_size"] == 1 and a["galaxy_stop"] == 7
+
+
+def test_containers_without_h5py_round_trip(tmp_path, monkeypatch):
+    """write_container / read_container when h5py is absent: uncompressed files are the raw container (JSON header + arrays at
+    aligned offsets, one write per array), compressed ones a deflated .npz; both give back dtypes, shapes, order-independent
+    contents and the attribute block (None, dicts and group attributes included)."""
+    monkeypatch.setenv("SYNFERENCE_B200_FORCE_NPZ", "1")
+    rng = np.random.default_rng(0)
+    data = {"Grid/Photometry": rng.random((3, 1001)), "Grid/Parameters": np.asfortranarray(rng.random((4, 7))),
+            "Model/names": np.array(["ab", "cde"]), "empty": np.zeros((0, 5)), "scalar": np.float64(3.0),
+            "f32": rng.random((5, 2)).astype(np.float32), "i32": np.arange(7, dtype=np.int32), "flags": np.array([True, False])}
+    attrs = {"ParameterNames": ["a", "b"], "Model@key": "total", "none": None, "nested": {"q": 1.5, "l": [1, 2]}, "n": 3}
+    for compress in (False, True, 3):
+        path = str(tmp_path / f"c_{compress}.hdf5")
+        assert U.write_container(path, data, attrs, compress=compress) == path
+        with open(path, "rb") as fh:
+            magic = fh.read(8)
+        assert (magic == b"SB2CONT1") == (compress is False)
+        got, a = U.read_container(path)
+        assert set(got) == set(data) and a == attrs
+        for k, v in data.items():
+            v = np.asarray(v)
+            assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v), k
+        assert got["Grid/Photometry"].flags.writeable
+    with pytest.raises(TypeError):
+        U.write_container(str(tmp_path / "bad.hdf5"), {"o": np.array([{"a": 1}], dtype=object)}, {}, compress=False)

@@ -24,8 +24,11 @@ cases = {
                                                                   dust_emission_birth=Greybody(40.0, 1.5)), "total",
                                             dict(tau_v_birth=rng.uniform(0, 2, n))),
 }
+only = os.environ.get("VAR_ONLY")          # substring of the case names to run (an ncu capture wants one)
 out = {}
 for name, (em, key, extra) in cases.items():
+    if only and only not in name:
+        continue
     eng = SynthEngine(w.grid, em, key, w.filters, max_batch=n)
     p = w.params.slice(slice(0, n))
     for k, v in extra.items():
