@@ -560,7 +560,9 @@ def main():
         if args.traffic is not None:
             traffic, traffic_src = args.traffic, "--traffic"
         else:
-            prof = os.path.join(ROOT, "profiles", "r02_synth3_summary.txt")
+            prof = os.path.join(ROOT, "profiles", "r02_synth3_final_summary.txt")      # the final kernel (fused output)
+            if not os.path.isfile(prof):
+                prof = os.path.join(ROOT, "profiles", "r02_synth3_summary.txt")
             if s3 and args.workload == "cfg2" and os.path.isfile(prof):
                 import re
                 txt = open(prof).read()
@@ -569,7 +571,7 @@ def main():
                 if rd and wr:
                     unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
                     traffic = (float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)]) * n / 1e6
-                    traffic_src = "ncu --set full capture in profiles/r02_synth3_summary.txt (one launch, 1M galaxies), scaled by batch size"
+                    traffic_src = "ncu --set full capture in profiles/%s (one launch, 1M galaxies), scaled by batch size" % os.path.basename(prof)
         tf32 = measure_tf32_peak(dev)
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         kname = "synth3_kernel (3xTF32 tcgen05, weights as the TMEM operand, fused epilogue)" if s3 else \

@@ -956,10 +956,13 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   }
   a.part = m->part;
   a.n_rows = (long long)a.n_tiles * rpu;
-  // fused output: synth3_kernel's epilogue writes the fluxes (the dust emission's share is finalize_kernel's business)
+  // fused output: synth3_kernel's epilogue writes the fluxes, the dust emission's share of the filter sums included
   m->last_fused = false;
-  a.fuse_out = (rpu != 256 && use_s3(m, p) && !m->dust_wnu && !m->sw.no_fuse) ? 1 : 0;
+  //               (with dust emission AND spectra the emission's spectrum is added from the e_part planes: not fused)
+  a.fuse_out = (rpu != 256 && use_s3(m, p) && !(m->dust_wnu && spec_out) && !m->sw.no_fuse) ? 1 : 0;
   a.scaled_ld = flux_scaled ? p->scaled_ld : 0;
+  a.dust_duv = m->dust_wnu ? reinterpret_cast<const float2*>(m->dust_duv) : nullptr;
+  a.dust_m_len = d.dust_m_len;
   if (rpu == 256) {
     const int grid = 2 * std::min(a.n_tiles, m->n_sm / 2);
     rc = launch_synth2(m, a, grid, st);

@@ -50,7 +50,8 @@ __host__ __device__ inline int synth3_n_tables(int feat) {
 __host__ __device__ inline size_t synth3_smem_bytes(int kn, int n_stages, int n_age, int uv_len, int kap_len, bool spec, int feat = 0,
                                                     int n_x = 0) {
   return 1024 + (size_t)n_stages * (2 * kn * kBK * 4) + (size_t)n_age * 1024 + (((size_t)uv_len * 8 + 15) & ~size_t(15)) +
-         (size_t)kap_len * 4 * synth3_n_tables(feat) + kS3BarBytes + (spec ? kSpecSmemBytes : 0) + (size_t)n_x * kBM * 8;
+         (size_t)kap_len * 4 * synth3_n_tables(feat) + kS3BarBytes + (spec ? kSpecSmemBytes : 0) +
+         (n_x ? (size_t)(n_x + 1) * kBM * 8 : 0);      // (+ one row for the absorbed energy)
 }
 
 template <int kComp, int kNF, bool kSpec, int kN, int kFeat = 0>

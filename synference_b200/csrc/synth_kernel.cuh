@@ -95,6 +95,8 @@ struct SynthArgs {
   // of a tile and group 0 writes the fluxes itself (what finalize_kernel does from the `part` planes in HBM otherwise)
   int fuse_out;
   long long scaled_ld;       // layout of out_scaled for the fused output (FinalizeArgs.scaled_ld)
+  const float2* dust_duv;    // fused output with dust emission: [dust_m_len][n_filt] (FinalizeArgs.dust_duv); nullptr: none
+  int dust_m_len;
   const float2* filt_uv;     // padded tables, uv_len entries
   const float* igm;          // [n_tiles][n_blue_pad][128]
   const int* g_m;
@@ -487,6 +489,7 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
 #pragma unroll
             for (int f = 0; f < kNF; ++f)
               if (f < A.n_filt) s_x[f * kBM + et] = acc[f];
+            if (absorbed) reinterpret_cast<float*>(s_x + A.n_filt * kBM)[et] = e_abs;   // (one more row of the exchange area)
             __threadfence_block();
             named_bar_arrive(1, 256);
           } else {
@@ -499,6 +502,15 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
               const bool tr = A.scaled_ld > 0;
               const bool vec = (A.n_filt % 4) == 0 &&
                                ((reinterpret_cast<uintptr_t>(A.out_base) | (tr ? 0 : reinterpret_cast<uintptr_t>(A.out_scaled))) & 15) == 0;
+              // dust emission: E_abs (group 0 + group 1, finalize_kernel's order) times the emission's filter numerators
+              // at this galaxy's integer redshift shift
+              float e_tot = 0.f;
+              const float2* duv = nullptr;
+              if (absorbed && A.dust_duv != nullptr) {
+                e_tot = e_abs + reinterpret_cast<const float*>(s_x + A.n_filt * kBM)[et];
+                const int mm = A.g_m[row];
+                if (mm >= 0 && mm < A.dust_m_len) duv = A.dust_duv + (size_t)mm * A.n_filt;
+              }
 #pragma unroll
               for (int f0 = 0; f0 < kNF; f0 += 4) {
                 if (f0 < A.n_filt) {
@@ -510,7 +522,11 @@ __device__ __forceinline__ void epilogue_loop(const SynthArgs& A, const float2* 
                     fl[q] = 0.f;
                     if (f < A.n_filt) {
                       const float2 o = s_x[f * kBM + et];
-                      const float nu = acc[f <= kLast ? f : kLast].x + o.x, nv = acc[f <= kLast ? f : kLast].y + o.y;
+                      float nu = acc[f <= kLast ? f : kLast].x + o.x, nv = acc[f <= kLast ? f : kLast].y + o.y;
+                      if (duv != nullptr) {
+                        const float2 dd = __ldg(duv + f);
+                        nu = fmaf(e_tot, dd.x, nu); nv = fmaf(e_tot, dd.y, nv);
+                      }
                       float flux = fmaf(beta, nv, gamma * nu) / fmaf(beta, A.filt_sdv[f], gamma * A.filt_su[f]) * scf;
                       if ((trunc >> f) & 1u) flux = __int_as_float(0x7fc00000);
                       fl[q] = flux;

@@ -373,3 +373,22 @@ def test_uncertainty_models_from_an_epochs_style_table():
         S.create_uncertainty_models_from_EPOCHS_cat(tab, "F200W")
     with pytest.raises(ValueError):
         S.create_uncertainty_models_from_EPOCHS_cat(tab, "F444W", model_class="nope")
+
+
+def test_energy_full_axis_flag_follows_the_largest_optical_depth():
+    """SynthEngine._fill (host logic, no GPU): a model with absorbed-energy pseudo-bins asks for the sum over the whole axis
+    (sb2_params.energy_full_axis) when a batch's largest tau_V (+ ratio x tau_V_birth) is beyond the range the pseudo-bins are
+    accurate for, or is not finite."""
+    from synference_b200.engine import GalaxyParams, SynthEngine
+    eng = SynthEngine.__new__(SynthEngine)
+    eng.tables = dict(single_is_unatt=False, lya_line=None, kappa_birth=np.zeros(4, np.float32), dust_global=None,
+                      x_bins=192, x_tau_max=10.0, x_birth_ratio=1.0)
+    n = 5
+    base = dict(redshift=np.ones(n), sfh_type=5, sfh_rows=np.zeros((n, 4)), zd_type=1, zd_value=np.full(n, -2.0), zd_sigma=None,
+                log_mass=None)
+    for tau, birth, want in ((3.0, 2.0, 0), (6.0, 3.9, 0), (6.0, 4.1, 1), (11.0, 0.0, 1), (np.nan, 0.0, 1)):
+        p = GalaxyParams(tau_v=np.full(n, tau), tau_v_birth=np.full(n, birth), **base)
+        assert eng._fill(p, lambda a: None).energy_full_axis == want, (tau, birth)
+    eng.tables["x_bins"] = 0
+    p = GalaxyParams(tau_v=np.full(n, 50.0), tau_v_birth=np.full(n, 0.0), **base)
+    assert eng._fill(p, lambda a: None).energy_full_axis == 0
