@@ -282,3 +282,30 @@ class ResampledFeatures:
             parameter_array=self.params, device=self.dev, return_torch=True, **self.kw)
         self.feature_names = names
         return f, p
+
+    def __len__(self):
+        """Training rows per epoch."""
+        return int(self.grid.shape[1]) * int(self.n_scatter)
+
+    def loader(self, batch_size: int, epochs: int, shuffle: bool = True, rank: int = 0, world_size: int = 1, start_epoch: int = 0):
+        """Mini-batches ``(features, parameters)`` for ``epochs`` epochs: what a ``DataLoader`` over the static, pre-scattered
+        array of the reference gives (``sbi_runner.py``: the feature array is built once with ``scatter_fluxes`` replicas),
+        except that every epoch is a fresh noise realisation drawn on the device.  The row order of an epoch is a permutation
+        keyed by ``(seed, epoch)``, the same on every rank; rank ``r`` of ``world_size`` takes every ``world_size``-th batch,
+        so the ranks of a data-parallel trainer see disjoint batches of one global epoch."""
+        import torch
+        n = len(self)
+        for e in range(int(start_epoch), int(start_epoch) + int(epochs)):
+            feats, par = self.epoch(e)
+            par_t = None if par is None else torch.as_tensor(np.asarray(par), device=feats.device)
+            if shuffle:
+                g = torch.Generator(device="cpu")
+                g.manual_seed((int(self.seed) * 1_000_003 + e) & 0x7FFFFFFFFFFFFFFF)
+                order = torch.randperm(n, generator=g).to(feats.device)
+            else:
+                order = torch.arange(n, device=feats.device)
+            for b, lo in enumerate(range(0, n, int(batch_size))):
+                if b % int(world_size) != int(rank):
+                    continue
+                idx = order[lo:lo + int(batch_size)]
+                yield feats[idx], (None if par_t is None else par_t[idx])

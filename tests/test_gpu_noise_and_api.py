@@ -103,6 +103,40 @@ def test_resampled_features_per_epoch():
     assert bool((f0 == f0b).all()) and not bool((f0 == f1).all())
 
 
+def test_resampled_features_loader_covers_every_row_once_per_epoch_across_ranks():
+    """ResampledFeatures.loader: per epoch the mini-batches of all ranks together are a permutation of that epoch's rows (features
+    paired with their parameters), the same (seed, epoch) gives the same batches again, and epochs differ in their noise."""
+    import torch
+    from synference_b200.features import ResampledFeatures
+    rng = np.random.default_rng(4)
+    n_gal, n_sc = 1000, 2
+    grid = np.abs(rng.normal(200, 30, (3, n_gal))) + 50
+    par = np.stack([np.arange(n_gal, dtype=float), rng.uniform(0, 1, n_gal)], 1)           # column 0 identifies the galaxy
+    rf = ResampledFeatures(grid, ["a", "b", "c"], depths=np.full(3, 27.0), parameter_array=par, n_scatter=n_sc, seed=3)
+    assert len(rf) == n_gal * n_sc
+    seen = {0: [], 1: []}
+    for r in (0, 1):
+        for feats, p in rf.loader(batch_size=300, epochs=2, rank=r, world_size=2):
+            assert feats.is_cuda and feats.shape[1] == 3 and p.shape[0] == feats.shape[0]
+            seen[r].append((feats, p))
+    n_batches = -(-len(rf) // 300)
+    assert len(seen[0]) + len(seen[1]) == 2 * n_batches
+    full0, par0 = rf.epoch(0)
+    par0 = torch.as_tensor(np.asarray(par0), device=full0.device)
+    # epoch 0 = the first n_batches batches in global order: rank r holds batches r, r + 2, ...
+    per_rank = [(n_batches + 1) // 2, n_batches // 2]
+    got = torch.cat([b[0] for r in (0, 1) for b in seen[r][:per_rank[r]]])
+    gpar = torch.cat([b[1] for r in (0, 1) for b in seen[r][:per_rank[r]]])
+    assert got.shape[0] == len(rf)
+    # pairing: a batch row's features are the epoch's row with the same (galaxy id, replica) -- match through a sort on a key
+    key_full = torch.argsort(full0[:, 0] * 1e3 + par0[:, 0]); key_got = torch.argsort(got[:, 0] * 1e3 + gpar[:, 0])
+    assert torch.equal(full0[key_full], got[key_got]) and torch.equal(par0[key_full], gpar[key_got])
+    again = [b for b in rf.loader(batch_size=300, epochs=1, rank=0, world_size=2)]
+    assert all(torch.equal(a[0], b[0]) for a, b in zip(again, seen[0][:per_rank[0]]))
+    e1 = torch.cat([b[0] for r in (0, 1) for b in seen[r][per_rank[r]:]])
+    assert e1.shape == got.shape and not torch.equal(torch.sort(e1[:, 0]).values, torch.sort(got[:, 0]).values)
+
+
 def _small_basis(n, tmp):
     raw = S.FilterCollection(filter_codes=["JWST/NIRCam.F070W", "JWST/NIRCam.F090W", "JWST/NIRCam.F115W",
                                            "JWST/NIRCam.F200W", "JWST/NIRCam.F277W", "JWST/NIRCam.F356W",
