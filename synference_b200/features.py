@@ -297,7 +297,7 @@ class ResampledFeatures:
         n = len(self)
         for e in range(int(start_epoch), int(start_epoch) + int(epochs)):
             feats, par = self.epoch(e)
-            par_t = None if par is None else torch.as_tensor(np.asarray(par), device=feats.device)
+            par_t = None if par is None else (par if isinstance(par, torch.Tensor) else torch.as_tensor(np.asarray(par))).to(feats.device)
             if shuffle:
                 g = torch.Generator(device="cpu")
                 g.manual_seed((int(self.seed) * 1_000_003 + e) & 0x7FFFFFFFFFFFFFFF)

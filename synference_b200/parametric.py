@@ -293,26 +293,40 @@ ZD_DELTA_LINEAR, ZD_DELTA_LOG10, ZD_NORMAL_LINEAR, ZD_NORMAL_LOG10 = range(4)
 
 
 class _ZDistCommon:
+    __slots__ = ()
     type_id = -1
 
     def __repr__(self):
         return f"ZDist.{type(self).__name__}({self.parameters})"
 
 
+_PLAIN_NUMBERS = (float, int, np.float64, np.float32)
+
+
 class _DeltaConstant(_ZDistCommon):
-    """All mass at one metallicity (shared between the two bracketing grid points)."""
+    """All mass at one metallicity (shared between the two bracketing grid points).
+
+    The README flow builds one of these per galaxy in a list comprehension (README.md:113-114): the object holds two slots
+    and derives the rest, so that a million of them cost what the comprehension itself costs."""
+
+    __slots__ = ("type_id", "value")
+    name = "DeltaConstant"
+    sigma = 0.0
 
     def __init__(self, metallicity=None, log10metallicity=None):
-        if (metallicity is None) == (log10metallicity is None):
-            raise ValueError("Give exactly one of metallicity / log10metallicity")
-        self.name = "DeltaConstant"
-        if metallicity is not None:
-            self.type_id, self.value = ZD_DELTA_LINEAR, float(strip_units(metallicity))
-            self.parameters = {"metallicity": self.value}
+        if metallicity is None:
+            if log10metallicity is None:
+                raise ValueError("Give exactly one of metallicity / log10metallicity")
+            self.type_id, v = ZD_DELTA_LOG10, log10metallicity
         else:
-            self.type_id, self.value = ZD_DELTA_LOG10, float(strip_units(log10metallicity))
-            self.parameters = {"log10metallicity": self.value}
-        self.sigma = 0.0
+            if log10metallicity is not None:
+                raise ValueError("Give exactly one of metallicity / log10metallicity")
+            self.type_id, v = ZD_DELTA_LINEAR, metallicity
+        self.value = float(v) if type(v) in _PLAIN_NUMBERS else float(strip_units(v))
+
+    @property
+    def parameters(self):
+        return {("metallicity" if self.type_id == ZD_DELTA_LINEAR else "log10metallicity"): self.value}
 
     def get_metallicity(self):
         return self.value if self.type_id == ZD_DELTA_LINEAR else 10.0**self.value
@@ -320,6 +334,8 @@ class _DeltaConstant(_ZDistCommon):
 
 class _Normal(_ZDistCommon):
     """Gaussian in Z (or log10 Z) evaluated at the grid metallicities, normalised."""
+
+    __slots__ = ("name", "type_id", "value", "sigma", "parameters")
 
     def __init__(self, mean, sigma, log10=True):
         self.name = "Normal"
@@ -374,11 +390,14 @@ def pack_zdist(zd) -> (int, np.ndarray, np.ndarray):
     if isinstance(zd, _ZDistCommon):
         zd = [zd]
     zd = list(zd)
-    tid = {d.type_id for d in zd}
-    if len(tid) != 1:
+    n = len(zd)
+    tids = np.fromiter((d.type_id for d in zd), dtype=np.int64, count=n)
+    if n == 0 or tids.min() != tids.max():
         raise ValueError("All metallicity distributions in one basis must share a type")
-    return tid.pop(), np.array([d.value for d in zd], dtype=float), \
-        np.array([d.sigma for d in zd], dtype=float)
+    value = np.fromiter((d.value for d in zd), dtype=np.float64, count=n)
+    sigma = np.zeros(n) if int(tids[0]) in (ZD_DELTA_LINEAR, ZD_DELTA_LOG10) else \
+        np.fromiter((d.sigma for d in zd), dtype=np.float64, count=n)
+    return int(tids[0]), value, sigma
 
 
 # --------------------------------------------------------------------------

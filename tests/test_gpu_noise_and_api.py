@@ -122,7 +122,7 @@ def test_resampled_features_loader_covers_every_row_once_per_epoch_across_ranks(
     n_batches = -(-len(rf) // 300)
     assert len(seen[0]) + len(seen[1]) == 2 * n_batches
     full0, par0 = rf.epoch(0)
-    par0 = torch.as_tensor(np.asarray(par0), device=full0.device)
+    par0 = (par0 if isinstance(par0, torch.Tensor) else torch.as_tensor(np.asarray(par0))).to(full0.device)
     # epoch 0 = the first n_batches batches in global order: rank r holds batches r, r + 2, ...
     per_rank = [(n_batches + 1) // 2, n_batches // 2]
     got = torch.cat([b[0] for r in (0, 1) for b in seen[r][:per_rank[r]]])

@@ -252,6 +252,47 @@ def test_emission_variants_match_c_oracle_at_20000(model):
     eng.close()
 
 
+@pytest.mark.parametrize("case", ["one_screen_tau_to_8", "two_screens_same_curve", "beyond_range_sums_over_the_axis"])
+def test_absorbed_energy_pseudo_bins_against_the_c_oracle(case):
+    """Spectrum 'total' with the absorbed-energy sum on pseudo-bins against the C oracle, which sums over the
+    whole axis: optical depths up to 8 on one screen, two screens with the same curve (exponent (tau_birth + tau_ism) kappa on
+    the pseudo-bins), and a batch beyond the range the model states for its pseudo-bins, which must take the full-axis sum
+    (sb2_params.energy_full_axis)."""
+    from synference_b200.parametric import BimodalPacmanEmission, Calzetti2000, Greybody, PacmanEmission
+    n = 4000
+    w = make_workload("cfg2", n)
+    lam = np.asarray(w.grid.lam)
+    filt = [(f.lam, f.t) for f in w.filters]
+    p = w.params.slice(slice(0, n))
+    rng = np.random.default_rng(12)
+    kw = dict(dust_shape=O.dust_emission_shape(lam, kind="Greybody", temperature=40.0, emissivity=1.5))
+    if case == "two_screens_same_curve":
+        em = BimodalPacmanEmission(grid=w.grid, dust_curve_ism=Calzetti2000(), dust_curve_birth=Calzetti2000(), age_pivot=7.0,
+                                   dust_emission_ism=Greybody(40.0, 1.5), dust_emission_birth=Greybody(40.0, 1.5), fesc_ly_alpha=0.4)
+        p.tau_v_birth = rng.uniform(0.0, 3.0, n)
+        ga, gu = O.emission_parts(w.grid.spectra, lam, "total", 0.0, 0.4)
+        kw["two_screens"] = dict(age_pivot=7.0, kappa_birth=O.dust_kappa(lam), tau_v_birth=p.tau_v_birth)
+    else:
+        em = PacmanEmission(grid=w.grid, fesc=0.1, fesc_ly_alpha=0.5, dust_curve=Calzetti2000(), dust_emission=Greybody(40.0, 1.5))
+        if case == "one_screen_tau_to_8":
+            p.tau_v = rng.uniform(0.0, 8.0, n)
+        ga, gu = O.emission_parts(w.grid.spectra, lam, "total", 0.1, 0.5)
+    eng = SynthEngine(w.grid, em, "total", w.filters, max_batch=1 << 15)
+    assert eng.tables["x_bins"] == 192 and eng.tables["x_tau_max"] > 9.0
+    if case == "beyond_range_sums_over_the_axis":
+        # (the mechanism, at optical depths where float32 is still meaningful: on the pinned Calzetti curve -- negative in the
+        #  mid-infrared -- tau_V = 12 means exp(+42) there, and the float32 energy sum of EITHER form is good to 1e-3 only)
+        eng.tables["x_tau_max"] = 1.0
+    flag = eng._fill(p, lambda a: None).energy_full_axis
+    assert flag == (1 if case == "beyond_range_sums_over_the_axis" else 0)
+    got = eng.photometry(p, scaled=False)
+    want = CO.synthesize(p, w.grid.log10ages, w.grid.metallicity, lam, ga, gu, filt, kappa=O.dust_kappa(lam),
+                         igm=(I.INOUE14_LAF, I.INOUE14_DLA), **kw)
+    err = assert_flux_close(got, want)
+    print(f"{case}: max rel err {err:.3e}")
+    eng.close()
+
+
 def test_float32_parameter_transport_is_exact_for_float32_draws(engines):
     """parameters cross PCIe as float32 (sb2_params.host_f32) and are widened on the device.  The draws of
     draw_from_hypercube ARE float32 (library.py:1098): sending the raw draws with max_age_from_z gives bit-identical fluxes
