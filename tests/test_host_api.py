@@ -392,3 +392,36 @@ def test_energy_full_axis_flag_follows_the_largest_optical_depth():
     eng.tables["x_bins"] = 0
     p = GalaxyParams(tau_v=np.full(n, 50.0), tau_v_birth=np.full(n, 0.0), **base)
     assert eng._fill(p, lambda a: None).energy_full_axis == 0
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The C ABI is plain structs: every field of the ctypes mirrors in synference_b200/_capi.py must sit at the offset a C
+    compiler gives it in include/synference_b200.h (a drifted mirror would scramble every argument behind it).  gcc compiles a
+    probe that prints sizeof and offsetof for every field; the field NAMES come from the mirrors, so a field missing on
+    either side fails to compile or to compare."""
+    import ctypes
+    import shutil
+    import subprocess
+    from synference_b200 import _capi
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = [("sb2_model_desc", _capi.ModelDesc), ("sb2_params", _capi.Params), ("sb2_resample_desc", _capi.ResampleDesc),
+             ("sb2_empirical_model", _capi.EmpiricalModel)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "synference_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, *_ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, *_ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    # and the header has no field the mirror lacks: same number of members (counted by the compiler through the sizes above
+    # only if every one is mirrored; a trailing unmirrored field shows up as a size mismatch)
