@@ -44,7 +44,7 @@ def create_feature_array_from_raw_photometry(
         photometry_to_remove: Optional[list] = None, drop_dropouts: bool = False,
         drop_dropout_fraction: float = 1.0, parameter_array=None, normals=None, seed: int = 0,
         epoch: int = 0, device: int = 0, return_torch: bool = False, empirical_noise_models=None,
-        depth_indices=None, asinh_softening_parameters=None):
+        depth_indices=None, asinh_softening_parameters=None, normalization_unit: str = "AB"):
     """``(N_filters, N_gal)`` library photometry -> ``(feature_array (N_rows, N_feat) float32,
     feature_names, parameter_array (N_rows, N_par) | None)``.
 
@@ -59,11 +59,31 @@ def create_feature_array_from_raw_photometry(
     ``normed_flux_units="asinh"`` (``sbi_runner.py:1598-1625, 1660-1676, 1718-1730``): asinh magnitudes with the softening
     ``asinh_softening_parameters`` -- one flux per filter (a Quantity array, or a list / dict of quantities), or ``"SNR_x"``:
     x times the 1-sigma depth of each filter.  No magnitude limit is applied in this branch, as in the reference.
+    Any other ``normed_flux_units`` (``sbi_runner.py:1734-1779``) is a flux unit (``"nJy"``, ``"uJy"``, ``"mJy"``, ``"Jy"``) or a
+    scaling of one, ``"log10 nJy"`` / ``"log nJy"`` / ``"sqrt nJy"``, with the reference's error propagation; such rows are
+    normalised by DIVISION -- by subtraction for the two logarithms, and, as in the reference, only when the rows carry errors.
+    ``normalize_method`` = a filter name: that filter leaves the rows, the others are normalised by it, and the last column
+    holds the filter's UNSCATTERED library flux in ``normalization_unit`` (``"AB"``, a flux unit, or ``"log10 <unit>"``;
+    ``sbi_runner.py:1783-1831``), named ``norm_<filter>_<normalization_unit>`` (``:2024-2027``).  (The reference can only do
+    this for at most one replica per galaxy -- its assignment of the column fails otherwise; here the value is repeated.)
     """
     import torch
-    if normed_flux_units not in ("AB", "asinh"):
-        raise NotImplementedError("the device feature builder implements normed_flux_units 'AB' and 'asinh'")
     asinh = normed_flux_units == "asinh"
+    other_scaling, other_unit = None, None
+    if normed_flux_units not in ("AB", "asinh"):
+        if str(normed_flux_units) in _TO_NJY:
+            other_scaling, other_unit = "", str(normed_flux_units)
+        else:
+            try:
+                other_scaling, other_unit = str(normed_flux_units).split(" ")
+            except ValueError:
+                raise ValueError("Don't understand normed_flux_units.If string, should be e.g. 'log10 nJy',Otherwise pass a Unit directly.")
+            if other_scaling not in ("log10", "log", "", "sqrt"):
+                raise ValueError(f'Scaling "{other_scaling}" not recognized. Use "log10", "log","", or "sqrt".')
+            if other_unit not in _TO_NJY:
+                raise ValueError(f"normed_flux_units: unknown flux unit '{other_unit}'")
+        if empirical_noise_models is not None and depths is None:
+            raise NotImplementedError("empirical noise models hand back AB (or asinh) magnitudes; other feature units take depths")
     if asinh:
         assert asinh_softening_parameters is not None, "asinh_softening_parameters must be provided for asinh normalization."
         if empirical_noise_models is not None and depths is None:
@@ -153,6 +173,23 @@ def create_feature_array_from_raw_photometry(
         pog = 2.5 * np.log10(np.e)
         mags = (-pog * (torch.asinh(f_jy / (2 * b)) + torch.log(b / 3631.0))).t()       # utils.py:647-675
         errs = (pog * e_jy / torch.sqrt(f_jy * f_jy + (2 * b) ** 2)).t()                # utils.py:678-704
+    elif other_unit is not None:
+        # a flux unit, optionally scaled (sbi_runner.py:1734-1779): noisy fluxes and their sigmas from the kernel, then the
+        # unit change, the scaling and the reference's error propagation
+        flux_gf = grid.t().contiguous()
+        noisy, sig, _ = depth_noise_features(flux_gf, sigma, n_scatter=n_sc, normals=normals, seed=seed, epoch=epoch,
+                                             norm_mag_limit=norm_mag_limit, min_flux_pc_error=min_flux_pc_error,
+                                             want_flux=True, want_features=False, device=device, set_index=set_index)
+        ph, er = noisy.t() / _TO_NJY[other_unit], sig.t() / _TO_NJY[other_unit]
+        if scatter_fluxes:
+            if other_scaling == "log10":
+                er = er / (ph * np.log(10.0))
+            elif other_scaling == "log":
+                er = er / ph
+            elif other_scaling == "sqrt":
+                er = er / (2.0 * torch.sqrt(ph))
+        ph = {"log10": torch.log10, "log": torch.log, "sqrt": torch.sqrt, "": lambda x: x}[other_scaling](ph)
+        mags, errs = ph, er
     else:
         flux_gf = grid.t().contiguous()                                   # (n_gal, n_filt), kernel layout
         _, _, feat = depth_noise_features(flux_gf, sigma, n_scatter=n_sc, normals=normals, seed=seed, epoch=epoch,
@@ -160,20 +197,39 @@ def create_feature_array_from_raw_photometry(
                                           want_flux=False, want_features=True, device=device, set_index=set_index)
         mags, errs = feat[:, :n_filt], feat[:, n_filt:]
     feature_names = list(names)
+    zero_norm = None
     if normalize_method is not None:
         if normalize_method not in names:
-            raise NotImplementedError("normalisation by a parameter is not part of the device path; "
+            raise NotImplementedError("normalisation by a supplementary parameter is not part of the device path; "
                                       "use a filter name")
         j = names.index(normalize_method)
         norm = mags[:, j:j + 1]
+        zero_norm = norm[:, 0] == 0.0                   # such rows are deleted (sbi_runner.py:1917-1925)
         others = [i for i in range(n_filt) if i != j]
-        mags = mags[:, others] - norm
-        if not asinh:
+        # magnitudes and logarithms are normalised by subtraction, fluxes by division; the reference switches the two
+        # logarithmic scalings to subtraction only where it propagates errors, i.e. when the rows were scattered
+        subtract = other_unit is None or (other_scaling in ("log10", "log") and bool(scatter_fluxes))
+        mags = (mags[:, others] - norm) if subtract else (mags[:, others] / norm)
+        if other_unit is None and not asinh:
             mags = torch.clamp(mags, max=norm_mag_limit)
         errs = errs[:, others]
         feature_names = [names[i] for i in others]
-        cols = [mags] + ([errs] if include_errors_in_feature_array and scatter_fluxes else []) + [norm]
-        tail = [f"norm_{normalize_method}"]
+        # the last column: the filter's library flux BEFORE the scatter, in normalization_unit (sbi_runner.py:1788-1831)
+        orig = grid[j].repeat_interleave(n_sc)
+        nu = str(normalization_unit)
+        nu_log = nu.startswith("log10")
+        nu_unit = nu.split(" ")[1] if nu_log else nu
+        if nu_unit == "AB":
+            norm_col = -2.5 * torch.log10(orig * 1e-3) + 23.9
+        elif nu_unit in _TO_NJY:
+            norm_col = orig / _TO_NJY[nu_unit]
+        else:
+            raise ValueError(f"normalization_unit: unknown unit '{nu_unit}'")
+        if nu_log:
+            norm_col = torch.log10(norm_col)
+            norm_col = torch.where(torch.isinf(norm_col), torch.zeros_like(norm_col), norm_col)
+        cols = [mags] + ([errs] if include_errors_in_feature_array and scatter_fluxes else []) + [norm_col[:, None].to(mags.dtype)]
+        tail = [f"norm_{normalize_method}_{normalization_unit}"]
     else:
         cols = [mags] + ([errs] if include_errors_in_feature_array and scatter_fluxes else [])
         tail = []
@@ -182,6 +238,8 @@ def create_feature_array_from_raw_photometry(
     feature_names = feature_names + tail
     out = torch.cat(cols, 1) if len(cols) > 1 else cols[0]
     keep_rows = torch.ones(out.shape[0], dtype=torch.bool, device=dev)
+    if zero_norm is not None:
+        keep_rows &= ~zero_norm
     if remove_nan_inf:
         keep_rows &= torch.isfinite(out).all(1)
     if drop_dropouts:

@@ -86,9 +86,50 @@ def test_feature_array_builder_matches_numpy_restatement():
     m0 = -2.5 * np.log10(grid * 1e-3) + 23.9
     np.testing.assert_allclose(feat2[:, 0], (m0[0] - m0[2]), atol=2e-4)
     np.testing.assert_allclose(feat2[:, -1], m0[2], atol=1e-4)
-    assert fn2[-1] == "norm_" + names[2] and len(fn2) == 6
+    assert fn2[-1] == "norm_" + names[2] + "_AB" and len(fn2) == 6           # norm_<filter>_<normalization_unit>, sbi_runner.py:2026
     with pytest.raises(ValueError):
         create_feature_array_from_raw_photometry(grid, names, photometry_to_remove=["nope"])
+
+
+def test_feature_rows_in_flux_units_and_their_scalings():
+    """normed_flux_units other than AB / asinh (sbi_runner.py:1734-1779): a flux unit, or log10 / log / sqrt of one with the
+    reference's error propagation; normalisation by a filter divides (subtracts for the logarithms, and -- the reference's own
+    rule -- only when the rows carry errors); the appended column is the filter's UNSCATTERED flux in normalization_unit."""
+    rng = np.random.default_rng(21)
+    n_gal, names = 3000, ["a", "b", "c", "d"]
+    grid = np.abs(rng.normal(300, 40, (4, n_gal))) + 50.0                   # nJy, far from zero: every logarithm is finite
+    depths = np.full(4, 29.0)
+    sigma = depths_to_sigma_njy(depths)
+    z = rng.standard_normal((4, n_gal * 2))
+    noisy, std = O.apply_depths(grid, sigma, z, 2)                            # (n_filt, n_rows)
+    # 1. plain unit with errors
+    f, fn, _ = create_feature_array_from_raw_photometry(grid, names, normed_flux_units="uJy", scatter_fluxes=2, depths=depths,
+                                                        normals=z, include_errors_in_feature_array=True)
+    np.testing.assert_allclose(f, np.concatenate([noisy * 1e-3, std * 1e-3], 0).T, rtol=2e-6)
+    assert fn == names + [f"unc_{n}" for n in names]
+    # 2. log10 with errors, normalised by filter c: subtraction; the last column from the library flux, repeated per replica
+    f, fn, _ = create_feature_array_from_raw_photometry(grid, names, normed_flux_units="log10 nJy", scatter_fluxes=2, depths=depths,
+                                                        normals=z, include_errors_in_feature_array=True, normalize_method="c",
+                                                        normalization_unit="log10 nJy")
+    lg, er = np.log10(noisy), std / (noisy * np.log(10.0))
+    want = np.concatenate([(lg[[0, 1, 3]] - lg[2]), er[[0, 1, 3]], np.log10(np.repeat(grid[2], 2))[None, :]], 0).T
+    np.testing.assert_allclose(f, want, rtol=3e-6, atol=3e-6)
+    assert fn == ["a", "b", "d", "unc_a", "unc_b", "unc_d", "norm_c_log10 nJy"]
+    # 3. log10 WITHOUT scatter: the reference keeps dividing; sqrt and plain units divide
+    f, fn, _ = create_feature_array_from_raw_photometry(grid, names, normed_flux_units="log10 uJy", normalize_method="a",
+                                                        normalization_unit="uJy")
+    lg = np.log10(grid * 1e-3)
+    np.testing.assert_allclose(f, np.concatenate([lg[1:] / lg[0], (grid[0] * 1e-3)[None, :]], 0).T, rtol=3e-6)
+    assert fn == ["b", "c", "d", "norm_a_uJy"]
+    f, _, _ = create_feature_array_from_raw_photometry(grid, names, normed_flux_units="sqrt nJy", scatter_fluxes=2, depths=depths,
+                                                       normals=z, include_errors_in_feature_array=True)
+    np.testing.assert_allclose(f, np.concatenate([np.sqrt(noisy), std / (2 * np.sqrt(noisy))], 0).T, rtol=3e-6)
+    f, fn, _ = create_feature_array_from_raw_photometry(grid, names, normed_flux_units="nJy", normalize_method="d")
+    np.testing.assert_allclose(f, np.concatenate([grid[:3] / grid[3], (-2.5 * np.log10(grid[3] * 1e-3) + 23.9)[None, :]], 0).T, rtol=3e-6)
+    assert fn[-1] == "norm_d_AB"
+    for bad in ("log10nJy", "cube nJy", "log10 parsec"):
+        with pytest.raises(ValueError):
+            create_feature_array_from_raw_photometry(grid, names, normed_flux_units=bad)
 
 
 def test_resampled_features_per_epoch():
@@ -500,8 +541,13 @@ def test_asinh_feature_rows():
     f2, n2, _ = create_feature_array_from_raw_photometry(grid, names, normed_flux_units="asinh", asinh_softening_parameters=soft,
                                                          normalize_method="b")
     m = O.asinh_mag(grid * 1e-9, (np.array([5.0, 8.0, 10.0]) * 1e-9)[:, None]).T
-    np.testing.assert_allclose(f2, np.stack([m[:, 0] - m[:, 1], m[:, 2] - m[:, 1], m[:, 1]], 1), rtol=2e-6, atol=2e-6)
-    assert n2 == ["a", "c", "norm_b"]
+    # (the appended column is the filter's library flux in normalization_unit -- AB by default -- whatever the rows' unit is)
+    with np.errstate(invalid="ignore"):
+        m_ab = -2.5 * np.log10(grid[1] * 1e-3) + 23.9
+    keep = np.isfinite(m_ab)            # a negative library flux has no AB magnitude: that row goes (remove_nan_inf)
+    assert 0 < keep.sum() and f2.shape[0] == keep.sum()
+    np.testing.assert_allclose(f2, np.stack([m[:, 0] - m[:, 1], m[:, 2] - m[:, 1], m_ab], 1)[keep], rtol=2e-6, atol=2e-6)
+    assert n2 == ["a", "c", "norm_b_AB"]
     with pytest.raises(AssertionError):
         create_feature_array_from_raw_photometry(grid, names, normed_flux_units="asinh")
 
