@@ -260,6 +260,17 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const double s0 = X.s0[(size_t)tile * kBM + t], s1 = X.s1[(size_t)tile * kBM + t];
+      if (SB2_DBG_BITS(A) & 4096) {
+        // experiment: the issue slots a fused weight builder would take on these warps -- (dbg >> 16) * 16 iterations of two
+        // dependent float64 FMAs and a shared-memory read per galaxy and tile (the real builder: ~8 k instructions)
+        double x0 = s0 + 1.0, x1 = s1 + 2.0;
+        const int reps = (SB2_DBG_BITS(A) >> 16) * 16;
+        for (int i = 0; i < reps; ++i) {
+          x0 = fma(x0, 1.0000001, 1e-9) + s_sf[(i & 31) * 128 + t];
+          x1 = fma(x1, 0.9999999, 1e-9);
+        }
+        if (x0 + x1 == 12345.678) s_sf[t] = x0;
+      }
       mbar_wait(sfull_bar, ti & 1u, 0x3700u);
       for (int r = 0; r < 2; ++r) {
         mbar_wait(&wfree_bar[r], (ti & 1u) ^ 1u, 0x3800u + (uint32_t)r);
