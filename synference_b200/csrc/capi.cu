@@ -500,10 +500,19 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   m->smem160_bytes = 1024 + (size_t)sb2::kStages * sb2::SynthCfg<160>::kStageBytesN + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + sb2::kBarBytes;
   m->smem2_bytes = 1024 + (size_t)sb2::kW2Bytes + (size_t)sb2::kG2Slots * sb2::kG2Slot + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + sb2::kBarBytes;
   if (m->smem2_bytes > (size_t)prop.sharedMemPerBlockOptin || m->wd_stride > sb2::kW2Kb * sb2::kBK || (m->n_sm & 1)) m->smem2_bytes = 0;  // CTA-pair kernel unavailable
-  if (m->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
-    sb2_model_destroy(m);
-    return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to the operand pipeline (" +
-                                     std::to_string(m->smem_bytes) + " B needed)");
+  {
+    // The filter tables share the SM's shared memory with a kernel's operand ring.  The variants differ in what they need
+    // (256-column chunks most, synth3_kernel least): a model is usable if ANY of them fits; a batch that needs one that does
+    // not is refused at launch (launch_synth_t), not here -- 28 filters fit synth3_kernel but not the 256-column kernel.
+    const size_t uvb = ((size_t)m->uv_len * 8 + 15) & ~size_t(15);
+    const size_t split_bytes = 1024 + (size_t)sb2::kStages * sb2::SynthCfg<128>::kStageBytesN + uvb + sb2::kBarBytes;
+    const bool any = m->smem_bytes <= m->smem_optin || (d->n_comp == 1 && m->smem160_bytes <= m->smem_optin) ||
+                     split_bytes <= m->smem_optin || m->s3_ok;
+    if (!any) {
+      sb2_model_destroy(m);
+      return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to the operand pipeline (" +
+                                       std::to_string(std::min(m->smem_bytes, split_bytes)) + " B needed)");
+    }
   }
   if (cudaHostAlloc(reinterpret_cast<void**>(&m->wait_dbg), 260 * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess) {
     std::memset(m->wait_dbg, 0, 260 * sizeof(unsigned int));
@@ -577,6 +586,7 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
     auto k = sb2::synth_kernel<C, NF, SPEC, 128, PG, kDenseSplit>;
     sb2::SynthArgs a2 = a;
     size_t bytes = 1024 + (size_t)sb2::kStages * sb2::SynthCfg<128>::kStageBytesN + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + sb2::kBarBytes;
+    if (bytes > m->smem_optin) return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to this batch's kernel (dense K)");
     if (SPEC && bytes + sb2::kSpecSmemBytes <= m->smem_optin) {
       bytes += sb2::kSpecSmemBytes;
       a2.spec_smem = 1;
@@ -591,6 +601,7 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
       auto k = sb2::synth_kernel<C, NF, SPEC, 160, PG>;
       sb2::SynthArgs a2 = a;
       size_t bytes = m->smem160_bytes;
+      if (bytes > m->smem_optin) return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to this batch's kernel (160-column chunks)");
       if (SPEC && bytes + sb2::kSpecSmemBytes <= m->smem_optin) {   // room for the spectra transpose tiles
         bytes += sb2::kSpecSmemBytes;
         a2.spec_smem = 1;
@@ -603,6 +614,7 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
     }
   }
   auto k = sb2::synth_kernel<C, NF, SPEC, sb2::kBN, PG>;
+  if (m->smem_bytes > m->smem_optin) return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to this batch's kernel (256-column chunks)");
   CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes));
   k<<<grid, sb2::kSynthThreads, m->smem_bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo,
                                                      m->tm_g_hi, m->tm_g_lo, a);

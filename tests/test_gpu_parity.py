@@ -293,6 +293,51 @@ def test_absorbed_energy_pseudo_bins_against_the_c_oracle(case):
     eng.close()
 
 
+@pytest.mark.parametrize("model", ["default", "total_two_screens"])
+def test_twenty_eight_filters_take_the_widest_instantiation(model):
+    """More than 24 filters: the 32-filter instantiations of the kernels, larger filter tables in shared memory and a larger
+    output exchange (fewer ring stages, or the two-kernel output where three stages no longer fit beside it).  cfg2's 20 bands
+    plus eight copies shifted in wavelength, against the numpy / C oracle."""
+    from synference_b200.parametric import BimodalPacmanEmission, Calzetti2000, Filter, FilterCollection, Greybody
+    n = 600
+    w = make_workload("cfg2", n)
+    lam = np.asarray(w.grid.lam)
+    extra = []
+    for k, f in enumerate(list(w.filters)[:8]):
+        shift = 37 + 11 * k                                             # bins: the copy sits redward of its original
+        t = np.zeros_like(f.t)
+        t[shift:] = f.t[:-shift]
+        extra.append(Filter(f"TEST/shifted.{k}", lam, t * (0.6 + 0.05 * k)))
+    fc = FilterCollection(filters=list(w.filters) + extra)
+    fc.lam = w.filters.lam
+    assert len(fc.filters) == 28
+    filt = [(f.lam, f.t) for f in fc.filters]
+    p = w.params.slice(slice(0, n))
+    kw = {}
+    if model == "default":
+        em, key = w.emission_model, w.emission_key
+        ga, gu = O.emission_parts(w.grid.spectra, lam, key, float(em.fesc), float(em.fesc_ly_alpha))
+    else:
+        em = BimodalPacmanEmission(grid=w.grid, dust_curve_ism=Calzetti2000(), dust_curve_birth=Calzetti2000(), age_pivot=7.0,
+                                   dust_emission_ism=Greybody(40.0, 1.5), dust_emission_birth=Greybody(40.0, 1.5), fesc_ly_alpha=0.4)
+        key = "total"
+        p.tau_v_birth = np.random.default_rng(3).uniform(0.0, 3.0, n)
+        ga, gu = O.emission_parts(w.grid.spectra, lam, key, 0.0, 0.4)
+        kw = dict(two_screens=dict(age_pivot=7.0, kappa_birth=O.dust_kappa(lam), tau_v_birth=p.tau_v_birth),
+                  dust_shape=O.dust_emission_shape(lam, kind="Greybody", temperature=40.0, emissivity=1.5))
+    eng = SynthEngine(w.grid, em, key, fc, max_batch=1 << 12)
+    assert eng.n_filt == 28
+    got = eng.photometry(p, scaled=False)
+    want = CO.synthesize(p, w.grid.log10ages, w.grid.metallicity, lam, ga, gu, filt, kappa=O.dust_kappa(lam),
+                         igm=(I.INOUE14_LAF, I.INOUE14_DLA), **kw)
+    err = assert_flux_close(got, want)
+    print(f"28 filters, {model}: max rel err {err:.3e}")
+    # the scaled and the base outputs of one pass agree with each other too
+    sc = eng.photometry(p, scaled=True)
+    np.testing.assert_allclose(sc, got.astype(np.float64) * (10.0 ** p.log_mass / 1e9)[:, None], rtol=1e-14)
+    eng.close()
+
+
 def test_float32_parameter_transport_is_exact_for_float32_draws(engines):
     """parameters cross PCIe as float32 (sb2_params.host_f32) and are widened on the device.  The draws of
     draw_from_hypercube ARE float32 (library.py:1098): sending the raw draws with max_age_from_z gives bit-identical fluxes
