@@ -9,6 +9,8 @@ required to be tiny instead.
 import numpy as np
 import pytest
 
+import synference_b200 as S
+
 from oracle import adapter as A, c_oracle as CO, oracle as O
 from synference_b200 import igm as I
 from synference_b200.configs import make_workload
@@ -335,6 +337,75 @@ def test_twenty_eight_filters_take_the_widest_instantiation(model):
     # the scaled and the base outputs of one pass agree with each other too
     sc = eng.photometry(p, scaled=True)
     np.testing.assert_allclose(sc, got.astype(np.float64) * (10.0 ** p.log_mass / 1e9)[:, None], rtol=1e-14)
+    eng.close()
+
+
+@pytest.mark.parametrize("shape", [(30, 5), (64, 6), (70, 6), (120, 4), (51, 1), (10, 2), (221, 7)])
+@pytest.mark.parametrize("zdist", ["delta", "normal"])
+def test_other_grid_shapes(shape, zdist):
+    """SPS grids come in many shapes (BPASS 51 x 13, FSPS ~100 x 12, BC03 221 x 7, single-metallicity grids): ages beyond the
+    64 that fit the tensor-memory weights take the round-1 kernel, a lone metallicity has no bracket, tiny grids pad K.  Each
+    against the numpy oracle, for delta and Normal metallicity distributions."""
+    from synference_b200.parametric import ZDistArray
+    from synference_b200.synthetic import synthetic_grid
+    n_age, n_z = shape
+    n = 160
+    w = make_workload("cfg2", n)
+    lam = np.asarray(w.grid.lam)
+    ages = np.linspace(6.0, 10.3, n_age)
+    zs = np.geomspace(1e-4, 3e-2, n_z) if n_z > 1 else np.array([0.02])
+    grid = synthetic_grid(w.grid.lam, log10ages=ages, metallicities=zs, seed=5)
+    from synference_b200.parametric import Calzetti2000, PacmanEmission
+    em = PacmanEmission(grid=grid, fesc=0.0, fesc_ly_alpha=1.0, dust_curve=Calzetti2000(), tau_v="tau_v")
+    p = w.params.slice(slice(0, n))
+    rng = np.random.default_rng(8)
+    if zdist == "normal":
+        zd = ZDistArray.normal(rng.uniform(-3.5, -1.7, n), rng.uniform(0.1, 0.5, n), log10=True)
+        p.zd_type, p.zd_value, p.zd_sigma = zd.type_id, zd.value, zd.sigma
+    eng = SynthEngine(grid, em, "emergent", w.filters, max_batch=1 << 12)
+    got = eng.photometry(p, scaled=False)
+    want = O.synthesize(A.galaxies_from_params(p), grid.log10ages, grid.metallicity, lam, grid.spectra,
+                        [(f.lam, f.t) for f in w.filters], key="emergent", fesc=0.0, fesc_ly_alpha=1.0,
+                        dust=dict(curve="Calzetti2000", **em.dust_curve.params), igm=(I.INOUE14_LAF, I.INOUE14_DLA))
+    err = assert_flux_close(got, want)
+    print(f"grid {n_age} x {n_z}, {zdist}: max rel err {err:.3e}")
+    eng.close()
+
+
+@pytest.mark.parametrize("case", ["R100", "R1000", "one_filter", "z_to_19"])
+def test_other_axes_filter_counts_and_redshift_ranges(case):
+    """Coarse and fine constant-R axes (a long axis' per-wavelength tables may not fit beside synth3_kernel's operand ring:
+    the round-1 kernel then runs), a single filter, and redshifts up to the axis' design limit -- against the numpy oracle."""
+    from synference_b200.parametric import Calzetti2000, PacmanEmission
+    from synference_b200.synthetic import NIRCAM_WIDE8, synthetic_filters, synthetic_grid
+    n = 200
+    R = {"R100": 100, "R1000": 1000}.get(case, 300)
+    codes = ["JWST/NIRCam.F277W"] if case == "one_filter" else NIRCAM_WIDE8
+    zmax = 20.0 if case == "z_to_19" else 12.0
+    raw = synthetic_filters(codes)
+    lam_q = S.generate_constant_R(R=R, auto_start_stop=True, filterset=raw, max_redshift=zmax)
+    filters = synthetic_filters(codes, new_lam=lam_q)
+    grid = synthetic_grid(lam_q)
+    lam = np.asarray(grid.lam)
+    em = PacmanEmission(grid=grid, fesc=0.0, fesc_ly_alpha=1.0, dust_curve=Calzetti2000(), tau_v="tau_v")
+    w = make_workload("cfg2", n)
+    p = w.params.slice(slice(0, n))
+    rng = np.random.default_rng(31)
+    p.redshift = rng.uniform(0.01, 19.0 if case == "z_to_19" else 11.5, n)
+    # (the SFH rows were built for cfg2's redshifts: keep every max_age inside the new redshifts' cosmic age)
+    from synference_b200.cosmology import Planck18
+    age_yr = np.asarray((Planck18.age(p.redshift) - Planck18.age(20.5 if case == "z_to_19" else 20.0)).to("yr").value)
+    p.sfh_rows = p.sfh_rows.copy()
+    scale = age_yr / p.sfh_rows[:, 1]
+    p.sfh_rows[:, 1] = age_yr
+    p.sfh_rows[:, 3] = p.sfh_rows[:, 3] * scale          # peak_age scales with max_age (a `_norm` parameter)
+    eng = SynthEngine(grid, em, "emergent", filters, max_batch=1 << 12)
+    got = eng.photometry(p, scaled=False)
+    want = O.synthesize(A.galaxies_from_params(p), grid.log10ages, grid.metallicity, lam, grid.spectra,
+                        [(f.lam, f.t) for f in filters], key="emergent", fesc=0.0, fesc_ly_alpha=1.0,
+                        dust=dict(curve="Calzetti2000", **em.dust_curve.params), igm=(I.INOUE14_LAF, I.INOUE14_DLA))
+    err = assert_flux_close(got, want)
+    print(f"{case}: n_lam {lam.size}, {len(codes)} filter(s): max rel err {err:.3e}")
     eng.close()
 
 
