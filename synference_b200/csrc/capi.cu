@@ -575,8 +575,13 @@ int s3_cols(const sb2_model* m) { return m->d.n_comp == 1 ? 96 : 128; }   // acc
 // Dense K (weights over every (age, Z) bin): the hi*hi terms of a chunk go to kDenseSplit accumulators of 128 columns by K
 // range, which divides the truncation error of the tensor core's FP32 accumulation by as much (synth_kernel, kSplit).
 constexpr int kDenseSplit = 3;
+// Bracket-grouped batches of grids with many ages (BC03: 221) do not fit synth3_kernel's tensor-memory weights and have a
+// long K too (2 x 224 columns): they take the same split -- 7.6e-6 -> see DESIGN 6.1 -- with the bracket's weight maps.
+constexpr int kDeltaSplitMinK8 = 24;      // K >= 192 columns: below that one accumulator is already at ~3e-6
 bool use_split(const sb2_model* m, bool delta) {
-  return !delta && !m->sw.no_split && (m->d.k_pad / 8 + 3) / 4 >= kDenseSplit;   // every accumulator gets a k-block
+  if (m->sw.no_split) return false;
+  if (delta) return m->wd_stride / 8 >= kDeltaSplitMinK8;
+  return (m->d.k_pad / 8 + 3) / 4 >= kDenseSplit;   // every accumulator gets a k-block
 }
 
 
@@ -592,7 +597,8 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
       a2.spec_smem = 1;
     }
     CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    k<<<grid, sb2::kSynthThreads, bytes, st>>>(m->tm_w_hi, m->tm_w_lo, m->tm_g2_hi, m->tm_g2_lo, a2);
+    k<<<grid, sb2::kSynthThreads, bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo, m->tm_g2_hi,
+                                               m->tm_g2_lo, a2);
     STAGE_CHECK("synth_kernel (split accumulators)", st);
     return SB2_OK;
   }
@@ -944,7 +950,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.tile_k0 = m->tile_k0;
   a.k8_total = (delta ? m->wd_stride : d.k_pad) / 8;
   a.dbg = m->sw.dbg;
-  a.two_pass = (!delta && !m->sw.one_pass) ? 1 : 0;
+  a.two_pass = ((!delta || (!use_s3(m, p) && use_split(m, delta))) && !m->sw.one_pass) ? 1 : 0;
   {
     const int lch = sb2::kBN / d.n_comp, lch3 = s3_cols(m) / d.n_comp;
     a.n_chunk = (d.n_lam + lch - 1) / lch;          // the real axis; the tables (kap_len) also cover the pseudo-bins
