@@ -409,6 +409,43 @@ def test_other_axes_filter_counts_and_redshift_ranges(case):
     eng.close()
 
 
+@pytest.mark.parametrize("n_filt", [2, 9, 24, 25, 32])
+def test_filter_counts_at_the_instantiation_boundaries(n_filt):
+    """The kernels are instantiated for up to 8, 24 and 32 filters: counts on both sides of every boundary (and the largest),
+    built from cfg1's eight NIRCam bands plus copies shifted in wavelength; fluxes and the mass-scaled output vs the oracle."""
+    from synference_b200.parametric import Filter, FilterCollection
+    n = 300
+    w = make_workload("cfg1", n)
+    lam = np.asarray(w.grid.lam)
+    base = list(w.filters)
+    fl = []
+    for k in range(n_filt):
+        # (two filters: two RED bands -- with only the two bluest, a dropout's fluxes are all within float32's last decades,
+        #  where the relative check of tests/helpers.py has no brighter band to measure them against)
+        f = base[(4, 7)[k]] if n_filt == 2 else base[k % 8]
+        shift = 23 * (k // 8)
+        t = np.zeros_like(f.t)                       # copies sit BLUEWARD of their original (the axis ends at the reddest band)
+        t[:len(f.t) - shift] = f.t[shift:]
+        fl.append(Filter(f"TEST/{f.filter_code}.{k // 8}", lam, t * (1.0 - 0.1 * (k // 8))))
+    fc = FilterCollection(filters=fl)
+    fc.lam = w.filters.lam
+    p = w.params.slice(slice(0, n))
+    eng = SynthEngine(w.grid, w.emission_model, w.emission_key, fc, max_batch=1 << 12)
+    assert eng.n_filt == n_filt
+    got = eng.photometry(p, scaled=False)
+    em = w.emission_model
+    want = O.synthesize(A.galaxies_from_params(p), w.grid.log10ages, w.grid.metallicity, lam, w.grid.spectra,
+                        [(f.lam, f.t) for f in fl], key=w.emission_key, fesc=float(em.fesc), fesc_ly_alpha=float(em.fesc_ly_alpha),
+                        dust=None, igm=(I.INOUE14_LAF, I.INOUE14_DLA))
+    assert_flux_close(got, want)
+    sc = eng.photometry(p, scaled=True)
+    np.testing.assert_allclose(sc, got.astype(np.float64) * (10.0 ** p.log_mass / 1e9)[:, None], rtol=1e-14)
+    mat = np.full((n_filt, n), -1.0)
+    eng.photometry(p, scaled=False, library_out=(mat, 0))
+    assert np.array_equal(mat, sc.T)
+    eng.close()
+
+
 def test_float32_parameter_transport_is_exact_for_float32_draws(engines):
     """parameters cross PCIe as float32 (sb2_params.host_f32) and are widened on the device.  The draws of
     draw_from_hypercube ARE float32 (library.py:1098): sending the raw draws with max_age_from_z gives bit-identical fluxes
