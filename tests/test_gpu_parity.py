@@ -409,6 +409,38 @@ def test_other_axes_filter_counts_and_redshift_ranges(case):
     eng.close()
 
 
+@pytest.mark.parametrize("workload", ["cfg1", "cfg2"])
+def test_device_outputs_are_written_inside_their_buffers_only(workload, engines):
+    """The contraction's epilogue scatters every galaxy's fluxes to the caller's row itself (fused output): with the output
+    tensors embedded in larger buffers of sentinels, ragged batch sizes leave every sentinel alone and write every row --
+    float32 base fluxes, float64 scaled fluxes, and the transposed (library) layout."""
+    import torch
+    w, eng = engines(workload, 1300)
+    nf = eng.n_filt
+    for n in (1, 127, 129, 1000, 1300):
+        p = w.params.slice(slice(0, n))
+        dp = eng.to_device(p)
+        pad = 3 * nf + 1
+        buf32 = torch.full((n * nf + 2 * pad,), -7.0, dtype=torch.float32, device="cuda")
+        buf64 = torch.full((n * nf + 2 * pad,), -7.0, dtype=torch.float64, device="cuda")
+        base = buf32[pad:pad + n * nf].view(n, nf)
+        scaled = buf64[pad:pad + n * nf].view(n, nf)
+        eng.photometry_device(dp, flux_base=base, flux_scaled=scaled)
+        torch.cuda.synchronize()
+        for buf in (buf32, buf64):
+            assert bool((buf[:pad] == -7.0).all()) and bool((buf[pad + n * nf:] == -7.0).all()), (workload, n)
+        ref = eng.photometry(p, scaled=False)
+        assert np.array_equal(base.cpu().numpy(), ref)
+        assert not bool((scaled == -7.0).any())
+        np.testing.assert_array_equal(scaled.cpu().numpy(), eng.photometry(p, scaled=True))
+    # transposed: columns [5, 5 + n) of an (n_filt, n + 9) matrix
+    n = 777
+    p = w.params.slice(slice(0, n))
+    mat = np.full((nf, n + 9), -7.0)
+    eng.photometry(p, scaled=False, library_out=(mat, 5))
+    assert np.all(mat[:, :5] == -7.0) and np.all(mat[:, 5 + n:] == -7.0) and not np.any(mat[:, 5:5 + n] == -7.0)
+
+
 @pytest.mark.parametrize("n_filt", [2, 9, 24, 25, 32])
 def test_filter_counts_at_the_instantiation_boundaries(n_filt):
     """The kernels are instantiated for up to 8, 24 and 32 filters: counts on both sides of every boundary (and the largest),
