@@ -44,7 +44,9 @@ def create_feature_array_from_raw_photometry(
         photometry_to_remove: Optional[list] = None, drop_dropouts: bool = False,
         drop_dropout_fraction: float = 1.0, parameter_array=None, normals=None, seed: int = 0,
         epoch: int = 0, device: int = 0, return_torch: bool = False, empirical_noise_models=None,
-        depth_indices=None, asinh_softening_parameters=None, normalization_unit: str = "AB"):
+        depth_indices=None, asinh_softening_parameters=None, normalization_unit: str = "AB",
+        simulate_missing_fluxes: bool = False, missing_flux_value: float = 99.0, missing_flux_fraction: float = 0.0,
+        missing_flux_options: Optional[list] = None, include_flags_in_feature_array: bool = False):
     """``(N_filters, N_gal)`` library photometry -> ``(feature_array (N_rows, N_feat) float32,
     feature_names, parameter_array (N_rows, N_par) | None)``.
 
@@ -66,6 +68,11 @@ def create_feature_array_from_raw_photometry(
     holds the filter's UNSCATTERED library flux in ``normalization_unit`` (``"AB"``, a flux unit, or ``"log10 <unit>"``;
     ``sbi_runner.py:1783-1831``), named ``norm_<filter>_<normalization_unit>`` (``:2024-2027``).  (The reference can only do
     this for at most one replica per galaxy -- its assignment of the column fails otherwise; here the value is repeated.)
+    ``simulate_missing_fluxes`` (``sbi_runner.py:1976-2012``): every row gets a mask over its filters -- one of
+    ``missing_flux_options`` (0/1 lists, 1 = missing) picked uniformly, or each band missing with probability
+    ``missing_flux_fraction`` -- masked bands (and their errors) become ``missing_flux_value``, and
+    ``include_flags_in_feature_array`` appends the mask as ``flag_<filter>`` columns after the errors.  The reference draws
+    the masks from numpy's global stream; here they come from a device generator keyed by ``(seed, epoch)``.
     """
     import torch
     asinh = normed_flux_units == "asinh"
@@ -228,13 +235,37 @@ def create_feature_array_from_raw_photometry(
         if nu_log:
             norm_col = torch.log10(norm_col)
             norm_col = torch.where(torch.isinf(norm_col), torch.zeros_like(norm_col), norm_col)
-        cols = [mags] + ([errs] if include_errors_in_feature_array and scatter_fluxes else []) + [norm_col[:, None].to(mags.dtype)]
+        last = [norm_col[:, None].to(mags.dtype)]
         tail = [f"norm_{normalize_method}_{normalization_unit}"]
     else:
-        cols = [mags] + ([errs] if include_errors_in_feature_array and scatter_fluxes else [])
-        tail = []
-    if include_errors_in_feature_array and scatter_fluxes:
-        feature_names = feature_names + [f"unc_{n}" for n in feature_names]
+        last, tail = [], []
+    with_errs = bool(include_errors_in_feature_array and scatter_fluxes)
+    band_names = list(feature_names)
+    flags = []
+    if simulate_missing_fluxes:
+        nb_, n_rows_ = mags.shape[1], mags.shape[0]
+        gen = torch.Generator(device=dev)
+        gen.manual_seed((int(seed) * 1_000_003 + int(epoch) * 7919 + 0x6D697373) & 0x7FFFFFFFFFFFFFFF)
+        if missing_flux_options is not None:
+            opts = torch.as_tensor(np.asarray(missing_flux_options, dtype=np.float32), device=dev)
+            if opts.ndim != 2 or opts.shape[1] != nb_:
+                raise ValueError(f"missing_flux_options: every mask needs {nb_} entries (one per filter in the rows)")
+            mask = opts[torch.randint(0, opts.shape[0], (n_rows_,), generator=gen, device=dev)]
+        else:
+            mask = (torch.rand((n_rows_, nb_), generator=gen, device=dev) < float(missing_flux_fraction)).to(torch.float32)
+        miss = mask == 1.0
+        mags = torch.where(miss, torch.full_like(mags, float(missing_flux_value)), mags)
+        if with_errs:
+            errs = torch.where(miss, torch.full_like(errs, float(missing_flux_value)), errs)
+        if include_flags_in_feature_array:
+            flags = [mask.to(mags.dtype)]
+    elif include_flags_in_feature_array:
+        flags = [torch.zeros_like(mags)]
+    cols = [mags] + ([errs] if with_errs else []) + flags + last
+    if with_errs:
+        feature_names = feature_names + [f"unc_{n}" for n in band_names]
+    if flags:
+        feature_names = feature_names + [f"flag_{n}" for n in band_names]
     feature_names = feature_names + tail
     out = torch.cat(cols, 1) if len(cols) > 1 else cols[0]
     keep_rows = torch.ones(out.shape[0], dtype=torch.bool, device=dev)

@@ -132,6 +132,38 @@ def test_feature_rows_in_flux_units_and_their_scalings():
             create_feature_array_from_raw_photometry(grid, names, normed_flux_units=bad)
 
 
+def test_missing_flux_simulation_and_flags():
+    """simulate_missing_fluxes (sbi_runner.py:1976-2012): masked bands and their errors take missing_flux_value, the mask is
+    appended as flag columns after the errors; masks come from the listed options or a per-band probability, keyed by
+    (seed, epoch)."""
+    rng = np.random.default_rng(23)
+    n_gal, names = 4000, ["a", "b", "c"]
+    grid = np.abs(rng.normal(300, 40, (3, n_gal))) + 50.0
+    depths = np.full(3, 29.0)
+    kw = dict(scatter_fluxes=2, depths=depths, include_errors_in_feature_array=True, seed=5, epoch=1,
+              simulate_missing_fluxes=True, include_flags_in_feature_array=True)
+    clean, cn, _ = create_feature_array_from_raw_photometry(grid, names, scatter_fluxes=2, depths=depths,
+                                                            include_errors_in_feature_array=True, seed=5, epoch=1)
+    f, fn, _ = create_feature_array_from_raw_photometry(grid, names, missing_flux_fraction=0.25, **kw)
+    assert fn == names + [f"unc_{n}" for n in names] + [f"flag_{n}" for n in names] and f.shape == (2 * n_gal, 9)
+    flag = f[:, 6:] == 1.0
+    assert set(np.unique(f[:, 6:])) == {0.0, 1.0} and abs(flag.mean() - 0.25) < 0.01
+    assert np.all(f[:, :3][flag] == 99.0) and np.all(f[:, 3:6][flag] == 99.0)
+    assert np.array_equal(f[:, :3][~flag], clean[:, :3][~flag]) and np.array_equal(f[:, 3:6][~flag], clean[:, 3:6][~flag])
+    f2, _, _ = create_feature_array_from_raw_photometry(grid, names, missing_flux_fraction=0.25, **kw)
+    f3, _, _ = create_feature_array_from_raw_photometry(grid, names, missing_flux_fraction=0.25, **dict(kw, epoch=2))
+    assert np.array_equal(f, f2) and not np.array_equal(f[:, 6:], f3[:, 6:])
+    # listed options: each row carries exactly one of them, in about equal shares
+    opts = [[0, 0, 1], [1, 0, 0], [0, 0, 0]]
+    f, _, _ = create_feature_array_from_raw_photometry(grid, names, missing_flux_options=opts, missing_flux_value=-1.0, **kw)
+    m = f[:, 6:]
+    share = [np.mean(np.all(m == np.array(o, dtype=np.float32), 1)) for o in opts]
+    assert abs(sum(share) - 1.0) < 1e-12 and all(abs(x - 1 / 3) < 0.03 for x in share)
+    assert np.all(f[:, :3][m == 1.0] == -1.0)
+    with pytest.raises(ValueError):
+        create_feature_array_from_raw_photometry(grid, names, missing_flux_options=[[0, 1]], **kw)
+
+
 def test_resampled_features_per_epoch():
     from synference_b200.features import ResampledFeatures
     rng = np.random.default_rng(2)
