@@ -1332,8 +1332,14 @@ class GalaxySimulator:
         filters = list(self.instrument.filters.filters)
         if photometry_to_remove:
             filters = [f for f in filters if f.filter_code not in set(photometry_to_remove)]
-        if photometry_to_add:
-            raise NotImplementedError("adding filters needs curves on the shared wavelength axis")
+        have = {f.filter_code for f in filters}
+        new_codes = [c for c in (photometry_to_add or []) if c not in have]
+        if new_codes:
+            # the reference re-fetches every curve by code (FilterCollection(filter_codes=...)); here the added curves are
+            # looked up the same way and resampled onto the axis the others already share
+            added = FilterCollection(filter_codes=new_codes, new_lam=self.instrument.filters.lam
+                                     if self.instrument.filters.lam is not None else self.grid.lam)
+            filters = filters + list(added.filters)
         fc = FilterCollection(filters=filters)
         fc.lam = self.instrument.filters.lam
         self.instrument = Instrument(self.instrument.label, filters=fc)

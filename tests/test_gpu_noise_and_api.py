@@ -230,6 +230,29 @@ def _small_basis(n, tmp):
     return basis, d, grid, inst, em
 
 
+def test_simulator_update_photo_filters_removes_and_adds(tmp_path):
+    """GalaxySimulator.update_photo_filters (library.py:5180-5216): removed codes leave, added codes are looked up and put on
+    the shared axis; the fluxes of the bands that stay do not change and the new band matches a simulator built with it."""
+    basis, d, grid, inst, em = _small_basis(8, tmp_path)
+    kw = dict(sfh_model=S.SFH.LogNormal, zdist_model=S.ZDist.DeltaConstant, grid=grid, emission_model=em,
+              emission_model_key="emergent", out_flux_unit="nJy", ignore_scatter=True,
+              param_units={"peak_age": S.Myr, "max_age": S.Myr},
+              param_order=["redshift", "log_mass", "tau", "peak_age", "max_age", "log10metallicity", "tau_v"])
+    vec = np.array([3.0, 9.5, 0.5, 100.0, 300.0, -1.0, 0.2])
+    sim = S.GalaxySimulator(instrument=inst, **kw)
+    before = sim(vec)
+    codes = list(inst.filters.filter_codes)
+    sim.update_photo_filters(photometry_to_remove=[codes[1], codes[5]], photometry_to_add=["JWST/NIRCam.F150W", codes[0]])
+    now = sim.instrument.filters.filter_codes
+    assert now == [c for c in codes if c not in (codes[1], codes[5])] + ["JWST/NIRCam.F150W"]
+    after = sim(vec)
+    keep = [i for i, c in enumerate(codes) if c not in (codes[1], codes[5])]
+    assert after.shape == (6,) and np.array_equal(after[:5], before[keep])
+    fc = S.FilterCollection(filter_codes=["JWST/NIRCam.F150W"], new_lam=grid.lam)
+    alone = S.GalaxySimulator(instrument=S.Instrument("JWST", filters=fc), **kw)(vec)
+    np.testing.assert_allclose(after[5], alone[0], rtol=1e-6)
+
+
 def test_create_mock_library_end_to_end(tmp_path):
     """The reference's test_full_single_cat_creation (tests/test_library.py:267-296) plus a numeric check."""
     n = 100
