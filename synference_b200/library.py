@@ -1485,8 +1485,13 @@ class GalaxySimulator:
         if "photo_lnu" in self.output_type:
             # rest-frame luminosities through the filters (library.py:5756-5761): no redshift, no IGM, no distance
             outputs["photo_lnu"] = self._get_engine(rest_frame=True).photometry(p, scaled=True)    # erg / s / Hz
+        if "lnu" in self.output_type:
+            # rest-frame luminosity spectrum on the grid's axis (library.py:5752-5754): the rest-frame engine's spectra
+            er = self._get_engine(rest_frame=True)
+            outputs["lnu"] = er.spectra(p).astype(np.float64) * (10.0 ** p.log_mass / er.base_mass)[:, None]    # erg / s / Hz
+            outputs["lnu_wav"] = np.asarray(self.grid.lam)
         for t in self.output_type:
-            if t not in ("photo_fnu", "fnu", "sfh", "photo_lnu"):
+            if t not in ("photo_fnu", "fnu", "sfh", "photo_lnu", "lnu"):
                 raise NotImplementedError(f"output_type '{t}' is not available in the batched path")
         conv = {"nJy": 1.0, "uJy": 1e-3, "mJy": 1e-6, "Jy": 1e-9}
         for k in ("photo_fnu", "fnu"):

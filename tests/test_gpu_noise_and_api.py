@@ -732,6 +732,14 @@ def test_simulator_sfh_and_rest_frame_photometry_outputs(tmp_path):
         lnu = (np.tensordot(w, ga, axes=([0, 1], [0, 1])) * np.exp(-g["tau_v"] * kap) + np.tensordot(w, gu, axes=([0, 1], [0, 1]))) * 10.0 ** vec[i, 1]
         want = np.array([O.apply_filter(lnu, lam, f.lam, f.t) for f in inst.filters])
         np.testing.assert_allclose(got[i], want, rtol=1e-5)
+    # --- lnu (library.py:5752-5754): the rest-frame luminosity spectrum itself, on the grid's axis
+    spec = S.GalaxySimulator(output_type="lnu", **kw)(vec)
+    assert spec.shape == (2, lam.size)
+    for i, g in enumerate(gals):
+        w = O.weights_for(g, grid.log10ages, grid.metallicity)
+        lnu = (np.tensordot(w, ga, axes=([0, 1], [0, 1])) * np.exp(-g["tau_v"] * kap) + np.tensordot(w, gu, axes=([0, 1], [0, 1]))) * 10.0 ** vec[i, 1]
+        big = lnu > 1e-20 * lnu.max()
+        np.testing.assert_allclose(spec[i][big], lnu[big], rtol=1e-5)
 
 
 def test_multi_base_supplementary_parameters(tmp_path):
