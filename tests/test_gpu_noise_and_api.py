@@ -761,3 +761,50 @@ def test_multi_base_supplementary_parameters(tmp_path):
     np.testing.assert_allclose(supp[1], supp[3], rtol=1e-12)                          # an age does not scale
     lib = S.load_library_from_hdf5(cb.library_path)
     assert list(lib["supplementary_parameter_names"]) == names
+
+
+def test_readme_quickstart_as_written(tmp_path):
+    """The reference's quick start (README.md:78-134) with the import line swapped: a prior dictionary with a unit on
+    `peak_age`, filters kept on their OWN tables, the SPS grid's native (non-constant-R) axis, one ZDist object
+    per galaxy, `generate_sfh_basis` with absolute peak ages, `GalaxyBasis(..., log_stellar_masses=)`,
+    `create_mock_library(out_name, emission_model_key='intrinsic')` -- then the library against the oracle."""
+    from synference_b200 import (FilterCollection, GalaxyBasis, Instrument, IntrinsicEmission, Myr, SFH, ZDist, draw_from_hypercube,
+                                 generate_sfh_basis)
+    from synference_b200.synthetic import synthetic_grid
+    N = 300
+    parameter_prior_ranges = {
+        "log_stellar_mass": (8.0, 12.0),
+        "redshift": (0.0, 10.0),
+        "log_zmet": (-4.0, -1.4),
+        "peak_age": (0.0, 100) * Myr,       # (README: 1000 Myr, older than the universe at z > 5 -> NaN SFHs there, which
+        "tau": (0.2, 2),                    #  _validate_library rejects, here as in the reference)
+    }
+    # (README.md:95 passes unlog_keys=['log_stellar_mass'], which RENAMES the key to 'stellar_mass' (library.py:1098-1103) and
+    #  makes the README's own `parameter_samples["log_stellar_mass"]` a KeyError -- in the reference too; the draw is kept in log)
+    unlogged = draw_from_hypercube(parameter_prior_ranges, N=16, unlog_keys=["log_stellar_mass"], rng=3)
+    assert "stellar_mass" in unlogged and "log_stellar_mass" not in unlogged and np.all(np.asarray(unlogged["stellar_mass"]) >= 1e8)
+    parameter_samples = draw_from_hypercube(parameter_prior_ranges, N=N, rng=3)
+    filter_names = [f"JWST/NIRCam.{f}" for f in ["F090W", "F115W", "F150W", "F200W", "F277W", "F356W", "F444W"]]
+    instrument = Instrument("JWST", filters=FilterCollection(filter_codes=filter_names))
+    # (the BPASS file of the README is not available offline: a grid of its shape on a native-looking, non-constant-R axis)
+    lam = np.concatenate([np.arange(200.0, 3000.0, 2.0), np.arange(3000.0, 12000.0, 10.0), 12000.0 * 1.003 ** np.arange(1, 520)])
+    grid = synthetic_grid(lam)
+    emission_model = IntrinsicEmission(grid=grid)
+    Z_dists = [ZDist.DeltaConstant(log10metallicity=log_z) for log_z in parameter_samples["log_zmet"]]
+    sfh_models, _ = generate_sfh_basis(sfh_type=SFH.LogNormal, sfh_param_names=["tau", "peak_age"],
+                                       sfh_param_arrays=(parameter_samples["tau"], parameter_samples["peak_age"]),
+                                       redshifts=parameter_samples["redshift"])
+    basis = GalaxyBasis(model_name="sps_test", redshifts=parameter_samples["redshift"],
+                        log_stellar_masses=parameter_samples["log_stellar_mass"], grid=grid, emission_model=emission_model,
+                        sfhs=sfh_models, instrument=instrument, metal_dists=Z_dists)
+    basis.create_mock_library(out_name="library_test", emission_model_key="intrinsic", overwrite=True, out_dir=str(tmp_path))
+    lib = S.load_library_from_hdf5(os.path.join(str(tmp_path), "library_test.hdf5"))
+    assert lib["photometry"].shape == (7, N) and lib["filter_codes"] == filter_names
+    p = basis.params
+    want = O.synthesize(A.galaxies_from_params(p), grid.log10ages, grid.metallicity, lam, grid.spectra,
+                        [(f.lam, f.t) for f in instrument.filters], key="intrinsic", fesc=0.0, fesc_ly_alpha=1.0, dust=None,
+                        igm=(I.INOUE14_LAF, I.INOUE14_DLA))
+    logm = np.asarray(lib["parameters"][lib["parameter_names"].index("log_mass")], dtype=float)
+    usable = np.isfinite(lib["photometry"]).all(0)
+    assert usable.mean() > 0.95
+    assert_flux_close(lib["photometry"].T[usable], O.scale_to_mass(want, logm)[usable])
