@@ -154,9 +154,46 @@ __global__ void group_layout_kernel(const int* __restrict__ counts, int n_groups
   }
 }
 
+// synth3_kernel's bfloat16 operand: per row and group of 8 k-values the 32 bytes [bf16(g_hi[0..7]) | bf16(g_lo[0..7])], i.e. the
+// K = 16 slice that meets the weights' [w_lo | w_hi] in one kind::f16 MMA (same bytes per row as the TF32 tiles)
+__global__ void cross_pack_kernel(const float* __restrict__ hi, const float* __restrict__ lo, uint32_t* __restrict__ x, size_t n_groups) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += (size_t)gridDim.x * blockDim.x) {
+    const float* h = hi + 8 * i;
+    const float* l = lo + 8 * i;
+    uint32_t* o = x + 8 * i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[j] = sb2::pack_bf16x2(h[2 * j], h[2 * j + 1]);
+      o[4 + j] = sb2::pack_bf16x2(l[2 * j], l[2 * j + 1]);
+    }
+  }
+}
+
 // float32 parameters staged by the host entry (sb2_params.host_f32) -> the float64 arrays the kernels read
-__global__ void widen_kernel(const float* __restrict__ src, double* __restrict__ dst, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+// (the float32 staging area mirrors the float64 one element for element, so a segment is one offset into both; all of a
+//  slice's arrays go in ONE launch: blockIdx.y picks the array)
+struct WidenSegs {
+  long long off[12];
+  long long cnt[12];
+};
+__global__ void widen_kernel(const float* __restrict__ src, double* __restrict__ dst, const __grid_constant__ WidenSegs sg) {
+  const long long off = sg.off[blockIdx.y], n = sg.cnt[blockIdx.y];
+  const float* __restrict__ s = src + off;
+  double* __restrict__ d = dst + off;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((off | (long long)(reinterpret_cast<uintptr_t>(src) >> 2)) & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) >> 3) & 1) == 0) {
+    // four elements per thread: one 16-byte load, two 16-byte stores
+    const long long n4 = n >> 2;
+    for (; i < n4; i += stride) {
+      const float4 v = reinterpret_cast<const float4*>(s)[i];
+      reinterpret_cast<double2*>(d)[2 * i] = make_double2((double)v.x, (double)v.y);
+      reinterpret_cast<double2*>(d)[2 * i + 1] = make_double2((double)v.z, (double)v.w);
+    }
+    for (long long j = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) d[j] = (double)s[j];
+    return;
+  }
+  for (; i < n; i += stride) d[i] = (double)s[i];
 }
 
 __global__ void group_scatter_kernel(const unsigned* __restrict__ keys_sorted, const int* __restrict__ perm_sorted,
@@ -174,14 +211,14 @@ __global__ void group_scatter_kernel(const unsigned* __restrict__ keys_sorted, c
 // Experiment / fallback switches (environment), read ONCE when a model is created -- never on the per-call path.
 struct Switches {
   bool n256 = false, cta_pair = false, libm = false, weights_v1 = false, one_pass = false, trace = false, no_synth3 = false, no_split = false;
-  bool no_fuse = false;
+  bool no_fuse = false, tf32x3 = false;
   int dbg = 0;
   long long host_slices = 0;   // 0: automatic
   static bool on(const char* k) { const char* e = std::getenv(k); return e && e[0] && e[0] != '0'; }
   void read() {
     n256 = on("SB2_N256"); cta_pair = on("SB2_CTA_PAIR"); libm = on("SB2_LIBM"); weights_v1 = on("SB2_WEIGHTS_V1");
     one_pass = on("SB2_ONE_PASS"); trace = on("SB2_TRACE"); no_synth3 = on("SB2_NO_SYNTH3"); no_split = on("SB2_NO_SPLIT");
-    no_fuse = on("SB2_NO_FUSE");
+    no_fuse = on("SB2_NO_FUSE"); tf32x3 = on("SB2_TF32X3");
     if (const char* e = std::getenv("SB2_DBG")) dbg = std::atoi(e);
     if (const char* e = std::getenv("SB2_HOST_SLICES")) host_slices = std::atoll(e);
   }
@@ -203,6 +240,7 @@ struct sb2_model {
   // model tables
   double *ages = nullptr, *edges = nullptr, *zmet = nullptr, *log10zmet = nullptr;
   float *gt_hi = nullptr, *gt_lo = nullptr, *kappa = nullptr, *filt_uv = nullptr;
+  float* gt_x = nullptr;   // synth3_kernel's bfloat16 operand of the split product's small terms (cross_pack_kernel)
   float *dust_d0 = nullptr, *dust_l2 = nullptr, *g_slope = nullptr, *g_ampl = nullptr;   // per-galaxy dust shape (optional)
   double* lya_line = nullptr;   // per-galaxy Lyman-alpha escape (optional)
   float* g_lya = nullptr;
@@ -246,6 +284,7 @@ struct sb2_model {
   cudaEvent_t ev_slot[2] = {nullptr, nullptr};   // slot's results are on the host
   bool slot_busy[2] = {false, false};
   CUtensorMap tm_w_hi, tm_w_lo, tm_g_hi, tm_g_lo;
+  CUtensorMap tm_g2_x, tm_g96_x;
   size_t smem_bytes = 0;
   // host entry point: copy-in / compute / copy-out streams and per-slice events (slices are pipelined)
   cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
@@ -285,7 +324,7 @@ int sb2_device_count(void) {
 int sb2_model_destroy(sb2_model* m) {
   if (!m) return SB2_OK;
   cudaSetDevice(m->device);
-  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->kappa, m->dust_d0, m->dust_l2, m->g_slope, m->g_ampl, m->lya_line, m->g_lya, m->kappa_birth, m->g_taub, m->dust_wnu, m->dust_g, m->dust_duv, m->e_part, m->filt_uv, m->filt_lo,
+  void* ptrs[] = {m->ages, m->edges, m->zmet, m->log10zmet, m->gt_hi, m->gt_lo, m->gt_x, m->kappa, m->dust_d0, m->dust_l2, m->g_slope, m->g_ampl, m->lya_line, m->g_lya, m->kappa_birth, m->g_taub, m->dust_wnu, m->dust_g, m->dust_duv, m->e_part, m->filt_uv, m->filt_lo,
                   m->filt_hi, m->bin_pow, m->thr, m->pre, m->nline, m->lc_on, m->dc, m->ddc, m->age, m->dage, m->fm_log, m->fm_exp, m->fm_tail,
                   m->w_hi, m->w_lo, m->igm, m->g_m, m->g_orig, m->perm, m->idx, m->g_beta, m->g_gamma, m->g_taut, m->g_scale,
                   m->g_ca, m->g_cb, m->keys, m->keys_sorted, m->perm_pad, m->grp, m->tile_k0, m->tile_range, m->part, m->g_mscale, m->zpow, m->g_trunc, m->cub_tmp, m->stage_params[0],
@@ -360,6 +399,9 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
   const size_t g_elems = (size_t)d->n_chunk * sb2::kBN * d->k_pad;
   UP(gt_hi, d->gt_hi, g_elems);
   UP(gt_lo, d->gt_lo, g_elems);
+  if (cudaMalloc(&m->gt_x, g_elems * sizeof(float)) != cudaSuccess) { sb2_model_destroy(m); return fail(SB2_ERR_CUDA, "out of device memory (gt_x)"); }
+  cross_pack_kernel<<<1024, 256>>>(m->gt_hi, m->gt_lo, reinterpret_cast<uint32_t*>(m->gt_x), g_elems / 8);
+  if (cudaDeviceSynchronize() != cudaSuccess) { sb2_model_destroy(m); return fail(SB2_ERR_CUDA, "cross_pack_kernel failed"); }
   {
     std::vector<float> kap((size_t)d->n_chunk * lch, 0.f);
     if (d->kappa) std::memcpy(kap.data(), d->kappa, kap.size() * sizeof(float));
@@ -490,6 +532,8 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
       (rc = make_tmap(&m->tm_g160_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 160)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g96_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 96)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g96_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 96)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g2_x, m->gt_x, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN2 / 2)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g96_x, m->gt_x, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 96)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK) {
     sb2_model_destroy(m);
@@ -669,6 +713,7 @@ int launch_synth3_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_
   sb2::Synth3Args x{};
   x.sf = m->sf; x.s0 = m->s0; x.s1 = m->s1; x.n_age = m->d.n_age; x.na_pad = m->d.n_age_pad; x.w_stride = m->wd_stride;
   x.kb_split = a.n_kb / 2;
+  x.cross = m->sw.tf32x3 ? 0 : 1;
   bool spec = false;
   const int kap_len = m->d.n_chunk * (sb2::kBN / C);
   const int feat_tab = a.x_count > 0 ? (FEAT & ~sb2::kFeatAbsorbed) : FEAT;    // pseudo-bins: the energy weights are 1, no table
@@ -684,7 +729,7 @@ int launch_synth3_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_
   x.n_stages = ns;
   CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   const CUtensorMap& th = C == 2 ? m->tm_g2_hi : m->tm_g96_hi;      // boxes of 64 rows (one component of a chunk) | 96 rows
-  const CUtensorMap& tl = C == 2 ? m->tm_g2_lo : m->tm_g96_lo;
+  const CUtensorMap& tl = x.cross ? (C == 2 ? m->tm_g2_x : m->tm_g96_x) : (C == 2 ? m->tm_g2_lo : m->tm_g96_lo);
   k<<<grid, sb2::kS3Threads, bytes, st>>>(th, tl, a2, x);
   STAGE_CHECK("synth3_kernel", st);
   return SB2_OK;
@@ -1173,13 +1218,19 @@ int sb2_synth_photometry_host_submit(sb2_model* m, const sb2_params* p, float* f
     CU_TRY(cudaStreamWaitEvent(m->st_comp, m->ev_in[sl], 0));
     if (trace) cudaEventRecord(tr[1 + sl * 4 + 1], m->st_comp);
     if (p->host_f32) {
+      WidenSegs sg{};
+      int n_seg = 0;
+      long long longest = 0;
       for (int i = 0; i < kNA; ++i) {
         if (!src[i]) continue;
         const size_t w = (i == kNA - 1) ? (size_t)p->sfh_stride : 1;
-        const long long cnt = (long long)((b - a) * w);
-        const float* d32 = m->stage_params32[slot] + (dev[i] - m->stage_params[slot]) + a * w;
-        widen_kernel<<<(unsigned)std::min<long long>((cnt + 255) / 256, 2048), 256, 0, m->st_comp>>>(d32, dev[i] + a * w, cnt);
+        sg.off[n_seg] = (long long)((dev[i] - m->stage_params[slot]) + a * w);
+        sg.cnt[n_seg] = (long long)((b - a) * w);
+        longest = std::max(longest, sg.cnt[n_seg]);
+        ++n_seg;
       }
+      const unsigned bx = (unsigned)std::min<long long>((longest / 4 + 255) / 256 + 1, 1024);
+      widen_kernel<<<dim3(bx, (unsigned)n_seg), 256, 0, m->st_comp>>>(m->stage_params32[slot], m->stage_params[slot], sg);
       STAGE_CHECK("widen_kernel", m->st_comp);
     }
     sb2_params dp = *p;

@@ -359,6 +359,36 @@ __device__ __forceinline__ void umma_tf32_ts_lo_e(uint32_t elected, uint32_t tme
       : "r"(tmem_d), "r"(tmem_a), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "r"(elected), "r"(kDescHiSw128)
       : "memory");
 }
+// kind::f16 instruction descriptor with BF16 operands: D=F32, A=B=BF16, both K-major, dense (K = 16 per instruction).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
+  return (1u << 4)            // c_format  = F32
+         | (1u << 7)          // a_format  = BF16
+         | (1u << 10)         // b_format  = BF16
+         | (0u << 15)         // a_major   = K
+         | (0u << 16)         // b_major   = K
+         | ((n >> 3) << 17)   // n_dim
+         | ((m >> 4) << 24);  // m_dim
+}
+// TS-mode MMA of 16-bit operands: A is M=128 lanes x K=16 elements packed two per 32-bit column (element 2j in the low half
+// of column tmem_a + j), B a K-major SWIZZLE_128B tile of the same 32 bytes per row as a K=8 tile of 32-bit elements.
+__device__ __forceinline__ void umma_bf16_ts_lo_e(uint32_t elected, uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_b_lo,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "r"(elected), "r"(kDescHiSw128)
+      : "memory");
+}
+// two floats -> one 32-bit word of two bfloat16 (round to nearest even): `even` in the low half, `odd` in the high half
+__device__ __forceinline__ uint32_t pack_bf16x2(float even, float odd) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));
+  return r;
+}
 // registers -> TMEM: thread t of the warp writes columns [c, c+N) of lane (base + t)  (mirror of tmem_ld_32x32b_x32)
 __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"

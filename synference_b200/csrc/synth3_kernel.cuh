@@ -34,6 +34,7 @@ struct Synth3Args {
   const double* s0;   // [n_rows] factor of the lower bracketing metallicity
   const double* s1;   // [n_rows] factor of the upper one
   int n_age, na_pad, w_stride, n_stages, kb_split;
+  int cross;          // 1: the two small terms of the split product as ONE bfloat16 MMA (see the header); 0: 3 x TF32
 };
 
 template <int kN>
@@ -167,7 +168,8 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
       // Issuing one M128 x N96 x K8 MMA costs this warp ~10 instructions of descriptor arithmetic, i.e. more than the 48 cycles
       // the tensor pipe needs for it: a single issuer warp was busy 80 % of the time for 64 % tensor-pipe activity (ncu).
       // Two issuers split the chunks by parity -- issuer g feeds epilogue group g -- each with its own commit stream.
-      constexpr uint32_t idesc = make_idesc_tf32(kBM, kN);
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, kN), idesc_x = make_idesc_bf16(kBM, kN);
+      const bool cross = X.cross != 0;
       const uint32_t me = warp == kWMma2 ? 1u : 0u;
       const uint32_t elected = elect_one() ? 1u : 0u;
       const uint32_t s_lo0 = ((smem_u32(smem) & 0x3FFFFu) >> 4) | kDescLoBase;
@@ -220,12 +222,24 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
             const uint32_t b_lo32 = s_lo0 + (uint32_t)stage * (uint32_t)(kStageBytes >> 4);
             const uint32_t a_hi = a_hi0 + (uint32_t)(kb * kBK), a_lo = a_lo0 + (uint32_t)(kb * kBK);
             const int k4n = min(kBK / 8, k8_total - kb * (kBK / 8));
+            if (cross) {
+              // w g = w_hi g_hi + (w_lo g_hi + w_hi g_lo): the bracket is 2^-11 of the product, so bfloat16 factors (2^-9
+              // each) leave 2^-19 of it -- one K16 kind::f16 MMA over [w_lo | w_hi] x [g_hi ; g_lo] at twice the TF32 rate
 #pragma unroll
-            for (int k4 = 0; k4 < kBK / 8; ++k4) {
-              if (k4 < k4n) {
-                umma_tf32_ts_lo_e(elected, d_tmem, a_lo + k4 * 8, b_lo32 + k4 * 2, idesc, (kb | k4) != 0);  // small terms first
-                umma_tf32_ts_lo_e(elected, d_tmem, a_hi + k4 * 8, b_lo32 + (kHalf >> 4) + k4 * 2, idesc, 1u);
-                umma_tf32_ts_lo_e(elected, d_tmem, a_hi + k4 * 8, b_lo32 + k4 * 2, idesc, 1u);
+              for (int k4 = 0; k4 < kBK / 8; ++k4) {
+                if (k4 < k4n) {
+                  umma_bf16_ts_lo_e(elected, d_tmem, a_lo + k4 * 8, b_lo32 + (kHalf >> 4) + k4 * 2, idesc_x, (kb | k4) != 0);  // small terms first
+                  umma_tf32_ts_lo_e(elected, d_tmem, a_hi + k4 * 8, b_lo32 + k4 * 2, idesc, 1u);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k4 = 0; k4 < kBK / 8; ++k4) {
+                if (k4 < k4n) {
+                  umma_tf32_ts_lo_e(elected, d_tmem, a_lo + k4 * 8, b_lo32 + k4 * 2, idesc, (kb | k4) != 0);  // small terms first
+                  umma_tf32_ts_lo_e(elected, d_tmem, a_hi + k4 * 8, b_lo32 + (kHalf >> 4) + k4 * 2, idesc, 1u);
+                  umma_tf32_ts_lo_e(elected, d_tmem, a_hi + k4 * 8, b_lo32 + k4 * 2, idesc, 1u);
+                }
               }
             }
             umma_commit_e(elected, &empty_bar[stage]);
@@ -281,12 +295,24 @@ synth3_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant
           const int a0 = c - (up ? X.na_pad : 0);
           const double s = up ? s1 : s0;
           uint32_t hi[8], lo[8];
+          float hf[8], lf[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const double w = (a0 + j < X.n_age) ? s_sf[(a0 + j) * 128 + t] * s : 0.0;
-            const float h = to_tf32_rna((float)w);
-            hi[j] = __float_as_uint(h);
-            lo[j] = __float_as_uint(to_tf32_rna((float)(w - (double)h)));
+            hf[j] = to_tf32_rna((float)w);
+            lf[j] = (float)(w - (double)hf[j]);
+            hi[j] = __float_as_uint(hf[j]);
+          }
+          if (X.cross) {
+            // the K16 bfloat16 operand of this group of 8 bins: [w_lo(0..7) | w_hi(0..7)], two elements per column
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              lo[j] = pack_bf16x2(lf[2 * j], lf[2 * j + 1]);
+              lo[4 + j] = pack_bf16x2(hf[2 * j], hf[2 * j + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) lo[j] = __float_as_uint(to_tf32_rna(lf[j]));
           }
           tmem_st_32x32b_x8(w_hi0 + (uint32_t)c, hi);
           tmem_st_32x32b_x8(w_lo0 + (uint32_t)c, lo);

@@ -97,6 +97,24 @@ def test_fluxes_match_c_oracle_at_20000(engines):
     assert_flux_close(got, want)
 
 
+def test_split_product_small_terms_in_bfloat16_and_in_tf32(engines):
+    """synth3_kernel forms w g = w_hi g_hi + (w_lo g_hi + w_hi g_lo); the bracket is 2^-11 of the product, so by default it
+    is ONE bfloat16 MMA (factors good to 2^-9 each: 2^-19 of the product at worst, before the sum over bins averages it);
+    ``SB2_TF32X3=1`` keeps both small terms as TF32 MMAs.  Both against the C oracle at 20 000 galaxies, and against each other."""
+    w, eng = engines("cfg2", 20000)
+    want = oracle_flux(w, c=True)
+    got = eng.photometry(w.params, scaled=False)
+    err = assert_flux_close(got, want)
+    _, eng3 = engines("cfg2", 20000, env={"SB2_TF32X3": "1"})
+    got3 = eng3.photometry(w.params, scaled=False)
+    err3 = assert_flux_close(got3, want)
+    ok = np.abs(want) > 1e-30 * np.abs(want).max(axis=1, keepdims=True)
+    between = np.max(np.abs(got[ok].astype(np.float64) - got3[ok]) / np.abs(want[ok]))
+    print(f"bfloat16 small terms: {err:.3e}; 3 x TF32: {err3:.3e}; between the two: {between:.3e}")
+    assert err <= 3e-6 and between <= 3e-6
+    assert not np.array_equal(got, got3)      # the switch really selects another arithmetic
+
+
 @pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 257])
 def test_ragged_batches(engines, n):
     w, eng = engines("cfg1", 257)
