@@ -284,7 +284,7 @@ struct sb2_model {
   cudaEvent_t ev_slot[2] = {nullptr, nullptr};   // slot's results are on the host
   bool slot_busy[2] = {false, false};
   CUtensorMap tm_w_hi, tm_w_lo, tm_g_hi, tm_g_lo;
-  CUtensorMap tm_g2_x, tm_g96_x;
+  CUtensorMap tm_g2_x, tm_g96_x, tm_g160_x, tm_g_x;
   size_t smem_bytes = 0;
   // host entry point: copy-in / compute / copy-out streams and per-slice events (slices are pipelined)
   cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
@@ -534,6 +534,8 @@ int sb2_model_create(const sb2_model_desc* d, int device, sb2_model** out) {
       (rc = make_tmap(&m->tm_g96_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 96)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g2_x, m->gt_x, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN2 / 2)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g96_x, m->gt_x, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 96)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g160_x, m->gt_x, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, 160)) != SB2_OK ||
+      (rc = make_tmap(&m->tm_g_x, m->gt_x, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_hi, m->gt_hi, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK ||
       (rc = make_tmap(&m->tm_g_lo, m->gt_lo, (uint64_t)d->n_chunk * sb2::kBN, d->k_pad, sb2::kBN)) != SB2_OK) {
     sb2_model_destroy(m);
@@ -622,6 +624,9 @@ constexpr int kDenseSplit = 3;
 // Bracket-grouped batches of grids with many ages (BC03: 221) do not fit synth3_kernel's tensor-memory weights and have a
 // long K too (2 x 224 columns): they take the same split -- 7.6e-6 -> see DESIGN 6.1 -- with the bracket's weight maps.
 constexpr int kDeltaSplitMinK8 = 24;      // K >= 192 columns: below that one accumulator is already at ~3e-6
+// The two small terms of the split product as ONE bfloat16 MMA (SynthArgs.cross / PrepModel.cross / Synth3Args.cross):
+// everywhere except the opt-in CTA-pair kernel; SB2_TF32X3=1 restores three TF32 passes.
+bool cross_mode(const sb2_model* m) { return !m->sw.tf32x3 && !m->sw.cta_pair; }
 bool use_split(const sb2_model* m, bool delta) {
   if (m->sw.no_split) return false;
   if (delta) return m->wd_stride / 8 >= kDeltaSplitMinK8;
@@ -642,7 +647,7 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
     }
     CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     k<<<grid, sb2::kSynthThreads, bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo, m->tm_g2_hi,
-                                               m->tm_g2_lo, a2);
+                                               a.cross ? m->tm_g2_x : m->tm_g2_lo, a2);
     STAGE_CHECK("synth_kernel (split accumulators)", st);
     return SB2_OK;
   }
@@ -658,7 +663,7 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
       }
       CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
       k<<<grid, sb2::kSynthThreads, bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo,
-                                                 m->tm_g160_hi, m->tm_g160_lo, a2);
+                                                 m->tm_g160_hi, a.cross ? m->tm_g160_x : m->tm_g160_lo, a2);
       STAGE_CHECK("synth_kernel", st);
       return SB2_OK;
     }
@@ -667,7 +672,7 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
   if (m->smem_bytes > m->smem_optin) return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to this batch's kernel (256-column chunks)");
   CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes));
   k<<<grid, sb2::kSynthThreads, m->smem_bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo,
-                                                     m->tm_g_hi, m->tm_g_lo, a);
+                                                     m->tm_g_hi, a.cross ? m->tm_g_x : m->tm_g_lo, a);
   STAGE_CHECK("synth_kernel", st);
   return SB2_OK;
 }
@@ -713,7 +718,7 @@ int launch_synth3_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_
   sb2::Synth3Args x{};
   x.sf = m->sf; x.s0 = m->s0; x.s1 = m->s1; x.n_age = m->d.n_age; x.na_pad = m->d.n_age_pad; x.w_stride = m->wd_stride;
   x.kb_split = a.n_kb / 2;
-  x.cross = m->sw.tf32x3 ? 0 : 1;
+  x.cross = cross_mode(m) ? 1 : 0;
   bool spec = false;
   const int kap_len = m->d.n_chunk * (sb2::kBN / C);
   const int feat_tab = a.x_count > 0 ? (FEAT & ~sb2::kFeatAbsorbed) : FEAT;    // pseudo-bins: the energy weights are 1, no table
@@ -897,6 +902,7 @@ int run_prep(sb2_model* m, const sb2_params* p, double* w_f64, bool sorted, bool
   sb2::PrepModel M = prep_model(m);
   M.delta = delta ? 1 : 0;
   M.w_stride = delta ? m->wd_stride : m->d.k_pad;
+  M.cross = cross_mode(m) ? 1 : 0;
   sb2::PrepParams P = prep_params(p);
   sb2::PrepOut O{};
   O.w_hi = m->w_hi; O.w_lo = m->w_lo; O.w_f64 = w_f64; O.igm = m->igm; O.g_m = m->g_m; O.g_beta = m->g_beta; O.g_gamma = m->g_gamma;
@@ -995,6 +1001,7 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   a.tile_k0 = m->tile_k0;
   a.k8_total = (delta ? m->wd_stride : d.k_pad) / 8;
   a.dbg = m->sw.dbg;
+  a.cross = cross_mode(m) ? 1 : 0;
   a.two_pass = ((!delta || (!use_s3(m, p) && use_split(m, delta))) && !m->sw.one_pass) ? 1 : 0;
   {
     const int lch = sb2::kBN / d.n_comp, lch3 = s3_cols(m) / d.n_comp;

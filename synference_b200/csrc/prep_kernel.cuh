@@ -20,6 +20,8 @@ struct PrepModel {
   int delta;     // 1: DeltaConstant batch grouped by metallicity bracket -> weights row holds only the
                  //    two bracketing grid metallicities: [sf*(1-f) (na_pad) | sf*f (na_pad)], stride w_stride
   int w_stride;  // floats per weights row (k_pad, or 2*na_pad in delta mode)
+  int cross;     // 1: w_lo holds, per group of 8 columns, the 16 bfloat16 [w_lo(0..7) | w_hi(0..7)] -- the K = 16 operand of
+                 //    the ONE bfloat16 MMA that forms both small terms of the split product (synth_kernel, SynthArgs.cross)
   const double* ages;      // [n_age] yr
   const double* edges;     // [n_age] e_0..e_{n_age-1} (bin a spans [e_a, e_{a+1}], a < n_age-1)
   const double* zmet;      // [n_z]
@@ -146,6 +148,24 @@ struct PrepOut {
   double* g_mscale; // [n_pad]
   unsigned* g_trunc;// [n_pad]  bit f set: filter f not fully covered by the grid at this z
 };
+
+// One column of a weights row: TF32 hi part, and the small part either as TF32 (three-pass product) or packed for the
+// bfloat16 MMA (PrepModel.cross).  `base` = row offset in floats (a multiple of 8), `w` the float64 weight.
+__device__ __forceinline__ void store_weight(const PrepOut& O, int cross, size_t base, int k, double w) {
+  const float hi = to_tf32_rna((float)w);
+  const float lo = (float)(w - (double)hi);
+  O.w_hi[base + k] = hi;
+  if (cross) {
+    unsigned short* x = reinterpret_cast<unsigned short*>(O.w_lo + base + (k & ~7));
+    unsigned short bl, bh;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(bl) : "f"(lo));
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(bh) : "f"(hi));
+    x[k & 7] = bl;
+    x[8 + (k & 7)] = bh;
+  } else {
+    O.w_lo[base + k] = to_tf32_rna(lo);
+  }
+}
 
 __device__ __forceinline__ double hermite_lut(const double* y, const double* dy, double ds, int n, double s) {
   double x = s / ds;
@@ -476,9 +496,7 @@ weights_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __re
       double w = 0.0;
       if (k < M.n_age) w = sf[k] * ((1.0 - zf) * inv_sf);
       else if (k >= M.na_pad && k - M.na_pad < M.n_age) w = sf[k - M.na_pad] * (zf * inv_sf);
-      const float hi = to_tf32_rna((float)w);
-      O.w_hi[t * M.w_stride + k] = hi;
-      O.w_lo[t * M.w_stride + k] = to_tf32_rna((float)(w - (double)hi));
+      store_weight(O, M.cross, (size_t)t * M.w_stride, k, w);
     }
     return;
   }
@@ -492,9 +510,7 @@ weights_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __re
   for (int k = slot; k < M.k_pad; k += kWSlots) {  // column k = iz*na_pad + ia
     const int iz = k / M.na_pad, a = k - iz * M.na_pad;
     const double w = (iz < M.n_z && a < M.n_age) ? sf[a] * (zd[iz] * inv) : 0.0;
-    const float hi = to_tf32_rna((float)w);
-    O.w_hi[t * M.k_pad + k] = hi;
-    O.w_lo[t * M.k_pad + k] = to_tf32_rna((float)(w - (double)hi));
+    store_weight(O, M.cross, (size_t)t * M.k_pad, k, w);
     if (O.w_f64 && iz < M.n_z && a < M.n_age) O.w_f64[g * M.K + iz * M.n_age + a] = w;
   }
 }
@@ -630,9 +646,7 @@ weights2_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __r
       double w = 0.0;
       if (k < M.n_age) w = sf[k] * s0;
       else if (k >= M.na_pad && k - M.na_pad < M.n_age) w = sf[k - M.na_pad] * s1;
-      const float hi = to_tf32_rna((float)w);
-      O.w_hi[t * M.w_stride + k] = hi;
-      O.w_lo[t * M.w_stride + k] = to_tf32_rna((float)(w - (double)hi));
+      store_weight(O, M.cross, (size_t)t * M.w_stride, k, w);
     }
     return;
   }
@@ -646,9 +660,7 @@ weights2_kernel(PrepModel M, FastMath F, PrepParams P, PrepOut O, const int* __r
     for (int a = hl; a < M.na_pad; a += 16) {
       const int k = iz * M.na_pad + a;
       const double w = (a < M.n_age) ? sf[a] * zw : 0.0;
-      const float hi = to_tf32_rna((float)w);
-      O.w_hi[t * M.k_pad + k] = hi;
-      O.w_lo[t * M.k_pad + k] = to_tf32_rna((float)(w - (double)hi));
+      store_weight(O, M.cross, (size_t)t * M.k_pad, k, w);
       if (O.w_f64 && valid && a < M.n_age) O.w_f64[g * M.K + iz * M.n_age + a] = w;
     }
   }

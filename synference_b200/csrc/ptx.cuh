@@ -265,6 +265,18 @@ __device__ __forceinline__ void umma_tf32_e(uint32_t elected, uint32_t tmem_d, u
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
       : "memory");
 }
+// both operands in shared memory, bfloat16 (K = 16 per instruction: the same 32 bytes per row as a K = 8 TF32 slice)
+__device__ __forceinline__ void umma_bf16_e(uint32_t elected, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
 __device__ __forceinline__ void umma_tf32_2sm_e(uint32_t elected, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                                 uint32_t idesc, uint32_t accumulate) {
   asm volatile(

@@ -69,6 +69,8 @@ struct SynthArgs {
   int k8_total;              // K/8 MMA steps actually needed (the last k-block may be partial)
   int dbg;                   // experiments only (SB2_DBG): 1 skip filter sums, 2 skip dust exp, 4 two ring slots
   int two_pass;              // 1: long K, cross terms summed before the hi*hi terms (single-CTA kernel only)
+  int cross;                 // 1: the W_lo / G_lo operands hold the packed bfloat16 pairs [lo | hi] x [hi ; lo] of the small
+                             //    terms, multiplied by ONE kind::f16 MMA per 8 k-values (synth_kernel; PrepModel.cross)
   const int* n_tiles_dev;    // actual tile count (<= n_tiles) when the batch was grouped on device, else nullptr
   const int* tile_k0;        // [n_tiles] first grid column (k) of each tile's weights, nullptr: 0
   const int4* tile_range;    // [n_tiles] {first, last wavelength chunk any filter of the tile needs, first bin & ~31, last bin}; nullptr: all
@@ -648,28 +650,33 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
           const int c = chunk_at(c_first, n_c, rot, j);
           for (int pass = 0; pass < n_pass; ++pass) {
             const bool lo_tiles = (pass == 0);   // single pass: everything in pass 0
+            // bfloat16 small terms (SynthArgs.cross): the packed "lo" tiles carry both factors of the small terms, so the
+            // first of two passes does not fetch the hi tiles at all (4 instead of 6 tile fetches per k-block and chunk)
+            const bool hi_tiles = !(A.cross && n_pass == 2 && pass == 0);
             for (int kb = 0; kb < n_kb; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               const uint32_t st = s_addr + (uint32_t)stage * kStageBytes, fb = full0 + (uint32_t)stage * 8u;
               if (SB2_DBG_BITS(A) & 64) {   // experiment: no operand traffic
                 mbar_expect_tx_e(elected, &full_bar[stage], 0);
               } else {
-              mbar_expect_tx_e(elected, &full_bar[stage], lo_tiles ? kStageBytes : kABytes + kBBytes);
-              tma_load_2d_e(elected, st, &tm_w_hi, fb, kb * kBK, tile * kBM, kEvictNormal);
+              mbar_expect_tx_e(elected, &full_bar[stage], (lo_tiles && hi_tiles) ? kStageBytes : kABytes + kBBytes);
+              if (hi_tiles) tma_load_2d_e(elected, st, &tm_w_hi, fb, kb * kBK, tile * kBM, kEvictNormal);
               if (lo_tiles) tma_load_2d_e(elected, st + kABytes, &tm_w_lo, fb, kb * kBK, tile * kBM, kEvictNormal);
               if constexpr (kSplit > 1) {
                 // rows of the chunk: one component = kLch consecutive wavelengths; with two components the grid's rows come
                 // in blocks of 256 [component 0: 128 wavelengths | component 1: the same 128] (as in synth3_kernel)
                 const int r0 = kComp == 1 ? c * kN : (c * kLch / (kBN / 2)) * kBN + (c * kLch) % (kBN / 2);
                 const int r1 = kComp == 1 ? r0 + 64 : r0 + kBN / 2;
-                tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, r0, kEvictLast);
-                tma_load_2d_e(elected, st + 2 * kABytes + kBBytes / 2, &tm_g_hi, fb, k0 + kb * kBK, r1, kEvictLast);
+                if (hi_tiles) {
+                  tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, r0, kEvictLast);
+                  tma_load_2d_e(elected, st + 2 * kABytes + kBBytes / 2, &tm_g_hi, fb, k0 + kb * kBK, r1, kEvictLast);
+                }
                 if (lo_tiles) {
                   tma_load_2d_e(elected, st + 2 * kABytes + kBBytes, &tm_g_lo, fb, k0 + kb * kBK, r0, kEvictLast);
                   tma_load_2d_e(elected, st + 2 * kABytes + kBBytes + kBBytes / 2, &tm_g_lo, fb, k0 + kb * kBK, r1, kEvictLast);
                 }
               } else {
-                tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, c * kN, kEvictLast);
+                if (hi_tiles) tma_load_2d_e(elected, st + 2 * kABytes, &tm_g_hi, fb, k0 + kb * kBK, c * kN, kEvictLast);
                 if (lo_tiles) tma_load_2d_e(elected, st + 2 * kABytes + kBBytes, &tm_g_lo, fb, k0 + kb * kBK, c * kN, kEvictLast);
               }
               }
@@ -685,7 +692,8 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
     // onto the (large) running sum: with a long K the small cross terms W_lo*G_hi + W_hi*G_lo are summed FIRST
     // (two_pass), while the accumulator is still small, and the W_hi*G_hi terms after.
     {
-      constexpr uint32_t idesc = make_idesc_tf32(kBM, kN);
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, kN), idesc_x = make_idesc_bf16(kBM, kN);
+      const bool cross = A.cross != 0;
       const uint32_t elected = elect_one() ? 1u : 0u;
       const uint32_t s_addr = smem_u32(smem);
       const uint64_t desc0 = make_kmajor_sw128_desc(0);
@@ -733,8 +741,12 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
                   const uint64_t b_hi = db + (uint64_t)(k4 * 2), b_lo = db + (uint64_t)((kBBytes >> 4) + k4 * 2);
                   if (!(SB2_DBG_BITS(A) & 32)) {
                   if (pass == 0) {
-                    umma_tf32_e(elected, d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
-                    umma_tf32_e(elected, d_tmem, a_hi, b_lo, idesc, 1u);
+                    if (cross) {
+                      umma_bf16_e(elected, d_tmem, a_lo, b_lo, idesc_x, (kb | k4) != 0);  // [w_lo | w_hi] x [g_hi ; g_lo], K = 16
+                    } else {
+                      umma_tf32_e(elected, d_tmem, a_lo, b_hi, idesc, (kb | k4) != 0);  // small terms first
+                      umma_tf32_e(elected, d_tmem, a_hi, b_lo, idesc, 1u);
+                    }
                   }
                   if (pass == two_pass) umma_tf32_e(elected, d_hh, a_hi, b_hi, idesc, (part_first && k4 == 0) ? 0u : 1u);
                   }

@@ -97,21 +97,23 @@ def test_fluxes_match_c_oracle_at_20000(engines):
     assert_flux_close(got, want)
 
 
-def test_split_product_small_terms_in_bfloat16_and_in_tf32(engines):
-    """synth3_kernel forms w g = w_hi g_hi + (w_lo g_hi + w_hi g_lo); the bracket is 2^-11 of the product, so by default it
-    is ONE bfloat16 MMA (factors good to 2^-9 each: 2^-19 of the product at worst, before the sum over bins averages it);
-    ``SB2_TF32X3=1`` keeps both small terms as TF32 MMAs.  Both against the C oracle at 20 000 galaxies, and against each other."""
-    w, eng = engines("cfg2", 20000)
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_split_product_small_terms_in_bfloat16_and_in_tf32(engines, name):
+    """The contraction kernels form w g = w_hi g_hi + (w_lo g_hi + w_hi g_lo); the bracket is 2^-11 of the product, so by
+    default it is ONE bfloat16 MMA (factors good to 2^-9 each: 2^-19 of the product at worst, before the sum over bins averages
+    it); ``SB2_TF32X3=1`` keeps both small terms as TF32 MMAs.  Both against the C oracle at 20 000 galaxies, and against each
+    other -- cfg2 through synth3_kernel (weights in tensor memory), cfg3 through the dense-K synth_kernel."""
+    w, eng = engines(name, 20000)
     want = oracle_flux(w, c=True)
     got = eng.photometry(w.params, scaled=False)
     err = assert_flux_close(got, want)
-    _, eng3 = engines("cfg2", 20000, env={"SB2_TF32X3": "1"})
+    _, eng3 = engines(name, 20000, env={"SB2_TF32X3": "1"})
     got3 = eng3.photometry(w.params, scaled=False)
     err3 = assert_flux_close(got3, want)
     ok = np.abs(want) > 1e-30 * np.abs(want).max(axis=1, keepdims=True)
     between = np.max(np.abs(got[ok].astype(np.float64) - got3[ok]) / np.abs(want[ok]))
-    print(f"bfloat16 small terms: {err:.3e}; 3 x TF32: {err3:.3e}; between the two: {between:.3e}")
-    assert err <= 3e-6 and between <= 3e-6
+    print(f"{name}: bfloat16 small terms: {err:.3e}; 3 x TF32: {err3:.3e}; between the two: {between:.3e}")
+    assert err <= (3e-6 if name == "cfg2" else 4e-6) and between <= 3e-6
     assert not np.array_equal(got, got3)      # the switch really selects another arithmetic
 
 
@@ -228,8 +230,9 @@ def test_cfg3_dense_path_matches_c_oracle_at_20000(engines):
     got = eng.photometry(w.params, scaled=False)
     err = assert_flux_close(got, want)
     print(f"cfg3 dense path, 20000 galaxies: max rel err {err:.3e}")
-    # split accumulators (K ranges summed in FP32 by the epilogue): 3x below the tolerance; one accumulator sat at 8.7e-6
-    assert err <= 3e-6
+    # split accumulators (K ranges summed in FP32 by the epilogue): 2.5x below the tolerance (3.1e-6 with the small terms of
+    # the split product in bfloat16, below 3e-6 with SB2_TF32X3=1); one accumulator sat at 8.7e-6
+    assert err <= 4e-6
     _, eng1 = engines("cfg3", 20000, env={"SB2_NO_SPLIT": "1"})
     err1 = assert_flux_close(eng1.photometry(w.params, scaled=False), want)
     print(f"  one accumulator per chunk (SB2_NO_SPLIT=1): {err1:.3e}")
@@ -611,7 +614,8 @@ def test_results_do_not_depend_on_batch_composition(engines):
 def test_cta_pair_kernel_matches_oracle_and_single_cta(engines, name):
     """synth2_kernel (cta_group::2, weights resident in shared memory) is opt-in; it must agree with the oracle
     and, since both kernels multiply the same operands in the same order, bit for bit with synth_kernel."""
-    w, eng = engines(name, 2500, env={"SB2_NO_SYNTH3": "1"})
+    # (the pair kernel keeps three TF32 passes: compare it with the single-CTA kernel in the same arithmetic)
+    w, eng = engines(name, 2500, env={"SB2_NO_SYNTH3": "1", "SB2_TF32X3": "1"})
     single = eng.photometry(w.params, scaled=False)
     _, peng = engines(name, 2500, env={"SB2_CTA_PAIR": "1"})
     pair = peng.photometry(w.params, scaled=False)
