@@ -214,6 +214,7 @@ struct Switches {
   bool no_fuse = false, tf32x3 = false;
   int dbg = 0;
   long long host_slices = 0;   // 0: automatic
+  int dense_grid = 0;          // CTAs of the dense-K contraction; 0: automatic (see dense_grid_size)
   static bool on(const char* k) { const char* e = std::getenv(k); return e && e[0] && e[0] != '0'; }
   void read() {
     n256 = on("SB2_N256"); cta_pair = on("SB2_CTA_PAIR"); libm = on("SB2_LIBM"); weights_v1 = on("SB2_WEIGHTS_V1");
@@ -221,6 +222,7 @@ struct Switches {
     no_fuse = on("SB2_NO_FUSE"); tf32x3 = on("SB2_TF32X3");
     if (const char* e = std::getenv("SB2_DBG")) dbg = std::atoi(e);
     if (const char* e = std::getenv("SB2_HOST_SLICES")) host_slices = std::atoll(e);
+    if (const char* e = std::getenv("SB2_DENSE_GRID")) dense_grid = std::atoi(e);
   }
 };
 
@@ -639,11 +641,20 @@ int launch_synth_t(sb2_model* m, const sb2::SynthArgs& a, int grid, bool delta, 
   if (use_split(m, delta)) {
     auto k = sb2::synth_kernel<C, NF, SPEC, 128, PG, kDenseSplit>;
     sb2::SynthArgs a2 = a;
-    size_t bytes = 1024 + (size_t)sb2::kStages * sb2::SynthCfg<128>::kStageBytesN + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + sb2::kBarBytes;
+    const size_t fixed = 1024 + (((size_t)m->uv_len * 8 + 15) & ~size_t(15)) + sb2::kBarBytes;
+    size_t bytes = fixed + (size_t)sb2::kStages * sb2::SynthCfg<128>::kStageBytesN;
     if (bytes > m->smem_optin) return fail(SB2_ERR_INVALID, "filter tables do not fit in shared memory next to this batch's kernel (dense K)");
     if (SPEC && bytes + sb2::kSpecSmemBytes <= m->smem_optin) {
       bytes += sb2::kSpecSmemBytes;
       a2.spec_smem = 1;
+    }
+    if (a.cross && a.two_pass) {
+      // half stages (one W tile + one G tile, 32 KB): as deep a ring as fits, at least the four that the full stages' space holds
+      const size_t half_stage = (size_t)sb2::kABytes + sb2::SynthCfg<128>::kBBytesN, extra = a2.spec_smem ? sb2::kSpecSmemBytes : 0;
+      int ns = 8;
+      while (ns > 4 && fixed + extra + ns * half_stage > m->smem_optin) --ns;
+      a2.n_stages = ns;
+      bytes = fixed + extra + ns * half_stage;
     }
     CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     k<<<grid, sb2::kSynthThreads, bytes, st>>>(delta ? m->tm_wd_hi : m->tm_w_hi, delta ? m->tm_wd_lo : m->tm_w_lo, m->tm_g2_hi,
@@ -1039,7 +1050,8 @@ int sb2_synth_photometry(sb2_model* m, const sb2_params* p, float* flux_base, do
   } else if (use_s3(m, p)) {
     rc = launch_synth3(m, a, a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm, st);
   } else {
-    const int grid = a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm;
+    int grid = a.n_tiles < m->n_sm ? a.n_tiles : m->n_sm;
+    if (m->sw.dense_grid > 0) grid = std::min(grid, m->sw.dense_grid);
     rc = launch_synth(m, a, grid, delta, st);
   }
   if (rc == SB2_OK) {

@@ -69,6 +69,7 @@ struct SynthArgs {
   int k8_total;              // K/8 MMA steps actually needed (the last k-block may be partial)
   int dbg;                   // experiments only (SB2_DBG): 1 skip filter sums, 2 skip dust exp, 4 two ring slots
   int two_pass;              // 1: long K, cross terms summed before the hi*hi terms (single-CTA kernel only)
+  int n_stages;              // split-accumulator kernel with cross and two_pass: ring depth of HALF stages (see synth_kernel); else unused
   int cross;                 // 1: the W_lo / G_lo operands hold the packed bfloat16 pairs [lo | hi] x [hi ; lo] of the small
                              //    terms, multiplied by ONE kind::f16 MMA per 8 k-values (synth_kernel; PrepModel.cross)
   const int* n_tiles_dev;    // actual tile count (<= n_tiles) when the batch was grouped on device, else nullptr
@@ -601,11 +602,18 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [stages][W_hi | W_lo | G_hi | G_lo], filter table, barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float2* s_uv = reinterpret_cast<float2*>(smem + kStages * kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + ((A.uv_len * 8 + 15) & ~15));
-  uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
-  uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * kStages;                       // [kTfPerGroup * kMaxGroups] MMA -> epilogue group (see epilogue_loop)
+  // Half stages (split-accumulator kernel, bfloat16 small terms, two passes): a pass needs only ONE tile per operand -- the
+  // packed pair tiles in pass 0, the hi tiles in pass 1 -- so a stage is [W tile | G tile] and the same shared memory holds
+  // twice as many k-blocks in flight (the two-stage ring of four-tile stages left this kernel waiting on L2 latency).
+  const bool half = kSplit > 1 && A.cross != 0 && A.two_pass != 0;
+  const int n_stages = half ? A.n_stages : kStages;
+  const int stage_bytes = half ? kABytes + kBBytes : kStageBytes;
+  constexpr int kMaxStages = kSplit > 1 ? 8 : kStages;
+  float2* s_uv = reinterpret_cast<float2*>(smem + n_stages * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes + ((A.uv_len * 8 + 15) & ~15));
+  uint64_t* full_bar = bars;                    // [kMaxStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kMaxStages;      // [kMaxStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;                    // [kTfPerGroup * kMaxGroups] MMA -> epilogue group (see epilogue_loop)
   uint64_t* tempty_bar = tfull_bar + kTfPerGroup * kMaxGroups;    // [kBuf]           epilogue -> MMA, per TMEM accumulator
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
 
@@ -615,7 +623,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
     prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo); prefetch_tmap(&tm_g_hi); prefetch_tmap(&tm_g_lo);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < kTfPerGroup * kMaxGroups; ++b) mbar_init(&tfull_bar[b], 1);
     for (int b = 0; b < (kSplit > 1 ? 4 : (int)kBuf); ++b) mbar_init(&tempty_bar[b], kSplit > 1 ? 8 : 4);  // 4 warps per epilogue group (split: both groups drain every chunk)
     fence_barrier_init();
@@ -655,9 +663,19 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
             const bool hi_tiles = !(A.cross && n_pass == 2 && pass == 0);
             for (int kb = 0; kb < n_kb; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              const uint32_t st = s_addr + (uint32_t)stage * kStageBytes, fb = full0 + (uint32_t)stage * 8u;
+              const uint32_t st = s_addr + (uint32_t)(stage * stage_bytes), fb = full0 + (uint32_t)stage * 8u;
               if (SB2_DBG_BITS(A) & 64) {   // experiment: no operand traffic
                 mbar_expect_tx_e(elected, &full_bar[stage], 0);
+              } else if (kSplit > 1 && half) {
+                // half stage: [W tile | G tile (two 64-row boxes)], packed pair tiles in pass 0, hi tiles in pass 1
+                const CUtensorMap* tw = pass == 0 ? &tm_w_lo : &tm_w_hi;
+                const CUtensorMap* tg = pass == 0 ? &tm_g_lo : &tm_g_hi;
+                const int r0 = kComp == 1 ? c * kN : (c * kLch / (kBN / 2)) * kBN + (c * kLch) % (kBN / 2);
+                const int r1 = kComp == 1 ? r0 + 64 : r0 + kBN / 2;
+                mbar_expect_tx_e(elected, &full_bar[stage], kABytes + kBBytes);
+                tma_load_2d_e(elected, st, tw, fb, kb * kBK, tile * kBM, kEvictNormal);
+                tma_load_2d_e(elected, st + kABytes, tg, fb, k0 + kb * kBK, r0, kEvictLast);
+                tma_load_2d_e(elected, st + kABytes + kBBytes / 2, tg, fb, k0 + kb * kBK, r1, kEvictLast);
               } else {
               mbar_expect_tx_e(elected, &full_bar[stage], (lo_tiles && hi_tiles) ? kStageBytes : kABytes + kBBytes);
               if (hi_tiles) tma_load_2d_e(elected, st, &tm_w_hi, fb, kb * kBK, tile * kBM, kEvictNormal);
@@ -680,7 +698,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
                 if (lo_tiles) tma_load_2d_e(elected, st + 2 * kABytes + kBBytes, &tm_g_lo, fb, k0 + kb * kBK, c * kN, kEvictLast);
               }
               }
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
           }
         }
@@ -731,14 +749,15 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
               }
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
-              const uint64_t da = desc0 + (uint64_t)(((s_addr + stage * kStageBytes) & 0x3FFFF) >> 4);
-              const uint64_t db = da + (uint64_t)((2 * kABytes) >> 4);
+              const uint64_t da = desc0 + (uint64_t)(((s_addr + stage * stage_bytes) & 0x3FFFF) >> 4);
+              const uint64_t db = da + (uint64_t)(((half ? 1 : 2) * kABytes) >> 4);
               const int k4n = min(kBK / 8, k8_total - kb * (kBK / 8));
 #pragma unroll
               for (int k4 = 0; k4 < kBK / 8; ++k4) {
                 if (k4 < k4n) {
-                  const uint64_t a_hi = da + (uint64_t)(k4 * 2), a_lo = da + (uint64_t)((kABytes >> 4) + k4 * 2);
-                  const uint64_t b_hi = db + (uint64_t)(k4 * 2), b_lo = db + (uint64_t)((kBBytes >> 4) + k4 * 2);
+                  // (half stages: the one W tile and the one G tile of the pass, whichever they are)
+                  const uint64_t a_hi = da + (uint64_t)(k4 * 2), a_lo = half ? a_hi : da + (uint64_t)((kABytes >> 4) + k4 * 2);
+                  const uint64_t b_hi = db + (uint64_t)(k4 * 2), b_lo = half ? b_hi : db + (uint64_t)((kBBytes >> 4) + k4 * 2);
                   if (!(SB2_DBG_BITS(A) & 32)) {
                   if (pass == 0) {
                     if (cross) {
@@ -753,7 +772,7 @@ synth_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
                 }
               }
               umma_commit_e(elected, &empty_bar[stage]);  // smem slot reusable once these MMAs retire
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
           }
           if (kSplit > 1) {   // both groups drain every chunk
