@@ -182,8 +182,8 @@ __global__ void widen_kernel(const float* __restrict__ src, double* __restrict__
   double* __restrict__ d = dst + off;
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (((off | (long long)(reinterpret_cast<uintptr_t>(src) >> 2)) & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) >> 3) & 1) == 0) {
-    // four elements per thread: one 16-byte load, two 16-byte stores
+  if ((off & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    // (segment starts on 16-byte boundaries of both areas) four elements per thread: one 16-byte load, two 16-byte stores
     const long long n4 = n >> 2;
     for (; i < n4; i += stride) {
       const float4 v = reinterpret_cast<const float4*>(s)[i];
