@@ -344,7 +344,7 @@ def run_cfg5(args, rank, world, local):
         line = {
             "metric": METRIC, "value": world * n * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 + bf16 small terms of the split product (fp32 accumulate); weights/IGM in f64; spectra f32",
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 accumulate; launches that write spectra keep three TF32 passes); weights/IGM in f64; spectra f32",
             "data": "synthetic",
             "config": {"workload": "cfg5: cfg2 physics, photometry + 1000-pixel PRISM-like spectra out (full-wavelength path)",
                        "galaxies_per_gpu_per_step": n, "n_lam": eng.n_lam, "n_px": plan.n_px, "n_filt": eng.n_filt,
@@ -619,7 +619,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 + bf16 small terms of the split product (fp32 accumulate; dense-K batches: tf32x3); weights/IGM in f64",
+            "scaling": "weak", "vs_baseline": None, "dtype": ("tf32 + bf16 small terms of the split product (fp32 accumulate); weights/IGM in f64" if cross else "tf32x3 (fp32 accumulate); weights/IGM in f64"),
             "data": "synthetic",
             "config": bench_config(args.workload, n, t, w.params),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -211,7 +211,7 @@ __global__ void group_scatter_kernel(const unsigned* __restrict__ keys_sorted, c
 // Experiment / fallback switches (environment), read ONCE when a model is created -- never on the per-call path.
 struct Switches {
   bool n256 = false, cta_pair = false, libm = false, weights_v1 = false, one_pass = false, trace = false, no_synth3 = false, no_split = false;
-  bool no_fuse = false, tf32x3 = false;
+  bool no_fuse = false, tf32x3 = false, bf16_dense = false;
   int dbg = 0;
   long long host_slices = 0;   // 0: automatic
   int dense_grid = 0;          // CTAs of the dense-K contraction; 0: automatic (see dense_grid_size)
@@ -219,7 +219,7 @@ struct Switches {
   void read() {
     n256 = on("SB2_N256"); cta_pair = on("SB2_CTA_PAIR"); libm = on("SB2_LIBM"); weights_v1 = on("SB2_WEIGHTS_V1");
     one_pass = on("SB2_ONE_PASS"); trace = on("SB2_TRACE"); no_synth3 = on("SB2_NO_SYNTH3"); no_split = on("SB2_NO_SPLIT");
-    no_fuse = on("SB2_NO_FUSE"); tf32x3 = on("SB2_TF32X3");
+    no_fuse = on("SB2_NO_FUSE"); tf32x3 = on("SB2_TF32X3"); bf16_dense = on("SB2_BF16_DENSE");
     if (const char* e = std::getenv("SB2_DBG")) dbg = std::atoi(e);
     if (const char* e = std::getenv("SB2_HOST_SLICES")) host_slices = std::atoll(e);
     if (const char* e = std::getenv("SB2_DENSE_GRID")) dense_grid = std::atoi(e);
@@ -626,9 +626,14 @@ constexpr int kDenseSplit = 3;
 // Bracket-grouped batches of grids with many ages (BC03: 221) do not fit synth3_kernel's tensor-memory weights and have a
 // long K too (2 x 224 columns): they take the same split -- 7.6e-6 -> see DESIGN 6.1 -- with the bracket's weight maps.
 constexpr int kDeltaSplitMinK8 = 24;      // K >= 192 columns: below that one accumulator is already at ~3e-6
-// The two small terms of the split product as ONE bfloat16 MMA (SynthArgs.cross / PrepModel.cross / Synth3Args.cross):
-// everywhere except the opt-in CTA-pair kernel; SB2_TF32X3=1 restores three TF32 passes.
-bool cross_mode(const sb2_model* m) { return !m->sw.tf32x3 && !m->sw.cta_pair; }
+// The two small terms of the split product as ONE bfloat16 MMA (Synth3Args.cross | SynthArgs.cross + PrepModel.cross).
+//   synth3_kernel: the default for launches that output photometry only -- the band integrals average the per-wavelength
+//   rounding of the bfloat16 factors; launches that also write spectra keep three TF32 passes (per-wavelength values see the
+//   worst case, 2^-17 of a product).  SB2_TF32X3=1 restores three TF32 passes everywhere.
+//   synth_kernel (dense K and the fallbacks): opt-in with SB2_BF16_DENSE=1 -- the dense configuration's margin (<= 3e-6) is
+//   worth more than the 3 % it gains there.
+bool cross_s3(const sb2_model* m) { return !m->sw.tf32x3 && !m->sw.cta_pair; }
+bool cross_mode(const sb2_model* m) { return m->sw.bf16_dense && !m->sw.tf32x3 && !m->sw.cta_pair; }
 bool use_split(const sb2_model* m, bool delta) {
   if (m->sw.no_split) return false;
   if (delta) return m->wd_stride / 8 >= kDeltaSplitMinK8;
@@ -729,7 +734,7 @@ int launch_synth3_t(sb2_model* m, const sb2::SynthArgs& a, int grid, cudaStream_
   sb2::Synth3Args x{};
   x.sf = m->sf; x.s0 = m->s0; x.s1 = m->s1; x.n_age = m->d.n_age; x.na_pad = m->d.n_age_pad; x.w_stride = m->wd_stride;
   x.kb_split = a.n_kb / 2;
-  x.cross = cross_mode(m) ? 1 : 0;
+  x.cross = (cross_s3(m) && a.out_spec == nullptr) ? 1 : 0;
   bool spec = false;
   const int kap_len = m->d.n_chunk * (sb2::kBN / C);
   const int feat_tab = a.x_count > 0 ? (FEAT & ~sb2::kFeatAbsorbed) : FEAT;    // pseudo-bins: the energy weights are 1, no table
